@@ -1,0 +1,40 @@
+// bvh_build.h — host-side builder of the flattened 4-wide BVH the trace kernels walk.
+// Replaces, for this path, what the reference delegates to the un-vendored Rust crate rtbvh
+// (RFW/system/bvh/src/bvh_tree.cpp:48-102, mbvh_tree.cpp:26-49) and the in-tree binned-SAH spec
+// (RFW/system/bvh/include/bvh/bvh_node.h:136-233) + MBVH collapse (src/mbvh_node.cpp:194-374).
+#pragma once
+#include "device_types.h"
+
+#include <cstddef>
+#include <vector>
+
+namespace rfwb200
+{
+
+struct BuildTriangle
+{
+	float v0[3], v1[3], v2[3]; // world space
+};
+
+struct BvhBuildResult
+{
+	std::vector<BvhNode4> nodes;	   // breadth-first, root = 0
+	std::vector<uint32_t> tri_order;   // leaf-ordered position -> input triangle index
+	std::vector<uint32_t> node_parent; // for refit: parent index per node (root: 0xffffffff)
+	float sah_cost = 0;
+	int depth = 0;
+	double build_ms = 0;
+};
+
+// Binned-SAH BVH2 (16 bins, 3 axes, leaves <= 4 triangles) built with a task pool over `threads`
+// host threads, collapsed to 4-wide by repeatedly opening the child with the largest area, then laid
+// out breadth-first.  max stack need of a depth-first traversal is 3*depth+1.
+void build_bvh4(const BuildTriangle *tris, size_t count, int threads, BvhBuildResult &out);
+
+// Recompute all boxes bottom-up for moved vertices with unchanged topology (the reference's refit,
+// bvh_tree.cpp:104-114, top_level_bvh.cpp:46-52).
+void refit_bvh4(const BuildTriangle *tris, size_t count, BvhBuildResult &bvh);
+
+constexpr int TRAVERSAL_STACK = 96; // ints per thread in the kernels; builder keeps 3*depth+1 below this
+
+} // namespace rfwb200

@@ -1,0 +1,1069 @@
+// context.cpp — implementation of the C ABI declared in include/rfwb200.h.
+//
+// Host side of the hot path: keeps a host copy of what the reference's RenderSystem uploads
+// (meshes, instances, materials, textures, lights, sky), flattens instances into one world-space
+// triangle soup on update() (memory is laid out for 180 GB of HBM, so instancing is traded for a
+// single-level BVH — DESIGN.md), builds / refits the 4-wide BVH, owns the SoA wavefront state and
+// enqueues the per-sample kernel sequence without any host synchronisation.
+//
+// Reference counterparts: backends/CUDART/src/Context.cpp (render_frame :65-159, set_materials
+// :160-198, set_textures :201-268, set_mesh :270-311, set_instance :313-321, set_lights :331-383,
+// update :394-456, buffers :462-483).
+#include "../../include/rfwb200.h"
+
+#include "bvh_build.h"
+#include "device_types.h"
+#include "kernels.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <thread>
+#include <vector>
+
+extern "C" const unsigned char rfwb200_bluenoise_table[];
+extern "C" const unsigned int rfwb200_bluenoise_table_size;
+
+using namespace rfwb200;
+
+namespace
+{
+thread_local std::string g_last_error;
+
+int set_error(int code, const std::string &msg)
+{
+	g_last_error = msg;
+	return code;
+}
+
+#define CK(expr)                                                                                                        \
+	do                                                                                                                  \
+	{                                                                                                                   \
+		const cudaError_t e__ = (expr);                                                                                 \
+		if (e__ != cudaSuccess)                                                                                         \
+			return set_error(e__ == cudaErrorMemoryAllocation ? RFWB200_ERR_OOM : RFWB200_ERR_CUDA,                     \
+							 std::string(#expr) + ": " + cudaGetErrorString(e__));                                      \
+	} while (0)
+
+#define REQUIRE(cond, msg)                                                                                              \
+	do                                                                                                                  \
+	{                                                                                                                   \
+		if (!(cond))                                                                                                    \
+			return set_error(RFWB200_ERR_INVALID, msg);                                                                 \
+	} while (0)
+
+// growable device buffer
+struct DevBuf
+{
+	void *ptr = nullptr;
+	size_t bytes = 0;
+	~DevBuf() { release(); }
+	void release()
+	{
+		if (ptr)
+			cudaFree(ptr);
+		ptr = nullptr, bytes = 0;
+	}
+	cudaError_t reserve(size_t n)
+	{
+		if (n <= bytes)
+			return cudaSuccess;
+		release();
+		const cudaError_t e = cudaMalloc(&ptr, std::max<size_t>(n, 16));
+		if (e == cudaSuccess)
+			bytes = std::max<size_t>(n, 16);
+		return e;
+	}
+	template <typename T> T *as() const { return static_cast<T *>(ptr); }
+};
+
+struct HostMesh
+{
+	std::vector<float> vertices;   // vec4
+	std::vector<uint32_t> indices; // 3 per tri or empty
+	std::vector<rfwb200_triangle> triangles;
+	uint64_t version = 0;
+};
+
+struct HostInstance
+{
+	int mesh = -1;
+	float transform[16];
+	float normal[9];
+};
+
+struct HostTexture
+{
+	int type;
+	uint32_t width, height, texel_count, addr;
+};
+
+inline void mul_point(const float *m, const float *p, float *o)
+{
+	for (int r = 0; r < 3; r++)
+		o[r] = m[r] * p[0] + m[4 + r] * p[1] + m[8 + r] * p[2] + m[12 + r];
+}
+inline void mul_mat3(const float *m, const float *p, float *o)
+{
+	for (int r = 0; r < 3; r++)
+		o[r] = m[r] * p[0] + m[3 + r] * p[1] + m[6 + r] * p[2];
+}
+} // namespace
+
+struct rfwb200_context
+{
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	bool initialised = false;
+	uint32_t width = 0, height = 0;
+	ShardView shard{};
+
+	// ---- host copies of the scene -------------------------------------------------------------
+	std::vector<HostMesh> meshes;
+	std::vector<HostInstance> instances;
+	std::vector<rfwb200_material> materials, materials_raw;
+	std::vector<HostTexture> textures;
+	bool geometry_dirty = true, topology_dirty = true;
+	std::vector<std::pair<int, size_t>> built_layout; // (mesh, tri count) per instance at last build
+
+	// ---- device scene ------------------------------------------------------------------------------
+	DevBuf d_nodes, d_tris, d_shade_tris, d_materials, d_materials_raw, d_uint_tex, d_float_tex, d_tex_desc, d_sky,
+		d_area, d_point, d_spot, d_dir, d_blue_noise;
+	SceneView scene{};
+	BvhBuildResult bvh;
+	std::vector<BuildTriangle> build_tris;
+	uint64_t flat_tri_count = 0;
+
+	// ---- wavefront state -----------------------------------------------------------------------------
+	DevBuf d_O[2], d_D[2], d_T[2], d_hit, d_sO, d_sD, d_sE, d_acc, d_fb, d_counters, d_probe, d_frame, d_scratch_cursor;
+	WavefrontView wf{};
+	uint32_t counters_capacity_spp = 0;
+
+	// ---- settings / state ------------------------------------------------------------------------------
+	RenderSettings rs{2, 10.0f, 1e-5f, 1, 256};
+	int spp = 1;
+	bool mode_pt = true;
+	LaunchDims dims{};
+	bool dims_valid = false;
+	uint32_t sample_index = 0;
+	uint32_t probe_x = 0, probe_y = 0;
+	uint32_t last_spp = 0, last_first_sample = 0;
+	uint64_t launches = 0;
+	rfwb200_render_stats stats{};
+	cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+	bool frame_in_flight = false;
+	std::vector<DepthCounters> host_counters;
+};
+
+using Ctx = rfwb200_context;
+
+namespace
+{
+
+int ensure_device(Ctx *c)
+{
+	CK(cudaSetDevice(c->device));
+	return RFWB200_OK;
+}
+
+uint32_t local_tile_count(const ShardView &s)
+{
+	const uint32_t total = s.tiles_x * s.tiles_y;
+	return total > s.rank ? (total - s.rank + s.world - 1) / s.world : 0;
+}
+
+void recompute_shard(Ctx *c)
+{
+	ShardView &s = c->shard;
+	s.width = c->width, s.height = c->height;
+	if (s.world == 0)
+		s.world = 1, s.rank = 0;
+	if (s.tile_w == 0)
+		s.tile_w = 32, s.tile_h = 8;
+	s.tiles_x = (s.width + s.tile_w - 1) / s.tile_w;
+	s.tiles_y = (s.height + s.tile_h - 1) / s.tile_h;
+	s.local_tiles = local_tile_count(s);
+	s.local_pixels = s.local_tiles * s.tile_w * s.tile_h;
+}
+
+size_t shard_stride_pixels(const ShardView &s)
+{
+	const uint32_t total = s.tiles_x * s.tiles_y;
+	return size_t((total + s.world - 1) / s.world) * s.tile_w * s.tile_h;
+}
+
+int alloc_wavefront(Ctx *c)
+{
+	const size_t P = std::max<size_t>(c->shard.local_pixels, 32);
+	const size_t plane = P * sizeof(float4);
+	for (int i = 0; i < 2; i++)
+	{
+		CK(c->d_O[i].reserve(plane));
+		CK(c->d_D[i].reserve(plane));
+		CK(c->d_T[i].reserve(plane));
+	}
+	CK(c->d_hit.reserve(plane));
+	CK(c->d_sO.reserve(plane));
+	CK(c->d_sD.reserve(plane));
+	CK(c->d_sE.reserve(plane));
+	CK(c->d_acc.reserve(plane));
+	const size_t fb_pixels = c->shard.world == 1 ? size_t(c->width) * c->height : shard_stride_pixels(c->shard);
+	CK(c->d_fb.reserve(std::max(fb_pixels, P) * sizeof(float4)));
+	CK(c->d_probe.reserve(sizeof(ProbeResult)));
+	CK(c->d_frame.reserve(sizeof(FrameParams)));
+	CK(c->d_scratch_cursor.reserve(256));
+	WavefrontView &w = c->wf;
+	for (int i = 0; i < 2; i++)
+		w.O[i] = c->d_O[i].as<float4>(), w.D[i] = c->d_D[i].as<float4>(), w.T[i] = c->d_T[i].as<float4>();
+	w.hit = c->d_hit.as<float4>();
+	w.sO = c->d_sO.as<float4>(), w.sD = c->d_sD.as<float4>(), w.sE = c->d_sE.as<float4>();
+	w.accumulator = c->d_acc.as<float4>();
+	w.framebuffer = c->d_fb.as<float4>();
+	w.probe = c->d_probe.as<ProbeResult>();
+	w.frame = c->d_frame.as<FrameParams>();
+	return RFWB200_OK;
+}
+
+int ensure_counters(Ctx *c, uint32_t spp)
+{
+	if (spp > c->counters_capacity_spp)
+	{
+		CK(c->d_counters.reserve(size_t(spp) * MAX_DEPTH_SLOTS * sizeof(DepthCounters)));
+		c->counters_capacity_spp = spp;
+	}
+	c->wf.counters = c->d_counters.as<DepthCounters>();
+	return RFWB200_OK;
+}
+
+// instance flattening: world-space triangles + repacked shading records
+int flatten_scene(Ctx *c, std::vector<ShadeTri> &shade, std::vector<float> &det_eps)
+{
+	size_t total = 0;
+	for (const HostInstance &in : c->instances)
+		if (in.mesh >= 0 && size_t(in.mesh) < c->meshes.size())
+			total += c->meshes[in.mesh].triangles.size();
+	c->build_tris.resize(total);
+	shade.resize(total);
+	det_eps.resize(total);
+	size_t at = 0;
+	for (size_t ii = 0; ii < c->instances.size(); ii++)
+	{
+		const HostInstance &in = c->instances[ii];
+		if (in.mesh < 0 || size_t(in.mesh) >= c->meshes.size())
+			continue;
+		const HostMesh &m = c->meshes[in.mesh];
+		const float *M = in.transform;
+		const float det = M[0] * (M[5] * M[10] - M[9] * M[6]) - M[4] * (M[1] * M[10] - M[9] * M[2]) +
+						  M[8] * (M[1] * M[6] - M[5] * M[2]);
+		const float eps = 1e-6f * std::fabs(det);
+		const size_t nt = m.triangles.size();
+		const size_t nv = m.vertices.size() / 4;
+		for (size_t t = 0; t < nt; t++, at++)
+		{
+			uint32_t vi[3];
+			for (int k = 0; k < 3; k++)
+				vi[k] = m.indices.empty() ? uint32_t(t * 3 + k) : m.indices[t * 3 + k];
+			if (vi[0] >= nv || vi[1] >= nv || vi[2] >= nv)
+				return set_error(RFWB200_ERR_INVALID, "mesh index out of range");
+			BuildTriangle &bt = c->build_tris[at];
+			mul_point(M, &m.vertices[4 * vi[0]], bt.v0);
+			mul_point(M, &m.vertices[4 * vi[1]], bt.v1);
+			mul_point(M, &m.vertices[4 * vi[2]], bt.v2);
+			const rfwb200_triangle &src = m.triangles[t];
+			ShadeTri &st = shade[at];
+			st.u0 = src.u0, st.u1 = src.u1, st.u2 = src.u2, st.light_tri_idx = src.light_tri_idx;
+			st.v0 = src.v0, st.v1 = src.v1, st.v2 = src.v2, st.material = src.material;
+			float n[3];
+			mul_mat3(in.normal, src.vN0, n);
+			st.n0x = n[0], st.n0y = n[1], st.n0z = n[2];
+			mul_mat3(in.normal, src.vN1, n);
+			st.n1x = n[0], st.n1y = n[1], st.n1z = n[2];
+			mul_mat3(in.normal, src.vN2, n);
+			st.n2x = n[0], st.n2y = n[1], st.n2z = n[2];
+			const float gn[3] = {src.Nx, src.Ny, src.Nz};
+			mul_mat3(in.normal, gn, n);
+			const float il = 1.0f / std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+			st.Nx = n[0] * il, st.Ny = n[1] * il, st.Nz = n[2] * il;
+			st.area = src.area, st.lod = src.LOD;
+			st.inst_id = uint32_t(ii), st.prim_id = uint32_t(t);
+			det_eps[at] = eps;
+		}
+	}
+	c->flat_tri_count = total;
+	return RFWB200_OK;
+}
+
+int upload_bvh(Ctx *c, const std::vector<float> &det_eps)
+{
+	const size_t n = c->bvh.tri_order.size();
+	std::vector<TriRec> recs(std::max<size_t>(n, 1));
+	memset(recs.data(), 0, recs.size() * sizeof(TriRec));
+	for (size_t i = 0; i < n; i++)
+	{
+		const uint32_t src = c->bvh.tri_order[i];
+		const BuildTriangle &t = c->build_tris[src];
+		TriRec &r = recs[i];
+		r.p0x = t.v0[0], r.p0y = t.v0[1], r.p0z = t.v0[2];
+		r.e1x = t.v1[0] - t.v0[0], r.e1y = t.v1[1] - t.v0[1], r.e1z = t.v1[2] - t.v0[2];
+		r.e2x = t.v2[0] - t.v0[0], r.e2y = t.v2[1] - t.v0[1], r.e2z = t.v2[2] - t.v0[2];
+		r.shade_idx = src;
+		r.det_eps = det_eps[src];
+	}
+	CK(c->d_nodes.reserve(c->bvh.nodes.size() * sizeof(BvhNode4)));
+	CK(c->d_tris.reserve(recs.size() * sizeof(TriRec)));
+	CK(cudaMemcpyAsync(c->d_nodes.ptr, c->bvh.nodes.data(), c->bvh.nodes.size() * sizeof(BvhNode4), cudaMemcpyHostToDevice,
+					   c->stream));
+	CK(cudaMemcpyAsync(c->d_tris.ptr, recs.data(), recs.size() * sizeof(TriRec), cudaMemcpyHostToDevice, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	c->scene.nodes = c->d_nodes.as<BvhNode4>();
+	c->scene.tris = c->d_tris.as<TriRec>();
+	c->scene.node_count = uint32_t(c->bvh.nodes.size());
+	c->scene.tri_count = uint32_t(n);
+	return RFWB200_OK;
+}
+
+int upload_frame_params(Ctx *c, const rfwb200_camera_view *view, uint32_t sample_base)
+{
+	FrameParams fp;
+	for (int i = 0; i < 3; i++)
+	{
+		fp.pos[i] = view->pos[i], fp.p1[i] = view->p1[i];
+		fp.right[i] = view->p2[i] - view->p1[i];
+		fp.up[i] = view->p3[i] - view->p1[i];
+	}
+	fp.aperture = view->aperture, fp.spread_angle = view->spread_angle;
+	fp.sample_base = sample_base;
+	fp.probe_pixel = (c->probe_x < c->width && c->probe_y < c->height) ? c->probe_y * c->width + c->probe_x : 0xffffffffu;
+	CK(cudaMemcpyAsync(c->d_frame.ptr, &fp, sizeof(fp), cudaMemcpyHostToDevice, c->stream));
+	return RFWB200_OK;
+}
+
+int ensure_dims(Ctx *c)
+{
+	if (c->dims_valid)
+		return RFWB200_OK;
+	CK(configure_launches(c->rs, c->scene.node_count, c->dims));
+	c->dims_valid = true;
+	return RFWB200_OK;
+}
+
+int check_ready(Ctx *c)
+{
+	if (!c->initialised)
+		return set_error(RFWB200_ERR_STATE, "rfwb200_init has not been called");
+	if (c->geometry_dirty || c->scene.nodes == nullptr)
+		return set_error(RFWB200_ERR_STATE, "scene changed: call rfwb200_update before rendering");
+	return RFWB200_OK;
+}
+
+} // namespace
+
+extern "C"
+{
+
+	const char *rfwb200_last_error(void) { return g_last_error.c_str(); }
+	const char *rfwb200_version(void) { return "rfwb200 0.1 (sm_100a)"; }
+
+	int rfwb200_create(int device, rfwb200_context **out)
+	{
+		REQUIRE(out != nullptr, "out is null");
+		*out = nullptr;
+		int count = 0;
+		const cudaError_t e = cudaGetDeviceCount(&count);
+		if (e != cudaSuccess || count == 0)
+			return set_error(RFWB200_ERR_NO_DEVICE,
+							 std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count == 0") +
+								 " (this library has no CPU fallback)");
+		REQUIRE(device >= 0 && device < count, "device ordinal out of range");
+		std::unique_ptr<Ctx> c(new Ctx());
+		c->device = device;
+		CK(cudaSetDevice(device));
+		cudaDeviceProp prop;
+		CK(cudaGetDeviceProperties(&prop, device));
+		if (prop.major < 10)
+			return set_error(RFWB200_ERR_NO_DEVICE, std::string("device '") + prop.name +
+														"' is not Blackwell (sm_100a code only, no fallback path)");
+		CK(cudaEventCreate(&c->ev_begin));
+		CK(cudaEventCreate(&c->ev_end));
+		// blue-noise tables (context/blue_noise.h:8204-8219 layout), embedded in the library
+		CK(c->d_blue_noise.reserve(rfwb200_bluenoise_table_size));
+		CK(cudaMemcpy(c->d_blue_noise.ptr, rfwb200_bluenoise_table, rfwb200_bluenoise_table_size, cudaMemcpyHostToDevice));
+		c->scene.blue_noise = c->d_blue_noise.as<uint8_t>();
+		// a 1x1 black sky so a miss is defined before set_sky
+		const float black[4] = {0, 0, 0, 0};
+		CK(c->d_sky.reserve(sizeof(black)));
+		CK(cudaMemcpy(c->d_sky.ptr, black, sizeof(black), cudaMemcpyHostToDevice));
+		c->scene.sky = c->d_sky.as<float>(), c->scene.sky_w = 1, c->scene.sky_h = 1;
+		c->shard.world = 1, c->shard.rank = 0, c->shard.tile_w = 32, c->shard.tile_h = 8;
+		*out = c.release();
+		return RFWB200_OK;
+	}
+
+	int rfwb200_cleanup(rfwb200_context *c)
+	{
+		if (!c)
+			return RFWB200_OK;
+		cudaSetDevice(c->device);
+		cudaStreamSynchronize(c->stream);
+		return RFWB200_OK;
+	}
+
+	int rfwb200_destroy(rfwb200_context *c)
+	{
+		if (!c)
+			return RFWB200_OK;
+		rfwb200_cleanup(c);
+		if (c->ev_begin)
+			cudaEventDestroy(c->ev_begin);
+		if (c->ev_end)
+			cudaEventDestroy(c->ev_end);
+		delete c;
+		return RFWB200_OK;
+	}
+
+	int rfwb200_init(rfwb200_context *c, uint32_t width, uint32_t height)
+	{
+		REQUIRE(c != nullptr, "context is null");
+		REQUIRE(width > 0 && height > 0, "width and height must be positive");
+		REQUIRE(uint64_t(width) * height < (1u << 24), "more than 2^24 pixels: path index no longer fits the state word");
+		if (int r = ensure_device(c))
+			return r;
+		c->width = width, c->height = height;
+		recompute_shard(c);
+		if (int r = alloc_wavefront(c))
+			return r;
+		CK(cudaMemsetAsync(c->d_acc.ptr, 0, c->d_acc.bytes, c->stream));
+		CK(cudaMemsetAsync(c->d_fb.ptr, 0, c->d_fb.bytes, c->stream));
+		c->sample_index = 0;
+		c->initialised = true;
+		return RFWB200_OK;
+	}
+
+	int rfwb200_set_shard(rfwb200_context *c, uint32_t rank, uint32_t world, uint32_t tile_w, uint32_t tile_h)
+	{
+		REQUIRE(c != nullptr, "context is null");
+		REQUIRE(world >= 1 && rank < world, "rank must be < world");
+		REQUIRE(tile_w >= 8 && tile_w % 8 == 0 && tile_h >= 4 && tile_h % 4 == 0, "tile must be a multiple of 8x4 pixels");
+		c->shard.rank = rank, c->shard.world = world, c->shard.tile_w = tile_w, c->shard.tile_h = tile_h;
+		if (c->initialised)
+			return rfwb200_init(c, c->width, c->height);
+		return RFWB200_OK;
+	}
+
+	int rfwb200_set_stream(rfwb200_context *c, void *cuda_stream)
+	{
+		REQUIRE(c != nullptr, "context is null");
+		c->stream = static_cast<cudaStream_t>(cuda_stream);
+		return RFWB200_OK;
+	}
+
+	int rfwb200_set_sky(rfwb200_context *c, const float *rgb, size_t width, size_t height)
+	{
+		REQUIRE(c && rgb && width > 0 && height > 0, "bad sky");
+		if (int r = ensure_device(c))
+			return r;
+		std::vector<float> tmp(width * height * 4);
+		for (size_t i = 0; i < width * height; i++)
+			tmp[4 * i] = rgb[3 * i], tmp[4 * i + 1] = rgb[3 * i + 1], tmp[4 * i + 2] = rgb[3 * i + 2], tmp[4 * i + 3] = 0.f;
+		CK(cudaStreamSynchronize(c->stream));
+		CK(c->d_sky.reserve(tmp.size() * sizeof(float)));
+		CK(cudaMemcpy(c->d_sky.ptr, tmp.data(), tmp.size() * sizeof(float), cudaMemcpyHostToDevice));
+		c->scene.sky = c->d_sky.as<float>(), c->scene.sky_w = uint32_t(width), c->scene.sky_h = uint32_t(height);
+		return RFWB200_OK;
+	}
+
+	int rfwb200_set_textures(rfwb200_context *c, const rfwb200_texture_data *tex, size_t count)
+	{
+		REQUIRE(c && (tex || count == 0), "bad textures");
+		if (int r = ensure_device(c))
+			return r;
+		// one linear uint array and one float4 array with per-texture offsets (CUDART/src/Context.cpp:201-268)
+		size_t nu = 0, nf = 0;
+		for (size_t i = 0; i < count; i++)
+		{
+			REQUIRE(tex[i].data != nullptr, "texture without data");
+			(tex[i].type == RFWB200_TEX_UINT ? nu : nf) += tex[i].texel_count;
+		}
+		REQUIRE(nu < (1ull << 32) && nf < (1ull << 32), "texture pool exceeds 2^32 texels");
+		std::vector<uint32_t> upool(std::max<size_t>(nu, 4), 0);
+		std::vector<float> fpool(std::max<size_t>(nf, 4) * 4, 0.f);
+		c->textures.resize(count);
+		std::vector<uint32_t> desc(std::max<size_t>(count, 1) * 4, 0);
+		size_t uo = 0, fo = 0;
+		for (size_t i = 0; i < count; i++)
+		{
+			HostTexture t{tex[i].type, tex[i].width, tex[i].height, tex[i].texel_count, 0};
+			if (tex[i].type == RFWB200_TEX_UINT)
+			{
+				t.addr = uint32_t(uo);
+				memcpy(&upool[uo], tex[i].data, size_t(tex[i].texel_count) * 4);
+				uo += tex[i].texel_count;
+			}
+			else
+			{
+				t.addr = uint32_t(fo);
+				memcpy(&fpool[fo * 4], tex[i].data, size_t(tex[i].texel_count) * 16);
+				fo += tex[i].texel_count;
+			}
+			c->textures[i] = t;
+			desc[4 * i] = uint32_t(t.type), desc[4 * i + 1] = t.width, desc[4 * i + 2] = t.height, desc[4 * i + 3] = t.addr;
+		}
+		CK(cudaStreamSynchronize(c->stream));
+		CK(c->d_uint_tex.reserve(upool.size() * 4));
+		CK(c->d_float_tex.reserve(fpool.size() * 4));
+		CK(c->d_tex_desc.reserve(desc.size() * 4));
+		CK(cudaMemcpy(c->d_uint_tex.ptr, upool.data(), upool.size() * 4, cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(c->d_float_tex.ptr, fpool.data(), fpool.size() * 4, cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(c->d_tex_desc.ptr, desc.data(), desc.size() * 4, cudaMemcpyHostToDevice));
+		c->scene.uint_texels = c->d_uint_tex.as<uint32_t>(), c->scene.uint_texel_count = uint32_t(upool.size());
+		c->scene.float_texels = c->d_float_tex.as<float>(), c->scene.float_texel_count = uint32_t(fpool.size() / 4);
+		return RFWB200_OK;
+	}
+
+	int rfwb200_set_materials(rfwb200_context *c, const rfwb200_material *mats, const rfwb200_material_tex_ids *ids,
+							  size_t count)
+	{
+		REQUIRE(c && (mats || count == 0), "bad materials");
+		if (int r = ensure_device(c))
+			return r;
+		c->materials.assign(mats, mats + count);
+		c->materials_raw.assign(mats, mats + count);
+		for (size_t i = 0; i < count && ids; i++)
+		{
+			// CUDART/src/Context.cpp:167-191 (slot 8 = ROUGHNESS1 has no descriptor)
+			rfwb200_material &m = c->materials[i];
+			rfwb200_map_desc *slots[11] = {&m.tex0, &m.tex1, &m.tex2, &m.nmap0, &m.nmap1, &m.nmap2,
+										   &m.smap, &m.rmap, nullptr, &m.cmap,	&m.amap};
+			for (int k = 0; k < 11; k++)
+			{
+				const int id = ids[i].texture[k];
+				if (id == -1 || !slots[k])
+					continue;
+				REQUIRE(id >= 0 && size_t(id) < c->textures.size(), "material references a texture that was not set");
+				slots[k]->texaddr = c->textures[id].addr;
+			}
+		}
+		CK(cudaStreamSynchronize(c->stream));
+		const size_t bytes = std::max<size_t>(count, 1) * sizeof(rfwb200_material);
+		CK(c->d_materials.reserve(bytes));
+		CK(c->d_materials_raw.reserve(bytes));
+		if (count)
+		{
+			CK(cudaMemcpy(c->d_materials.ptr, c->materials.data(), count * sizeof(rfwb200_material), cudaMemcpyHostToDevice));
+			CK(cudaMemcpy(c->d_materials_raw.ptr, c->materials_raw.data(), count * sizeof(rfwb200_material),
+						  cudaMemcpyHostToDevice));
+		}
+		c->scene.materials = c->d_materials.ptr, c->scene.material_count = uint32_t(count);
+		return RFWB200_OK;
+	}
+
+	int rfwb200_set_mesh(rfwb200_context *c, size_t index, const rfwb200_mesh *mesh)
+	{
+		REQUIRE(c && mesh, "bad mesh");
+		REQUIRE(mesh->vertices && mesh->triangles, "mesh needs vertices and triangles");
+		REQUIRE(index < (1u << 24), "mesh index too large");
+		if (index >= c->meshes.size())
+			c->meshes.resize(index + 1), c->topology_dirty = true;
+		HostMesh &m = c->meshes[index];
+		// same vertex and triangle count => refit (EmbreeRT/src/Mesh.cpp:21-36, top_level_bvh.cpp:26)
+		if (m.vertices.size() != mesh->vertex_count * 4 || m.triangles.size() != mesh->triangle_count ||
+			m.indices.size() != (mesh->indices ? mesh->triangle_count * 3 : 0))
+			c->topology_dirty = true;
+		m.vertices.assign(mesh->vertices, mesh->vertices + mesh->vertex_count * 4);
+		if (mesh->indices)
+			m.indices.assign(mesh->indices, mesh->indices + mesh->triangle_count * 3);
+		else
+			m.indices.clear();
+		m.triangles.assign(mesh->triangles, mesh->triangles + mesh->triangle_count);
+		m.version++;
+		c->geometry_dirty = true;
+		return RFWB200_OK;
+	}
+
+	int rfwb200_set_instance(rfwb200_context *c, size_t i, size_t mesh_index, const float transform[16],
+							 const float normal_matrix[9])
+	{
+		REQUIRE(c && transform && normal_matrix, "bad instance");
+		REQUIRE(mesh_index < c->meshes.size(), "instance references a mesh that was not set");
+		REQUIRE(i <= c->instances.size() + (1u << 20), "instance index too large");
+		if (i >= c->instances.size())
+			c->instances.resize(i + 1), c->topology_dirty = true;
+		HostInstance &in = c->instances[i];
+		if (in.mesh != int(mesh_index))
+			c->topology_dirty = true;
+		in.mesh = int(mesh_index);
+		memcpy(in.transform, transform, sizeof(float) * 16);
+		memcpy(in.normal, normal_matrix, sizeof(float) * 9);
+		c->geometry_dirty = true;
+		return RFWB200_OK;
+	}
+
+	int rfwb200_set_lights(rfwb200_context *c, rfwb200_light_count n, const rfwb200_area_light *a,
+						   const rfwb200_point_light *p, const rfwb200_spot_light *s, const rfwb200_directional_light *d)
+	{
+		REQUIRE(c != nullptr, "context is null");
+		REQUIRE((n.area == 0 || a) && (n.point == 0 || p) && (n.spot == 0 || s) && (n.directional == 0 || d),
+				"light count without array");
+		if (int r = ensure_device(c))
+			return r;
+		CK(cudaStreamSynchronize(c->stream));
+		CK(c->d_area.reserve(std::max<size_t>(n.area, 1) * sizeof(rfwb200_area_light)));
+		CK(c->d_point.reserve(std::max<size_t>(n.point, 1) * sizeof(rfwb200_point_light)));
+		CK(c->d_spot.reserve(std::max<size_t>(n.spot, 1) * sizeof(rfwb200_spot_light)));
+		CK(c->d_dir.reserve(std::max<size_t>(n.directional, 1) * sizeof(rfwb200_directional_light)));
+		if (n.area)
+			CK(cudaMemcpy(c->d_area.ptr, a, n.area * sizeof(*a), cudaMemcpyHostToDevice));
+		if (n.point)
+			CK(cudaMemcpy(c->d_point.ptr, p, n.point * sizeof(*p), cudaMemcpyHostToDevice));
+		if (n.spot)
+			CK(cudaMemcpy(c->d_spot.ptr, s, n.spot * sizeof(*s), cudaMemcpyHostToDevice));
+		if (n.directional)
+			CK(cudaMemcpy(c->d_dir.ptr, d, n.directional * sizeof(*d), cudaMemcpyHostToDevice));
+		c->scene.area_lights = c->d_area.ptr, c->scene.point_lights = c->d_point.ptr;
+		c->scene.spot_lights = c->d_spot.ptr, c->scene.dir_lights = c->d_dir.ptr;
+		c->scene.lights = LightCounts{n.area, n.point, n.spot, n.directional};
+		return RFWB200_OK;
+	}
+
+	int rfwb200_update(rfwb200_context *c)
+	{
+		REQUIRE(c != nullptr, "context is null");
+		if (int r = ensure_device(c))
+			return r;
+		if (!c->geometry_dirty && c->scene.nodes)
+			return RFWB200_OK;
+		CK(cudaStreamSynchronize(c->stream));
+		std::vector<ShadeTri> shade;
+		std::vector<float> det_eps;
+		if (int r = flatten_scene(c, shade, det_eps))
+			return r;
+		// topology unchanged since the last build => refit (bvh_tree.cpp:104-114)
+		std::vector<std::pair<int, size_t>> layout;
+		for (const HostInstance &in : c->instances)
+			layout.emplace_back(in.mesh, in.mesh >= 0 ? c->meshes[in.mesh].triangles.size() : 0);
+		const bool can_refit = !c->topology_dirty && layout == c->built_layout && !c->bvh.nodes.empty() &&
+							   c->bvh.tri_order.size() == c->build_tris.size();
+		const auto t0 = std::chrono::steady_clock::now();
+		if (can_refit)
+			refit_bvh4(c->build_tris.data(), c->build_tris.size(), c->bvh);
+		else
+		{
+			const int threads = int(std::max(1u, std::thread::hardware_concurrency()));
+			build_bvh4(c->build_tris.data(), c->build_tris.size(), threads, c->bvh);
+		}
+		c->bvh.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+		if (3 * c->bvh.depth + 1 > TRAVERSAL_STACK)
+			return set_error(RFWB200_ERR_INVALID, "BVH deeper than the traversal stack allows");
+		c->built_layout = layout;
+		if (int r = upload_bvh(c, det_eps))
+			return r;
+		CK(c->d_shade_tris.reserve(std::max<size_t>(shade.size(), 1) * sizeof(ShadeTri)));
+		if (!shade.empty())
+			CK(cudaMemcpy(c->d_shade_tris.ptr, shade.data(), shade.size() * sizeof(ShadeTri), cudaMemcpyHostToDevice));
+		c->scene.shade_tris = c->d_shade_tris.as<ShadeTri>();
+		c->geometry_dirty = false, c->topology_dirty = false;
+		c->dims_valid = false; // node count may have changed the staged prefix
+		return RFWB200_OK;
+	}
+
+	int rfwb200_set_setting(rfwb200_context *c, const char *key, const char *value)
+	{
+		REQUIRE(c && key && value, "bad setting");
+		const std::string k = key, v = value;
+		if (k == "spp")
+		{
+			const int n = atoi(v.c_str());
+			REQUIRE(n >= 1 && n <= 65536, "spp must be in [1, 65536]");
+			c->spp = n;
+		}
+		else if (k == "mode")
+		{
+			REQUIRE(v == "pt" || v == "embree", "mode must be 'pt' or 'embree'");
+			c->mode_pt = (v == "pt");
+		}
+		else if (k == "max_path_length")
+		{
+			const int n = atoi(v.c_str());
+			REQUIRE(n >= 0 && n < MAX_DEPTH_SLOTS, "max_path_length must be in [0, 7]");
+			c->rs.max_path_length = n;
+		}
+		else if (k == "clamp")
+			c->rs.clamp_value = float(atof(v.c_str()));
+		else if (k == "survival_scale")
+			c->rs.survival_scale = (v == "on" || v == "1") ? 1 : 0;
+		else if (k == "smem_nodes")
+		{
+			const int n = atoi(v.c_str());
+			REQUIRE(n >= 0 && n <= 1700, "smem_nodes must be in [0, 1700] (227 KB of shared memory)");
+			c->rs.smem_nodes = n;
+			c->dims_valid = false;
+		}
+		else if (k == "threads")
+		{
+		}
+		else
+			return set_error(RFWB200_ERR_INVALID, "unknown setting '" + k + "'");
+		return RFWB200_OK;
+	}
+
+	int rfwb200_get_settings(const rfwb200_context *c, char *buf, size_t buf_size)
+	{
+		REQUIRE(c && buf && buf_size > 0, "bad buffer");
+		const std::string s = "spp=" + std::to_string(c->spp) + "\nmode=pt|embree\nmax_path_length=" +
+							  std::to_string(c->rs.max_path_length) + "\nclamp=" + std::to_string(c->rs.clamp_value) +
+							  "\nsurvival_scale=on|off\nsmem_nodes=" + std::to_string(c->rs.smem_nodes) + "\n";
+		snprintf(buf, buf_size, "%s", s.c_str());
+		return RFWB200_OK;
+	}
+
+	int rfwb200_render_frame(rfwb200_context *c, const rfwb200_camera_view *view, int status)
+	{
+		REQUIRE(c && view, "bad arguments");
+		if (int r = ensure_device(c))
+			return r;
+		if (int r = check_ready(c))
+			return r;
+		if (int r = ensure_dims(c))
+			return r;
+		const uint32_t spp = c->mode_pt ? uint32_t(c->spp) : 1u;
+		if (int r = ensure_counters(c, spp))
+			return r;
+		cudaStream_t st = c->stream;
+		CK(cudaEventRecord(c->ev_begin, st));
+		if (status == RFWB200_RESET)
+		{
+			CK(cudaMemsetAsync(c->d_acc.ptr, 0, size_t(c->shard.local_pixels) * sizeof(float4), st));
+			c->sample_index = 0;
+		}
+		CK(cudaMemsetAsync(c->d_counters.ptr, 0, size_t(spp) * MAX_DEPTH_SLOTS * sizeof(DepthCounters), st));
+		if (c->sample_index == 0)
+		{
+			const ProbeResult none{0, 0, 0.f, 0};
+			CK(cudaMemcpyAsync(c->d_probe.ptr, &none, sizeof(none), cudaMemcpyHostToDevice, st));
+		}
+		if (int r = upload_frame_params(c, view, c->sample_index))
+			return r;
+		c->last_first_sample = c->sample_index;
+		if (c->mode_pt)
+		{
+			const uint32_t maxd = uint32_t(c->rs.max_path_length);
+			for (uint32_t s = 0; s < spp; s++)
+			{
+				CK(launch_primary(c->scene, c->shard, c->wf, c->rs, s, c->dims, st));
+				CK(launch_shade(c->scene, c->shard, c->wf, c->rs, s, 0, c->dims, st));
+				c->launches += 2;
+				for (uint32_t d = 1; d <= maxd; d++)
+				{
+					CK(launch_trace(c->scene, c->shard, c->wf, c->rs, s, d, c->dims, st));
+					CK(launch_shade(c->scene, c->shard, c->wf, c->rs, s, d, c->dims, st));
+					c->launches += 2;
+				}
+			}
+			c->sample_index += spp;
+			CK(launch_finalize(c->shard, c->wf, 1.0f / float(c->sample_index), st)); // blit_buffer, Kernels.cu:181-203
+			c->launches += 1;
+		}
+		else
+		{
+			// EmbreeRT renders one un-accumulated sample per call (Context.cpp:104-300)
+			CK(launch_emode(c->scene, c->shard, c->wf, c->rs, c->d_materials_raw.ptr, c->d_tex_desc.as<uint32_t>(),
+							uint32_t(c->textures.size()), c->dims, st));
+			c->launches += 1;
+			c->sample_index += 1;
+		}
+		CK(cudaEventRecord(c->ev_end, st));
+		c->last_spp = spp;
+		c->frame_in_flight = true;
+		return RFWB200_OK;
+	}
+
+	void *rfwb200_device_framebuffer(rfwb200_context *c) { return c ? c->d_fb.ptr : nullptr; }
+
+	size_t rfwb200_local_pixel_count(const rfwb200_context *c)
+	{
+		if (!c)
+			return 0;
+		return c->shard.world == 1 ? size_t(c->width) * c->height : size_t(c->shard.local_pixels);
+	}
+
+	size_t rfwb200_shard_stride(const rfwb200_context *c) { return c ? shard_stride_pixels(c->shard) : 0; }
+
+	int rfwb200_read_framebuffer(rfwb200_context *c, float *host_rgba, size_t capacity_pixels)
+	{
+		REQUIRE(c && host_rgba, "bad arguments");
+		if (int r = ensure_device(c))
+			return r;
+		const size_t n = rfwb200_local_pixel_count(c);
+		REQUIRE(capacity_pixels >= n, "host buffer too small");
+		CK(cudaMemcpyAsync(host_rgba, c->d_fb.ptr, n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+		return RFWB200_OK;
+	}
+
+	int rfwb200_assemble_shards(rfwb200_context *c, const void *gathered, void *image_out)
+	{
+		REQUIRE(c && gathered && image_out, "bad arguments");
+		if (int r = ensure_device(c))
+			return r;
+		CK(launch_assemble(c->shard, static_cast<const float4 *>(gathered), shard_stride_pixels(c->shard),
+						   static_cast<float4 *>(image_out), c->stream));
+		c->launches += 1;
+		return RFWB200_OK;
+	}
+
+	int rfwb200_synchronize(rfwb200_context *c)
+	{
+		REQUIRE(c != nullptr, "context is null");
+		if (int r = ensure_device(c))
+			return r;
+		CK(cudaStreamSynchronize(c->stream));
+		return RFWB200_OK;
+	}
+
+	int rfwb200_set_probe_index(rfwb200_context *c, uint32_t x, uint32_t y)
+	{
+		REQUIRE(c != nullptr, "context is null");
+		c->probe_x = x, c->probe_y = y;
+		return RFWB200_OK;
+	}
+
+	int rfwb200_get_probe_results(rfwb200_context *c, uint32_t *inst, uint32_t *prim, float *dist)
+	{
+		REQUIRE(c && inst && prim && dist, "bad arguments");
+		if (int r = ensure_device(c))
+			return r;
+		ProbeResult p{0, 0, 0.f, 0};
+		if (c->d_probe.ptr)
+		{
+			CK(cudaMemcpyAsync(&p, c->d_probe.ptr, sizeof(p), cudaMemcpyDeviceToHost, c->stream));
+			CK(cudaStreamSynchronize(c->stream));
+		}
+		*inst = uint32_t(p.inst), *prim = uint32_t(p.prim), *dist = p.dist;
+		return RFWB200_OK;
+	}
+
+	static int fetch_counters(Ctx *c)
+	{
+		const size_t n = size_t(c->last_spp) * MAX_DEPTH_SLOTS;
+		c->host_counters.assign(n, DepthCounters{});
+		if (n == 0)
+			return RFWB200_OK;
+		CK(cudaMemcpyAsync(c->host_counters.data(), c->d_counters.ptr, n * sizeof(DepthCounters), cudaMemcpyDeviceToHost,
+						   c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+		return RFWB200_OK;
+	}
+
+	int rfwb200_get_frame_counters(rfwb200_context *c, rfwb200_frame_counters *out)
+	{
+		REQUIRE(c && out, "bad arguments");
+		if (int r = ensure_device(c))
+			return r;
+		memset(out, 0, sizeof(*out));
+		if (int r = fetch_counters(c))
+			return r;
+		// live pixels of this shard
+		uint64_t live = 0;
+		{
+			const ShardView &s = c->shard;
+			for (uint32_t lt = 0; lt < s.local_tiles; lt++)
+			{
+				const uint32_t gt = lt * s.world + s.rank;
+				const uint32_t ty = gt / s.tiles_x, tx = gt % s.tiles_x;
+				const uint32_t w = std::min(s.tile_w, s.width - std::min(s.width, tx * s.tile_w));
+				const uint32_t h = std::min(s.tile_h, s.height - std::min(s.height, ty * s.tile_h));
+				live += uint64_t(w) * h;
+			}
+		}
+		out->pixels = live;
+		out->samples = c->last_spp;
+		if (!c->mode_pt)
+		{
+			out->n_gen = out->n_ext = live;
+			return RFWB200_OK;
+		}
+		const uint32_t maxd = uint32_t(c->rs.max_path_length);
+		for (uint32_t s = 0; s < c->last_spp; s++)
+		{
+			const DepthCounters *dc = &c->host_counters[size_t(s) * MAX_DEPTH_SLOTS];
+			out->n_gen += live, out->n_ext += live, out->n_shade += live;
+			for (uint32_t d = 0; d <= maxd; d++)
+			{
+				out->n_ext_out += dc[d].ext;
+				out->n_acc += dc[d].acc;
+				if (d >= 1)
+				{
+					out->n_ext += dc[d - 1].ext;
+					out->n_shade += dc[d - 1].ext;
+					out->n_nee += dc[d].shadow_traced;
+				}
+			}
+		}
+		return RFWB200_OK;
+	}
+
+	int rfwb200_get_stats(rfwb200_context *c, rfwb200_render_stats *out)
+	{
+		REQUIRE(c && out, "bad arguments");
+		if (int r = ensure_device(c))
+			return r;
+		memset(out, 0, sizeof(*out));
+		if (!c->frame_in_flight)
+			return RFWB200_OK;
+		CK(cudaEventSynchronize(c->ev_end));
+		float ms = 0;
+		CK(cudaEventElapsedTime(&ms, c->ev_begin, c->ev_end));
+		out->render_time = ms;
+		rfwb200_frame_counters fc;
+		if (int r = rfwb200_get_frame_counters(c, &fc))
+			return r;
+		out->primary_count = uint32_t(fc.n_gen);
+		if (c->mode_pt && c->last_spp)
+		{
+			uint64_t sec = 0, deep = 0, shadow = 0;
+			for (uint32_t s = 0; s < c->last_spp; s++)
+			{
+				const DepthCounters *dc = &c->host_counters[size_t(s) * MAX_DEPTH_SLOTS];
+				for (uint32_t d = 1; d <= uint32_t(c->rs.max_path_length); d++)
+				{
+					(d == 1 ? sec : deep) += dc[d - 1].ext;
+					shadow += dc[d].shadow_traced;
+				}
+			}
+			out->secondary_count = uint32_t(sec), out->deep_count = uint32_t(deep), out->shadow_count = uint32_t(shadow);
+		}
+		return RFWB200_OK;
+	}
+
+	uint64_t rfwb200_launch_count(const rfwb200_context *c) { return c ? c->launches : 0; }
+
+	int rfwb200_get_bvh_info(const rfwb200_context *c, uint64_t *nodes, uint64_t *triangles, float *sah_cost, float *build_ms)
+	{
+		REQUIRE(c != nullptr, "context is null");
+		if (nodes)
+			*nodes = c->bvh.nodes.size();
+		if (triangles)
+			*triangles = c->bvh.tri_order.size();
+		if (sah_cost)
+			*sah_cost = c->bvh.sah_cost;
+		if (build_ms)
+			*build_ms = float(c->bvh.build_ms);
+		return RFWB200_OK;
+	}
+
+	// ---- stage-level entry points -----------------------------------------------------------------
+
+	int rfwb200_trace_closest(rfwb200_context *c, const float *origins, const float *directions, size_t n, float t_min,
+							  rfwb200_hit *hits_out)
+	{
+		REQUIRE(c && origins && directions && hits_out, "bad arguments");
+		REQUIRE(n < (1ull << 31), "too many rays");
+		if (int r = ensure_device(c))
+			return r;
+		if (c->geometry_dirty || !c->scene.nodes)
+			return set_error(RFWB200_ERR_STATE, "call rfwb200_update first");
+		if (int r = ensure_dims(c))
+			return r;
+		if (n == 0)
+			return RFWB200_OK;
+		CK(c->d_scratch_cursor.reserve(256));
+		DevBuf dO, dD, dH;
+		CK(dO.reserve(n * 16));
+		CK(dD.reserve(n * 16));
+		CK(dH.reserve(n * 16));
+		cudaStream_t st = c->stream;
+		CK(cudaMemcpyAsync(dO.ptr, origins, n * 16, cudaMemcpyHostToDevice, st));
+		CK(cudaMemcpyAsync(dD.ptr, directions, n * 16, cudaMemcpyHostToDevice, st));
+		CK(cudaMemsetAsync(c->d_scratch_cursor.ptr, 0, 4, st));
+		CK(launch_trace_closest(c->scene, c->rs, dO.as<float4>(), dD.as<float4>(), uint32_t(n), t_min, dH.as<float4>(),
+								c->d_scratch_cursor.as<uint32_t>(), c->dims, st));
+		c->launches += 1;
+		std::vector<float> raw(n * 4);
+		CK(cudaMemcpyAsync(raw.data(), dH.ptr, n * 16, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		// translate shading-record indices back to (instance, primitive)
+		std::vector<ShadeTri> shade(c->flat_tri_count);
+		if (c->flat_tri_count)
+			CK(cudaMemcpy(shade.data(), c->d_shade_tris.ptr, shade.size() * sizeof(ShadeTri), cudaMemcpyDeviceToHost));
+		for (size_t i = 0; i < n; i++)
+		{
+			uint32_t tri;
+			memcpy(&tri, &raw[4 * i + 3], 4);
+			hits_out[i].t = raw[4 * i], hits_out[i].u = raw[4 * i + 1], hits_out[i].v = raw[4 * i + 2];
+			if (tri == 0xffffffffu || tri >= shade.size())
+				hits_out[i].inst_id = -1, hits_out[i].prim_id = -1, hits_out[i].u = 0, hits_out[i].v = 0;
+			else
+				hits_out[i].inst_id = int32_t(shade[tri].inst_id), hits_out[i].prim_id = int32_t(shade[tri].prim_id);
+		}
+		return RFWB200_OK;
+	}
+
+	int rfwb200_trace_occluded(rfwb200_context *c, const float *origins, const float *directions, const float *t_max,
+							   size_t n, float t_min, uint8_t *occluded_out)
+	{
+		REQUIRE(c && origins && directions && t_max && occluded_out, "bad arguments");
+		REQUIRE(n < (1ull << 31), "too many rays");
+		if (int r = ensure_device(c))
+			return r;
+		if (c->geometry_dirty || !c->scene.nodes)
+			return set_error(RFWB200_ERR_STATE, "call rfwb200_update first");
+		if (int r = ensure_dims(c))
+			return r;
+		if (n == 0)
+			return RFWB200_OK;
+		std::vector<float> dt(n * 4);
+		for (size_t i = 0; i < n; i++)
+			dt[4 * i] = directions[4 * i], dt[4 * i + 1] = directions[4 * i + 1], dt[4 * i + 2] = directions[4 * i + 2],
+					dt[4 * i + 3] = t_max[i];
+		CK(c->d_scratch_cursor.reserve(256));
+		DevBuf dO, dD, dR;
+		CK(dO.reserve(n * 16));
+		CK(dD.reserve(n * 16));
+		CK(dR.reserve(n));
+		cudaStream_t st = c->stream;
+		CK(cudaMemcpyAsync(dO.ptr, origins, n * 16, cudaMemcpyHostToDevice, st));
+		CK(cudaMemcpyAsync(dD.ptr, dt.data(), n * 16, cudaMemcpyHostToDevice, st));
+		CK(cudaMemsetAsync(c->d_scratch_cursor.ptr, 0, 4, st));
+		CK(launch_trace_occluded(c->scene, c->rs, dO.as<float4>(), dD.as<float4>(), uint32_t(n), t_min, dR.as<uint8_t>(),
+								 c->d_scratch_cursor.as<uint32_t>(), c->dims, st));
+		c->launches += 1;
+		CK(cudaMemcpyAsync(occluded_out, dR.ptr, n, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		return RFWB200_OK;
+	}
+
+	int rfwb200_generate_primary(rfwb200_context *c, const rfwb200_camera_view *view, uint32_t sample_index,
+								 float *origins_out, float *directions_out, size_t capacity_rays)
+	{
+		REQUIRE(c && view && origins_out && directions_out, "bad arguments");
+		if (int r = ensure_device(c))
+			return r;
+		if (!c->initialised)
+			return set_error(RFWB200_ERR_STATE, "rfwb200_init has not been called");
+		REQUIRE(c->shard.world == 1, "generate_primary is a single-shard debug entry point");
+		const size_t P = size_t(c->width) * c->height;
+		REQUIRE(capacity_rays >= P, "host buffers too small");
+		if (int r = upload_frame_params(c, view, sample_index))
+			return r;
+		DevBuf dO, dD;
+		CK(dO.reserve(P * 16));
+		CK(dD.reserve(P * 16));
+		cudaStream_t st = c->stream;
+		CK(cudaMemsetAsync(dO.ptr, 0, P * 16, st));
+		CK(cudaMemsetAsync(dD.ptr, 0, P * 16, st));
+		CK(launch_generate_only(c->scene, c->shard, c->wf, sample_index, c->mode_pt ? 0 : 1, dO.as<float4>(), dD.as<float4>(), st));
+		c->launches += 1;
+		CK(cudaMemcpyAsync(origins_out, dO.ptr, P * 16, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(directions_out, dD.ptr, P * 16, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		return RFWB200_OK;
+	}
+
+} // extern "C"

@@ -1,0 +1,143 @@
+// device_types.h — HBM-resident data layouts shared by the host side (context.cpp, bvh_build.cpp)
+// and the kernels (kernels.cu).  See DESIGN.md "Data layout in HBM".
+#pragma once
+#include <stdint.h>
+#include <vector_types.h>
+
+namespace rfwb200
+{
+
+// 4-wide BVH node, 128 B = one L2 line.  SoA child boxes like the reference's MBVHNode
+// (RFW/system/bvh/include/bvh/mbvh_node.h:60-106) so one slab test is four independent FMAs per
+// plane, but with a single signed child word: >= 0 inner-node index, < 0 leaf with
+// ~child = (first_triangle << 2) | (count - 1).  Unused slots carry an inverted box (never hit).
+// Nodes are stored breadth-first, so the top of the tree is one contiguous prefix that a CTA can
+// stage into shared memory with a single bulk (TMA) copy.
+struct alignas(16) BvhNode4
+{
+	float minx[4], maxx[4], miny[4], maxy[4], minz[4], maxz[4];
+	int32_t child[4];
+	int32_t pad[4];
+};
+static_assert(sizeof(BvhNode4) == 128, "node must be one 128-byte line");
+
+// Intersection record of one (instance-flattened, world-space) triangle, 48 B, stored in BVH leaf
+// order so a leaf is one contiguous run: p0 and the two edges Moller-Trumbore needs
+// (the reference precomputes the same triple on the CPU, RFW/system/bvh/src/bvh_tree.cpp:413-415).
+struct alignas(16) TriRec
+{
+	float p0x, p0y, p0z, e1x;
+	float e1y, e1z, e2x, e2y;
+	float e2z;
+	uint32_t shade_idx; // index into ShadeTri[]
+	float det_eps;		// T_EPSILON * |det(instance linear part)|: the reference tests the determinant in
+						// object space (CUDART/src/Kernels.cu:269-271 + CUDAIntersect.h:61-63)
+	uint32_t pad0;
+};
+static_assert(sizeof(TriRec) == 48, "triangle record is 3 x 16 bytes");
+
+// What shade needs from rfw::DeviceTriangle (160 B, device_structs.h:22-34), repacked to 96 B with
+// the instance's normal matrix already applied to the four normals (the reference applies it per
+// path, CUDART/src/getShadingData.h:129-130).
+struct alignas(16) ShadeTri
+{
+	float u0, u1, u2;
+	int32_t light_tri_idx;
+	float v0, v1, v2;
+	uint32_t material;
+	float n0x, n0y, n0z, Nx; // normal-matrix * vN0 (not normalised), world geometric normal x
+	float n1x, n1y, n1z, Ny;
+	float n2x, n2y, n2z, Nz;
+	float area, lod;
+	uint32_t inst_id, prim_id;
+};
+static_assert(sizeof(ShadeTri) == 96, "shading triangle is 6 x 16 bytes");
+
+// per (sample, depth) queue sizes and per-launch work cursors; zeroed once per frame.
+struct DepthCounters
+{
+	uint32_t ext;		  // extension rays emitted by shade(depth)          (counters->extensionRays)
+	uint32_t shadow;	  // shadow rays emitted by shade(depth)             (counters->shadowRays)
+	uint32_t trace_cursor; // persistent-thread work cursor of the trace launch consuming them
+	uint32_t shade_cursor; // work cursor of the shade launch at this depth
+	uint32_t acc;		  // accumulator read-modify-writes at this depth
+	uint32_t shadow_traced; // shadow rays actually traced by connect (reference drops some)
+	uint32_t pad0, pad1;
+};
+static_assert(sizeof(DepthCounters) == 32, "");
+
+constexpr int MAX_DEPTH_SLOTS = 8; // max_path_length + 1 <= 8
+
+struct ProbeResult
+{
+	int32_t inst, prim;
+	float dist;
+	uint32_t pad;
+};
+
+// constant per frame; lives in device memory so a captured CUDA graph stays valid across frames
+struct FrameParams
+{
+	float pos[3], p1[3], right[3], up[3]; // CameraView with right = p2-p1, up = p3-p1
+	float aperture, spread_angle;
+	uint32_t sample_base; // sample index of the first sample of this frame
+	uint32_t probe_pixel; // global pixel id, 0xffffffff = none
+};
+
+struct LightCounts
+{
+	uint32_t area, point, spot, directional;
+};
+
+// everything a kernel needs; passed by value (fits the 4 KB parameter space easily)
+struct SceneView
+{
+	const BvhNode4 *nodes;
+	const TriRec *tris;
+	const ShadeTri *shade_tris;
+	uint32_t node_count, tri_count;
+	const void *materials; // rfwb200_material[ ] (192 B, texaddr patched)
+	uint32_t material_count;
+	const uint32_t *uint_texels;
+	uint32_t uint_texel_count;
+	const float *float_texels; // float4
+	uint32_t float_texel_count;
+	const float *sky; // float4 per texel (rgb, 0)
+	uint32_t sky_w, sky_h;
+	const void *area_lights, *point_lights, *spot_lights, *dir_lights;
+	LightCounts lights;
+	const uint8_t *blue_noise; // 327,680 table bytes at the offsets of createBlueNoiseBuffer (blue_noise.h:8204-8219)
+};
+
+struct ShardView
+{
+	uint32_t width, height;		// full image
+	uint32_t rank, world;		// this context's shard
+	uint32_t tile_w, tile_h;	// multiples of 8 / 4
+	uint32_t tiles_x, tiles_y;	// tile grid of the full image
+	uint32_t local_tiles;		// tiles owned by this rank
+	uint32_t local_pixels;		// local_tiles * tile_w * tile_h (padded: edge tiles carry dead pixels)
+};
+
+struct WavefrontView
+{
+	float4 *O[2], *D[2], *T[2]; // ping-pong planes: origin|pathIdx<<8|flags, direction|packed normal, throughput|pdf
+	float4 *hit;				// bits(u16|v16<<16), bits(shade_idx), bits(prim or -1), t
+	float4 *sO, *sD, *sE;		// connect queue: origin, direction|tmax, contribution|bits(local pixel)
+	float4 *accumulator;		// per local pixel
+	float4 *framebuffer;		// finalised
+	DepthCounters *counters;	// [spp][MAX_DEPTH_SLOTS]
+	ProbeResult *probe;
+	const FrameParams *frame;
+};
+
+struct RenderSettings
+{
+	int max_path_length;
+	float clamp_value;
+	float geometry_epsilon;
+	int survival_scale;
+	int smem_nodes;
+};
+
+} // namespace rfwb200

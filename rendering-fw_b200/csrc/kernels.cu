@@ -1,0 +1,1753 @@
+// kernels.cu — sm_100a wavefront path-tracing kernels.
+//
+// Stage map (reference semantics in parentheses; paths relative to /root/reference/RFW):
+//   k_primary   generate + extend for camera rays  (backends/CUDART/src/Kernels.cu:383-460)
+//   k_shade     material eval + NEE + BSDF sample + compaction (Kernels.cu:571-794,
+//               CUDART/src/getShadingData.h, CUDART/src/lights.h, system/context/rfw/bsdf/*.h)
+//   k_trace     extend (closest hit) for extension rays and connect (any hit) for shadow rays of
+//               one bounce in ONE persistent launch (Kernels.cu:461-498, CUDAIntersect.h)
+//   k_finalize  accumulator / samples (Kernels.cu:181-203)
+//   k_emode     the image model of backends/EmbreeRT/src/Context.cpp:104-300 as one fused kernel
+//
+// B200 design: persistent CTAs sized from the occupancy API (multiples of 148 SMs)
+// pull 32-ray chunks from a device cursor, so no launch depends on a host-read count; the
+// breadth-first prefix of the BVH is staged into shared memory once per CTA with one TMA bulk copy
+// (cp.async.bulk + mbarrier; SASS: UBLKCP); ray / hit / throughput state is float4 SoA moved with
+// 128-bit coalesced loads and stores; queue compaction is warp-aggregated (ballot + popc, one
+// atomic per warp); tensor cores are not used (no dense contraction on this path).
+#include "kernels.h"
+
+#include "../../include/rfwb200.h"
+#include "bvh_build.h"
+
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace rfwb200
+{
+
+// ------------------------------------------------------------------------------------------------
+// small math
+// ------------------------------------------------------------------------------------------------
+struct V3
+{
+	float x, y, z;
+};
+__device__ __forceinline__ V3 mk(float x, float y, float z) { return V3{x, y, z}; }
+__device__ __forceinline__ V3 mk(float a) { return V3{a, a, a}; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 operator*(V3 a, V3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ V3 operator*(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ V3 operator*(float s, V3 a) { return mk(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ V3 operator/(V3 a, float s) { return mk(a.x / s, a.y / s, a.z / s); }
+__device__ __forceinline__ V3 operator-(V3 a) { return mk(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 cross(V3 a, V3 b)
+{
+	return mk(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y);
+}
+__device__ __forceinline__ float length(V3 a) { return sqrtf(dot(a, a)); }
+__device__ __forceinline__ V3 normalize(V3 a) { return a * (1.0f / sqrtf(dot(a, a))); }
+__device__ __forceinline__ V3 reflect(V3 I, V3 N) { return I - N * (dot(N, I) * 2.0f); }
+__device__ __forceinline__ bool any_nan(V3 a) { return isnan(a.x) || isnan(a.y) || isnan(a.z); }
+__device__ __forceinline__ V3 ld3(const float *p) { return mk(p[0], p[1], p[2]); }
+__device__ __forceinline__ float lerpf(float a, float b, float t) { return a + t * (b - a); }
+__device__ __forceinline__ V3 lerp3(V3 a, V3 b, float t) { return a + (b - a) * t; }
+__device__ __forceinline__ float sqr(float x) { return x * x; }
+__device__ __forceinline__ float signf(float v) { return v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f); }
+
+constexpr float INVPI = 0.318309886183790671537767526745028724f;
+constexpr float PI = 3.14159265358979323846264338327950288f;
+constexpr float INV2PI = 0.159154943091895335768883763372514362f;
+constexpr float TWOPI = 6.28318530717958647692528676655900576f;
+constexpr int MIPLEVELCOUNT = 5;		 // context/settings.h:3
+constexpr float MIN_ROUGHNESS = 0.01f;	 // context/settings.h:4
+constexpr int MAX_IS_LIGHTS = 16;		 // CUDART/src/Kernels.cu:21
+constexpr uint32_t IS_SPECULAR = 1u;	 // CUDART/src/Kernels.cu:20
+constexpr int32_t PRIM_MISS = -1;		 // hit.z on a miss (Kernels.cu:454)
+constexpr int32_t PRIM_DEAD = -2;		 // padded pixel of an edge tile: never shaded
+constexpr float T_EPSILON = 1e-6f;		 // CUDART/src/Kernels.cu:23
+
+enum MatFlagBits
+{
+	HasDiffuseMap = 2,
+	HasNormalMap = 3,
+	HasSpecularityMap = 4,
+	HasRoughnessMap = 5,
+	Has2ndNormalMap = 7,
+	Has3rdNormalMap = 8,
+	Has2ndDiffuseMap = 9,
+	Has3rdDiffuseMap = 10,
+	HasSmoothNormals = 11,
+	HasAlpha = 12,
+	HasAlphaMap = 13
+};
+__device__ __forceinline__ bool has_flag(uint32_t f, int b) { return (f >> b) & 1u; }
+
+// ------------------------------------------------------------------------------------------------
+// hashing / samplers — bsdf/tools.h:218-235, Kernels.cu:205-224, utils/xor128.h:20-27
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t WangHash(uint32_t s)
+{
+	s = (s ^ 61u) ^ (s >> 16);
+	s *= 9u;
+	s = s ^ (s >> 4);
+	s *= 0x27d4eb2du;
+	s = s ^ (s >> 15);
+	return s;
+}
+__device__ __forceinline__ uint32_t RandomInt(uint32_t &s)
+{
+	s ^= s << 13;
+	s ^= s >> 17;
+	s ^= s << 5;
+	return s;
+}
+__device__ __forceinline__ float RandomFloat(uint32_t &s) { return float(RandomInt(s)) * 2.3283064365387e-10f; }
+
+__device__ __forceinline__ float blueNoiseSampler(const uint8_t *__restrict__ bn, int x, int y, int sampleIdx, int dim)
+{
+	x &= 127, y &= 127, sampleIdx &= 255, dim &= 255;
+	const int ranked = sampleIdx ^ int(__ldg(bn + dim + (x + y * 128) * 8 + 65536 * 3));
+	int value = int(__ldg(bn + dim + ranked * 256));
+	value ^= int(__ldg(bn + (dim & 7) + (x + y * 128) * 8 + 65536));
+	return (0.5f + float(value)) * (1.0f / 256.0f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// screen tiling: local work index -> pixel.  A tile is tile_w x tile_h pixels, tiles are dealt
+// round-robin to ranks, and inside a tile consecutive 32 indices form an 8x4 pixel block so one
+// warp traces a compact bundle of camera rays.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool local_to_pixel(const ShardView &sh, uint32_t j, uint32_t &x, uint32_t &y)
+{
+	const uint32_t tp = sh.tile_w * sh.tile_h;
+	const uint32_t lt = j / tp, w = j - lt * tp;
+	const uint32_t gt = lt * sh.world + sh.rank;
+	const uint32_t ty = gt / sh.tiles_x, tx = gt - ty * sh.tiles_x;
+	const uint32_t blk = w >> 5, lane = w & 31u;
+	const uint32_t bpr = sh.tile_w >> 3;
+	const uint32_t by = blk / bpr, bx = blk - by * bpr;
+	x = tx * sh.tile_w + bx * 8u + (lane & 7u);
+	y = ty * sh.tile_h + by * 4u + (lane >> 3);
+	return (x < sh.width) & (y < sh.height) & (ty < sh.tiles_y);
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA bulk staging of the BVH prefix into shared memory
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void stage_nodes(float4 *smem_nodes, const BvhNode4 *gnodes, uint32_t n_stage, uint64_t *mbar)
+{
+	if (n_stage == 0)
+		return;
+	const uint32_t bar = smem_u32(mbar);
+	if (threadIdx.x == 0)
+	{
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		const uint32_t bytes = n_stage * uint32_t(sizeof(BvhNode4));
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+						 smem_u32(smem_nodes)),
+					 "l"(gnodes), "r"(bytes), "r"(bar)
+					 : "memory");
+	}
+	// every thread waits for the bytes to land (phase 0)
+	uint32_t done = 0;
+	while (!done)
+	{
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+					 : "=r"(done)
+					 : "r"(bar), "r"(0u)
+					 : "memory");
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// extend / connect: stack-based traversal of the flattened BVH4 + Moller-Trumbore
+// (CUDAIntersect.h:48-94,155-197,270-322,391-439).  Children hit by the ray are ordered near to far
+// with the reference's trick of stuffing the slot index into the two mantissa LSBs of tmin.
+// ------------------------------------------------------------------------------------------------
+struct NodeRegs
+{
+	float4 minx, maxx, miny, maxy, minz, maxz;
+	int4 child;
+};
+
+__device__ __forceinline__ NodeRegs load_node(const SceneView &sc, const float4 *__restrict__ snodes, uint32_t n_smem,
+											  uint32_t idx)
+{
+	NodeRegs n;
+	if (idx < n_smem)
+	{
+		const float4 *p = snodes + size_t(idx) * 8;
+		n.minx = p[0], n.maxx = p[1], n.miny = p[2], n.maxy = p[3], n.minz = p[4], n.maxz = p[5];
+		n.child = *reinterpret_cast<const int4 *>(p + 6);
+	}
+	else
+	{
+		const float4 *p = reinterpret_cast<const float4 *>(sc.nodes) + size_t(idx) * 8;
+		n.minx = __ldg(p + 0), n.maxx = __ldg(p + 1), n.miny = __ldg(p + 2), n.maxy = __ldg(p + 3);
+		n.minz = __ldg(p + 4), n.maxz = __ldg(p + 5);
+		n.child = __ldg(reinterpret_cast<const int4 *>(p + 6));
+	}
+	return n;
+}
+
+__device__ __forceinline__ float slab(float lo, float hi, float idir, float ood, float &tfar_out)
+{
+	const float t1 = fmaf(lo, idir, -ood), t2 = fmaf(hi, idir, -ood);
+	tfar_out = fmaxf(t1, t2);
+	return fminf(t1, t2);
+}
+
+#define CHILD_T(K, C)                                                                                                   \
+	{                                                                                                                   \
+		float fx, fy, fz;                                                                                               \
+		const float nx = slab(n.minx.C, n.maxx.C, idx, oodx, fx);                                                       \
+		const float ny = slab(n.miny.C, n.maxy.C, idy, oody, fy);                                                       \
+		const float nz = slab(n.minz.C, n.maxz.C, idz, oodz, fz);                                                       \
+		const float tn = fmaxf(fmaxf(nx, ny), nz), tf = fminf(fminf(fx, fy), fz);                                       \
+		const bool h = (tf >= tn) & (tn < tmax) & (tf >= tmin);                                                         \
+		nh += h ? 1 : 0;                                                                                                \
+		key##K = h ? __uint_as_float((__float_as_uint(fmaxf(tn, 0.0f)) & 0xFFFFFFFCu) | uint32_t(K)) : MISSKEY(K);      \
+	}
+#define MISSKEY(K) __uint_as_float(0x7f000000u | uint32_t(K))
+#define CSWAP(A, B)                                                                                                     \
+	{                                                                                                                   \
+		const float lo_ = fminf(A, B), hi_ = fmaxf(A, B);                                                               \
+		A = lo_, B = hi_;                                                                                               \
+	}
+#define PICK(KEY) (((__float_as_uint(KEY) & 3u) == 0u) ? n.child.x : (((__float_as_uint(KEY) & 3u) == 1u) ? n.child.y : (((__float_as_uint(KEY) & 3u) == 2u) ? n.child.z : n.child.w)))
+
+template <bool ANY_HIT>
+__device__ __forceinline__ bool traverse(const SceneView &sc, const float4 *__restrict__ snodes, uint32_t n_smem, V3 o,
+										 V3 d, float tmin, float &tmax, uint32_t &hit_tri, float &hit_u, float &hit_v)
+{
+	const float tiny = 1e-30f;
+	const float idx = 1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));
+	const float idy = 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));
+	const float idz = 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
+	const float oodx = o.x * idx, oody = o.y * idy, oodz = o.z * idz;
+	int stack[TRAVERSAL_STACK];
+	int sp = 0;
+	int cur = 0;
+	bool found = false;
+	const float4 *__restrict__ tris = reinterpret_cast<const float4 *>(sc.tris);
+	for (;;)
+	{
+		if (cur >= 0)
+		{
+			const NodeRegs n = load_node(sc, snodes, n_smem, uint32_t(cur));
+			float key0, key1, key2, key3;
+			int nh = 0;
+			CHILD_T(0, x)
+			CHILD_T(1, y)
+			CHILD_T(2, z)
+			CHILD_T(3, w)
+			if (nh == 0)
+			{
+				if (sp == 0)
+					break;
+				cur = stack[--sp];
+				continue;
+			}
+			CSWAP(key0, key1)
+			CSWAP(key2, key3)
+			CSWAP(key0, key2)
+			CSWAP(key1, key3)
+			CSWAP(key1, key2)
+			cur = PICK(key0);
+			if (nh > 1)
+			{
+				if (nh > 3)
+					stack[sp++] = PICK(key3);
+				if (nh > 2)
+					stack[sp++] = PICK(key2);
+				stack[sp++] = PICK(key1);
+			}
+		}
+		else
+		{
+			const uint32_t v = uint32_t(~cur), first = v >> 2, cnt = (v & 3u) + 1u;
+			for (uint32_t i = 0; i < cnt; i++)
+			{
+				const float4 a = __ldg(tris + size_t(first + i) * 3 + 0);
+				const float4 b = __ldg(tris + size_t(first + i) * 3 + 1);
+				const float4 c = __ldg(tris + size_t(first + i) * 3 + 2);
+				const V3 p0 = mk(a.x, a.y, a.z), e1 = mk(a.w, b.x, b.y), e2 = mk(b.z, b.w, c.x);
+				const V3 h = cross(d, e2);
+				const float det = dot(e1, h);
+				const float eps = c.z;
+				if (det > -eps && det < eps)
+					continue;
+				const float f = 1.0f / det;
+				const V3 s = o - p0;
+				const float u = f * dot(s, h);
+				if (u < 0.0f || u > 1.0f)
+					continue;
+				const V3 q = cross(s, e1);
+				const float vv = f * dot(d, q);
+				if (vv < 0.0f || u + vv > 1.0f)
+					continue;
+				const float t = f * dot(e2, q);
+				if (t > tmin && tmax > t)
+				{
+					if (ANY_HIT)
+						return true;
+					tmax = t, hit_u = u, hit_v = vv, hit_tri = __float_as_uint(c.y);
+					found = true;
+				}
+			}
+			if (sp == 0)
+				break;
+			cur = stack[--sp];
+		}
+	}
+	return found;
+}
+
+// ------------------------------------------------------------------------------------------------
+// generate — Kernels.cu:383-426 (PT: blue noise dims 0-3), EmbreeRT/src/Ray.cpp:16-47 (E-mode: xor128)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void camera_ray(const FrameParams &fp, const ShardView &sh, uint32_t x, uint32_t y, float r0,
+										   float r1, float r2, float r3, bool cuda_sincos_order, V3 &O, V3 &D)
+{
+	const float blade = float(int(r0 * 9));
+	r2 = (r2 - blade * (1.0f / 9.0f)) * 9.0f;
+	constexpr float piOver4point5 = 3.14159265359f / 4.5f;
+	float s1, c1, s2, c2;
+	sincosf(blade * piOver4point5, &s1, &c1);
+	sincosf((blade + 1.0f) * piOver4point5, &s2, &c2);
+	// CUDART: __sincosf(a,&x1,&y1) => x = sin, y = cos (Kernels.cu:406-407); EmbreeRT: x = cos, y = sin
+	const float x1 = cuda_sincos_order ? s1 : c1, y1 = cuda_sincos_order ? c1 : s1;
+	const float x2 = cuda_sincos_order ? s2 : c2, y2 = cuda_sincos_order ? c2 : s2;
+	if ((r2 + r3) > 1.0f)
+		r2 = 1.0f - r2, r3 = 1.0f - r3;
+	const float xr = x1 * r2 + x2 * r3;
+	const float yr = y1 * r2 + y2 * r3;
+	const V3 pos = ld3(fp.pos), p1 = ld3(fp.p1), right = ld3(fp.right), up = ld3(fp.up);
+	O = pos + (right * xr + up * yr) * fp.aperture;
+	const float u = (float(x) + r0) * (1.0f / float(sh.width));
+	const float v = (float(y) + r1) * (1.0f / float(sh.height));
+	D = normalize(p1 + right * u + up * v - O);
+}
+
+__device__ __forceinline__ void generate_pt(const SceneView &sc, const FrameParams &fp, const ShardView &sh, uint32_t x,
+											uint32_t y, uint32_t sampleIndex, V3 &O, V3 &D)
+{
+	const float r0 = blueNoiseSampler(sc.blue_noise, int(x), int(y), int(sampleIndex), 0);
+	const float r1 = blueNoiseSampler(sc.blue_noise, int(x), int(y), int(sampleIndex), 1);
+	const float r2 = blueNoiseSampler(sc.blue_noise, int(x), int(y), int(sampleIndex), 2);
+	const float r3 = blueNoiseSampler(sc.blue_noise, int(x), int(y), int(sampleIndex), 3);
+	camera_ray(fp, sh, x, y, r0, r1, r2, r3, true, O, D);
+}
+
+__device__ __forceinline__ void generate_emode(const FrameParams &fp, const ShardView &sh, uint32_t x, uint32_t y,
+											   uint32_t sampleIndex, V3 &O, V3 &D)
+{
+	// determinism contract: xor128 with x seeded per (pixel, sample)
+	const uint32_t pixel = y * sh.width + x;
+	uint32_t sx = 123456789u ^ WangHash(pixel * 16789u + sampleIndex * 1791u), sy = 362436069u, sz = 521288629u,
+			 sw = 88675123u;
+	float r[4];
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+	{
+		const uint32_t t = sx ^ (sx << 11);
+		sx = sy, sy = sz, sz = sw;
+		sw = sw ^ (sw >> 19) ^ (t ^ (t >> 8));
+		r[i] = float(sw) * 2.3283064365387e-10f;
+	}
+	camera_ray(fp, sh, x, y, r[0], r[1], r[2], r[3], false, O, D);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_primary — generate + extend for every local pixel of one sample
+// ------------------------------------------------------------------------------------------------
+extern __shared__ __align__(128) unsigned char g_dyn_smem[];
+
+__global__ void __launch_bounds__(256) k_primary(const SceneView sc, const ShardView sh, const WavefrontView wf,
+												const RenderSettings rs, const uint32_t sample_in_frame)
+{
+	__shared__ uint64_t mbar;
+	float4 *snodes = reinterpret_cast<float4 *>(g_dyn_smem);
+	const uint32_t n_smem = min(uint32_t(rs.smem_nodes), sc.node_count);
+	stage_nodes(snodes, sc.nodes, n_smem, &mbar);
+
+	const FrameParams fp = *wf.frame;
+	const uint32_t sampleIndex = fp.sample_base + sample_in_frame;
+	uint32_t *cursor = &wf.counters[sample_in_frame * MAX_DEPTH_SLOTS + 0].trace_cursor;
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t total = sh.local_pixels;
+	for (;;)
+	{
+		uint32_t base = 0;
+		if (lane == 0)
+			base = atomicAdd(cursor, 32u);
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (base >= total)
+			break;
+		const uint32_t j = base + lane;
+		if (j >= total)
+			continue;
+		uint32_t x, y;
+		float4 hit = make_float4(0.f, 0.f, __int_as_float(PRIM_DEAD), 0.f);
+		if (local_to_pixel(sh, j, x, y))
+		{
+			V3 O, D;
+			generate_pt(sc, fp, sh, x, y, sampleIndex, O, D);
+			wf.O[0][j] = make_float4(O.x, O.y, O.z, __uint_as_float((j << 8) + 1u));
+			wf.D[0][j] = make_float4(D.x, D.y, D.z, 0.0f);
+			float t = 1e34f, u = 0.f, v = 0.f;
+			uint32_t tri = 0;
+			hit = make_float4(0.f, 0.f, __int_as_float(PRIM_MISS), 0.f);
+			if (traverse<false>(sc, snodes, n_smem, O, D, 1e-5f, t, tri, u, v))
+				hit = make_float4(__uint_as_float(uint32_t(65535.0f * u) | (uint32_t(65535.0f * v) << 16)),
+								  __uint_as_float(tri), __int_as_float(0), t);
+		}
+		wf.hit[j] = hit;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_trace — one bounce: closest hit for the extension queue, any hit for the connect queue
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_trace(const SceneView sc, const ShardView sh, const WavefrontView wf,
+											  const RenderSettings rs, const uint32_t sample_in_frame,
+											  const uint32_t depth)
+{
+	__shared__ uint64_t mbar;
+	float4 *snodes = reinterpret_cast<float4 *>(g_dyn_smem);
+	const uint32_t n_smem = min(uint32_t(rs.smem_nodes), sc.node_count);
+	stage_nodes(snodes, sc.nodes, n_smem, &mbar);
+
+	DepthCounters *prev = &wf.counters[sample_in_frame * MAX_DEPTH_SLOTS + depth - 1];
+	DepthCounters *curc = &wf.counters[sample_in_frame * MAX_DEPTH_SLOTS + depth];
+	const uint32_t n_ext = prev->ext;
+	// the reference only traces the connect queue when the bounce loop continues, i.e. when at least
+	// one extension ray exists (CUDART/src/Context.cpp:109-120)
+	const uint32_t n_shadow = n_ext > 0 ? prev->shadow : 0u;
+	const uint32_t ext_pad = (n_ext + 31u) & ~31u;
+	const uint32_t total = ext_pad + n_shadow;
+	const uint32_t buf = depth & 1u;
+	const float4 *__restrict__ Oin = wf.O[buf];
+	const float4 *__restrict__ Din = wf.D[buf];
+	uint32_t *cursor = &curc->trace_cursor;
+	const uint32_t lane = threadIdx.x & 31u;
+	uint32_t acc_count = 0;
+	for (;;)
+	{
+		uint32_t base = 0;
+		if (lane == 0)
+			base = atomicAdd(cursor, 32u);
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (base >= total)
+			break;
+		const uint32_t i = base + lane;
+		if (base < ext_pad)
+		{
+			if (i < n_ext)
+			{
+				const float4 O4 = Oin[i], D4 = Din[i];
+				float t = 1e34f, u = 0.f, v = 0.f;
+				uint32_t tri = 0;
+				float4 hit = make_float4(0.f, 0.f, __int_as_float(PRIM_MISS), 0.f);
+				if (traverse<false>(sc, snodes, n_smem, mk(O4.x, O4.y, O4.z), mk(D4.x, D4.y, D4.z), 1e-5f, t, tri, u, v))
+					hit = make_float4(__uint_as_float(uint32_t(65535.0f * u) + (uint32_t(65535.0f * v) << 16)),
+									  __uint_as_float(tri), __int_as_float(0), t);
+				wf.hit[i] = hit;
+			}
+		}
+		else
+		{
+			const uint32_t k = i - ext_pad;
+			if (k < n_shadow)
+			{
+				const float4 O4 = wf.sO[k], D4 = wf.sD[k];
+				float tmax = D4.w, u, v;
+				uint32_t tri;
+				if (!traverse<true>(sc, snodes, n_smem, mk(O4.x, O4.y, O4.z), mk(D4.x, D4.y, D4.z), rs.geometry_epsilon, tmax,
+									tri, u, v))
+				{
+					const float4 E = wf.sE[k];
+					const uint32_t pixel = __float_as_uint(E.w);
+					float4 a = wf.accumulator[pixel];
+					a.x += E.x, a.y += E.y, a.z += E.z, a.w += 1.0f;
+					wf.accumulator[pixel] = a;
+					acc_count++;
+				}
+			}
+		}
+	}
+	// bookkeeping for the algorithmic-bytes formula: one atomic per warp
+	acc_count = __reduce_add_sync(0xffffffffu, acc_count);
+	if (lane == 0 && acc_count)
+		atomicAdd(&curc->acc, acc_count);
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+		curc->shadow_traced = n_shadow;
+}
+
+// ------------------------------------------------------------------------------------------------
+// shading helpers — bsdf/tools.h, bsdf/compat.h, bsdf/disney.h, CUDART/src/getShadingData.h,
+// CUDART/src/lights.h
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t PackNormal(V3 N) // tools.h:10-21
+{
+	const float f = 65535.0f / fmaxf(sqrtf(8.0f * N.z + 8.0f), 0.0001f);
+	return uint32_t(N.x * f + 32767.0f) + (uint32_t(N.y * f + 32767.0f) << 16);
+}
+__device__ __forceinline__ V3 UnpackNormal(uint32_t p) // tools.h:22-29
+{
+	float nx = float(p & 65535u) * (2.0f / 65535.0f), ny = float(p >> 16) * (2.0f / 65535.0f);
+	nx += -1.f, ny += -1.f;
+	float l = nx * -nx + ny * -ny + 1.0f;
+	const float nz = l;
+	l = sqrtf(l);
+	nx *= l, ny *= l;
+	return mk(nx, ny, nz) * 2.0f + mk(0.f, 0.f, -1.f);
+}
+__device__ __forceinline__ float SurvivalProbability(V3 d) { return fminf(1.0f, fmaxf(fmaxf(d.x, d.y), d.z)); }
+__device__ __forceinline__ void clampIntensity(V3 &v, float clampValue) // tools.h:184-192
+{
+	const float m = fmaxf(v.x, fmaxf(v.y, v.z));
+	if (m > clampValue)
+		v = v * (clampValue / m);
+}
+__device__ __forceinline__ void createTangentSpace(V3 N, V3 &T, V3 &B) // tools.h:205-212
+{
+	const float s = signf(N.z);
+	const float a = -1.0f / (s + N.z);
+	const float b = N.x * N.y * a;
+	T = mk(1.0f + s * N.x * N.x * a, s * b, -s * N.x);
+	B = mk(b, s + N.y * N.y * a, -N.y);
+}
+__device__ __forceinline__ V3 DiffuseReflectionUniform(float r0, float r1) // tools.h:102-108
+{
+	const float term1 = TWOPI * r0, term2 = sqrtf(1 - r1 * r1);
+	float s, c;
+	sincosf(term1, &s, &c);
+	return mk(c * term2, s * term2, r1);
+}
+__device__ __forceinline__ V3 DiffuseReflectionCosWeighted(float r0, float r1) // tools.h:110-117
+{
+	const float term1 = TWOPI * r0;
+	const float term2 = sqrtf(1.0f - r1);
+	float s, c;
+	sincosf(term1, &s, &c);
+	return normalize(mk(c * term2, s * term2, sqrtf(r1)));
+}
+
+struct ShadingData // bsdf/compat.h:47-74
+{
+	V3 color;
+	uint32_t flags;
+	V3 absorption;
+	uint32_t p0, p1, p2;
+	__device__ __forceinline__ static float c2f(uint32_t v, int s) { return float((v >> s) & 255u) * (1.0f / 255.0f); }
+	__device__ __forceinline__ float metallic() const { return c2f(p0, 0); }
+	__device__ __forceinline__ float subsurface() const { return c2f(p0, 8); }
+	__device__ __forceinline__ float specular() const { return c2f(p0, 16); }
+	__device__ __forceinline__ float roughness() const { return fmaxf(0.001f, c2f(p0, 24)); }
+	__device__ __forceinline__ float spectint() const { return c2f(p1, 0); }
+	__device__ __forceinline__ float clearcoat() const { return c2f(p2, 0); }
+	__device__ __forceinline__ float clearcoatgloss() const { return c2f(p2, 8); }
+	__device__ __forceinline__ float transmission() const { return c2f(p2, 16); }
+	__device__ __forceinline__ float eta() const { return c2f(p2, 24); }
+	__device__ __forceinline__ bool isEmissive() const { return color.x > 1.0f || color.y > 1.0f || color.z > 1.0f; }
+};
+
+__device__ __forceinline__ bool Refract(V3 wi, V3 n, float eta, V3 &wt) // disney.h:20-30
+{
+	const float cosThetaI = dot(n, wi);
+	const float sin2ThetaI = fmaxf(0.0f, 1.0f - cosThetaI * cosThetaI);
+	const float sin2ThetaT = eta * eta * sin2ThetaI;
+	if (sin2ThetaT >= 1)
+		return false;
+	const float cosThetaT = sqrtf(1.0f - sin2ThetaT);
+	wt = (wi * -1.0f) * eta + n * (eta * cosThetaI - cosThetaT);
+	return true;
+}
+__device__ __forceinline__ float SchlickFresnel(float u) // disney.h:32-36
+{
+	const float m = fminf(fmaxf(1 - u, 0.0f), 1.0f);
+	return (m * m) * (m * m) * m;
+}
+__device__ __forceinline__ float GTR1(float NDotH, float a) // disney.h:38-45
+{
+	if (a >= 1.0f)
+		return INVPI;
+	const float a2 = a * a;
+	const float t = 1 + (a2 - 1) * NDotH * NDotH;
+	return (a2 - 1) / (PI * logf(a2) * t);
+}
+__device__ __forceinline__ float GTR2(float NDotH, float a) // disney.h:47-52
+{
+	const float a2 = a * a;
+	const float t = 1.0f + (a2 - 1.0f) * NDotH * NDotH;
+	return a2 / (PI * t * t);
+}
+__device__ __forceinline__ float SmithGGX(float NDotv, float alphaG) // disney.h:54-59
+{
+	const float a = alphaG * alphaG;
+	const float b = NDotv * NDotv;
+	return 1 / (NDotv + sqrtf(a + b - a * b));
+}
+__device__ __forceinline__ float Fr(float VDotN, float eio) // disney.h:61-72
+{
+	const float SinThetaT2 = sqr(eio) * (1.0f - VDotN * VDotN);
+	if (SinThetaT2 > 1.0f)
+		return 1.0f;
+	const float LDotN = sqrtf(1.0f - SinThetaT2);
+	const float eta = 1.0f / eio;
+	const float r1 = (VDotN - eta * LDotN) / (VDotN + eta * LDotN);
+	const float r2 = (LDotN - eta * VDotN) / (LDotN + eta * VDotN);
+	return 0.5f * (sqr(r1) + sqr(r2));
+}
+__device__ __forceinline__ V3 SafeNormalize(V3 a) // disney.h:74-81
+{
+	const float ls = dot(a, a);
+	if (ls > 0.0f)
+		return a * (1.0f / sqrtf(ls));
+	return mk(0.f);
+}
+
+__device__ float BSDFPdf(const ShadingData &sd, V3 N, V3 wo, V3 wi) // disney.h:83-101
+{
+	float bsdfPdf = 0.0f, brdfPdf;
+	if (dot(wi, N) <= 0.0f)
+		brdfPdf = INV2PI * sd.subsurface() * 0.5f;
+	else
+	{
+		const float F = Fr(dot(N, wo), sd.eta());
+		const V3 halfway = SafeNormalize(wi + wo);
+		const float cosThetaHalf = fabsf(dot(halfway, N));
+		const float pdfHalf = GTR2(cosThetaHalf, sd.roughness()) * cosThetaHalf;
+		const float pdfSpec = 0.25f * pdfHalf / fmaxf(1.e-6f, dot(wi, halfway));
+		const float pdfDiff = fabsf(dot(wi, N)) * INVPI * (1.0f - sd.subsurface());
+		bsdfPdf = pdfSpec * F;
+		brdfPdf = lerpf(pdfDiff, pdfSpec, 0.5f);
+	}
+	return lerpf(brdfPdf, bsdfPdf, sd.transmission());
+}
+
+__device__ V3 BSDFEval(const ShadingData &sd, V3 N, V3 wo, V3 wi, float t, bool backfacing) // disney.h:104-185
+{
+	const float NDotL = dot(N, wi);
+	const float NDotV = dot(N, wo);
+	const V3 H = normalize(wi + wo);
+	const float NDotH = dot(N, H);
+	const float LDotH = dot(wi, H);
+	const V3 Cdlin = sd.color;
+	const float Cdlum = .3f * Cdlin.x + .6f * Cdlin.y + .1f * Cdlin.z;
+	const V3 Ctint = Cdlum > 0.0f ? Cdlin / Cdlum : mk(1.0f);
+	const float TRANSMISSION = sd.transmission(), METALLIC = sd.metallic(), SUBSURFACE = sd.subsurface();
+	const V3 Cspec0 = lerp3(lerp3(mk(1.0f), Ctint, sd.spectint()) * (sd.specular() * .08f), Cdlin, METALLIC);
+	V3 bsdf = mk(0.f), brdf = mk(0.f);
+	if (TRANSMISSION > 0.0f)
+	{
+		if (NDotL <= 0)
+		{
+			const float F = Fr(NDotV, sd.eta());
+			bsdf = mk((1.0f - F) / fabsf(NDotL) * (1.0f - METALLIC) * TRANSMISSION);
+		}
+		else
+		{
+			const float a = sd.roughness();
+			const float Ds = GTR2(NDotH, a);
+			const float FH = Fr(LDotH, sd.eta());
+			const V3 Fs = lerp3(Cspec0, mk(1.0f), FH);
+			const float Gs = SmithGGX(NDotV, a) * SmithGGX(NDotL, a);
+			bsdf = Fs * (Gs * Ds);
+		}
+	}
+	if (TRANSMISSION < 1.0f)
+	{
+		if (NDotL <= 0)
+		{
+			if (SUBSURFACE > 0.0f)
+			{
+				const V3 s = mk(sqrtf(sd.color.x), sqrtf(sd.color.y), sqrtf(sd.color.z));
+				const float FL = SchlickFresnel(fabsf(NDotL)), FV = SchlickFresnel(NDotV);
+				const float Fd = (1.0f - 0.5f * FL) * (1.0f - 0.5f * FV);
+				brdf = s * INVPI * SUBSURFACE * Fd * (1.0f - METALLIC);
+			}
+		}
+		else
+		{
+			const float a = sd.roughness();
+			const float Ds = GTR2(NDotH, a);
+			const float FH = SchlickFresnel(LDotH);
+			const V3 Fs = lerp3(Cspec0, mk(1.0f), FH);
+			const float Gs = SmithGGX(NDotV, a) * SmithGGX(NDotL, a);
+			const float FL = SchlickFresnel(NDotL), FV = SchlickFresnel(NDotV);
+			const float Fd90 = 0.5f + 2.0f * LDotH * LDotH * a;
+			const float Fd = lerpf(1.0f, Fd90, FL) * lerpf(1.0f, Fd90, FV);
+			const float Dr = GTR1(NDotH, lerpf(.1f, .001f, sd.clearcoatgloss()));
+			const float Fc = lerpf(.04f, 1.0f, FH);
+			const float Gr = SmithGGX(NDotL, .25f) * SmithGGX(NDotV, .25f);
+			brdf = Cdlin * (INVPI * Fd) * (1.0f - METALLIC) * (1.0f - SUBSURFACE) + Fs * Gs * Ds +
+				   mk(sd.clearcoat() * Gr * Fc * Dr);
+		}
+	}
+	const V3 fin = lerp3(brdf, bsdf, TRANSMISSION);
+	if (backfacing)
+		return fin * mk(expf(-sd.absorption.x * t), expf(-sd.absorption.y * t), expf(-sd.absorption.z * t));
+	return fin;
+}
+
+__device__ void BSDFSample(const ShadingData &sd, V3 T, V3 B, V3 N, V3 wo, V3 &wi, float &pdf, float r3,
+						   float r4) // disney.h:188-262
+{
+	const float transmission = sd.transmission();
+	if (r3 < transmission)
+	{
+		const float F = Fr(dot(N, wo), sd.eta());
+		if (r4 < F)
+		{
+			const float r1 = r3 / transmission;
+			const float r2 = r4 / F;
+			const float cosThetaHalf = sqrtf((1.0f - r2) / (1.0f + (sqr(sd.roughness()) - 1.0f) * r2));
+			const float sinThetaHalf = sqrtf(fmaxf(0.0f, 1.0f - sqr(cosThetaHalf)));
+			float sinPhiHalf, cosPhiHalf;
+			sincosf(r1 * TWOPI, &sinPhiHalf, &cosPhiHalf);
+			V3 halfway = T * (sinThetaHalf * cosPhiHalf) + B * (sinThetaHalf * sinPhiHalf) + N * cosThetaHalf;
+			if (dot(halfway, wo) <= 0.0f)
+				halfway = halfway * -1.0f;
+			wi = reflect(wo * -1.0f, halfway);
+		}
+		else
+		{
+			pdf = 0;
+			if (Refract(wo, N, sd.eta(), wi))
+				pdf = (1.0f - F) * transmission;
+		}
+		return;
+	}
+	const float r1 = (r3 - transmission) / (1 - transmission);
+	if (r4 < 0.5f)
+	{
+		const float r2 = r4 * 2;
+		const float subsurface = sd.subsurface();
+		V3 d;
+		if (r2 < subsurface)
+		{
+			const float r5 = r2 / subsurface;
+			d = DiffuseReflectionUniform(r1, r5);
+			d.z *= -1.0f;
+		}
+		else
+		{
+			const float r5 = (r2 - subsurface) / (1.0f - subsurface);
+			d = DiffuseReflectionCosWeighted(r1, r5);
+		}
+		wi = T * d.x + B * d.y + N * d.z;
+	}
+	else
+	{
+		const float r2 = (r4 - 0.5f) * 2.0f;
+		const float cosThetaHalf = sqrtf((1.0f - r2) / (1.0f + (sqr(sd.roughness()) - 1.0f) * r2));
+		const float sinThetaHalf = sqrtf(fmaxf(0.0f, 1.0f - sqr(cosThetaHalf)));
+		float sinPhiHalf, cosPhiHalf;
+		sincosf(r1 * TWOPI, &sinPhiHalf, &cosPhiHalf);
+		V3 halfway = T * (sinThetaHalf * cosPhiHalf) + B * (sinThetaHalf * sinPhiHalf) + N * cosThetaHalf;
+		if (dot(halfway, wo) <= 0.0f)
+			halfway = halfway * -1.0f;
+		wi = reflect(wo * -1.0f, halfway);
+	}
+	pdf = BSDFPdf(sd, N, wo, wi);
+}
+
+// ---- textures: CUDART/src/getShadingData.h:23-98 ------------------------------------------------
+__device__ __forceinline__ float4 texel_rgba8(const SceneView &sc, uint32_t i)
+{
+	if (i >= sc.uint_texel_count)
+		return make_float4(0.f, 0.f, 0.f, 0.f);
+	const uint32_t v = __ldg(sc.uint_texels + i);
+	const float r = 1.0f / 256.0f;
+	return make_float4(float(v & 255u) * r, float((v >> 8) & 255u) * r, float((v >> 16) & 255u) * r, float(v >> 24) * r);
+}
+__device__ float4 FetchTexel(const SceneView &sc, float tcx, float tcy, int o, int w, int h)
+{
+	if (w <= 0 || h <= 0)
+		return make_float4(0.f, 0.f, 0.f, 0.f);
+	const float tx = (fmaxf(tcx + 1000, 0.0f) * float(w)) - 0.5f, ty = (fmaxf(tcy + 1000, 0.0f) * float(h)) - 0.5f;
+	const int iu = __float2int_rz(tx) % w;
+	const int iv = __float2int_rz(ty) % h;
+	const float fu = tx - floorf(tx);
+	const float fv = ty - floorf(ty);
+	const float w0 = (1 - fu) * (1 - fv);
+	const float w1 = fu * (1 - fv);
+	const float w2 = (1 - fu) * fv;
+	const float w3 = 1 - (w0 + w1 + w2);
+	const uint32_t iu1 = uint32_t(iu + 1) % uint32_t(w), iv1 = uint32_t(iv + 1) % uint32_t(h);
+	const float4 p0 = texel_rgba8(sc, uint32_t(o) + iu + uint32_t(iv) * w), p1 = texel_rgba8(sc, uint32_t(o) + iu1 + uint32_t(iv) * w);
+	const float4 p2 = texel_rgba8(sc, uint32_t(o) + iu + iv1 * w), p3 = texel_rgba8(sc, uint32_t(o) + iu1 + iv1 * w);
+	return make_float4(p0.x * w0 + p1.x * w1 + p2.x * w2 + p3.x * w3, p0.y * w0 + p1.y * w1 + p2.y * w2 + p3.y * w3,
+					   p0.z * w0 + p1.z * w1 + p2.z * w2 + p3.z * w3, p0.w * w0 + p1.w * w1 + p2.w * w2 + p3.w * w3);
+}
+__device__ float4 FetchTexelTrilinear(const SceneView &sc, float lambda, float tcx, float tcy, int offset, int width,
+									  int height)
+{
+	const int level0 = min(MIPLEVELCOUNT - 1, __float2int_rz(lambda));
+	const int level1 = min(MIPLEVELCOUNT - 1, level0 + 1);
+	const float f = lambda - floorf(lambda);
+	uint32_t offset0 = offset, width0 = width, height0 = height;
+	for (int i = 0; i < level0; i++)
+		offset0 += width0 * height0, width0 >>= 1u, height0 >>= 1u;
+	// level1 = min(4, level0 + 1) differs from level0 only for 0 <= level0 < 4 (negative levels select
+	// the base level for both fetches, exactly like the reference's zero-trip loops)
+	const bool second = level0 >= 0 && level0 < MIPLEVELCOUNT - 1;
+	const float4 p0 = FetchTexel(sc, tcx, tcy, int(offset0), int(width0), int(height0));
+	float4 p1 = p0;
+	if (second)
+		p1 = FetchTexel(sc, tcx, tcy, int(offset0 + width0 * height0), int(width0 >> 1u), int(height0 >> 1u));
+	return make_float4((1.0f - f) * p0.x + f * p1.x, (1.0f - f) * p0.y + f * p1.y, (1.0f - f) * p0.z + f * p1.z,
+					   (1.0f - f) * p0.w + f * p1.w);
+}
+
+struct MapDesc
+{
+	int w, h;
+	float us, vs, uo, vo;
+	uint32_t addr;
+};
+__device__ __forceinline__ MapDesc load_map(const rfwb200_map_desc *m)
+{
+	const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(m));
+	MapDesc d;
+	d.w = int(short(raw.x & 0xffffu)), d.h = int(short(raw.x >> 16));
+	d.us = __half2float(__ushort_as_half((unsigned short)(raw.y & 0xffffu)));
+	d.vs = __half2float(__ushort_as_half((unsigned short)(raw.y >> 16)));
+	d.uo = __half2float(__ushort_as_half((unsigned short)(raw.z & 0xffffu)));
+	d.vo = __half2float(__ushort_as_half((unsigned short)(raw.z >> 16)));
+	d.addr = raw.w;
+	return d;
+}
+
+// getShadingData.h:100-217 on the repacked ShadeTri (normals are already in world space)
+__device__ ShadingData getShadingData(const SceneView &sc, V3 D, float u, float v, float coneWidth, const ShadeTri &tri, V3 &N,
+									  V3 &iN, V3 &T, V3 &B)
+{
+	ShadingData r;
+	const rfwb200_material *mat = reinterpret_cast<const rfwb200_material *>(sc.materials) + tri.material;
+	const uint4 base = __ldg(reinterpret_cast<const uint4 *>(mat));
+	const uint4 par = __ldg(reinterpret_cast<const uint4 *>(mat) + 1);
+	const uint32_t flags = base.w;
+	r.flags = 0;
+	r.color = mk(__half2float(__ushort_as_half((unsigned short)(base.x & 0xffffu))),
+				 __half2float(__ushort_as_half((unsigned short)(base.x >> 16))),
+				 __half2float(__ushort_as_half((unsigned short)(base.y & 0xffffu))));
+	r.absorption = mk(__half2float(__ushort_as_half((unsigned short)(base.y >> 16))),
+					  __half2float(__ushort_as_half((unsigned short)(base.z & 0xffffu))),
+					  __half2float(__ushort_as_half((unsigned short)(base.z >> 16))));
+	r.p0 = par.x, r.p1 = par.y, r.p2 = par.z;
+	const float w = 1.0f - u - v;
+	N = mk(tri.Nx, tri.Ny, tri.Nz);
+	iN = N;
+	if (has_flag(flags, HasSmoothNormals))
+		iN = normalize(mk(tri.n0x, tri.n0y, tri.n0z) * w + mk(tri.n1x, tri.n1y, tri.n1z) * u + mk(tri.n2x, tri.n2y, tri.n2z) * v);
+	createTangentSpace(iN, T, B);
+	if (has_flag(flags, HasDiffuseMap))
+	{
+		const float tu = w * tri.u0 + u * tri.u1 + v * tri.u2;
+		const float tv = w * tri.v0 + u * tri.v1 + v * tri.v2;
+		const float lambda = tri.lod + log2f(coneWidth * (1.0f / fabsf(dot(-D, N))));
+		const MapDesc m0 = load_map(&mat->tex0);
+		const float4 texel = FetchTexelTrilinear(sc, lambda, m0.us * (m0.uo + tu), m0.vs * (m0.vo + tv), int(m0.addr), m0.w, m0.h);
+		if (has_flag(flags, HasAlpha) && texel.w < 0.5f)
+		{
+			r.flags |= 1;
+			return r;
+		}
+		r.color = r.color * mk(texel.x, texel.y, texel.z);
+		if (has_flag(flags, Has2ndDiffuseMap))
+		{
+			const MapDesc m = load_map(&mat->tex1);
+			const float4 t = FetchTexelTrilinear(sc, lambda, m.us * (m.uo + tu), m.vs * (m.vo + tv), int(m.addr), m.w, m.h);
+			r.color = r.color + mk(t.x, t.y, t.z);
+		}
+		if (has_flag(flags, Has3rdDiffuseMap))
+		{
+			const MapDesc m = load_map(&mat->tex2);
+			const float4 t = FetchTexelTrilinear(sc, lambda, m.us * (m.uo + tu), m.vs * (m.vo + tv), int(m.addr), m.w, m.h);
+			r.color = r.color + mk(t.x, t.y, t.z);
+		}
+		if (has_flag(flags, HasNormalMap))
+		{
+			const MapDesc m = load_map(&mat->nmap0);
+			const float4 t = FetchTexel(sc, m.us * (m.uo + tu), m.vs * (m.vo + tv), int(m.addr), m.w, m.h);
+			V3 sn = (mk(t.x, t.y, t.z) - mk(0.5f)) * 2.0f;
+			if (has_flag(flags, Has2ndNormalMap) || has_flag(flags, Has3rdNormalMap))
+			{
+				// the reference reads layer 1 for both the 2nd and the 3rd layer (getShadingData.h:194-200)
+				const MapDesc m1 = load_map(&mat->nmap1);
+				const float4 t1 = FetchTexel(sc, m1.us * (m1.uo + tu), m1.vs * (m1.vo + tv), int(m1.addr), m1.w, m1.h);
+				const V3 l1 = (mk(t1.x, t1.y, t1.z) - mk(0.5f)) * 2.0f;
+				if (has_flag(flags, Has2ndNormalMap))
+					sn = sn + l1;
+				if (has_flag(flags, Has3rdNormalMap))
+					sn = sn + l1;
+			}
+			sn = normalize(sn);
+			iN = normalize(T * sn.x + B * sn.y + iN * sn.z);
+		}
+		r.color = r.color * mk(texel.x, texel.y, texel.z); // second multiply, getShadingData.h:213
+	}
+	return r;
+}
+
+// ---- lights: CUDART/src/lights.h ---------------------------------------------------------------
+struct AreaLightRegs
+{
+	V3 normal, radiance, v0, v1, v2;
+	float energy, area;
+};
+__device__ __forceinline__ AreaLightRegs load_area_light(const SceneView &sc, int idx)
+{
+	const float4 *p = reinterpret_cast<const float4 *>(sc.area_lights) + size_t(idx) * 6;
+	const float4 a = __ldg(p + 0), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3), e = __ldg(p + 4), f = __ldg(p + 5);
+	AreaLightRegs l;
+	l.energy = a.w;
+	l.normal = mk(b.x, b.y, b.z), l.area = b.w;
+	l.radiance = mk(c.x, c.y, c.z);
+	l.v0 = mk(d.x, d.y, d.z), l.v1 = mk(e.x, e.y, e.z), l.v2 = mk(f.x, f.y, f.z);
+	return l;
+}
+__device__ float PotentialAreaLightContribution(const SceneView &sc, int idx, V3 O, V3 N, V3 I, V3 bary) // :17-36
+{
+	const AreaLightRegs light = load_area_light(sc, idx);
+	V3 L = I;
+	if (bary.x >= 0)
+		L = light.v0 * bary.x + light.v1 * bary.y + light.v2 * bary.z;
+	L = L - O;
+	const float att = 1.0f / dot(L, L);
+	L = normalize(L);
+	const float LNdotL = fmaxf(0.0f, -dot(light.normal, L));
+	const float NdotL = fmaxf(0.0f, dot(N, L));
+	return light.energy * LNdotL * NdotL * att;
+}
+__device__ float PotentialPointLightContribution(const SceneView &sc, int idx, V3 I, V3 N) // :38-46
+{
+	const float4 *p = reinterpret_cast<const float4 *>(sc.point_lights) + size_t(idx) * 2;
+	const float4 a = __ldg(p);
+	const V3 L = mk(a.x, a.y, a.z) - I;
+	const float NdotL = fmaxf(0.0f, dot(N, L));
+	const float att = 1.0f / dot(L, L);
+	return a.w * NdotL * att;
+}
+__device__ float PotentialSpotLightContribution(const SceneView &sc, int idx, V3 I, V3 N) // :48-68
+{
+	const float4 *p = reinterpret_cast<const float4 *>(sc.spot_lights) + size_t(idx) * 3;
+	const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+	V3 L = mk(a.x, a.y, a.z) - I;
+	const float att = 1.0f / dot(L, L);
+	L = normalize(L);
+	const float d = (fmaxf(0.0f, -dot(L, mk(c.x, c.y, c.z))) - b.w) / (a.w - b.w);
+	const float NdotL = fmaxf(0.0f, dot(N, L));
+	const float LNdotL = fmaxf(0.0f, fminf(1.0f, d));
+	return c.w * LNdotL * NdotL * att;
+}
+__device__ float PotentialDirectionalLightContribution(const SceneView &sc, int idx, V3 N) // :70-76
+{
+	const float4 a = __ldg(reinterpret_cast<const float4 *>(sc.dir_lights) + size_t(idx) * 2);
+	const float LNdotL = fmaxf(0.0f, -dot(mk(a.x, a.y, a.z), N));
+	return a.w * LNdotL;
+}
+__device__ float LightPickProb(const SceneView &sc, int idx, V3 O, V3 N, V3 I) // :83-116
+{
+	float sum = 0, mine = 0;
+	const int na = int(sc.lights.area);
+	for (int i = 0; i < na; i++)
+	{
+		const float c = PotentialAreaLightContribution(sc, i, O, N, I, mk(-1.0f));
+		if (i == idx)
+			mine = c;
+		sum += c;
+	}
+	for (uint32_t i = 0; i < sc.lights.point; i++)
+		sum += PotentialPointLightContribution(sc, int(i), O, N);
+	for (uint32_t i = 0; i < sc.lights.spot; i++)
+		sum += PotentialSpotLightContribution(sc, int(i), O, N);
+	for (uint32_t i = 0; i < sc.lights.directional; i++)
+		sum += PotentialDirectionalLightContribution(sc, int(i), N);
+	if (sum <= 0)
+		return 0;
+	if (idx < 0 || idx >= na || idx >= MAX_IS_LIGHTS)
+		return 0;
+	return mine / sum;
+}
+__device__ V3 RandomBarycentrics(float r0) // :119-157
+{
+	const uint32_t uf = __float2uint_rz(r0 * 4294967295.0f);
+	float Ax = 1.f, Ay = 0.f, Bx = 0.f, By = 1.f, Cx = 0.f, Cy = 0.f;
+#pragma unroll 1
+	for (int i = 0; i < 16; ++i)
+	{
+		const int d = int((uf >> (2 * (15 - i))) & 0x3);
+		float Anx, Any, Bnx, Bny, Cnx, Cny;
+		if (d == 0)
+			Anx = (Bx + Cx) * 0.5f, Any = (By + Cy) * 0.5f, Bnx = (Ax + Cx) * 0.5f, Bny = (Ay + Cy) * 0.5f,
+			Cnx = (Ax + Bx) * 0.5f, Cny = (Ay + By) * 0.5f;
+		else if (d == 1)
+			Anx = Ax, Any = Ay, Bnx = (Ax + Bx) * 0.5f, Bny = (Ay + By) * 0.5f, Cnx = (Ax + Cx) * 0.5f, Cny = (Ay + Cy) * 0.5f;
+		else if (d == 2)
+			Anx = (Bx + Ax) * 0.5f, Any = (By + Ay) * 0.5f, Bnx = Bx, Bny = By, Cnx = (Bx + Cx) * 0.5f, Cny = (By + Cy) * 0.5f;
+		else
+			Anx = (Cx + Ax) * 0.5f, Any = (Cy + Ay) * 0.5f, Bnx = (Cx + Bx) * 0.5f, Bny = (Cy + By) * 0.5f, Cnx = Cx, Cny = Cy;
+		Ax = Anx, Ay = Any, Bx = Bnx, By = Bny, Cx = Cnx, Cy = Cny;
+	}
+	const float rx = (Ax + Bx + Cx) * 0.3333333f, ry = (Ay + By + Cy) * 0.3333333f;
+	return mk(rx, ry, 1.0f - rx - ry);
+}
+__device__ V3 RandomPointOnLight(const SceneView &sc, float r0, float r1, V3 I, V3 N, float &pickProb, float &lightPdf,
+								 V3 &lightColor) // :159-265
+{
+	const int na = int(sc.lights.area), np = int(sc.lights.point), ns = int(sc.lights.spot), nd = int(sc.lights.directional);
+	const int lightCount = na + np + ns + nd;
+	const V3 bary = RandomBarycentrics(r0);
+	float potential[MAX_IS_LIGHTS];
+	float sum = 0, total = 0;
+	int lights = 0, lightIdx = 0;
+	for (int i = 0; i < na; i++)
+	{
+		const float c = PotentialAreaLightContribution(sc, i, I, N, mk(0.f), bary);
+		if (lights < MAX_IS_LIGHTS)
+			potential[lights] = c;
+		lights++, sum += c;
+	}
+	for (int i = 0; i < np; i++)
+	{
+		const float c = PotentialPointLightContribution(sc, i, I, N);
+		if (lights < MAX_IS_LIGHTS)
+			potential[lights] = c;
+		lights++, sum += c;
+	}
+	for (int i = 0; i < ns; i++)
+	{
+		const float c = PotentialSpotLightContribution(sc, i, I, N);
+		if (lights < MAX_IS_LIGHTS)
+			potential[lights] = c;
+		lights++, sum += c;
+	}
+	for (int i = 0; i < nd; i++)
+	{
+		const float c = PotentialDirectionalLightContribution(sc, i, N);
+		if (lights < MAX_IS_LIGHTS)
+			potential[lights] = c;
+		lights++, sum += c;
+	}
+	lights = min(lights, MAX_IS_LIGHTS);
+	if (sum <= 0)
+	{
+		lightPdf = 0;
+		return mk(1.0f);
+	}
+	r1 *= sum;
+	float picked = potential[0];
+	for (int i = 0; i < lights; i++)
+	{
+		total += potential[i];
+		if (total >= r1)
+		{
+			lightIdx = i, picked = potential[i];
+			break;
+		}
+	}
+	pickProb = picked / sum;
+	lightIdx = min(max(lightIdx, 0), lightCount - 1);
+	if (lightIdx < na)
+	{
+		const AreaLightRegs light = load_area_light(sc, lightIdx);
+		lightColor = light.radiance;
+		const V3 P = light.v0 * bary.x + light.v1 * bary.y + light.v2 * bary.z;
+		V3 L = I - P;
+		const float sqDist = dot(L, L);
+		L = normalize(L);
+		const float LNdotL = dot(L, light.normal);
+		const float reciSolidAngle = sqDist / (light.area * LNdotL);
+		// DeviceAreaLight::getEnergy() is length(radiance), not the stored field (device_structs.h:116)
+		lightPdf = (LNdotL > 0 && dot(L, N) < 0) ? (reciSolidAngle * (1.0f / length(light.radiance))) : 0;
+		return P;
+	}
+	if (lightIdx < na + np)
+	{
+		const float4 *p = reinterpret_cast<const float4 *>(sc.point_lights) + size_t(lightIdx - na) * 2;
+		const float4 a = __ldg(p), b = __ldg(p + 1);
+		const V3 pos = mk(a.x, a.y, a.z);
+		lightColor = mk(b.x, b.y, b.z);
+		const V3 L = I - pos;
+		const float sqDist = dot(L, L);
+		lightPdf = dot(L, N) < 0 ? (sqDist / a.w) : 0;
+		return pos;
+	}
+	if (lightIdx < na + np + ns)
+	{
+		const float4 *p = reinterpret_cast<const float4 *>(sc.spot_lights) + size_t(lightIdx - (na + np)) * 3;
+		const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+		const V3 P = mk(a.x, a.y, a.z), Dl = mk(c.x, c.y, c.z);
+		V3 L = I - P;
+		const float sqDist = dot(L, L);
+		L = normalize(L);
+		const float d = fmaxf(0.0f, dot(L, Dl) - b.w) / (a.w - b.w);
+		const float LNdotL = fminf(1.0f, d);
+		lightPdf = (LNdotL > 0 && dot(L, N) < 0) ? (sqDist / (LNdotL * c.w)) : 0;
+		lightColor = mk(b.x, b.y, b.z);
+		return P;
+	}
+	const float4 *p = reinterpret_cast<const float4 *>(sc.dir_lights) + size_t(lightIdx - (na + np + ns)) * 2;
+	const float4 a = __ldg(p), b = __ldg(p + 1);
+	const V3 L = mk(a.x, a.y, a.z);
+	lightColor = mk(b.x, b.y, b.z);
+	const float NdotL = dot(L, N);
+	lightPdf = NdotL < 0 ? (1.0f / a.w) : 0;
+	return I - L * 1000.0f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_shade — Kernels.cu:571-794.  Each thread shades one path into registers; the three outputs
+// (accumulate, connect-queue entry, extension-queue entry) are committed at one converged point
+// with warp-aggregated slot allocation.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_shade(const SceneView sc, const ShardView sh, const WavefrontView wf,
+											  const RenderSettings rs, const uint32_t sample_in_frame,
+											  const uint32_t pathLength)
+{
+	DepthCounters *curc = &wf.counters[sample_in_frame * MAX_DEPTH_SLOTS + pathLength];
+	const uint32_t n_paths = pathLength == 0 ? sh.local_pixels : wf.counters[sample_in_frame * MAX_DEPTH_SLOTS + pathLength - 1].ext;
+	const FrameParams fp = *wf.frame;
+	const uint32_t samplesTaken = fp.sample_base + sample_in_frame;
+	const uint32_t buf = pathLength & 1u, nbuf = buf ^ 1u;
+	const uint32_t lane = threadIdx.x & 31u;
+	uint32_t acc_count = 0;
+	for (;;)
+	{
+		uint32_t base = 0;
+		if (lane == 0)
+			base = atomicAdd(&curc->shade_cursor, 32u);
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (base >= n_paths)
+			break;
+		const uint32_t job = base + lane;
+
+		bool do_acc = false, do_shadow = false, do_ext = false;
+		V3 accv = mk(0.f);
+		uint32_t pathIndex = 0;
+		float4 eO, eD, eT, cO, cD, cE;
+		eO = eD = eT = cO = cD = cE = make_float4(0.f, 0.f, 0.f, 0.f);
+
+		if (job < n_paths)
+		{
+			const float4 hitData = wf.hit[job];
+			const int primIdx = __float_as_int(hitData.z);
+			if (primIdx != PRIM_DEAD)
+			{
+				const float4 O4 = wf.O[buf][job];
+				const float4 D4 = wf.D[buf][job];
+				const float4 T4 = pathLength == 0 ? make_float4(1.f, 1.f, 1.f, 1.f) : wf.T[buf][job];
+				uint32_t flags = __float_as_uint(O4.w) & 0xFFu;
+				V3 throughput = mk(T4.x, T4.y, T4.z);
+				const float bsdfPdf = T4.w;
+				const V3 D = mk(D4.x, D4.y, D4.z);
+				pathIndex = __float_as_uint(O4.w) >> 8; // local pixel index
+				if (primIdx == PRIM_MISS)
+				{
+					// Kernels.cu:593-610
+					const uint32_t u = __float2uint_rz(float(sc.sky_w) * 0.5f * (1.0f + atan2f(D.x, -D.z) * INVPI));
+					const uint32_t v = __float2uint_rz(float(sc.sky_h) * acosf(D.y) * INVPI);
+					const uint32_t idx = u + v * sc.sky_w;
+					V3 sky = mk(0.f);
+					if (idx < sc.sky_h * sc.sky_w)
+					{
+						const float4 s4 = __ldg(reinterpret_cast<const float4 *>(sc.sky) + idx);
+						sky = mk(s4.x, s4.y, s4.z);
+					}
+					V3 contribution = throughput * (1.0f / bsdfPdf) * sky;
+					if (!any_nan(contribution))
+					{
+						clampIntensity(contribution, rs.clamp_value);
+						do_acc = true, accv = contribution;
+					}
+				}
+				else
+				{
+					const V3 O = mk(O4.x, O4.y, O4.z);
+					const V3 I = O + D * hitData.w;
+					const uint32_t ub = __float_as_uint(hitData.x);
+					const uint32_t shadeIdx = __float_as_uint(hitData.y);
+					ShadeTri tri;
+					{
+						const float4 *tp = reinterpret_cast<const float4 *>(sc.shade_tris + shadeIdx);
+						float4 *dst = reinterpret_cast<float4 *>(&tri);
+#pragma unroll
+						for (int k = 0; k < 6; k++)
+							dst[k] = __ldg(tp + k);
+					}
+					const float bu = float(ub & 65535u) * (1.0f / 65535.0f), bv = float((ub >> 16) & 65535u) * (1.0f / 65535.0f);
+					V3 N, iN, T, B;
+					const ShadingData sd = getShadingData(sc, D, bu, bv, fp.spread_angle * hitData.w, tri, N, iN, T, B);
+
+					if (pathLength == 0)
+					{
+						uint32_t px, py;
+						local_to_pixel(sh, pathIndex, px, py);
+						if (py * sh.width + px == fp.probe_pixel) // Kernels.cu:626-631
+						{
+							wf.probe->inst = int(tri.inst_id), wf.probe->prim = int(tri.prim_id), wf.probe->dist = hitData.w;
+						}
+					}
+
+					if (sd.flags & 1u)
+					{
+						// alpha cut-out: continue through the surface (Kernels.cu:634-647; throughput plane per
+						// VulkanRTX/shaders/rt_shade.comp:155)
+						if (int(pathLength) < rs.max_path_length && !any_nan(throughput))
+						{
+							do_ext = true;
+							const V3 no = I + D * rs.geometry_epsilon;
+							eO = make_float4(no.x, no.y, no.z, O4.w);
+							eD = D4;
+							eT = T4;
+						}
+					}
+					else if (sd.isEmissive())
+					{
+						// Kernels.cu:650-692
+						const float DdotNL = -dot(D, N);
+						V3 contribution = mk(0.f);
+						bool skip = false;
+						if (DdotNL > 0)
+						{
+							if (pathLength == 0)
+								contribution = sd.color;
+							else if (flags & IS_SPECULAR)
+								contribution = throughput * sd.color * (1.0f / bsdfPdf);
+							else
+							{
+								const V3 lastN = UnpackNormal(__float_as_uint(D4.w));
+								const float lightPdf = (hitData.w * hitData.w) / (-dot(D, N) * tri.area); // lights.h:78-81
+								const float pickProb = LightPickProb(sc, tri.light_tri_idx, O, lastN, I);
+								if ((bsdfPdf + lightPdf * pickProb) <= 0)
+									skip = true;
+								else
+									contribution = throughput * sd.color * (1.0f / (bsdfPdf + lightPdf * pickProb));
+							}
+						}
+						if (!skip)
+						{
+							if (any_nan(contribution))
+								contribution = mk(0.f);
+							clampIntensity(contribution, rs.clamp_value);
+							do_acc = true, accv = contribution;
+						}
+					}
+					else
+					{
+						if (sd.roughness() < MIN_ROUGHNESS)
+							flags |= IS_SPECULAR;
+						else
+							flags &= ~IS_SPECULAR;
+						uint32_t gx, gy;
+						local_to_pixel(sh, pathIndex, gx, gy);
+						const uint32_t globalPixel = gy * sh.width + gx;
+						uint32_t seed = WangHash(globalPixel * 16789u + samplesTaken * 1791u + pathLength * 720898027u);
+						const float flip = (dot(D, N) > 0) ? -1.0f : 1.0f;
+						N = N * flip;
+						iN = iN * flip;
+						throughput = throughput * (1.0f / bsdfPdf);
+						const uint32_t nlights = sc.lights.area + sc.lights.point + sc.lights.spot + sc.lights.directional;
+						// shadow rays emitted at the last depth are never traced by the reference's host loop
+						// (CUDART/src/Context.cpp:109-120); skipping them is exact, except that the seed must
+						// advance identically when samplesTaken >= 256
+						const bool nee = (flags & IS_SPECULAR) == 0 && nlights > 0;
+						if (nee)
+						{
+							float r0, r1;
+							if (samplesTaken < 256)
+							{
+								r0 = blueNoiseSampler(sc.blue_noise, int(gx), int(gy), int(samplesTaken), 4);
+								r1 = blueNoiseSampler(sc.blue_noise, int(gx), int(gy), int(samplesTaken), 5);
+							}
+							else
+							{
+								r0 = RandomFloat(seed);
+								r1 = RandomFloat(seed);
+							}
+							if (int(pathLength) < rs.max_path_length)
+							{
+								V3 lightColor = mk(0.f);
+								float pickProb = 0, lightPdf = 0;
+								V3 L = RandomPointOnLight(sc, r0, r1, I, iN, pickProb, lightPdf, lightColor) - I;
+								const float dist = length(L);
+								L = L * (1.0f / dist);
+								const float NdotL = dot(L, iN);
+								if (NdotL > 0 && lightPdf > 0)
+								{
+									const V3 wo = D * -1.0f;
+									const V3 sampledBSDF = BSDFEval(sd, iN, wo, L, 0.0f, false);
+									const float shadowPdf = BSDFPdf(sd, iN, wo, L);
+									if (shadowPdf > 0)
+									{
+										V3 contribution = throughput * sampledBSDF * lightColor * (NdotL / (shadowPdf + lightPdf * pickProb));
+										clampIntensity(contribution, rs.clamp_value);
+										if (!any_nan(contribution))
+										{
+											do_shadow = true;
+											const V3 so = I + N * 1e-5f; // SafeOrigin, tools.h:119-123
+											cO = make_float4(so.x, so.y, so.z, 0.f);
+											cD = make_float4(L.x, L.y, L.z, dist - 2.0f * rs.geometry_epsilon);
+											cE = make_float4(contribution.x, contribution.y, contribution.z, __uint_as_float(pathIndex));
+										}
+									}
+								}
+							}
+						}
+						if (int(pathLength) < rs.max_path_length)
+						{
+							V3 R = mk(0.f);
+							float newBsdfPdf = 0.0f;
+							const V3 wo = D * -1.0f;
+							const float r3 = RandomFloat(seed);
+							const float r4 = RandomFloat(seed);
+							BSDFSample(sd, T, B, iN, wo, R, newBsdfPdf, r3, r4);
+							const V3 bsdf = BSDFEval(sd, iN, wo, R, hitData.w, flip < 0);
+							if (rs.survival_scale) // Kernels.cu:783
+								throughput = throughput * 1.0f / SurvivalProbability(throughput) * bsdf * fabsf(dot(iN, R));
+							else
+								throughput = throughput * bsdf * fabsf(dot(iN, R));
+							if (!(newBsdfPdf < 1e-6f || isnan(newBsdfPdf) || throughput.x < 0.0f || throughput.y < 0.0f ||
+								  throughput.z < 0.0f))
+							{
+								do_ext = true;
+								const V3 so = I + N * 1e-5f;
+								eO = make_float4(so.x, so.y, so.z, __uint_as_float((pathIndex << 8) | flags));
+								eD = make_float4(R.x, R.y, R.z, __uint_as_float(PackNormal(iN)));
+								eT = make_float4(throughput.x, throughput.y, throughput.z, newBsdfPdf);
+							}
+						}
+					}
+				}
+			}
+		}
+
+		// ---- converged commit: warp-aggregated compaction --------------------------------------
+		if (do_acc)
+		{
+			float4 a = wf.accumulator[pathIndex];
+			a.x += accv.x, a.y += accv.y, a.z += accv.z;
+			wf.accumulator[pathIndex] = a;
+			acc_count++;
+		}
+		const uint32_t lt_mask = (1u << lane) - 1u;
+		const uint32_t m_sh = __ballot_sync(0xffffffffu, do_shadow);
+		if (m_sh)
+		{
+			uint32_t sbase = 0;
+			if (lane == 0)
+				sbase = atomicAdd(&curc->shadow, __popc(m_sh));
+			sbase = __shfl_sync(0xffffffffu, sbase, 0);
+			if (do_shadow)
+			{
+				const uint32_t slot = sbase + __popc(m_sh & lt_mask);
+				wf.sO[slot] = cO, wf.sD[slot] = cD, wf.sE[slot] = cE;
+			}
+		}
+		const uint32_t m_ex = __ballot_sync(0xffffffffu, do_ext);
+		if (m_ex)
+		{
+			uint32_t ebase = 0;
+			if (lane == 0)
+				ebase = atomicAdd(&curc->ext, __popc(m_ex));
+			ebase = __shfl_sync(0xffffffffu, ebase, 0);
+			if (do_ext)
+			{
+				const uint32_t slot = ebase + __popc(m_ex & lt_mask);
+				wf.O[nbuf][slot] = eO, wf.D[nbuf][slot] = eD, wf.T[nbuf][slot] = eT;
+			}
+		}
+	}
+	acc_count = __reduce_add_sync(0xffffffffu, acc_count);
+	if (lane == 0 && acc_count)
+		atomicAdd(&curc->acc, acc_count);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_finalize — Kernels.cu:181-203: framebuffer = accumulator * 1/samples.  world == 1 writes the
+// row-major image; world > 1 keeps the tile-major shard for the gather.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_finalize(const ShardView sh, const WavefrontView wf, const float scale)
+{
+	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= sh.local_pixels)
+		return;
+	float4 a = wf.accumulator[j];
+	a.x *= scale, a.y *= scale, a.z *= scale, a.w *= scale;
+	if (sh.world == 1)
+	{
+		uint32_t x, y;
+		if (local_to_pixel(sh, j, x, y))
+			wf.framebuffer[size_t(y) * sh.width + x] = a;
+	}
+	else
+		wf.framebuffer[j] = a;
+}
+
+__global__ void k_assemble(const ShardView sh, const float4 *__restrict__ gathered, const size_t stride,
+						   float4 *__restrict__ image)
+{
+	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t r = blockIdx.y;
+	ShardView s = sh;
+	s.rank = r;
+	const uint32_t total_tiles = s.tiles_x * s.tiles_y;
+	const uint32_t ltiles = (total_tiles > r) ? (total_tiles - r + s.world - 1) / s.world : 0;
+	if (j >= ltiles * s.tile_w * s.tile_h)
+		return;
+	uint32_t x, y;
+	if (local_to_pixel(s, j, x, y))
+		image[size_t(y) * s.width + x] = gathered[size_t(r) * stride + j];
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_emode — EmbreeRT/src/Context.cpp:104-300 + retrieve_material :417-476, one thread per pixel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_emode(const SceneView sc, const ShardView sh, const WavefrontView wf,
+											  const RenderSettings rs, const rfwb200_material *__restrict__ raw_materials,
+											  const uint32_t *__restrict__ tex_desc, const uint32_t tex_count)
+{
+	__shared__ uint64_t mbar;
+	float4 *snodes = reinterpret_cast<float4 *>(g_dyn_smem);
+	const uint32_t n_smem = min(uint32_t(rs.smem_nodes), sc.node_count);
+	stage_nodes(snodes, sc.nodes, n_smem, &mbar);
+	const FrameParams fp = *wf.frame;
+	uint32_t *cursor = &wf.counters[0].trace_cursor;
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t total = sh.local_pixels;
+	// only whole 4x2 tiles are rendered by the reference (Context.cpp:137-139)
+	const uint32_t wlim = (sh.width / 4u) * 4u, hlim = (sh.height / 2u) * 2u;
+	for (;;)
+	{
+		uint32_t base = 0;
+		if (lane == 0)
+			base = atomicAdd(cursor, 32u);
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (base >= total)
+			break;
+		const uint32_t j = base + lane;
+		uint32_t x, y;
+		if (j >= total || !local_to_pixel(sh, j, x, y))
+			continue;
+		float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+		if (x < wlim && y < hlim)
+		{
+			V3 O, D;
+			generate_emode(fp, sh, x, y, fp.sample_base, O, D);
+			float t = 1e34f, u = 0.f, v = 0.f;
+			uint32_t triIdx = 0;
+			if (!traverse<false>(sc, snodes, n_smem, O, D, 1e-5f, t, triIdx, u, v))
+			{
+				const float su = 0.5f * (1.0f + atan2f(D.x, -D.z) * INVPI);
+				const float sv = acosf(D.y) * INVPI;
+				const uint32_t px = __float2uint_rz(su * float(sc.sky_w - 1)), py = __float2uint_rz(sv * float(sc.sky_h - 1));
+				const size_t si = size_t(py) * sc.sky_w + px;
+				if (si < size_t(sc.sky_w) * sc.sky_h)
+				{
+					const float4 s4 = __ldg(reinterpret_cast<const float4 *>(sc.sky) + si);
+					out = make_float4(s4.x, s4.y, s4.z, 0.f);
+				}
+			}
+			else
+			{
+				ShadeTri tri;
+				{
+					const float4 *tp = reinterpret_cast<const float4 *>(sc.shade_tris + triIdx);
+					float4 *dst = reinterpret_cast<float4 *>(&tri);
+#pragma unroll
+					for (int k = 0; k < 6; k++)
+						dst[k] = __ldg(tp + k);
+				}
+				if (y * sh.width + x == fp.probe_pixel)
+					wf.probe->inst = int(tri.inst_id), wf.probe->prim = int(tri.prim_id), wf.probe->dist = t;
+				const float b0 = 1.0f - u - v;
+				const V3 p = O + D * t;
+				const V3 iN = normalize(mk(tri.n0x, tri.n0y, tri.n0z) * b0 + mk(tri.n1x, tri.n1y, tri.n1z) * u + mk(tri.n2x, tri.n2y, tri.n2z) * v);
+				const rfwb200_material *mat = raw_materials + tri.material;
+				const uint4 basew = __ldg(reinterpret_cast<const uint4 *>(mat));
+				const uint32_t flags = basew.w;
+				V3 color = mk(__half2float(__ushort_as_half((unsigned short)(basew.x & 0xffffu))),
+							  __half2float(__ushort_as_half((unsigned short)(basew.x >> 16))),
+							  __half2float(__ushort_as_half((unsigned short)(basew.y & 0xffffu))));
+				if (has_flag(flags, HasDiffuseMap))
+				{
+					const MapDesc m = load_map(&mat->tex0);
+					if (m.addr < tex_count)
+					{
+						const float tu = b0 * tri.u0 + u * tri.u1 + v * tri.u2;
+						const float tv = b0 * tri.v0 + u * tri.v1 + v * tri.v2;
+						const float uu = (tu + m.uo) * m.us, vv2 = (tv + m.vo) * m.vs;
+						float tx = fmodf(uu, 1.0f), ty = fmodf(vv2, 1.0f);
+						if (tx < 0.f)
+							tx = 1.f + tx;
+						if (ty < 0.f)
+							ty = 1.f + ty;
+						const uint32_t ttype = tex_desc[m.addr * 4 + 0], tw = tex_desc[m.addr * 4 + 1], th = tex_desc[m.addr * 4 + 2],
+									   taddr = tex_desc[m.addr * 4 + 3];
+						const uint32_t ix = __float2uint_rz(tx * float(tw - 1)), iy = __float2uint_rz(ty * float(th - 1));
+						const uint32_t id = iy * tw + ix;
+						constexpr float tsc = 1.0f / 256.0f;
+						if (ttype == RFWB200_TEX_UINT)
+						{
+							const uint32_t tc = __ldg(sc.uint_texels + taddr + id);
+							color = color * tsc * mk(float(tc & 0xFFu), float((tc >> 8) & 0xFFu), float((tc >> 16) & 0xFFu));
+						}
+						else
+						{
+							// FLOAT4 falls through into the UINT case in the reference (Context.cpp:458-472)
+							const float4 tf = __ldg(reinterpret_cast<const float4 *>(sc.float_texels) + taddr + id);
+							color = color * mk(tf.x, tf.y, tf.z);
+							const uint32_t tc = __float_as_uint(tf.x);
+							color = color * tsc * mk(float(tc & 0xFFu), float((tc >> 8) & 0xFFu), float((tc >> 16) & 0xFFu));
+						}
+					}
+				}
+				if (color.x > 1 || color.y > 1 || color.z > 1)
+					out = make_float4(color.x, color.y, color.z, 1.0f);
+				else
+				{
+					V3 contrib = mk(0.1f);
+					for (uint32_t li = 0; li < sc.lights.area; li++)
+					{
+						const float4 *lp = reinterpret_cast<const float4 *>(sc.area_lights) + size_t(li) * 6;
+						const float4 la = __ldg(lp), lb = __ldg(lp + 1), lc = __ldg(lp + 2);
+						V3 L = mk(la.x, la.y, la.z) - p;
+						const float sq_dist = dot(L, L);
+						const float dist = sqrtf(sq_dist);
+						L = L / dist;
+						const float NdotL = dot(iN, L);
+						const float LNdotL = -dot(mk(lb.x, lb.y, lb.z), L);
+						if (NdotL <= 0 || LNdotL <= 0)
+							continue;
+						float tmax = dist * (1.0f - 1e-4f), uu, vv2;
+						uint32_t tt;
+						if (!traverse<true>(sc, snodes, n_smem, p, L, 1e-4f, tmax, tt, uu, vv2))
+							contrib = contrib + mk(lc.x, lc.y, lc.z) * lb.w / sq_dist * NdotL * LNdotL;
+					}
+					for (uint32_t li = 0; li < sc.lights.point; li++)
+					{
+						const float4 *lp = reinterpret_cast<const float4 *>(sc.point_lights) + size_t(li) * 2;
+						const float4 la = __ldg(lp), lb = __ldg(lp + 1);
+						V3 L = mk(la.x, la.y, la.z) - p;
+						const float sq_dist = dot(L, L);
+						const float dist = sqrtf(sq_dist);
+						L = L / dist;
+						const float NdotL = dot(iN, L);
+						if (NdotL <= 0)
+							continue;
+						float tmax = dist * (1.0f - 1e-4f), uu, vv2;
+						uint32_t tt;
+						if (!traverse<true>(sc, snodes, n_smem, p, L, 1e-4f, tmax, tt, uu, vv2))
+							contrib = contrib + mk(lb.x, lb.y, lb.z) / sq_dist * NdotL;
+					}
+					const V3 c = color * contrib;
+					out = make_float4(c.x, c.y, c.z, 1.0f);
+				}
+			}
+		}
+		if (sh.world == 1)
+			wf.framebuffer[size_t(y) * sh.width + x] = out;
+		else
+			wf.framebuffer[j] = out;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage-level kernels on caller rays
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_trace_closest(const SceneView sc, const RenderSettings rs,
+													  const float4 *__restrict__ origins, const float4 *__restrict__ dirs,
+													  const uint32_t n, const float t_min, float4 *__restrict__ hits,
+													  uint32_t *cursor)
+{
+	__shared__ uint64_t mbar;
+	float4 *snodes = reinterpret_cast<float4 *>(g_dyn_smem);
+	const uint32_t n_smem = min(uint32_t(rs.smem_nodes), sc.node_count);
+	stage_nodes(snodes, sc.nodes, n_smem, &mbar);
+	const uint32_t lane = threadIdx.x & 31u;
+	for (;;)
+	{
+		uint32_t base = 0;
+		if (lane == 0)
+			base = atomicAdd(cursor, 32u);
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (base >= n)
+			break;
+		const uint32_t i = base + lane;
+		if (i >= n)
+			continue;
+		const float4 O4 = origins[i], D4 = dirs[i];
+		float t = 1e34f, u = 0.f, v = 0.f;
+		uint32_t tri = 0xffffffffu;
+		const bool h = traverse<false>(sc, snodes, n_smem, mk(O4.x, O4.y, O4.z), mk(D4.x, D4.y, D4.z), t_min, t, tri, u, v);
+		hits[i] = make_float4(h ? t : 1e34f, u, v, __uint_as_float(h ? tri : 0xffffffffu));
+	}
+}
+
+__global__ void __launch_bounds__(256) k_trace_occluded(const SceneView sc, const RenderSettings rs,
+													   const float4 *__restrict__ origins,
+													   const float4 *__restrict__ dirs_tmax, const uint32_t n,
+													   const float t_min, uint8_t *__restrict__ occluded, uint32_t *cursor)
+{
+	__shared__ uint64_t mbar;
+	float4 *snodes = reinterpret_cast<float4 *>(g_dyn_smem);
+	const uint32_t n_smem = min(uint32_t(rs.smem_nodes), sc.node_count);
+	stage_nodes(snodes, sc.nodes, n_smem, &mbar);
+	const uint32_t lane = threadIdx.x & 31u;
+	for (;;)
+	{
+		uint32_t base = 0;
+		if (lane == 0)
+			base = atomicAdd(cursor, 32u);
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (base >= n)
+			break;
+		const uint32_t i = base + lane;
+		if (i >= n)
+			continue;
+		const float4 O4 = origins[i], D4 = dirs_tmax[i];
+		float tmax = D4.w, u, v;
+		uint32_t tri;
+		occluded[i] = traverse<true>(sc, snodes, n_smem, mk(O4.x, O4.y, O4.z), mk(D4.x, D4.y, D4.z), t_min, tmax, tri, u, v) ? 1 : 0;
+	}
+}
+
+__global__ void k_generate_only(const SceneView sc, const ShardView sh, const WavefrontView wf, const uint32_t sample_index,
+								const int emode, float4 *__restrict__ origins, float4 *__restrict__ dirs)
+{
+	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= sh.local_pixels)
+		return;
+	uint32_t x, y;
+	if (!local_to_pixel(sh, j, x, y))
+		return;
+	const FrameParams fp = *wf.frame;
+	V3 O, D;
+	if (emode)
+		generate_emode(fp, sh, x, y, sample_index, O, D);
+	else
+		generate_pt(sc, fp, sh, x, y, sample_index, O, D);
+	const uint32_t pixel = y * sh.width + x;
+	origins[pixel] = make_float4(O.x, O.y, O.z, __uint_as_float((pixel << 8) + 1u));
+	dirs[pixel] = make_float4(D.x, D.y, D.z, 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+cudaError_t configure_launches(const RenderSettings &rs, uint32_t node_count, LaunchDims &dims)
+{
+	int dev = 0, sms = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess)
+		return e;
+	e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	if (e != cudaSuccess)
+		return e;
+	const uint32_t staged = rs.smem_nodes > 0 ? (uint32_t(rs.smem_nodes) < node_count ? uint32_t(rs.smem_nodes) : node_count) : 0u;
+	dims.trace_smem = size_t(staged) * sizeof(BvhNode4);
+	const void *trace_kernels[] = {(const void *)k_primary, (const void *)k_trace, (const void *)k_emode,
+								   (const void *)k_trace_closest, (const void *)k_trace_occluded};
+	for (const void *k : trace_kernels)
+	{
+		e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dims.trace_smem));
+		if (e != cudaSuccess)
+			return e;
+	}
+	int per_sm = 0;
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace, dims.trace_block, dims.trace_smem);
+	if (e != cudaSuccess)
+		return e;
+	if (per_sm < 1)
+		per_sm = 1;
+	dims.trace_grid = sms * per_sm; // a whole number of CTAs per SM: no partial wave
+	int shade_per_sm = 0;
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shade_per_sm, k_shade, dims.shade_block, 0);
+	if (e != cudaSuccess)
+		return e;
+	if (shade_per_sm < 1)
+		shade_per_sm = 1;
+	dims.shade_grid = sms * shade_per_sm;
+	return cudaSuccess;
+}
+
+cudaError_t launch_primary(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
+						   uint32_t sample_in_frame, const LaunchDims &dims, cudaStream_t stream)
+{
+	k_primary<<<dims.trace_grid, dims.trace_block, dims.trace_smem, stream>>>(sc, sh, wf, rs, sample_in_frame);
+	return cudaGetLastError();
+}
+cudaError_t launch_shade(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
+						 uint32_t sample_in_frame, uint32_t depth, const LaunchDims &dims, cudaStream_t stream)
+{
+	k_shade<<<dims.shade_grid, dims.shade_block, 0, stream>>>(sc, sh, wf, rs, sample_in_frame, depth);
+	return cudaGetLastError();
+}
+cudaError_t launch_trace(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
+						 uint32_t sample_in_frame, uint32_t depth, const LaunchDims &dims, cudaStream_t stream)
+{
+	k_trace<<<dims.trace_grid, dims.trace_block, dims.trace_smem, stream>>>(sc, sh, wf, rs, sample_in_frame, depth);
+	return cudaGetLastError();
+}
+cudaError_t launch_finalize(const ShardView &sh, const WavefrontView &wf, float scale, cudaStream_t stream)
+{
+	const uint32_t n = sh.local_pixels;
+	k_finalize<<<(n + 255) / 256, 256, 0, stream>>>(sh, wf, scale);
+	return cudaGetLastError();
+}
+cudaError_t launch_emode(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
+						 const void *raw_materials, const uint32_t *tex_desc, uint32_t tex_count, const LaunchDims &dims,
+						 cudaStream_t stream)
+{
+	k_emode<<<dims.trace_grid, dims.trace_block, dims.trace_smem, stream>>>(
+		sc, sh, wf, rs, reinterpret_cast<const rfwb200_material *>(raw_materials), tex_desc, tex_count);
+	return cudaGetLastError();
+}
+cudaError_t launch_trace_closest(const SceneView &sc, const RenderSettings &rs, const float4 *origins, const float4 *directions,
+								 uint32_t n, float t_min, float4 *hits_out, uint32_t *cursor, const LaunchDims &dims,
+								 cudaStream_t stream)
+{
+	k_trace_closest<<<dims.trace_grid, dims.trace_block, dims.trace_smem, stream>>>(sc, rs, origins, directions, n, t_min,
+																				   hits_out, cursor);
+	return cudaGetLastError();
+}
+cudaError_t launch_trace_occluded(const SceneView &sc, const RenderSettings &rs, const float4 *origins,
+								  const float4 *directions_tmax, uint32_t n, float t_min, uint8_t *occluded_out,
+								  uint32_t *cursor, const LaunchDims &dims, cudaStream_t stream)
+{
+	k_trace_occluded<<<dims.trace_grid, dims.trace_block, dims.trace_smem, stream>>>(sc, rs, origins, directions_tmax, n,
+																					t_min, occluded_out, cursor);
+	return cudaGetLastError();
+}
+cudaError_t launch_generate_only(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, uint32_t sample_index,
+								 int emode, float4 *origins_out, float4 *directions_out, cudaStream_t stream)
+{
+	const uint32_t n = sh.local_pixels;
+	k_generate_only<<<(n + 255) / 256, 256, 0, stream>>>(sc, sh, wf, sample_index, emode, origins_out, directions_out);
+	return cudaGetLastError();
+}
+cudaError_t launch_assemble(const ShardView &sh, const float4 *gathered, size_t stride, float4 *image, cudaStream_t stream)
+{
+	const uint32_t total_tiles = sh.tiles_x * sh.tiles_y;
+	const uint32_t max_local = ((total_tiles + sh.world - 1) / sh.world) * sh.tile_w * sh.tile_h;
+	dim3 grid((max_local + 255) / 256, sh.world);
+	k_assemble<<<grid, 256, 0, stream>>>(sh, gathered, stride, image);
+	return cudaGetLastError();
+}
+
+} // namespace rfwb200

@@ -1,0 +1,35 @@
+import sys
+from pathlib import Path
+
+import pytest
+
+REPO = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(REPO / "rendering-fw_b200" / "python"))
+sys.path.insert(0, str(REPO))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def built():
+    """Build the product library and the oracle once per session (no-op when up to date)."""
+    import __graft_entry__ as g
+
+    g.build()
+    return True
+
+
+@pytest.fixture(scope="session")
+def oracle_lib(built):
+    import rfwb200 as R
+
+    return R.load_oracle()
+
+
+@pytest.fixture(scope="session")
+def product_lib(built):
+    import rfwb200 as R
+
+    return R.load_product()

@@ -1,0 +1,293 @@
+"""GPU parity tests: the CUDA path (through the C ABI, librfwb200.so) against the CPU oracle on identical
+seeded inputs.  Run on the B200 box with `pytest -m gpu`.
+
+Tolerances (written here once, used below):
+  * integer / index work (pixel mapping, queue counts at depth 0, probe ids, hit ids away from edges): exact;
+  * hit distance: |dt| <= 1e-4 * max(1, t)  (fp32 Moller-Trumbore in world space vs the oracle's object-space
+    two-level evaluation);
+  * images: per channel |d| <= 2e-3 * (1 + |ref|); E-mode on >= 99.9 % of pixels, PT-mode on >= 99.5 % of
+    pixels per sample (fp32 transcendentals differ between CUDA libm and glibc, and a hit that flips at a
+    geometric edge changes the whole path).
+"""
+import numpy as np
+import pytest
+
+import rfwb200 as R
+import scenes as S
+
+pytestmark = pytest.mark.gpu
+
+IMG_TOL = 2e-3
+
+
+def make_pair(product_lib, oracle_lib, scene_fn, W, H, **settings):
+    out = []
+    for lib in (product_lib, oracle_lib):
+        sc = scene_fn()
+        ctx = R.RenderContext(lib)
+        S.upload(ctx, sc, W, H)
+        for k, v in settings.items():
+            ctx.set_setting(k, v)
+        out.append((ctx, sc))
+    return out
+
+
+def frac_bad(a, b, tol=IMG_TOL):
+    err = np.abs(a - b) / (1.0 + np.abs(b))
+    return float((err.max(axis=-1) > tol).mean())
+
+
+def unit_cornell():
+    return S.cornell_box(unit_scale=True)
+
+
+SCENES = {"cornell": unit_cornell, "soup": S.feature_soup}
+
+
+# ---- generate ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["pt", "embree"])
+@pytest.mark.parametrize("sample", [0, 3, 300])
+def test_generate_parity(product_lib, oracle_lib, mode, sample):
+    (g, sc), (o, _) = make_pair(product_lib, oracle_lib, unit_cornell, 96, 64, mode=mode)
+    cam = sc.camera(96, 64)
+    go, gd = g.generate_primary(cam, sample)
+    oo, od = o.generate_primary(cam, sample)
+    # the path-index word is integer work: exact
+    assert np.array_equal(go[:, 3].view(np.uint32), oo[:, 3].view(np.uint32))
+    assert np.allclose(go[:, :3], oo[:, :3], rtol=0, atol=1e-6)
+    assert np.allclose(gd[:, :3], od[:, :3], rtol=0, atol=2e-6)
+    assert np.allclose(np.linalg.norm(gd[:, :3], axis=1), 1.0, atol=1e-5)
+
+
+# ---- extend --------------------------------------------------------------------------------------
+def _check_hits(g, o, origins, dirs, hits_g, hits_o):
+    same = (hits_g["inst_id"] == hits_o["inst_id"]) & (hits_g["prim_id"] == hits_o["prim_id"])
+    hit = hits_o["prim_id"] >= 0
+    ok_t = np.abs(hits_g["t"] - hits_o["t"]) <= 1e-4 * np.maximum(1.0, np.abs(hits_o["t"]))
+    assert ok_t[same & hit].all()
+    assert np.abs(hits_g["u"] - hits_o["u"])[same & hit].max() < 1e-3
+    assert np.abs(hits_g["v"] - hits_o["v"])[same & hit].max() < 1e-3
+    # every disagreement must be a tie: the GPU's triangle, evaluated by the oracle, is as close as the
+    # oracle's own closest hit (shared edges, coplanar duplicates) — or a det-epsilon / edge-on case
+    diff = np.nonzero(~same)[0]
+    assert len(diff) <= max(4, 2e-3 * len(origins)), f"{len(diff)} of {len(origins)} rays disagree"
+    for i in diff:
+        if hits_g["prim_id"][i] >= 0 and hits_o["prim_id"][i] >= 0:
+            t_alt = o.intersect_prim(origins[i, :3], dirs[i, :3], int(hits_g["inst_id"][i]), int(hits_g["prim_id"][i]))
+            assert abs(t_alt - hits_o["t"][i]) <= 2e-4 * max(1.0, hits_o["t"][i]) or t_alt > 1e33
+    return len(diff)
+
+
+@pytest.mark.parametrize("scene", ["cornell", "soup"])
+def test_extend_primary_parity(product_lib, oracle_lib, scene):
+    W, H = 160, 120
+    (g, sc), (o, _) = make_pair(product_lib, oracle_lib, SCENES[scene], W, H)
+    origins, dirs = o.generate_primary(sc.camera(W, H), 0)
+    hg, ho = g.trace_closest(origins, dirs), o.trace_closest(origins, dirs)
+    assert (ho["prim_id"] >= 0).mean() > 0.3
+    _check_hits(g, o, origins, dirs, hg, ho)
+
+
+def test_extend_random_rays_and_occlusion(product_lib, oracle_lib):
+    (g, sc), (o, _) = make_pair(product_lib, oracle_lib, S.feature_soup, 32, 32)
+    rng = np.random.default_rng(5)
+    n = 20000
+    origins = np.zeros((n, 4), np.float32)
+    origins[:, :3] = rng.uniform(-2.5, 2.5, size=(n, 3))
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    dirs = np.zeros((n, 4), np.float32)
+    dirs[:, :3] = d
+    dirs[: n // 50, 0] = 0.0  # axis-parallel components (1/0 in the slab test)
+    dirs[n // 50: n // 25, 1] = 0.0
+    nrm = np.linalg.norm(dirs[:, :3], axis=1, keepdims=True)
+    dirs[:, :3] /= np.maximum(nrm, 1e-20)
+    hg, ho = g.trace_closest(origins, dirs), o.trace_closest(origins, dirs)
+    _check_hits(g, o, origins, dirs, hg, ho)
+    # connect: any hit in (eps, tmax); pick tmax on both sides of the closest hit
+    tmax = np.where(ho["prim_id"] >= 0, ho["t"] * rng.choice([0.5, 0.999, 1.5, 3.0], size=n), 10.0).astype(np.float32)
+    og, oo = g.trace_occluded(origins, dirs, tmax), o.trace_occluded(origins, dirs, tmax)
+    assert (og != oo).mean() < 1e-3
+    assert 0.05 < oo.mean() < 0.95
+
+
+def test_empty_and_degenerate_scenes(product_lib, oracle_lib):
+    # no geometry at all: every ray misses, the image is the sky
+    def empty():
+        s = S.Scene(name="empty")
+        S.add_material(s, (0.5, 0.5, 0.5))
+        s.sky = (np.full((1, 3), 0.25, np.float32), 1, 1)
+        return s
+
+    (g, sc), (o, _) = make_pair(product_lib, oracle_lib, empty, 64, 40, spp=2)
+    cam = sc.camera(64, 40)
+    g.render_frame(cam, R.RESET), o.render_frame(cam, R.RESET)
+    a, b = g.read_image(), o.read_image()
+    assert np.allclose(a, b, atol=1e-6) and np.allclose(a[..., :3], 0.25, atol=1e-6)
+
+    # a single degenerate (zero-area) triangle plus one real one
+    def degenerate():
+        s = S.Scene(name="degenerate")
+        m = S.add_material(s, (0.5, 0.5, 0.5))
+        pos = np.array([[[0, 0, 2], [0, 0, 2], [0, 0, 2]], [[-1, -1, 3], [1, -1, 3], [0, 1, 3]]], np.float32)
+        tri = S.make_triangles(pos, None, None, m)
+        v = np.concatenate([pos.reshape(-1, 3), np.ones((6, 1), np.float32)], 1)
+        s.meshes = [S.SceneMesh(v, tri, None)]
+        s.instances = [(0, np.eye(4))]
+        return s
+
+    (g, sc), (o, _) = make_pair(product_lib, oracle_lib, degenerate, 64, 64)
+    origins, dirs = o.generate_primary(sc.camera(64, 64), 0)
+    hg, ho = g.trace_closest(origins, dirs), o.trace_closest(origins, dirs)
+    assert (ho["prim_id"] == 1).sum() > 100 and np.array_equal(hg["prim_id"], ho["prim_id"])
+
+
+# ---- E-mode image ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("scene", ["cornell", "soup"])
+def test_emode_image_parity(product_lib, oracle_lib, scene):
+    W, H = 256, 192
+    (g, sc), (o, _) = make_pair(product_lib, oracle_lib, SCENES[scene], W, H, mode="embree")
+    cam = sc.camera(W, H)
+    g.set_probe_index(W // 2, H // 2), o.set_probe_index(W // 2, H // 2)
+    g.render_frame(cam, R.RESET), o.render_frame(cam, R.RESET)
+    a, b = g.read_image(), o.read_image()
+    assert np.isfinite(a).all()
+    assert frac_bad(a, b) < 1e-3 if scene == "cornell" else frac_bad(a, b) < 5e-3
+    pg, po = g.get_probe_results(), o.get_probe_results()
+    assert pg[:2] == po[:2] and abs(pg[2] - po[2]) <= 1e-4 * max(1.0, po[2])
+
+
+def test_config1_cornell_512_emode(product_lib, oracle_lib):
+    """BASELINE.json configs[0]: Cornell box 512x512 1 spp, the Embree image model."""
+    W = H = 512
+    (g, sc), (o, _) = make_pair(product_lib, oracle_lib, unit_cornell, W, H, mode="embree")
+    cam = sc.camera(W, H)
+    g.render_frame(cam, R.RESET), o.render_frame(cam, R.RESET)
+    a, b = g.read_image(), o.read_image()
+    assert frac_bad(a, b) < 1e-3
+    assert abs(a[..., :3].mean() - b[..., :3].mean()) < 1e-4
+
+
+# ---- PT-mode image, stage by stage ---------------------------------------------------------------------
+@pytest.mark.parametrize("scene", ["cornell", "soup"])
+@pytest.mark.parametrize("depth", [0, 1, 2])
+def test_pt_image_parity_per_depth(product_lib, oracle_lib, scene, depth):
+    """max_path_length = 0 isolates generate+extend+shade(0); 1 adds connect, compaction and one bounce;
+    2 is the reference's configuration (settings.h:5)."""
+    W, H = 192, 128
+    (g, sc), (o, _) = make_pair(product_lib, oracle_lib, SCENES[scene], W, H, max_path_length=depth, spp=1)
+    cam = sc.camera(W, H)
+    g.render_frame(cam, R.RESET), o.render_frame(cam, R.RESET)
+    a, b = g.read_image(), o.read_image()
+    assert np.isfinite(a).all()
+    limit = {0: 2e-3, 1: 5e-3, 2: 8e-3}[depth] * (1 if scene == "cornell" else 3)
+    assert frac_bad(a, b) < limit, (frac_bad(a, b), limit)
+    cg, co = g.get_frame_counters().as_dict(), o.get_frame_counters().as_dict()
+    assert cg["n_gen"] == co["n_gen"] and cg["pixels"] == co["pixels"]
+    for k in ("n_ext", "n_shade", "n_ext_out", "n_nee", "n_acc"):
+        assert abs(cg[k] - co[k]) <= 2e-3 * max(co[k], 1) + 2, (k, cg[k], co[k])
+
+
+def test_pt_multi_sample_accumulation_and_converge(product_lib, oracle_lib):
+    W, H = 128, 96
+    (g, sc), (o, _) = make_pair(product_lib, oracle_lib, unit_cornell, W, H, spp=4)
+    cam = sc.camera(W, H)
+    g.render_frame(cam, R.RESET), o.render_frame(cam, R.RESET)
+    a4, b4 = g.read_image().copy(), o.read_image().copy()
+    assert frac_bad(a4, b4) < 2e-2  # 4 samples: any flipped path of any sample marks the pixel
+    assert abs(a4[..., :3].mean() - b4[..., :3].mean()) < 2e-3 * b4[..., :3].mean() + 1e-4
+    # Reset + 1 spp, then three Converge calls of 1 spp == one Reset call of 4 spp (same sample indices)
+    g.set_setting("spp", 1)
+    g.render_frame(cam, R.RESET)
+    for _ in range(3):
+        g.render_frame(cam, R.CONVERGE)
+    c4 = g.read_image()
+    assert np.allclose(a4, c4, rtol=1e-6, atol=1e-7)
+
+
+def test_pt_sample_index_beyond_blue_noise(product_lib, oracle_lib):
+    """samples >= 256 switch NEE randoms from blue noise to the xorshift stream (Kernels.cu:713-724)."""
+    W, H = 96, 64
+    (g, sc), (o, _) = make_pair(product_lib, oracle_lib, unit_cornell, W, H, spp=258, max_path_length=1)
+    cam = sc.camera(W, H)
+    g.render_frame(cam, R.RESET), o.render_frame(cam, R.RESET)
+    a, b = g.read_image(), o.read_image()
+    assert np.abs(a[..., :3] - b[..., :3]).mean() < 2e-3 * b[..., :3].mean()
+
+
+def test_probe_and_stats(product_lib, oracle_lib):
+    W, H = 128, 128
+    (g, sc), (o, _) = make_pair(product_lib, oracle_lib, unit_cornell, W, H)
+    cam = sc.camera(W, H)
+    for px, py in ((64, 100), (20, 64), (64, 40)):
+        g.set_probe_index(px, py), o.set_probe_index(px, py)
+        g.render_frame(cam, R.RESET), o.render_frame(cam, R.RESET)
+        pg, po = g.get_probe_results(), o.get_probe_results()
+        assert pg[:2] == po[:2], (pg, po)
+        assert abs(pg[2] - po[2]) <= 1e-4 * max(1.0, po[2])
+    st = g.get_stats()
+    assert st.primary_count == W * H and st.render_time > 0
+
+
+# ---- refit ------------------------------------------------------------------------------------------------
+def test_set_mesh_refit_matches_rebuild(product_lib, oracle_lib):
+    W, H = 128, 96
+    (g, sc), (o, _) = make_pair(product_lib, oracle_lib, S.feature_soup, W, H)
+    cam = sc.camera(W, H)
+    # move the vertices of mesh 1 (same counts => refit on the product side)
+    m = sc.meshes[1]
+    rng = np.random.default_rng(3)
+    v2 = m.vertices.copy()
+    v2[:, :3] += rng.normal(0, 0.05, size=v2[:, :3].shape).astype(np.float32)
+    pos = v2[:, :3].reshape(-1, 3, 3) if m.indices is None else v2[m.indices][:, :, :3]
+    tri2 = m.triangles.copy()
+    tri2["vertex0"], tri2["vertex1"], tri2["vertex2"] = pos[:, 0], pos[:, 1], pos[:, 2]
+    for ctx in (g, o):
+        ctx.set_mesh(1, v2, tri2, m.indices)
+        ctx.update()
+    origins, dirs = o.generate_primary(cam, 0)
+    hg, ho = g.trace_closest(origins, dirs), o.trace_closest(origins, dirs)
+    _check_hits(g, o, origins, dirs, hg, ho)
+
+
+# ---- sharding ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_tile_sharded_frame_is_bit_identical(product_lib, world):
+    """config 5's partitioning: every rank renders its tiles with global pixel ids for the seeds, so the
+    assembled image equals the single-GPU image bit for bit."""
+    W, H = 200, 100  # not a multiple of the tile size: exercises padded edge tiles
+    sc = unit_cornell()
+    full = R.RenderContext(product_lib)
+    S.upload(full, sc, W, H)
+    full.set_setting("spp", 2)
+    cam = sc.camera(W, H)
+    full.render_frame(cam, R.RESET)
+    ref = full.read_image().copy()
+    shards = []
+    for r in range(world):
+        ctx = R.RenderContext(product_lib)
+        ctx.set_shard(r, world, 32, 8)
+        S.upload(ctx, unit_cornell(), W, H)
+        ctx.set_setting("spp", 2)
+        ctx.render_frame(cam, R.RESET)
+        shards.append(ctx.read_framebuffer().copy())
+        ctx.close()
+    img = R.assemble_shards_host(shards, W, H, 32, 8)
+    assert np.array_equal(img, ref)
+
+
+# ---- error behaviour ----------------------------------------------------------------------------------------
+def test_error_codes(product_lib):
+    ctx = R.RenderContext(product_lib)
+    with pytest.raises(R.Rfwb200Error):
+        ctx.render_frame(S.cornell_box().camera(8, 8), R.RESET)  # before init
+    ctx.init(64, 64)
+    with pytest.raises(R.Rfwb200Error):
+        ctx.render_frame(S.cornell_box().camera(64, 64), R.RESET)  # before update
+    with pytest.raises(R.Rfwb200Error):
+        ctx.set_setting("no_such_key", 1)
+    with pytest.raises(R.Rfwb200Error):
+        ctx.set_instance(0, 5, np.eye(4))  # unknown mesh
+    with pytest.raises(R.Rfwb200Error):
+        ctx.set_shard(3, 2)
+    assert "mesh" in product_lib.last_error() or "rank" in product_lib.last_error()
