@@ -8,6 +8,7 @@
 #include <condition_variable>
 #include <cstring>
 #include <deque>
+#include <limits>
 #include <mutex>
 #include <thread>
 
@@ -277,11 +278,16 @@ inline void set_child_box(BvhNode4 &n, int slot, const Box &b)
 	n.minx[slot] = b.lo[0], n.miny[slot] = b.lo[1], n.minz[slot] = b.lo[2];
 	n.maxx[slot] = b.hi[0], n.maxy[slot] = b.hi[1], n.maxz[slot] = b.hi[2];
 }
+// An unused slot must never be entered: min/max slab arithmetic turns an inverted box into a valid
+// one (the reference relies on count == 0 for that, mbvh_node.cpp:207-212), so the box is NaN — every
+// comparison in the hit test is false — and the child word is a harmless 1-triangle leaf reference.
+// pad[0] of the node holds the number of used slots.
 inline void set_child_empty(BvhNode4 &n, int slot)
 {
-	n.minx[slot] = n.miny[slot] = n.minz[slot] = 3.0e38f;
-	n.maxx[slot] = n.maxy[slot] = n.maxz[slot] = -3.0e38f;
-	n.child[slot] = 0x7fffffff;
+	const float q = std::numeric_limits<float>::quiet_NaN();
+	n.minx[slot] = n.miny[slot] = n.minz[slot] = q;
+	n.maxx[slot] = n.maxy[slot] = n.maxz[slot] = q;
+	n.child[slot] = -1;
 }
 inline Box child_box(const BvhNode4 &n, int slot)
 {
@@ -412,6 +418,7 @@ void build_bvh4(const BuildTriangle *tris, size_t count, int threads, BvhBuildRe
 				max_depth = std::max(max_depth, depth4[head] + 1);
 			}
 		}
+		node.pad[0] = nk;
 		out.nodes.push_back(node);
 		out.node_parent.push_back(p.parent);
 	}
@@ -427,11 +434,9 @@ void refit_bvh4(const BuildTriangle *tris, size_t count, BvhBuildResult &bvh)
 	for (size_t ni = bvh.nodes.size(); ni-- > 0;)
 	{
 		BvhNode4 &n = bvh.nodes[ni];
-		for (int s = 0; s < 4; s++)
+		for (int s = 0; s < n.pad[0]; s++)
 		{
 			const int32_t c = n.child[s];
-			if (c == 0x7fffffff)
-				continue;
 			Box b;
 			b.reset();
 			if (c < 0)
@@ -443,9 +448,8 @@ void refit_bvh4(const BuildTriangle *tris, size_t count, BvhBuildResult &bvh)
 			else
 			{
 				const BvhNode4 &ch = bvh.nodes[c];
-				for (int k = 0; k < 4; k++)
-					if (ch.child[k] != 0x7fffffff)
-						b.grow(child_box(ch, k));
+				for (int k = 0; k < ch.pad[0]; k++)
+					b.grow(child_box(ch, k));
 			}
 			set_child_box(n, s, b);
 		}

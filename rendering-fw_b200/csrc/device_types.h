@@ -10,7 +10,8 @@ namespace rfwb200
 // 4-wide BVH node, 128 B = one L2 line.  SoA child boxes like the reference's MBVHNode
 // (RFW/system/bvh/include/bvh/mbvh_node.h:60-106) so one slab test is four independent FMAs per
 // plane, but with a single signed child word: >= 0 inner-node index, < 0 leaf with
-// ~child = (first_triangle << 2) | (count - 1).  Unused slots carry an inverted box (never hit).
+// ~child = (first_triangle << 2) | (count - 1).  Unused slots carry a NaN box (every comparison of the
+// hit test is false); pad[0] is the number of used slots.
 // Nodes are stored breadth-first, so the top of the tree is one contiguous prefix that a CTA can
 // stage into shared memory with a single bulk (TMA) copy.
 struct alignas(16) BvhNode4
