@@ -242,7 +242,8 @@ RFWB200_API int rfwb200_update(rfwb200_context *ctx);
 /* replaces RenderContext::set_setting (context.h:107). Keys: "spp" (samples per render_frame,
  * default 1), "mode" ("pt" wavefront path tracer | "embree" = image model of the EmbreeRT
  * backend), "max_path_length" (default 2 = settings.h:5), "clamp" (default 10, camera.h:36),
- * "smem_nodes" (BVH nodes staged in shared memory per CTA). */
+ * "smem_nodes" (BVH nodes staged in shared memory per CTA), "timing" (on|off: per-stage CUDA-event
+ * times in get_stats), "survival_scale" (on|off, the 1/p throughput scale of Kernels.cu:783). */
 RFWB200_API int rfwb200_set_setting(rfwb200_context *ctx, const char *key, const char *value);
 /* replaces RenderContext::get_settings (context.h:106): writes a '\n'-separated "key=v1|v2" list */
 RFWB200_API int rfwb200_get_settings(const rfwb200_context *ctx, char *buf, size_t buf_size);

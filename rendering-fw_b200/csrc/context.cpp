@@ -159,6 +159,15 @@ struct rfwb200_context
 	rfwb200_render_stats stats{};
 	cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
 	bool frame_in_flight = false;
+	// optional per-stage timing (setting "timing"): events bracket every launch of the last frame
+	bool timing = false;
+	struct StageEvent
+	{
+		int category; // 0 primary, 1 secondary (trace depth 1), 2 deep (trace depth >= 2), 3 shade, 4 finalize
+		cudaEvent_t a, b;
+	};
+	std::vector<StageEvent> stage_events;
+	size_t stage_events_used = 0;
 	std::vector<DepthCounters> host_counters;
 };
 
@@ -354,6 +363,34 @@ int ensure_dims(Ctx *c)
 	return RFWB200_OK;
 }
 
+// brackets one launch with events when per-stage timing is on
+struct StageTimer
+{
+	Ctx *c;
+	cudaEvent_t b = nullptr;
+	StageTimer(Ctx *ctx, int category) : c(ctx)
+	{
+		if (!c->timing)
+			return;
+		if (c->stage_events_used == c->stage_events.size())
+		{
+			Ctx::StageEvent e{category, nullptr, nullptr};
+			if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess)
+				return;
+			c->stage_events.push_back(e);
+		}
+		Ctx::StageEvent &e = c->stage_events[c->stage_events_used++];
+		e.category = category;
+		cudaEventRecord(e.a, c->stream);
+		b = e.b;
+	}
+	~StageTimer()
+	{
+		if (b)
+			cudaEventRecord(b, c->stream);
+	}
+};
+
 int check_ready(Ctx *c)
 {
 	if (!c->initialised)
@@ -424,6 +461,8 @@ extern "C"
 			cudaEventDestroy(c->ev_begin);
 		if (c->ev_end)
 			cudaEventDestroy(c->ev_end);
+		for (auto &e : c->stage_events)
+			cudaEventDestroy(e.a), cudaEventDestroy(e.b);
 		delete c;
 		return RFWB200_OK;
 	}
@@ -705,6 +744,8 @@ extern "C"
 			c->rs.smem_nodes = n;
 			c->dims_valid = false;
 		}
+		else if (k == "timing")
+			c->timing = (v == "on" || v == "1");
 		else if (k == "threads")
 		{
 		}
@@ -751,28 +792,45 @@ extern "C"
 		if (int r = upload_frame_params(c, view, c->sample_index))
 			return r;
 		c->last_first_sample = c->sample_index;
+		c->stage_events_used = 0;
 		if (c->mode_pt)
 		{
 			const uint32_t maxd = uint32_t(c->rs.max_path_length);
 			for (uint32_t s = 0; s < spp; s++)
 			{
-				CK(launch_primary(c->scene, c->shard, c->wf, c->rs, s, c->dims, st));
-				CK(launch_shade(c->scene, c->shard, c->wf, c->rs, s, 0, c->dims, st));
+				{
+					StageTimer t(c, 0);
+					CK(launch_primary(c->scene, c->shard, c->wf, c->rs, s, c->dims, st));
+				}
+				{
+					StageTimer t(c, 3);
+					CK(launch_shade(c->scene, c->shard, c->wf, c->rs, s, 0, c->dims, st));
+				}
 				c->launches += 2;
 				for (uint32_t d = 1; d <= maxd; d++)
 				{
-					CK(launch_trace(c->scene, c->shard, c->wf, c->rs, s, d, c->dims, st));
-					CK(launch_shade(c->scene, c->shard, c->wf, c->rs, s, d, c->dims, st));
+					{
+						StageTimer t(c, d == 1 ? 1 : 2);
+						CK(launch_trace(c->scene, c->shard, c->wf, c->rs, s, d, c->dims, st));
+					}
+					{
+						StageTimer t(c, 3);
+						CK(launch_shade(c->scene, c->shard, c->wf, c->rs, s, d, c->dims, st));
+					}
 					c->launches += 2;
 				}
 			}
 			c->sample_index += spp;
-			CK(launch_finalize(c->shard, c->wf, 1.0f / float(c->sample_index), st)); // blit_buffer, Kernels.cu:181-203
+			{
+				StageTimer t(c, 4);
+				CK(launch_finalize(c->shard, c->wf, 1.0f / float(c->sample_index), st)); // blit_buffer, Kernels.cu:181-203
+			}
 			c->launches += 1;
 		}
 		else
 		{
 			// EmbreeRT renders one un-accumulated sample per call (Context.cpp:104-300)
+			StageTimer t(c, 0);
 			CK(launch_emode(c->scene, c->shard, c->wf, c->rs, c->d_materials_raw.ptr, c->d_tex_desc.as<uint32_t>(),
 							uint32_t(c->textures.size()), c->dims, st));
 			c->launches += 1;
@@ -921,6 +979,24 @@ extern "C"
 		float ms = 0;
 		CK(cudaEventElapsedTime(&ms, c->ev_begin, c->ev_end));
 		out->render_time = ms;
+		// per-stage device times of the last frame (reference fields, context.h:50-72). Connect rays are
+		// traced inside the same launch as the extension rays of their bounce, so shadow_time stays 0 and
+		// their cost is part of secondary_time / deep_time.
+		for (size_t i = 0; i < c->stage_events_used; i++)
+		{
+			const Ctx::StageEvent &e = c->stage_events[i];
+			float t = 0;
+			if (cudaEventElapsedTime(&t, e.a, e.b) != cudaSuccess)
+				continue;
+			switch (e.category)
+			{
+			case 0: out->primary_time += t; break;
+			case 1: out->secondary_time += t; break;
+			case 2: out->deep_time += t; break;
+			case 3: out->shade_time += t; break;
+			default: out->finalize_time += t; break;
+			}
+		}
 		rfwb200_frame_counters fc;
 		if (int r = rfwb200_get_frame_counters(c, &fc))
 			return r;
