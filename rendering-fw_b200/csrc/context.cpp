@@ -147,7 +147,7 @@ struct rfwb200_context
 	uint32_t counters_capacity_spp = 0;
 
 	// ---- settings / state ------------------------------------------------------------------------------
-	RenderSettings rs{2, 10.0f, 1e-5f, 1, 256};
+	RenderSettings rs{2, 10.0f, 1e-5f, 1, 0, 16}; // smem_nodes 0: measured fastest on B200 (DESIGN.md "staging")
 	int spp = 1;
 	bool mode_pt = true;
 	LaunchDims dims{};
@@ -743,6 +743,12 @@ extern "C"
 			REQUIRE(n >= 0 && n <= 1700, "smem_nodes must be in [0, 1700] (227 KB of shared memory)");
 			c->rs.smem_nodes = n;
 			c->dims_valid = false;
+		}
+		else if (k == "fetch_threshold")
+		{
+			const int n = atoi(v.c_str());
+			REQUIRE(n >= 1 && n <= 32, "fetch_threshold must be in [1, 32]");
+			c->rs.fetch_threshold = n;
 		}
 		else if (k == "timing")
 			c->timing = (v == "on" || v == "1");

@@ -139,6 +139,7 @@ struct RenderSettings
 	float geometry_epsilon;
 	int survival_scale;
 	int smem_nodes;
+	int fetch_threshold; // idle lanes per warp that trigger a refill from the work cursor
 };
 
 } // namespace rfwb200

@@ -1,11 +1,11 @@
 // kernels.cu — sm_100a wavefront path-tracing kernels.
 //
 // Stage map (reference semantics in parentheses; paths relative to /root/reference/RFW):
-//   k_primary   generate + extend for camera rays  (backends/CUDART/src/Kernels.cu:383-460)
+//   k_wavefront_trace<true>   generate + extend for camera rays (backends/CUDART/src/Kernels.cu:383-460)
 //   k_shade     material eval + NEE + BSDF sample + compaction (Kernels.cu:571-794,
 //               CUDART/src/getShadingData.h, CUDART/src/lights.h, system/context/rfw/bsdf/*.h)
-//   k_trace     extend (closest hit) for extension rays and connect (any hit) for shadow rays of
-//               one bounce in ONE persistent launch (Kernels.cu:461-498, CUDAIntersect.h)
+//   k_wavefront_trace<false>  extend (closest hit) for extension rays and connect (any hit) for shadow
+//               rays of one bounce in ONE persistent launch (Kernels.cu:461-498, CUDAIntersect.h)
 //   k_finalize  accumulator / samples (Kernels.cu:181-203)
 //   k_emode     the image model of backends/EmbreeRT/src/Context.cpp:104-300 as one fused kernel
 //
@@ -184,20 +184,14 @@ struct NodeRegs
 __device__ __forceinline__ NodeRegs load_node(const SceneView &sc, const float4 *__restrict__ snodes, uint32_t n_smem,
 											  uint32_t idx)
 {
+	// One generic 128-bit load path for both homes of a node (staged shared-memory prefix or global):
+	// selecting the pointer instead of branching keeps the lanes of a warp together — a branch here split
+	// every warp into a shared-memory half and a global half that executed one after the other
+	// (profiles/r01: 11 + 11 of 32 threads on the two load sequences).
+	const float4 *p = idx < n_smem ? snodes + size_t(idx) * 8 : reinterpret_cast<const float4 *>(sc.nodes) + size_t(idx) * 8;
 	NodeRegs n;
-	if (idx < n_smem)
-	{
-		const float4 *p = snodes + size_t(idx) * 8;
-		n.minx = p[0], n.maxx = p[1], n.miny = p[2], n.maxy = p[3], n.minz = p[4], n.maxz = p[5];
-		n.child = *reinterpret_cast<const int4 *>(p + 6);
-	}
-	else
-	{
-		const float4 *p = reinterpret_cast<const float4 *>(sc.nodes) + size_t(idx) * 8;
-		n.minx = __ldg(p + 0), n.maxx = __ldg(p + 1), n.miny = __ldg(p + 2), n.maxy = __ldg(p + 3);
-		n.minz = __ldg(p + 4), n.maxz = __ldg(p + 5);
-		n.child = __ldg(reinterpret_cast<const int4 *>(p + 6));
-	}
+	n.minx = p[0], n.maxx = p[1], n.miny = p[2], n.maxy = p[3], n.minz = p[4], n.maxz = p[5];
+	n.child = *reinterpret_cast<const int4 *>(p + 6);
 	return n;
 }
 
@@ -370,129 +364,266 @@ __device__ __forceinline__ void generate_emode(const FrameParams &fp, const Shar
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_primary — generate + extend for every local pixel of one sample
+// k_wavefront_trace — the persistent-threads traversal kernel of both trace stages.
+//
+//   PRIMARY = true : work item = local pixel; generate the camera ray (Kernels.cu:383-426), closest hit
+//   PRIMARY = false: work items [0, n_ext) = extension rays (closest hit, Kernels.cu:461-483),
+//                    [n_ext, n_ext + n_shadow) = connect rays (any hit + accumulate, Kernels.cu:484-498)
+//
+// Every lane owns one ray at a time.  "While-while" traversal: all lanes descend inner nodes until
+// each holds a leaf, then the leaves are intersected together; a lane whose ray is finished stays idle
+// only until at least rs.fetch_threshold lanes of its warp are idle, then the idle lanes pull new work
+// items from the device cursor with ONE atomic for the warp.  This keeps SIMD lanes busy when rays of
+// very different cost (incoherent bounces, early-out shadow rays) share a warp — the first version
+// with one ray per lane per 32-ray chunk ran at 9-12 of 32 active threads per instruction
+// (profiles/r01).
 // ------------------------------------------------------------------------------------------------
+
 extern __shared__ __align__(128) unsigned char g_dyn_smem[];
 
-__global__ void __launch_bounds__(256) k_primary(const SceneView sc, const ShardView sh, const WavefrontView wf,
-												const RenderSettings rs, const uint32_t sample_in_frame)
+template <bool PRIMARY>
+__global__ void __launch_bounds__(256) k_wavefront_trace(const SceneView sc, const ShardView sh, const WavefrontView wf,
+															const RenderSettings rs, const uint32_t sample_in_frame,
+															const uint32_t depth)
 {
 	__shared__ uint64_t mbar;
 	float4 *snodes = reinterpret_cast<float4 *>(g_dyn_smem);
 	const uint32_t n_smem = min(uint32_t(rs.smem_nodes), sc.node_count);
 	stage_nodes(snodes, sc.nodes, n_smem, &mbar);
 
-	const FrameParams fp = *wf.frame;
-	const uint32_t sampleIndex = fp.sample_base + sample_in_frame;
-	uint32_t *cursor = &wf.counters[sample_in_frame * MAX_DEPTH_SLOTS + 0].trace_cursor;
-	const uint32_t lane = threadIdx.x & 31u;
-	const uint32_t total = sh.local_pixels;
-	for (;;)
-	{
-		uint32_t base = 0;
-		if (lane == 0)
-			base = atomicAdd(cursor, 32u);
-		base = __shfl_sync(0xffffffffu, base, 0);
-		if (base >= total)
-			break;
-		const uint32_t j = base + lane;
-		if (j >= total)
-			continue;
-		uint32_t x, y;
-		float4 hit = make_float4(0.f, 0.f, __int_as_float(PRIM_DEAD), 0.f);
-		if (local_to_pixel(sh, j, x, y))
-		{
-			V3 O, D;
-			generate_pt(sc, fp, sh, x, y, sampleIndex, O, D);
-			wf.O[0][j] = make_float4(O.x, O.y, O.z, __uint_as_float((j << 8) + 1u));
-			wf.D[0][j] = make_float4(D.x, D.y, D.z, 0.0f);
-			float t = 1e34f, u = 0.f, v = 0.f;
-			uint32_t tri = 0;
-			hit = make_float4(0.f, 0.f, __int_as_float(PRIM_MISS), 0.f);
-			if (traverse<false>(sc, snodes, n_smem, O, D, 1e-5f, t, tri, u, v))
-				hit = make_float4(__uint_as_float(uint32_t(65535.0f * u) | (uint32_t(65535.0f * v) << 16)),
-								  __uint_as_float(tri), __int_as_float(0), t);
-		}
-		wf.hit[j] = hit;
-	}
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_trace — one bounce: closest hit for the extension queue, any hit for the connect queue
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_trace(const SceneView sc, const ShardView sh, const WavefrontView wf,
-											  const RenderSettings rs, const uint32_t sample_in_frame,
-											  const uint32_t depth)
-{
-	__shared__ uint64_t mbar;
-	float4 *snodes = reinterpret_cast<float4 *>(g_dyn_smem);
-	const uint32_t n_smem = min(uint32_t(rs.smem_nodes), sc.node_count);
-	stage_nodes(snodes, sc.nodes, n_smem, &mbar);
-
-	DepthCounters *prev = &wf.counters[sample_in_frame * MAX_DEPTH_SLOTS + depth - 1];
 	DepthCounters *curc = &wf.counters[sample_in_frame * MAX_DEPTH_SLOTS + depth];
-	const uint32_t n_ext = prev->ext;
-	// the reference only traces the connect queue when the bounce loop continues, i.e. when at least
-	// one extension ray exists (CUDART/src/Context.cpp:109-120)
-	const uint32_t n_shadow = n_ext > 0 ? prev->shadow : 0u;
-	const uint32_t ext_pad = (n_ext + 31u) & ~31u;
-	const uint32_t total = ext_pad + n_shadow;
+	uint32_t n_ext, n_shadow;
+	if (PRIMARY)
+		n_ext = sh.local_pixels, n_shadow = 0;
+	else
+	{
+		const DepthCounters *prev = &wf.counters[sample_in_frame * MAX_DEPTH_SLOTS + depth - 1];
+		n_ext = prev->ext;
+		// the reference only traces the connect queue when the bounce loop continues, i.e. when at least
+		// one extension ray exists (CUDART/src/Context.cpp:109-120)
+		n_shadow = n_ext > 0 ? prev->shadow : 0u;
+	}
+	const uint32_t total = n_ext + n_shadow;
 	const uint32_t buf = depth & 1u;
 	const float4 *__restrict__ Oin = wf.O[buf];
 	const float4 *__restrict__ Din = wf.D[buf];
+	const float4 *__restrict__ tris = reinterpret_cast<const float4 *>(sc.tris);
 	uint32_t *cursor = &curc->trace_cursor;
 	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t lt_mask = (1u << lane) - 1u;
+	FrameParams fp;
+	uint32_t sampleIndex = 0;
+	if (PRIMARY)
+	{
+		fp = *wf.frame;
+		sampleIndex = fp.sample_base + sample_in_frame;
+	}
+
+	// per-lane ray state
+	bool alive = false;
+	bool shadow = false;
+	uint32_t item = 0;
+	V3 o = mk(0.f), d = mk(0.f);
+	float idx = 0.f, idy = 0.f, idz = 0.f, oodx = 0.f, oody = 0.f, oodz = 0.f;
+	float tmin = 0.f, tmax = 0.f, hit_u = 0.f, hit_v = 0.f;
+	uint32_t hit_tri = 0xffffffffu;
+	int stack[TRAVERSAL_STACK];
+	constexpr int SENTINEL = 0x7fffffff; // bottom-of-stack marker: popping it ends the ray
+	constexpr int NO_LEAF = 0;			 // leaf references are negative, so 0 can mean "none postponed"
+	int sp = 0, cur = SENTINEL, leaf = NO_LEAF;
+	bool exhausted = false; // warp-uniform: the queue has no more items
 	uint32_t acc_count = 0;
+
 	for (;;)
 	{
-		uint32_t base = 0;
-		if (lane == 0)
-			base = atomicAdd(cursor, 32u);
-		base = __shfl_sync(0xffffffffu, base, 0);
-		if (base >= total)
+		// ---- refill idle lanes ---------------------------------------------------------------------------
+		const uint32_t idle_mask = __ballot_sync(0xffffffffu, !alive);
+		if (idle_mask == 0xffffffffu && exhausted)
 			break;
-		const uint32_t i = base + lane;
-		if (base < ext_pad)
+		const int n_idle = __popc(idle_mask);
+		if (!exhausted && (n_idle >= rs.fetch_threshold))
 		{
-			if (i < n_ext)
+			uint32_t base = 0;
+			if (lane == 0)
+				base = atomicAdd(cursor, uint32_t(n_idle));
+			base = __shfl_sync(0xffffffffu, base, 0);
+			if (base + uint32_t(n_idle) >= total)
+				exhausted = true;
+			if (!alive)
 			{
-				const float4 O4 = Oin[i], D4 = Din[i];
-				float t = 1e34f, u = 0.f, v = 0.f;
-				uint32_t tri = 0;
-				float4 hit = make_float4(0.f, 0.f, __int_as_float(PRIM_MISS), 0.f);
-				if (traverse<false>(sc, snodes, n_smem, mk(O4.x, O4.y, O4.z), mk(D4.x, D4.y, D4.z), 1e-5f, t, tri, u, v))
-					hit = make_float4(__uint_as_float(uint32_t(65535.0f * u) + (uint32_t(65535.0f * v) << 16)),
-									  __uint_as_float(tri), __int_as_float(0), t);
-				wf.hit[i] = hit;
-			}
-		}
-		else
-		{
-			const uint32_t k = i - ext_pad;
-			if (k < n_shadow)
-			{
-				const float4 O4 = wf.sO[k], D4 = wf.sD[k];
-				float tmax = D4.w, u, v;
-				uint32_t tri;
-				if (!traverse<true>(sc, snodes, n_smem, mk(O4.x, O4.y, O4.z), mk(D4.x, D4.y, D4.z), rs.geometry_epsilon, tmax,
-									tri, u, v))
+				item = base + __popc(idle_mask & lt_mask);
+				if (item < total)
 				{
-					const float4 E = wf.sE[k];
-					const uint32_t pixel = __float_as_uint(E.w);
-					float4 a = wf.accumulator[pixel];
-					a.x += E.x, a.y += E.y, a.z += E.z, a.w += 1.0f;
-					wf.accumulator[pixel] = a;
-					acc_count++;
+					bool valid = true;
+					if (PRIMARY)
+					{
+						uint32_t x, y;
+						if (local_to_pixel(sh, item, x, y))
+						{
+							generate_pt(sc, fp, sh, x, y, sampleIndex, o, d);
+							wf.O[0][item] = make_float4(o.x, o.y, o.z, __uint_as_float((item << 8) + 1u));
+							wf.D[0][item] = make_float4(d.x, d.y, d.z, 0.0f);
+							tmin = 1e-5f, tmax = 1e34f, shadow = false;
+						}
+						else
+						{
+							wf.hit[item] = make_float4(0.f, 0.f, __int_as_float(PRIM_DEAD), 0.f);
+							valid = false;
+						}
+					}
+					else if (item < n_ext)
+					{
+						const float4 O4 = Oin[item], D4 = Din[item];
+						o = mk(O4.x, O4.y, O4.z), d = mk(D4.x, D4.y, D4.z);
+						tmin = 1e-5f, tmax = 1e34f, shadow = false;
+					}
+					else
+					{
+						const uint32_t k = item - n_ext;
+						const float4 O4 = wf.sO[k], D4 = wf.sD[k];
+						o = mk(O4.x, O4.y, O4.z), d = mk(D4.x, D4.y, D4.z);
+						tmin = rs.geometry_epsilon, tmax = D4.w, shadow = true;
+					}
+					if (valid)
+					{
+						const float tiny = 1e-30f;
+						idx = 1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));
+						idy = 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));
+						idz = 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
+						oodx = o.x * idx, oody = o.y * idy, oodz = o.z * idz;
+						stack[0] = SENTINEL;
+						sp = 1, cur = 0, leaf = NO_LEAF, hit_tri = 0xffffffffu, hit_u = 0.f, hit_v = 0.f;
+						alive = true;
+					}
 				}
 			}
 		}
+
+		// ---- traverse (Aila/Laine "while-while" with a postponed leaf, adapted to 4-wide nodes) ------------------------
+		bool finished = false;
+		if (alive)
+		{
+			while (cur != SENTINEL || leaf != NO_LEAF)
+			{
+				// descend inner nodes; the first leaf a lane meets is postponed and the lane keeps descending
+				// (speculatively) so it stays useful until every lane of the warp holds a leaf
+				while (uint32_t(cur) < uint32_t(SENTINEL))
+				{
+					const NodeRegs n = load_node(sc, snodes, n_smem, uint32_t(cur));
+					float key0, key1, key2, key3;
+					int nh = 0;
+					CHILD_T(0, x)
+					CHILD_T(1, y)
+					CHILD_T(2, z)
+					CHILD_T(3, w)
+					if (nh == 0)
+						cur = stack[--sp];
+					else
+					{
+						CSWAP(key0, key1)
+						CSWAP(key2, key3)
+						CSWAP(key0, key2)
+						CSWAP(key1, key3)
+						CSWAP(key1, key2)
+						cur = PICK(key0);
+						if (nh > 1)
+						{
+							if (nh > 3)
+								stack[sp++] = PICK(key3);
+							if (nh > 2)
+								stack[sp++] = PICK(key2);
+							stack[sp++] = PICK(key1);
+						}
+					}
+					if (cur < 0 && leaf == NO_LEAF)
+					{
+						leaf = cur;
+						cur = stack[--sp];
+					}
+					if (!__any_sync(__activemask(), leaf == NO_LEAF))
+						break;
+				}
+				// intersect the postponed leaf (and any leaf that directly follows it on the stack)
+				while (leaf != NO_LEAF)
+				{
+					const uint32_t v = uint32_t(~leaf), first = v >> 2, cnt = (v & 3u) + 1u;
+					for (uint32_t i = 0; i < cnt; i++)
+					{
+						const float4 a = __ldg(tris + size_t(first + i) * 3 + 0);
+						const float4 b = __ldg(tris + size_t(first + i) * 3 + 1);
+						const float4 c = __ldg(tris + size_t(first + i) * 3 + 2);
+						const V3 p0 = mk(a.x, a.y, a.z), e1 = mk(a.w, b.x, b.y), e2 = mk(b.z, b.w, c.x);
+						const V3 h = cross(d, e2);
+						const float det = dot(e1, h);
+						const float eps = c.z;
+						if (det > -eps && det < eps)
+							continue;
+						const float f = 1.0f / det;
+						const V3 s = o - p0;
+						const float u = f * dot(s, h);
+						if (u < 0.0f || u > 1.0f)
+							continue;
+						const V3 q = cross(s, e1);
+						const float vv = f * dot(d, q);
+						if (vv < 0.0f || u + vv > 1.0f)
+							continue;
+						const float t = f * dot(e2, q);
+						if (t > tmin && tmax > t)
+						{
+							tmax = t, hit_u = u, hit_v = vv, hit_tri = __float_as_uint(c.y);
+							if (shadow)
+							{
+								cur = SENTINEL; // any hit ends a connect ray
+								break;
+							}
+						}
+					}
+					leaf = NO_LEAF;
+					if (cur < 0)
+					{
+						leaf = cur;
+						cur = stack[--sp];
+					}
+				}
+				// too few lanes left in this loop: leave it so the idle lanes can fetch new rays
+				if (__popc(__activemask()) <= 32 - rs.fetch_threshold)
+					break;
+			}
+			finished = (cur == SENTINEL && leaf == NO_LEAF);
+		}
+		// ---- retire --------------------------------------------------------------------------------------------------
+		if (alive && finished)
+		{
+			alive = false;
+			if (!shadow)
+			{
+				float4 hit = make_float4(0.f, 0.f, __int_as_float(PRIM_MISS), 0.f);
+				if (hit_tri != 0xffffffffu)
+					hit = make_float4(__uint_as_float(uint32_t(65535.0f * hit_u) | (uint32_t(65535.0f * hit_v) << 16)),
+									  __uint_as_float(hit_tri), __int_as_float(0), tmax);
+				wf.hit[item] = hit;
+			}
+			else if (hit_tri == 0xffffffffu)
+			{
+				// unoccluded: accumulator[pixel] += (contribution, 1)  (Kernels.cu:495-497)
+				const float4 E = wf.sE[item - n_ext];
+				const uint32_t pixel = __float_as_uint(E.w);
+				float4 a = wf.accumulator[pixel];
+				a.x += E.x, a.y += E.y, a.z += E.z, a.w += 1.0f;
+				wf.accumulator[pixel] = a;
+				acc_count++;
+			}
+		}
 	}
-	// bookkeeping for the algorithmic-bytes formula: one atomic per warp
-	acc_count = __reduce_add_sync(0xffffffffu, acc_count);
-	if (lane == 0 && acc_count)
-		atomicAdd(&curc->acc, acc_count);
-	if (blockIdx.x == 0 && threadIdx.x == 0)
-		curc->shadow_traced = n_shadow;
+	if (!PRIMARY)
+	{
+		// bookkeeping for the algorithmic-bytes formula: one atomic per warp
+		acc_count = __reduce_add_sync(0xffffffffu, acc_count);
+		if (lane == 0 && acc_count)
+			atomicAdd(&curc->acc, acc_count);
+		if (blockIdx.x == 0 && threadIdx.x == 0)
+			curc->shadow_traced = n_shadow;
+	}
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1661,7 +1792,7 @@ cudaError_t configure_launches(const RenderSettings &rs, uint32_t node_count, La
 		return e;
 	const uint32_t staged = rs.smem_nodes > 0 ? (uint32_t(rs.smem_nodes) < node_count ? uint32_t(rs.smem_nodes) : node_count) : 0u;
 	dims.trace_smem = size_t(staged) * sizeof(BvhNode4);
-	const void *trace_kernels[] = {(const void *)k_primary, (const void *)k_trace, (const void *)k_emode,
+	const void *trace_kernels[] = {(const void *)k_wavefront_trace<true>, (const void *)k_wavefront_trace<false>, (const void *)k_emode,
 								   (const void *)k_trace_closest, (const void *)k_trace_occluded};
 	for (const void *k : trace_kernels)
 	{
@@ -1670,7 +1801,7 @@ cudaError_t configure_launches(const RenderSettings &rs, uint32_t node_count, La
 			return e;
 	}
 	int per_sm = 0;
-	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace, dims.trace_block, dims.trace_smem);
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wavefront_trace<false>, dims.trace_block, dims.trace_smem);
 	if (e != cudaSuccess)
 		return e;
 	if (per_sm < 1)
@@ -1689,7 +1820,7 @@ cudaError_t configure_launches(const RenderSettings &rs, uint32_t node_count, La
 cudaError_t launch_primary(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
 						   uint32_t sample_in_frame, const LaunchDims &dims, cudaStream_t stream)
 {
-	k_primary<<<dims.trace_grid, dims.trace_block, dims.trace_smem, stream>>>(sc, sh, wf, rs, sample_in_frame);
+	k_wavefront_trace<true><<<dims.trace_grid, dims.trace_block, dims.trace_smem, stream>>>(sc, sh, wf, rs, sample_in_frame, 0u);
 	return cudaGetLastError();
 }
 cudaError_t launch_shade(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
@@ -1701,7 +1832,7 @@ cudaError_t launch_shade(const SceneView &sc, const ShardView &sh, const Wavefro
 cudaError_t launch_trace(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
 						 uint32_t sample_in_frame, uint32_t depth, const LaunchDims &dims, cudaStream_t stream)
 {
-	k_trace<<<dims.trace_grid, dims.trace_block, dims.trace_smem, stream>>>(sc, sh, wf, rs, sample_in_frame, depth);
+	k_wavefront_trace<false><<<dims.trace_grid, dims.trace_block, dims.trace_smem, stream>>>(sc, sh, wf, rs, sample_in_frame, depth);
 	return cudaGetLastError();
 }
 cudaError_t launch_finalize(const ShardView &sh, const WavefrontView &wf, float scale, cudaStream_t stream)

@@ -16,6 +16,8 @@ ap.add_argument("--width", type=int, default=1920)
 ap.add_argument("--height", type=int, default=1080)
 ap.add_argument("--smem-nodes", type=int, default=None)
 ap.add_argument("--scene", default="sponza")
+ap.add_argument("--set", nargs="*", default=[], help="key=value settings")
+ap.add_argument("--timing", action="store_true")
 a = ap.parse_args()
 sc = S.sponza_or_standin() if a.scene == "sponza" else S.cornell_box(unit_scale=True)
 ctx = R.RenderContext(R.load_product())
@@ -23,9 +25,14 @@ S.upload(ctx, sc, a.width, a.height)
 ctx.set_setting("spp", a.spp)
 if a.smem_nodes is not None:
     ctx.set_setting("smem_nodes", a.smem_nodes)
+for kv in a.set:
+    k, v = kv.split("=")
+    ctx.set_setting(k, v)
+if a.timing:
+    ctx.set_setting("timing", "on")
 cam = sc.camera(a.width, a.height)
 for _ in range(a.frames):
     ctx.render_frame(cam, R.RESET)
 ctx.synchronize()
 st = ctx.get_stats()
-print("frame ms", st.render_time, ctx.get_frame_counters().as_dict())
+print("frame ms %.3f primary %.3f trace %.3f shade %.3f" % (st.render_time, st.primary_time, st.secondary_time + st.deep_time, st.shade_time), a.set)
