@@ -492,7 +492,7 @@ def atrium(target_tris=262_000, seed=11) -> Scene:
     # Sponza-like proportions in the reference's scaled space (≈ 740 x 310 x 450 units at scale 0.2)
     L, Wd, Ht = 370.0, 160.0, 290.0  # half length (x), half width (z), height
     aisle = 55.0
-    f = max(1.0, math.sqrt(target_tris / 262_000.0))
+    f = math.sqrt(target_tris / 148_000.0)  # the base tessellation below yields ~148k triangles
     k = lambda n: max(1, int(round(n * f)))
     dims = (256, 256)
     M = []
