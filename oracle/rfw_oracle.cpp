@@ -5,12 +5,18 @@
 // and bench.py's cpu_baseline / --impl reference leg as the checker for the CUDA path in
 // rendering-fw_b200/csrc.  Nothing under rendering-fw_b200/ includes, links or calls this file.
 //
-// PARITY UNPINNED: the reference holds no tests, golden vectors or fixtures for this path
-//  and neither of its implementations can be built in this image (Embree,
-// TBB, glm, GL, cargo/rtbvh absent; CUDART uses CUDA-11-only surface references).  The oracle
-// is therefore anchored on the reference's own call sites and source, cited function by
-// function below (paths relative to /root/reference/RFW unless noted), and on
-// oracle/_ref (the reference's bsdf/light headers compiled against our glm shim) where built.
+// PARITY PINNING: the reference holds no tests, golden vectors or fixtures for this path
+// and neither of its renderers can be built in this image (Embree, TBB, glm, GL, cargo/rtbvh absent; CUDART
+// uses CUDA-11-only surface references and CUDA launch syntax).  What CAN be built is the arithmetic the
+// renderers are made of: oracle/ref_build compiles the reference's own headers — bsdf/{disney,tools,compat}.h,
+// CUDART/src/{CUDAIntersect,getShadingData,lights}.h — from /root/reference against a small glm/CUDA stand-in
+// into oracle/_ref/librfwref.so, and tests/test_ref_pin.py checks this oracle against it (live in the build
+// container, and everywhere through the committed vectors tests/golden/ref_vectors.npz): hashes, RNG, normal
+// packing, blue noise, Disney eval/sample/pdf, Moller-Trumbore, MBVH closest/any-hit traversal, getShadingData
+// incl. trilinear texture fetch, light sampling and pick probabilities.  PINNED on reference code: those
+// building blocks.  UNPINNED (restated from source, cited line by line, no executable reference): the glue —
+// generatePrimaryRay, the shade_rays control flow, the host bounce loop, the EmbreeRT frame loop — and the BVH
+// builder (rtbvh is an un-vendored Rust crate; only the in-tree binned-SAH spec exists).
 //
 // Two image models are restated:
 //   PT-mode  = the wavefront estimator of backends/CUDART/src/Kernels.cu (+ getShadingData.h,
@@ -2322,7 +2328,91 @@ extern "C"
 		return RFWB200_OK;
 	}
 
-	// ---- scalar known-answer hooks (tests/test_oracle_kat.py) ----
+
+	// ---- hooks for pinning against the reference's own headers (oracle/ref_build, tests/test_ref_pin.py) ----
+	ORACLE_API int rfworacle_export_mesh_mbvh(rfworacle_context *c, size_t mesh, void *nodes_out, size_t node_cap,
+											  uint32_t *prims_out, size_t prim_cap, size_t *n_nodes, size_t *n_prims)
+	{
+		if (mesh >= c->meshes.size())
+			return fail("bad mesh");
+		const Bvh &b = c->meshes[mesh].bvh;
+		*n_nodes = b.mnodes.size(), *n_prims = b.prim_indices.size();
+		if (nodes_out && node_cap >= b.mnodes.size())
+			memcpy(nodes_out, b.mnodes.data(), b.mnodes.size() * sizeof(MBVHNode));
+		if (prims_out && prim_cap >= b.prim_indices.size())
+			memcpy(prims_out, b.prim_indices.data(), b.prim_indices.size() * sizeof(uint32_t));
+		return RFWB200_OK;
+	}
+	ORACLE_API int rfworacle_shading_data(rfworacle_context *c, int inst, int prim, const float *D, float u, float v,
+										  float cone_width, float *color_out, uint32_t *flags_out, float *N_out, float *iN_out)
+	{
+		if (inst < 0 || size_t(inst) >= c->instances.size())
+			return fail("bad instance");
+		const Instance &in = c->instances[inst];
+		const MeshData &m = c->meshes[in.mesh];
+		if (prim < 0 || size_t(prim) >= m.triangles.size())
+			return fail("bad prim");
+		vec3 N, iN, T, B;
+		const ShadingData sd = getShadingData(*c, vec3(D), u, v, cone_width, m.triangles[prim], N, iN, T, B, in.normal);
+		color_out[0] = sd.color.x, color_out[1] = sd.color.y, color_out[2] = sd.color.z;
+		*flags_out = sd.flags;
+		N_out[0] = N.x, N_out[1] = N.y, N_out[2] = N.z;
+		iN_out[0] = iN.x, iN_out[1] = iN.y, iN_out[2] = iN.z;
+		return RFWB200_OK;
+	}
+	ORACLE_API void rfworacle_random_point_on_light(rfworacle_context *c, float r0, float r1, const float *I, const float *N,
+													float *P_out, float *pick_out, float *pdf_out, float *color_out)
+	{
+		float pick = 0, pdf = 0;
+		vec3 color(0.0f);
+		const vec3 P = RandomPointOnLight(*c, r0, r1, vec3(I), vec3(N), pick, pdf, color);
+		P_out[0] = P.x, P_out[1] = P.y, P_out[2] = P.z;
+		*pick_out = pick, *pdf_out = pdf;
+		color_out[0] = color.x, color_out[1] = color.y, color_out[2] = color.z;
+	}
+	ORACLE_API float rfworacle_light_pick_prob(rfworacle_context *c, int idx, const float *O, const float *N, const float *I)
+	{
+		return LightPickProb(*c, idx, vec3(O), vec3(N), vec3(I));
+	}
+	ORACLE_API float rfworacle_light_pdf(const float *D, float t, float area, const float *LN)
+	{
+		return CalculateLightPDF(vec3(D), t, area, vec3(LN));
+	}
+	ORACLE_API void rfworacle_bsdf_sample_r(const float *color, const float *absorption, const uint32_t *params, const float *N,
+											const float *wo, float t, int backfacing, float r3, float r4, float *wi_out,
+											float *bsdf_out, float *pdf_out)
+	{
+		ShadingData sd;
+		sd.color = vec3(color);
+		sd.absorption = absorption ? vec3(absorption) : vec3(0.0f);
+		for (int i = 0; i < 4; i++)
+			sd.parameters[i] = params[i];
+		vec3 T, B, wi(0.0f);
+		createTangentSpace(vec3(N), T, B);
+		float pdf = 0;
+		BSDFSample(sd, T, B, vec3(N), vec3(wo), wi, pdf, r3, r4);
+		const vec3 r = BSDFEval(sd, vec3(N), vec3(wo), wi, t, backfacing != 0);
+		wi_out[0] = wi.x, wi_out[1] = wi.y, wi_out[2] = wi.z;
+		bsdf_out[0] = r.x, bsdf_out[1] = r.y, bsdf_out[2] = r.z;
+		*pdf_out = pdf;
+	}
+	ORACLE_API int rfworacle_intersect_triangle(const float *org, const float *dir, float tmin, float tmax, const float *p0,
+												const float *p1, const float *p2, float eps, float *t_out, float *uv_out)
+	{
+		float t = tmax;
+		vec2 b = {0, 0};
+		const bool hit = intersect_triangle(vec3(org), vec3(dir), tmin, &t, vec3(p0), vec3(p1), vec3(p2), &b, eps);
+		*t_out = t, uv_out[0] = b.x, uv_out[1] = b.y;
+		return hit ? 1 : 0;
+	}
+	ORACLE_API void rfworacle_tangent_space(const float *n, float *T, float *B)
+	{
+		vec3 t, b;
+		createTangentSpace(vec3(n), t, b);
+		T[0] = t.x, T[1] = t.y, T[2] = t.z, B[0] = b.x, B[1] = b.y, B[2] = b.z;
+	}
+
+	// ---- scalar known-answer hooks (tests/test_oracle.py) ----
 	ORACLE_API uint32_t rfworacle_wang_hash(uint32_t s) { return WangHash(s); }
 	ORACLE_API uint32_t rfworacle_random_int(uint32_t *s) { return RandomInt(*s); }
 	ORACLE_API uint32_t rfworacle_xor128(uint32_t x, uint32_t n)

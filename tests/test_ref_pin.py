@@ -1,0 +1,167 @@
+"""Pins the oracle on the REFERENCE's own code: tests/golden/ref_vectors.npz holds seeded inputs and the outputs of
+the reference's headers (bsdf/disney.h, bsdf/tools.h, CUDART/src/{CUDAIntersect,getShadingData,lights}.h compiled from
+/root/reference by oracle/ref_build).  The oracle must reproduce them; where oracle/_ref/librfwref.so is present (build
+container) the stored vectors are also re-checked against the live reference so they cannot go stale.
+
+Convention differences that are part of the documented deviations (oracle header D1-D6) are applied explicitly here:
+barycentrics (D4) and the explicit r3/r4 of the BSDF sample (D5)."""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import rfwb200 as R
+import scenes as S
+from ref_pin_common import REF_LIB, OracleScalar, RefLib, fp, patched_materials, reference_soup_outputs, soup_scene
+
+G = dict(np.load(Path(__file__).resolve().parent / "golden" / "ref_vectors.npz"))  # materialise: NpzFile re-reads (and frees) per access
+F, U, I, P = C.c_float, C.c_uint32, C.c_int, C.c_void_p
+
+
+@pytest.fixture(scope="module")
+def orc(built):
+    return OracleScalar()
+
+
+def close(a, b, rtol=2e-5, atol=2e-6):
+    return np.allclose(np.asarray(a, np.float64), np.asarray(b, np.float64), rtol=rtol, atol=atol, equal_nan=True)
+
+
+def test_hashes_and_packing_match_reference_bit_for_bit(orc):
+    assert [orc.wang(int(s)) for s in G["wang_in"]] == list(G["wang_out"])
+    assert np.array_equal(orc.random_stream(0xC0FFEE, 16), G["rand_stream"])
+    assert [orc.pack_normal(v) for v in G["pn_in"]] == list(G["pn_packed"])
+    un = np.array([orc.unpack_normal(int(p)) for p in G["pn_packed"]])
+    assert close(un, G["pn_unpacked"])
+    bn = np.array([orc.blue_noise(*map(int, r)) for r in G["bn_in"]], np.float32)
+    assert np.array_equal(bn, G["bn_out"])
+    ts = np.array([np.concatenate(orc.tangent_space(v)) for v in G["ts_in"]])
+    assert close(ts, G["ts_out"])
+
+
+def test_disney_bsdf_eval_and_pdf_match_reference(orc):
+    n = len(G["bsdf_color"])
+    got = []
+    for i in range(n):
+        b, pdf = orc.bsdf_eval(G["bsdf_color"][i], G["bsdf_params"][i], G["bsdf_N"][i], G["bsdf_wo"][i], G["bsdf_wi"][i])
+        got.append(np.concatenate([b, [pdf]]))
+    got, ref = np.array(got), G["bsdf_eval_out"]
+    assert np.isfinite(ref).mean() > 0.95
+    assert close(got, ref, rtol=1e-4, atol=1e-6)
+
+
+def test_disney_bsdf_sample_matches_reference(orc):
+    n = len(G["bsdf_color"])
+    got = []
+    for i in range(n):
+        wi, b, pdf = orc.bsdf_sample(G["bsdf_color"][i], G["bsdf_absorption"][i], G["bsdf_params"][i], G["bsdf_N"][i], G["bsdf_wo"][i],
+                                     float(G["bsdf_t"][i]), int(G["bsdf_backfacing"][i]), float(G["bsdf_r3"][i]), float(G["bsdf_r4"][i]))
+        got.append(np.concatenate([wi, b, [pdf]]))
+    got, ref = np.array(got), G["bsdf_sample_out"]
+    ok = np.isclose(got, ref, rtol=2e-4, atol=2e-6, equal_nan=True).all(axis=1)
+    assert ok.mean() > 0.995, np.nonzero(~ok)[0][:10]  # a sample on a lobe boundary may flip with 1-ulp differences
+
+
+def test_moller_trumbore_matches_reference(orc):
+    f = orc.f("intersect_triangle", I, [P, P, F, F, P, P, P, F, P, P])
+    ref = G["tri_out"]
+    hits = 0
+    for i in range(len(ref)):
+        t, uv = F(), np.zeros(2, np.float32)
+        hit = f(fp(G["tri_o"][i]), fp(G["tri_d"][i]), 1e-5, 1e34, fp(G["tri_p"][i, 0]), fp(G["tri_p"][i, 1]), fp(G["tri_p"][i, 2]), 1e-6,
+                C.addressof(t), uv.ctypes.data)
+        assert hit == int(ref[i, 0])
+        if hit:
+            hits += 1
+            assert abs(t.value - ref[i, 1]) <= 1e-5 * max(1, abs(ref[i, 1]))
+            # D4: reference returns area-ratio weights of (v0, v1); ours are Moller-Trumbore (v1, v2)
+            assert abs((1 - uv[0] - uv[1]) - ref[i, 2]) < 2e-4 and abs(uv[0] - ref[i, 3]) < 2e-4
+    assert hits > 50
+
+
+def _single_mesh_context(sc, mi):
+    s2 = S.Scene(name="single")
+    s2.materials, s2.tex_ids, s2.textures = sc.materials, sc.tex_ids, sc.textures
+    s2.meshes = [sc.meshes[mi]]
+    s2.instances = [(0, np.eye(4))]
+    ctx = R.RenderContext(R.load_oracle())
+    S.upload(ctx, s2, 8, 8)
+    return ctx
+
+
+@pytest.mark.parametrize("mi", [0, 1])
+def test_mbvh_traversal_matches_reference(mi):
+    """the reference's intersect_mbvh / intersect_mbvh_shadow walked the oracle's own MBVH of this mesh"""
+    sc = soup_scene()
+    ctx = _single_mesh_context(sc, mi)
+    o4 = np.concatenate([G["trav_o"], np.zeros((len(G["trav_o"]), 1), np.float32)], 1)
+    d4 = np.concatenate([G["trav_d"], np.zeros((len(G["trav_d"]), 1), np.float32)], 1)
+    hits = ctx.trace_closest(o4, d4)
+    occ = ctx.trace_occluded(o4, d4, G["trav_tmax"])
+    ref = G[f"trav_out_mesh{mi}"]
+    assert np.array_equal(hits["prim_id"] >= 0, ref[:, 0] == 1)
+    h = ref[:, 0] == 1
+    assert h.sum() > 30
+    assert np.array_equal(hits["prim_id"][h], ref[h, 2].astype(np.int32))
+    assert np.allclose(hits["t"][h], ref[h, 1], rtol=1e-6)
+    assert np.array_equal(occ, ref[:, 3].astype(np.uint8))
+
+
+def test_get_shading_data_matches_reference():
+    sc = soup_scene()
+    ctx = R.RenderContext(R.load_oracle())
+    S.upload(ctx, sc, 8, 8)
+    f = ctx.L.fn("shading_data", C.c_int, [P, I, I, P, F, F, F, P, P, P, P])
+    got = []
+    for i in range(len(G["sd_inst"])):
+        color, flags, N, iN = np.zeros(3, np.float32), U(), np.zeros(3, np.float32), np.zeros(3, np.float32)
+        rc = f(ctx._h, int(G["sd_inst"][i]), int(G["sd_prim"][i]), fp(G["sd_D"][i]), float(G["sd_u"][i]), float(G["sd_v"][i]),
+               float(G["sd_cone"][i]), color.ctypes.data, C.addressof(flags), N.ctypes.data, iN.ctypes.data)
+        assert rc == 0
+        got.append(np.concatenate([color, [flags.value], N, iN]))
+    got, ref = np.array(got, np.float32), G["sd_out"]
+    assert np.array_equal(got[:, 3], ref[:, 3])  # alpha flag
+    live = ref[:, 3] == 0  # the reference returns early (N, iN partly unset) on an alpha cut-out
+    assert live.sum() > 100 and (~live).sum() > 3
+    assert close(got[live][:, :3], ref[live][:, :3], rtol=2e-4, atol=2e-6)  # colour incl. trilinear texture fetch
+    assert close(got[live][:, 4:], ref[live][:, 4:], rtol=1e-4, atol=2e-6)  # N, iN incl. normal mapping
+
+
+def test_light_sampling_matches_reference():
+    sc = soup_scene()
+    ctx = R.RenderContext(R.load_oracle())
+    S.upload(ctx, sc, 8, 8)
+    rpl = ctx.L.fn("random_point_on_light", None, [P, F, F, P, P, P, P, P, P])
+    lpp = ctx.L.fn("light_pick_prob", F, [P, I, P, P, P])
+    rb = ctx.L.fn("random_barycentrics", None, [F, P])
+    got, gb = [], []
+    for i in range(len(G["li_I"])):
+        Pp, pick, pdf, col = np.zeros(3, np.float32), F(), F(), np.zeros(3, np.float32)
+        rpl(ctx._h, float(G["li_r"][i, 0]), float(G["li_r"][i, 1]), fp(G["li_I"][i]), fp(G["li_N"][i]), Pp.ctypes.data, C.addressof(pick),
+            C.addressof(pdf), col.ctypes.data)
+        pp = lpp(ctx._h, i % max(len(sc.area_lights), 1), fp(G["li_O"][i]), fp(G["li_N"][i]), fp(G["li_I"][i]))
+        got.append(np.concatenate([Pp, [pick.value, pdf.value], col, [pp]]))
+        b = np.zeros(3, np.float32)
+        rb(float(G["li_r"][i, 0]), b.ctypes.data)
+        gb.append(b)
+    got, ref = np.array(got, np.float32), G["li_out"]
+    assert close(np.array(gb), G["rb_out"], rtol=1e-6, atol=1e-7)
+    picked = ref[:, 4] > 0  # a light was selected (pdf > 0); otherwise outputs are unspecified placeholders
+    assert picked.sum() > 80
+    ok = np.isclose(got[picked], ref[picked], rtol=2e-4, atol=2e-6).all(axis=1)
+    assert ok.mean() > 0.99  # the cumulative pick can flip when r1*sum lands on a boundary
+    assert close(got[:, 8], ref[:, 8], rtol=2e-4, atol=1e-6)  # LightPickProb (with the D1 index fix the same function)
+
+
+@pytest.mark.skipif(not REF_LIB.exists(), reason="oracle/_ref is only built where /root/reference exists")
+def test_stored_vectors_are_what_the_live_reference_produces():
+    ref = RefLib()
+    assert [ref.wang(int(s)) for s in G["wang_in"]] == list(G["wang_out"])
+    i = 7
+    b, pdf = ref.bsdf_eval(G["bsdf_color"][i], G["bsdf_params"][i], G["bsdf_N"][i], G["bsdf_wo"][i], G["bsdf_wi"][i])
+    assert close(np.concatenate([b, [pdf]]), G["bsdf_eval_out"][i], rtol=1e-6)
+    inp = {k: G[k] for k in G if k.startswith(("trav_", "sd_", "li_")) and not k.endswith(("_out", "_out_mesh0", "_out_mesh1"))}
+    live = reference_soup_outputs(ref, soup_scene(), inp)
+    for k, v in live.items():
+        assert close(v, G[k], rtol=1e-6, atol=1e-7), k
