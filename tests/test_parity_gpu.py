@@ -88,6 +88,24 @@ def test_extend_primary_parity(product_lib, oracle_lib, scene):
     _check_hits(g, o, origins, dirs, hg, ho)
 
 
+@pytest.mark.parametrize("smem_nodes,fetch_threshold", [(0, 16), (96, 8), (1500, 32)])
+def test_pt_frame_is_independent_of_staging_and_fetch_tunables(product_lib, smem_nodes, fetch_threshold):
+    """the TMA-staged BVH prefix (cp.async.bulk + mbarrier) and the dynamic-fetch threshold change scheduling only"""
+    W, H = 160, 96
+    imgs = []
+    for tuned in (False, True):
+        sc = S.feature_soup()
+        ctx = R.RenderContext(product_lib)
+        S.upload(ctx, sc, W, H)
+        ctx.set_setting("spp", 2)
+        if tuned:
+            ctx.set_setting("smem_nodes", smem_nodes)
+            ctx.set_setting("fetch_threshold", fetch_threshold)
+        ctx.render_frame(sc.camera(W, H), R.RESET)
+        imgs.append(ctx.read_image().copy())
+    assert np.array_equal(imgs[0], imgs[1])
+
+
 def test_extend_random_rays_and_occlusion(product_lib, oracle_lib):
     (g, sc), (o, _) = make_pair(product_lib, oracle_lib, S.feature_soup, 32, 32)
     rng = np.random.default_rng(5)
