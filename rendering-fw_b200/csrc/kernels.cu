@@ -214,6 +214,15 @@ __device__ __forceinline__ float slab(float lo, float hi, float idir, float ood,
 		key##K = h ? __uint_as_float((__float_as_uint(fmaxf(tn, 0.0f)) & 0xFFFFFFFCu) | uint32_t(K)) : MISSKEY(K);      \
 	}
 #define MISSKEY(K) __uint_as_float(0x7f000000u | uint32_t(K))
+// same test with the near / far planes already selected by the sign of the ray direction (no per-axis min/max)
+#define CHILD_N(K, C)                                                                                                   \
+	{                                                                                                                   \
+		const float tn = fmaxf(fmaxf(fmaf(nearx.C, idx, -oodx), fmaf(neary.C, idy, -oody)), fmaf(nearz.C, idz, -oodz));  \
+		const float tf = fminf(fminf(fmaf(farx.C, idx, -oodx), fmaf(fary.C, idy, -oody)), fmaf(farz.C, idz, -oodz));     \
+		const bool h = (tf >= tn) & (tn < tmax) & (tf >= tmin);                                                         \
+		nh += h ? 1 : 0;                                                                                                \
+		key##K = h ? __uint_as_float((__float_as_uint(fmaxf(tn, 0.0f)) & 0xFFFFFFFCu) | uint32_t(K)) : MISSKEY(K);      \
+	}
 #define CSWAP(A, B)                                                                                                     \
 	{                                                                                                                   \
 		const float lo_ = fminf(A, B), hi_ = fmaxf(A, B);                                                               \
@@ -425,6 +434,7 @@ __global__ void __launch_bounds__(256) k_wavefront_trace(const SceneView sc, con
 	uint32_t item = 0;
 	V3 o = mk(0.f), d = mk(0.f);
 	float idx = 0.f, idy = 0.f, idz = 0.f, oodx = 0.f, oody = 0.f, oodz = 0.f;
+	uint32_t sgx = 0, sgy = 0, sgz = 0; // 1 when the ray runs towards -axis: the max plane is the near plane
 	float tmin = 0.f, tmax = 0.f, hit_u = 0.f, hit_v = 0.f;
 	uint32_t hit_tri = 0xffffffffu;
 	int stack[TRAVERSAL_STACK];
@@ -491,6 +501,7 @@ __global__ void __launch_bounds__(256) k_wavefront_trace(const SceneView sc, con
 						idy = 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));
 						idz = 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
 						oodx = o.x * idx, oody = o.y * idy, oodz = o.z * idz;
+						sgx = idx < 0.0f ? 1u : 0u, sgy = idy < 0.0f ? 1u : 0u, sgz = idz < 0.0f ? 1u : 0u;
 						stack[0] = SENTINEL;
 						sp = 1, cur = 0, leaf = NO_LEAF, hit_tri = 0xffffffffu, hit_u = 0.f, hit_v = 0.f;
 						alive = true;
@@ -509,13 +520,23 @@ __global__ void __launch_bounds__(256) k_wavefront_trace(const SceneView sc, con
 				// (speculatively) so it stays useful until every lane of the warp holds a leaf
 				while (uint32_t(cur) < uint32_t(SENTINEL))
 				{
-					const NodeRegs n = load_node(sc, snodes, n_smem, uint32_t(cur));
+					// one node = one 128-byte line: six plane quads picked by the ray's octant + the child words
+					const float4 *np_ = uint32_t(cur) < n_smem ? snodes + size_t(cur) * 8
+															   : reinterpret_cast<const float4 *>(sc.nodes) + size_t(cur) * 8;
+					const float4 nearx = np_[sgx], farx = np_[sgx ^ 1u];
+					const float4 neary = np_[2u + sgy], fary = np_[3u - sgy];
+					const float4 nearz = np_[4u + sgz], farz = np_[5u - sgz];
+					struct
+					{
+						int4 child;
+					} n;
+					n.child = *reinterpret_cast<const int4 *>(np_ + 6);
 					float key0, key1, key2, key3;
 					int nh = 0;
-					CHILD_T(0, x)
-					CHILD_T(1, y)
-					CHILD_T(2, z)
-					CHILD_T(3, w)
+					CHILD_N(0, x)
+					CHILD_N(1, y)
+					CHILD_N(2, z)
+					CHILD_N(3, w)
 					if (nh == 0)
 						cur = stack[--sp];
 					else
