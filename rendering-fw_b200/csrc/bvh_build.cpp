@@ -1,4 +1,12 @@
 // bvh_build.cpp — see bvh_build.h
+//
+// Builder: top-down SAH over triangle *references* (primitive id + clipped box) with spatial splits
+// (Stich, Friedrich, Dietrich: "Spatial Splits in Bounding Volume Hierarchies", HPG 2009) — the reference
+// asks its Rust crate for the same kind of tree (BVHTree::SpatialSAH, RFW/system/bvh/src/top_level_bvh.cpp:41).
+// Object splits are binned (16 bins on reference-box centroids), spatial splits use chopped binning with
+// exact triangle clipping; a spatial split is only tried when the object-split children overlap, and a global
+// budget bounds the number of duplicated references.  Large subtrees are built by a pool of host threads.
+// The BVH2 is then collapsed to 4-wide (open the child with the largest area) and laid out breadth-first.
 #include "bvh_build.h"
 
 #include <algorithm>
@@ -9,6 +17,7 @@
 #include <cstring>
 #include <deque>
 #include <limits>
+#include <memory>
 #include <mutex>
 #include <thread>
 
@@ -18,10 +27,13 @@ namespace
 {
 
 constexpr int BINS = 16;
+constexpr int SPATIAL_BINS = 32;
 constexpr int MAX_LEAF = 4;
-constexpr int MAX_DEPTH2 = 31;		   // BVH2 depth bound => BVH4 depth <= 31 => stack <= 94 < TRAVERSAL_STACK
-constexpr size_t PAR_THRESHOLD = 16384; // subtrees above this size become pool tasks
-constexpr float BOX_PAD = 1e-5f;		   // reference pads primitive and node boxes by 1e-5 (bvh_tree.cpp:446, bvh_node.h:221)
+constexpr int MAX_DEPTH2 = 31;			// BVH2 depth bound => BVH4 depth <= 31 => stack <= 94 + sentinel <= TRAVERSAL_STACK
+constexpr size_t PAR_THRESHOLD = 16384; // subtrees above this many references become pool tasks
+constexpr float BOX_PAD = 1e-5f;		// reference pads primitive and node boxes by 1e-5 (bvh_tree.cpp:446, bvh_node.h:221)
+constexpr float SPATIAL_ALPHA = 1e-5f;	// overlap / root area above which a spatial split is considered
+constexpr float REF_BUDGET = 0.6f;		// at most this fraction of extra (duplicated) references
 
 struct Box
 {
@@ -41,6 +53,12 @@ struct Box
 		for (int a = 0; a < 3; a++)
 			lo[a] = std::min(lo[a], p[a]), hi[a] = std::max(hi[a], p[a]);
 	}
+	void clip_to(const Box &b)
+	{
+		for (int a = 0; a < 3; a++)
+			lo[a] = std::max(lo[a], b.lo[a]), hi[a] = std::min(hi[a], b.hi[a]);
+	}
+	bool valid() const { return lo[0] <= hi[0] && lo[1] <= hi[1] && lo[2] <= hi[2]; }
 	float area() const
 	{
 		const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
@@ -50,64 +68,120 @@ struct Box
 	}
 };
 
+inline Box intersection(const Box &a, const Box &b)
+{
+	Box r = a;
+	r.clip_to(b);
+	return r;
+}
+
+struct Ref
+{
+	Box box;
+	uint32_t prim;
+};
+
 struct Node2
 {
 	Box box;
 	int32_t left = -1, right = -1; // children (inner)
-	uint32_t first = 0, count = 0; // leaf range in idx[] when count > 0
-	int32_t depth = 0;
+	std::vector<uint32_t> prims;   // leaf content
+	bool leaf = false;
 };
 
 struct Task
 {
 	int32_t node;
-	uint32_t first, count;
+	std::vector<Ref> refs;
 	int32_t depth;
 };
 
+inline int ceil_log2(uint32_t v)
+{
+	int r = 0;
+	while ((1u << r) < v)
+		r++;
+	return r;
+}
+
+// clip the triangle of `r` against the plane x[axis] = pos, bound both halves (SBVH reference splitting)
+inline void split_ref(const Ref &r, const BuildTriangle &t, int axis, float pos, Ref &l, Ref &rt)
+{
+	l.prim = rt.prim = r.prim;
+	l.box.reset(), rt.box.reset();
+	const float *v[3] = {t.v0, t.v1, t.v2};
+	for (int i = 0; i < 3; i++)
+	{
+		const float *a = v[i], *b = v[(i + 1) % 3];
+		const float pa = a[axis], pb = b[axis];
+		if (pa <= pos)
+			l.box.grow(a);
+		if (pa >= pos)
+			rt.box.grow(a);
+		if ((pa < pos && pb > pos) || (pa > pos && pb < pos))
+		{
+			const float s = std::min(std::max((pos - pa) / (pb - pa), 0.0f), 1.0f);
+			float p[3];
+			for (int k = 0; k < 3; k++)
+				p[k] = a[k] + (b[k] - a[k]) * s;
+			p[axis] = pos;
+			l.box.grow(p), rt.box.grow(p);
+		}
+	}
+	l.box.hi[axis] = std::min(l.box.hi[axis], pos);
+	rt.box.lo[axis] = std::max(rt.box.lo[axis], pos);
+	l.box.clip_to(r.box), rt.box.clip_to(r.box);
+}
+
 struct Builder
 {
-	const Box *boxes;
-	const float *cent; // 3 per prim
-	std::vector<uint32_t> idx;
+	const BuildTriangle *tris = nullptr;
 	std::vector<Node2> nodes;
 	std::atomic<int32_t> next_node{1};
+	std::atomic<int64_t> spare_refs{0}; // remaining duplication budget
+	float root_area = 1.0f;
+	bool spatial = true;
 
 	std::mutex mtx;
 	std::condition_variable cv;
-	std::deque<Task> queue;
+	std::deque<std::unique_ptr<Task>> queue;
 	std::atomic<int> outstanding{0};
 	bool parallel = false;
 
-	static int ceil_log2(uint32_t v)
+	void make_leaf(Node2 &node, const std::vector<Ref> &refs)
 	{
-		int r = 0;
-		while ((1u << r) < v)
-			r++;
-		return r;
+		node.leaf = true;
+		node.prims.resize(refs.size());
+		for (size_t i = 0; i < refs.size(); i++)
+			node.prims[i] = refs[i].prim;
 	}
 
-	// returns false when the range became a leaf
-	bool split(const Task &t, Task &lt, Task &rt)
+	// returns false when the node became a leaf; otherwise fills the two child tasks
+	bool split(Task &t, Task &lt, Task &rt)
 	{
 		Node2 &node = nodes[t.node];
-		node.depth = t.depth;
-		const uint32_t first = t.first, count = t.count;
+		std::vector<Ref> &refs = t.refs;
+		const uint32_t count = uint32_t(refs.size());
 		if (count <= 1)
 		{
-			node.first = first, node.count = count;
+			make_leaf(node, refs);
 			return false;
 		}
 		Box cb;
 		cb.reset();
-		for (uint32_t i = first; i < first + count; i++)
-			cb.grow(cent + 3 * size_t(idx[i]));
-
+		for (const Ref &r : refs)
+		{
+			float c[3];
+			for (int a = 0; a < 3; a++)
+				c[a] = (r.box.lo[a] + r.box.hi[a]) * 0.5f;
+			cb.grow(c);
+		}
 		const int levels_needed = ceil_log2((count + MAX_LEAF - 1) / MAX_LEAF);
 		const bool force_median = t.depth + levels_needed >= MAX_DEPTH2;
 
-		int best_axis = -1, best_bin = -1;
-		float best_cost = 3.0e38f;
+		// ---- object split: binned SAH on reference centroids -------------------------------------------
+		int obj_axis = -1, obj_bin = -1;
+		float obj_cost = 3.0e38f, obj_overlap = 0.0f;
 		if (!force_median)
 		{
 			for (int axis = 0; axis < 3; axis++)
@@ -120,15 +194,14 @@ struct Builder
 				for (int b = 0; b < BINS; b++)
 					bb[b].reset(), bc[b] = 0;
 				const float scale = float(BINS) * (1.0f - 1e-6f) / ext;
-				for (uint32_t i = first; i < first + count; i++)
+				for (const Ref &r : refs)
 				{
-					const uint32_t p = idx[i];
-					int b = int((cent[3 * size_t(p) + axis] - cb.lo[axis]) * scale);
+					int b = int(((r.box.lo[axis] + r.box.hi[axis]) * 0.5f - cb.lo[axis]) * scale);
 					b = b < 0 ? 0 : (b >= BINS ? BINS - 1 : b);
-					bb[b].grow(boxes[p]);
+					bb[b].grow(r.box);
 					bc[b]++;
 				}
-				float right_area[BINS];
+				Box right_box[BINS];
 				uint32_t right_count[BINS];
 				Box acc;
 				acc.reset();
@@ -137,7 +210,7 @@ struct Builder
 				{
 					acc.grow(bb[b]);
 					c += bc[b];
-					right_area[b] = acc.area(), right_count[b] = c;
+					right_box[b] = acc, right_count[b] = c;
 				}
 				acc.reset();
 				c = 0;
@@ -147,90 +220,194 @@ struct Builder
 					c += bc[b];
 					if (c == 0 || right_count[b + 1] == 0)
 						continue;
-					const float cost = acc.area() * float(c) + right_area[b + 1] * float(right_count[b + 1]);
-					if (cost < best_cost)
-						best_cost = cost, best_axis = axis, best_bin = b;
+					const float cost = acc.area() * float(c) + right_box[b + 1].area() * float(right_count[b + 1]);
+					if (cost < obj_cost)
+					{
+						obj_cost = cost, obj_axis = axis, obj_bin = b;
+						const Box ov = intersection(acc, right_box[b + 1]);
+						obj_overlap = ov.valid() ? ov.area() : 0.0f;
+					}
 				}
 			}
 		}
+
+		// ---- spatial split: chopped binning over the node box ---------------------------------------------
+		int sp_axis = -1;
+		float sp_pos = 0.0f, sp_cost = 3.0e38f;
+		if (spatial && !force_median && count > MAX_LEAF && spare_refs.load(std::memory_order_relaxed) > 0 &&
+			(obj_axis < 0 || obj_overlap > SPATIAL_ALPHA * root_area))
+		{
+			for (int axis = 0; axis < 3; axis++)
+			{
+				const float lo = node.box.lo[axis], ext = node.box.hi[axis] - lo;
+				if (!(ext > 1e-12f))
+					continue;
+				struct SBin
+				{
+					Box box;
+					uint32_t enter, exit;
+				} bins[SPATIAL_BINS];
+				for (auto &b : bins)
+					b.box.reset(), b.enter = b.exit = 0;
+				const float scale = float(SPATIAL_BINS) / ext, binw = ext / float(SPATIAL_BINS);
+				for (const Ref &r : refs)
+				{
+					int first = int((r.box.lo[axis] - lo) * scale), last = int((r.box.hi[axis] - lo) * scale);
+					first = std::min(std::max(first, 0), SPATIAL_BINS - 1);
+					last = std::min(std::max(last, first), SPATIAL_BINS - 1);
+					Ref cur = r;
+					for (int b = first; b < last; b++)
+					{
+						Ref l, rr;
+						split_ref(cur, tris[r.prim], axis, lo + binw * float(b + 1), l, rr);
+						if (l.box.valid())
+							bins[b].box.grow(l.box);
+						cur = rr;
+						if (!cur.box.valid())
+							break;
+					}
+					if (cur.box.valid())
+						bins[last].box.grow(cur.box);
+					bins[first].enter++, bins[last].exit++;
+				}
+				Box right_box[SPATIAL_BINS];
+				Box acc;
+				acc.reset();
+				for (int b = SPATIAL_BINS - 1; b > 0; b--)
+				{
+					acc.grow(bins[b].box);
+					right_box[b] = acc;
+				}
+				acc.reset();
+				uint32_t ln = 0, rn = count;
+				for (int b = 1; b < SPATIAL_BINS; b++)
+				{
+					acc.grow(bins[b - 1].box);
+					ln += bins[b - 1].enter;
+					rn -= bins[b - 1].exit;
+					if (ln == 0 || rn == 0)
+						continue;
+					const float cost = acc.area() * float(ln) + right_box[b].area() * float(rn);
+					if (cost < sp_cost)
+						sp_cost = cost, sp_axis = axis, sp_pos = lo + binw * float(b);
+				}
+			}
+		}
+
 		const float node_area = node.box.area();
 		const float leaf_cost = float(count) * node_area;
+		const float best_cost = std::min(obj_cost, sp_cost);
 		const float split_cost = node_area * 1.0f + best_cost; // C_trav = C_isect = 1
-		if (count <= MAX_LEAF && (best_axis < 0 || split_cost >= leaf_cost))
+		if (count <= MAX_LEAF && (best_cost >= 3.0e38f || split_cost >= leaf_cost))
 		{
-			node.first = first, node.count = count;
+			make_leaf(node, refs);
 			return false;
 		}
-		uint32_t mid;
-		if (best_axis >= 0)
+
+		std::vector<Ref> left, right;
+		bool done = false;
+		if (sp_axis >= 0 && sp_cost < obj_cost)
 		{
-			const float ext = cb.hi[best_axis] - cb.lo[best_axis];
-			const float scale = float(BINS) * (1.0f - 1e-6f) / ext;
-			const float lo = cb.lo[best_axis];
-			const int axis = best_axis, bin = best_bin;
-			auto it = std::partition(idx.begin() + first, idx.begin() + first + count, [&](uint32_t p) {
-				int b = int((cent[3 * size_t(p) + axis] - lo) * scale);
-				b = b < 0 ? 0 : (b >= BINS ? BINS - 1 : b);
-				return b <= bin;
-			});
-			mid = uint32_t(it - idx.begin());
+			left.reserve(count), right.reserve(count);
+			for (const Ref &r : refs)
+			{
+				if (r.box.hi[sp_axis] <= sp_pos)
+					left.push_back(r);
+				else if (r.box.lo[sp_axis] >= sp_pos)
+					right.push_back(r);
+				else
+				{
+					Ref l, rr;
+					split_ref(r, tris[r.prim], sp_axis, sp_pos, l, rr);
+					const bool lv = l.box.valid(), rv = rr.box.valid();
+					if (lv && rv)
+						left.push_back(l), right.push_back(rr);
+					else if (lv)
+						left.push_back(r);
+					else
+						right.push_back(r);
+				}
+			}
+			if (!left.empty() && !right.empty() && left.size() < count + count / 2 && right.size() < count + count / 2 &&
+				(left.size() < count || right.size() < count))
+			{
+				spare_refs.fetch_sub(int64_t(left.size() + right.size()) - int64_t(count), std::memory_order_relaxed);
+				done = true;
+			}
+			else
+				left.clear(), right.clear();
 		}
-		else
+		if (!done && obj_axis >= 0)
 		{
-			// all centroids coincide, or the depth budget forces balanced splits: object median on
-			// the widest centroid axis
+			const float ext = cb.hi[obj_axis] - cb.lo[obj_axis];
+			const float scale = float(BINS) * (1.0f - 1e-6f) / ext, lo = cb.lo[obj_axis];
+			left.reserve(count), right.reserve(count);
+			for (const Ref &r : refs)
+			{
+				int b = int(((r.box.lo[obj_axis] + r.box.hi[obj_axis]) * 0.5f - lo) * scale);
+				b = b < 0 ? 0 : (b >= BINS ? BINS - 1 : b);
+				(b <= obj_bin ? left : right).push_back(r);
+			}
+			done = !left.empty() && !right.empty();
+			if (!done)
+				left.clear(), right.clear();
+		}
+		if (!done)
+		{
+			// all centroids coincide, or the depth budget forces balanced splits: object median on the widest axis
 			int axis = 0;
 			float w = cb.hi[0] - cb.lo[0];
 			for (int a = 1; a < 3; a++)
 				if (cb.hi[a] - cb.lo[a] > w)
 					w = cb.hi[a] - cb.lo[a], axis = a;
-			mid = first + count / 2;
-			std::nth_element(idx.begin() + first, idx.begin() + mid, idx.begin() + first + count, [&](uint32_t a, uint32_t b) {
-				return cent[3 * size_t(a) + axis] < cent[3 * size_t(b) + axis];
+			const size_t mid = count / 2;
+			std::nth_element(refs.begin(), refs.begin() + mid, refs.end(), [&](const Ref &a, const Ref &b) {
+				return a.box.lo[axis] + a.box.hi[axis] < b.box.lo[axis] + b.box.hi[axis];
 			});
+			left.assign(refs.begin(), refs.begin() + mid);
+			right.assign(refs.begin() + mid, refs.end());
 		}
-		if (mid == first || mid == first + count)
-			mid = first + count / 2;
+		std::vector<Ref>().swap(refs);
+
 		const int32_t l = next_node.fetch_add(2), r = l + 1;
-		node.left = l, node.right = r, node.count = 0;
+		node.left = l, node.right = r;
 		Box lb, rb;
 		lb.reset(), rb.reset();
-		for (uint32_t i = first; i < mid; i++)
-			lb.grow(boxes[idx[i]]);
-		for (uint32_t i = mid; i < first + count; i++)
-			rb.grow(boxes[idx[i]]);
+		for (const Ref &x : left)
+			lb.grow(x.box);
+		for (const Ref &x : right)
+			rb.grow(x.box);
 		nodes[l].box = lb, nodes[r].box = rb;
-		lt = {l, first, mid - first, t.depth + 1};
-		rt = {r, mid, first + count - mid, t.depth + 1};
+		lt.node = l, lt.refs = std::move(left), lt.depth = t.depth + 1;
+		rt.node = r, rt.refs = std::move(right), rt.depth = t.depth + 1;
 		return true;
 	}
 
-	void build_serial(const Task &t)
+	void build_serial(std::unique_ptr<Task> root)
 	{
-		// explicit stack: depth-first, large right halves may be handed to the pool
-		std::vector<Task> stack;
-		stack.push_back(t);
+		std::vector<std::unique_ptr<Task>> stack;
+		stack.push_back(std::move(root));
 		while (!stack.empty())
 		{
-			const Task cur = stack.back();
+			std::unique_ptr<Task> cur = std::move(stack.back());
 			stack.pop_back();
-			Task l, r;
-			if (!split(cur, l, r))
+			std::unique_ptr<Task> l(new Task()), r(new Task());
+			if (!split(*cur, *l, *r))
 				continue;
-			if (parallel && r.count > PAR_THRESHOLD)
-				push_task(r);
+			if (parallel && r->refs.size() > PAR_THRESHOLD)
+				push_task(std::move(r));
 			else
-				stack.push_back(r);
-			stack.push_back(l);
+				stack.push_back(std::move(r));
+			stack.push_back(std::move(l));
 		}
 	}
 
-	void push_task(const Task &t)
+	void push_task(std::unique_ptr<Task> t)
 	{
 		outstanding.fetch_add(1);
 		{
 			std::lock_guard<std::mutex> lk(mtx);
-			queue.push_back(t);
+			queue.push_back(std::move(t));
 		}
 		cv.notify_one();
 	}
@@ -239,16 +416,16 @@ struct Builder
 	{
 		for (;;)
 		{
-			Task t;
+			std::unique_ptr<Task> t;
 			{
 				std::unique_lock<std::mutex> lk(mtx);
 				cv.wait(lk, [&] { return !queue.empty() || outstanding.load() == 0; });
 				if (queue.empty())
 					return;
-				t = queue.front();
+				t = std::move(queue.front());
 				queue.pop_front();
 			}
-			build_serial(t);
+			build_serial(std::move(t));
 			if (outstanding.fetch_sub(1) == 1)
 			{
 				std::lock_guard<std::mutex> lk(mtx);
@@ -263,9 +440,15 @@ inline Box tri_box(const BuildTriangle &t)
 	Box b;
 	b.reset();
 	b.grow(t.v0), b.grow(t.v1), b.grow(t.v2);
+	return b;
+}
+
+// pad relative to magnitude as well: 1e-5 absolute vanishes next to coordinates ~1e3
+inline Box padded(const Box &in)
+{
+	Box b = in;
 	for (int a = 0; a < 3; a++)
 	{
-		// pad relative to magnitude as well: 1e-5 absolute vanishes next to coordinates ~1e3
 		const float m = std::max(std::fabs(b.lo[a]), std::fabs(b.hi[a]));
 		const float pad = std::max(BOX_PAD, m * 2.4e-7f);
 		b.lo[a] -= pad, b.hi[a] += pad;
@@ -299,7 +482,7 @@ inline Box child_box(const BvhNode4 &n, int slot)
 
 } // namespace
 
-void build_bvh4(const BuildTriangle *tris, size_t count, int threads, BvhBuildResult &out)
+void build_bvh4(const BuildTriangle *tris, size_t count, int threads, BvhBuildResult &out, bool spatial_splits)
 {
 	const auto t0 = std::chrono::steady_clock::now();
 	out = BvhBuildResult();
@@ -313,30 +496,30 @@ void build_bvh4(const BuildTriangle *tris, size_t count, int threads, BvhBuildRe
 		out.node_parent.push_back(0xffffffffu);
 		return;
 	}
-	std::vector<Box> boxes(count);
-	std::vector<float> cent(count * 3);
+	std::unique_ptr<Task> root(new Task());
+	root->node = 0, root->depth = 0;
+	root->refs.resize(count);
 	Box root_box;
 	root_box.reset();
 	for (size_t i = 0; i < count; i++)
 	{
-		boxes[i] = tri_box(tris[i]);
-		for (int a = 0; a < 3; a++)
-			cent[3 * i + a] = (boxes[i].lo[a] + boxes[i].hi[a]) * 0.5f;
-		root_box.grow(boxes[i]);
+		root->refs[i].box = tri_box(tris[i]);
+		root->refs[i].prim = uint32_t(i);
+		root_box.grow(root->refs[i].box);
 	}
 	Builder b;
-	b.boxes = boxes.data();
-	b.cent = cent.data();
-	b.idx.resize(count);
-	for (size_t i = 0; i < count; i++)
-		b.idx[i] = uint32_t(i);
-	b.nodes.resize(2 * count + 2);
+	b.tris = tris;
+	b.spatial = spatial_splits;
+	b.root_area = std::max(root_box.area(), 1e-30f);
+	b.spare_refs.store(int64_t(double(count) * REF_BUDGET));
+	const size_t max_refs = count + size_t(double(count) * REF_BUDGET) + 64;
+	b.nodes.resize(2 * max_refs + 2);
 	b.nodes[0].box = root_box;
 	threads = std::max(1, threads);
 	b.parallel = threads > 1 && count > 4 * PAR_THRESHOLD;
 	if (b.parallel)
 	{
-		b.push_task({0, 0, uint32_t(count), 0});
+		b.push_task(std::move(root));
 		std::vector<std::thread> pool;
 		for (int t = 1; t < threads; t++)
 			pool.emplace_back([&] { b.worker(); });
@@ -345,21 +528,22 @@ void build_bvh4(const BuildTriangle *tris, size_t count, int threads, BvhBuildRe
 			t.join();
 	}
 	else
-		b.build_serial({0, 0, uint32_t(count), 0});
+		b.build_serial(std::move(root));
 
-	// ---- collapse to 4-wide, breadth-first layout ----
+	// ---- collapse to 4-wide, breadth-first layout; leaves get their slice of the triangle order here ----
 	const std::vector<Node2> &n2 = b.nodes;
 	struct Pending
 	{
-		int32_t n2; // BVH2 inner node (or -1: synthetic root around a leaf root)
+		int32_t n2;
 		uint32_t parent;
 	};
 	std::vector<Pending> fifo;
 	fifo.reserve(count);
 	out.nodes.reserve(count / 2 + 1);
+	out.tri_order.reserve(max_refs);
 	fifo.push_back({0, 0xffffffffu});
 	float cost = 0;
-	const float inv_root_area = root_box.area() > 0 ? 1.0f / root_box.area() : 0.0f;
+	const float inv_root_area = 1.0f / b.root_area;
 	std::vector<int> depth4;
 	depth4.push_back(1);
 	int max_depth = 1;
@@ -371,7 +555,7 @@ void build_bvh4(const BuildTriangle *tris, size_t count, int threads, BvhBuildRe
 		int32_t kids[4];
 		int nk = 0;
 		const Node2 &src = n2[p.n2];
-		if (src.count > 0 || src.left < 0)
+		if (src.leaf)
 			kids[nk++] = p.n2; // root is a leaf
 		else
 		{
@@ -383,7 +567,7 @@ void build_bvh4(const BuildTriangle *tris, size_t count, int threads, BvhBuildRe
 				for (int k = 0; k < nk; k++)
 				{
 					const Node2 &c = n2[kids[k]];
-					if (c.count == 0 && c.left >= 0 && c.box.area() > best_area)
+					if (!c.leaf && c.box.area() > best_area)
 						best_area = c.box.area(), best = k;
 				}
 				if (best < 0)
@@ -403,12 +587,21 @@ void build_bvh4(const BuildTriangle *tris, size_t count, int threads, BvhBuildRe
 				continue;
 			}
 			const Node2 &c = n2[kids[k]];
-			set_child_box(node, k, c.box);
-			if (c.count > 0 || c.left < 0)
+			set_child_box(node, k, padded(c.box));
+			if (c.leaf)
 			{
-				const uint32_t cnt = std::max<uint32_t>(c.count, 1u);
-				node.child[k] = ~int32_t((c.first << 2) | (cnt - 1));
-				cost += c.box.area() * inv_root_area * float(c.count);
+				const uint32_t first = uint32_t(out.tri_order.size());
+				const uint32_t cnt = uint32_t(std::min<size_t>(std::max<size_t>(c.prims.size(), 1), MAX_LEAF));
+				if (c.prims.empty())
+					out.tri_order.push_back(0);
+				for (size_t i = 0; i < c.prims.size(); i++)
+				{
+					if (i >= size_t(MAX_LEAF))
+						break; // cannot happen: leaves are only made at <= MAX_LEAF references
+					out.tri_order.push_back(c.prims[i]);
+				}
+				node.child[k] = ~int32_t((first << 2) | (cnt - 1));
+				cost += c.box.area() * inv_root_area * float(c.prims.size());
 			}
 			else
 			{
@@ -422,7 +615,6 @@ void build_bvh4(const BuildTriangle *tris, size_t count, int threads, BvhBuildRe
 		out.nodes.push_back(node);
 		out.node_parent.push_back(p.parent);
 	}
-	out.tri_order = std::move(b.idx);
 	out.sah_cost = cost;
 	out.depth = max_depth;
 	out.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -431,6 +623,7 @@ void build_bvh4(const BuildTriangle *tris, size_t count, int threads, BvhBuildRe
 void refit_bvh4(const BuildTriangle *tris, size_t count, BvhBuildResult &bvh)
 {
 	(void)count;
+	// boxes are recomputed from whole triangles: a tree built with spatial splits stays valid (looser) after a refit
 	for (size_t ni = bvh.nodes.size(); ni-- > 0;)
 	{
 		BvhNode4 &n = bvh.nodes[ni];
@@ -443,7 +636,7 @@ void refit_bvh4(const BuildTriangle *tris, size_t count, BvhBuildResult &bvh)
 			{
 				const uint32_t v = uint32_t(~c), first = v >> 2, cnt = (v & 3u) + 1u;
 				for (uint32_t i = first; i < first + cnt; i++)
-					b.grow(tri_box(tris[bvh.tri_order[i]]));
+					b.grow(padded(tri_box(tris[bvh.tri_order[i]])));
 			}
 			else
 			{

@@ -19,17 +19,19 @@ struct BuildTriangle
 struct BvhBuildResult
 {
 	std::vector<BvhNode4> nodes;	   // breadth-first, root = 0
-	std::vector<uint32_t> tri_order;   // leaf-ordered position -> input triangle index
+	std::vector<uint32_t> tri_order;   // leaf-ordered position -> input triangle index (spatial splits may
+									   // reference a triangle from several leaves, so size() >= triangle count)
 	std::vector<uint32_t> node_parent; // for refit: parent index per node (root: 0xffffffff)
 	float sah_cost = 0;
 	int depth = 0;
 	double build_ms = 0;
 };
 
-// Binned-SAH BVH2 (16 bins, 3 axes, leaves <= 4 triangles) built with a task pool over `threads`
-// host threads, collapsed to 4-wide by repeatedly opening the child with the largest area, then laid
-// out breadth-first.  max stack need of a depth-first traversal is 3*depth+1.
-void build_bvh4(const BuildTriangle *tris, size_t count, int threads, BvhBuildResult &out);
+// SAH BVH2 with spatial splits (binned object splits + chopped-binning spatial splits, leaves <= 4
+// triangles) built with a task pool over `threads` host threads, collapsed to 4-wide by repeatedly
+// opening the child with the largest area, then laid out breadth-first.  Max stack need of a
+// depth-first traversal is 3*depth+1.
+void build_bvh4(const BuildTriangle *tris, size_t count, int threads, BvhBuildResult &out, bool spatial_splits = true);
 
 // Recompute all boxes bottom-up for moved vertices with unchanged topology (the reference's refit,
 // bvh_tree.cpp:104-114, top_level_bvh.cpp:46-52).

@@ -132,6 +132,8 @@ struct rfwb200_context
 	std::vector<HostTexture> textures;
 	bool geometry_dirty = true, topology_dirty = true;
 	std::vector<std::pair<int, size_t>> built_layout; // (mesh, tri count) per instance at last build
+	size_t built_tri_count = 0;
+	bool spatial_splits = true;
 
 	// ---- device scene ------------------------------------------------------------------------------
 	DevBuf d_nodes, d_tris, d_shade_tris, d_materials, d_materials_raw, d_uint_tex, d_float_tex, d_tex_desc, d_sky,
@@ -688,14 +690,15 @@ extern "C"
 		for (const HostInstance &in : c->instances)
 			layout.emplace_back(in.mesh, in.mesh >= 0 ? c->meshes[in.mesh].triangles.size() : 0);
 		const bool can_refit = !c->topology_dirty && layout == c->built_layout && !c->bvh.nodes.empty() &&
-							   c->bvh.tri_order.size() == c->build_tris.size();
+							   c->built_tri_count == c->build_tris.size();
 		const auto t0 = std::chrono::steady_clock::now();
 		if (can_refit)
 			refit_bvh4(c->build_tris.data(), c->build_tris.size(), c->bvh);
 		else
 		{
 			const int threads = int(std::max(1u, std::thread::hardware_concurrency()));
-			build_bvh4(c->build_tris.data(), c->build_tris.size(), threads, c->bvh);
+			build_bvh4(c->build_tris.data(), c->build_tris.size(), threads, c->bvh, c->spatial_splits);
+			c->built_tri_count = c->build_tris.size();
 		}
 		c->bvh.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 		if (3 * c->bvh.depth + 1 > TRAVERSAL_STACK)
@@ -743,6 +746,11 @@ extern "C"
 			REQUIRE(n >= 0 && n <= 1700, "smem_nodes must be in [0, 1700] (227 KB of shared memory)");
 			c->rs.smem_nodes = n;
 			c->dims_valid = false;
+		}
+		else if (k == "spatial_splits")
+		{
+			c->spatial_splits = (v == "on" || v == "1");
+			c->geometry_dirty = c->topology_dirty = true; // takes effect at the next update()
 		}
 		else if (k == "fetch_threshold")
 		{
@@ -1145,6 +1153,110 @@ extern "C"
 		CK(cudaMemcpyAsync(origins_out, dO.ptr, P * 16, cudaMemcpyDeviceToHost, st));
 		CK(cudaMemcpyAsync(directions_out, dD.ptr, P * 16, cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
+		return RFWB200_OK;
+	}
+
+	// Host-only self check of the BVH builder (no GPU involved): builds the 4-wide BVH over `n_tris` world-space
+	// triangles (float[9] each) and walks it on the CPU for `n_rays` rays with the kernels' node semantics.
+	int rfwb200_host_bvh_check(const float *tris9, size_t n_tris, int spatial_splits, const float *origins3,
+							   const float *dirs3, size_t n_rays, float *t_out, int32_t *tri_out, uint64_t *nodes_out,
+							   uint64_t *refs_out, int32_t *depth_out, float *sah_out)
+	{
+		REQUIRE(tris9 && origins3 && dirs3 && t_out && tri_out, "bad arguments");
+		std::vector<BuildTriangle> bt(n_tris);
+		for (size_t i = 0; i < n_tris; i++)
+			memcpy(&bt[i], tris9 + 9 * i, 9 * sizeof(float));
+		BvhBuildResult bvh;
+		build_bvh4(bt.data(), n_tris, int(std::max(1u, std::thread::hardware_concurrency())), bvh, spatial_splits != 0);
+		if (nodes_out)
+			*nodes_out = bvh.nodes.size();
+		if (refs_out)
+			*refs_out = bvh.tri_order.size();
+		if (depth_out)
+			*depth_out = bvh.depth;
+		if (sah_out)
+			*sah_out = bvh.sah_cost;
+		REQUIRE(3 * bvh.depth + 2 <= TRAVERSAL_STACK, "BVH deeper than the traversal stack allows");
+		for (size_t r = 0; r < n_rays; r++)
+		{
+			const float *o = origins3 + 3 * r, *d = dirs3 + 3 * r;
+			float id[3], ood[3];
+			for (int a = 0; a < 3; a++)
+			{
+				const float dd = std::fabs(d[a]) > 1e-30f ? d[a] : std::copysign(1e-30f, d[a]);
+				id[a] = 1.0f / dd, ood[a] = o[a] * id[a];
+			}
+			float tmax = 1e34f;
+			int32_t best = -1;
+			int stack[TRAVERSAL_STACK], sp = 0, cur = 0;
+			for (;;)
+			{
+				if (cur >= 0)
+				{
+					const BvhNode4 &n = bvh.nodes[cur];
+					int hit[4], nh = 0;
+					float key[4];
+					for (int k = 0; k < 4; k++)
+					{
+						const float lo[3] = {n.minx[k], n.miny[k], n.minz[k]}, hi[3] = {n.maxx[k], n.maxy[k], n.maxz[k]};
+						float tn = -3e38f, tf = 3e38f;
+						bool nan = false;
+						for (int a = 0; a < 3; a++)
+						{
+							const float t1 = lo[a] * id[a] - ood[a], t2 = hi[a] * id[a] - ood[a];
+							nan |= std::isnan(t1) || std::isnan(t2);
+							tn = std::max(tn, std::min(t1, t2)), tf = std::min(tf, std::max(t1, t2));
+						}
+						if (!nan && tf >= tn && tn < tmax && tf >= 1e-5f)
+							hit[nh] = k, key[nh] = tn, nh++;
+					}
+					for (int i = 0; i < nh; i++) // far to near onto the stack
+						for (int j = i + 1; j < nh; j++)
+							if (key[j] > key[i])
+								std::swap(key[i], key[j]), std::swap(hit[i], hit[j]);
+					if (nh == 0)
+					{
+						if (sp == 0)
+							break;
+						cur = stack[--sp];
+						continue;
+					}
+					for (int i = 0; i + 1 < nh; i++)
+						stack[sp++] = n.child[hit[i]];
+					cur = n.child[hit[nh - 1]];
+				}
+				else
+				{
+					const uint32_t v = uint32_t(~cur), first = v >> 2, cnt = (v & 3u) + 1u;
+					for (uint32_t i = first; i < first + cnt && i < bvh.tri_order.size(); i++)
+					{
+						const BuildTriangle &t = bt[bvh.tri_order[i]];
+						const float e1[3] = {t.v1[0] - t.v0[0], t.v1[1] - t.v0[1], t.v1[2] - t.v0[2]};
+						const float e2[3] = {t.v2[0] - t.v0[0], t.v2[1] - t.v0[1], t.v2[2] - t.v0[2]};
+						const float h[3] = {d[1] * e2[2] - e2[1] * d[2], d[2] * e2[0] - e2[2] * d[0], d[0] * e2[1] - e2[0] * d[1]};
+						const float det = e1[0] * h[0] + e1[1] * h[1] + e1[2] * h[2];
+						if (det > -1e-12f && det < 1e-12f)
+							continue;
+						const float f = 1.0f / det;
+						const float s[3] = {o[0] - t.v0[0], o[1] - t.v0[1], o[2] - t.v0[2]};
+						const float u = f * (s[0] * h[0] + s[1] * h[1] + s[2] * h[2]);
+						if (u < 0.0f || u > 1.0f)
+							continue;
+						const float q[3] = {s[1] * e1[2] - e1[1] * s[2], s[2] * e1[0] - e1[2] * s[0], s[0] * e1[1] - e1[0] * s[1]};
+						const float vv = f * (d[0] * q[0] + d[1] * q[1] + d[2] * q[2]);
+						if (vv < 0.0f || u + vv > 1.0f)
+							continue;
+						const float tt = f * (e2[0] * q[0] + e2[1] * q[1] + e2[2] * q[2]);
+						if (tt > 1e-5f && tt < tmax)
+							tmax = tt, best = int32_t(bvh.tri_order[i]);
+					}
+					if (sp == 0)
+						break;
+					cur = stack[--sp];
+				}
+			}
+			t_out[r] = tmax, tri_out[r] = best;
+		}
 		return RFWB200_OK;
 	}
 

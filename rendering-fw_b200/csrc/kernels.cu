@@ -390,8 +390,11 @@ __device__ __forceinline__ void generate_emode(const FrameParams &fp, const Shar
 
 extern __shared__ __align__(128) unsigned char g_dyn_smem[];
 
+#ifndef TRACE_MINB
+#define TRACE_MINB 4 // resident CTAs per SM the register allocation is sized for (measured)
+#endif
 template <bool PRIMARY>
-__global__ void __launch_bounds__(256) k_wavefront_trace(const SceneView sc, const ShardView sh, const WavefrontView wf,
+__global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const SceneView sc, const ShardView sh, const WavefrontView wf,
 															const RenderSettings rs, const uint32_t sample_in_frame,
 															const uint32_t depth)
 {

@@ -20,7 +20,7 @@ import numpy as np
 
 PKG_DIR = Path(__file__).resolve().parent.parent
 REPO_DIR = PKG_DIR.parent
-PRODUCT_LIB = PKG_DIR / "librfwb200.so"
+PRODUCT_LIB = Path(os.environ.get("RFWB200_LIB", PKG_DIR / "librfwb200.so"))  # override: tuning experiments only
 ORACLE_LIB = REPO_DIR / "oracle" / "librfworacle.so"
 ORACLE_FAST_LIB = REPO_DIR / "oracle" / "librfworacle_fast.so"
 BLUENOISE_BIN = PKG_DIR / "data" / "bluenoise_256spp.bin"

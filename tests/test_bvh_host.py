@@ -1,0 +1,108 @@
+"""Host-side checks of the product's BVH builder (csrc/bvh_build.cpp) through rfwb200_host_bvh_check — no GPU:
+the flattened 4-wide BVH, with and without spatial splits, must return exactly the brute-force closest hits."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import rfwb200 as R
+import scenes as S
+
+
+def flatten(sc):
+    out = []
+    for mi, M in sc.instances:
+        m = sc.meshes[mi]
+        v = m.vertices[:, :3].astype(np.float64)
+        idx = m.indices if m.indices is not None else np.arange(len(m.triangles) * 3).reshape(-1, 3)
+        out.append((v[idx] @ np.asarray(M)[:3, :3].T + np.asarray(M)[:3, 3]).astype(np.float32))
+    return np.ascontiguousarray(np.concatenate(out).reshape(-1, 9))
+
+
+def host_check(lib, tris, o, d, spatial):
+    f = lib.fn("host_bvh_check", C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p])
+    t, tri = np.zeros(len(o), np.float32), np.zeros(len(o), np.int32)
+    nodes, refs, depth, sah = C.c_uint64(), C.c_uint64(), C.c_int32(), C.c_float()
+    o, d = np.ascontiguousarray(o, np.float32), np.ascontiguousarray(d, np.float32)
+    rc = f(tris.ctypes.data, len(tris), int(spatial), o.ctypes.data, d.ctypes.data, len(o), t.ctypes.data, tri.ctypes.data,
+           C.byref(nodes), C.byref(refs), C.byref(depth), C.byref(sah))
+    assert rc == 0, lib.last_error()
+    return t, tri, {"nodes": nodes.value, "refs": refs.value, "depth": depth.value, "sah": sah.value}
+
+
+def brute(tris, o, d):
+    P = tris.reshape(-1, 3, 3).astype(np.float64)
+    e1, e2 = P[:, 1] - P[:, 0], P[:, 2] - P[:, 0]
+    bt = np.full(len(o), 1e34)
+    for r in range(len(o)):
+        oo, dd = o[r].astype(np.float64), d[r].astype(np.float64)
+        h = np.cross(dd, e2)
+        a = np.einsum("ij,ij->i", e1, h)
+        ok = np.abs(a) > 1e-12
+        f = np.where(ok, 1.0 / np.where(ok, a, 1), 0)
+        s = oo - P[:, 0]
+        u = f * np.einsum("ij,ij->i", s, h)
+        q = np.cross(s, e1)
+        v = f * (q @ dd)
+        t = f * np.einsum("ij,ij->i", e2, q)
+        hit = ok & (u >= 0) & (u <= 1) & (v >= 0) & (u + v <= 1) & (t > 1e-5)
+        if hit.any():
+            bt[r] = t[hit].min()
+    return bt
+
+
+def rays(n, seed, scale):
+    rng = np.random.default_rng(seed)
+    o = (rng.uniform(-1, 1, size=(n, 3)) * scale).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    d[:5, 0] = 0  # axis-parallel rays
+    d[:5] /= np.linalg.norm(d[:5], axis=1, keepdims=True)
+    return o, d
+
+
+@pytest.mark.parametrize("spatial", [False, True])
+@pytest.mark.parametrize("scene", ["soup", "cornell", "atrium"])
+def test_builder_matches_brute_force(product_lib, scene, spatial):
+    sc = {"soup": lambda: S.feature_soup(1500), "cornell": lambda: S.cornell_box(unit_scale=True), "atrium": lambda: S.atrium(6000)}[scene]()
+    tris = flatten(sc)
+    ext = float(np.abs(tris).max())
+    o, d = rays(300, 3, ext * 0.7)
+    t, tri, info = host_check(product_lib, tris, o, d, spatial)
+    bt = brute(tris, o, d)
+    hit = bt < 1e33
+    assert np.array_equal(t < 1e33, hit)
+    assert np.allclose(t[hit], bt[hit], rtol=2e-4, atol=1e-5 * ext)
+    assert info["refs"] >= len(tris) and info["refs"] <= 1.7 * len(tris) + 64
+    assert 3 * info["depth"] + 2 <= 96
+    if not spatial:
+        assert info["refs"] == len(tris)
+
+
+def test_spatial_splits_lower_the_sah_cost_on_long_thin_triangles(product_lib):
+    """Sponza-like failure case for object splits: long diagonal slivers crossing many small triangles"""
+    rng = np.random.default_rng(1)
+    small = rng.uniform(-10, 10, size=(4000, 1, 3)) + rng.normal(0, 0.05, size=(4000, 3, 3))
+    a = rng.uniform(-10, 10, size=(60, 3))
+    b = rng.uniform(-10, 10, size=(60, 3))
+    big = np.stack([a, b, b + rng.normal(0, 0.05, size=(60, 3))], axis=1)
+    tris = np.ascontiguousarray(np.concatenate([small, big]).reshape(-1, 9).astype(np.float32))
+    o, d = rays(50, 2, 8.0)
+    _, _, plain = host_check(product_lib, tris, o, d, False)
+    t, _, sbvh = host_check(product_lib, tris, o, d, True)
+    assert sbvh["sah"] < 0.9 * plain["sah"]
+    assert sbvh["refs"] > len(tris)
+    bt = brute(tris, o, d)
+    assert np.allclose(t[bt < 1e33], bt[bt < 1e33], rtol=2e-4, atol=1e-4)
+
+
+def test_empty_and_single_triangle(product_lib):
+    o, d = rays(8, 1, 1.0)
+    t, tri, info = host_check(product_lib, np.zeros((0, 9), np.float32), o, d, True)
+    assert (t > 1e33).all() and info["nodes"] == 1
+    one = np.array([[-1, -1, 2, 1, -1, 2, 0, 1, 2]], np.float32)
+    o = np.zeros((1, 3), np.float32)
+    d = np.array([[0, 0, 1]], np.float32)
+    t, tri, info = host_check(product_lib, one, o, d, True)
+    assert tri[0] == 0 and abs(t[0] - 2) < 1e-5
