@@ -1271,7 +1271,10 @@ __device__ V3 RandomPointOnLight(const SceneView &sc, float r0, float r1, V3 I, 
 // (accumulate, connect-queue entry, extension-queue entry) are committed at one converged point
 // with warp-aggregated slot allocation.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_shade(const SceneView sc, const ShardView sh, const WavefrontView wf,
+#ifndef SHADE_MINB
+#define SHADE_MINB 6 // 80 registers: measured 4.94 ms/frame vs 5.67 at 4 and 4.92 at 8 (spilling)
+#endif
+__global__ void __launch_bounds__(128, SHADE_MINB) k_shade(const SceneView sc, const ShardView sh, const WavefrontView wf,
 											  const RenderSettings rs, const uint32_t sample_in_frame,
 											  const uint32_t pathLength)
 {

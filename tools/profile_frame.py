@@ -28,6 +28,7 @@ if a.smem_nodes is not None:
 for kv in a.set:
     k, v = kv.split("=")
     ctx.set_setting(k, v)
+ctx.update()
 if a.timing:
     ctx.set_setting("timing", "on")
 cam = sc.camera(a.width, a.height)
