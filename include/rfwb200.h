@@ -242,7 +242,7 @@ RFWB200_API int rfwb200_update(rfwb200_context *ctx);
 /* replaces RenderContext::set_setting (context.h:107). Keys: "spp" (samples per render_frame,
  * default 1), "mode" ("pt" wavefront path tracer | "embree" = image model of the EmbreeRT
  * backend), "max_path_length" (default 2 = settings.h:5), "clamp" (default 10, camera.h:36),
- * "smem_nodes" (BVH nodes staged in shared memory per CTA), "spatial_splits" (on|off), "fetch_threshold", "timing" (on|off: per-stage CUDA-event
+ * "smem_nodes" (BVH nodes staged in shared memory per CTA), "spatial_splits" (on|off), "sample_lanes" (1-4 concurrent samples), "fetch_threshold", "timing" (on|off: per-stage CUDA-event
  * times in get_stats), "survival_scale" (on|off, the 1/p throughput scale of Kernels.cu:783). */
 RFWB200_API int rfwb200_set_setting(rfwb200_context *ctx, const char *key, const char *value);
 /* replaces RenderContext::get_settings (context.h:106): writes a '\n'-separated "key=v1|v2" list */
@@ -304,13 +304,23 @@ RFWB200_API uint64_t rfwb200_launch_count(const rfwb200_context *ctx);
 RFWB200_API int rfwb200_get_bvh_info(const rfwb200_context *ctx, uint64_t *nodes, uint64_t *triangles, float *sah_cost,
 									 float *build_ms);
 
+/* Debug / test hooks: copy a wavefront plane (float4 elements) or the per-depth counters (8 uint32 per slot:
+ * ext, shadow, trace_cursor, shade_cursor, acc, shadow_traced, -, -) of the last frame to the host. */
+RFWB200_API int rfwb200_debug_read_plane(rfwb200_context *ctx, int which, float *host, size_t n);
+RFWB200_API int rfwb200_debug_read_counters(rfwb200_context *ctx, uint32_t *out8_per_depth, size_t depth_slots);
+/* host == NULL arms a per-warp timeline {start ns, end ns, rays, smid} for trace launches at `depth`; a second call
+ * with a host buffer reads it back and disarms it (tools/diag_timeline.py). */
+RFWB200_API int rfwb200_debug_trace_timeline(rfwb200_context *ctx, int depth, unsigned long long *host, size_t max_warps,
+											 size_t *n_warps);
+
 /* Host-only self check of the BVH builder (runs without a GPU): builds the flattened 4-wide BVH over n_tris
  * world-space triangles (float[9] each) and walks it on the CPU for n_rays rays (float[3] origins / directions)
  * with the node semantics of the kernels; reports closest t (1e34 = miss) and triangle index per ray plus tree
  * statistics.  Counterpart in the reference: MBVHNode::validate (RFW/system/bvh/src/mbvh_node.cpp:390-423). */
 RFWB200_API int rfwb200_host_bvh_check(const float *tris9, size_t n_tris, int spatial_splits, const float *origins3,
 									   const float *dirs3, size_t n_rays, float *t_out, int32_t *tri_out, uint64_t *nodes_out,
-									   uint64_t *refs_out, int32_t *depth_out, float *sah_out);
+									   uint64_t *refs_out, int32_t *depth_out, float *sah_out,
+									   uint32_t *visits_out /* optional: node visits, triangle tests per ray */);
 
 #ifdef __cplusplus
 } /* extern "C" */

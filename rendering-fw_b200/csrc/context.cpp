@@ -144,12 +144,27 @@ struct rfwb200_context
 	uint64_t flat_tri_count = 0;
 
 	// ---- wavefront state -----------------------------------------------------------------------------
+	DevBuf d_debug;
 	DevBuf d_O[2], d_D[2], d_T[2], d_hit, d_sO, d_sD, d_sE, d_acc, d_fb, d_counters, d_probe, d_frame, d_scratch_cursor;
 	WavefrontView wf{};
 	uint32_t counters_capacity_spp = 0;
+	// Sample lanes: sample s of a frame runs on lane s % n_lanes.  Lane 0 is the caller's stream and the buffers above;
+	// every further lane owns a CUDA stream and a full set of wavefront planes + accumulator, so the tail of one
+	// sample's launch (a single long ray can keep one warp busy for 200+ us, profiles/r01) overlaps with the next
+	// sample's work.  finalize sums the lane accumulators in lane order, so the result is deterministic.
+	struct Lane
+	{
+		DevBuf O[2], D[2], T[2], hit, sO, sD, sE, acc;
+		WavefrontView wf{};
+		cudaStream_t stream = nullptr;
+		cudaEvent_t done = nullptr;
+	};
+	std::vector<std::unique_ptr<Lane>> lanes; // lanes 1..n_lanes-1
+	int n_lanes = 4; // measured on Sponza 1080p 8 spp: 17.20 ms (1 lane), 15.84 (2), 15.76 (3), 15.68 (4)
+	cudaEvent_t ev_fork = nullptr;
 
 	// ---- settings / state ------------------------------------------------------------------------------
-	RenderSettings rs{2, 10.0f, 1e-5f, 1, 0, 16}; // smem_nodes 0: measured fastest on B200 (DESIGN.md "staging")
+	RenderSettings rs{2, 10.0f, 1e-5f, 1, 0, 16, nullptr, -1}; // smem_nodes 0: measured fastest on B200 (DESIGN.md "staging")
 	int spp = 1;
 	bool mode_pt = true;
 	LaunchDims dims{};
@@ -239,6 +254,39 @@ int alloc_wavefront(Ctx *c)
 	w.framebuffer = c->d_fb.as<float4>();
 	w.probe = c->d_probe.as<ProbeResult>();
 	w.frame = c->d_frame.as<FrameParams>();
+	w.n_acc_extra = 0;
+	while (int(c->lanes.size()) < c->n_lanes - 1)
+	{
+		std::unique_ptr<Ctx::Lane> l(new Ctx::Lane());
+		CK(cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking));
+		CK(cudaEventCreateWithFlags(&l->done, cudaEventDisableTiming));
+		c->lanes.push_back(std::move(l));
+	}
+	if (!c->ev_fork)
+		CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+	for (int li = 0; li < c->n_lanes - 1; li++)
+	{
+		Ctx::Lane &l = *c->lanes[li];
+		for (int i = 0; i < 2; i++)
+		{
+			CK(l.O[i].reserve(plane));
+			CK(l.D[i].reserve(plane));
+			CK(l.T[i].reserve(plane));
+		}
+		CK(l.hit.reserve(plane));
+		CK(l.sO.reserve(plane));
+		CK(l.sD.reserve(plane));
+		CK(l.sE.reserve(plane));
+		CK(l.acc.reserve(plane));
+		l.wf = w;
+		for (int i = 0; i < 2; i++)
+			l.wf.O[i] = l.O[i].as<float4>(), l.wf.D[i] = l.D[i].as<float4>(), l.wf.T[i] = l.T[i].as<float4>();
+		l.wf.hit = l.hit.as<float4>();
+		l.wf.sO = l.sO.as<float4>(), l.wf.sD = l.sD.as<float4>(), l.wf.sE = l.sE.as<float4>();
+		l.wf.accumulator = l.acc.as<float4>();
+		w.acc_extra[li] = l.acc.as<float4>();
+		w.n_acc_extra = li + 1;
+	}
 	return RFWB200_OK;
 }
 
@@ -250,6 +298,8 @@ int ensure_counters(Ctx *c, uint32_t spp)
 		c->counters_capacity_spp = spp;
 	}
 	c->wf.counters = c->d_counters.as<DepthCounters>();
+	for (auto &l : c->lanes)
+		l->wf.counters = c->wf.counters;
 	return RFWB200_OK;
 }
 
@@ -465,6 +515,10 @@ extern "C"
 			cudaEventDestroy(c->ev_end);
 		for (auto &e : c->stage_events)
 			cudaEventDestroy(e.a), cudaEventDestroy(e.b);
+		for (auto &l : c->lanes)
+			cudaStreamDestroy(l->stream), cudaEventDestroy(l->done);
+		if (c->ev_fork)
+			cudaEventDestroy(c->ev_fork);
 		delete c;
 		return RFWB200_OK;
 	}
@@ -481,6 +535,8 @@ extern "C"
 		if (int r = alloc_wavefront(c))
 			return r;
 		CK(cudaMemsetAsync(c->d_acc.ptr, 0, c->d_acc.bytes, c->stream));
+		for (int li = 0; li < c->n_lanes - 1; li++)
+			CK(cudaMemsetAsync(c->lanes[li]->acc.ptr, 0, c->lanes[li]->acc.bytes, c->stream));
 		CK(cudaMemsetAsync(c->d_fb.ptr, 0, c->d_fb.bytes, c->stream));
 		c->sample_index = 0;
 		c->initialised = true;
@@ -747,6 +803,23 @@ extern "C"
 			c->rs.smem_nodes = n;
 			c->dims_valid = false;
 		}
+		else if (k == "sample_lanes")
+		{
+			const int n = atoi(v.c_str());
+			REQUIRE(n >= 1 && n <= 4, "sample_lanes must be in [1, 4]");
+			if (n != c->n_lanes)
+			{
+				CK(cudaDeviceSynchronize());
+				c->n_lanes = n;
+				while (int(c->lanes.size()) > n - 1)
+				{
+					cudaStreamDestroy(c->lanes.back()->stream), cudaEventDestroy(c->lanes.back()->done);
+					c->lanes.pop_back();
+				}
+				if (c->initialised)
+					return rfwb200_init(c, c->width, c->height);
+			}
+		}
 		else if (k == "spatial_splits")
 		{
 			c->spatial_splits = (v == "on" || v == "1");
@@ -795,6 +868,8 @@ extern "C"
 		if (status == RFWB200_RESET)
 		{
 			CK(cudaMemsetAsync(c->d_acc.ptr, 0, size_t(c->shard.local_pixels) * sizeof(float4), st));
+			for (int li = 0; li < c->n_lanes - 1; li++)
+				CK(cudaMemsetAsync(c->lanes[li]->acc.ptr, 0, size_t(c->shard.local_pixels) * sizeof(float4), st));
 			c->sample_index = 0;
 		}
 		CK(cudaMemsetAsync(c->d_counters.ptr, 0, size_t(spp) * MAX_DEPTH_SLOTS * sizeof(DepthCounters), st));
@@ -810,30 +885,49 @@ extern "C"
 		if (c->mode_pt)
 		{
 			const uint32_t maxd = uint32_t(c->rs.max_path_length);
+			// per-stage timing wants undisturbed kernels: it runs every sample on lane 0
+			const int lanes = c->timing ? 1 : c->n_lanes;
+			if (lanes > 1)
+			{
+				CK(cudaEventRecord(c->ev_fork, st)); // lanes start after the frame's clears / parameter upload
+				for (int li = 0; li < lanes - 1; li++)
+					CK(cudaStreamWaitEvent(c->lanes[li]->stream, c->ev_fork, 0));
+			}
 			for (uint32_t s = 0; s < spp; s++)
 			{
+				// the lane is a function of the GLOBAL sample index, so Converge sequences and one multi-spp call
+				// accumulate every sample into the same lane in the same order (bit-identical frames)
+				const int lane = int((c->sample_index + s) % uint32_t(lanes));
+				const WavefrontView &wf = lane == 0 ? c->wf : c->lanes[lane - 1]->wf;
+				cudaStream_t ls = lane == 0 ? st : c->lanes[lane - 1]->stream;
 				{
 					StageTimer t(c, 0);
-					CK(launch_primary(c->scene, c->shard, c->wf, c->rs, s, c->dims, st));
+					CK(launch_primary(c->scene, c->shard, wf, c->rs, s, c->dims, ls));
 				}
 				{
 					StageTimer t(c, 3);
-					CK(launch_shade(c->scene, c->shard, c->wf, c->rs, s, 0, c->dims, st));
+					CK(launch_shade(c->scene, c->shard, wf, c->rs, s, 0, c->dims, ls));
 				}
 				c->launches += 2;
 				for (uint32_t d = 1; d <= maxd; d++)
 				{
 					{
 						StageTimer t(c, d == 1 ? 1 : 2);
-						CK(launch_trace(c->scene, c->shard, c->wf, c->rs, s, d, c->dims, st));
+						CK(launch_trace(c->scene, c->shard, wf, c->rs, s, d, c->dims, ls));
 					}
 					{
 						StageTimer t(c, 3);
-						CK(launch_shade(c->scene, c->shard, c->wf, c->rs, s, d, c->dims, st));
+						CK(launch_shade(c->scene, c->shard, wf, c->rs, s, d, c->dims, ls));
 					}
 					c->launches += 2;
 				}
 			}
+			if (lanes > 1)
+				for (int li = 0; li < lanes - 1; li++)
+				{
+					CK(cudaEventRecord(c->lanes[li]->done, c->lanes[li]->stream));
+					CK(cudaStreamWaitEvent(st, c->lanes[li]->done, 0)); // join before finalize
+				}
 			c->sample_index += spp;
 			{
 				StageTimer t(c, 4);
@@ -1156,11 +1250,61 @@ extern "C"
 		return RFWB200_OK;
 	}
 
+	// Debug/test hook: copy one wavefront plane of the last frame to the host.  which: 0/1 = O[0]/O[1], 2/3 = D[0]/D[1],
+	// 4/5 = T[0]/T[1], 6 = hit, 7/8/9 = connect O/D/E, 10 = accumulator; n float4 elements.
+	int rfwb200_debug_read_plane(rfwb200_context *c, int which, float *host, size_t n)
+	{
+		REQUIRE(c && host, "bad arguments");
+		if (int r = ensure_device(c))
+			return r;
+		const DevBuf *planes[11] = {&c->d_O[0], &c->d_O[1], &c->d_D[0], &c->d_D[1], &c->d_T[0], &c->d_T[1],
+									&c->d_hit,	&c->d_sO,	&c->d_sD,	&c->d_sE,	&c->d_acc};
+		REQUIRE(which >= 0 && which < 11, "bad plane");
+		REQUIRE(n * 16 <= planes[which]->bytes, "plane smaller than requested");
+		CK(cudaMemcpyAsync(host, planes[which]->ptr, n * 16, cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+		return RFWB200_OK;
+	}
+	// Debug hook: per-warp {start ns, end ns, rays, smid} of the trace launch at `depth` (sample 0 of the next frames).
+	int rfwb200_debug_trace_timeline(rfwb200_context *c, int depth, unsigned long long *host, size_t max_warps, size_t *n_warps)
+	{
+		REQUIRE(c != nullptr, "context is null");
+		if (int r = ensure_device(c))
+			return r;
+		if (int r = ensure_dims(c))
+			return r;
+		const size_t warps = size_t(c->dims.trace_grid) * (c->dims.trace_block / 32);
+		if (n_warps)
+			*n_warps = warps;
+		if (!host)
+		{
+			CK(c->d_debug.reserve(warps * 32));
+			CK(cudaMemset(c->d_debug.ptr, 0, warps * 32));
+			c->rs.debug = static_cast<unsigned long long *>(c->d_debug.ptr), c->rs.debug_depth = depth;
+			return RFWB200_OK;
+		}
+		REQUIRE(max_warps >= warps && c->d_debug.ptr, "buffer too small or timeline not armed");
+		CK(cudaStreamSynchronize(c->stream));
+		CK(cudaMemcpy(host, c->d_debug.ptr, warps * 32, cudaMemcpyDeviceToHost));
+		c->rs.debug = nullptr, c->rs.debug_depth = -1;
+		return RFWB200_OK;
+	}
+	int rfwb200_debug_read_counters(rfwb200_context *c, uint32_t *out8_per_depth, size_t depth_slots)
+	{
+		REQUIRE(c && out8_per_depth, "bad arguments");
+		if (int r = ensure_device(c))
+			return r;
+		REQUIRE(depth_slots <= size_t(c->counters_capacity_spp) * MAX_DEPTH_SLOTS, "more slots than allocated");
+		CK(cudaMemcpyAsync(out8_per_depth, c->d_counters.ptr, depth_slots * sizeof(DepthCounters), cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+		return RFWB200_OK;
+	}
+
 	// Host-only self check of the BVH builder (no GPU involved): builds the 4-wide BVH over `n_tris` world-space
 	// triangles (float[9] each) and walks it on the CPU for `n_rays` rays with the kernels' node semantics.
 	int rfwb200_host_bvh_check(const float *tris9, size_t n_tris, int spatial_splits, const float *origins3,
 							   const float *dirs3, size_t n_rays, float *t_out, int32_t *tri_out, uint64_t *nodes_out,
-							   uint64_t *refs_out, int32_t *depth_out, float *sah_out)
+							   uint64_t *refs_out, int32_t *depth_out, float *sah_out, uint32_t *visits_out)
 	{
 		REQUIRE(tris9 && origins3 && dirs3 && t_out && tri_out, "bad arguments");
 		std::vector<BuildTriangle> bt(n_tris);
@@ -1189,10 +1333,12 @@ extern "C"
 			float tmax = 1e34f;
 			int32_t best = -1;
 			int stack[TRAVERSAL_STACK], sp = 0, cur = 0;
+			uint32_t node_visits = 0, tri_tests = 0;
 			for (;;)
 			{
 				if (cur >= 0)
 				{
+					node_visits++;
 					const BvhNode4 &n = bvh.nodes[cur];
 					int hit[4], nh = 0;
 					float key[4];
@@ -1230,6 +1376,7 @@ extern "C"
 					const uint32_t v = uint32_t(~cur), first = v >> 2, cnt = (v & 3u) + 1u;
 					for (uint32_t i = first; i < first + cnt && i < bvh.tri_order.size(); i++)
 					{
+						tri_tests++;
 						const BuildTriangle &t = bt[bvh.tri_order[i]];
 						const float e1[3] = {t.v1[0] - t.v0[0], t.v1[1] - t.v0[1], t.v1[2] - t.v0[2]};
 						const float e2[3] = {t.v2[0] - t.v0[0], t.v2[1] - t.v0[1], t.v2[2] - t.v0[2]};
@@ -1256,6 +1403,8 @@ extern "C"
 				}
 			}
 			t_out[r] = tmax, tri_out[r] = best;
+			if (visits_out)
+				visits_out[2 * r] = node_visits, visits_out[2 * r + 1] = tri_tests;
 		}
 		return RFWB200_OK;
 	}

@@ -125,7 +125,9 @@ struct WavefrontView
 	float4 *O[2], *D[2], *T[2]; // ping-pong planes: origin|pathIdx<<8|flags, direction|packed normal, throughput|pdf
 	float4 *hit;				// bits(u16|v16<<16), bits(shade_idx), bits(prim or -1), t
 	float4 *sO, *sD, *sE;		// connect queue: origin, direction|tmax, contribution|bits(local pixel)
-	float4 *accumulator;		// per local pixel
+	float4 *accumulator;		// per local pixel (of this sample lane)
+	float4 *acc_extra[3];		// accumulators of the other sample lanes, summed by finalize in fixed order
+	int n_acc_extra;
 	float4 *framebuffer;		// finalised
 	DepthCounters *counters;	// [spp][MAX_DEPTH_SLOTS]
 	ProbeResult *probe;
@@ -140,6 +142,8 @@ struct RenderSettings
 	int survival_scale;
 	int smem_nodes;
 	int fetch_threshold; // idle lanes per warp that trigger a refill from the work cursor
+	unsigned long long *debug; // optional per-warp {start ns, end ns, rays} records of one trace launch (tools/diag)
+	int debug_depth;
 };
 
 } // namespace rfwb200

@@ -431,6 +431,11 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 		sampleIndex = fp.sample_base + sample_in_frame;
 	}
 
+	unsigned long long dbg_t0 = 0, dbg_rays = 0;
+	const bool dbg = !PRIMARY && rs.debug != nullptr && int(depth) == rs.debug_depth;
+	if (dbg)
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+
 	// per-lane ray state
 	bool alive = false;
 	bool shadow = false;
@@ -499,6 +504,7 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 					}
 					if (valid)
 					{
+						dbg_rays++;
 						const float tiny = 1e-30f;
 						idx = 1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));
 						idy = 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));
@@ -637,6 +643,19 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 				wf.accumulator[pixel] = a;
 				acc_count++;
 			}
+		}
+	}
+	if (dbg)
+	{
+		unsigned long long t1;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+		const unsigned long long n = __reduce_add_sync(0xffffffffu, uint32_t(dbg_rays));
+		if (lane == 0)
+		{
+			unsigned long long *rec = rs.debug + size_t(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4;
+			uint32_t smid;
+			asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+			rec[0] = dbg_t0, rec[1] = t1, rec[2] = n, rec[3] = smid;
 		}
 	}
 	if (!PRIMARY)
@@ -1546,6 +1565,11 @@ __global__ void k_finalize(const ShardView sh, const WavefrontView wf, const flo
 	if (j >= sh.local_pixels)
 		return;
 	float4 a = wf.accumulator[j];
+	for (int k = 0; k < wf.n_acc_extra; k++) // sample lanes: fixed summation order keeps the frame deterministic
+	{
+		const float4 b = wf.acc_extra[k][j];
+		a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+	}
 	a.x *= scale, a.y *= scale, a.z *= scale, a.w *= scale;
 	if (sh.world == 1)
 	{

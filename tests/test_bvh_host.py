@@ -21,14 +21,15 @@ def flatten(sc):
 
 def host_check(lib, tris, o, d, spatial):
     f = lib.fn("host_bvh_check", C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
-                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p])
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p])
     t, tri = np.zeros(len(o), np.float32), np.zeros(len(o), np.int32)
     nodes, refs, depth, sah = C.c_uint64(), C.c_uint64(), C.c_int32(), C.c_float()
+    visits = np.zeros((len(o), 2), np.uint32)
     o, d = np.ascontiguousarray(o, np.float32), np.ascontiguousarray(d, np.float32)
     rc = f(tris.ctypes.data, len(tris), int(spatial), o.ctypes.data, d.ctypes.data, len(o), t.ctypes.data, tri.ctypes.data,
-           C.byref(nodes), C.byref(refs), C.byref(depth), C.byref(sah))
+           C.byref(nodes), C.byref(refs), C.byref(depth), C.byref(sah), visits.ctypes.data)
     assert rc == 0, lib.last_error()
-    return t, tri, {"nodes": nodes.value, "refs": refs.value, "depth": depth.value, "sah": sah.value}
+    return t, tri, {"nodes": nodes.value, "refs": refs.value, "depth": depth.value, "sah": sah.value, "visits": visits}
 
 
 def brute(tris, o, d):

@@ -36,4 +36,4 @@ for _ in range(a.frames):
     ctx.render_frame(cam, R.RESET)
 ctx.synchronize()
 st = ctx.get_stats()
-print("frame ms %.3f primary %.3f trace %.3f shade %.3f" % (st.render_time, st.primary_time, st.secondary_time + st.deep_time, st.shade_time), a.set)
+print("frame ms %.3f primary %.3f trace %.3f (d1 %.3f d2+ %.3f) shade %.3f" % (st.render_time, st.primary_time, st.secondary_time + st.deep_time, st.secondary_time, st.deep_time, st.shade_time), a.set)
