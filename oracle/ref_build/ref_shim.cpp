@@ -1,7 +1,7 @@
 // ref_shim.cpp — compiles the REFERENCE's own shading / intersection headers, where they lie under
 // /root/reference, into oracle/_ref/librfwref.so so that tests can pin the oracle's restatement on the real
 // reference arithmetic.  TEST INFRASTRUCTURE.  No reference source is copied: the headers are #included from
-// their original location; what is ours is the glm / CUDA stand-in under shim/ and the C exports below.
+// their original location; what is ours is the glm / CUDA stand-in under /shims and the C exports below.
 //
 // Reference code exercised:
 //   RFW/system/context/rfw/bsdf/{tools,compat,disney}.h       (EvaluateBSDF, SampleBSDF, PackNormal, WangHash, ...)
