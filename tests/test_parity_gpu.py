@@ -309,3 +309,66 @@ def test_error_codes(product_lib):
     with pytest.raises(R.Rfwb200Error):
         ctx.set_shard(3, 2)
     assert "mesh" in product_lib.last_error() or "rank" in product_lib.last_error()
+
+
+# ---- the headline scene ----------------------------------------------------------------------------------------
+def test_sponza_config2_primary_hits_and_statistics(product_lib, oracle_lib):
+    """BASELINE.json configs[1] on the real asset (when baked; else the procedural stand-in), reduced resolution:
+    per-ray parity of the primary hits, and — because the reference's fixed 1e-5 epsilons make secondary rays
+    self-intersect pseudo-randomly at Sponza scale (DESIGN.md 'Epsilons') — statistical parity of the 16-spp image."""
+    W, H = 240, 136
+    (g, sc), (o, _) = make_pair(product_lib, oracle_lib, S.sponza_or_standin, W, H, spp=16)
+    cam = sc.camera(W, H)
+    origins, dirs = o.generate_primary(cam, 0)
+    hg, ho = g.trace_closest(origins, dirs), o.trace_closest(origins, dirs)
+    assert (ho["prim_id"] >= 0).mean() > 0.9
+    _check_hits(g, o, origins, dirs, hg, ho)
+    g.render_frame(cam, R.RESET), o.render_frame(cam, R.RESET)
+    a, b = g.read_image(), o.read_image()
+    assert np.isfinite(a).all()
+    # image statistics: global mean within 1 %; 8x8 block means (1024 samples each) within 15 % on >= 97 % of blocks.
+    # A flipped self-intersection changes one sample by up to the clamp value (10) against a block mean of ~4, i.e.
+    # sigma(block mean) ~ 5 % when a third of the connect rays flip independently on the two sides: 15 % = 3 sigma.
+    assert abs(a[..., :3].mean() - b[..., :3].mean()) <= 0.01 * b[..., :3].mean()
+    blk = lambda x: x[: H // 8 * 8, : W // 8 * 8, :3].reshape(H // 8, 8, W // 8, 8, 3).mean(axis=(1, 3, 4))
+    ba, bb = blk(a), blk(b)
+    assert (np.abs(ba - bb) <= 0.15 * bb + 0.02).mean() >= 0.97
+    cg, co = g.get_frame_counters().as_dict(), o.get_frame_counters().as_dict()
+    for k in ("n_ext", "n_shade", "n_ext_out", "n_nee"):
+        assert abs(cg[k] - co[k]) <= 0.01 * co[k], (k, cg[k], co[k])
+
+
+def test_config5_lights_sharded_4k_tile_layout(product_lib):
+    """BASELINE.json configs[4] ingredients at reduced size: area + point + directional lights, 16 spp, 8 shards with the
+    32x8 tile layout of a 3840x2160 frame (here 480x270 so the test stays small); shards assemble bit-exactly."""
+    W, H, world = 480, 270, 8
+
+    def scene():
+        sc = S.cornell_box(unit_scale=True)
+        pl = np.zeros(1, R.POINT_LIGHT_DTYPE)
+        pl["position"], pl["radiance"] = (1.0, 4.5, 1.0), (2.0, 2.0, 2.0)
+        pl["energy"] = np.linalg.norm(pl["radiance"][0])
+        dl = np.zeros(1, R.DIR_LIGHT_DTYPE)
+        d = np.array([-0.3, -1.0, 0.2])
+        dl["direction"], dl["radiance"] = d / np.linalg.norm(d), (3.0, 3.0, 3.0)
+        dl["energy"] = np.linalg.norm(dl["radiance"][0])
+        sc.point_lights, sc.dir_lights = pl, dl
+        return sc
+
+    full = R.RenderContext(product_lib)
+    S.upload(full, scene(), W, H)
+    full.set_setting("spp", 16)
+    cam = scene().camera(W, H)
+    full.render_frame(cam, R.RESET)
+    ref = full.read_image().copy()
+    shards = []
+    for r in range(world):
+        ctx = R.RenderContext(product_lib)
+        ctx.set_shard(r, world, 32, 8)
+        S.upload(ctx, scene(), W, H)
+        ctx.set_setting("spp", 16)
+        ctx.render_frame(cam, R.RESET)
+        shards.append(ctx.read_framebuffer().copy())
+        ctx.close()
+    assert np.array_equal(R.assemble_shards_host(shards, W, H), ref)
+    assert ref[..., :3].mean() > 0.05
