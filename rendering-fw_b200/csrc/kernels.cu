@@ -23,7 +23,17 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 
+// This file is compiled twice (rendering-fw_b200/Makefile): RFW_PART=1 builds the trace side — traversal, generate,
+// finalize, E-mode, stage-level kernels — with IEEE arithmetic, so hit points do not depend on approximate division;
+// RFW_PART=2 builds k_shade with -use_fast_math, as the reference builds its whole CUDA backend
+// (RFW/backends/CUDART/CMakeLists.txt:7-9).  RFW_PART=0 (default) is everything in one unit.
+#ifndef RFW_PART
+#define RFW_PART 0
+#endif
+
 namespace rfwb200
+{
+namespace // device code and kernels have internal linkage: the file is compiled into two objects
 {
 
 // ------------------------------------------------------------------------------------------------
@@ -211,9 +221,13 @@ __device__ __forceinline__ float slab(float lo, float hi, float idir, float ood,
 		const float tn = fmaxf(fmaxf(nx, ny), nz), tf = fminf(fminf(fx, fy), fz);                                       \
 		const bool h = (tf >= tn) & (tn < tmax) & (tf >= tmin);                                                         \
 		nh += h ? 1 : 0;                                                                                                \
-		key##K = h ? __uint_as_float((__float_as_uint(fmaxf(tn, 0.0f)) & 0xFFFFFFFCu) | uint32_t(K)) : MISSKEY(K);      \
+		key##K = h ? ((__float_as_uint(fmaxf(tn, 0.0f)) & 0xFFFFFFFCu) | uint32_t(K)) : MISSKEY(K);      \
 	}
-#define MISSKEY(K) __uint_as_float(0x7f000000u | uint32_t(K))
+// Sort keys are the BIT PATTERNS of the clamped (>= 0) entry distances compared as unsigned integers — monotonic for
+// non-negative floats and, unlike float min/max, immune to flush-to-zero: a ray that starts inside a box has
+// tn = 0 and its key is just the slot index, a denormal as a float (the reference compares them as floats,
+// CUDAIntersect.h:185-194, which only works without -ftz).
+#define MISSKEY(K) (0x7f000000u | uint32_t(K))
 // same test with the near / far planes already selected by the sign of the ray direction (no per-axis min/max)
 #define CHILD_N(K, C)                                                                                                   \
 	{                                                                                                                   \
@@ -221,14 +235,14 @@ __device__ __forceinline__ float slab(float lo, float hi, float idir, float ood,
 		const float tf = fminf(fminf(fmaf(farx.C, idx, -oodx), fmaf(fary.C, idy, -oody)), fmaf(farz.C, idz, -oodz));     \
 		const bool h = (tf >= tn) & (tn < tmax) & (tf >= tmin);                                                         \
 		nh += h ? 1 : 0;                                                                                                \
-		key##K = h ? __uint_as_float((__float_as_uint(fmaxf(tn, 0.0f)) & 0xFFFFFFFCu) | uint32_t(K)) : MISSKEY(K);      \
+		key##K = h ? ((__float_as_uint(fmaxf(tn, 0.0f)) & 0xFFFFFFFCu) | uint32_t(K)) : MISSKEY(K);      \
 	}
 #define CSWAP(A, B)                                                                                                     \
 	{                                                                                                                   \
-		const float lo_ = fminf(A, B), hi_ = fmaxf(A, B);                                                               \
+		const uint32_t lo_ = min(A, B), hi_ = max(A, B);                                                                \
 		A = lo_, B = hi_;                                                                                               \
 	}
-#define PICK(KEY) (((__float_as_uint(KEY) & 3u) == 0u) ? n.child.x : (((__float_as_uint(KEY) & 3u) == 1u) ? n.child.y : (((__float_as_uint(KEY) & 3u) == 2u) ? n.child.z : n.child.w)))
+#define PICK(KEY) ((((KEY)&3u) == 0u) ? n.child.x : ((((KEY)&3u) == 1u) ? n.child.y : ((((KEY)&3u) == 2u) ? n.child.z : n.child.w)))
 
 template <bool ANY_HIT>
 __device__ __forceinline__ bool traverse(const SceneView &sc, const float4 *__restrict__ snodes, uint32_t n_smem, V3 o,
@@ -249,7 +263,7 @@ __device__ __forceinline__ bool traverse(const SceneView &sc, const float4 *__re
 		if (cur >= 0)
 		{
 			const NodeRegs n = load_node(sc, snodes, n_smem, uint32_t(cur));
-			float key0, key1, key2, key3;
+			uint32_t key0, key1, key2, key3;
 			int nh = 0;
 			CHILD_T(0, x)
 			CHILD_T(1, y)
@@ -372,6 +386,7 @@ __device__ __forceinline__ void generate_emode(const FrameParams &fp, const Shar
 	camera_ray(fp, sh, x, y, r[0], r[1], r[2], r[3], false, O, D);
 }
 
+#if RFW_PART != 2 // ---- trace part: compiled with IEEE arithmetic ----
 // ------------------------------------------------------------------------------------------------
 // k_wavefront_trace — the persistent-threads traversal kernel of both trace stages.
 //
@@ -540,7 +555,7 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 						int4 child;
 					} n;
 					n.child = *reinterpret_cast<const int4 *>(np_ + 6);
-					float key0, key1, key2, key3;
+					uint32_t key0, key1, key2, key3;
 					int nh = 0;
 					CHILD_N(0, x)
 					CHILD_N(1, y)
@@ -668,6 +683,8 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 			curc->shadow_traced = n_shadow;
 	}
 }
+
+#endif // RFW_PART != 2 (trace part)
 
 // ------------------------------------------------------------------------------------------------
 // shading helpers — bsdf/tools.h, bsdf/compat.h, bsdf/disney.h, CUDART/src/getShadingData.h,
@@ -1285,6 +1302,7 @@ __device__ V3 RandomPointOnLight(const SceneView &sc, float r0, float r1, V3 I, 
 	return I - L * 1000.0f;
 }
 
+#if RFW_PART != 1 // ---- shade part: compiled with -use_fast_math (Makefile) ----
 // ------------------------------------------------------------------------------------------------
 // k_shade — Kernels.cu:571-794.  Each thread shades one path into registers; the three outputs
 // (accumulate, connect-queue entry, extension-queue entry) are committed at one converged point
@@ -1555,6 +1573,9 @@ __global__ void __launch_bounds__(128, SHADE_MINB) k_shade(const SceneView sc, c
 		atomicAdd(&curc->acc, acc_count);
 }
 
+#endif // RFW_PART != 1 (shade part)
+
+#if RFW_PART != 2 // ---- trace part ----
 // ------------------------------------------------------------------------------------------------
 // k_finalize — Kernels.cu:181-203: framebuffer = accumulator * 1/samples.  world == 1 writes the
 // row-major image; world > 1 keeps the tile-major shard for the gather.
@@ -1829,6 +1850,10 @@ __global__ void k_generate_only(const SceneView sc, const ShardView sh, const Wa
 	dirs[pixel] = make_float4(D.x, D.y, D.z, 0.f);
 }
 
+#endif // RFW_PART != 2
+} // namespace
+
+#if RFW_PART != 2 // ---- trace part: launchers ----
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
@@ -1859,7 +1884,7 @@ cudaError_t configure_launches(const RenderSettings &rs, uint32_t node_count, La
 		per_sm = 1;
 	dims.trace_grid = sms * per_sm; // a whole number of CTAs per SM: no partial wave
 	int shade_per_sm = 0;
-	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shade_per_sm, k_shade, dims.shade_block, 0);
+	e = shade_occupancy(dims.shade_block, &shade_per_sm);
 	if (e != cudaSuccess)
 		return e;
 	if (shade_per_sm < 1)
@@ -1872,12 +1897,6 @@ cudaError_t launch_primary(const SceneView &sc, const ShardView &sh, const Wavef
 						   uint32_t sample_in_frame, const LaunchDims &dims, cudaStream_t stream)
 {
 	k_wavefront_trace<true><<<dims.trace_grid, dims.trace_block, dims.trace_smem, stream>>>(sc, sh, wf, rs, sample_in_frame, 0u);
-	return cudaGetLastError();
-}
-cudaError_t launch_shade(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
-						 uint32_t sample_in_frame, uint32_t depth, const LaunchDims &dims, cudaStream_t stream)
-{
-	k_shade<<<dims.shade_grid, dims.shade_block, 0, stream>>>(sc, sh, wf, rs, sample_in_frame, depth);
 	return cudaGetLastError();
 }
 cudaError_t launch_trace(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
@@ -1931,5 +1950,20 @@ cudaError_t launch_assemble(const ShardView &sh, const float4 *gathered, size_t 
 	k_assemble<<<grid, 256, 0, stream>>>(sh, gathered, stride, image);
 	return cudaGetLastError();
 }
+
+#endif // RFW_PART != 2 (trace part)
+
+#if RFW_PART != 1 // ---- shade part ----
+cudaError_t launch_shade(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
+						 uint32_t sample_in_frame, uint32_t depth, const LaunchDims &dims, cudaStream_t stream)
+{
+	k_shade<<<dims.shade_grid, dims.shade_block, 0, stream>>>(sc, sh, wf, rs, sample_in_frame, depth);
+	return cudaGetLastError();
+}
+cudaError_t shade_occupancy(int block, int *per_sm)
+{
+	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_shade, block, 0);
+}
+#endif // RFW_PART != 1 (shade part)
 
 } // namespace rfwb200

@@ -16,6 +16,7 @@ struct LaunchDims
 };
 
 // queries occupancy for the current device and smem_nodes setting, sets function attributes
+cudaError_t shade_occupancy(int block, int *per_sm); // defined next to k_shade
 cudaError_t configure_launches(const RenderSettings &rs, uint32_t node_count, LaunchDims &dims);
 
 // --- PT-mode stages (one sample = primary, shade(0), [trace(d), shade(d)] for d = 1..max) ---
