@@ -180,6 +180,15 @@ typedef struct rfwb200_frame_counters {
 	uint64_t samples;	/* samples per pixel rendered by the last render_frame    */
 } rfwb200_frame_counters;
 
+/* What the last rfwb200_update did (extension: the reference reports nothing about its acceleration structure) */
+typedef struct rfwb200_geometry_stats {
+	int32_t on_device; /* 1: refit ran as GPU kernels (no host flatten / refit / re-upload)                  */
+	int32_t was_refit; /* 1: topology kept (bvh_tree.cpp:104-114), 0: rebuilt                              */
+	float device_ms;   /* GPU time of the geometry kernels of the last update (records, boxes)             */
+	float host_ms;	   /* host time of the last build / host refit                                         */
+	uint64_t refits, builds;
+} rfwb200_geometry_stats;
+
 /* one closest-hit record returned by rfwb200_trace_closest */
 typedef struct rfwb200_hit {
 	float t;		  /* 1e34f on miss */
@@ -236,14 +245,33 @@ RFWB200_API int rfwb200_set_instance(rfwb200_context *ctx, size_t instance, size
 RFWB200_API int rfwb200_set_lights(rfwb200_context *ctx, rfwb200_light_count count,
 								   const rfwb200_area_light *area, const rfwb200_point_light *point,
 								   const rfwb200_spot_light *spot, const rfwb200_directional_light *directional);
-/* replaces RenderContext::update (context.h:108): commits geometry, (re)builds the BVH */
+/* replaces RenderContext::update (context.h:108): commits geometry, (re)builds the BVH.  When only vertices or
+ * instance transforms changed since the last build, the refit (RFW/system/bvh/src/bvh_tree.cpp:104-114,
+ * top_level_bvh.cpp:46-52) runs on the GPU: changed meshes are copied into a device-resident geometry arena and two
+ * kernels regenerate the world-space triangle records and every box of the tree (setting "refit" = device|host). */
 RFWB200_API int rfwb200_update(rfwb200_context *ctx);
+
+/* ---- device skinning (extension) ------------------------------------------------------------
+ * The reference skins on the CPU before set_mesh (rfw::geometry::gltf::SceneMesh::set_pose,
+ * RFW/system/src/rfw/geometry/gltf/mesh.cpp:18-48, then update_triangles :428-449) and re-sends the whole mesh.
+ * Here the bind pose stays on the GPU: rfwb200_set_mesh_skin registers it once (arrays of vertex_count elements:
+ * base_vertices vec4, base_normals vec4 (w ignored), joints uvec4, weights vec4 — SceneMesh::baseVertices/baseNormals/
+ * joints/weights), rfwb200_set_mesh_pose sends only the joint matrices (column-major mat4 each,
+ * MeshSkin::jointMatrices) and runs skinning + triangle update as kernels; the next rfwb200_update refits on the GPU. */
+RFWB200_API int rfwb200_set_mesh_skin(rfwb200_context *ctx, size_t mesh_index, const float *base_vertices,
+									  const float *base_normals, const uint32_t *joints, const float *weights,
+									  size_t vertex_count);
+RFWB200_API int rfwb200_set_mesh_pose(rfwb200_context *ctx, size_t mesh_index, const float *joint_matrices,
+									  size_t joint_count);
+RFWB200_API int rfwb200_get_geometry_stats(rfwb200_context *ctx, rfwb200_geometry_stats *out);
 
 /* replaces RenderContext::set_setting (context.h:107). Keys: "spp" (samples per render_frame,
  * default 1), "mode" ("pt" wavefront path tracer | "embree" = image model of the EmbreeRT
  * backend), "max_path_length" (default 2 = settings.h:5), "clamp" (default 10, camera.h:36),
  * "smem_nodes" (BVH nodes staged in shared memory per CTA), "spatial_splits" (on|off), "sample_lanes" (1-4 concurrent samples), "fetch_threshold", "timing" (on|off: per-stage CUDA-event
- * times in get_stats), "survival_scale" (on|off, the 1/p throughput scale of Kernels.cu:783). */
+ * times in get_stats), "survival_scale" (on|off, the 1/p throughput scale of Kernels.cu:783), "refit" (device|host),
+ * "shade_math" (fast = the shade kernel built with -use_fast_math like the reference's CUDA backend,
+ * CUDART/CMakeLists.txt:7-9 | ieee = the same kernel with IEEE division/sqrt, the arithmetic of the CPU oracle). */
 RFWB200_API int rfwb200_set_setting(rfwb200_context *ctx, const char *key, const char *value);
 /* replaces RenderContext::get_settings (context.h:106): writes a '\n'-separated "key=v1|v2" list */
 RFWB200_API int rfwb200_get_settings(const rfwb200_context *ctx, char *buf, size_t buf_size);
@@ -308,6 +336,10 @@ RFWB200_API int rfwb200_get_bvh_info(const rfwb200_context *ctx, uint64_t *nodes
  * ext, shadow, trace_cursor, shade_cursor, acc, shadow_traced, -, -) of the last frame to the host. */
 RFWB200_API int rfwb200_debug_read_plane(rfwb200_context *ctx, int which, float *host, size_t n);
 RFWB200_API int rfwb200_debug_read_counters(rfwb200_context *ctx, uint32_t *out8_per_depth, size_t depth_slots);
+/* copy the committed device scene to the host: which = 0 BVH nodes (128 B each), 1 triangle records (48 B), 2 shading
+ * triangles (96 B); host == NULL only reports the size */
+RFWB200_API int rfwb200_debug_read_scene(rfwb200_context *ctx, int which, void *host, size_t capacity_bytes,
+										 size_t *bytes_out);
 /* host == NULL arms a per-warp timeline {start ns, end ns, rays, smid} for trace launches at `depth`; a second call
  * with a host buffer reads it back and disarms it (tools/diag_timeline.py). */
 RFWB200_API int rfwb200_debug_trace_timeline(rfwb200_context *ctx, int depth, unsigned long long *host, size_t max_warps,

@@ -13,6 +13,7 @@
 
 #include "bvh_build.h"
 #include "device_types.h"
+#include "geometry.h"
 #include "kernels.h"
 
 #include <cuda_runtime.h>
@@ -142,6 +143,27 @@ struct rfwb200_context
 	BvhBuildResult bvh;
 	std::vector<BuildTriangle> build_tris;
 	uint64_t flat_tri_count = 0;
+
+	// ---- device geometry arena (geometry.cu): every mesh back to back + the instance table, so a refit never
+	// touches the host: set_mesh uploads only the changed mesh, update() launches k_refit + k_flatten_shade ----
+	DevBuf d_verts, d_indices, d_mesh_tris, d_instances, d_flat_inst, d_tri_order, d_parent_slot, d_arrivals;
+	std::vector<uint32_t> mesh_vert_off, mesh_tri_off; // arena offsets per mesh
+	std::vector<uint8_t> mesh_dirty;				   // host copy newer than the arena
+	bool arena_valid = false;
+	bool device_geometry = true; // setting "refit" = device | host
+	GeometryView geo{};
+	struct Skin
+	{
+		DevBuf base_v, base_n, joints, weights, matrices, normals;
+		size_t vertex_count = 0;
+		uint32_t max_joint = 0;
+		bool device_newer = false; // the arena holds a pose the host copy of the mesh does not
+	};
+	std::vector<std::unique_ptr<Skin>> skins; // per mesh index, null when the mesh has no skin
+	cudaEvent_t ev_geo_a = nullptr, ev_geo_b = nullptr;
+	bool geo_timed = false, last_update_on_device = false, last_update_was_refit = false;
+	uint64_t refits = 0, builds = 0;
+	bool shade_ieee = false; // setting "shade_math" = fast | ieee
 
 	// ---- wavefront state -----------------------------------------------------------------------------
 	DevBuf d_debug;
@@ -304,15 +326,21 @@ int ensure_counters(Ctx *c, uint32_t spp)
 }
 
 // instance flattening: world-space triangles + repacked shading records
-int flatten_scene(Ctx *c, std::vector<ShadeTri> &shade, std::vector<float> &det_eps)
+// (shade_out / det_eps_out are null on the device path: geometry.cu produces those records itself)
+int flatten_scene(Ctx *c, std::vector<ShadeTri> *shade_out, std::vector<float> *det_eps_out)
 {
+	std::vector<ShadeTri> shade_dummy;
+	std::vector<float> eps_dummy;
+	const bool want_shade = shade_out != nullptr;
+	std::vector<ShadeTri> &shade = want_shade ? *shade_out : shade_dummy;
+	std::vector<float> &det_eps = det_eps_out ? *det_eps_out : eps_dummy;
 	size_t total = 0;
 	for (const HostInstance &in : c->instances)
 		if (in.mesh >= 0 && size_t(in.mesh) < c->meshes.size())
 			total += c->meshes[in.mesh].triangles.size();
 	c->build_tris.resize(total);
-	shade.resize(total);
-	det_eps.resize(total);
+	if (want_shade)
+		shade.resize(total), det_eps.resize(total);
 	size_t at = 0;
 	for (size_t ii = 0; ii < c->instances.size(); ii++)
 	{
@@ -337,6 +365,8 @@ int flatten_scene(Ctx *c, std::vector<ShadeTri> &shade, std::vector<float> &det_
 			mul_point(M, &m.vertices[4 * vi[0]], bt.v0);
 			mul_point(M, &m.vertices[4 * vi[1]], bt.v1);
 			mul_point(M, &m.vertices[4 * vi[2]], bt.v2);
+			if (!want_shade)
+				continue;
 			const rfwb200_triangle &src = m.triangles[t];
 			ShadeTri &st = shade[at];
 			st.u0 = src.u0, st.u1 = src.u1, st.u2 = src.u2, st.light_tri_idx = src.light_tri_idx;
@@ -387,6 +417,175 @@ int upload_bvh(Ctx *c, const std::vector<float> &det_eps)
 	c->scene.tris = c->d_tris.as<TriRec>();
 	c->scene.node_count = uint32_t(c->bvh.nodes.size());
 	c->scene.tri_count = uint32_t(n);
+	return RFWB200_OK;
+}
+
+
+// ---- device geometry path (geometry.cu) --------------------------------------------------------------------------------
+int upload_mesh_to_arena(Ctx *c, size_t mi)
+{
+	const HostMesh &m = c->meshes[mi];
+	const size_t nv = m.vertices.size() / 4, nt = m.triangles.size();
+	if (nv)
+		CK(cudaMemcpyAsync(c->d_verts.as<float4>() + c->mesh_vert_off[mi], m.vertices.data(), nv * sizeof(float4),
+						   cudaMemcpyHostToDevice, c->stream));
+	if (nt)
+	{
+		CK(cudaMemcpyAsync(static_cast<char *>(c->d_mesh_tris.ptr) + size_t(c->mesh_tri_off[mi]) * sizeof(rfwb200_triangle),
+						   m.triangles.data(), nt * sizeof(rfwb200_triangle), cudaMemcpyHostToDevice, c->stream));
+		uint32_t *dst = c->d_indices.as<uint32_t>() + size_t(c->mesh_tri_off[mi]) * 3;
+		if (!m.indices.empty())
+			CK(cudaMemcpyAsync(dst, m.indices.data(), nt * 3 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+		else
+		{
+			std::vector<uint32_t> seq(nt * 3);
+			for (size_t i = 0; i < seq.size(); i++)
+				seq[i] = uint32_t(i);
+			CK(cudaMemcpyAsync(dst, seq.data(), seq.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+			CK(cudaStreamSynchronize(c->stream)); // seq dies here
+		}
+	}
+	c->mesh_dirty[mi] = 0;
+	return RFWB200_OK;
+}
+
+int upload_arena(Ctx *c)
+{
+	const size_t n = c->meshes.size();
+	c->mesh_vert_off.assign(n, 0), c->mesh_tri_off.assign(n, 0), c->mesh_dirty.assign(n, 1);
+	size_t nv = 0, nt = 0;
+	for (size_t i = 0; i < n; i++)
+	{
+		c->mesh_vert_off[i] = uint32_t(nv), c->mesh_tri_off[i] = uint32_t(nt);
+		nv += c->meshes[i].vertices.size() / 4, nt += c->meshes[i].triangles.size();
+	}
+	if (nv >= (1ull << 32) || nt * 3 >= (1ull << 32))
+		return set_error(RFWB200_ERR_INVALID, "geometry arena exceeds 32-bit offsets");
+	CK(c->d_verts.reserve(std::max<size_t>(nv, 1) * sizeof(float4)));
+	CK(c->d_mesh_tris.reserve(std::max<size_t>(nt, 1) * sizeof(rfwb200_triangle)));
+	CK(c->d_indices.reserve(std::max<size_t>(nt, 1) * 3 * sizeof(uint32_t)));
+	for (size_t i = 0; i < n; i++)
+		if (int r = upload_mesh_to_arena(c, i))
+			return r;
+	c->arena_valid = true;
+	return RFWB200_OK;
+}
+
+int upload_instances(Ctx *c, bool with_flat_inst)
+{
+	std::vector<DeviceInstance> di(std::max<size_t>(c->instances.size(), 1));
+	memset(di.data(), 0, di.size() * sizeof(DeviceInstance));
+	std::vector<uint32_t> flat_inst;
+	uint32_t flat = 0;
+	for (size_t ii = 0; ii < c->instances.size(); ii++)
+	{
+		const HostInstance &in = c->instances[ii];
+		DeviceInstance &d = di[ii];
+		d.flat_off = flat;
+		if (in.mesh < 0 || size_t(in.mesh) >= c->meshes.size())
+			continue;
+		memcpy(d.transform, in.transform, sizeof(d.transform));
+		memcpy(d.normal, in.normal, sizeof(d.normal));
+		const float *M = in.transform;
+		const float det = M[0] * (M[5] * M[10] - M[9] * M[6]) - M[4] * (M[1] * M[10] - M[9] * M[2]) +
+						  M[8] * (M[1] * M[6] - M[5] * M[2]);
+		d.det_eps = 1e-6f * std::fabs(det);
+		d.vert_off = c->mesh_vert_off[in.mesh], d.tri_off = c->mesh_tri_off[in.mesh];
+		d.tri_count = uint32_t(c->meshes[in.mesh].triangles.size());
+		if (with_flat_inst)
+			flat_inst.insert(flat_inst.end(), d.tri_count, uint32_t(ii));
+		flat += d.tri_count;
+	}
+	CK(c->d_instances.reserve(di.size() * sizeof(DeviceInstance)));
+	CK(cudaMemcpyAsync(c->d_instances.ptr, di.data(), di.size() * sizeof(DeviceInstance), cudaMemcpyHostToDevice, c->stream));
+	if (with_flat_inst)
+	{
+		CK(c->d_flat_inst.reserve(std::max<size_t>(flat_inst.size(), 1) * sizeof(uint32_t)));
+		if (!flat_inst.empty())
+			CK(cudaMemcpyAsync(c->d_flat_inst.ptr, flat_inst.data(), flat_inst.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
+							   c->stream));
+	}
+	CK(cudaStreamSynchronize(c->stream)); // the staging vectors die here
+	return RFWB200_OK;
+}
+
+// nodes (topology + the builder's boxes), leaf order and the parent links the bottom-up refit climbs
+int upload_topology(Ctx *c)
+{
+	const size_t nn = c->bvh.nodes.size(), nr = c->bvh.tri_order.size();
+	if (nn >= (1u << 30))
+		return set_error(RFWB200_ERR_INVALID, "BVH has more than 2^30 nodes");
+	std::vector<uint32_t> parent_slot(std::max<size_t>(nn, 1), 0xffffffffu);
+	for (size_t n = 0; n < nn; n++)
+		for (int s = 0; s < c->bvh.nodes[n].pad[0]; s++)
+			if (c->bvh.nodes[n].child[s] >= 0)
+				parent_slot[c->bvh.nodes[n].child[s]] = uint32_t(n << 2) | uint32_t(s);
+	CK(c->d_nodes.reserve(nn * sizeof(BvhNode4)));
+	CK(c->d_tris.reserve(std::max<size_t>(nr, 1) * sizeof(TriRec)));
+	CK(c->d_tri_order.reserve(std::max<size_t>(nr, 1) * sizeof(uint32_t)));
+	CK(c->d_parent_slot.reserve(parent_slot.size() * sizeof(uint32_t)));
+	CK(c->d_arrivals.reserve(parent_slot.size() * sizeof(uint32_t)));
+	CK(c->d_shade_tris.reserve(std::max<size_t>(c->flat_tri_count, 1) * sizeof(ShadeTri)));
+	CK(cudaMemcpyAsync(c->d_nodes.ptr, c->bvh.nodes.data(), nn * sizeof(BvhNode4), cudaMemcpyHostToDevice, c->stream));
+	if (nr)
+		CK(cudaMemcpyAsync(c->d_tri_order.ptr, c->bvh.tri_order.data(), nr * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+	CK(cudaMemcpyAsync(c->d_parent_slot.ptr, parent_slot.data(), parent_slot.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
+					   c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	GeometryView &g = c->geo;
+	g.verts = c->d_verts.as<float4>(), g.indices = c->d_indices.as<uint32_t>(), g.mesh_tris = c->d_mesh_tris.ptr;
+	g.instances = c->d_instances.as<DeviceInstance>(), g.flat_inst = c->d_flat_inst.as<uint32_t>();
+	g.flat_count = uint32_t(c->flat_tri_count);
+	g.nodes = c->d_nodes.as<BvhNode4>(), g.tri_order = c->d_tri_order.as<uint32_t>();
+	g.parent_slot = c->d_parent_slot.as<uint32_t>(), g.arrivals = c->d_arrivals.as<uint32_t>();
+	g.node_count = uint32_t(nn), g.ref_count = uint32_t(nr);
+	g.out_tris = c->d_tris.as<TriRec>(), g.out_shade = c->d_shade_tris.as<ShadeTri>();
+	c->scene.nodes = c->d_nodes.as<BvhNode4>(), c->scene.tris = c->d_tris.as<TriRec>();
+	c->scene.shade_tris = c->d_shade_tris.as<ShadeTri>();
+	c->scene.node_count = uint32_t(nn), c->scene.tri_count = uint32_t(nr);
+	return RFWB200_OK;
+}
+
+// world-space intersection + shading records (and, for a refit, every box of the tree) from the arena
+int device_generate(Ctx *c, bool refit_boxes)
+{
+	if (!c->ev_geo_a)
+	{
+		CK(cudaEventCreate(&c->ev_geo_a));
+		CK(cudaEventCreate(&c->ev_geo_b));
+	}
+	CK(cudaEventRecord(c->ev_geo_a, c->stream));
+	c->geo.write_boxes = refit_boxes ? 1 : 0;
+	CK(launch_refit(c->geo, c->stream));
+	CK(launch_flatten_shade(c->geo, c->stream));
+	CK(cudaEventRecord(c->ev_geo_b, c->stream));
+	c->launches += 2;
+	c->geo_timed = true;
+	return RFWB200_OK;
+}
+
+// a rebuild needs the current pose of device-skinned meshes on the host
+int sync_skinned_meshes_to_host(Ctx *c)
+{
+	bool any = false;
+	for (size_t mi = 0; mi < c->skins.size() && mi < c->meshes.size(); mi++)
+	{
+		Ctx::Skin *sk = c->skins[mi].get();
+		// (the arena LAYOUT may already be stale — a new mesh was added — but this mesh's slice is still intact:
+		// set_mesh on the mesh itself clears device_newer)
+		if (!sk || !sk->device_newer || mi >= c->mesh_vert_off.size() || !c->d_verts.ptr)
+			continue;
+		HostMesh &hm = c->meshes[mi];
+		CK(cudaMemcpyAsync(hm.vertices.data(), c->d_verts.as<float4>() + c->mesh_vert_off[mi], hm.vertices.size() * sizeof(float),
+						   cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaMemcpyAsync(hm.triangles.data(),
+						   static_cast<const char *>(c->d_mesh_tris.ptr) + size_t(c->mesh_tri_off[mi]) * sizeof(rfwb200_triangle),
+						   hm.triangles.size() * sizeof(rfwb200_triangle), cudaMemcpyDeviceToHost, c->stream));
+		sk->device_newer = false;
+		any = true;
+	}
+	if (any)
+		CK(cudaStreamSynchronize(c->stream));
 	return RFWB200_OK;
 }
 
@@ -519,6 +718,8 @@ extern "C"
 			cudaStreamDestroy(l->stream), cudaEventDestroy(l->done);
 		if (c->ev_fork)
 			cudaEventDestroy(c->ev_fork);
+		if (c->ev_geo_a)
+			cudaEventDestroy(c->ev_geo_a), cudaEventDestroy(c->ev_geo_b);
 		delete c;
 		return RFWB200_OK;
 	}
@@ -681,6 +882,18 @@ extern "C"
 		m.triangles.assign(mesh->triangles, mesh->triangles + mesh->triangle_count);
 		m.version++;
 		c->geometry_dirty = true;
+		if (c->mesh_dirty.size() < c->meshes.size())
+			c->mesh_dirty.resize(c->meshes.size(), 1);
+		c->mesh_dirty[index] = 1;
+		if (c->topology_dirty)
+			c->arena_valid = false;
+		if (index < c->skins.size() && c->skins[index])
+		{
+			if (c->skins[index]->vertex_count != mesh->vertex_count)
+				c->skins[index].reset(); // a different mesh: the skin no longer applies
+			else
+				c->skins[index]->device_newer = false;
+		}
 		return RFWB200_OK;
 	}
 
@@ -736,38 +949,182 @@ extern "C"
 			return r;
 		if (!c->geometry_dirty && c->scene.nodes)
 			return RFWB200_OK;
-		CK(cudaStreamSynchronize(c->stream));
-		std::vector<ShadeTri> shade;
-		std::vector<float> det_eps;
-		if (int r = flatten_scene(c, shade, det_eps))
-			return r;
 		// topology unchanged since the last build => refit (bvh_tree.cpp:104-114)
 		std::vector<std::pair<int, size_t>> layout;
+		size_t total = 0;
 		for (const HostInstance &in : c->instances)
-			layout.emplace_back(in.mesh, in.mesh >= 0 ? c->meshes[in.mesh].triangles.size() : 0);
-		const bool can_refit = !c->topology_dirty && layout == c->built_layout && !c->bvh.nodes.empty() &&
-							   c->built_tri_count == c->build_tris.size();
+		{
+			const bool ok = in.mesh >= 0 && size_t(in.mesh) < c->meshes.size();
+			layout.emplace_back(in.mesh, ok ? c->meshes[in.mesh].triangles.size() : 0);
+			total += layout.back().second;
+		}
+		const bool can_refit = !c->topology_dirty && layout == c->built_layout && !c->bvh.nodes.empty() && c->built_tri_count == total;
+		const bool device = c->device_geometry && total > 0;
+		if (device && can_refit && c->arena_valid)
+		{
+			// Device refit: only the meshes that changed and the 128-B instance records cross PCIe; the boxes, the
+			// intersection records and the shading records are regenerated by two launches on the render stream.
+			for (size_t mi = 0; mi < c->meshes.size(); mi++)
+				if (c->mesh_dirty[mi])
+					if (int r = upload_mesh_to_arena(c, mi))
+						return r;
+			if (int r = upload_instances(c, false))
+				return r;
+			if (int r = device_generate(c, true))
+				return r;
+			c->refits++, c->last_update_on_device = true, c->last_update_was_refit = true;
+			c->geometry_dirty = false;
+			return RFWB200_OK;
+		}
+		CK(cudaStreamSynchronize(c->stream));
+		if (int r = sync_skinned_meshes_to_host(c))
+			return r;
+		std::vector<ShadeTri> shade;
+		std::vector<float> det_eps;
+		if (int r = flatten_scene(c, device ? nullptr : &shade, device ? nullptr : &det_eps))
+			return r;
 		const auto t0 = std::chrono::steady_clock::now();
 		if (can_refit)
-			refit_bvh4(c->build_tris.data(), c->build_tris.size(), c->bvh);
+			refit_bvh4(c->build_tris.data(), c->build_tris.size(), c->bvh), c->refits++;
 		else
 		{
 			const int threads = int(std::max(1u, std::thread::hardware_concurrency()));
 			build_bvh4(c->build_tris.data(), c->build_tris.size(), threads, c->bvh, c->spatial_splits);
 			c->built_tri_count = c->build_tris.size();
+			c->builds++;
 		}
 		c->bvh.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 		if (3 * c->bvh.depth + 1 > TRAVERSAL_STACK)
 			return set_error(RFWB200_ERR_INVALID, "BVH deeper than the traversal stack allows");
 		c->built_layout = layout;
-		if (int r = upload_bvh(c, det_eps))
-			return r;
-		CK(c->d_shade_tris.reserve(std::max<size_t>(shade.size(), 1) * sizeof(ShadeTri)));
-		if (!shade.empty())
-			CK(cudaMemcpy(c->d_shade_tris.ptr, shade.data(), shade.size() * sizeof(ShadeTri), cudaMemcpyHostToDevice));
-		c->scene.shade_tris = c->d_shade_tris.as<ShadeTri>();
+		c->last_update_on_device = false, c->last_update_was_refit = can_refit;
+		c->geo_timed = false;
+		if (device)
+		{
+			// the host only builds the topology; records are produced on the device from the arena (the builder's
+			// clipped boxes of spatially split references are kept: write_boxes = 0)
+			if (int r = upload_arena(c))
+				return r;
+			if (int r = upload_instances(c, true))
+				return r;
+			if (int r = upload_topology(c))
+				return r;
+			if (int r = device_generate(c, false))
+				return r;
+		}
+		else
+		{
+			c->arena_valid = false;
+			if (int r = upload_bvh(c, det_eps))
+				return r;
+			CK(c->d_shade_tris.reserve(std::max<size_t>(shade.size(), 1) * sizeof(ShadeTri)));
+			if (!shade.empty())
+				CK(cudaMemcpy(c->d_shade_tris.ptr, shade.data(), shade.size() * sizeof(ShadeTri), cudaMemcpyHostToDevice));
+			c->scene.shade_tris = c->d_shade_tris.as<ShadeTri>();
+		}
 		c->geometry_dirty = false, c->topology_dirty = false;
 		c->dims_valid = false; // node count may have changed the staged prefix
+		return RFWB200_OK;
+	}
+
+	/* ---- device skinning (extension; replaces the CPU skinning in front of set_mesh, gltf/mesh.cpp:18-48) ---- */
+	int rfwb200_set_mesh_skin(rfwb200_context *c, size_t mesh_index, const float *base_vertices, const float *base_normals,
+							  const uint32_t *joints, const float *weights, size_t vertex_count)
+	{
+		REQUIRE(c && base_vertices && base_normals && joints && weights, "bad skin");
+		REQUIRE(mesh_index < c->meshes.size(), "skin references a mesh that was not set");
+		REQUIRE(c->meshes[mesh_index].vertices.size() == vertex_count * 4, "skin and mesh vertex counts differ");
+		if (int r = ensure_device(c))
+			return r;
+		if (c->skins.size() <= mesh_index)
+			c->skins.resize(mesh_index + 1);
+		auto sk = std::make_unique<Ctx::Skin>();
+		sk->vertex_count = vertex_count;
+		uint32_t max_joint = 0;
+		for (size_t i = 0; i < vertex_count * 4; i++)
+			max_joint = std::max(max_joint, joints[i]);
+		sk->max_joint = max_joint;
+		const size_t b16 = std::max<size_t>(vertex_count, 1) * 16;
+		CK(sk->base_v.reserve(b16));
+		CK(sk->base_n.reserve(b16));
+		CK(sk->joints.reserve(b16));
+		CK(sk->weights.reserve(b16));
+		CK(sk->normals.reserve(b16));
+		CK(cudaMemcpy(sk->base_v.ptr, base_vertices, vertex_count * 16, cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(sk->base_n.ptr, base_normals, vertex_count * 16, cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(sk->joints.ptr, joints, vertex_count * 16, cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(sk->weights.ptr, weights, vertex_count * 16, cudaMemcpyHostToDevice));
+		c->skins[mesh_index] = std::move(sk);
+		return RFWB200_OK;
+	}
+
+	int rfwb200_set_mesh_pose(rfwb200_context *c, size_t mesh_index, const float *joint_matrices, size_t joint_count)
+	{
+		REQUIRE(c && joint_matrices && joint_count > 0, "bad pose");
+		REQUIRE(mesh_index < c->skins.size() && c->skins[mesh_index], "mesh has no skin (rfwb200_set_mesh_skin)");
+		if (int r = ensure_device(c))
+			return r;
+		Ctx::Skin &sk = *c->skins[mesh_index];
+		REQUIRE(sk.max_joint < joint_count, "a vertex references a joint beyond joint_count");
+		if (!c->device_geometry)
+			return set_error(RFWB200_ERR_STATE, "device skinning needs setting refit=device");
+		if (!c->arena_valid || c->topology_dirty)
+			return set_error(RFWB200_ERR_STATE, "call rfwb200_update once after set_mesh before posing a mesh");
+		if (c->mesh_dirty[mesh_index]) // a newer host copy (uv, materials, ...) goes first, the pose on top of it
+			if (int r = upload_mesh_to_arena(c, mesh_index))
+				return r;
+		const HostMesh &hm = c->meshes[mesh_index];
+		CK(sk.matrices.reserve(joint_count * 64));
+		CK(cudaMemcpyAsync(sk.matrices.ptr, joint_matrices, joint_count * 64, cudaMemcpyHostToDevice, c->stream));
+		SkinView v{};
+		v.base_vertices = sk.base_v.as<float4>(), v.base_normals = sk.base_n.as<float4>();
+		v.joints = sk.joints.as<uint4>(), v.weights = sk.weights.as<float4>();
+		v.joint_matrices = sk.matrices.as<float>();
+		v.indices = c->d_indices.as<uint32_t>() + size_t(c->mesh_tri_off[mesh_index]) * 3;
+		v.out_vertices = c->d_verts.as<float4>() + c->mesh_vert_off[mesh_index];
+		v.out_normals = sk.normals.as<float4>();
+		v.mesh_tris = static_cast<char *>(c->d_mesh_tris.ptr) + size_t(c->mesh_tri_off[mesh_index]) * sizeof(rfwb200_triangle);
+		v.vertex_count = uint32_t(sk.vertex_count), v.triangle_count = uint32_t(hm.triangles.size());
+		CK(launch_skin(v, c->stream));
+		c->launches += 2;
+		sk.device_newer = true;
+		c->geometry_dirty = true;
+		return RFWB200_OK;
+	}
+
+	int rfwb200_get_geometry_stats(rfwb200_context *c, rfwb200_geometry_stats *out)
+	{
+		REQUIRE(c && out, "bad arguments");
+		memset(out, 0, sizeof(*out));
+		out->on_device = c->last_update_on_device, out->was_refit = c->last_update_was_refit;
+		out->host_ms = c->last_update_on_device ? 0.0f : float(c->bvh.build_ms);
+		out->refits = c->refits, out->builds = c->builds;
+		if (c->geo_timed)
+		{
+			CK(cudaEventSynchronize(c->ev_geo_b));
+			CK(cudaEventElapsedTime(&out->device_ms, c->ev_geo_a, c->ev_geo_b));
+		}
+		return RFWB200_OK;
+	}
+
+	/* test hook: 0 = BvhNode4[], 1 = TriRec[], 2 = ShadeTri[] of the committed scene */
+	int rfwb200_debug_read_scene(rfwb200_context *c, int which, void *host, size_t capacity_bytes, size_t *bytes_out)
+	{
+		REQUIRE(c && bytes_out, "bad arguments");
+		REQUIRE(which >= 0 && which <= 2, "which must be 0 (nodes), 1 (triangles) or 2 (shading triangles)");
+		if (int r = check_ready(c))
+			return r;
+		const void *src = which == 0 ? (const void *)c->scene.nodes : which == 1 ? (const void *)c->scene.tris : (const void *)c->scene.shade_tris;
+		const size_t bytes = which == 0	  ? size_t(c->scene.node_count) * sizeof(BvhNode4)
+							 : which == 1 ? size_t(c->scene.tri_count) * sizeof(TriRec)
+										  : size_t(c->flat_tri_count) * sizeof(ShadeTri);
+		*bytes_out = bytes;
+		if (!host)
+			return RFWB200_OK;
+		REQUIRE(capacity_bytes >= bytes, "buffer too small");
+		CK(cudaStreamSynchronize(c->stream));
+		if (bytes)
+			CK(cudaMemcpy(host, src, bytes, cudaMemcpyDeviceToHost));
 		return RFWB200_OK;
 	}
 
@@ -833,6 +1190,18 @@ extern "C"
 		}
 		else if (k == "timing")
 			c->timing = (v == "on" || v == "1");
+		else if (k == "refit")
+		{
+			REQUIRE(v == "device" || v == "host", "refit must be 'device' or 'host'");
+			const bool dev = (v == "device");
+			if (dev != c->device_geometry)
+				c->device_geometry = dev, c->arena_valid = false, c->geometry_dirty = c->topology_dirty = true;
+		}
+		else if (k == "shade_math")
+		{
+			REQUIRE(v == "fast" || v == "ieee", "shade_math must be 'fast' or 'ieee'");
+			c->shade_ieee = (v == "ieee");
+		}
 		else if (k == "threads")
 		{
 		}
@@ -906,7 +1275,7 @@ extern "C"
 				}
 				{
 					StageTimer t(c, 3);
-					CK(launch_shade(c->scene, c->shard, wf, c->rs, s, 0, c->dims, ls));
+					CK((c->shade_ieee ? launch_shade_ieee : launch_shade)(c->scene, c->shard, wf, c->rs, s, 0, c->dims, ls));
 				}
 				c->launches += 2;
 				for (uint32_t d = 1; d <= maxd; d++)
@@ -917,7 +1286,7 @@ extern "C"
 					}
 					{
 						StageTimer t(c, 3);
-						CK(launch_shade(c->scene, c->shard, wf, c->rs, s, d, c->dims, ls));
+						CK((c->shade_ieee ? launch_shade_ieee : launch_shade)(c->scene, c->shard, wf, c->rs, s, d, c->dims, ls));
 					}
 					c->launches += 2;
 				}

@@ -1,0 +1,295 @@
+// geometry.cu — device-side geometry pipeline in front of the trace kernels:
+//
+//   k_skin_vertices    linear-blend skinning of a mesh's vertices and normals from joint matrices
+//                      (reference: CPU + TBB, RFW/system/src/rfw/geometry/gltf/mesh.cpp:18-48)
+//   k_update_triangles rebuild the 160-B triangle records of a skinned mesh (mesh.cpp:428-449)
+//   k_flatten_shade    instance flattening of the shading records (ShadeTri, device_types.h); the reference
+//                      applies the instance normal matrix per path (CUDART/src/getShadingData.h:129-130)
+//   k_refit            ONE launch: every leaf slot transforms its triangles to world space, writes their
+//                      intersection records (TriRec) and its own box, then walks towards the root — the last
+//                      thread to finish a node's slots (atomic arrival counter) carries the node's union into its
+//                      parent's slot.  Replaces the host refit (RFW/system/bvh/src/bvh_tree.cpp:104-114,
+//                      top_level_bvh.cpp:46-52) + full re-upload (CUDART/src/Context.cpp:270-311).
+//
+// This file is compiled with -fmad=false and IEEE division/sqrt: every expression below is evaluated in the same
+// order as the host builder's (bvh_build.cpp tri_box/padded, context.cpp mul_point/mul_mat3), so a device refit is
+// BIT-IDENTICAL to the host refit of the same vertices (tests/test_parity_gpu.py::test_device_refit_bit_exact).
+#include "geometry.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace rfwb200
+{
+
+namespace
+{
+
+struct F3
+{
+	float x, y, z;
+};
+
+__device__ __forceinline__ F3 xf_point(const float *__restrict__ m, const float4 p)
+{
+	F3 o; // context.cpp mul_point: m[r]*p0 + m[4+r]*p1 + m[8+r]*p2 + m[12+r], left to right
+	o.x = m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12];
+	o.y = m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13];
+	o.z = m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14];
+	return o;
+}
+
+__device__ __forceinline__ F3 xf_normal(const float *__restrict__ m, const float x, const float y, const float z)
+{
+	F3 o; // context.cpp mul_mat3
+	o.x = m[0] * x + m[3] * y + m[6] * z;
+	o.y = m[1] * x + m[4] * y + m[7] * z;
+	o.z = m[2] * x + m[5] * y + m[8] * z;
+	return o;
+}
+
+constexpr float BOX_PAD = 1e-5f; // bvh_build.cpp
+
+__device__ __forceinline__ void pad_axis(float &lo, float &hi)
+{
+	const float m = fmaxf(fabsf(lo), fabsf(hi)); // bvh_build.cpp padded()
+	const float pad = fmaxf(BOX_PAD, m * 2.4e-7f);
+	lo -= pad, hi += pad;
+}
+
+struct Box3
+{
+	float lo[3], hi[3];
+};
+
+__device__ __forceinline__ void box_reset(Box3 &b)
+{
+	b.lo[0] = b.lo[1] = b.lo[2] = 1e30f; // bvh_build.cpp Box::reset
+	b.hi[0] = b.hi[1] = b.hi[2] = -1e30f;
+}
+
+__device__ __forceinline__ void store_slot(BvhNode4 *n, int s, const Box3 &b)
+{
+	n->minx[s] = b.lo[0], n->miny[s] = b.lo[1], n->minz[s] = b.lo[2];
+	n->maxx[s] = b.hi[0], n->maxy[s] = b.hi[1], n->maxz[s] = b.hi[2];
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------
+// k_refit — one thread per (node, slot)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_refit(const GeometryView g)
+{
+	const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t node = gid >> 2;
+	int slot = int(gid & 3u);
+	if (node >= g.node_count)
+		return;
+	BvhNode4 *nodes = g.nodes;
+	if (slot >= nodes[node].pad[0])
+		return;
+	const int32_t c = nodes[node].child[slot];
+	if (c >= 0)
+		return; // inner slots are filled by whichever thread completes the child node
+	Box3 b;
+	box_reset(b);
+	{
+		const uint32_t v = uint32_t(~c), first = v >> 2, cnt = (v & 3u) + 1u;
+		for (uint32_t i = first; i < first + cnt; i++)
+		{
+			const uint32_t src = g.tri_order[i];
+			const uint32_t ii = g.flat_inst[src];
+			const DeviceInstance &in = g.instances[ii];
+			const uint32_t prim = src - in.flat_off;
+			const uint32_t *ix = g.indices + size_t(in.tri_off + prim) * 3;
+			const float4 *vb = g.verts + in.vert_off;
+			const F3 v0 = xf_point(in.transform, vb[ix[0]]);
+			const F3 v1 = xf_point(in.transform, vb[ix[1]]);
+			const F3 v2 = xf_point(in.transform, vb[ix[2]]);
+			float4 *rec = reinterpret_cast<float4 *>(g.out_tris + i);
+			rec[0] = make_float4(v0.x, v0.y, v0.z, v1.x - v0.x);
+			rec[1] = make_float4(v1.y - v0.y, v1.z - v0.z, v2.x - v0.x, v2.y - v0.y);
+			rec[2] = make_float4(v2.z - v0.z, __uint_as_float(src), in.det_eps, 0.0f);
+			float lo[3] = {fminf(fminf(v0.x, v1.x), v2.x), fminf(fminf(v0.y, v1.y), v2.y), fminf(fminf(v0.z, v1.z), v2.z)};
+			float hi[3] = {fmaxf(fmaxf(v0.x, v1.x), v2.x), fmaxf(fmaxf(v0.y, v1.y), v2.y), fmaxf(fmaxf(v0.z, v1.z), v2.z)};
+#pragma unroll
+			for (int a = 0; a < 3; a++)
+			{
+				pad_axis(lo[a], hi[a]);
+				b.lo[a] = fminf(b.lo[a], lo[a]), b.hi[a] = fmaxf(b.hi[a], hi[a]);
+			}
+		}
+	}
+	if (!g.write_boxes)
+		return;
+	// walk up: write the slot, announce it, and continue only as the last arrival of the node
+	for (;;)
+	{
+		store_slot(&nodes[node], slot, b);
+		__threadfence();
+		const uint32_t used = uint32_t(nodes[node].pad[0]);
+		const uint32_t arrived = atomicAdd(&g.arrivals[node], 1u) + 1u;
+		if (arrived < used)
+			return;
+		const uint32_t up = g.parent_slot[node];
+		if (up == 0xffffffffu)
+			return; // root complete
+		__threadfence();
+		// union of the finished node (its other slots were written by other threads: read past L1)
+		box_reset(b);
+		const volatile BvhNode4 *vn = nodes + node;
+		for (uint32_t k = 0; k < used; k++)
+		{
+			b.lo[0] = fminf(b.lo[0], vn->minx[k]), b.lo[1] = fminf(b.lo[1], vn->miny[k]), b.lo[2] = fminf(b.lo[2], vn->minz[k]);
+			b.hi[0] = fmaxf(b.hi[0], vn->maxx[k]), b.hi[1] = fmaxf(b.hi[1], vn->maxy[k]), b.hi[2] = fmaxf(b.hi[2], vn->maxz[k]);
+		}
+		node = up >> 2, slot = int(up & 3u);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_flatten_shade — one thread per flattened triangle (context.cpp flatten_scene, shading half)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_flatten_shade(const GeometryView g)
+{
+	const uint32_t src = blockIdx.x * blockDim.x + threadIdx.x;
+	if (src >= g.flat_count)
+		return;
+	const uint32_t ii = g.flat_inst[src];
+	const DeviceInstance &in = g.instances[ii];
+	const uint32_t prim = src - in.flat_off;
+	const float4 *t = reinterpret_cast<const float4 *>(g.mesh_tris) + size_t(in.tri_off + prim) * 10; // 160-B rfwb200_triangle
+	const float4 q0 = t[0], q1 = t[1], q2 = t[2], q3 = t[3], q4 = t[4], q5 = t[5], q6 = t[6];
+	const F3 n0 = xf_normal(in.normal, q2.x, q2.y, q2.z);
+	const F3 n1 = xf_normal(in.normal, q3.x, q3.y, q3.z);
+	const F3 n2 = xf_normal(in.normal, q4.x, q4.y, q4.z);
+	const F3 gn = xf_normal(in.normal, q2.w, q3.w, q4.w);
+	const float il = 1.0f / sqrtf(gn.x * gn.x + gn.y * gn.y + gn.z * gn.z);
+	float4 *o = reinterpret_cast<float4 *>(g.out_shade + src);
+	o[0] = q0; // u0 u1 u2 light_tri_idx
+	o[1] = q1; // v0 v1 v2 material
+	o[2] = make_float4(n0.x, n0.y, n0.z, gn.x * il);
+	o[3] = make_float4(n1.x, n1.y, n1.z, gn.y * il);
+	o[4] = make_float4(n2.x, n2.y, n2.z, gn.z * il);
+	o[5] = make_float4(q5.w, q6.w, __uint_as_float(ii), __uint_as_float(prim)); // area, LOD, instance, primitive
+}
+
+// ------------------------------------------------------------------------------------------------
+// skinning — gltf/mesh.cpp:18-48: S = sum_k w_k J[j_k];  v' = S v;  n' = (n^T S^-1).xyz / |n^T S^-1|_4
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_skin_vertices(const SkinView s)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= s.vertex_count)
+		return;
+	const uint4 j4 = s.joints[i];
+	const float4 w4 = s.weights[i];
+	float S[16]; // column-major like glm
+	{
+		const float *a = s.joint_matrices + size_t(j4.x) * 16, *b = s.joint_matrices + size_t(j4.y) * 16;
+		const float *c = s.joint_matrices + size_t(j4.z) * 16, *d = s.joint_matrices + size_t(j4.w) * 16;
+#pragma unroll
+		for (int k = 0; k < 16; k++)
+			S[k] = ((a[k] * w4.x + b[k] * w4.y) + c[k] * w4.z) + d[k] * w4.w;
+	}
+	const float4 p = s.base_vertices[i];
+	float4 r;
+	r.x = S[0] * p.x + S[4] * p.y + S[8] * p.z + S[12] * p.w;
+	r.y = S[1] * p.x + S[5] * p.y + S[9] * p.z + S[13] * p.w;
+	r.z = S[2] * p.x + S[6] * p.y + S[10] * p.z + S[14] * p.w;
+	r.w = S[3] * p.x + S[7] * p.y + S[11] * p.z + S[15] * p.w;
+	s.out_vertices[i] = r;
+
+	// n^T S^-1 with the w of the base normal = 0: only the upper-left 3x3 rows of the inverse matter for xyz; use
+	// the adjugate / determinant of the full 4x4 the way a general inverse does (joint matrices are affine, last
+	// row (0,0,0,1) up to rounding, but keep the general formula)
+	const float a00 = S[0], a01 = S[4], a02 = S[8], a03 = S[12];
+	const float a10 = S[1], a11 = S[5], a12 = S[9], a13 = S[13];
+	const float a20 = S[2], a21 = S[6], a22 = S[10], a23 = S[14];
+	const float a30 = S[3], a31 = S[7], a32 = S[11], a33 = S[15];
+	const float b00 = a00 * a11 - a01 * a10, b01 = a00 * a12 - a02 * a10, b02 = a00 * a13 - a03 * a10;
+	const float b03 = a01 * a12 - a02 * a11, b04 = a01 * a13 - a03 * a11, b05 = a02 * a13 - a03 * a12;
+	const float b06 = a20 * a31 - a21 * a30, b07 = a20 * a32 - a22 * a30, b08 = a20 * a33 - a23 * a30;
+	const float b09 = a21 * a32 - a22 * a31, b10 = a21 * a33 - a23 * a31, b11 = a22 * a33 - a23 * a32;
+	const float det = b00 * b11 - b01 * b10 + b02 * b09 + b03 * b08 - b04 * b07 + b05 * b06;
+	const float id = 1.0f / det;
+	// inverse entries inv[r][c] (row r, column c), rows 0..2 only
+	const float i00 = (a11 * b11 - a12 * b10 + a13 * b09) * id, i01 = (-a01 * b11 + a02 * b10 - a03 * b09) * id;
+	const float i02 = (a31 * b05 - a32 * b04 + a33 * b03) * id;
+	const float i10 = (-a10 * b11 + a12 * b08 - a13 * b07) * id, i11 = (a00 * b11 - a02 * b08 + a03 * b07) * id;
+	const float i12 = (-a30 * b05 + a32 * b02 - a33 * b01) * id;
+	const float i20 = (a10 * b10 - a11 * b08 + a13 * b06) * id, i21 = (-a00 * b10 + a01 * b08 - a03 * b06) * id;
+	const float i22 = (a30 * b04 - a31 * b02 + a33 * b00) * id;
+	const float i03 = (a22 * b04 - a21 * b05 - a23 * b03) * id, i13 = (a20 * b05 - a22 * b02 + a23 * b01) * id;
+	const float i23 = (a21 * b02 - a20 * b04 - a23 * b00) * id;
+	const float4 n = s.base_normals[i];
+	// row vector times matrix: out[c] = sum_r n[r] * inv[r][c]
+	float nx = n.x * i00 + n.y * i10 + n.z * i20;
+	float ny = n.x * i01 + n.y * i11 + n.z * i21;
+	float nz = n.x * i02 + n.y * i12 + n.z * i22;
+	// Reference behaviour kept: the product is a vec4 whose w = n . (translation column of the inverse) is NOT zero,
+	// and `result / result.length()` (mesh.cpp:43) divides by the length of all four components (math.h:797-806), so
+	// skinned normals come out slightly shorter than 1 wherever the skin matrix translates.
+	const float nw = n.x * i03 + n.y * i13 + n.z * i23;
+	const float len = sqrtf(nx * nx + ny * ny + nz * nz + nw * nw);
+	nx /= len, ny /= len, nz /= len;
+	s.out_normals[i] = make_float4(nx, ny, nz, 0.0f);
+}
+
+// mesh.cpp:428-449 (indexed) — vertex0..2, vN0..2 and the geometric normal of every triangle record
+__global__ void __launch_bounds__(128) k_update_triangles(const SkinView s)
+{
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= s.triangle_count)
+		return;
+	const uint32_t *ix = s.indices + size_t(t) * 3;
+	const float4 v0 = s.out_vertices[ix[0]], v1 = s.out_vertices[ix[1]], v2 = s.out_vertices[ix[2]];
+	const float4 n0 = s.out_normals[ix[0]], n1 = s.out_normals[ix[1]], n2 = s.out_normals[ix[2]];
+	const float e1x = v1.x - v0.x, e1y = v1.y - v0.y, e1z = v1.z - v0.z;
+	const float e2x = v2.x - v0.x, e2y = v2.y - v0.y, e2z = v2.z - v0.z;
+	float Nx = e1y * e2z - e1z * e2y, Ny = e1z * e2x - e1x * e2z, Nz = e1x * e2y - e1y * e2x;
+	const float il = 1.0f / sqrtf(Nx * Nx + Ny * Ny + Nz * Nz);
+	Nx *= il, Ny *= il, Nz *= il;
+	float4 *q = reinterpret_cast<float4 *>(s.mesh_tris) + size_t(t) * 10;
+	q[2] = make_float4(n0.x, n0.y, n0.z, Nx);
+	q[3] = make_float4(n1.x, n1.y, n1.z, Ny);
+	q[4] = make_float4(n2.x, n2.y, n2.z, Nz);
+	q[7] = make_float4(v0.x, v0.y, v0.z, q[7].w);
+	q[8] = make_float4(v1.x, v1.y, v1.z, q[8].w);
+	q[9] = make_float4(v2.x, v2.y, v2.z, q[9].w);
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+cudaError_t launch_refit(const GeometryView &g, cudaStream_t stream)
+{
+	if (g.node_count == 0)
+		return cudaSuccess;
+	cudaError_t e = cudaMemsetAsync(g.arrivals, 0, size_t(g.node_count) * sizeof(uint32_t), stream);
+	if (e != cudaSuccess)
+		return e;
+	const uint32_t threads = g.node_count * 4u;
+	k_refit<<<(threads + 255u) / 256u, 256, 0, stream>>>(g);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_flatten_shade(const GeometryView &g, cudaStream_t stream)
+{
+	if (g.flat_count == 0)
+		return cudaSuccess;
+	k_flatten_shade<<<(g.flat_count + 255u) / 256u, 256, 0, stream>>>(g);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_skin(const SkinView &s, cudaStream_t stream)
+{
+	if (s.vertex_count)
+		k_skin_vertices<<<(s.vertex_count + 127u) / 128u, 128, 0, stream>>>(s);
+	if (s.triangle_count)
+		k_update_triangles<<<(s.triangle_count + 127u) / 128u, 128, 0, stream>>>(s);
+	return cudaGetLastError();
+}
+
+} // namespace rfwb200

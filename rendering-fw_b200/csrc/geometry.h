@@ -1,0 +1,62 @@
+// geometry.h — device-side geometry pipeline (geometry.cu): instance flattening, BVH refit and skinning on the GPU
+#pragma once
+#include "device_types.h"
+
+#include <cuda_runtime.h>
+
+namespace rfwb200
+{
+
+// one instance of a mesh inside the device geometry arena, 128 B
+struct alignas(16) DeviceInstance
+{
+	float transform[16]; // column-major mat4 (rfw::RenderContext::set_instance, context.h:91)
+	float normal[9];	 // column-major normal matrix
+	float det_eps;		 // 1e-6 * |det(linear part)| (TriRec::det_eps)
+	uint32_t vert_off;	 // first vertex of the mesh in GeometryView::verts
+	uint32_t tri_off;	 // first triangle of the mesh in GeometryView::mesh_tris / indices
+	uint32_t flat_off;	 // first flattened triangle of this instance
+	uint32_t tri_count;
+	uint32_t pad[2];
+};
+static_assert(sizeof(DeviceInstance) == 128, "");
+
+struct GeometryView
+{
+	// arena (all meshes back to back)
+	const float4 *verts;	 // mesh-local vertices
+	const uint32_t *indices; // 3 per mesh triangle, mesh-local
+	const void *mesh_tris;	 // rfwb200_triangle[ ] (160 B)
+	const DeviceInstance *instances;
+	const uint32_t *flat_inst; // flattened triangle -> instance
+	uint32_t flat_count;
+	// BVH topology (static between builds)
+	BvhNode4 *nodes;
+	const uint32_t *tri_order;	 // leaf-ordered reference -> flattened triangle
+	const uint32_t *parent_slot; // (parent << 2) | slot, root 0xffffffff
+	uint32_t *arrivals;			 // one counter per node (zeroed by launch_refit)
+	uint32_t node_count, ref_count;
+	int write_boxes; // 1 = refit (recompute every box), 0 = only the records (fresh build: keep the builder's boxes)
+	// outputs
+	TriRec *out_tris;	 // [ref_count]
+	ShadeTri *out_shade; // [flat_count]
+};
+
+struct SkinView
+{
+	const float4 *base_vertices, *base_normals; // bind pose
+	const uint4 *joints;
+	const float4 *weights;
+	const float *joint_matrices; // mat4 column-major per joint
+	const uint32_t *indices;	 // of this mesh
+	float4 *out_vertices;		 // the mesh's slice of the arena
+	float4 *out_normals;		 // scratch, vertex_count
+	void *mesh_tris;			 // the mesh's slice of the arena's triangle records
+	uint32_t vertex_count, triangle_count;
+};
+
+cudaError_t launch_refit(const GeometryView &g, cudaStream_t stream);
+cudaError_t launch_flatten_shade(const GeometryView &g, cudaStream_t stream);
+cudaError_t launch_skin(const SkinView &s, cudaStream_t stream);
+
+} // namespace rfwb200

@@ -26,9 +26,23 @@
 // This file is compiled twice (rendering-fw_b200/Makefile): RFW_PART=1 builds the trace side — traversal, generate,
 // finalize, E-mode, stage-level kernels — with IEEE arithmetic, so hit points do not depend on approximate division;
 // RFW_PART=2 builds k_shade with -use_fast_math, as the reference builds its whole CUDA backend
-// (RFW/backends/CUDART/CMakeLists.txt:7-9).  RFW_PART=0 (default) is everything in one unit.
+// (RFW/backends/CUDART/CMakeLists.txt:7-9).  RFW_PART=3 builds the same shade kernel once more WITHOUT fast math under
+// the name k_shade_ieee (setting "shade_math" = "ieee"): the arithmetic of the CPU oracle, used by the parity tests that
+// compare images at scene scales where one ulp decides a connect ray.  RFW_PART=0 (default) is everything in one unit.
 #ifndef RFW_PART
 #define RFW_PART 0
+#endif
+#if RFW_PART == 3
+#define RFW_SHADE_ONLY 1
+#define K_SHADE k_shade_ieee
+#define LAUNCH_SHADE launch_shade_ieee
+#define SHADE_OCCUPANCY shade_occupancy_ieee
+#undef RFW_PART
+#define RFW_PART 2
+#else
+#define K_SHADE k_shade
+#define LAUNCH_SHADE launch_shade
+#define SHADE_OCCUPANCY shade_occupancy
 #endif
 
 namespace rfwb200
@@ -1311,7 +1325,7 @@ __device__ V3 RandomPointOnLight(const SceneView &sc, float r0, float r1, V3 I, 
 #ifndef SHADE_MINB
 #define SHADE_MINB 6 // 80 registers: measured 4.94 ms/frame vs 5.67 at 4 and 4.92 at 8 (spilling)
 #endif
-__global__ void __launch_bounds__(128, SHADE_MINB) k_shade(const SceneView sc, const ShardView sh, const WavefrontView wf,
+__global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, const ShardView sh, const WavefrontView wf,
 											  const RenderSettings rs, const uint32_t sample_in_frame,
 											  const uint32_t pathLength)
 {
@@ -1954,15 +1968,15 @@ cudaError_t launch_assemble(const ShardView &sh, const float4 *gathered, size_t 
 #endif // RFW_PART != 2 (trace part)
 
 #if RFW_PART != 1 // ---- shade part ----
-cudaError_t launch_shade(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
+cudaError_t LAUNCH_SHADE(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
 						 uint32_t sample_in_frame, uint32_t depth, const LaunchDims &dims, cudaStream_t stream)
 {
-	k_shade<<<dims.shade_grid, dims.shade_block, 0, stream>>>(sc, sh, wf, rs, sample_in_frame, depth);
+	K_SHADE<<<dims.shade_grid, dims.shade_block, 0, stream>>>(sc, sh, wf, rs, sample_in_frame, depth);
 	return cudaGetLastError();
 }
-cudaError_t shade_occupancy(int block, int *per_sm)
+cudaError_t SHADE_OCCUPANCY(int block, int *per_sm)
 {
-	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_shade, block, 0);
+	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, K_SHADE, block, 0);
 }
 #endif // RFW_PART != 1 (shade part)
 

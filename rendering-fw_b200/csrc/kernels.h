@@ -24,6 +24,9 @@ cudaError_t launch_primary(const SceneView &sc, const ShardView &sh, const Wavef
 						   uint32_t sample_in_frame, const LaunchDims &dims, cudaStream_t stream);
 cudaError_t launch_shade(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
 						 uint32_t sample_in_frame, uint32_t depth, const LaunchDims &dims, cudaStream_t stream);
+// the same kernel built without -use_fast_math (setting "shade_math" = "ieee")
+cudaError_t launch_shade_ieee(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
+							  uint32_t sample_in_frame, uint32_t depth, const LaunchDims &dims, cudaStream_t stream);
 cudaError_t launch_trace(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
 						 uint32_t sample_in_frame, uint32_t depth, const LaunchDims &dims, cudaStream_t stream);
 cudaError_t launch_finalize(const ShardView &sh, const WavefrontView &wf, float scale, cudaStream_t stream);

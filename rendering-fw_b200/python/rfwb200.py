@@ -113,6 +113,19 @@ class FrameCounters(C.Structure):
                 self.n_acc * 32 + self.pixels * 32)
 
 
+class GeometryStats(C.Structure):
+    _fields_ = [("on_device", C.c_int32), ("was_refit", C.c_int32), ("device_ms", C.c_float), ("host_ms", C.c_float),
+                ("refits", C.c_uint64), ("builds", C.c_uint64)]
+
+
+BVH_NODE_DTYPE = np.dtype([("minx", "<f4", 4), ("maxx", "<f4", 4), ("miny", "<f4", 4), ("maxy", "<f4", 4), ("minz", "<f4", 4),
+                           ("maxz", "<f4", 4), ("child", "<i4", 4), ("pad", "<i4", 4)])
+TRI_REC_DTYPE = np.dtype([("p0", "<f4", 3), ("e1", "<f4", 3), ("e2", "<f4", 3), ("shade_idx", "<u4"), ("det_eps", "<f4"), ("pad0", "<u4")])
+SHADE_TRI_DTYPE = np.dtype([("u", "<f4", 3), ("light_tri_idx", "<i4"), ("v", "<f4", 3), ("material", "<u4"),
+                            ("n0", "<f4", 3), ("Nx", "<f4"), ("n1", "<f4", 3), ("Ny", "<f4"), ("n2", "<f4", 3), ("Nz", "<f4"),
+                            ("area", "<f4"), ("lod", "<f4"), ("inst_id", "<u4"), ("prim_id", "<u4")])
+assert BVH_NODE_DTYPE.itemsize == 128 and TRI_REC_DTYPE.itemsize == 48 and SHADE_TRI_DTYPE.itemsize == 96
+
 assert C.sizeof(TextureData) == 32 and C.sizeof(Mesh) == 56 and C.sizeof(CameraView) == 56 and C.sizeof(RenderStats) == 48
 
 
@@ -365,6 +378,43 @@ class RenderContext:
         self._check(self.L.fn("get_bvh_info", C.c_int, [C.c_void_p] + [C.c_void_p] * 4)(
             self._h, C.byref(n), C.byref(t), C.byref(s), C.byref(ms)))
         return {"nodes": int(n.value), "triangles": int(t.value), "sah_cost": float(s.value), "build_ms": float(ms.value)}
+
+    # -- device geometry (product-only extensions: GPU skinning + refit) --
+    def set_mesh_skin(self, mesh_index: int, base_vertices, base_normals, joints, weights):
+        """bind pose of a skinned mesh: vec4 vertices, vec3/vec4 normals, uvec4 joints, vec4 weights per vertex
+        (rfw::geometry::gltf::SceneMesh::baseVertices/baseNormals/joints/weights)."""
+        v = _f32(base_vertices, (-1, 4))
+        n = np.asarray(base_normals, np.float32)
+        n = n.reshape(len(v), -1)
+        n4 = np.zeros((len(v), 4), np.float32)
+        n4[:, : min(n.shape[1], 3)] = n[:, :3]
+        j = np.ascontiguousarray(joints, dtype=np.uint32).reshape(len(v), 4)
+        w = _f32(weights, (len(v), 4))
+        self._check(self.L.fn("set_mesh_skin", C.c_int, [C.c_void_p, C.c_size_t] + [C.c_void_p] * 4 + [C.c_size_t])(
+            self._h, mesh_index, v.ctypes.data, n4.ctypes.data, j.ctypes.data, w.ctypes.data, len(v)))
+
+    def set_mesh_pose(self, mesh_index: int, joint_matrices):
+        """joint_matrices: (n_joints, 4, 4) in the mathematical (row, col) convention; sent column-major like glm."""
+        m = np.asarray(joint_matrices, np.float32).reshape(-1, 4, 4)
+        cm = np.ascontiguousarray(np.transpose(m, (0, 2, 1)))
+        self._check(self.L.fn("set_mesh_pose", C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t])(
+            self._h, mesh_index, cm.ctypes.data, len(cm)))
+
+    def get_geometry_stats(self) -> GeometryStats:
+        g = GeometryStats()
+        self._check(self.L.fn("get_geometry_stats", C.c_int, [C.c_void_p, C.c_void_p])(self._h, C.byref(g)))
+        return g
+
+    def debug_read_scene(self, which: str) -> np.ndarray:
+        """'nodes' | 'tris' | 'shade' of the committed device scene, as structured arrays."""
+        code, dt = {"nodes": (0, BVH_NODE_DTYPE), "tris": (1, TRI_REC_DTYPE), "shade": (2, SHADE_TRI_DTYPE)}[which]
+        f = self.L.fn("debug_read_scene", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p])
+        nbytes = C.c_size_t()
+        self._check(f(self._h, code, None, 0, C.byref(nbytes)))
+        out = np.zeros(nbytes.value // dt.itemsize, dt)
+        if nbytes.value:
+            self._check(f(self._h, code, out.ctypes.data, out.nbytes, C.byref(nbytes)))
+        return out
 
     # -- stage-level --
     def trace_closest(self, origins: np.ndarray, directions: np.ndarray, t_min: float = 1e-5) -> np.ndarray:

@@ -480,6 +480,118 @@ def _cylinder(base, radius, height, seg, rings, material, tex_dims=None):
     return SceneMesh(np.concatenate([verts, np.ones((len(verts), 1), np.float32)], 1), tri, idx)
 
 
+# ------------------------------------------------------------------------------------------------
+# config 4 ingredients: a skinned mesh (stand-in for CesiumMan when the asset is not baked): a tube with a chain of
+# joints and smooth weights, standing on a floor under the config-2 light rule
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class Skin:
+    mesh_index: int
+    base_vertices: np.ndarray  # (nv, 4)
+    base_normals: np.ndarray  # (nv, 3)
+    joints: np.ndarray  # (nv, 4) uint32
+    weights: np.ndarray  # (nv, 4)
+    n_joints: int
+    poses: object = None  # callable t -> (n_joints, 4, 4) float32 joint matrices, or an array (frames, n_joints, 4, 4)
+
+    def joint_matrices(self, k: int) -> np.ndarray:
+        if callable(self.poses):
+            return self.poses(k)
+        return np.asarray(self.poses[k % len(self.poses)], np.float32)
+
+
+def _rot_z(a):
+    m = np.eye(4)
+    m[0, 0], m[0, 1], m[1, 0], m[1, 1] = math.cos(a), -math.sin(a), math.sin(a), math.cos(a)
+    return m
+
+
+def skinned_tube(seg=24, rings=32, n_joints=4, height=2.0, radius=0.25):
+    """-> (Scene, Skin).  Mesh 0 = floor, 1 = light, 2 = the tube (indexed, smooth normals)."""
+    s = Scene(name="skinned-tube")
+    grey = add_material(s, (0.7, 0.7, 0.7))
+    light = add_material(s, (20, 20, 18))
+    skin_mat = add_material(s, (0.8, 0.45, 0.3), roughness=0.6)
+    tube = _cylinder((0, 0, 0), radius, height, seg, rings, skin_mat)
+    s.meshes = [quad((0, 1, 0), (0, 0, 0), 12, 12, grey), quad((0, -1, 0), (0, 4.5, 0), 3, 3, light), tube]
+    s.instances = [(0, np.eye(4)), (1, np.eye(4)), (2, translate(0.2, 0.0, 0.1) @ rotate_y(20))]
+    s.sky = (np.full((1, 3), 0.15, np.float32), 1, 1)
+    s.camera_pos, s.camera_dir, s.fov = (0.0, 1.4, -5.0), (0.0, -0.05, 1.0), 40.0
+    v = tube.vertices
+    # joint j sits at height j * height / n_joints; a vertex is bound to the two (up to four) nearest joints
+    seg_h = height / n_joints
+    jpos = np.arange(n_joints) * seg_h
+    d = np.abs(v[:, 1:2] - (jpos[None, :] + 0.5 * seg_h))
+    order = np.argsort(d, axis=1)[:, :4]
+    if order.shape[1] < 4:
+        order = np.concatenate([order, np.repeat(order[:, :1], 4 - order.shape[1], 1)], 1)
+    w = np.maximum(1.0 - np.take_along_axis(d, order, 1) / seg_h, 0.0)
+    w[:, 2:] = 0.0
+    w = (w / np.maximum(w.sum(1, keepdims=True), 1e-9)).astype(np.float32)
+    nrm = np.zeros((len(v), 3), np.float32)
+    idx = tube.indices
+    for k, key in enumerate(("vN0", "vN1", "vN2")):
+        nrm[idx[:, k]] = tube.triangles[key]
+
+    def poses(k: int) -> np.ndarray:
+        t = k / 60.0
+        out, acc = [], np.eye(4)
+        for j in range(n_joints):
+            a = 0.35 * math.sin(2.0 * t + 0.9 * j)
+            # rotate about the joint's own pivot (0, jpos[j], 0), accumulated down the chain
+            acc = acc @ translate(0, jpos[j], 0) @ _rot_z(a) @ translate(0, -jpos[j], 0)
+            out.append(acc.copy())
+        return np.asarray(out, np.float32)
+
+    return s, Skin(2, v.copy(), nrm, order.astype(np.uint32), w, n_joints, poses)
+
+
+CESIUMMAN_BAKED = R.PKG_DIR / "data" / "_baked" / "cesiumman.npz"
+
+
+def animated_config4(copies: int = 1):
+    """BASELINE.json configs[3]: CesiumMan (baked by tools/bake_cesiumman.py; the skinned tube
+    stands in when the bake is absent) on a 50x50 floor under the config-2 light quad (20x100, radiance 100, y = 60).
+    -> (Scene, [Skin per skinned mesh]).  `copies` > 1 places several independently skinned copies (scaling runs)."""
+    s = Scene(name="config4")
+    grey = add_material(s, (0.6, 0.6, 0.6))
+    light = add_material(s, (100, 100, 100))
+    s.meshes = [quad((0, 1, 0), (0, 0, 0), 50, 50, grey), quad((0, -1, 0), (0, 0, 0), 20, 100, light)]
+    s.instances = [(0, np.eye(4)), (1, translate(0, 60, 0))]
+    skins = []
+    if CESIUMMAN_BAKED.exists():
+        d = np.load(CESIUMMAN_BAKED)
+        s.name = "config4-cesiumman"
+        tex = -1
+        if d["texture"].size:
+            tex = add_texture_rgba8(s, d["texture"])
+        mat = add_material(s, (1, 1, 1), roughness=0.8, tex0=tex)
+        pos, nrm, uv, idx = d["positions"], d["normals"], d["uvs"], d["indices"]
+        tex_dims = d["texture"].shape[1::-1] if d["texture"].size else None
+        tri = make_triangles(pos[idx], nrm[idx], uv[idx], mat, tex_dims)
+        v4 = np.concatenate([pos, np.ones((len(pos), 1), np.float32)], 1)
+        base_xf, poses = d["mesh_transform"], d["poses"]
+        for c in range(copies):
+            mi = len(s.meshes)
+            s.meshes.append(SceneMesh(v4.copy(), tri.copy(), idx.copy()))
+            s.instances.append((mi, translate(1.2 * ((c + 1) // 2) * (-1 if c % 2 else 1), 0, 0.8 * (c // 8)) @ base_xf))
+            skins.append(Skin(mi, v4, nrm, d["joints"], d["weights"], poses.shape[1], np.roll(poses, 7 * c, axis=0)))
+        s.camera_pos, s.camera_dir, s.fov = (0.6, 0.95, 2.3), (-0.25, -0.08, -1.0), 40.0
+    else:
+        tube_scene, sk = skinned_tube(seg=48, rings=48)
+        mat = add_material(s, (0.8, 0.45, 0.3), roughness=0.6)
+        tube = tube_scene.meshes[sk.mesh_index]
+        tube.triangles["material"] = mat
+        for c in range(copies):
+            mi = len(s.meshes)
+            s.meshes.append(SceneMesh(tube.vertices.copy(), tube.triangles.copy(), tube.indices.copy()))
+            s.instances.append((mi, translate(1.2 * ((c + 1) // 2) * (-1 if c % 2 else 1), 0, 0.8 * (c // 8))))
+            skins.append(Skin(mi, sk.base_vertices, sk.base_normals, sk.joints, sk.weights, sk.n_joints, sk.poses))
+        s.camera_pos, s.camera_dir, s.fov = (0.0, 1.2, -5.0), (0.0, -0.04, 1.0), 40.0
+    s.sky = (np.full((1, 3), 0.3, np.float32), 1, 1)
+    return s, skins
+
+
 def atrium(target_tris=262_000, seed=11) -> Scene:
     rng = np.random.default_rng(seed)
     s = Scene(name=f"atrium-{target_tris}")

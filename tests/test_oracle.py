@@ -215,3 +215,41 @@ def test_golden_frames(oracle_lib, scene):
         assert np.allclose(img, ref, rtol=2e-4, atol=2e-5), (mode, depth, np.abs(img - ref).max())
         counters = np.array(list(ctx.get_frame_counters().as_dict().values()), np.uint64)
         assert np.abs(counters.astype(np.int64) - g[f"{scene}_{mode}_d{depth}_counters"].astype(np.int64)).max() <= 2
+
+
+# ---- skinning restatement (oracle/skinning.py; gltf/mesh.cpp:18-48, 428-449) ---------------------------------
+def test_skinning_restatement_known_answers():
+    from oracle import skinning as K
+
+    sc, sk = S.skinned_tube()
+    m = sc.meshes[sk.mesh_index]
+    # identity joints: the bind pose comes back
+    I = np.broadcast_to(np.eye(4, dtype=np.float32), (sk.n_joints, 4, 4))
+    v, n = K.set_pose(sk.base_vertices, sk.base_normals, sk.joints, sk.weights, I)
+    assert np.allclose(v, sk.base_vertices, atol=1e-6) and np.allclose(n, sk.base_normals, atol=1e-6)
+    t = K.update_triangles(m.triangles, v, n, m.indices)
+    assert np.allclose(t["vertex1"], m.triangles["vertex1"], atol=1e-6)
+    # one rotation on every joint: vertices move rigidly, normals rotate, lengths stay 1
+    Rm = S.rotate_y(33.0).astype(np.float32)
+    v, n = K.set_pose(sk.base_vertices, sk.base_normals, sk.joints, sk.weights, np.broadcast_to(Rm, (sk.n_joints, 4, 4)))
+    assert np.allclose(v, sk.base_vertices @ Rm.T, atol=2e-6)
+    assert np.allclose(n, sk.base_normals @ Rm[:3, :3].T, atol=2e-6)
+    assert np.allclose(np.linalg.norm(n, axis=1), 1.0, atol=1e-6)
+    # with a translation the reference's vec4 length (math.h:797-806) includes w = n . t_inv: direction right, length < 1
+    Tm = (S.translate(0.3, -0.1, 0.2) @ S.rotate_y(33.0)).astype(np.float32)
+    v, n = K.set_pose(sk.base_vertices, sk.base_normals, sk.joints, sk.weights, np.broadcast_to(Tm, (sk.n_joints, 4, 4)))
+    assert np.allclose(v, sk.base_vertices @ Tm.T, atol=2e-6)
+    rot = sk.base_normals @ Tm[:3, :3].T
+    ln = np.linalg.norm(n, axis=1, keepdims=True)
+    assert np.allclose(n / ln, rot, atol=2e-6) and (ln <= 1.0 + 1e-6).all() and ln.min() < 0.999
+    # non-uniform scale: normals follow the inverse transpose
+    Sm = np.diag([2.0, 0.5, 1.0, 1.0]).astype(np.float32)
+    v, n = K.set_pose(sk.base_vertices, sk.base_normals, sk.joints, sk.weights, np.broadcast_to(Sm, (sk.n_joints, 4, 4)))
+    expect = sk.base_normals @ np.linalg.inv(Sm[:3, :3])
+    expect /= np.linalg.norm(expect, axis=1, keepdims=True)
+    assert np.allclose(n, expect, atol=2e-6)
+    # the animated pose keeps the surface closed: geometric normals agree with the skinned vertex normals
+    v, n = K.set_pose(sk.base_vertices, sk.base_normals, sk.joints, sk.weights, sk.joint_matrices(40))
+    t = K.update_triangles(m.triangles, v, n, m.indices)
+    gn = np.stack([t["Nx"], t["Ny"], t["Nz"]], 1)
+    assert (np.einsum("ij,ij->i", gn, t["vN0"]) > 0.5).mean() > 0.99
