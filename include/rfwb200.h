@@ -354,6 +354,13 @@ RFWB200_API int rfwb200_host_bvh_check(const float *tris9, size_t n_tris, int sp
 									   uint64_t *refs_out, int32_t *depth_out, float *sah_out,
 									   uint32_t *visits_out /* optional: node visits, triangle tests per ray */);
 
+/* The same check for the compressed 8-wide BVH (csrc/cwbvh.h) the kernels walk by default; refit_jitter > 0 moves the
+ * vertices and refits on the host before tracing; tris9_out (optional) receives the triangles that were traced. */
+RFWB200_API int rfwb200_host_cwbvh_check(const float *tris9, size_t n_tris, int spatial_splits, float refit_jitter,
+										 const float *origins3, const float *dirs3, size_t n_rays, float *t_out,
+										 int32_t *tri_out, uint64_t *nodes_out, uint64_t *refs_out, int32_t *depth_out,
+										 float *sah_out, uint32_t *visits_out, float *tris9_out);
+
 #ifdef __cplusplus
 } /* extern "C" */
 

@@ -8,6 +8,7 @@
 // budget bounds the number of duplicated references.  Large subtrees are built by a pool of host threads.
 // The BVH2 is then collapsed to 4-wide (open the child with the largest area) and laid out breadth-first.
 #include "bvh_build.h"
+#include "cwbvh.h"
 
 #include <algorithm>
 #include <atomic>
@@ -28,7 +29,7 @@ namespace
 
 constexpr int BINS = 16;
 constexpr int SPATIAL_BINS = 32;
-constexpr int MAX_LEAF = 4;
+constexpr int MAX_LEAF = 4; // 4-wide layout; the compressed 8-wide layout takes 3 (Builder::max_leaf)
 constexpr int MAX_DEPTH2 = 31;			// BVH2 depth bound => BVH4 depth <= 31 => stack <= 94 + sentinel <= TRAVERSAL_STACK
 constexpr size_t PAR_THRESHOLD = 16384; // subtrees above this many references become pool tasks
 constexpr float BOX_PAD = 1e-5f;		// reference pads primitive and node boxes by 1e-5 (bvh_tree.cpp:446, bvh_node.h:221)
@@ -141,6 +142,8 @@ struct Builder
 	std::atomic<int64_t> spare_refs{0}; // remaining duplication budget
 	float root_area = 1.0f;
 	bool spatial = true;
+	int max_leaf = MAX_LEAF;
+	int max_depth2 = MAX_DEPTH2;
 
 	std::mutex mtx;
 	std::condition_variable cv;
@@ -176,8 +179,8 @@ struct Builder
 				c[a] = (r.box.lo[a] + r.box.hi[a]) * 0.5f;
 			cb.grow(c);
 		}
-		const int levels_needed = ceil_log2((count + MAX_LEAF - 1) / MAX_LEAF);
-		const bool force_median = t.depth + levels_needed >= MAX_DEPTH2;
+		const int levels_needed = ceil_log2((count + max_leaf - 1) / max_leaf);
+		const bool force_median = t.depth + levels_needed >= max_depth2;
 
 		// ---- object split: binned SAH on reference centroids -------------------------------------------
 		int obj_axis = -1, obj_bin = -1;
@@ -234,7 +237,7 @@ struct Builder
 		// ---- spatial split: chopped binning over the node box ---------------------------------------------
 		int sp_axis = -1;
 		float sp_pos = 0.0f, sp_cost = 3.0e38f;
-		if (spatial && !force_median && count > MAX_LEAF && spare_refs.load(std::memory_order_relaxed) > 0 &&
+		if (spatial && !force_median && count > uint32_t(max_leaf) && spare_refs.load(std::memory_order_relaxed) > 0 &&
 			(obj_axis < 0 || obj_overlap > SPATIAL_ALPHA * root_area))
 		{
 			for (int axis = 0; axis < 3; axis++)
@@ -298,7 +301,7 @@ struct Builder
 		const float leaf_cost = float(count) * node_area;
 		const float best_cost = std::min(obj_cost, sp_cost);
 		const float split_cost = node_area * 1.0f + best_cost; // C_trav = C_isect = 1
-		if (count <= MAX_LEAF && (best_cost >= 3.0e38f || split_cost >= leaf_cost))
+		if (count <= uint32_t(max_leaf) && (best_cost >= 3.0e38f || split_cost >= leaf_cost))
 		{
 			make_leaf(node, refs);
 			return false;
@@ -482,20 +485,9 @@ inline Box child_box(const BvhNode4 &n, int slot)
 
 } // namespace
 
-void build_bvh4(const BuildTriangle *tris, size_t count, int threads, BvhBuildResult &out, bool spatial_splits)
+// top-down SBVH over the triangles into b.nodes (BVH2); returns the number of references the tree may hold
+static size_t build_tree2(Builder &b, const BuildTriangle *tris, size_t count, int threads, bool spatial_splits)
 {
-	const auto t0 = std::chrono::steady_clock::now();
-	out = BvhBuildResult();
-	if (count == 0)
-	{
-		BvhNode4 root;
-		memset(&root, 0, sizeof(root));
-		for (int s = 0; s < 4; s++)
-			set_child_empty(root, s);
-		out.nodes.push_back(root);
-		out.node_parent.push_back(0xffffffffu);
-		return;
-	}
 	std::unique_ptr<Task> root(new Task());
 	root->node = 0, root->depth = 0;
 	root->refs.resize(count);
@@ -507,7 +499,6 @@ void build_bvh4(const BuildTriangle *tris, size_t count, int threads, BvhBuildRe
 		root->refs[i].prim = uint32_t(i);
 		root_box.grow(root->refs[i].box);
 	}
-	Builder b;
 	b.tris = tris;
 	b.spatial = spatial_splits;
 	b.root_area = std::max(root_box.area(), 1e-30f);
@@ -529,6 +520,25 @@ void build_bvh4(const BuildTriangle *tris, size_t count, int threads, BvhBuildRe
 	}
 	else
 		b.build_serial(std::move(root));
+	return max_refs;
+}
+
+void build_bvh4(const BuildTriangle *tris, size_t count, int threads, BvhBuildResult &out, bool spatial_splits)
+{
+	const auto t0 = std::chrono::steady_clock::now();
+	out = BvhBuildResult();
+	if (count == 0)
+	{
+		BvhNode4 root;
+		memset(&root, 0, sizeof(root));
+		for (int s = 0; s < 4; s++)
+			set_child_empty(root, s);
+		out.nodes.push_back(root);
+		out.node_parent.push_back(0xffffffffu);
+		return;
+	}
+	Builder b;
+	const size_t max_refs = build_tree2(b, tris, count, threads, spatial_splits);
 
 	// ---- collapse to 4-wide, breadth-first layout; leaves get their slice of the triangle order here ----
 	const std::vector<Node2> &n2 = b.nodes;
@@ -646,6 +656,212 @@ void refit_bvh4(const BuildTriangle *tris, size_t count, BvhBuildResult &bvh)
 			}
 			set_child_box(n, s, b);
 		}
+	}
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// compressed 8-wide layout (cwbvh.h)
+// ------------------------------------------------------------------------------------------------
+void build_cwbvh(const BuildTriangle *tris, size_t count, int threads, BvhBuildResult &out, bool spatial_splits)
+{
+	const auto t0 = std::chrono::steady_clock::now();
+	out = BvhBuildResult();
+	out.wide8 = true;
+	if (count == 0)
+	{
+		CwNode root;
+		memset(&root, 0, sizeof(root));
+		CwAux aux;
+		memset(&aux, 0, sizeof(aux));
+		cw_quantize(root, aux);
+		out.cw_nodes.push_back(root), out.cw_aux.push_back(aux), out.cw_parent_slot.push_back(0xffffffffu);
+		return;
+	}
+	Builder b;
+	b.max_leaf = 3;				  // a leaf slot holds 1-3 triangles (unary count in three meta bits)
+	b.max_depth2 = CW_MAX_DEPTH; // one stack entry per level at most
+	const size_t max_refs = build_tree2(b, tris, count, threads, spatial_splits);
+	const std::vector<Node2> &n2 = b.nodes;
+	// The SAH builder (C_trav = C_isect) splits down to 1-2 triangles per leaf, which leaves wide nodes half empty.
+	// A BVH2 subtree holding <= 3 distinct triangles becomes ONE leaf slot here (the wide node pays per node visit,
+	// not per triangle: Ylitie et al. section 3.1 fold the same decision into their collapse cost).
+	const int32_t n_nodes2 = b.next_node.load();
+	std::vector<uint32_t> sub(size_t(n_nodes2), 0);
+	for (int32_t i = n_nodes2; i-- > 0;) // children are allocated after their parents
+		sub[i] = n2[i].leaf ? uint32_t(n2[i].prims.size()) : (sub[n2[i].left] + sub[n2[i].right]);
+	auto gather = [&](int32_t root, std::vector<uint32_t> &prims) {
+		prims.clear();
+		int32_t st[16];
+		int sp = 0;
+		st[sp++] = root;
+		while (sp)
+		{
+			const Node2 &c = n2[st[--sp]];
+			if (c.leaf)
+			{
+				for (uint32_t pr : c.prims)
+					if (std::find(prims.begin(), prims.end(), pr) == prims.end())
+						prims.push_back(pr);
+			}
+			else
+				st[sp++] = c.left, st[sp++] = c.right;
+		}
+	};
+	auto is_leaf = [&](int32_t i) { return n2[i].leaf || sub[i] <= 3u; };
+	std::vector<uint32_t> leaf_prims;
+	struct Pending
+	{
+		int32_t n2;
+		uint32_t parent_slot;
+		int depth;
+	};
+	std::vector<Pending> fifo;
+	fifo.reserve(count / 2 + 1);
+	out.tri_order.reserve(max_refs);
+	fifo.push_back({0, 0xffffffffu, 1});
+	float cost = 0;
+	const float inv_root_area = 1.0f / b.root_area;
+	int max_depth = 1;
+	for (size_t head = 0; head < fifo.size(); head++)
+	{
+		const Pending p = fifo[head];
+		const Node2 &src = n2[p.n2];
+		int32_t kids[8];
+		int nk = 0;
+		if (is_leaf(p.n2))
+			kids[nk++] = p.n2; // the root is a leaf
+		else
+		{
+			kids[nk++] = src.left, kids[nk++] = src.right;
+			while (nk < 8)
+			{
+				int best = -1;
+				float best_area = -1;
+				for (int k = 0; k < nk; k++)
+				{
+					const Node2 &c = n2[kids[k]];
+					if (!is_leaf(kids[k]) && c.box.area() > best_area)
+						best_area = c.box.area(), best = k;
+				}
+				if (best < 0)
+					break;
+				const Node2 &c = n2[kids[best]];
+				kids[best] = c.left;
+				kids[nk++] = c.right;
+			}
+		}
+		cost += src.box.area() * inv_root_area;
+		// slot assignment: child with the largest projection of (centroid - node centroid) on a slot's octant
+		// direction takes that slot, greedily (Ylitie et al. section 3.2 use an auction; greedy is within a few %)
+		float nc[3];
+		for (int a = 0; a < 3; a++)
+			nc[a] = 0.5f * (src.box.lo[a] + src.box.hi[a]);
+		int slot_of[8], kid_in[8];
+		for (int k = 0; k < 8; k++)
+			slot_of[k] = -1, kid_in[k] = -1;
+		for (int round = 0; round < nk; round++)
+		{
+			float best = -3.0e38f;
+			int bk = -1, bs = -1;
+			for (int k = 0; k < nk; k++)
+			{
+				if (slot_of[k] >= 0)
+					continue;
+				const Box &cb = n2[kids[k]].box;
+				const float d[3] = {0.5f * (cb.lo[0] + cb.hi[0]) - nc[0], 0.5f * (cb.lo[1] + cb.hi[1]) - nc[1],
+									0.5f * (cb.lo[2] + cb.hi[2]) - nc[2]};
+				for (int sl = 0; sl < 8; sl++)
+				{
+					if (kid_in[sl] >= 0)
+						continue;
+					const float v = ((sl & 4) ? d[0] : -d[0]) + ((sl & 2) ? d[1] : -d[1]) + ((sl & 1) ? d[2] : -d[2]);
+					if (v > best)
+						best = v, bk = k, bs = sl;
+				}
+			}
+			slot_of[bk] = bs, kid_in[bs] = bk;
+		}
+		CwNode node;
+		memset(&node, 0, sizeof(node));
+		CwAux aux;
+		memset(&aux, 0, sizeof(aux));
+		node.child_base = uint32_t(fifo.size());
+		node.tri_base = uint32_t(out.tri_order.size());
+		const uint32_t self = uint32_t(head);
+		for (int sl = 0; sl < 8; sl++)
+		{
+			if (kid_in[sl] < 0)
+				continue;
+			const Node2 &c = n2[kids[kid_in[sl]]];
+			const Box pb = padded(c.box);
+			for (int a = 0; a < 3; a++)
+				aux.lo[a][sl] = pb.lo[a], aux.hi[a][sl] = pb.hi[a];
+			if (is_leaf(kids[kid_in[sl]]))
+			{
+				gather(kids[kid_in[sl]], leaf_prims);
+				const uint32_t off = uint32_t(out.tri_order.size()) - node.tri_base;
+				const uint32_t cnt = uint32_t(std::min<size_t>(leaf_prims.size(), 3));
+				if (cnt == 0)
+					continue; // cannot happen: the builder never makes empty leaves
+				for (uint32_t i = 0; i < cnt; i++)
+					out.tri_order.push_back(leaf_prims[i]);
+				node.meta[sl] = uint8_t((((1u << cnt) - 1u) << 5) | off);
+				cost += c.box.area() * inv_root_area * float(cnt);
+			}
+			else
+			{
+				node.meta[sl] = uint8_t(0x20u | (24u + uint32_t(sl)));
+				node.imask |= uint8_t(1u << sl);
+				fifo.push_back({kids[kid_in[sl]], (self << 3) | uint32_t(sl), p.depth + 1});
+				max_depth = std::max(max_depth, p.depth + 1);
+			}
+		}
+		cw_quantize(node, aux);
+		out.cw_nodes.push_back(node), out.cw_aux.push_back(aux), out.cw_parent_slot.push_back(p.parent_slot);
+	}
+	out.sah_cost = cost;
+	out.depth = max_depth;
+	out.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+void refit_cwbvh(const BuildTriangle *tris, size_t count, BvhBuildResult &bvh)
+{
+	(void)count;
+	// children are stored after their parents (breadth-first): walk backwards so a child's boxes are final before its
+	// parent reads them; boxes come from whole triangles, as in refit_bvh4
+	for (size_t ni = bvh.cw_nodes.size(); ni-- > 0;)
+	{
+		CwNode &n = bvh.cw_nodes[ni];
+		CwAux &a = bvh.cw_aux[ni];
+		uint32_t inner_rank = 0;
+		for (int s = 0; s < 8; s++)
+		{
+			const uint32_t meta = n.meta[s];
+			if (!meta)
+				continue;
+			Box b;
+			b.reset();
+			if ((meta & 0x18u) == 0x18u)
+			{
+				const size_t ci = size_t(n.child_base) + inner_rank++;
+				const CwNode &cn = bvh.cw_nodes[ci];
+				const CwAux &ca = bvh.cw_aux[ci];
+				for (int k = 0; k < 8; k++)
+					if (cn.meta[k])
+						for (int ax = 0; ax < 3; ax++)
+							b.lo[ax] = std::min(b.lo[ax], ca.lo[ax][k]), b.hi[ax] = std::max(b.hi[ax], ca.hi[ax][k]);
+			}
+			else
+			{
+				const uint32_t first = n.tri_base + (meta & 31u), cnt = uint32_t(__builtin_popcount(meta >> 5));
+				for (uint32_t i = first; i < first + cnt; i++)
+					b.grow(padded(tri_box(tris[bvh.tri_order[i]])));
+			}
+			for (int ax = 0; ax < 3; ax++)
+				a.lo[ax][s] = b.lo[ax], a.hi[ax][s] = b.hi[ax];
+		}
+		cw_quantize(n, a);
 	}
 }
 

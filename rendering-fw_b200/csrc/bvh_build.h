@@ -3,6 +3,7 @@
 // (RFW/system/bvh/src/bvh_tree.cpp:48-102, mbvh_tree.cpp:26-49) and the in-tree binned-SAH spec
 // (RFW/system/bvh/include/bvh/bvh_node.h:136-233) + MBVH collapse (src/mbvh_node.cpp:194-374).
 #pragma once
+#include "cwbvh.h"
 #include "device_types.h"
 
 #include <cstddef>
@@ -22,6 +23,11 @@ struct BvhBuildResult
 	std::vector<uint32_t> tri_order;   // leaf-ordered position -> input triangle index (spatial splits may
 									   // reference a triangle from several leaves, so size() >= triangle count)
 	std::vector<uint32_t> node_parent; // for refit: parent index per node (root: 0xffffffff)
+	// compressed 8-wide layout (cwbvh.h), filled by build_cwbvh instead of nodes / node_parent
+	bool wide8 = false;
+	std::vector<CwNode> cw_nodes;			// breadth-first, root = 0
+	std::vector<CwAux> cw_aux;				// full-precision child boxes, for refits
+	std::vector<uint32_t> cw_parent_slot;	// (parent << 3) | slot, root 0xffffffff
 	float sah_cost = 0;
 	int depth = 0;
 	double build_ms = 0;
@@ -36,6 +42,11 @@ void build_bvh4(const BuildTriangle *tris, size_t count, int threads, BvhBuildRe
 // Recompute all boxes bottom-up for moved vertices with unchanged topology (the reference's refit,
 // bvh_tree.cpp:104-114, top_level_bvh.cpp:46-52).
 void refit_bvh4(const BuildTriangle *tris, size_t count, BvhBuildResult &bvh);
+
+// The same SBVH collapsed to 8-wide nodes with quantised child boxes (cwbvh.h): leaves of <= 3 triangles, children
+// placed in octant-ordered slots, depth <= CW_MAX_DEPTH.
+void build_cwbvh(const BuildTriangle *tris, size_t count, int threads, BvhBuildResult &out, bool spatial_splits = true);
+void refit_cwbvh(const BuildTriangle *tris, size_t count, BvhBuildResult &bvh);
 
 constexpr int TRAVERSAL_STACK = 96; // ints per thread in the kernels; builder keeps 3*depth+1 below this
 

@@ -164,6 +164,8 @@ struct rfwb200_context
 	bool geo_timed = false, last_update_on_device = false, last_update_was_refit = false;
 	uint64_t refits = 0, builds = 0;
 	bool shade_ieee = false; // setting "shade_math" = fast | ieee
+	bool wide8 = false;		 // setting "bvh" = 4 | 8 (compressed 8-wide layout, cwbvh.h)
+	DevBuf d_cw_nodes, d_nodes16;
 
 	// ---- wavefront state -----------------------------------------------------------------------------
 	DevBuf d_debug;
@@ -186,7 +188,7 @@ struct rfwb200_context
 	cudaEvent_t ev_fork = nullptr;
 
 	// ---- settings / state ------------------------------------------------------------------------------
-	RenderSettings rs{2, 10.0f, 1e-5f, 1, 0, 16, nullptr, -1}; // smem_nodes 0: measured fastest on B200 (DESIGN.md "staging")
+	RenderSettings rs{2, 10.0f, 1e-5f, 1, 0, 16, nullptr, -1, 0}; // smem_nodes 0: measured fastest on B200 (DESIGN.md "staging")
 	int spp = 1;
 	bool mode_pt = true;
 	LaunchDims dims{};
@@ -421,6 +423,19 @@ int upload_bvh(Ctx *c, const std::vector<float> &det_eps)
 }
 
 
+// the 80-byte form of the nodes the wavefront trace kernel reads (device_types.h BvhNode4Packed), after any build / refit
+int pack_nodes(Ctx *c)
+{
+	c->scene.nodes16 = nullptr;
+	if (c->scene.cw_nodes || c->scene.node_count == 0)
+		return RFWB200_OK;
+	CK(c->d_nodes16.reserve(size_t(c->scene.node_count) * sizeof(BvhNode4Packed)));
+	CK(launch_pack_nodes(c->scene.nodes, c->d_nodes16.as<BvhNode4Packed>(), c->scene.node_count, c->stream));
+	c->scene.nodes16 = c->d_nodes16.as<uint4>();
+	c->launches += 1;
+	return RFWB200_OK;
+}
+
 // ---- device geometry path (geometry.cu) --------------------------------------------------------------------------------
 int upload_mesh_to_arena(Ctx *c, size_t mi)
 {
@@ -512,6 +527,34 @@ int upload_instances(Ctx *c, bool with_flat_inst)
 // nodes (topology + the builder's boxes), leaf order and the parent links the bottom-up refit climbs
 int upload_topology(Ctx *c)
 {
+	if (c->bvh.wide8)
+	{
+		// compressed 8-wide layout: the nodes as the host builder quantised them; refits of this layout run on the host
+		const size_t nn8 = c->bvh.cw_nodes.size(), nr8 = c->bvh.tri_order.size();
+		CK(c->d_cw_nodes.reserve(nn8 * sizeof(CwNode)));
+		CK(c->d_nodes.reserve(sizeof(BvhNode4)));
+		CK(c->d_tris.reserve(std::max<size_t>(nr8, 1) * sizeof(TriRec)));
+		CK(c->d_tri_order.reserve(std::max<size_t>(nr8, 1) * sizeof(uint32_t)));
+		CK(c->d_shade_tris.reserve(std::max<size_t>(c->flat_tri_count, 1) * sizeof(ShadeTri)));
+		CK(cudaMemcpyAsync(c->d_cw_nodes.ptr, c->bvh.cw_nodes.data(), nn8 * sizeof(CwNode), cudaMemcpyHostToDevice, c->stream));
+		if (nr8)
+			CK(cudaMemcpyAsync(c->d_tri_order.ptr, c->bvh.tri_order.data(), nr8 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+		GeometryView &g8 = c->geo;
+		g8 = GeometryView{};
+		g8.verts = c->d_verts.as<float4>(), g8.indices = c->d_indices.as<uint32_t>(), g8.mesh_tris = c->d_mesh_tris.ptr;
+		g8.instances = c->d_instances.as<DeviceInstance>(), g8.flat_inst = c->d_flat_inst.as<uint32_t>();
+		g8.flat_count = uint32_t(c->flat_tri_count);
+		g8.tri_order = c->d_tri_order.as<uint32_t>();
+		g8.node_count = 0, g8.ref_count = uint32_t(nr8);
+		g8.out_tris = c->d_tris.as<TriRec>(), g8.out_shade = c->d_shade_tris.as<ShadeTri>();
+		c->scene.nodes = c->d_nodes.as<BvhNode4>(), c->scene.node_count = 0; // unused by the kernels in this mode
+		c->scene.cw_nodes = c->d_cw_nodes.as<uint4>(), c->scene.cw_node_count = uint32_t(nn8);
+		c->scene.tris = c->d_tris.as<TriRec>(), c->scene.shade_tris = c->d_shade_tris.as<ShadeTri>();
+		c->scene.tri_count = uint32_t(nr8);
+		return RFWB200_OK;
+	}
+	c->scene.cw_nodes = nullptr, c->scene.cw_node_count = 0;
 	const size_t nn = c->bvh.nodes.size(), nr = c->bvh.tri_order.size();
 	if (nn >= (1u << 30))
 		return set_error(RFWB200_ERR_INVALID, "BVH has more than 2^30 nodes");
@@ -556,8 +599,13 @@ int device_generate(Ctx *c, bool refit_boxes)
 	}
 	CK(cudaEventRecord(c->ev_geo_a, c->stream));
 	c->geo.write_boxes = refit_boxes ? 1 : 0;
-	CK(launch_refit(c->geo, c->stream));
+	if (c->bvh.wide8)
+		CK(launch_records(c->geo, c->stream));
+	else
+		CK(launch_refit(c->geo, c->stream));
 	CK(launch_flatten_shade(c->geo, c->stream));
+	if (int r = pack_nodes(c))
+		return r;
 	CK(cudaEventRecord(c->ev_geo_b, c->stream));
 	c->launches += 2;
 	c->geo_timed = true;
@@ -958,9 +1006,9 @@ extern "C"
 			layout.emplace_back(in.mesh, ok ? c->meshes[in.mesh].triangles.size() : 0);
 			total += layout.back().second;
 		}
-		const bool can_refit = !c->topology_dirty && layout == c->built_layout && !c->bvh.nodes.empty() && c->built_tri_count == total;
+		const bool can_refit = !c->topology_dirty && layout == c->built_layout && (!c->bvh.nodes.empty() || !c->bvh.cw_nodes.empty()) && c->built_tri_count == total;
 		const bool device = c->device_geometry && total > 0;
-		if (device && can_refit && c->arena_valid)
+		if (device && can_refit && c->arena_valid && !c->wide8)
 		{
 			// Device refit: only the meshes that changed and the 128-B instance records cross PCIe; the boxes, the
 			// intersection records and the shading records are regenerated by two launches on the render stream.
@@ -984,17 +1032,26 @@ extern "C"
 		if (int r = flatten_scene(c, device ? nullptr : &shade, device ? nullptr : &det_eps))
 			return r;
 		const auto t0 = std::chrono::steady_clock::now();
-		if (can_refit)
-			refit_bvh4(c->build_tris.data(), c->build_tris.size(), c->bvh), c->refits++;
+		if (can_refit && c->bvh.wide8 == c->wide8)
+		{
+			if (c->wide8)
+				refit_cwbvh(c->build_tris.data(), c->build_tris.size(), c->bvh);
+			else
+				refit_bvh4(c->build_tris.data(), c->build_tris.size(), c->bvh);
+			c->refits++;
+		}
 		else
 		{
 			const int threads = int(std::max(1u, std::thread::hardware_concurrency()));
-			build_bvh4(c->build_tris.data(), c->build_tris.size(), threads, c->bvh, c->spatial_splits);
+			if (c->wide8)
+				build_cwbvh(c->build_tris.data(), c->build_tris.size(), threads, c->bvh, c->spatial_splits);
+			else
+				build_bvh4(c->build_tris.data(), c->build_tris.size(), threads, c->bvh, c->spatial_splits);
 			c->built_tri_count = c->build_tris.size();
 			c->builds++;
 		}
 		c->bvh.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-		if (3 * c->bvh.depth + 1 > TRAVERSAL_STACK)
+		if (c->wide8 ? (c->bvh.depth > CW_MAX_DEPTH) : (3 * c->bvh.depth + 1 > TRAVERSAL_STACK))
 			return set_error(RFWB200_ERR_INVALID, "BVH deeper than the traversal stack allows");
 		c->built_layout = layout;
 		c->last_update_on_device = false, c->last_update_was_refit = can_refit;
@@ -1014,7 +1071,9 @@ extern "C"
 		}
 		else
 		{
+			REQUIRE(!c->wide8, "bvh=8 needs refit=device and a non-empty scene");
 			c->arena_valid = false;
+			c->scene.cw_nodes = nullptr, c->scene.cw_node_count = 0;
 			if (int r = upload_bvh(c, det_eps))
 				return r;
 			CK(c->d_shade_tris.reserve(std::max<size_t>(shade.size(), 1) * sizeof(ShadeTri)));
@@ -1022,6 +1081,9 @@ extern "C"
 				CK(cudaMemcpy(c->d_shade_tris.ptr, shade.data(), shade.size() * sizeof(ShadeTri), cudaMemcpyHostToDevice));
 			c->scene.shade_tris = c->d_shade_tris.as<ShadeTri>();
 		}
+		if (!device)
+			if (int r = pack_nodes(c))
+				return r;
 		c->geometry_dirty = false, c->topology_dirty = false;
 		c->dims_valid = false; // node count may have changed the staged prefix
 		return RFWB200_OK;
@@ -1114,8 +1176,10 @@ extern "C"
 		REQUIRE(which >= 0 && which <= 2, "which must be 0 (nodes), 1 (triangles) or 2 (shading triangles)");
 		if (int r = check_ready(c))
 			return r;
-		const void *src = which == 0 ? (const void *)c->scene.nodes : which == 1 ? (const void *)c->scene.tris : (const void *)c->scene.shade_tris;
-		const size_t bytes = which == 0	  ? size_t(c->scene.node_count) * sizeof(BvhNode4)
+		const void *src = which == 0 ? (c->scene.cw_nodes ? (const void *)c->scene.cw_nodes : (const void *)c->scene.nodes)
+						  : which == 1 ? (const void *)c->scene.tris
+									   : (const void *)c->scene.shade_tris;
+		const size_t bytes = which == 0	  ? (c->scene.cw_nodes ? size_t(c->scene.cw_node_count) * sizeof(CwNode) : size_t(c->scene.node_count) * sizeof(BvhNode4))
 							 : which == 1 ? size_t(c->scene.tri_count) * sizeof(TriRec)
 										  : size_t(c->flat_tri_count) * sizeof(ShadeTri);
 		*bytes_out = bytes;
@@ -1190,12 +1254,25 @@ extern "C"
 		}
 		else if (k == "timing")
 			c->timing = (v == "on" || v == "1");
+		else if (k == "trace_variant")
+		{
+			const int n = atoi(v.c_str());
+			REQUIRE(n >= 0 && n <= 10, "trace_variant must be in [0, 10]");
+			c->rs.trace_variant = n;
+		}
 		else if (k == "refit")
 		{
 			REQUIRE(v == "device" || v == "host", "refit must be 'device' or 'host'");
 			const bool dev = (v == "device");
 			if (dev != c->device_geometry)
 				c->device_geometry = dev, c->arena_valid = false, c->geometry_dirty = c->topology_dirty = true;
+		}
+		else if (k == "bvh")
+		{
+			REQUIRE(v == "4" || v == "8", "bvh must be 4 or 8");
+			const bool w8 = (v == "8");
+			if (w8 != c->wide8)
+				c->wide8 = w8, c->arena_valid = false, c->geometry_dirty = c->topology_dirty = true;
 		}
 		else if (k == "shade_math")
 		{
@@ -1501,7 +1578,7 @@ extern "C"
 	{
 		REQUIRE(c != nullptr, "context is null");
 		if (nodes)
-			*nodes = c->bvh.nodes.size();
+			*nodes = c->bvh.wide8 ? c->bvh.cw_nodes.size() : c->bvh.nodes.size();
 		if (triangles)
 			*triangles = c->bvh.tri_order.size();
 		if (sah_cost)
@@ -1769,6 +1846,129 @@ extern "C"
 					if (sp == 0)
 						break;
 					cur = stack[--sp];
+				}
+			}
+			t_out[r] = tmax, tri_out[r] = best;
+			if (visits_out)
+				visits_out[2 * r] = node_visits, visits_out[2 * r + 1] = tri_tests;
+		}
+		return RFWB200_OK;
+	}
+
+	// Same self check for the compressed 8-wide layout (cwbvh.h): the walk below is the kernels' traversal loop
+	// (cw_intersect_children is the very function k_wavefront_trace uses), so the builder, the quantisation and the
+	// group / octant bit logic are validated without a GPU.  `refit_jitter` > 0 additionally moves every vertex by a
+	// seeded pseudo-random offset of that size and refits on the host before tracing (the moved triangles are the ones
+	// traced), exercising refit_cwbvh.
+	int rfwb200_host_cwbvh_check(const float *tris9, size_t n_tris, int spatial_splits, float refit_jitter, const float *origins3,
+								 const float *dirs3, size_t n_rays, float *t_out, int32_t *tri_out, uint64_t *nodes_out,
+								 uint64_t *refs_out, int32_t *depth_out, float *sah_out, uint32_t *visits_out, float *tris9_out)
+	{
+		REQUIRE(tris9 && origins3 && dirs3 && t_out && tri_out, "bad arguments");
+		std::vector<BuildTriangle> bt(n_tris);
+		for (size_t i = 0; i < n_tris; i++)
+			memcpy(&bt[i], tris9 + 9 * i, 9 * sizeof(float));
+		BvhBuildResult bvh;
+		build_cwbvh(bt.data(), n_tris, int(std::max(1u, std::thread::hardware_concurrency())), bvh, spatial_splits != 0);
+		if (refit_jitter > 0.0f)
+		{
+			uint32_t seed = 12345u;
+			for (size_t i = 0; i < n_tris; i++)
+				for (int k = 0; k < 9; k++)
+				{
+					seed = seed * 1664525u + 1013904223u;
+					(&bt[i].v0[0])[k] += refit_jitter * (float(seed >> 8) * (1.0f / 8388608.0f) - 1.0f);
+				}
+			refit_cwbvh(bt.data(), n_tris, bvh);
+		}
+		if (tris9_out)
+			for (size_t i = 0; i < n_tris; i++)
+				memcpy(tris9_out + 9 * i, &bt[i], 9 * sizeof(float));
+		if (nodes_out)
+			*nodes_out = bvh.cw_nodes.size();
+		if (refs_out)
+			*refs_out = bvh.tri_order.size();
+		if (depth_out)
+			*depth_out = bvh.depth;
+		if (sah_out)
+			*sah_out = bvh.sah_cost;
+		REQUIRE(bvh.depth <= CW_MAX_DEPTH, "BVH deeper than the traversal stack allows");
+		for (size_t r = 0; r < n_rays; r++)
+		{
+			const float *o = origins3 + 3 * r, *d = dirs3 + 3 * r;
+			CwRay ray;
+			ray.ox = o[0], ray.oy = o[1], ray.oz = o[2];
+			float id[3];
+			for (int a = 0; a < 3; a++)
+			{
+				const float dd = std::fabs(d[a]) > 1e-30f ? d[a] : std::copysign(1e-30f, d[a]);
+				id[a] = 1.0f / dd;
+			}
+			ray.idx = id[0], ray.idy = id[1], ray.idz = id[2];
+			ray.octinv = cw_octinv(id[0], id[1], id[2]);
+			const float tmin = 1e-5f;
+			float tmax = 1e34f;
+			int32_t best = -1;
+			uint32_t stack[2 * CW_STACK];
+			int sp = 0;
+			uint32_t ng_x = 0, ng_y = 0x80000000u, tg_x = 0, tg_y = 0; // node group (base, hits|imask), triangle group (base, bits)
+			uint32_t node_visits = 0, tri_tests = 0;
+			for (;;)
+			{
+				if (ng_y > 0x00ffffffu)
+				{
+					const uint32_t hits = ng_y;
+					const uint32_t bit = 31u - uint32_t(__builtin_clz(hits));
+					ng_y &= ~(1u << bit);
+					if (ng_y > 0x00ffffffu)
+					{
+						REQUIRE(sp < CW_STACK, "traversal stack overflow");
+						stack[2 * sp] = ng_x, stack[2 * sp + 1] = ng_y, sp++;
+					}
+					const uint32_t slot = (bit - 24u) ^ ray.octinv;
+					const uint32_t rel = uint32_t(__builtin_popcount(hits & ~(0xffffffffu << slot) & 0xffu));
+					const uint32_t ni = ng_x + rel;
+					REQUIRE(ni < bvh.cw_nodes.size(), "child index out of range");
+					const uint32_t *w = reinterpret_cast<const uint32_t *>(&bvh.cw_nodes[ni]);
+					node_visits++;
+					const uint32_t hm = cw_intersect_children(w, ray, tmin, tmax);
+					ng_x = w[4], tg_x = w[5];
+					ng_y = (hm & 0xff000000u) | (w[3] >> 24), tg_y = hm & 0x00ffffffu;
+				}
+				else
+					tg_x = ng_x, tg_y = ng_y, ng_x = ng_y = 0;
+				while (tg_y)
+				{
+					const uint32_t bit = 31u - uint32_t(__builtin_clz(tg_y));
+					tg_y &= ~(1u << bit);
+					const uint32_t i = tg_x + bit;
+					REQUIRE(i < bvh.tri_order.size(), "triangle index out of range");
+					tri_tests++;
+					const BuildTriangle &t = bt[bvh.tri_order[i]];
+					const float e1[3] = {t.v1[0] - t.v0[0], t.v1[1] - t.v0[1], t.v1[2] - t.v0[2]};
+					const float e2[3] = {t.v2[0] - t.v0[0], t.v2[1] - t.v0[1], t.v2[2] - t.v0[2]};
+					const float h[3] = {d[1] * e2[2] - e2[1] * d[2], d[2] * e2[0] - e2[2] * d[0], d[0] * e2[1] - e2[0] * d[1]};
+					const float det = e1[0] * h[0] + e1[1] * h[1] + e1[2] * h[2];
+					if (det > -1e-12f && det < 1e-12f)
+						continue;
+					const float f = 1.0f / det;
+					const float s[3] = {o[0] - t.v0[0], o[1] - t.v0[1], o[2] - t.v0[2]};
+					const float u = f * (s[0] * h[0] + s[1] * h[1] + s[2] * h[2]);
+					if (u < 0.0f || u > 1.0f)
+						continue;
+					const float q[3] = {s[1] * e1[2] - e1[1] * s[2], s[2] * e1[0] - e1[2] * s[0], s[0] * e1[1] - e1[0] * s[1]};
+					const float vv = f * (d[0] * q[0] + d[1] * q[1] + d[2] * q[2]);
+					if (vv < 0.0f || u + vv > 1.0f)
+						continue;
+					const float tt = f * (e2[0] * q[0] + e2[1] * q[1] + e2[2] * q[2]);
+					if (tt > tmin && tt < tmax)
+						tmax = tt, best = int32_t(bvh.tri_order[i]);
+				}
+				if (ng_y <= 0x00ffffffu)
+				{
+					if (sp == 0)
+						break;
+					sp--, ng_x = stack[2 * sp], ng_y = stack[2 * sp + 1];
 				}
 			}
 			t_out[r] = tmax, tri_out[r] = best;

@@ -22,6 +22,21 @@ struct alignas(16) BvhNode4
 };
 static_assert(sizeof(BvhNode4) == 128, "node must be one 128-byte line");
 
+// The same node in 80 B = five 16-byte pieces (instead of eight), the form the wavefront trace kernel reads by default:
+// ncu shows the kernel bound by L1 wavefronts — a divergent 128-bit load costs about the same whatever it returns
+// (profiles/r01b: 6.4 wavefronts per LDG.128 at 16 active lanes) — so what counts is the NUMBER of loads per node visit,
+// 7 for BvhNode4.  Child planes are stored relative to the node's min corner `p` as bfloat16 (the upper half of a
+// float: one shift or mask rebuilds the float), rounded outwards, so the packed box always contains the exact one and
+// the closest hit is unchanged.  Derived from BvhNode4 by k_pack_nodes (geometry.cu) after every build / refit.
+struct alignas(16) BvhNode4Packed
+{
+	float p[3];
+	uint32_t pad;
+	uint32_t plane[3][4]; // per axis: lo0|lo1<<16, lo2|lo3<<16, hi0|hi1<<16, hi2|hi3<<16
+	int32_t child[4];
+};
+static_assert(sizeof(BvhNode4Packed) == 80, "packed node is 5 x 16 bytes");
+
 // Intersection record of one (instance-flattened, world-space) triangle, 48 B, stored in BVH leaf
 // order so a leaf is one contiguous run: p0 and the two edges Moller-Trumbore needs
 // (the reference precomputes the same triple on the CPU, RFW/system/bvh/src/bvh_tree.cpp:413-415).
@@ -97,6 +112,9 @@ struct SceneView
 	const TriRec *tris;
 	const ShadeTri *shade_tris;
 	uint32_t node_count, tri_count;
+	const uint4 *nodes16;  // BvhNode4Packed[node_count] (5 x 16 B per node), derived from `nodes`
+	const uint4 *cw_nodes; // compressed 8-wide BVH (cwbvh.h, 5 x 16 B per node) when setting bvh=8, else null
+	uint32_t cw_node_count;
 	const void *materials; // rfwb200_material[ ] (192 B, texaddr patched)
 	uint32_t material_count;
 	const uint32_t *uint_texels;
@@ -144,6 +162,7 @@ struct RenderSettings
 	int fetch_threshold; // idle lanes per warp that trigger a refill from the work cursor
 	unsigned long long *debug; // optional per-warp {start ns, end ns, rays} records of one trace launch (tools/diag)
 	int debug_depth;
+	int trace_variant; // which instantiation of k_wavefront_trace runs (kernels.cu launch_trace; tuning)
 };
 
 } // namespace rfwb200

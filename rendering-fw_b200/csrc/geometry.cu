@@ -149,6 +149,85 @@ __global__ void __launch_bounds__(256) k_refit(const GeometryView g)
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_pack_nodes — BvhNode4 (128 B, fp32 planes) -> BvhNode4Packed (80 B, bfloat16 planes relative to the node's min
+// corner, rounded outwards).  One thread per node.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bf16_down(float v, float p, float exact_lo)
+{
+	// largest bfloat16 <= v (v >= 0: truncation), then make sure p + decoded <= the exact plane
+	uint32_t b = __float_as_uint(v) >> 16;
+	while (b > 0u && p + __uint_as_float(b << 16) > exact_lo)
+		b -= 1u;
+	return b;
+}
+__device__ __forceinline__ uint32_t bf16_up(float v, float p, float exact_hi)
+{
+	const uint32_t bits = __float_as_uint(v);
+	uint32_t b = (bits >> 16) + ((bits & 0xffffu) ? 1u : 0u);
+	while (b < 0x7f7fu && p + __uint_as_float(b << 16) < exact_hi)
+		b += 1u;
+	return b;
+}
+
+__global__ void __launch_bounds__(256) k_pack_nodes(const BvhNode4 *__restrict__ nodes, BvhNode4Packed *__restrict__ out, uint32_t n)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	const BvhNode4 nd = nodes[i];
+	const int used = nd.pad[0];
+	const float *lo[3] = {nd.minx, nd.miny, nd.minz}, *hi[3] = {nd.maxx, nd.maxy, nd.maxz};
+	BvhNode4Packed o;
+	o.pad = uint32_t(used);
+	for (int a = 0; a < 3; a++)
+	{
+		float p = 3.0e38f;
+		for (int k = 0; k < used; k++)
+			p = fminf(p, lo[a][k]);
+		if (used == 0)
+			p = 0.0f;
+		o.p[a] = p;
+		uint32_t l[4], h[4];
+		for (int k = 0; k < 4; k++)
+		{
+			if (k < used)
+				l[k] = bf16_down(lo[a][k] - p, p, lo[a][k]), h[k] = bf16_up(hi[a][k] - p, p, hi[a][k]);
+			else
+				l[k] = h[k] = 0x7fc0u; // NaN: an unused slot never passes the hit test
+		}
+		o.plane[a][0] = l[0] | (l[1] << 16), o.plane[a][1] = l[2] | (l[3] << 16);
+		o.plane[a][2] = h[0] | (h[1] << 16), o.plane[a][3] = h[2] | (h[3] << 16);
+	}
+	for (int k = 0; k < 4; k++)
+		o.child[k] = nd.child[k];
+	out[i] = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_records — one thread per leaf reference: the intersection record only (compressed 8-wide layout, whose boxes are
+// refitted and re-quantised by the host builder)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_records(const GeometryView g)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= g.ref_count)
+		return;
+	const uint32_t src = g.tri_order[i];
+	const uint32_t ii = g.flat_inst[src];
+	const DeviceInstance &in = g.instances[ii];
+	const uint32_t prim = src - in.flat_off;
+	const uint32_t *ix = g.indices + size_t(in.tri_off + prim) * 3;
+	const float4 *vb = g.verts + in.vert_off;
+	const F3 v0 = xf_point(in.transform, vb[ix[0]]);
+	const F3 v1 = xf_point(in.transform, vb[ix[1]]);
+	const F3 v2 = xf_point(in.transform, vb[ix[2]]);
+	float4 *rec = reinterpret_cast<float4 *>(g.out_tris + i);
+	rec[0] = make_float4(v0.x, v0.y, v0.z, v1.x - v0.x);
+	rec[1] = make_float4(v1.y - v0.y, v1.z - v0.z, v2.x - v0.x, v2.y - v0.y);
+	rec[2] = make_float4(v2.z - v0.z, __uint_as_float(src), in.det_eps, 0.0f);
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_flatten_shade — one thread per flattened triangle (context.cpp flatten_scene, shading half)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_flatten_shade(const GeometryView g)
@@ -272,6 +351,22 @@ cudaError_t launch_refit(const GeometryView &g, cudaStream_t stream)
 		return e;
 	const uint32_t threads = g.node_count * 4u;
 	k_refit<<<(threads + 255u) / 256u, 256, 0, stream>>>(g);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_pack_nodes(const BvhNode4 *nodes, BvhNode4Packed *out, uint32_t n, cudaStream_t stream)
+{
+	if (n == 0)
+		return cudaSuccess;
+	k_pack_nodes<<<(n + 255u) / 256u, 256, 0, stream>>>(nodes, out, n);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_records(const GeometryView &g, cudaStream_t stream)
+{
+	if (g.ref_count == 0)
+		return cudaSuccess;
+	k_records<<<(g.ref_count + 255u) / 256u, 256, 0, stream>>>(g);
 	return cudaGetLastError();
 }
 

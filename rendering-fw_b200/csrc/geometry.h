@@ -56,6 +56,8 @@ struct SkinView
 };
 
 cudaError_t launch_refit(const GeometryView &g, cudaStream_t stream);
+cudaError_t launch_pack_nodes(const BvhNode4 *nodes, BvhNode4Packed *out, uint32_t n, cudaStream_t stream);
+cudaError_t launch_records(const GeometryView &g, cudaStream_t stream); // TriRec only (bvh=8)
 cudaError_t launch_flatten_shade(const GeometryView &g, cudaStream_t stream);
 cudaError_t launch_skin(const SkinView &s, cudaStream_t stream);
 

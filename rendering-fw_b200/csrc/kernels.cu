@@ -258,10 +258,88 @@ __device__ __forceinline__ float slab(float lo, float hi, float idir, float ood,
 	}
 #define PICK(KEY) ((((KEY)&3u) == 0u) ? n.child.x : ((((KEY)&3u) == 1u) ? n.child.y : ((((KEY)&3u) == 2u) ? n.child.z : n.child.w)))
 
+// one ray through the compressed 8-wide BVH (cwbvh.h): the per-thread form of k_wavefront_trace_cw's loop, used by the
+// stage-level kernels and E-mode
+template <bool ANY_HIT>
+__device__ bool traverse_cw(const SceneView &sc, V3 o, V3 d, float tmin, float &tmax, uint32_t &hit_tri, float &hit_u, float &hit_v)
+{
+	const float tiny = 1e-30f;
+	CwRay ray;
+	ray.ox = o.x, ray.oy = o.y, ray.oz = o.z;
+	ray.idx = 1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));
+	ray.idy = 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));
+	ray.idz = 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
+	ray.octinv = cw_octinv(ray.idx, ray.idy, ray.idz);
+	const float4 *__restrict__ tris = reinterpret_cast<const float4 *>(sc.tris);
+	uint2 stack[CW_STACK];
+	int sp = 0;
+	uint2 ng = make_uint2(0u, 0x80000000u), tg = make_uint2(0u, 0u);
+	bool found = false;
+	for (;;)
+	{
+		if (ng.y > 0x00ffffffu)
+		{
+			const uint32_t bit = 31u - uint32_t(__clz(ng.y));
+			const uint32_t imask = ng.y;
+			ng.y &= ~(1u << bit);
+			if (ng.y > 0x00ffffffu)
+				stack[sp++] = ng;
+			const uint32_t slot = (bit - 24u) ^ ray.octinv;
+			const uint32_t node = ng.x + uint32_t(__popc(imask & ~(0xffffffffu << slot)));
+			const uint4 *np_ = sc.cw_nodes + size_t(node) * 5;
+			const uint4 q0 = __ldg(np_), q1 = __ldg(np_ + 1), q2 = __ldg(np_ + 2), q3 = __ldg(np_ + 3), q4 = __ldg(np_ + 4);
+			const uint32_t w[20] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y,
+									q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z, q4.w};
+			const uint32_t hm = cw_intersect_children(w, ray, tmin, tmax);
+			ng = make_uint2(q1.x, (hm & 0xff000000u) | (q0.w >> 24));
+			tg = make_uint2(q1.y, hm & 0x00ffffffu);
+		}
+		while (tg.y != 0u)
+		{
+			const uint32_t bit = 31u - uint32_t(__clz(tg.y));
+			tg.y &= ~(1u << bit);
+			const size_t ti = size_t(tg.x + bit) * 3;
+			const float4 a = __ldg(tris + ti + 0), b = __ldg(tris + ti + 1), c = __ldg(tris + ti + 2);
+			const V3 p0 = mk(a.x, a.y, a.z), e1 = mk(a.w, b.x, b.y), e2 = mk(b.z, b.w, c.x);
+			const V3 h = cross(d, e2);
+			const float det = dot(e1, h);
+			const float eps = c.z;
+			if (det > -eps && det < eps)
+				continue;
+			const float f = 1.0f / det;
+			const V3 s = o - p0;
+			const float u = f * dot(s, h);
+			if (u < 0.0f || u > 1.0f)
+				continue;
+			const V3 q = cross(s, e1);
+			const float vv = f * dot(d, q);
+			if (vv < 0.0f || u + vv > 1.0f)
+				continue;
+			const float t = f * dot(e2, q);
+			if (t > tmin && tmax > t)
+			{
+				if (ANY_HIT)
+					return true;
+				tmax = t, hit_u = u, hit_v = vv, hit_tri = __float_as_uint(c.y);
+				found = true;
+			}
+		}
+		if (ng.y <= 0x00ffffffu)
+		{
+			if (sp == 0)
+				break;
+			ng = stack[--sp];
+		}
+	}
+	return found;
+}
+
 template <bool ANY_HIT>
 __device__ __forceinline__ bool traverse(const SceneView &sc, const float4 *__restrict__ snodes, uint32_t n_smem, V3 o,
 										 V3 d, float tmin, float &tmax, uint32_t &hit_tri, float &hit_u, float &hit_v)
 {
+	if (sc.cw_nodes != nullptr)
+		return traverse_cw<ANY_HIT>(sc, o, d, tmin, tmax, hit_tri, hit_u, hit_v);
 	const float tiny = 1e-30f;
 	const float idx = 1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));
 	const float idy = 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));
@@ -422,15 +500,24 @@ extern __shared__ __align__(128) unsigned char g_dyn_smem[];
 #ifndef TRACE_MINB
 #define TRACE_MINB 4 // resident CTAs per SM the register allocation is sized for (measured)
 #endif
-template <bool PRIMARY>
+// Template parameters: LQ = leaves a lane may hold back before it has to wait for the warp's leaf phase (1 = the
+// classic single postponed leaf); LEAN = node step without the four-key sorting network: the nearest hit child is
+// entered, the others are pushed in slot order (about 45 fewer instructions per node visit for a slightly less
+// ordered traversal; LEAN = 2 applies it to connect rays only, which stop at any hit and gain nothing from the order);
+// PACKED = read the 80-byte BvhNode4Packed form of a node (five 128-bit loads per visit instead of seven, bfloat16
+// planes decoded with one shift / mask each); the staged shared-memory prefix (setting smem_nodes) exists only in
+// the <LQ 1, LEAN 0, !PACKED> variant.
+template <bool PRIMARY, int LQ, int LEAN, bool PACKED>
 __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const SceneView sc, const ShardView sh, const WavefrontView wf,
 															const RenderSettings rs, const uint32_t sample_in_frame,
 															const uint32_t depth)
 {
+	constexpr bool STAGED = (LQ == 1 && LEAN == 0 && !PACKED);
 	__shared__ uint64_t mbar;
 	float4 *snodes = reinterpret_cast<float4 *>(g_dyn_smem);
-	const uint32_t n_smem = min(uint32_t(rs.smem_nodes), sc.node_count);
-	stage_nodes(snodes, sc.nodes, n_smem, &mbar);
+	const uint32_t n_smem = STAGED ? min(uint32_t(rs.smem_nodes), sc.node_count) : 0u;
+	if (STAGED)
+		stage_nodes(snodes, sc.nodes, n_smem, &mbar);
 
 	DepthCounters *curc = &wf.counters[sample_in_frame * MAX_DEPTH_SLOTS + depth];
 	uint32_t n_ext, n_shadow;
@@ -478,6 +565,7 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 	constexpr int SENTINEL = 0x7fffffff; // bottom-of-stack marker: popping it ends the ray
 	constexpr int NO_LEAF = 0;			 // leaf references are negative, so 0 can mean "none postponed"
 	int sp = 0, cur = SENTINEL, leaf = NO_LEAF;
+	int leaf1 = NO_LEAF, leaf2 = NO_LEAF; // further held-back leaves (LQ > 1)
 	bool exhausted = false; // warp-uniform: the queue has no more items
 	uint32_t acc_count = 0;
 
@@ -541,7 +629,7 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 						oodx = o.x * idx, oody = o.y * idy, oodz = o.z * idz;
 						sgx = idx < 0.0f ? 1u : 0u, sgy = idy < 0.0f ? 1u : 0u, sgz = idz < 0.0f ? 1u : 0u;
 						stack[0] = SENTINEL;
-						sp = 1, cur = 0, leaf = NO_LEAF, hit_tri = 0xffffffffu, hit_u = 0.f, hit_v = 0.f;
+						sp = 1, cur = 0, leaf = leaf1 = leaf2 = NO_LEAF, hit_tri = 0xffffffffu, hit_u = 0.f, hit_v = 0.f;
 						alive = true;
 					}
 				}
@@ -558,24 +646,76 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 				// (speculatively) so it stays useful until every lane of the warp holds a leaf
 				while (uint32_t(cur) < uint32_t(SENTINEL))
 				{
-					// one node = one 128-byte line: six plane quads picked by the ray's octant + the child words
-					const float4 *np_ = uint32_t(cur) < n_smem ? snodes + size_t(cur) * 8
-															   : reinterpret_cast<const float4 *>(sc.nodes) + size_t(cur) * 8;
-					const float4 nearx = np_[sgx], farx = np_[sgx ^ 1u];
-					const float4 neary = np_[2u + sgy], fary = np_[3u - sgy];
-					const float4 nearz = np_[4u + sgz], farz = np_[5u - sgz];
 					struct
 					{
 						int4 child;
 					} n;
-					n.child = *reinterpret_cast<const int4 *>(np_ + 6);
 					uint32_t key0, key1, key2, key3;
 					int nh = 0;
-					CHILD_N(0, x)
-					CHILD_N(1, y)
-					CHILD_N(2, z)
-					CHILD_N(3, w)
-					if (nh == 0)
+					if (PACKED)
+					{
+						// five 16-byte pieces: min corner, three axes of bfloat16 planes (lo0 lo1 | lo2 lo3 | hi0 hi1 | hi2 hi3), children
+						const uint4 *np_ = sc.nodes16 + size_t(cur) * 5;
+						const uint4 hp = np_[0], px = np_[1], py = np_[2], pz = np_[3];
+						n.child = *reinterpret_cast<const int4 *>(np_ + 4);
+						// t = plane * idir - o * idir with plane = p + v:  v * idir + (p * idir - o * idir)
+						const float cx = fmaf(__uint_as_float(hp.x), idx, -oodx), cy = fmaf(__uint_as_float(hp.y), idy, -oody),
+									cz = fmaf(__uint_as_float(hp.z), idz, -oodz);
+						const uint32_t nx01 = sgx ? px.z : px.x, nx23 = sgx ? px.w : px.y, fx01 = sgx ? px.x : px.z, fx23 = sgx ? px.y : px.w;
+						const uint32_t ny01 = sgy ? py.z : py.x, ny23 = sgy ? py.w : py.y, fy01 = sgy ? py.x : py.z, fy23 = sgy ? py.y : py.w;
+						const uint32_t nz01 = sgz ? pz.z : pz.x, nz23 = sgz ? pz.w : pz.y, fz01 = sgz ? pz.x : pz.z, fz23 = sgz ? pz.y : pz.w;
+#define BF_LO(W) __uint_as_float((W) << 16)
+#define BF_HI(W) __uint_as_float((W)&0xffff0000u)
+#define CHILD_P(K, NX, FX, NY, FY, NZ, FZ)                                                                              \
+	{                                                                                                                   \
+		const float tn = fmaxf(fmaxf(fmaf(NX, idx, cx), fmaf(NY, idy, cy)), fmaf(NZ, idz, cz));                         \
+		const float tf = fminf(fminf(fmaf(FX, idx, cx), fmaf(FY, idy, cy)), fmaf(FZ, idz, cz));                         \
+		const bool h = (tf >= tn) & (tn < tmax) & (tf >= tmin);                                                         \
+		nh += h ? 1 : 0;                                                                                                \
+		key##K = h ? ((__float_as_uint(fmaxf(tn, 0.0f)) & 0xFFFFFFFCu) | uint32_t(K)) : MISSKEY(K);                     \
+	}
+						CHILD_P(0, BF_LO(nx01), BF_LO(fx01), BF_LO(ny01), BF_LO(fy01), BF_LO(nz01), BF_LO(fz01))
+						CHILD_P(1, BF_HI(nx01), BF_HI(fx01), BF_HI(ny01), BF_HI(fy01), BF_HI(nz01), BF_HI(fz01))
+						CHILD_P(2, BF_LO(nx23), BF_LO(fx23), BF_LO(ny23), BF_LO(fy23), BF_LO(nz23), BF_LO(fz23))
+						CHILD_P(3, BF_HI(nx23), BF_HI(fx23), BF_HI(ny23), BF_HI(fy23), BF_HI(nz23), BF_HI(fz23))
+#undef CHILD_P
+#undef BF_LO
+#undef BF_HI
+					}
+					else
+					{
+						// one node = one 128-byte line: six plane quads picked by the ray's octant + the child words
+						const float4 *np_ = (STAGED && uint32_t(cur) < n_smem) ? snodes + size_t(cur) * 8
+																			   : reinterpret_cast<const float4 *>(sc.nodes) + size_t(cur) * 8;
+						const float4 nearx = np_[sgx], farx = np_[sgx ^ 1u];
+						const float4 neary = np_[2u + sgy], fary = np_[3u - sgy];
+						const float4 nearz = np_[4u + sgz], farz = np_[5u - sgz];
+						n.child = *reinterpret_cast<const int4 *>(np_ + 6);
+						CHILD_N(0, x)
+						CHILD_N(1, y)
+						CHILD_N(2, z)
+						CHILD_N(3, w)
+					}
+					if (LEAN == 1 || (LEAN == 2 && shadow))
+					{
+						const uint32_t km = min(min(key0, key1), min(key2, key3));
+						if (nh == 0)
+							cur = stack[--sp];
+						else
+						{
+							cur = PICK(km);
+							// the other hit children in slot order (predicated stores, no sorting network)
+							if (key0 < 0x7f000000u && key0 != km)
+								stack[sp++] = n.child.x;
+							if (key1 < 0x7f000000u && key1 != km)
+								stack[sp++] = n.child.y;
+							if (key2 < 0x7f000000u && key2 != km)
+								stack[sp++] = n.child.z;
+							if (key3 < 0x7f000000u && key3 != km)
+								stack[sp++] = n.child.w;
+						}
+					}
+					else if (nh == 0)
 						cur = stack[--sp];
 					else
 					{
@@ -594,9 +734,20 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 							stack[sp++] = PICK(key1);
 						}
 					}
+					// hold back up to LQ leaves and keep descending
 					if (cur < 0 && leaf == NO_LEAF)
 					{
 						leaf = cur;
+						cur = stack[--sp];
+					}
+					if (LQ > 1 && cur < 0 && leaf1 == NO_LEAF)
+					{
+						leaf1 = cur;
+						cur = stack[--sp];
+					}
+					if (LQ > 2 && cur < 0 && leaf2 == NO_LEAF)
+					{
+						leaf2 = cur;
 						cur = stack[--sp];
 					}
 					if (!__any_sync(__activemask(), leaf == NO_LEAF))
@@ -633,12 +784,15 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 							if (shadow)
 							{
 								cur = SENTINEL; // any hit ends a connect ray
+								leaf1 = leaf2 = NO_LEAF;
 								break;
 							}
 						}
 					}
 					leaf = NO_LEAF;
-					if (cur < 0)
+					if (LQ > 1)
+						leaf = leaf1, leaf1 = leaf2, leaf2 = NO_LEAF;
+					if (leaf == NO_LEAF && cur < 0)
 					{
 						leaf = cur;
 						cur = stack[--sp];
@@ -697,6 +851,266 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 			curc->shadow_traced = n_shadow;
 	}
 }
+
+// ------------------------------------------------------------------------------------------------
+// k_wavefront_trace_cw — the same persistent kernel over the compressed 8-wide BVH (cwbvh.h, setting bvh=8).
+// Per node visit a lane loads 80 B (five 128-bit loads) instead of 112 B and tests eight children; children come out
+// in octant order, so there is no sorting network, and the stack holds one 8-byte node group per level.
+// ------------------------------------------------------------------------------------------------
+template <bool PRIMARY>
+__global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace_cw(const SceneView sc, const ShardView sh, const WavefrontView wf,
+															const RenderSettings rs, const uint32_t sample_in_frame,
+															const uint32_t depth)
+{
+	const uint4 *__restrict__ cwn = sc.cw_nodes;
+
+	DepthCounters *curc = &wf.counters[sample_in_frame * MAX_DEPTH_SLOTS + depth];
+	uint32_t n_ext, n_shadow;
+	if (PRIMARY)
+		n_ext = sh.local_pixels, n_shadow = 0;
+	else
+	{
+		const DepthCounters *prev = &wf.counters[sample_in_frame * MAX_DEPTH_SLOTS + depth - 1];
+		n_ext = prev->ext;
+		// the reference only traces the connect queue when the bounce loop continues, i.e. when at least
+		// one extension ray exists (CUDART/src/Context.cpp:109-120)
+		n_shadow = n_ext > 0 ? prev->shadow : 0u;
+	}
+	const uint32_t total = n_ext + n_shadow;
+	const uint32_t buf = depth & 1u;
+	const float4 *__restrict__ Oin = wf.O[buf];
+	const float4 *__restrict__ Din = wf.D[buf];
+	const float4 *__restrict__ tris = reinterpret_cast<const float4 *>(sc.tris);
+	uint32_t *cursor = &curc->trace_cursor;
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t lt_mask = (1u << lane) - 1u;
+	FrameParams fp;
+	uint32_t sampleIndex = 0;
+	if (PRIMARY)
+	{
+		fp = *wf.frame;
+		sampleIndex = fp.sample_base + sample_in_frame;
+	}
+
+	unsigned long long dbg_t0 = 0, dbg_rays = 0;
+	const bool dbg = !PRIMARY && rs.debug != nullptr && int(depth) == rs.debug_depth;
+	if (dbg)
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+
+	// per-lane ray state
+	bool alive = false;
+	bool shadow = false;
+	uint32_t item = 0;
+	V3 o = mk(0.f), d = mk(0.f);
+	CwRay ray;
+	ray.ox = ray.oy = ray.oz = 0.f, ray.idx = ray.idy = ray.idz = 1.f, ray.octinv = 0u;
+	float tmin = 0.f, tmax = 0.f, hit_u = 0.f, hit_v = 0.f;
+	uint32_t hit_tri = 0xffffffffu;
+	// node group (x = index of the first inner child, y = hits in bits 24..31 | imask), the triangle group held back
+	// (x = first triangle record, y = one bit per triangle) and the one found after it; stack of node groups
+	uint2 stack[CW_STACK];
+	uint2 ng = make_uint2(0u, 0u), held = make_uint2(0u, 0u), tg = make_uint2(0u, 0u);
+	int sp = 0;
+	bool trav_done = true;
+	bool exhausted = false; // warp-uniform: the queue has no more items
+	uint32_t acc_count = 0;
+
+	for (;;)
+	{
+		// ---- refill idle lanes ---------------------------------------------------------------------------
+		const uint32_t idle_mask = __ballot_sync(0xffffffffu, !alive);
+		if (idle_mask == 0xffffffffu && exhausted)
+			break;
+		const int n_idle = __popc(idle_mask);
+		if (!exhausted && (n_idle >= rs.fetch_threshold))
+		{
+			uint32_t base = 0;
+			if (lane == 0)
+				base = atomicAdd(cursor, uint32_t(n_idle));
+			base = __shfl_sync(0xffffffffu, base, 0);
+			if (base + uint32_t(n_idle) >= total)
+				exhausted = true;
+			if (!alive)
+			{
+				item = base + __popc(idle_mask & lt_mask);
+				if (item < total)
+				{
+					bool valid = true;
+					if (PRIMARY)
+					{
+						uint32_t x, y;
+						if (local_to_pixel(sh, item, x, y))
+						{
+							generate_pt(sc, fp, sh, x, y, sampleIndex, o, d);
+							wf.O[0][item] = make_float4(o.x, o.y, o.z, __uint_as_float((item << 8) + 1u));
+							wf.D[0][item] = make_float4(d.x, d.y, d.z, 0.0f);
+							tmin = 1e-5f, tmax = 1e34f, shadow = false;
+						}
+						else
+						{
+							wf.hit[item] = make_float4(0.f, 0.f, __int_as_float(PRIM_DEAD), 0.f);
+							valid = false;
+						}
+					}
+					else if (item < n_ext)
+					{
+						const float4 O4 = Oin[item], D4 = Din[item];
+						o = mk(O4.x, O4.y, O4.z), d = mk(D4.x, D4.y, D4.z);
+						tmin = 1e-5f, tmax = 1e34f, shadow = false;
+					}
+					else
+					{
+						const uint32_t k = item - n_ext;
+						const float4 O4 = wf.sO[k], D4 = wf.sD[k];
+						o = mk(O4.x, O4.y, O4.z), d = mk(D4.x, D4.y, D4.z);
+						tmin = rs.geometry_epsilon, tmax = D4.w, shadow = true;
+					}
+					if (valid)
+					{
+						dbg_rays++;
+						const float tiny = 1e-30f;
+						ray.ox = o.x, ray.oy = o.y, ray.oz = o.z;
+						ray.idx = 1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));
+						ray.idy = 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));
+						ray.idz = 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
+						ray.octinv = cw_octinv(ray.idx, ray.idy, ray.idz);
+						ng = make_uint2(0u, 0x80000000u), held = tg = make_uint2(0u, 0u); // the root is "child 7 ^ octinv of nothing"
+						sp = 0, trav_done = false, hit_tri = 0xffffffffu, hit_u = 0.f, hit_v = 0.f;
+						alive = true;
+					}
+				}
+			}
+		}
+
+		// ---- traverse: while-while over node groups with one triangle group held back ------------------------------------
+		bool finished = false;
+		if (alive)
+		{
+			while (!trav_done || held.y != 0u)
+			{
+				// node phase: every lane enters the nearest hit child of its node group; the triangles found there are held
+				// back (the lane keeps descending) until every lane of the warp holds some
+				while (!trav_done)
+				{
+					if (ng.y <= 0x00ffffffu)
+					{
+						if (sp == 0)
+						{
+							trav_done = true;
+							break;
+						}
+						ng = stack[--sp];
+					}
+					const uint32_t bit = 31u - uint32_t(__clz(ng.y));
+					const uint32_t imask = ng.y;
+					ng.y &= ~(1u << bit);
+					if (ng.y > 0x00ffffffu)
+						stack[sp++] = ng;
+					const uint32_t slot = (bit - 24u) ^ ray.octinv;
+					const uint32_t node = ng.x + uint32_t(__popc(imask & ~(0xffffffffu << slot)));
+					const uint4 *np_ = cwn + size_t(node) * 5;
+					const uint4 q0 = __ldg(np_), q1 = __ldg(np_ + 1), q2 = __ldg(np_ + 2), q3 = __ldg(np_ + 3), q4 = __ldg(np_ + 4);
+					const uint32_t w[20] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y,
+											q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z, q4.w};
+					const uint32_t hm = cw_intersect_children(w, ray, tmin, tmax);
+					ng = make_uint2(q1.x, (hm & 0xff000000u) | (q0.w >> 24));
+					const uint32_t tbits = hm & 0x00ffffffu;
+					if (tbits)
+					{
+						if (held.y == 0u)
+							held = make_uint2(q1.y, tbits);
+						else
+						{
+							tg = make_uint2(q1.y, tbits); // a second group: this lane waits for the triangle phase
+							break;
+						}
+					}
+					if (!__any_sync(__activemask(), held.y == 0u))
+						break;
+				}
+				// triangle phase: the held group, then the one that stopped the lane
+				while (held.y != 0u)
+				{
+					const uint32_t bit = 31u - uint32_t(__clz(held.y));
+					held.y &= ~(1u << bit);
+					const size_t ti = size_t(held.x + bit) * 3;
+					const float4 a = __ldg(tris + ti + 0);
+					const float4 b = __ldg(tris + ti + 1);
+					const float4 c = __ldg(tris + ti + 2);
+					const V3 p0 = mk(a.x, a.y, a.z), e1 = mk(a.w, b.x, b.y), e2 = mk(b.z, b.w, c.x);
+					const V3 h = cross(d, e2);
+					const float det = dot(e1, h);
+					const float eps = c.z;
+					const float f = 1.0f / det;
+					const V3 s = o - p0;
+					const float u = f * dot(s, h);
+					const V3 q = cross(s, e1);
+					const float vv = f * dot(d, q);
+					const float t = f * dot(e2, q);
+					const bool ok = !(det > -eps && det < eps) && !(u < 0.0f || u > 1.0f) && !(vv < 0.0f || u + vv > 1.0f) && t > tmin && tmax > t;
+					if (ok)
+					{
+						tmax = t, hit_u = u, hit_v = vv, hit_tri = __float_as_uint(c.y);
+						if (shadow)
+							trav_done = true, sp = 0, held.y = 0u, tg.y = 0u, ng.y = 0u; // any hit ends a connect ray
+					}
+					if (held.y == 0u)
+						held = tg, tg.y = 0u;
+				}
+				// too few lanes left in this loop: leave it so the idle lanes can fetch new rays
+				if (__popc(__activemask()) <= 32 - rs.fetch_threshold)
+					break;
+			}
+			finished = trav_done && held.y == 0u;
+		}
+		// ---- retire --------------------------------------------------------------------------------------------------
+		if (alive && finished)
+		{
+			alive = false;
+			if (!shadow)
+			{
+				float4 hit = make_float4(0.f, 0.f, __int_as_float(PRIM_MISS), 0.f);
+				if (hit_tri != 0xffffffffu)
+					hit = make_float4(__uint_as_float(uint32_t(65535.0f * hit_u) | (uint32_t(65535.0f * hit_v) << 16)),
+									  __uint_as_float(hit_tri), __int_as_float(0), tmax);
+				wf.hit[item] = hit;
+			}
+			else if (hit_tri == 0xffffffffu)
+			{
+				// unoccluded: accumulator[pixel] += (contribution, 1)  (Kernels.cu:495-497)
+				const float4 E = wf.sE[item - n_ext];
+				const uint32_t pixel = __float_as_uint(E.w);
+				float4 a = wf.accumulator[pixel];
+				a.x += E.x, a.y += E.y, a.z += E.z, a.w += 1.0f;
+				wf.accumulator[pixel] = a;
+				acc_count++;
+			}
+		}
+	}
+	if (dbg)
+	{
+		unsigned long long t1;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+		const unsigned long long n = __reduce_add_sync(0xffffffffu, uint32_t(dbg_rays));
+		if (lane == 0)
+		{
+			unsigned long long *rec = rs.debug + size_t(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4;
+			uint32_t smid;
+			asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+			rec[0] = dbg_t0, rec[1] = t1, rec[2] = n, rec[3] = smid;
+		}
+	}
+	if (!PRIMARY)
+	{
+		// bookkeeping for the algorithmic-bytes formula: one atomic per warp
+		acc_count = __reduce_add_sync(0xffffffffu, acc_count);
+		if (lane == 0 && acc_count)
+			atomicAdd(&curc->acc, acc_count);
+		if (blockIdx.x == 0 && threadIdx.x == 0)
+			curc->shadow_traced = n_shadow;
+	}
+}
+
 
 #endif // RFW_PART != 2 (trace part)
 
@@ -1882,8 +2296,8 @@ cudaError_t configure_launches(const RenderSettings &rs, uint32_t node_count, La
 		return e;
 	const uint32_t staged = rs.smem_nodes > 0 ? (uint32_t(rs.smem_nodes) < node_count ? uint32_t(rs.smem_nodes) : node_count) : 0u;
 	dims.trace_smem = size_t(staged) * sizeof(BvhNode4);
-	const void *trace_kernels[] = {(const void *)k_wavefront_trace<true>, (const void *)k_wavefront_trace<false>, (const void *)k_emode,
-								   (const void *)k_trace_closest, (const void *)k_trace_occluded};
+	const void *trace_kernels[] = {(const void *)k_wavefront_trace<true, 1, 0, false>, (const void *)k_wavefront_trace<false, 1, 0, false>,
+								   (const void *)k_emode, (const void *)k_trace_closest, (const void *)k_trace_occluded};
 	for (const void *k : trace_kernels)
 	{
 		e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dims.trace_smem));
@@ -1891,7 +2305,7 @@ cudaError_t configure_launches(const RenderSettings &rs, uint32_t node_count, La
 			return e;
 	}
 	int per_sm = 0;
-	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wavefront_trace<false>, dims.trace_block, dims.trace_smem);
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wavefront_trace<false, 1, 0, false>, dims.trace_block, dims.trace_smem);
 	if (e != cudaSuccess)
 		return e;
 	if (per_sm < 1)
@@ -1910,13 +2324,55 @@ cudaError_t configure_launches(const RenderSettings &rs, uint32_t node_count, La
 cudaError_t launch_primary(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
 						   uint32_t sample_in_frame, const LaunchDims &dims, cudaStream_t stream)
 {
-	k_wavefront_trace<true><<<dims.trace_grid, dims.trace_block, dims.trace_smem, stream>>>(sc, sh, wf, rs, sample_in_frame, 0u);
+	if (sc.cw_nodes != nullptr)
+	{
+		k_wavefront_trace_cw<true><<<dims.trace_grid, dims.trace_block, 0, stream>>>(sc, sh, wf, rs, sample_in_frame, 0u);
+		return cudaGetLastError();
+	}
+	switch (rs.trace_variant)
+	{
+#define RFW_TRACE_CASE(V, LQ, LEAN, PACKED)                                                                                     \
+	case V:                                                                                                             \
+		k_wavefront_trace<true, LQ, LEAN, PACKED><<<dims.trace_grid, dims.trace_block, (LQ == 1 && LEAN == 0 && !PACKED) ? dims.trace_smem : 0, stream>>>( \
+			sc, sh, wf, rs, sample_in_frame, 0u);                                                                       \
+		break;
+		RFW_TRACE_CASE(1, 2, 0, false)
+		RFW_TRACE_CASE(3, 1, 1, false)
+		RFW_TRACE_CASE(5, 1, 2, false)
+		RFW_TRACE_CASE(8, 1, 0, true)
+		RFW_TRACE_CASE(9, 1, 2, true)
+		RFW_TRACE_CASE(10, 1, 1, true)
+	default:
+		RFW_TRACE_CASE(0, 1, 0, false)
+#undef RFW_TRACE_CASE
+	}
 	return cudaGetLastError();
 }
 cudaError_t launch_trace(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
 						 uint32_t sample_in_frame, uint32_t depth, const LaunchDims &dims, cudaStream_t stream)
 {
-	k_wavefront_trace<false><<<dims.trace_grid, dims.trace_block, dims.trace_smem, stream>>>(sc, sh, wf, rs, sample_in_frame, depth);
+	if (sc.cw_nodes != nullptr)
+	{
+		k_wavefront_trace_cw<false><<<dims.trace_grid, dims.trace_block, 0, stream>>>(sc, sh, wf, rs, sample_in_frame, depth);
+		return cudaGetLastError();
+	}
+	switch (rs.trace_variant)
+	{
+#define RFW_TRACE_CASE(V, LQ, LEAN, PACKED)                                                                                     \
+	case V:                                                                                                             \
+		k_wavefront_trace<false, LQ, LEAN, PACKED><<<dims.trace_grid, dims.trace_block, (LQ == 1 && LEAN == 0 && !PACKED) ? dims.trace_smem : 0, stream>>>( \
+			sc, sh, wf, rs, sample_in_frame, depth);                                                                    \
+		break;
+		RFW_TRACE_CASE(1, 2, 0, false)
+		RFW_TRACE_CASE(3, 1, 1, false)
+		RFW_TRACE_CASE(5, 1, 2, false)
+		RFW_TRACE_CASE(8, 1, 0, true)
+		RFW_TRACE_CASE(9, 1, 2, true)
+		RFW_TRACE_CASE(10, 1, 1, true)
+	default:
+		RFW_TRACE_CASE(0, 1, 0, false)
+#undef RFW_TRACE_CASE
+	}
 	return cudaGetLastError();
 }
 cudaError_t launch_finalize(const ShardView &sh, const WavefrontView &wf, float scale, cudaStream_t stream)

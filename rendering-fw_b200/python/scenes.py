@@ -686,14 +686,19 @@ def save_baked(scene: Scene, path: Path):
     put(scene.materials), put(scene.tex_ids.astype(np.int32))
     for t in scene.textures:
         parts.append(struct.pack("<III", t["type"], t["width"], t["height"]))
-        put(t["data"])
+        data = np.asarray(t["data"])
+        if t["type"] == R.TEX_UINT:  # level 0 only: the mip chain is rebuilt by build_mips on load (keeps the snapshot small)
+            level0 = data.reshape(-1)[: t["width"] * t["height"]]
+            assert np.array_equal(build_mips(level0.reshape(t["height"], t["width"])), data.reshape(-1))
+            data = level0
+        put(data)
     sky, sw, sh = scene.sky
     parts.append(struct.pack("<II", sw, sh))
     put(np.asarray(sky, np.float32))
     put(scene.point_lights), put(scene.spot_lights), put(scene.dir_lights)
     raw = b"".join(parts)
     Path(path).parent.mkdir(parents=True, exist_ok=True)
-    Path(path).write_bytes(BAKE_MAGIC + struct.pack("<Q", len(raw)) + zlib.compress(raw, 1))
+    Path(path).write_bytes(BAKE_MAGIC + struct.pack("<Q", len(raw)) + zlib.compress(raw, 6))
 
 
 def load_baked(path: Path) -> Scene:
@@ -737,7 +742,10 @@ def load_baked(path: Path) -> Scene:
     s.tex_ids = get(np.int32).reshape(-1, 11)
     for _ in range(ntex):
         ty, w, h = take("<III")
-        s.textures.append({"type": ty, "width": w, "height": h, "data": get(np.uint32 if ty == R.TEX_UINT else np.float32)})
+        data = get(np.uint32 if ty == R.TEX_UINT else np.float32)
+        if ty == R.TEX_UINT and data.size == w * h:
+            data = build_mips(data.reshape(h, w))
+        s.textures.append({"type": ty, "width": w, "height": h, "data": data})
     sw, sh = take("<II")
     s.sky = (get(np.float32).reshape(-1, 3), sw, sh)
     s.point_lights, s.spot_lights, s.dir_lights = get(R.POINT_LIGHT_DTYPE), get(R.SPOT_LIGHT_DTYPE), get(R.DIR_LIGHT_DTYPE)

@@ -107,3 +107,65 @@ def test_empty_and_single_triangle(product_lib):
     d = np.array([[0, 0, 1]], np.float32)
     t, tri, info = host_check(product_lib, one, o, d, True)
     assert tri[0] == 0 and abs(t[0] - 2) < 1e-5
+
+
+# ---- compressed 8-wide layout (csrc/cwbvh.h) ---------------------------------------------------------------------
+def host_check_cw(lib, tris, o, d, spatial, refit_jitter=0.0):
+    f = lib.fn("host_cwbvh_check", C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p])
+    t, tri = np.zeros(len(o), np.float32), np.zeros(len(o), np.int32)
+    nodes, refs, depth, sah = C.c_uint64(), C.c_uint64(), C.c_int32(), C.c_float()
+    visits = np.zeros((len(o), 2), np.uint32)
+    moved = np.zeros_like(tris)
+    o, d = np.ascontiguousarray(o, np.float32), np.ascontiguousarray(d, np.float32)
+    rc = f(tris.ctypes.data, len(tris), int(spatial), float(refit_jitter), o.ctypes.data, d.ctypes.data, len(o), t.ctypes.data,
+           tri.ctypes.data, C.byref(nodes), C.byref(refs), C.byref(depth), C.byref(sah), visits.ctypes.data, moved.ctypes.data)
+    assert rc == 0, lib.last_error()
+    return t, tri, {"nodes": nodes.value, "refs": refs.value, "depth": depth.value, "sah": sah.value, "visits": visits, "tris": moved}
+
+
+@pytest.mark.parametrize("spatial", [False, True])
+@pytest.mark.parametrize("scene", ["soup", "cornell", "atrium"])
+def test_cwbvh_matches_brute_force(product_lib, scene, spatial):
+    """builder + quantisation + octant-ordered group traversal (the kernels' own cw_intersect_children) against brute force"""
+    sc = {"soup": lambda: S.feature_soup(1500), "cornell": lambda: S.cornell_box(unit_scale=True), "atrium": lambda: S.atrium(6000)}[scene]()
+    tris = flatten(sc)
+    ext = float(np.abs(tris).max())
+    o, d = rays(300, 3, ext * 0.7)
+    t, tri, info = host_check_cw(product_lib, tris, o, d, spatial)
+    bt = brute(tris, o, d)
+    hit = bt < 1e33
+    assert np.array_equal(t < 1e33, hit)
+    assert np.allclose(t[hit], bt[hit], rtol=2e-4, atol=1e-5 * ext)
+    assert info["refs"] >= len(tris) and info["refs"] <= 1.7 * len(tris) + 64
+    assert info["depth"] <= 30
+    if not spatial:
+        assert info["refs"] == len(tris)
+    # the point of the wide layout: fewer node visits than the 4-wide tree on the same rays (measured: 0.79-0.85x with
+    # the greedy collapse; the trade against 2.3x the instructions per visit is in DESIGN.md)
+    _, _, info4 = host_check(product_lib, tris, o, d, spatial)
+    if scene != "cornell":
+        assert info["visits"][:, 0].sum() < 0.9 * info4["visits"][:, 0].sum()
+        assert info["nodes"] < 0.75 * info4["nodes"]
+
+
+def test_cwbvh_host_refit_matches_brute_force(product_lib):
+    sc = S.atrium(6000)
+    tris = flatten(sc)
+    ext = float(np.abs(tris).max())
+    o, d = rays(300, 5, ext * 0.7)
+    t, tri, info = host_check_cw(product_lib, tris, o, d, True, refit_jitter=0.01 * ext)
+    assert np.abs(info["tris"] - tris).max() > 0.002 * ext
+    bt = brute(info["tris"], o, d)
+    hit = bt < 1e33
+    assert np.array_equal(t < 1e33, hit)
+    assert np.allclose(t[hit], bt[hit], rtol=2e-4, atol=1e-5 * ext)
+
+
+def test_cwbvh_empty_and_single_triangle(product_lib):
+    o, d = rays(8, 1, 1.0)
+    t, tri, info = host_check_cw(product_lib, np.zeros((0, 9), np.float32), o, d, True)
+    assert (t > 1e33).all() and info["nodes"] == 1
+    one = np.array([[-1, -1, 2, 1, -1, 2, 0, 1, 2]], np.float32)
+    t, tri, info = host_check_cw(product_lib, one, np.zeros((1, 3), np.float32), np.array([[0, 0, 1]], np.float32), True)
+    assert tri[0] == 0 and abs(t[0] - 2) < 1e-5
