@@ -188,7 +188,7 @@ struct rfwb200_context
 	cudaEvent_t ev_fork = nullptr;
 
 	// ---- settings / state ------------------------------------------------------------------------------
-	RenderSettings rs{2, 10.0f, 1e-5f, 1, 0, 16, nullptr, -1, 0}; // smem_nodes 0: measured fastest on B200 (DESIGN.md "staging")
+	RenderSettings rs{2, 10.0f, 1e-5f, 1, 0, 16, nullptr, -1, 9}; // trace_variant 9: packed nodes + unsorted connect rays (DESIGN.md sweep) // smem_nodes 0: measured fastest on B200 (DESIGN.md "staging")
 	int spp = 1;
 	bool mode_pt = true;
 	LaunchDims dims{};

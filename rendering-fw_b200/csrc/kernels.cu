@@ -22,6 +22,7 @@
 
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 // This file is compiled twice (rendering-fw_b200/Makefile): RFW_PART=1 builds the trace side — traversal, generate,
 // finalize, E-mode, stage-level kernels — with IEEE arithmetic, so hit points do not depend on approximate division;
@@ -2304,6 +2305,23 @@ cudaError_t configure_launches(const RenderSettings &rs, uint32_t node_count, La
 		if (e != cudaSuccess)
 			return e;
 	}
+	// kernels that use no shared memory ask for the whole unified array as L1 (traversal is bound by L1 hits on nodes)
+	if (getenv("RFWB200_NO_CARVEOUT") == nullptr)
+	{
+		const void *l1_kernels[] = {(const void *)k_wavefront_trace<true, 2, 0, false>,  (const void *)k_wavefront_trace<false, 2, 0, false>,
+									(const void *)k_wavefront_trace<true, 1, 1, false>,  (const void *)k_wavefront_trace<false, 1, 1, false>,
+									(const void *)k_wavefront_trace<true, 1, 2, false>,  (const void *)k_wavefront_trace<false, 1, 2, false>,
+									(const void *)k_wavefront_trace<true, 1, 0, true>,	 (const void *)k_wavefront_trace<false, 1, 0, true>,
+									(const void *)k_wavefront_trace<true, 1, 2, true>,	 (const void *)k_wavefront_trace<false, 1, 2, true>,
+									(const void *)k_wavefront_trace<true, 1, 1, true>,	 (const void *)k_wavefront_trace<false, 1, 1, true>,
+									(const void *)k_wavefront_trace_cw<true>,			 (const void *)k_wavefront_trace_cw<false>};
+		for (const void *k : l1_kernels)
+		{
+			e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+			if (e != cudaSuccess)
+				return e;
+		}
+	}
 	int per_sm = 0;
 	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wavefront_trace<false, 1, 0, false>, dims.trace_block, dims.trace_smem);
 	if (e != cudaSuccess)
@@ -2329,7 +2347,7 @@ cudaError_t launch_primary(const SceneView &sc, const ShardView &sh, const Wavef
 		k_wavefront_trace_cw<true><<<dims.trace_grid, dims.trace_block, 0, stream>>>(sc, sh, wf, rs, sample_in_frame, 0u);
 		return cudaGetLastError();
 	}
-	switch (rs.trace_variant)
+	switch (rs.smem_nodes > 0 ? 0 : rs.trace_variant) // the staged prefix only exists in variant 0
 	{
 #define RFW_TRACE_CASE(V, LQ, LEAN, PACKED)                                                                                     \
 	case V:                                                                                                             \
@@ -2356,7 +2374,7 @@ cudaError_t launch_trace(const SceneView &sc, const ShardView &sh, const Wavefro
 		k_wavefront_trace_cw<false><<<dims.trace_grid, dims.trace_block, 0, stream>>>(sc, sh, wf, rs, sample_in_frame, depth);
 		return cudaGetLastError();
 	}
-	switch (rs.trace_variant)
+	switch (rs.smem_nodes > 0 ? 0 : rs.trace_variant)
 	{
 #define RFW_TRACE_CASE(V, LQ, LEAN, PACKED)                                                                                     \
 	case V:                                                                                                             \
