@@ -14,6 +14,7 @@
 #include "bvh_build.h"
 #include "device_types.h"
 #include "geometry.h"
+#include "lbvh.h"
 #include "kernels.h"
 
 #include <cuda_runtime.h>
@@ -165,6 +166,10 @@ struct rfwb200_context
 	uint64_t refits = 0, builds = 0;
 	bool shade_ieee = false; // setting "shade_math" = fast | ieee
 	bool wide8 = false;		 // setting "bvh" = 4 | 8 (compressed 8-wide layout, cwbvh.h)
+	bool lbvh = false;		 // setting "builder" = sbvh (host, SAH + spatial splits) | lbvh (device, lbvh.h)
+	bool device_built = false; // the current tree was built on the device: the host has no copy of its topology
+	int device_depth = 0;
+	DevBuf d_lbvh_scratch;
 	DevBuf d_cw_nodes, d_nodes16;
 
 	// ---- wavefront state -----------------------------------------------------------------------------
@@ -524,6 +529,24 @@ int upload_instances(Ctx *c, bool with_flat_inst)
 	return RFWB200_OK;
 }
 
+// point the kernels' views at the 4-wide tree in d_nodes / d_tri_order / d_parent_slot (nn nodes, nr leaf references)
+void bind_geometry_views(Ctx *c, size_t nn, size_t nr)
+{
+	GeometryView &g = c->geo;
+	g = GeometryView{};
+	g.verts = c->d_verts.as<float4>(), g.indices = c->d_indices.as<uint32_t>(), g.mesh_tris = c->d_mesh_tris.ptr;
+	g.instances = c->d_instances.as<DeviceInstance>(), g.flat_inst = c->d_flat_inst.as<uint32_t>();
+	g.flat_count = uint32_t(c->flat_tri_count);
+	g.nodes = c->d_nodes.as<BvhNode4>(), g.tri_order = c->d_tri_order.as<uint32_t>();
+	g.parent_slot = c->d_parent_slot.as<uint32_t>(), g.arrivals = c->d_arrivals.as<uint32_t>();
+	g.node_count = uint32_t(nn), g.ref_count = uint32_t(nr);
+	g.out_tris = c->d_tris.as<TriRec>(), g.out_shade = c->d_shade_tris.as<ShadeTri>();
+	c->scene.nodes = c->d_nodes.as<BvhNode4>(), c->scene.tris = c->d_tris.as<TriRec>();
+	c->scene.shade_tris = c->d_shade_tris.as<ShadeTri>();
+	c->scene.node_count = uint32_t(nn), c->scene.tri_count = uint32_t(nr);
+	c->scene.cw_nodes = nullptr, c->scene.cw_node_count = 0;
+}
+
 // nodes (topology + the builder's boxes), leaf order and the parent links the bottom-up refit climbs
 int upload_topology(Ctx *c)
 {
@@ -575,29 +598,20 @@ int upload_topology(Ctx *c)
 	CK(cudaMemcpyAsync(c->d_parent_slot.ptr, parent_slot.data(), parent_slot.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
 					   c->stream));
 	CK(cudaStreamSynchronize(c->stream));
-	GeometryView &g = c->geo;
-	g.verts = c->d_verts.as<float4>(), g.indices = c->d_indices.as<uint32_t>(), g.mesh_tris = c->d_mesh_tris.ptr;
-	g.instances = c->d_instances.as<DeviceInstance>(), g.flat_inst = c->d_flat_inst.as<uint32_t>();
-	g.flat_count = uint32_t(c->flat_tri_count);
-	g.nodes = c->d_nodes.as<BvhNode4>(), g.tri_order = c->d_tri_order.as<uint32_t>();
-	g.parent_slot = c->d_parent_slot.as<uint32_t>(), g.arrivals = c->d_arrivals.as<uint32_t>();
-	g.node_count = uint32_t(nn), g.ref_count = uint32_t(nr);
-	g.out_tris = c->d_tris.as<TriRec>(), g.out_shade = c->d_shade_tris.as<ShadeTri>();
-	c->scene.nodes = c->d_nodes.as<BvhNode4>(), c->scene.tris = c->d_tris.as<TriRec>();
-	c->scene.shade_tris = c->d_shade_tris.as<ShadeTri>();
-	c->scene.node_count = uint32_t(nn), c->scene.tri_count = uint32_t(nr);
+	bind_geometry_views(c, nn, nr);
 	return RFWB200_OK;
 }
 
 // world-space intersection + shading records (and, for a refit, every box of the tree) from the arena
-int device_generate(Ctx *c, bool refit_boxes)
+int device_generate(Ctx *c, bool refit_boxes, bool record_begin = true)
 {
 	if (!c->ev_geo_a)
 	{
 		CK(cudaEventCreate(&c->ev_geo_a));
 		CK(cudaEventCreate(&c->ev_geo_b));
 	}
-	CK(cudaEventRecord(c->ev_geo_a, c->stream));
+	if (record_begin)
+		CK(cudaEventRecord(c->ev_geo_a, c->stream));
 	c->geo.write_boxes = refit_boxes ? 1 : 0;
 	if (c->bvh.wide8)
 		CK(launch_records(c->geo, c->stream));
@@ -1006,7 +1020,7 @@ extern "C"
 			layout.emplace_back(in.mesh, ok ? c->meshes[in.mesh].triangles.size() : 0);
 			total += layout.back().second;
 		}
-		const bool can_refit = !c->topology_dirty && layout == c->built_layout && (!c->bvh.nodes.empty() || !c->bvh.cw_nodes.empty()) && c->built_tri_count == total;
+		const bool can_refit = !c->topology_dirty && layout == c->built_layout && (!c->bvh.nodes.empty() || !c->bvh.cw_nodes.empty() || c->device_built) && c->built_tri_count == total;
 		const bool device = c->device_geometry && total > 0;
 		if (device && can_refit && c->arena_valid && !c->wide8)
 		{
@@ -1027,6 +1041,56 @@ extern "C"
 		CK(cudaStreamSynchronize(c->stream));
 		if (int r = sync_skinned_meshes_to_host(c))
 			return r;
+		if (c->lbvh && device && !c->wide8)
+		{
+			// Device build (lbvh.h): the host only re-uploads the arena; Morton sort, radix tree, boxes and the 4-wide
+			// collapse run as kernels, then the same record / pack kernels as after a host build.
+			REQUIRE(total < (1u << 30), "more than 2^30 triangles");
+			c->flat_tri_count = total;
+			c->bvh = BvhBuildResult(); // no host copy of this tree
+			if (int r = upload_arena(c))
+				return r;
+			if (int r = upload_instances(c, true))
+				return r;
+			const size_t nn_cap = total; // a 4-wide node has at least two children
+			CK(c->d_nodes.reserve(nn_cap * sizeof(BvhNode4)));
+			CK(c->d_tris.reserve(total * sizeof(TriRec)));
+			CK(c->d_tri_order.reserve(total * sizeof(uint32_t)));
+			CK(c->d_parent_slot.reserve(nn_cap * sizeof(uint32_t)));
+			CK(c->d_arrivals.reserve(nn_cap * sizeof(uint32_t)));
+			CK(c->d_shade_tris.reserve(total * sizeof(ShadeTri)));
+			CK(c->d_lbvh_scratch.reserve(lbvh_scratch_bytes(total)));
+			bind_geometry_views(c, 0, total);
+			if (!c->ev_geo_a)
+			{
+				CK(cudaEventCreate(&c->ev_geo_a));
+				CK(cudaEventCreate(&c->ev_geo_b));
+			}
+			const auto tb0 = std::chrono::steady_clock::now();
+			CK(cudaEventRecord(c->ev_geo_a, c->stream));
+			uint32_t nn = 0;
+			int depth = 0, launches = 0;
+			CK(lbvh_build(c->geo, c->d_lbvh_scratch.ptr, c->d_lbvh_scratch.bytes, c->d_nodes.as<BvhNode4>(), nn_cap, c->d_tri_order.as<uint32_t>(),
+						  c->d_parent_slot.as<uint32_t>(), &nn, &depth, &launches, c->stream));
+			c->launches += uint64_t(launches);
+			if (3 * depth + 1 > TRAVERSAL_STACK)
+				return set_error(RFWB200_ERR_INVALID, "LBVH deeper than the traversal stack allows (use builder=sbvh)");
+			bind_geometry_views(c, nn, total);
+			if (int r = device_generate(c, false, false))
+				return r;
+			CK(cudaStreamSynchronize(c->stream));
+			c->bvh.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb0).count();
+			c->bvh.depth = depth;
+			c->device_built = true, c->device_depth = depth;
+			c->built_layout = layout, c->built_tri_count = total;
+			c->builds++, c->last_update_on_device = true, c->last_update_was_refit = false;
+			c->geometry_dirty = false, c->topology_dirty = false;
+			c->dims_valid = false;
+			return RFWB200_OK;
+		}
+		REQUIRE(!(c->lbvh && !c->device_geometry), "builder=lbvh needs the device geometry path (refit=device)");
+		REQUIRE(!(can_refit && c->device_built && c->bvh.nodes.empty()), "a device-built tree can only be refitted on the device (refit=device)");
+		c->device_built = false;
 		std::vector<ShadeTri> shade;
 		std::vector<float> det_eps;
 		if (int r = flatten_scene(c, device ? nullptr : &shade, device ? nullptr : &det_eps))
@@ -1266,6 +1330,13 @@ extern "C"
 			const bool dev = (v == "device");
 			if (dev != c->device_geometry)
 				c->device_geometry = dev, c->arena_valid = false, c->geometry_dirty = c->topology_dirty = true;
+		}
+		else if (k == "builder")
+		{
+			REQUIRE(v == "sbvh" || v == "lbvh", "builder must be 'sbvh' (host) or 'lbvh' (device)");
+			const bool lb = (v == "lbvh");
+			if (lb != c->lbvh)
+				c->lbvh = lb, c->arena_valid = false, c->geometry_dirty = c->topology_dirty = true;
 		}
 		else if (k == "bvh")
 		{
@@ -1578,9 +1649,9 @@ extern "C"
 	{
 		REQUIRE(c != nullptr, "context is null");
 		if (nodes)
-			*nodes = c->bvh.wide8 ? c->bvh.cw_nodes.size() : c->bvh.nodes.size();
+			*nodes = c->device_built ? c->scene.node_count : (c->bvh.wide8 ? c->bvh.cw_nodes.size() : c->bvh.nodes.size());
 		if (triangles)
-			*triangles = c->bvh.tri_order.size();
+			*triangles = c->device_built ? c->scene.tri_count : c->bvh.tri_order.size();
 		if (sah_cost)
 			*sah_cost = c->bvh.sah_cost;
 		if (build_ms)
@@ -1748,24 +1819,10 @@ extern "C"
 
 	// Host-only self check of the BVH builder (no GPU involved): builds the 4-wide BVH over `n_tris` world-space
 	// triangles (float[9] each) and walks it on the CPU for `n_rays` rays with the kernels' node semantics.
-	int rfwb200_host_bvh_check(const float *tris9, size_t n_tris, int spatial_splits, const float *origins3,
-							   const float *dirs3, size_t n_rays, float *t_out, int32_t *tri_out, uint64_t *nodes_out,
-							   uint64_t *refs_out, int32_t *depth_out, float *sah_out, uint32_t *visits_out)
+	// CPU walk of a flattened 4-wide BVH with the node semantics of the kernels (shared by the self checks below)
+	static int walk_bvh4_host(const BvhBuildResult &bvh, const std::vector<BuildTriangle> &bt, const float *origins3, const float *dirs3,
+							  size_t n_rays, float *t_out, int32_t *tri_out, uint32_t *visits_out)
 	{
-		REQUIRE(tris9 && origins3 && dirs3 && t_out && tri_out, "bad arguments");
-		std::vector<BuildTriangle> bt(n_tris);
-		for (size_t i = 0; i < n_tris; i++)
-			memcpy(&bt[i], tris9 + 9 * i, 9 * sizeof(float));
-		BvhBuildResult bvh;
-		build_bvh4(bt.data(), n_tris, int(std::max(1u, std::thread::hardware_concurrency())), bvh, spatial_splits != 0);
-		if (nodes_out)
-			*nodes_out = bvh.nodes.size();
-		if (refs_out)
-			*refs_out = bvh.tri_order.size();
-		if (depth_out)
-			*depth_out = bvh.depth;
-		if (sah_out)
-			*sah_out = bvh.sah_cost;
 		REQUIRE(3 * bvh.depth + 2 <= TRAVERSAL_STACK, "BVH deeper than the traversal stack allows");
 		for (size_t r = 0; r < n_rays; r++)
 		{
@@ -1853,6 +1910,128 @@ extern "C"
 				visits_out[2 * r] = node_visits, visits_out[2 * r + 1] = tri_tests;
 		}
 		return RFWB200_OK;
+	}
+
+	int rfwb200_host_bvh_check(const float *tris9, size_t n_tris, int spatial_splits, const float *origins3,
+							   const float *dirs3, size_t n_rays, float *t_out, int32_t *tri_out, uint64_t *nodes_out,
+							   uint64_t *refs_out, int32_t *depth_out, float *sah_out, uint32_t *visits_out)
+	{
+		REQUIRE(tris9 && origins3 && dirs3 && t_out && tri_out, "bad arguments");
+		std::vector<BuildTriangle> bt(n_tris);
+		for (size_t i = 0; i < n_tris; i++)
+			memcpy(&bt[i], tris9 + 9 * i, 9 * sizeof(float));
+		BvhBuildResult bvh;
+		build_bvh4(bt.data(), n_tris, int(std::max(1u, std::thread::hardware_concurrency())), bvh, spatial_splits != 0);
+		if (nodes_out)
+			*nodes_out = bvh.nodes.size();
+		if (refs_out)
+			*refs_out = bvh.tri_order.size();
+		if (depth_out)
+			*depth_out = bvh.depth;
+		if (sah_out)
+			*sah_out = bvh.sah_cost;
+		return walk_bvh4_host(bvh, bt, origins3, dirs3, n_rays, t_out, tri_out, visits_out);
+	}
+
+	struct SerialAlloc // what atomicAdd on the level counter does, for one "thread" at a time
+	{
+		uint32_t *next;
+		LB_HD uint32_t operator()(uint32_t k) const
+		{
+			const uint32_t r = *next;
+			*next += k;
+			return r;
+		}
+	};
+
+	// Self check of the GPU builder's algorithm without a GPU: the per-element functions of lbvh.h — the very code the
+	// kernels in geometry.cu run one element per thread — executed in loops on the host (std::sort in place of the radix
+	// sort), then walked like any other 4-wide tree.
+	int rfwb200_host_lbvh_check(const float *tris9, size_t n_tris, const float *origins3, const float *dirs3, size_t n_rays, float *t_out,
+								int32_t *tri_out, uint64_t *nodes_out, int32_t *depth_out, uint32_t *visits_out)
+	{
+		REQUIRE(tris9 && origins3 && dirs3 && t_out && tri_out, "bad arguments");
+		REQUIRE(n_tris >= 1 && n_tris < (1u << 30), "need 1 .. 2^30 triangles");
+		const int n = int(n_tris);
+		std::vector<BuildTriangle> bt(n_tris);
+		for (size_t i = 0; i < n_tris; i++)
+			memcpy(&bt[i], tris9 + 9 * i, 9 * sizeof(float));
+		std::vector<LbvhBox> boxes(n), leaf_box(n), inner_box(n);
+		float slo[3] = {3e38f, 3e38f, 3e38f}, shi[3] = {-3e38f, -3e38f, -3e38f};
+		for (int i = 0; i < n; i++)
+		{
+			LbvhBox &b = boxes[i];
+			for (int a = 0; a < 3; a++)
+			{
+				b.lo[a] = std::min(std::min(bt[i].v0[a], bt[i].v1[a]), bt[i].v2[a]);
+				b.hi[a] = std::max(std::max(bt[i].v0[a], bt[i].v1[a]), bt[i].v2[a]);
+				const float c = 0.5f * (b.lo[a] + b.hi[a]);
+				slo[a] = std::min(slo[a], c), shi[a] = std::max(shi[a], c);
+				const float m = std::max(std::fabs(b.lo[a]), std::fabs(b.hi[a])), pad = std::max(1e-5f, m * 2.4e-7f);
+				b.lo[a] -= pad, b.hi[a] += pad;
+			}
+			b.pad0 = b.pad1 = 0;
+		}
+		float inv[3];
+		for (int a = 0; a < 3; a++)
+			inv[a] = shi[a] > slo[a] ? 1.0f / (shi[a] - slo[a]) : 0.0f;
+		std::vector<uint64_t> keys(n);
+		for (int i = 0; i < n; i++)
+			keys[i] = (uint64_t(lb_morton30(0.5f * (boxes[i].lo[0] + boxes[i].hi[0]), 0.5f * (boxes[i].lo[1] + boxes[i].hi[1]),
+											 0.5f * (boxes[i].lo[2] + boxes[i].hi[2]), slo, inv))
+					   << 32) |
+					  uint64_t(i);
+		std::sort(keys.begin(), keys.end());
+		BvhBuildResult bvh;
+		bvh.tri_order.resize(n);
+		for (int i = 0; i < n; i++)
+			bvh.tri_order[i] = uint32_t(keys[i] & 0xffffffffull), leaf_box[i] = boxes[bvh.tri_order[i]];
+		std::vector<int32_t> left(n), right(n), first(n), last(n), parent_inner(n), parent_leaf(n);
+		std::vector<uint32_t> arrivals(n, 0u);
+		Lbvh2View t{};
+		t.keys = keys.data(), t.n = n;
+		t.left = left.data(), t.right = right.data(), t.first = first.data(), t.last = last.data();
+		t.parent_inner = parent_inner.data(), t.parent_leaf = parent_leaf.data();
+		t.inner_box = inner_box.data(), t.leaf_box = leaf_box.data(), t.arrivals = arrivals.data();
+		for (int i = 0; i < n - 1; i++)
+			lb_build_inner(t, i);
+		for (int i = 0; i < n && n > 1; i++) // k_lbvh_boxes, one "thread" after the other
+		{
+			int cur = parent_leaf[i];
+			while (cur >= 0)
+			{
+				if (arrivals[cur]++ == 0u)
+					break;
+				inner_box[cur] = lb_union(lb_box(t, left[cur]), lb_box(t, right[cur]));
+				cur = parent_inner[cur];
+			}
+		}
+		bvh.nodes.resize(n);
+		bvh.node_parent.resize(n);
+		std::vector<LbvhPending> qa(n), qb(n);
+		qa[0] = LbvhPending{n == 1 ? ~0 : 0, 0xffffffffu};
+		uint32_t level_base = 0, count = 1;
+		int levels = 0;
+		while (count > 0)
+		{
+			uint32_t next = 0;
+			for (uint32_t i = 0; i < count; i++)
+				lb_collapse_node(t, qa[i], level_base + i, level_base + count, bvh.nodes.data(), bvh.node_parent.data(), qb.data(),
+								 SerialAlloc{&next});
+			level_base += count, count = next, levels++;
+			std::swap(qa, qb);
+			REQUIRE(levels <= 64, "radix tree deeper than 64 levels");
+		}
+		bvh.nodes.resize(level_base);
+		bvh.depth = levels;
+		if (nodes_out)
+			*nodes_out = level_base;
+		if (depth_out)
+			*depth_out = levels;
+		// every inner node must have been completed by exactly two arrivals
+		for (int i = 0; i < n - 1; i++)
+			REQUIRE(arrivals[i] == 2u, "bottom-up pass did not reach every inner node");
+		return walk_bvh4_host(bvh, bt, origins3, dirs3, n_rays, t_out, tri_out, visits_out);
 	}
 
 	// Same self check for the compressed 8-wide layout (cwbvh.h): the walk below is the kernels' traversal loop

@@ -15,9 +15,13 @@
 // order as the host builder's (bvh_build.cpp tri_box/padded, context.cpp mul_point/mul_mat3), so a device refit is
 // BIT-IDENTICAL to the host refit of the same vertices (tests/test_parity_gpu.py::test_device_refit_bit_exact).
 #include "geometry.h"
+#include "lbvh.h"
+
+#include <cub/device/device_radix_sort.cuh>
 
 #include <cuda_runtime.h>
 #include <math.h>
+#include <string.h>
 
 namespace rfwb200
 {
@@ -337,6 +341,231 @@ __global__ void __launch_bounds__(128) k_update_triangles(const SkinView s)
 	q[7] = make_float4(v0.x, v0.y, v0.z, q[7].w);
 	q[8] = make_float4(v1.x, v1.y, v1.z, q[8].w);
 	q[9] = make_float4(v2.x, v2.y, v2.z, q[9].w);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LBVH build on the device (lbvh.h): bounds + Morton keys -> cub radix sort -> radix tree -> boxes -> 4-wide collapse
+// ------------------------------------------------------------------------------------------------
+namespace
+{
+__device__ __forceinline__ int32_t float_to_ordered(float f)
+{
+	const int32_t i = __float_as_int(f);
+	return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__host__ __device__ __forceinline__ float ordered_to_float(int32_t i)
+{
+	const int32_t b = i >= 0 ? i : i ^ 0x7fffffff;
+#if defined(__CUDA_ARCH__)
+	return __int_as_float(b);
+#else
+	float f;
+	memcpy(&f, &b, 4);
+	return f;
+#endif
+}
+} // namespace
+
+// per flattened triangle: padded world-space box (the same arithmetic as k_refit) + scene bounds of the centroids
+__global__ void __launch_bounds__(256) k_lbvh_bounds(const GeometryView g, LbvhBox *__restrict__ boxes, int32_t *__restrict__ scene_bounds)
+{
+	const uint32_t src = blockIdx.x * blockDim.x + threadIdx.x;
+	float c[3] = {0.f, 0.f, 0.f};
+	const bool live = src < g.flat_count;
+	if (live)
+	{
+		const uint32_t ii = g.flat_inst[src];
+		const DeviceInstance &in = g.instances[ii];
+		const uint32_t prim = src - in.flat_off;
+		const uint32_t *ix = g.indices + size_t(in.tri_off + prim) * 3;
+		const float4 *vb = g.verts + in.vert_off;
+		const F3 v0 = xf_point(in.transform, vb[ix[0]]);
+		const F3 v1 = xf_point(in.transform, vb[ix[1]]);
+		const F3 v2 = xf_point(in.transform, vb[ix[2]]);
+		LbvhBox b;
+		b.lo[0] = fminf(fminf(v0.x, v1.x), v2.x), b.lo[1] = fminf(fminf(v0.y, v1.y), v2.y), b.lo[2] = fminf(fminf(v0.z, v1.z), v2.z);
+		b.hi[0] = fmaxf(fmaxf(v0.x, v1.x), v2.x), b.hi[1] = fmaxf(fmaxf(v0.y, v1.y), v2.y), b.hi[2] = fmaxf(fmaxf(v0.z, v1.z), v2.z);
+		for (int a = 0; a < 3; a++)
+		{
+			c[a] = 0.5f * (b.lo[a] + b.hi[a]);
+			pad_axis(b.lo[a], b.hi[a]);
+		}
+		b.pad0 = b.pad1 = 0.0f;
+		boxes[src] = b;
+	}
+	// warp-reduced atomics on the centroid bounds
+	for (int a = 0; a < 3; a++)
+	{
+		const int32_t lo = __reduce_min_sync(0xffffffffu, live ? float_to_ordered(c[a]) : 0x7fffffff);
+		const int32_t hi = __reduce_max_sync(0xffffffffu, live ? float_to_ordered(c[a]) : int32_t(0x80000000));
+		if ((threadIdx.x & 31u) == 0u)
+		{
+			atomicMin(&scene_bounds[a], lo);
+			atomicMax(&scene_bounds[3 + a], hi);
+		}
+	}
+}
+
+__global__ void __launch_bounds__(256) k_lbvh_keys(const LbvhBox *__restrict__ boxes, uint32_t n, const int32_t *__restrict__ scene_bounds,
+												   uint64_t *__restrict__ keys)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	float lo[3], inv[3];
+	for (int a = 0; a < 3; a++)
+	{
+		lo[a] = ordered_to_float(scene_bounds[a]);
+		const float ext = ordered_to_float(scene_bounds[3 + a]) - lo[a];
+		inv[a] = ext > 0.0f ? 1.0f / ext : 0.0f;
+	}
+	const LbvhBox b = boxes[i];
+	// centroid of the padded box = centroid of the exact box up to rounding: only the ordering matters
+	const uint32_t m = lb_morton30(0.5f * (b.lo[0] + b.hi[0]), 0.5f * (b.lo[1] + b.hi[1]), 0.5f * (b.lo[2] + b.hi[2]), lo, inv);
+	keys[i] = (uint64_t(m) << 32) | uint64_t(i);
+}
+
+__global__ void __launch_bounds__(256) k_lbvh_gather(const uint64_t *__restrict__ keys, const LbvhBox *__restrict__ boxes, uint32_t n,
+													 LbvhBox *__restrict__ leaf_box, uint32_t *__restrict__ tri_order)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	const uint32_t src = uint32_t(keys[i] & 0xffffffffull);
+	leaf_box[i] = boxes[src];
+	tri_order[i] = src;
+}
+
+__global__ void __launch_bounds__(256) k_lbvh_inner(const Lbvh2View t)
+{
+	const int i = int(blockIdx.x * blockDim.x + threadIdx.x);
+	if (i < t.n - 1)
+		lb_build_inner(t, i);
+}
+
+__global__ void __launch_bounds__(256) k_lbvh_boxes(const Lbvh2View t)
+{
+	const int i = int(blockIdx.x * blockDim.x + threadIdx.x);
+	if (i >= t.n)
+		return;
+	int cur = t.parent_leaf[i];
+	while (cur >= 0)
+	{
+		__threadfence();
+		if (atomicAdd(&t.arrivals[cur], 1u) == 0u)
+			return; // the sibling subtree is not done yet: its last thread continues from here
+		__threadfence();
+		const int32_t l = t.left[cur], r = t.right[cur];
+		const volatile LbvhBox *bl = l < 0 ? &t.leaf_box[~l] : &t.inner_box[l];
+		const volatile LbvhBox *br = r < 0 ? &t.leaf_box[~r] : &t.inner_box[r];
+		LbvhBox u;
+		for (int k = 0; k < 3; k++)
+			u.lo[k] = fminf(bl->lo[k], br->lo[k]), u.hi[k] = fmaxf(bl->hi[k], br->hi[k]);
+		u.pad0 = u.pad1 = 0.0f;
+		t.inner_box[cur] = u;
+		cur = t.parent_inner[cur];
+	}
+}
+
+__global__ void __launch_bounds__(128) k_lbvh_collapse(const Lbvh2View t, const LbvhPending *__restrict__ queue, uint32_t count, uint32_t level_base,
+													   uint32_t next_level_base, BvhNode4 *nodes, uint32_t *parent_slot, LbvhPending *next_queue,
+													   uint32_t *next_count)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count)
+		return;
+	lb_collapse_node(t, queue[i], level_base + i, next_level_base, nodes, parent_slot, next_queue,
+					 [next_count] __device__(uint32_t k) { return atomicAdd(next_count, k); });
+}
+
+size_t lbvh_scratch_bytes(size_t n)
+{
+	size_t sort_tmp = 0;
+	cub::DeviceRadixSort::SortKeys(nullptr, sort_tmp, (const uint64_t *)nullptr, (uint64_t *)nullptr, int(n), 0, 62);
+	auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
+	return al(sort_tmp) + 2 * al(n * 8) + 3 * al(n * sizeof(LbvhBox)) + 6 * al(n * 4) + al(n * 4) + 2 * al(n * sizeof(LbvhPending)) + al(64) + 4096;
+}
+
+// Builds nodes[0..*node_count), tri_order[0..flat_count), parent_slot[0..*node_count) on `stream` (synchronises once per
+// tree level to read the size of the next level).
+cudaError_t lbvh_build(const GeometryView &g, void *scratch, size_t scratch_bytes, BvhNode4 *nodes, size_t node_capacity, uint32_t *tri_order,
+					   uint32_t *parent_slot, uint32_t *node_count, int *depth, int *launches, cudaStream_t stream)
+{
+	const uint32_t n = g.flat_count;
+	*node_count = 0, *depth = 0;
+	if (n == 0 || scratch_bytes < lbvh_scratch_bytes(n))
+		return cudaErrorInvalidValue;
+	auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
+	char *p = static_cast<char *>(scratch);
+	auto take = [&](size_t b) {
+		char *r = p;
+		p += al(b);
+		return r;
+	};
+	size_t sort_tmp = 0;
+	cub::DeviceRadixSort::SortKeys(nullptr, sort_tmp, (const uint64_t *)nullptr, (uint64_t *)nullptr, int(n), 0, 62);
+	void *d_sort = take(sort_tmp);
+	uint64_t *keys_a = reinterpret_cast<uint64_t *>(take(size_t(n) * 8)), *keys_b = reinterpret_cast<uint64_t *>(take(size_t(n) * 8));
+	LbvhBox *boxes = reinterpret_cast<LbvhBox *>(take(size_t(n) * sizeof(LbvhBox)));
+	Lbvh2View t{};
+	t.n = int32_t(n);
+	t.leaf_box = reinterpret_cast<LbvhBox *>(take(size_t(n) * sizeof(LbvhBox)));
+	t.inner_box = reinterpret_cast<LbvhBox *>(take(size_t(n) * sizeof(LbvhBox)));
+	t.left = reinterpret_cast<int32_t *>(take(size_t(n) * 4)), t.right = reinterpret_cast<int32_t *>(take(size_t(n) * 4));
+	t.first = reinterpret_cast<int32_t *>(take(size_t(n) * 4)), t.last = reinterpret_cast<int32_t *>(take(size_t(n) * 4));
+	t.parent_inner = reinterpret_cast<int32_t *>(take(size_t(n) * 4)), t.parent_leaf = reinterpret_cast<int32_t *>(take(size_t(n) * 4));
+	t.arrivals = reinterpret_cast<uint32_t *>(take(size_t(n) * 4));
+	LbvhPending *queue_a = reinterpret_cast<LbvhPending *>(take(size_t(n) * sizeof(LbvhPending)));
+	LbvhPending *queue_b = reinterpret_cast<LbvhPending *>(take(size_t(n) * sizeof(LbvhPending)));
+	int32_t *bounds = reinterpret_cast<int32_t *>(take(64)); // 6 ordered ints + the level counter
+	uint32_t *next_count = reinterpret_cast<uint32_t *>(bounds + 8);
+	const uint32_t blocks = (n + 255u) / 256u;
+	cudaError_t e;
+	const int32_t init[12] = {0x7fffffff, 0x7fffffff, 0x7fffffff, int32_t(0x80000000), int32_t(0x80000000), int32_t(0x80000000), 0, 0, 0, 0, 0, 0};
+	if ((e = cudaMemcpyAsync(bounds, init, sizeof(init), cudaMemcpyHostToDevice, stream)) != cudaSuccess)
+		return e;
+	k_lbvh_bounds<<<blocks, 256, 0, stream>>>(g, boxes, bounds);
+	k_lbvh_keys<<<blocks, 256, 0, stream>>>(boxes, n, bounds, keys_a);
+	if ((e = cub::DeviceRadixSort::SortKeys(d_sort, sort_tmp, keys_a, keys_b, int(n), 0, 62, stream)) != cudaSuccess)
+		return e;
+	t.keys = keys_b;
+	k_lbvh_gather<<<blocks, 256, 0, stream>>>(keys_b, boxes, n, t.leaf_box, tri_order);
+	*launches += 4 + 3; // + the sort's passes, roughly
+	LbvhPending root{n == 1 ? ~0 : 0, 0xffffffffu};
+	if (n > 1)
+	{
+		if ((e = cudaMemsetAsync(t.arrivals, 0, size_t(n) * 4, stream)) != cudaSuccess)
+			return e;
+		k_lbvh_inner<<<blocks, 256, 0, stream>>>(t);
+		k_lbvh_boxes<<<blocks, 256, 0, stream>>>(t);
+		*launches += 2;
+	}
+	if ((e = cudaMemcpyAsync(queue_a, &root, sizeof(root), cudaMemcpyHostToDevice, stream)) != cudaSuccess)
+		return e;
+	uint32_t level_base = 0, count = 1;
+	LbvhPending *qin = queue_a, *qout = queue_b;
+	int levels = 0;
+	while (count > 0)
+	{
+		if (size_t(level_base) + count > node_capacity)
+			return cudaErrorMemoryAllocation;
+		if ((e = cudaMemsetAsync(next_count, 0, 4, stream)) != cudaSuccess)
+			return e;
+		k_lbvh_collapse<<<(count + 127u) / 128u, 128, 0, stream>>>(t, qin, count, level_base, level_base + count, nodes, parent_slot, qout, next_count);
+		*launches += 1;
+		uint32_t next = 0;
+		if ((e = cudaMemcpyAsync(&next, next_count, 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess)
+			return e;
+		if ((e = cudaStreamSynchronize(stream)) != cudaSuccess)
+			return e;
+		level_base += count, count = next, levels++;
+		LbvhPending *tmp = qin;
+		qin = qout, qout = tmp;
+		if (levels > 64)
+			return cudaErrorUnknown;
+	}
+	*node_count = level_base, *depth = levels;
+	return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1,0 +1,231 @@
+// lbvh.h — per-element steps of the GPU BVH builder (setting "builder" = lbvh), written once as host/device functions:
+// the kernels in lbvh.cu run them one element per thread, the host self check (rfwb200_host_lbvh_check, no GPU) runs the
+// very same functions in a loop.
+//
+// Replaces, for scenes whose topology changes (new meshes / instances, or first load of very large scenes), the host-side
+// builder the reference delegates to its Rust crate (RFW/system/bvh/src/bvh_tree.cpp:48-102, top_level_bvh.cpp:54-102;
+// CUDART rebuilds its TLAS on the CPU every update, CUDART/src/Context.cpp:394-456):
+//   1. Morton code of every triangle centroid (30 bits) | triangle index  -> radix sort
+//   2. binary radix tree over the sorted keys (Karras, "Maximizing Parallelism in the Construction of BVHs, Octrees, and
+//      k-d Trees", HPG 2012): every inner node finds its range and split independently
+//   3. boxes bottom-up with one arrival counter per inner node
+//   4. collapse to the 4-wide BvhNode4 layout level by level (a subtree of <= 4 triangles becomes a leaf: its triangles
+//      are contiguous in the sorted order), children allocated contiguously -> the same node format, leaf encoding and
+//      parent links as the host builder's output, so the refit / pack / trace kernels do not care who built the tree.
+// Quality is that of an LBVH (no SAH, no spatial splits): traversal is slower than on the host-built SBVH; it is the
+// fast path for dynamic topology, not the default for static scenes.
+#pragma once
+#include "device_types.h"
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define LB_HD __host__ __device__ __forceinline__
+#else
+#define LB_HD inline
+#endif
+
+namespace rfwb200
+{
+
+struct LbvhBox
+{
+	float lo[3], pad0;
+	float hi[3], pad1;
+};
+
+// BVH2 produced by steps 2-3: inner nodes 0..n-2 (root 0), leaves 0..n-1 in sorted order; a child word >= 0 is an inner
+// node, < 0 is leaf ~child
+struct Lbvh2View
+{
+	const uint64_t *keys; // sorted (morton30 << 32 | triangle index): unique
+	int32_t n;			  // triangles
+	int32_t *left, *right;		   // [n-1]
+	int32_t *first, *last;		   // [n-1] leaf range covered by an inner node
+	int32_t *parent_inner;		   // [n-1] parent of an inner node (root: -1)
+	int32_t *parent_leaf;		   // [n]
+	LbvhBox *inner_box, *leaf_box; // [n-1], [n] (leaf boxes in sorted order, padded like the host builder's)
+	uint32_t *arrivals;			   // [n-1]
+};
+
+LB_HD uint32_t lb_expand10(uint32_t v)
+{
+	v = (v * 0x00010001u) & 0xFF0000FFu;
+	v = (v * 0x00000101u) & 0x0F00F00Fu;
+	v = (v * 0x00000011u) & 0xC30C30C3u;
+	v = (v * 0x00000005u) & 0x49249249u;
+	return v;
+}
+
+// centroid relative to the scene box -> 30-bit Morton code
+LB_HD uint32_t lb_morton30(float cx, float cy, float cz, const float *scene_lo, const float *scene_inv_ext)
+{
+	float f[3] = {(cx - scene_lo[0]) * scene_inv_ext[0], (cy - scene_lo[1]) * scene_inv_ext[1], (cz - scene_lo[2]) * scene_inv_ext[2]};
+	uint32_t q[3];
+	for (int a = 0; a < 3; a++)
+	{
+		float v = f[a] * 1024.0f;
+		v = v < 0.0f ? 0.0f : (v > 1023.0f ? 1023.0f : v);
+		q[a] = uint32_t(v);
+	}
+	return (lb_expand10(q[0]) << 2) | (lb_expand10(q[1]) << 1) | lb_expand10(q[2]);
+}
+
+LB_HD int lb_clz64(uint64_t x)
+{
+#if defined(__CUDA_ARCH__)
+	return __clzll((long long)x);
+#else
+	return x ? __builtin_clzll(x) : 64;
+#endif
+}
+
+// length of the common prefix of keys i and j, -1 outside the array
+LB_HD int lb_delta(const uint64_t *keys, int n, int i, int j)
+{
+	if (j < 0 || j >= n)
+		return -1;
+	return lb_clz64(keys[i] ^ keys[j]);
+}
+
+// step 2: inner node i of the radix tree
+LB_HD void lb_build_inner(const Lbvh2View &t, int i)
+{
+	const uint64_t *k = t.keys;
+	const int n = t.n;
+	const int d = (lb_delta(k, n, i, i + 1) - lb_delta(k, n, i, i - 1)) >= 0 ? 1 : -1;
+	const int dmin = lb_delta(k, n, i, i - d);
+	int lmax = 2;
+	while (lb_delta(k, n, i, i + lmax * d) > dmin)
+		lmax *= 2;
+	int l = 0;
+	for (int s = lmax / 2; s >= 1; s /= 2)
+		if (lb_delta(k, n, i, i + (l + s) * d) > dmin)
+			l += s;
+	const int j = i + l * d;
+	const int dnode = lb_delta(k, n, i, j);
+	int s = 0;
+	int step = l;
+	do
+	{
+		step = (step + 1) >> 1;
+		if (lb_delta(k, n, i, i + (s + step) * d) > dnode)
+			s += step;
+	} while (step > 1);
+	const int gamma = i + s * d + (d < 0 ? d : 0);
+	const int lo = i < j ? i : j, hi = i < j ? j : i;
+	const int32_t lc = (lo == gamma) ? ~gamma : gamma;
+	const int32_t rc = (hi == gamma + 1) ? ~(gamma + 1) : (gamma + 1);
+	t.left[i] = lc, t.right[i] = rc;
+	t.first[i] = lo, t.last[i] = hi;
+	if (lc >= 0)
+		t.parent_inner[lc] = i;
+	else
+		t.parent_leaf[~lc] = i;
+	if (rc >= 0)
+		t.parent_inner[rc] = i;
+	else
+		t.parent_leaf[~rc] = i;
+	if (i == 0)
+		t.parent_inner[0] = -1;
+}
+
+LB_HD LbvhBox lb_union(const LbvhBox &a, const LbvhBox &b)
+{
+	LbvhBox r;
+	for (int k = 0; k < 3; k++)
+	{
+		r.lo[k] = fminf(a.lo[k], b.lo[k]);
+		r.hi[k] = fmaxf(a.hi[k], b.hi[k]);
+	}
+	r.pad0 = r.pad1 = 0.0f;
+	return r;
+}
+
+LB_HD float lb_area(const LbvhBox &b)
+{
+	const float ex = b.hi[0] - b.lo[0], ey = b.hi[1] - b.lo[1], ez = b.hi[2] - b.lo[2];
+	return ex * ey + ey * ez + ez * ex;
+}
+
+// one entry of the level queue of step 4
+struct LbvhPending
+{
+	int32_t node2;		  // BVH2 inner node this 4-wide node is made from (or ~leaf when the whole scene is one leaf)
+	uint32_t parent_slot; // (parent << 2) | slot, root 0xffffffff
+};
+
+constexpr int LBVH_MAX_LEAF = 4;
+
+LB_HD int lb_count(const Lbvh2View &t, int32_t c) { return c < 0 ? 1 : (t.last[c] - t.first[c] + 1); }
+LB_HD int lb_first(const Lbvh2View &t, int32_t c) { return c < 0 ? ~c : t.first[c]; }
+LB_HD const LbvhBox &lb_box(const Lbvh2View &t, int32_t c) { return c < 0 ? t.leaf_box[~c] : t.inner_box[c]; }
+
+// step 4: 4-wide node `self` from BVH2 node p.node2.  Children that stay inner are appended to the next level:
+// `alloc(count)` returns the position of the first of `count` consecutive entries (atomicAdd on the device).
+template <typename Alloc>
+LB_HD void lb_collapse_node(const Lbvh2View &t, const LbvhPending &p, uint32_t self, uint32_t next_level_base, BvhNode4 *nodes,
+							uint32_t *parent_slot_out, LbvhPending *next_queue, Alloc alloc)
+{
+	int32_t kids[4];
+	int nk = 0;
+	if (p.node2 < 0 || lb_count(t, p.node2) <= LBVH_MAX_LEAF)
+		kids[nk++] = p.node2; // the whole tree is one leaf
+	else
+	{
+		kids[nk++] = t.left[p.node2], kids[nk++] = t.right[p.node2];
+		while (nk < 4)
+		{
+			int best = -1;
+			float best_area = -1.0f;
+			for (int k = 0; k < nk; k++)
+				if (kids[k] >= 0 && lb_count(t, kids[k]) > LBVH_MAX_LEAF)
+				{
+					const float a = lb_area(lb_box(t, kids[k]));
+					if (a > best_area)
+						best_area = a, best = k;
+				}
+			if (best < 0)
+				break;
+			const int32_t c = kids[best];
+			kids[best] = t.left[c];
+			kids[nk++] = t.right[c];
+		}
+	}
+	int n_inner = 0;
+	for (int k = 0; k < nk; k++)
+		if (kids[k] >= 0 && lb_count(t, kids[k]) > LBVH_MAX_LEAF)
+			n_inner++;
+	const uint32_t pos = n_inner ? alloc(uint32_t(n_inner)) : 0u;
+	BvhNode4 node;
+	const float qnan = nanf("");
+	int inner_rank = 0;
+	for (int k = 0; k < 4; k++)
+	{
+		if (k >= nk)
+		{
+			node.minx[k] = node.miny[k] = node.minz[k] = node.maxx[k] = node.maxy[k] = node.maxz[k] = qnan;
+			node.child[k] = -1;
+			continue;
+		}
+		const LbvhBox &b = lb_box(t, kids[k]);
+		node.minx[k] = b.lo[0], node.miny[k] = b.lo[1], node.minz[k] = b.lo[2];
+		node.maxx[k] = b.hi[0], node.maxy[k] = b.hi[1], node.maxz[k] = b.hi[2];
+		const int cnt = lb_count(t, kids[k]);
+		if (cnt <= LBVH_MAX_LEAF)
+			node.child[k] = ~int32_t((uint32_t(lb_first(t, kids[k])) << 2) | uint32_t(cnt - 1));
+		else
+		{
+			const uint32_t q = pos + uint32_t(inner_rank++);
+			node.child[k] = int32_t(next_level_base + q);
+			next_queue[q].node2 = kids[k];
+			next_queue[q].parent_slot = (self << 2) | uint32_t(k);
+		}
+	}
+	node.pad[0] = nk, node.pad[1] = node.pad[2] = node.pad[3] = 0;
+	nodes[self] = node;
+	parent_slot_out[self] = p.parent_slot;
+}
+
+} // namespace rfwb200

@@ -376,6 +376,54 @@ def test_device_geometry_is_bit_identical_to_the_host_path(product_lib):
     assert np.array_equal(d.read_image(), h.read_image())
 
 
+def test_device_lbvh_build_then_device_refit(product_lib, oracle_lib):
+    """builder=lbvh: Morton sort + radix tree + 4-wide collapse as kernels (csrc/lbvh.h, geometry.cu); the tree it makes is
+    refitted by the same k_refit as a host-built one.  Hits against the oracle, frame against the host-built frame."""
+    W, H = 160, 96
+    (g, sc), (o, _) = make_pair(product_lib, oracle_lib, S.feature_soup, W, H)
+    ref = R.RenderContext(product_lib)
+    S.upload(ref, S.feature_soup(), W, H)
+    g.set_setting("builder", "lbvh")
+    g.update()
+    st = g.get_geometry_stats()
+    assert (st.on_device, st.was_refit, st.builds, st.refits) == (1, 0, 2, 0) and st.device_ms > 0
+    info = g.get_bvh_info()
+    assert info["triangles"] == sc.triangle_count() and 1 <= info["nodes"] <= info["triangles"]
+    cam = sc.camera(W, H)
+    origins, dirs = o.generate_primary(cam, 0)
+    _check_hits(g, o, origins, dirs, g.trace_closest(origins, dirs), o.trace_closest(origins, dirs))
+    for ctx in (g, ref):
+        ctx.set_setting("spp", 2)
+        ctx.render_frame(cam, R.RESET)
+    assert (np.abs(g.read_image() - ref.read_image()).max(axis=-1) > 0).mean() < 2e-3
+    # move a mesh: refit of the device-built tree, on the device
+    m = sc.meshes[1]
+    rng = np.random.default_rng(9)
+    v2 = m.vertices.copy()
+    v2[:, :3] += rng.normal(0, 0.05, size=v2[:, :3].shape).astype(np.float32)
+    pos = v2[:, :3].reshape(-1, 3, 3) if m.indices is None else v2[m.indices][:, :, :3]
+    tri2 = m.triangles.copy()
+    tri2["vertex0"], tri2["vertex1"], tri2["vertex2"] = pos[:, 0], pos[:, 1], pos[:, 2]
+    for ctx in (g, o):
+        ctx.set_mesh(1, v2, tri2, m.indices)
+        ctx.update()
+    st = g.get_geometry_stats()
+    assert (st.on_device, st.was_refit, st.builds, st.refits) == (1, 1, 2, 1)
+    _check_hits(g, o, origins, dirs, g.trace_closest(origins, dirs), o.trace_closest(origins, dirs))
+    # a new mesh: rebuilt on the device again
+    extra = S.box_mesh((-0.3, 0, -0.3), (0.3, 0.5, 0.3), 0)
+    for ctx in (g, o):
+        ctx.set_mesh(len(sc.meshes), extra.vertices, extra.triangles, extra.indices)
+        ctx.set_instance(len(sc.instances), len(sc.meshes), S.translate(0.4, 0.1, 0.3))
+        ctx.update()
+    st = g.get_geometry_stats()
+    assert (st.on_device, st.was_refit, st.builds) == (1, 0, 3)
+    _check_hits(g, o, origins, dirs, g.trace_closest(origins, dirs), o.trace_closest(origins, dirs))
+    g.set_setting("refit", "host")
+    with pytest.raises(R.Rfwb200Error):
+        g.update()  # builder=lbvh needs the device geometry path
+
+
 def _skinned_reference(sc, sk, k):
     """CPU restatement of set_pose + update_triangles (oracle/skinning.py) for frame k of the skin's animation."""
     from oracle import skinning as K

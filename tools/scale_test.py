@@ -8,9 +8,12 @@ sys.path.insert(0, str(REPO / "rendering-fw_b200" / "python"))
 import numpy as np
 import rfwb200 as R, scenes as S
 n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 10_000_000
+builder = sys.argv[2] if len(sys.argv) > 2 else "sbvh"  # sbvh = host SAH builder with spatial splits, lbvh = device builder
 t0 = time.time(); sc = S.atrium(target_tris=n); print("scene", sc.name, sc.triangle_count(), "tris, gen %.1fs" % (time.time() - t0))
 ctx = R.RenderContext(R.load_product())
-t0 = time.time(); S.upload(ctx, sc, 1920, 1080); print("upload+build %.1fs" % (time.time() - t0), ctx.get_bvh_info())
+ctx.set_setting("builder", builder)
+t0 = time.time(); S.upload(ctx, sc, 1920, 1080); print(builder, "upload+build %.1fs" % (time.time() - t0), ctx.get_bvh_info())
+g = ctx.get_geometry_stats(); print("geometry: on_device", g.on_device, "device_ms %.2f host_ms %.1f" % (g.device_ms, g.host_ms))
 ctx.set_setting("spp", 4)
 cam = sc.camera(1920, 1080)
 for i in range(3):
