@@ -87,6 +87,7 @@ struct Node2
 	Box box;
 	int32_t left = -1, right = -1; // children (inner)
 	std::vector<uint32_t> prims;   // leaf content
+	std::vector<Box> prim_boxes;   // the (possibly clipped) box of each reference
 	bool leaf = false;
 };
 
@@ -155,8 +156,9 @@ struct Builder
 	{
 		node.leaf = true;
 		node.prims.resize(refs.size());
+		node.prim_boxes.resize(refs.size());
 		for (size_t i = 0; i < refs.size(); i++)
-			node.prims[i] = refs[i].prim;
+			node.prims[i] = refs[i].prim, node.prim_boxes[i] = refs[i].box;
 	}
 
 	// returns false when the node became a leaf; otherwise fills the two child tasks
@@ -603,12 +605,17 @@ void build_bvh4(const BuildTriangle *tris, size_t count, int threads, BvhBuildRe
 				const uint32_t first = uint32_t(out.tri_order.size());
 				const uint32_t cnt = uint32_t(std::min<size_t>(std::max<size_t>(c.prims.size(), 1), MAX_LEAF));
 				if (c.prims.empty())
+				{
 					out.tri_order.push_back(0);
+					out.ref_boxes.insert(out.ref_boxes.end(), {0.f, 0.f, 0.f, 0.f, 0.f, 0.f});
+				}
 				for (size_t i = 0; i < c.prims.size(); i++)
 				{
 					if (i >= size_t(MAX_LEAF))
 						break; // cannot happen: leaves are only made at <= MAX_LEAF references
 					out.tri_order.push_back(c.prims[i]);
+					const Box &rb = c.prim_boxes[i];
+					out.ref_boxes.insert(out.ref_boxes.end(), {rb.lo[0], rb.lo[1], rb.lo[2], rb.hi[0], rb.hi[1], rb.hi[2]});
 				}
 				node.child[k] = ~int32_t((first << 2) | (cnt - 1));
 				cost += c.box.area() * inv_root_area * float(c.prims.size());
@@ -630,10 +637,27 @@ void build_bvh4(const BuildTriangle *tris, size_t count, int threads, BvhBuildRe
 	out.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
 
-void refit_bvh4(const BuildTriangle *tris, size_t count, BvhBuildResult &bvh)
+// box of leaf reference i for a refit: whole (moved) triangle, or the builder's clipped box when the triangle has not
+// moved since the build
+static inline Box refit_ref_box(const BuildTriangle *tris, const BvhBuildResult &bvh, const uint8_t *tri_moved, uint32_t i)
+{
+	const uint32_t src = bvh.tri_order[i];
+	if (tri_moved && !tri_moved[src] && bvh.ref_boxes.size() >= 6 * size_t(i + 1))
+	{
+		Box b;
+		for (int a = 0; a < 3; a++)
+			b.lo[a] = bvh.ref_boxes[6 * size_t(i) + a], b.hi[a] = bvh.ref_boxes[6 * size_t(i) + 3 + a];
+		return padded(b);
+	}
+	return padded(tri_box(tris[src]));
+}
+
+void refit_bvh4(const BuildTriangle *tris, size_t count, BvhBuildResult &bvh, const uint8_t *tri_moved)
 {
 	(void)count;
-	// boxes are recomputed from whole triangles: a tree built with spatial splits stays valid (looser) after a refit
+	// Only triangles that moved since the build get whole-triangle boxes; the others keep the builder's reference boxes,
+	// so the spatial splits of the static part of a scene survive any number of refits (refitting every reference from
+	// its whole triangle made Sponza 7x slower to trace after the first animated frame, profiles/r01b).
 	for (size_t ni = bvh.nodes.size(); ni-- > 0;)
 	{
 		BvhNode4 &n = bvh.nodes[ni];
@@ -646,7 +670,7 @@ void refit_bvh4(const BuildTriangle *tris, size_t count, BvhBuildResult &bvh)
 			{
 				const uint32_t v = uint32_t(~c), first = v >> 2, cnt = (v & 3u) + 1u;
 				for (uint32_t i = first; i < first + cnt; i++)
-					b.grow(padded(tri_box(tris[bvh.tri_order[i]])));
+					b.grow(refit_ref_box(tris, bvh, tri_moved, i));
 			}
 			else
 			{
@@ -690,8 +714,10 @@ void build_cwbvh(const BuildTriangle *tris, size_t count, int threads, BvhBuildR
 	std::vector<uint32_t> sub(size_t(n_nodes2), 0);
 	for (int32_t i = n_nodes2; i-- > 0;) // children are allocated after their parents
 		sub[i] = n2[i].leaf ? uint32_t(n2[i].prims.size()) : (sub[n2[i].left] + sub[n2[i].right]);
+	std::vector<Box> leaf_boxes;
 	auto gather = [&](int32_t root, std::vector<uint32_t> &prims) {
 		prims.clear();
+		leaf_boxes.clear();
 		int32_t st[16];
 		int sp = 0;
 		st[sp++] = root;
@@ -700,9 +726,14 @@ void build_cwbvh(const BuildTriangle *tris, size_t count, int threads, BvhBuildR
 			const Node2 &c = n2[st[--sp]];
 			if (c.leaf)
 			{
-				for (uint32_t pr : c.prims)
-					if (std::find(prims.begin(), prims.end(), pr) == prims.end())
-						prims.push_back(pr);
+				for (size_t pi = 0; pi < c.prims.size(); pi++)
+				{
+					const auto it = std::find(prims.begin(), prims.end(), c.prims[pi]);
+					if (it == prims.end())
+						prims.push_back(c.prims[pi]), leaf_boxes.push_back(c.prim_boxes[pi]);
+					else
+						leaf_boxes[size_t(it - prims.begin())].grow(c.prim_boxes[pi]); // two halves of one split triangle
+				}
 			}
 			else
 				st[sp++] = c.left, st[sp++] = c.right;
@@ -805,7 +836,11 @@ void build_cwbvh(const BuildTriangle *tris, size_t count, int threads, BvhBuildR
 				if (cnt == 0)
 					continue; // cannot happen: the builder never makes empty leaves
 				for (uint32_t i = 0; i < cnt; i++)
+				{
 					out.tri_order.push_back(leaf_prims[i]);
+					const Box &rb = leaf_boxes[i];
+					out.ref_boxes.insert(out.ref_boxes.end(), {rb.lo[0], rb.lo[1], rb.lo[2], rb.hi[0], rb.hi[1], rb.hi[2]});
+				}
 				node.meta[sl] = uint8_t((((1u << cnt) - 1u) << 5) | off);
 				cost += c.box.area() * inv_root_area * float(cnt);
 			}
@@ -825,7 +860,7 @@ void build_cwbvh(const BuildTriangle *tris, size_t count, int threads, BvhBuildR
 	out.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
 
-void refit_cwbvh(const BuildTriangle *tris, size_t count, BvhBuildResult &bvh)
+void refit_cwbvh(const BuildTriangle *tris, size_t count, BvhBuildResult &bvh, const uint8_t *tri_moved)
 {
 	(void)count;
 	// children are stored after their parents (breadth-first): walk backwards so a child's boxes are final before its
@@ -856,7 +891,7 @@ void refit_cwbvh(const BuildTriangle *tris, size_t count, BvhBuildResult &bvh)
 			{
 				const uint32_t first = n.tri_base + (meta & 31u), cnt = uint32_t(__builtin_popcount(meta >> 5));
 				for (uint32_t i = first; i < first + cnt; i++)
-					b.grow(padded(tri_box(tris[bvh.tri_order[i]])));
+					b.grow(refit_ref_box(tris, bvh, tri_moved, i));
 			}
 			for (int ax = 0; ax < 3; ax++)
 				a.lo[ax][s] = b.lo[ax], a.hi[ax][s] = b.hi[ax];

@@ -23,6 +23,8 @@ struct BvhBuildResult
 	std::vector<uint32_t> tri_order;   // leaf-ordered position -> input triangle index (spatial splits may
 									   // reference a triangle from several leaves, so size() >= triangle count)
 	std::vector<uint32_t> node_parent; // for refit: parent index per node (root: 0xffffffff)
+	std::vector<float> ref_boxes;	   // 6 floats (lo, hi) per leaf-ordered reference: the builder's box of that reference
+									   // (clipped by spatial splits), kept by refits for triangles that did not move
 	// compressed 8-wide layout (cwbvh.h), filled by build_cwbvh instead of nodes / node_parent
 	bool wide8 = false;
 	std::vector<CwNode> cw_nodes;			// breadth-first, root = 0
@@ -41,12 +43,14 @@ void build_bvh4(const BuildTriangle *tris, size_t count, int threads, BvhBuildRe
 
 // Recompute all boxes bottom-up for moved vertices with unchanged topology (the reference's refit,
 // bvh_tree.cpp:104-114, top_level_bvh.cpp:46-52).
-void refit_bvh4(const BuildTriangle *tris, size_t count, BvhBuildResult &bvh);
+// `tri_moved` (one byte per input triangle, may be null = all moved): triangles that have not moved since the build keep
+// their reference boxes, the others are bounded as whole triangles.
+void refit_bvh4(const BuildTriangle *tris, size_t count, BvhBuildResult &bvh, const uint8_t *tri_moved = nullptr);
 
 // The same SBVH collapsed to 8-wide nodes with quantised child boxes (cwbvh.h): leaves of <= 3 triangles, children
 // placed in octant-ordered slots, depth <= CW_MAX_DEPTH.
 void build_cwbvh(const BuildTriangle *tris, size_t count, int threads, BvhBuildResult &out, bool spatial_splits = true);
-void refit_cwbvh(const BuildTriangle *tris, size_t count, BvhBuildResult &bvh);
+void refit_cwbvh(const BuildTriangle *tris, size_t count, BvhBuildResult &bvh, const uint8_t *tri_moved = nullptr);
 
 constexpr int TRAVERSAL_STACK = 96; // ints per thread in the kernels; builder keeps 3*depth+1 below this
 

@@ -150,6 +150,9 @@ struct rfwb200_context
 	DevBuf d_verts, d_indices, d_mesh_tris, d_instances, d_flat_inst, d_tri_order, d_parent_slot, d_arrivals;
 	std::vector<uint32_t> mesh_vert_off, mesh_tri_off; // arena offsets per mesh
 	std::vector<uint8_t> mesh_dirty;				   // host copy newer than the arena
+	std::vector<uint8_t> inst_moved;				   // instance (or its mesh) changed since the last build: refits bound it whole
+	std::vector<uint8_t> tri_moved;					   // the same per flattened triangle (host refit)
+	DevBuf d_ref_boxes;
 	bool arena_valid = false;
 	bool device_geometry = true; // setting "refit" = device | host
 	GeometryView geo{};
@@ -441,6 +444,16 @@ int pack_nodes(Ctx *c)
 	return RFWB200_OK;
 }
 
+// instances whose triangles no longer are where the builder saw them: refits bound those triangles whole, all others keep
+// the builder's (spatially split) reference boxes
+void mark_mesh_moved(Ctx *c, size_t mesh_index)
+{
+	c->inst_moved.resize(c->instances.size(), 0);
+	for (size_t ii = 0; ii < c->instances.size(); ii++)
+		if (c->instances[ii].mesh == int(mesh_index))
+			c->inst_moved[ii] = 1;
+}
+
 // ---- device geometry path (geometry.cu) --------------------------------------------------------------------------------
 int upload_mesh_to_arena(Ctx *c, size_t mi)
 {
@@ -512,6 +525,7 @@ int upload_instances(Ctx *c, bool with_flat_inst)
 		d.det_eps = 1e-6f * std::fabs(det);
 		d.vert_off = c->mesh_vert_off[in.mesh], d.tri_off = c->mesh_tri_off[in.mesh];
 		d.tri_count = uint32_t(c->meshes[in.mesh].triangles.size());
+		d.moved = (ii < c->inst_moved.size() && c->inst_moved[ii]) ? 1u : 0u;
 		if (with_flat_inst)
 			flat_inst.insert(flat_inst.end(), d.tri_count, uint32_t(ii));
 		flat += d.tri_count;
@@ -539,6 +553,7 @@ void bind_geometry_views(Ctx *c, size_t nn, size_t nr)
 	g.flat_count = uint32_t(c->flat_tri_count);
 	g.nodes = c->d_nodes.as<BvhNode4>(), g.tri_order = c->d_tri_order.as<uint32_t>();
 	g.parent_slot = c->d_parent_slot.as<uint32_t>(), g.arrivals = c->d_arrivals.as<uint32_t>();
+	g.ref_boxes = (c->bvh.ref_boxes.size() == 6 * nr && nr > 0) ? c->d_ref_boxes.as<float>() : nullptr;
 	g.node_count = uint32_t(nn), g.ref_count = uint32_t(nr);
 	g.out_tris = c->d_tris.as<TriRec>(), g.out_shade = c->d_shade_tris.as<ShadeTri>();
 	c->scene.nodes = c->d_nodes.as<BvhNode4>(), c->scene.tris = c->d_tris.as<TriRec>();
@@ -597,6 +612,12 @@ int upload_topology(Ctx *c)
 		CK(cudaMemcpyAsync(c->d_tri_order.ptr, c->bvh.tri_order.data(), nr * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
 	CK(cudaMemcpyAsync(c->d_parent_slot.ptr, parent_slot.data(), parent_slot.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
 					   c->stream));
+	if (c->bvh.ref_boxes.size() == 6 * nr && nr > 0)
+	{
+		CK(c->d_ref_boxes.reserve(c->bvh.ref_boxes.size() * sizeof(float)));
+		CK(cudaMemcpyAsync(c->d_ref_boxes.ptr, c->bvh.ref_boxes.data(), c->bvh.ref_boxes.size() * sizeof(float), cudaMemcpyHostToDevice,
+						   c->stream));
+	}
 	CK(cudaStreamSynchronize(c->stream));
 	bind_geometry_views(c, nn, nr);
 	return RFWB200_OK;
@@ -973,6 +994,8 @@ extern "C"
 		in.mesh = int(mesh_index);
 		memcpy(in.transform, transform, sizeof(float) * 16);
 		memcpy(in.normal, normal_matrix, sizeof(float) * 9);
+		c->inst_moved.resize(c->instances.size(), 0);
+		c->inst_moved[i] = 1;
 		c->geometry_dirty = true;
 		return RFWB200_OK;
 	}
@@ -1022,6 +1045,11 @@ extern "C"
 		}
 		const bool can_refit = !c->topology_dirty && layout == c->built_layout && (!c->bvh.nodes.empty() || !c->bvh.cw_nodes.empty() || c->device_built) && c->built_tri_count == total;
 		const bool device = c->device_geometry && total > 0;
+		c->mesh_dirty.resize(c->meshes.size(), 1);
+		if (can_refit)
+			for (size_t mi = 0; mi < c->meshes.size(); mi++)
+				if (c->mesh_dirty[mi])
+					mark_mesh_moved(c, mi);
 		if (device && can_refit && c->arena_valid && !c->wide8)
 		{
 			// Device refit: only the meshes that changed and the 128-B instance records cross PCIe; the boxes, the
@@ -1048,6 +1076,7 @@ extern "C"
 			REQUIRE(total < (1u << 30), "more than 2^30 triangles");
 			c->flat_tri_count = total;
 			c->bvh = BvhBuildResult(); // no host copy of this tree
+			c->inst_moved.assign(c->instances.size(), 0);
 			if (int r = upload_arena(c))
 				return r;
 			if (int r = upload_instances(c, true))
@@ -1098,10 +1127,14 @@ extern "C"
 		const auto t0 = std::chrono::steady_clock::now();
 		if (can_refit && c->bvh.wide8 == c->wide8)
 		{
+			c->tri_moved.clear();
+			c->inst_moved.resize(c->instances.size(), 0);
+			for (size_t ii = 0; ii < c->instances.size(); ii++)
+				c->tri_moved.insert(c->tri_moved.end(), layout[ii].second, c->inst_moved[ii]);
 			if (c->wide8)
-				refit_cwbvh(c->build_tris.data(), c->build_tris.size(), c->bvh);
+				refit_cwbvh(c->build_tris.data(), c->build_tris.size(), c->bvh, c->tri_moved.data());
 			else
-				refit_bvh4(c->build_tris.data(), c->build_tris.size(), c->bvh);
+				refit_bvh4(c->build_tris.data(), c->build_tris.size(), c->bvh, c->tri_moved.data());
 			c->refits++;
 		}
 		else
@@ -1112,6 +1145,7 @@ extern "C"
 			else
 				build_bvh4(c->build_tris.data(), c->build_tris.size(), threads, c->bvh, c->spatial_splits);
 			c->built_tri_count = c->build_tris.size();
+			c->inst_moved.assign(c->instances.size(), 0);
 			c->builds++;
 		}
 		c->bvh.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -1214,6 +1248,7 @@ extern "C"
 		CK(launch_skin(v, c->stream));
 		c->launches += 2;
 		sk.device_newer = true;
+		mark_mesh_moved(c, mesh_index);
 		c->geometry_dirty = true;
 		return RFWB200_OK;
 	}

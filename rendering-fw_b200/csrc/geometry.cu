@@ -117,6 +117,13 @@ __global__ void __launch_bounds__(256) k_refit(const GeometryView g)
 			rec[2] = make_float4(v2.z - v0.z, __uint_as_float(src), in.det_eps, 0.0f);
 			float lo[3] = {fminf(fminf(v0.x, v1.x), v2.x), fminf(fminf(v0.y, v1.y), v2.y), fminf(fminf(v0.z, v1.z), v2.z)};
 			float hi[3] = {fmaxf(fmaxf(v0.x, v1.x), v2.x), fmaxf(fmaxf(v0.y, v1.y), v2.y), fmaxf(fmaxf(v0.z, v1.z), v2.z)};
+			if (g.ref_boxes != nullptr && in.moved == 0u)
+			{
+				// a triangle that has not moved since the build keeps the builder's box of this reference (clipped by
+				// spatial splits); refitting it from the whole triangle would undo the splits (bvh_build.cpp refit_ref_box)
+				const float *rb = g.ref_boxes + size_t(i) * 6;
+				lo[0] = rb[0], lo[1] = rb[1], lo[2] = rb[2], hi[0] = rb[3], hi[1] = rb[4], hi[2] = rb[5];
+			}
 #pragma unroll
 			for (int a = 0; a < 3; a++)
 			{

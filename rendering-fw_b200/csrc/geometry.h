@@ -17,7 +17,8 @@ struct alignas(16) DeviceInstance
 	uint32_t tri_off;	 // first triangle of the mesh in GeometryView::mesh_tris / indices
 	uint32_t flat_off;	 // first flattened triangle of this instance
 	uint32_t tri_count;
-	uint32_t pad[2];
+	uint32_t moved; // 1: transform or mesh changed since the last build (refit bounds its triangles whole)
+	uint32_t pad;
 };
 static_assert(sizeof(DeviceInstance) == 128, "");
 
@@ -34,6 +35,7 @@ struct GeometryView
 	BvhNode4 *nodes;
 	const uint32_t *tri_order;	 // leaf-ordered reference -> flattened triangle
 	const uint32_t *parent_slot; // (parent << 2) | slot, root 0xffffffff
+	const float *ref_boxes;		 // 6 floats per leaf reference: the builder's box (null: bound every triangle whole)
 	uint32_t *arrivals;			 // one counter per node (zeroed by launch_refit)
 	uint32_t node_count, ref_count;
 	int write_boxes; // 1 = refit (recompute every box), 0 = only the records (fresh build: keep the builder's boxes)
