@@ -263,6 +263,13 @@ RFWB200_API int rfwb200_set_mesh_skin(rfwb200_context *ctx, size_t mesh_index, c
 									  size_t vertex_count);
 RFWB200_API int rfwb200_set_mesh_pose(rfwb200_context *ctx, size_t mesh_index, const float *joint_matrices,
 									  size_t joint_count);
+/* Morph targets on the GPU, replacing SceneMesh::set_pose(weights) (gltf/mesh.cpp:126-148) + set_mesh: poses are
+ * (target_count + 1) arrays of vertex_count vec4 (pose 0 = base; SceneMesh::poses[].positions / .normals, w ignored);
+ * vertex = (pose0, 1) + sum_j w_j (pose_j, 0), normal likewise without renormalisation, then update_triangles. */
+RFWB200_API int rfwb200_set_mesh_morph_targets(rfwb200_context *ctx, size_t mesh_index, const float *pose_positions,
+											   const float *pose_normals, size_t target_count, size_t vertex_count);
+RFWB200_API int rfwb200_set_mesh_morph_weights(rfwb200_context *ctx, size_t mesh_index, const float *weights,
+											   size_t weight_count);
 RFWB200_API int rfwb200_get_geometry_stats(rfwb200_context *ctx, rfwb200_geometry_stats *out);
 
 /* replaces RenderContext::set_setting (context.h:107). Keys: "spp" (samples per render_frame,

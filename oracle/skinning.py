@@ -3,6 +3,7 @@ product path; only tests/, __graft_entry__.smoke() and bench.py's cpu legs may u
 
 Follows RFW/system/src/rfw/geometry/gltf/mesh.cpp:
   * set_pose(skin)      :18-48   S = sum_k w_k * J[j_k];  v' = S * v;  n' = normalize((n^T * S^-1).xyz)
+  * set_pose(weights)   :126-148 morph targets: v = pose0 + sum_j w_j pose_j (normals likewise, not renormalised)
   * update_triangles()  :428-449 vertex0..2 / vN0..2 from the indexed vertices, N = normalize(cross(v1-v0, v2-v0))
   * joint matrices      node.cpp:97-104  J[j] = inverse(meshNode.combined) * jointNode.combined * inverseBind[j]
 Parity of this restatement is unpinned (the reference has no tests or vectors for it); the GPU kernels
@@ -37,6 +38,18 @@ def set_pose(base_vertices, base_normals, joints, weights, joint_matrices):
     # the reference divides the whole vec4 by ITS length (w included); with an affine S and n.w = 0 the w term is 0
     r = r / np.linalg.norm(np.einsum("nj,nji->ni", n4, Sinv), axis=1, keepdims=True)
     return out_v, r.astype(np.float32)
+
+
+def set_pose_morph(pose_positions, pose_normals, weights):
+    """mesh.cpp:126-148: poses (n_targets + 1, nv, 3); -> (vertices (nv,4) with w = 1, normals (nv,3), NOT renormalised)"""
+    P, N = np.asarray(pose_positions, np.float32)[..., :3], np.asarray(pose_normals, np.float32)[..., :3]
+    w = np.asarray(weights, np.float32)
+    assert len(w) == len(P) - 1
+    v, n = P[0].copy(), N[0].copy()
+    for j in range(len(w)):
+        v = v + w[j] * P[j + 1]
+        n = n + w[j] * N[j + 1]
+    return np.concatenate([v, np.ones((len(v), 1), np.float32)], 1).astype(np.float32), n.astype(np.float32)
 
 
 def update_triangles(triangles, vertices, normals, indices):

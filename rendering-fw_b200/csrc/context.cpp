@@ -161,6 +161,9 @@ struct rfwb200_context
 		DevBuf base_v, base_n, joints, weights, matrices, normals;
 		size_t vertex_count = 0;
 		uint32_t max_joint = 0;
+		DevBuf pose_p, pose_n, morph_w; // morph targets: (n_targets + 1) poses of vertex_count float4 each
+		size_t n_targets = 0;			// 0: no morph targets registered
+		bool has_skin = false;
 		bool device_newer = false; // the arena holds a pose the host copy of the mesh does not
 	};
 	std::vector<std::unique_ptr<Skin>> skins; // per mesh index, null when the mesh has no skin
@@ -196,7 +199,7 @@ struct rfwb200_context
 	cudaEvent_t ev_fork = nullptr;
 
 	// ---- settings / state ------------------------------------------------------------------------------
-	RenderSettings rs{2, 10.0f, 1e-5f, 1, 0, 16, nullptr, -1, 9}; // trace_variant 9: packed nodes + unsorted connect rays (DESIGN.md sweep) // smem_nodes 0: measured fastest on B200 (DESIGN.md "staging")
+	RenderSettings rs{2, 10.0f, 1e-5f, 1, 0, 16, nullptr, -1, 9, 5}; // bounces: packed nodes + unsorted connect rays; camera rays: fp32 nodes (DESIGN.md sweep) // smem_nodes 0: measured fastest on B200 (DESIGN.md "staging")
 	int spp = 1;
 	bool mode_pt = true;
 	LaunchDims dims{};
@@ -1171,6 +1174,7 @@ extern "C"
 		{
 			REQUIRE(!c->wide8, "bvh=8 needs refit=device and a non-empty scene");
 			c->arena_valid = false;
+			std::fill(c->mesh_dirty.begin(), c->mesh_dirty.end(), uint8_t(0)); // consumed by the host flatten above
 			c->scene.cw_nodes = nullptr, c->scene.cw_node_count = 0;
 			if (int r = upload_bvh(c, det_eps))
 				return r;
@@ -1214,14 +1218,72 @@ extern "C"
 		CK(cudaMemcpy(sk->base_n.ptr, base_normals, vertex_count * 16, cudaMemcpyHostToDevice));
 		CK(cudaMemcpy(sk->joints.ptr, joints, vertex_count * 16, cudaMemcpyHostToDevice));
 		CK(cudaMemcpy(sk->weights.ptr, weights, vertex_count * 16, cudaMemcpyHostToDevice));
+		sk->has_skin = true;
 		c->skins[mesh_index] = std::move(sk);
+		return RFWB200_OK;
+	}
+
+	int rfwb200_set_mesh_morph_targets(rfwb200_context *c, size_t mesh_index, const float *pose_positions, const float *pose_normals,
+									   size_t target_count, size_t vertex_count)
+	{
+		REQUIRE(c && pose_positions && pose_normals && target_count >= 1, "bad morph targets");
+		REQUIRE(mesh_index < c->meshes.size(), "morph targets reference a mesh that was not set");
+		REQUIRE(c->meshes[mesh_index].vertices.size() == vertex_count * 4, "morph target and mesh vertex counts differ");
+		if (int r = ensure_device(c))
+			return r;
+		if (c->skins.size() <= mesh_index)
+			c->skins.resize(mesh_index + 1);
+		auto sk = std::make_unique<Ctx::Skin>();
+		sk->vertex_count = vertex_count, sk->n_targets = target_count;
+		const size_t bytes = (target_count + 1) * vertex_count * 16;
+		CK(sk->pose_p.reserve(bytes));
+		CK(sk->pose_n.reserve(bytes));
+		CK(sk->morph_w.reserve(target_count * sizeof(float)));
+		CK(sk->normals.reserve(std::max<size_t>(vertex_count, 1) * 16));
+		CK(cudaMemcpy(sk->pose_p.ptr, pose_positions, bytes, cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(sk->pose_n.ptr, pose_normals, bytes, cudaMemcpyHostToDevice));
+		c->skins[mesh_index] = std::move(sk);
+		return RFWB200_OK;
+	}
+
+	int rfwb200_set_mesh_morph_weights(rfwb200_context *c, size_t mesh_index, const float *weights, size_t weight_count)
+	{
+		REQUIRE(c && weights, "bad morph weights");
+		REQUIRE(mesh_index < c->skins.size() && c->skins[mesh_index] && c->skins[mesh_index]->n_targets > 0,
+				"mesh has no morph targets (rfwb200_set_mesh_morph_targets)");
+		if (int r = ensure_device(c))
+			return r;
+		Ctx::Skin &sk = *c->skins[mesh_index];
+		REQUIRE(weight_count == sk.n_targets, "one weight per morph target (gltf/mesh.cpp:128)");
+		if (!c->device_geometry)
+			return set_error(RFWB200_ERR_STATE, "device morphing needs setting refit=device");
+		if (!c->arena_valid || c->topology_dirty)
+			return set_error(RFWB200_ERR_STATE, "call rfwb200_update once after set_mesh before posing a mesh");
+		if (c->mesh_dirty[mesh_index])
+			if (int r = upload_mesh_to_arena(c, mesh_index))
+				return r;
+		const HostMesh &hm = c->meshes[mesh_index];
+		CK(cudaMemcpyAsync(sk.morph_w.ptr, weights, weight_count * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+		MorphView v{};
+		v.pose_positions = sk.pose_p.as<float4>(), v.pose_normals = sk.pose_n.as<float4>();
+		v.weights = sk.morph_w.as<float>(), v.n_weights = uint32_t(weight_count);
+		v.indices = c->d_indices.as<uint32_t>() + size_t(c->mesh_tri_off[mesh_index]) * 3;
+		v.out_vertices = c->d_verts.as<float4>() + c->mesh_vert_off[mesh_index];
+		v.out_normals = sk.normals.as<float4>();
+		v.mesh_tris = static_cast<char *>(c->d_mesh_tris.ptr) + size_t(c->mesh_tri_off[mesh_index]) * sizeof(rfwb200_triangle);
+		v.vertex_count = uint32_t(sk.vertex_count), v.triangle_count = uint32_t(hm.triangles.size());
+		CK(launch_morph(v, c->stream));
+		c->launches += 2;
+		sk.device_newer = true;
+		mark_mesh_moved(c, mesh_index);
+		c->geometry_dirty = true;
 		return RFWB200_OK;
 	}
 
 	int rfwb200_set_mesh_pose(rfwb200_context *c, size_t mesh_index, const float *joint_matrices, size_t joint_count)
 	{
 		REQUIRE(c && joint_matrices && joint_count > 0, "bad pose");
-		REQUIRE(mesh_index < c->skins.size() && c->skins[mesh_index], "mesh has no skin (rfwb200_set_mesh_skin)");
+		REQUIRE(mesh_index < c->skins.size() && c->skins[mesh_index] && c->skins[mesh_index]->has_skin, "mesh has no skin (rfwb200_set_mesh_skin)");
 		if (int r = ensure_device(c))
 			return r;
 		Ctx::Skin &sk = *c->skins[mesh_index];
@@ -1356,8 +1418,14 @@ extern "C"
 		else if (k == "trace_variant")
 		{
 			const int n = atoi(v.c_str());
-			REQUIRE(n >= 0 && n <= 10, "trace_variant must be in [0, 10]");
-			c->rs.trace_variant = n;
+			REQUIRE(n >= 0 && n <= 12, "trace_variant must be in [0, 12]");
+			c->rs.trace_variant = c->rs.primary_variant = n; // one value for both kinds of launch; primary_variant overrides
+		}
+		else if (k == "primary_variant")
+		{
+			const int n = atoi(v.c_str());
+			REQUIRE(n >= 0 && n <= 12, "primary_variant must be in [0, 12]");
+			c->rs.primary_variant = n;
 		}
 		else if (k == "refit")
 		{

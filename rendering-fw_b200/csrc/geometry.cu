@@ -327,6 +327,25 @@ __global__ void __launch_bounds__(128) k_skin_vertices(const SkinView s)
 	s.out_normals[i] = make_float4(nx, ny, nz, 0.0f);
 }
 
+// morph targets — gltf/mesh.cpp:126-148: vertex = (pose0, 1) + sum_j w_j * (pose_j, 0), normal = pose0.n + sum_j w_j * pose_j.n
+__global__ void __launch_bounds__(128) k_morph_vertices(const MorphView m)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= m.vertex_count)
+		return;
+	float4 p = m.pose_positions[i], n = m.pose_normals[i];
+	p.w = 1.0f, n.w = 0.0f;
+	for (uint32_t j = 0; j < m.n_weights; j++)
+	{
+		const float w = m.weights[j];
+		const float4 dp = m.pose_positions[size_t(j + 1) * m.vertex_count + i], dn = m.pose_normals[size_t(j + 1) * m.vertex_count + i];
+		p.x += w * dp.x, p.y += w * dp.y, p.z += w * dp.z;
+		n.x += w * dn.x, n.y += w * dn.y, n.z += w * dn.z;
+	}
+	m.out_vertices[i] = p;
+	m.out_normals[i] = n;
+}
+
 // mesh.cpp:428-449 (indexed) — vertex0..2, vN0..2 and the geometric normal of every triangle record
 __global__ void __launch_bounds__(128) k_update_triangles(const SkinView s)
 {
@@ -611,6 +630,20 @@ cudaError_t launch_flatten_shade(const GeometryView &g, cudaStream_t stream)
 	if (g.flat_count == 0)
 		return cudaSuccess;
 	k_flatten_shade<<<(g.flat_count + 255u) / 256u, 256, 0, stream>>>(g);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_morph(const MorphView &m, cudaStream_t stream)
+{
+	if (m.vertex_count)
+		k_morph_vertices<<<(m.vertex_count + 127u) / 128u, 128, 0, stream>>>(m);
+	if (m.triangle_count)
+	{
+		SkinView s{};
+		s.indices = m.indices, s.out_vertices = m.out_vertices, s.out_normals = m.out_normals, s.mesh_tris = m.mesh_tris;
+		s.vertex_count = m.vertex_count, s.triangle_count = m.triangle_count;
+		k_update_triangles<<<(m.triangle_count + 127u) / 128u, 128, 0, stream>>>(s);
+	}
 	return cudaGetLastError();
 }
 

@@ -67,4 +67,18 @@ cudaError_t launch_records(const GeometryView &g, cudaStream_t stream); // TriRe
 cudaError_t launch_flatten_shade(const GeometryView &g, cudaStream_t stream);
 cudaError_t launch_skin(const SkinView &s, cudaStream_t stream);
 
+// morph targets (gltf/mesh.cpp:126-148): v = pose0 + sum_j w_j * pose_j, n likewise (not renormalised), then triangle update
+struct MorphView
+{
+	const float4 *pose_positions; // [(n_weights + 1)][vertex_count], xyz
+	const float4 *pose_normals;	  // [(n_weights + 1)][vertex_count], xyz
+	const float *weights;		  // [n_weights]
+	uint32_t n_weights;
+	const uint32_t *indices;
+	float4 *out_vertices, *out_normals;
+	void *mesh_tris;
+	uint32_t vertex_count, triangle_count;
+};
+cudaError_t launch_morph(const MorphView &m, cudaStream_t stream);
+
 } // namespace rfwb200

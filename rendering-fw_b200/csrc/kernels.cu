@@ -697,7 +697,7 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 						CHILD_N(2, z)
 						CHILD_N(3, w)
 					}
-					if (LEAN == 1 || (LEAN == 2 && shadow))
+					if (LEAN == 1 || ((LEAN == 2 || LEAN == 3) && shadow))
 					{
 						const uint32_t km = min(min(key0, key1), min(key2, key3));
 						if (nh == 0)
@@ -715,6 +715,33 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 							if (key3 < 0x7f000000u && key3 != km)
 								stack[sp++] = n.child.w;
 						}
+					}
+					else if (LEAN >= 3)
+					{
+						// the same order as the key-only network below, but the child words travel with their keys (no
+						// slot -> child selects afterwards) and the pushes are predicated stores instead of nested branches
+						int c0 = n.child.x, c1 = n.child.y, c2 = n.child.z, c3 = n.child.w;
+#define CSWAP2(KA, KB, CA, CB)                                                                                          \
+	{                                                                                                                   \
+		const bool sw_ = KA > KB;                                                                                       \
+		const uint32_t ka_ = sw_ ? KB : KA, kb_ = sw_ ? KA : KB;                                                        \
+		const int ca_ = sw_ ? CB : CA, cb_ = sw_ ? CA : CB;                                                             \
+		KA = ka_, KB = kb_, CA = ca_, CB = cb_;                                                                         \
+	}
+						CSWAP2(key0, key1, c0, c1)
+						CSWAP2(key2, key3, c2, c3)
+						CSWAP2(key0, key2, c0, c2)
+						CSWAP2(key1, key3, c1, c3)
+						CSWAP2(key1, key2, c1, c2)
+#undef CSWAP2
+						if (nh > 3)
+							stack[sp++] = c3;
+						if (nh > 2)
+							stack[sp++] = c2;
+						if (nh > 1)
+							stack[sp++] = c1;
+						cur = nh > 0 ? c0 : stack[sp - 1];
+						sp -= nh > 0 ? 0 : 1;
 					}
 					else if (nh == 0)
 						cur = stack[--sp];
@@ -2314,6 +2341,8 @@ cudaError_t configure_launches(const RenderSettings &rs, uint32_t node_count, La
 									(const void *)k_wavefront_trace<true, 1, 0, true>,	 (const void *)k_wavefront_trace<false, 1, 0, true>,
 									(const void *)k_wavefront_trace<true, 1, 2, true>,	 (const void *)k_wavefront_trace<false, 1, 2, true>,
 									(const void *)k_wavefront_trace<true, 1, 1, true>,	 (const void *)k_wavefront_trace<false, 1, 1, true>,
+									(const void *)k_wavefront_trace<true, 1, 3, true>,	 (const void *)k_wavefront_trace<false, 1, 3, true>,
+									(const void *)k_wavefront_trace<true, 1, 4, true>,	 (const void *)k_wavefront_trace<false, 1, 4, true>,
 									(const void *)k_wavefront_trace_cw<true>,			 (const void *)k_wavefront_trace_cw<false>};
 		for (const void *k : l1_kernels)
 		{
@@ -2347,7 +2376,7 @@ cudaError_t launch_primary(const SceneView &sc, const ShardView &sh, const Wavef
 		k_wavefront_trace_cw<true><<<dims.trace_grid, dims.trace_block, 0, stream>>>(sc, sh, wf, rs, sample_in_frame, 0u);
 		return cudaGetLastError();
 	}
-	switch (rs.smem_nodes > 0 ? 0 : rs.trace_variant) // the staged prefix only exists in variant 0
+	switch (rs.smem_nodes > 0 ? 0 : rs.primary_variant) // the staged prefix only exists in variant 0
 	{
 #define RFW_TRACE_CASE(V, LQ, LEAN, PACKED)                                                                                     \
 	case V:                                                                                                             \
@@ -2360,6 +2389,8 @@ cudaError_t launch_primary(const SceneView &sc, const ShardView &sh, const Wavef
 		RFW_TRACE_CASE(8, 1, 0, true)
 		RFW_TRACE_CASE(9, 1, 2, true)
 		RFW_TRACE_CASE(10, 1, 1, true)
+		RFW_TRACE_CASE(11, 1, 3, true)
+		RFW_TRACE_CASE(12, 1, 4, true)
 	default:
 		RFW_TRACE_CASE(0, 1, 0, false)
 #undef RFW_TRACE_CASE
@@ -2387,6 +2418,8 @@ cudaError_t launch_trace(const SceneView &sc, const ShardView &sh, const Wavefro
 		RFW_TRACE_CASE(8, 1, 0, true)
 		RFW_TRACE_CASE(9, 1, 2, true)
 		RFW_TRACE_CASE(10, 1, 1, true)
+		RFW_TRACE_CASE(11, 1, 3, true)
+		RFW_TRACE_CASE(12, 1, 4, true)
 	default:
 		RFW_TRACE_CASE(0, 1, 0, false)
 #undef RFW_TRACE_CASE

@@ -400,6 +400,22 @@ class RenderContext:
         self._check(self.L.fn("set_mesh_pose", C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t])(
             self._h, mesh_index, cm.ctypes.data, len(cm)))
 
+    def set_mesh_morph_targets(self, mesh_index: int, pose_positions, pose_normals):
+        """poses: (n_targets + 1, nv, 3|4); pose 0 is the base (SceneMesh::poses, gltf/mesh.h)."""
+        def as4(a):
+            a = np.asarray(a, np.float32)
+            out = np.zeros(a.shape[:2] + (4,), np.float32)
+            out[..., :3] = a[..., :3]
+            return np.ascontiguousarray(out)
+        p, n = as4(pose_positions), as4(pose_normals)
+        self._check(self.L.fn("set_mesh_morph_targets", C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t])(
+            self._h, mesh_index, p.ctypes.data, n.ctypes.data, p.shape[0] - 1, p.shape[1]))
+
+    def set_mesh_morph_weights(self, mesh_index: int, weights):
+        w = _f32(weights, (-1,))
+        self._check(self.L.fn("set_mesh_morph_weights", C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t])(
+            self._h, mesh_index, w.ctypes.data, len(w)))
+
     def get_geometry_stats(self) -> GeometryStats:
         g = GeometryStats()
         self._check(self.L.fn("get_geometry_stats", C.c_int, [C.c_void_p, C.c_void_p])(self._h, C.byref(g)))

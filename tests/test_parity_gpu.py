@@ -498,6 +498,48 @@ def test_device_skinning_and_refit_against_the_cpu_restatement(product_lib, orac
     _check_hits(g, o, origins, dirs, g.trace_closest(origins, dirs), o.trace_closest(origins, dirs))
 
 
+def test_device_morph_targets_against_the_cpu_restatement(product_lib, oracle_lib):
+    """SceneMesh::set_pose(weights) (gltf/mesh.cpp:126-148) as a kernel: two morph targets on the tube"""
+    from oracle import skinning as K
+
+    W, H = 128, 96
+    sc, sk = S.skinned_tube()
+    m = sc.meshes[sk.mesh_index]
+    base_p, base_n = sk.base_vertices[:, :3], sk.base_normals
+    y = base_p[:, 1:2]
+    bulge = np.concatenate([base_p[:, 0:1] * np.sin(y * 2.0), np.zeros_like(y), base_p[:, 2:3] * np.sin(y * 2.0)], 1).astype(np.float32)
+    lean = np.concatenate([0.3 * y * y, np.zeros_like(y), -0.1 * y], 1).astype(np.float32)
+    dn = np.zeros_like(base_n)
+    dn[:, 1] = 0.2
+    poses_p, poses_n = np.stack([base_p, bulge, lean]), np.stack([base_n, dn, -dn])
+    g, o = R.RenderContext(product_lib), R.RenderContext(oracle_lib)
+    S.upload(g, sc, W, H)
+    S.upload(o, S.skinned_tube()[0], W, H)
+    g.set_mesh_morph_targets(sk.mesh_index, poses_p, poses_n)
+    cam = sc.camera(W, H)
+    inst = [i for i, (mi, _) in enumerate(sc.instances) if mi == sk.mesh_index][0]
+    for n_pose, w in enumerate(([0.0, 0.0], [0.7, 0.2], [-0.3, 1.0])):
+        g.set_mesh_morph_weights(sk.mesh_index, w)
+        g.update()
+        st = g.get_geometry_stats()
+        assert (st.on_device, st.was_refit, st.refits) == (1, 1, n_pose + 1)
+        v, n = K.set_pose_morph(poses_p, poses_n, w)
+        tris = K.update_triangles(m.triangles, v, n, m.indices)
+        shade = g.debug_read_scene("shade")
+        mine = shade[shade["inst_id"] == inst]
+        mine = mine[np.argsort(mine["prim_id"])]
+        NM = np.linalg.inv(sc.instances[inst][1][:3, :3]).T.astype(np.float32)
+        assert np.abs(mine["n0"] - tris["vN0"] @ NM.T).max() < 1e-4
+        o.set_mesh(sk.mesh_index, v, tris, m.indices)
+        o.update()
+        origins, dirs = o.generate_primary(cam, 0)
+        _check_hits(g, o, origins, dirs, g.trace_closest(origins, dirs), o.trace_closest(origins, dirs))
+    with pytest.raises(R.Rfwb200Error):
+        g.set_mesh_morph_weights(sk.mesh_index, [0.5])  # one weight per target
+    with pytest.raises(R.Rfwb200Error):
+        g.set_mesh_pose(sk.mesh_index, sk.joint_matrices(0))  # morph targets are not a skin
+
+
 def test_skinning_error_behaviour(product_lib):
     sc, sk = S.skinned_tube()
     ctx = R.RenderContext(product_lib)
