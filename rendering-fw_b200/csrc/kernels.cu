@@ -1285,7 +1285,10 @@ __device__ float BSDFPdf(const ShadingData &sd, V3 N, V3 wo, V3 wi) // disney.h:
 	return lerpf(brdfPdf, bsdfPdf, sd.transmission());
 }
 
-__device__ V3 BSDFEval(const ShadingData &sd, V3 N, V3 wo, V3 wi, float t, bool backfacing) // disney.h:104-185
+#ifndef RFW_BSDF_NOINLINE
+#define RFW_BSDF_NOINLINE
+#endif
+RFW_BSDF_NOINLINE __device__ V3 BSDFEval(const ShadingData &sd, V3 N, V3 wo, V3 wi, float t, bool backfacing) // disney.h:104-185
 {
 	const float NDotL = dot(N, wi);
 	const float NDotV = dot(N, wo);
@@ -1440,7 +1443,10 @@ __device__ float4 FetchTexel(const SceneView &sc, float tcx, float tcy, int o, i
 	return make_float4(p0.x * w0 + p1.x * w1 + p2.x * w2 + p3.x * w3, p0.y * w0 + p1.y * w1 + p2.y * w2 + p3.y * w3,
 					   p0.z * w0 + p1.z * w1 + p2.z * w2 + p3.z * w3, p0.w * w0 + p1.w * w1 + p2.w * w2 + p3.w * w3);
 }
-__device__ float4 FetchTexelTrilinear(const SceneView &sc, float lambda, float tcx, float tcy, int offset, int width,
+#ifndef RFW_TEX_NOINLINE
+#define RFW_TEX_NOINLINE // experiment hook: -DRFW_TEX_NOINLINE=__noinline__ shrinks k_shade
+#endif
+RFW_TEX_NOINLINE __device__ float4 FetchTexelTrilinear(const SceneView &sc, float lambda, float tcx, float tcy, int offset, int width,
 									  int height)
 {
 	const int level0 = min(MIPLEVELCOUNT - 1, __float2int_rz(lambda));

@@ -182,7 +182,7 @@ template <typename T> constexpr T one_over_pi() { return T(0.3183098861837906715
 struct mat3
 {
 	vec3 c[3];
-	mat3() {}
+	mat3() = default;
 	mat3(float d) { c[0] = vec3(d, 0, 0), c[1] = vec3(0, d, 0), c[2] = vec3(0, 0, d); }
 	vec3 &operator[](int i) { return c[i]; }
 	const vec3 &operator[](int i) const { return c[i]; }
@@ -191,7 +191,7 @@ inline vec3 operator*(const mat3 &m, const vec3 &v) { return m.c[0] * v.x + m.c[
 struct mat4
 {
 	vec4 c[4];
-	mat4() {}
+	mat4() = default;
 	mat4(float d) { c[0] = vec4(d, 0, 0, 0), c[1] = vec4(0, d, 0, 0), c[2] = vec4(0, 0, d, 0), c[3] = vec4(0, 0, 0, d); }
 	vec4 &operator[](int i) { return c[i]; }
 	const vec4 &operator[](int i) const { return c[i]; }

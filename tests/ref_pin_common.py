@@ -9,7 +9,26 @@ import rfwb200 as R
 import scenes as S
 
 REF_LIB = R.REPO_DIR / "oracle" / "_ref" / "librfwref.so"
+REF_SKIN_LIB = R.REPO_DIR / "oracle" / "_ref" / "librfwref_skin.so"
 F, U, I, P = C.c_float, C.c_uint32, C.c_int, C.c_void_p
+
+
+def ref_set_pose(joint_matrices, base_vertices, base_normals, joints, weights):
+    """the reference's own SIMD math around the loop body of gltf/mesh.cpp:30-45 (oracle/ref_build/ref_skin_shim.cpp).
+    joint_matrices: (nj, 4, 4) in the mathematical (row, col) convention -> (vertices (nv,4), normals (nv,3))"""
+    lib = C.CDLL(str(REF_SKIN_LIB))
+    f = lib.rfwref_set_pose
+    f.restype, f.argtypes = None, [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 2
+    J = np.ascontiguousarray(np.transpose(np.asarray(joint_matrices, np.float32), (0, 2, 1)))  # column-major like glm
+    bv = np.ascontiguousarray(base_vertices, np.float32).reshape(-1, 4)
+    nv = len(bv)
+    bn = np.zeros((nv, 4), np.float32)
+    bn[:, :3] = np.asarray(base_normals, np.float32).reshape(nv, -1)[:, :3]
+    j = np.ascontiguousarray(joints, np.uint32).reshape(nv, 4)
+    w = np.ascontiguousarray(weights, np.float32).reshape(nv, 4)
+    ov, on = np.zeros((nv, 4), np.float32), np.zeros((nv, 3), np.float32)
+    f(J.ctypes.data, bv.ctypes.data, bn.ctypes.data, j.ctypes.data, w.ctypes.data, nv, ov.ctypes.data, on.ctypes.data)
+    return ov, on
 
 
 def fp(a):

@@ -498,6 +498,40 @@ def test_device_skinning_and_refit_against_the_cpu_restatement(product_lib, orac
     _check_hits(g, o, origins, dirs, g.trace_closest(origins, dirs), o.trace_closest(origins, dirs))
 
 
+def test_device_skinning_against_the_reference_math_vectors(product_lib):
+    """k_skin_vertices + k_update_triangles against tests/golden/ref_skin_vectors.npz — outputs of the REFERENCE's own SIMD
+    math (rfw/math.h compiled from /root/reference around the loop body of gltf/mesh.cpp:30-45): vertices within 2e-6
+    relative, normals (with the reference's 4-component-length division) within 2e-6 absolute."""
+    from pathlib import Path
+
+    G = dict(np.load(Path(__file__).resolve().parent / "golden" / "ref_skin_vectors.npz"))
+    nv = len(G["base_vertices"])
+    assert nv % 3 == 0
+    sc = S.Scene(name="skin-golden")
+    mat = S.add_material(sc, (0.7, 0.7, 0.7))
+    pos = G["base_vertices"][:, :3].reshape(-1, 3, 3)
+    tri = S.make_triangles(pos, G["base_normals"].reshape(-1, 3, 3), None, mat)
+    idx = np.arange(nv, dtype=np.uint32).reshape(-1, 3)
+    sc.meshes = [S.SceneMesh(G["base_vertices"].copy(), tri, idx)]
+    sc.instances = [(0, np.eye(4))]
+    g = R.RenderContext(product_lib)
+    S.upload(g, sc, 32, 32)
+    g.set_mesh_skin(0, G["base_vertices"], G["base_normals"], G["joints"], G["weights"])
+    for k in range(len(G["joint_matrices"])):
+        g.set_mesh_pose(0, G["joint_matrices"][k])
+        g.update()
+        shade, rec = g.debug_read_scene("shade"), g.debug_read_scene("tris")
+        order = np.argsort(shade["prim_id"])
+        rv, rn = G["ref_vertices"][k][:, :3].reshape(-1, 3, 3), G["ref_normals"][k].reshape(-1, 3, 3)
+        for key, col in (("n0", 0), ("n1", 1), ("n2", 2)):
+            assert np.abs(shade[key][order] - rn[:, col]).max() < 2e-6
+        prim = shade["prim_id"][rec["shade_idx"]]
+        scale = np.abs(rv).max()
+        assert np.abs(rec["p0"] - rv[prim, 0]).max() < 2e-6 * scale
+        assert np.abs(rec["e1"] - (rv[prim, 1] - rv[prim, 0])).max() < 4e-6 * scale
+        assert np.abs(rec["e2"] - (rv[prim, 2] - rv[prim, 0])).max() < 4e-6 * scale
+
+
 def test_device_morph_targets_against_the_cpu_restatement(product_lib, oracle_lib):
     """SceneMesh::set_pose(weights) (gltf/mesh.cpp:126-148) as a kernel: two morph targets on the tube"""
     from oracle import skinning as K

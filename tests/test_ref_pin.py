@@ -165,3 +165,26 @@ def test_stored_vectors_are_what_the_live_reference_produces():
     live = reference_soup_outputs(ref, soup_scene(), inp)
     for k, v in live.items():
         assert close(v, G[k], rtol=1e-6, atol=1e-7), k
+
+
+# ---- skinning: oracle/skinning.py pinned on the reference's own SIMD math (rfw/math.h) ------------------------------
+GS = dict(np.load(Path(__file__).resolve().parent / "golden" / "ref_skin_vectors.npz"))
+
+
+def test_skinning_restatement_matches_reference_math():
+    """vertices bit for bit, normals within 2 ulp — including the reference's division of the skinned normal by its
+    4-component length (math.h:797-806), which leaves normals shorter than 1 wherever the skin matrix translates."""
+    from oracle import skinning as K
+
+    from ref_pin_common import REF_SKIN_LIB, ref_set_pose
+
+    short = 1.0
+    for k in range(len(GS["joint_matrices"])):
+        v, n = K.set_pose(GS["base_vertices"], GS["base_normals"], GS["joints"], GS["weights"], GS["joint_matrices"][k])
+        assert np.array_equal(v, GS["ref_vertices"][k])
+        assert np.abs(n - GS["ref_normals"][k]).max() <= 3e-7
+        short = min(short, float(np.linalg.norm(GS["ref_normals"][k], axis=1).min()))
+        if REF_SKIN_LIB.exists():  # the stored vectors cannot go stale where the reference is present
+            rv, rn = ref_set_pose(GS["joint_matrices"][k], GS["base_vertices"], GS["base_normals"], GS["joints"], GS["weights"])
+            assert np.array_equal(rv, GS["ref_vertices"][k]) and np.array_equal(rn, GS["ref_normals"][k])
+    assert short < 0.97  # the quirk is real in the reference's output

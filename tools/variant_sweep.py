@@ -18,7 +18,8 @@ ap.add_argument("--frames", type=int, default=12)
 ap.add_argument("--spp", type=int, default=8)
 ap.add_argument("--width", type=int, default=1920)
 ap.add_argument("--height", type=int, default=1080)
-ap.add_argument("--variants", default="trace_variant=0;trace_variant=5;trace_variant=8;trace_variant=9;trace_variant=10")
+ap.add_argument("--variants", default="default;trace_variant=0;trace_variant=5;trace_variant=8;trace_variant=9;trace_variant=10;default",
+                help="';'-separated variants, each a ','-separated list of key=value settings ('default' = none)")
 a = ap.parse_args()
 
 sc = S.sponza_or_standin()
@@ -28,7 +29,7 @@ ctx.set_setting("spp", a.spp)
 cam = sc.camera(a.width, a.height)
 ref = None
 for var in a.variants.split(";"):
-    kvs = [kv.split("=") for kv in var.split(",") if kv]
+    kvs = [kv.split("=") for kv in var.split(",") if kv and kv != "default"]
     for k, v in kvs:
         ctx.set_setting(k, v)
     ctx.update()
@@ -51,4 +52,5 @@ for var in a.variants.split(";"):
                       "pixels_differing_from_first": float((np.abs(img - ref).max(axis=-1) > 0).mean()),
                       "mean": float(img[..., :3].mean()), "bvh": ctx.get_bvh_info()}), flush=True)
     for k, v in kvs:  # back to the defaults
-        ctx.set_setting(k, {"trace_variant": "0", "bvh": "4"}.get(k, v))
+        ctx.set_setting(k, {"trace_variant": "9", "primary_variant": "5", "bvh": "4"}.get(k, v))
+    ctx.set_setting("primary_variant", "5")
