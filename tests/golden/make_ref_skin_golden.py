@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Run seeded skinning inputs through the REFERENCE's own SIMD math (oracle/_ref/librfwref_skin.so = rfw/math.h compiled
+"""Run seeded skinning and camera inputs through the REFERENCE's own SIMD math (oracle/_ref/librfwref_skin.so = rfw/math.h compiled
 from /root/reference around the loop body of gltf/mesh.cpp:30-45) and commit inputs + reference outputs as
 tests/golden/ref_skin_vectors.npz.  tests/test_ref_pin.py checks oracle/skinning.py against them everywhere and against
 the live library where it exists.  Runs only in the build container (the reference does not travel)."""
@@ -12,7 +12,7 @@ REPO = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(REPO / "rendering-fw_b200" / "python"))
 sys.path.insert(0, str(REPO / "tests"))
 import scenes as S  # noqa: E402
-from ref_pin_common import ref_set_pose  # noqa: E402
+from ref_pin_common import ref_camera_get_view, ref_set_pose  # noqa: E402
 
 OUT = Path(__file__).resolve().parent / "ref_skin_vectors.npz"
 
@@ -32,6 +32,16 @@ def main():
         v, n = ref_set_pose(J, out["base_vertices"], out["base_normals"], out["joints"], out["weights"])
         mats.append(J), vs.append(v), ns.append(n)
     out["joint_matrices"], out["ref_vertices"], out["ref_normals"] = np.array(mats, np.float32), np.array(vs), np.array(ns)
+    # rfw::Camera::get_view (Camera.cpp:74-88) on seeded cameras: inputs (pos3, dir3, fov, focal, aperture, w, h) and the 14 outputs
+    cams, views = [], []
+    for _ in range(64):
+        pos = rng.uniform(-300, 300, 3).astype(np.float32)
+        d = rng.normal(size=3).astype(np.float32)
+        d /= np.float32(np.linalg.norm(d))
+        row = np.array([*pos, *d, rng.uniform(20, 100), rng.uniform(0.5, 20), rng.uniform(0, 0.1), rng.integers(16, 4000), rng.integers(16, 2200)], np.float32)
+        cams.append(row)
+        views.append(ref_camera_get_view(row[0:3], row[3:6], float(row[6]), float(row[7]), float(row[8]), int(row[9]), int(row[10])))
+    out["camera_in"], out["camera_view"] = np.array(cams, np.float32), np.array(views, np.float32)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, {k: v.shape for k, v in out.items()})
 

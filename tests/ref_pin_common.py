@@ -13,6 +13,20 @@ REF_SKIN_LIB = R.REPO_DIR / "oracle" / "_ref" / "librfwref_skin.so"
 F, U, I, P = C.c_float, C.c_uint32, C.c_int, C.c_void_p
 
 
+REF_CAMERA_LIB = R.REPO_DIR / "oracle" / "_ref" / "librfwref_camera.so"
+
+
+def ref_camera_get_view(position, direction, fov, focal_distance, aperture, width, height):
+    """rfw::Camera::get_view of the reference's own Camera.cpp (oracle/ref_build/ref_camera_shim.cpp) -> 14 floats"""
+    lib = C.CDLL(str(REF_CAMERA_LIB))
+    f = lib.rfwref_camera_get_view
+    f.restype, f.argtypes = None, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p]
+    p, d = np.ascontiguousarray(position, np.float32), np.ascontiguousarray(direction, np.float32)
+    out = np.zeros(14, np.float32)
+    f(p.ctypes.data, d.ctypes.data, fov, focal_distance, aperture, width, height, out.ctypes.data)
+    return out
+
+
 def ref_set_pose(joint_matrices, base_vertices, base_normals, joints, weights):
     """the reference's own SIMD math around the loop body of gltf/mesh.cpp:30-45 (oracle/ref_build/ref_skin_shim.cpp).
     joint_matrices: (nj, 4, 4) in the mathematical (row, col) convention -> (vertices (nv,4), normals (nv,3))"""

@@ -188,3 +188,18 @@ def test_skinning_restatement_matches_reference_math():
             rv, rn = ref_set_pose(GS["joint_matrices"][k], GS["base_vertices"], GS["base_normals"], GS["joints"], GS["weights"])
             assert np.array_equal(rv, GS["ref_vertices"][k]) and np.array_equal(rn, GS["ref_normals"][k])
     assert short < 0.97  # the quirk is real in the reference's output
+
+
+def test_camera_get_view_matches_reference_camera_cpp():
+    """rfwb200.Camera.get_view (the python caller-side mirror) against the reference's own Camera.cpp:74-88 compiled in place:
+    focal-plane corners and spread angle within 5e-6 relative (numpy evaluates the same float32 expression in another order)."""
+    from ref_pin_common import REF_CAMERA_LIB, ref_camera_get_view
+
+    for row, ref in zip(GS["camera_in"], GS["camera_view"]):
+        cam = R.Camera(row[0:3], row[3:6], float(row[6]), int(row[9]), int(row[10]), float(row[7]), float(row[8]))
+        v = cam.get_view()
+        mine = np.array(list(v.pos) + list(v.p1) + list(v.p2) + list(v.p3) + [v.aperture, v.spread_angle], np.float32)
+        assert np.all(np.abs(mine - ref) <= 5e-6 * np.maximum(1.0, np.abs(ref)))
+        if REF_CAMERA_LIB.exists():
+            live = ref_camera_get_view(row[0:3], np.asarray(cam.direction, np.float32), float(row[6]), float(row[7]), float(row[8]), int(row[9]), int(row[10]))
+            assert np.all(np.abs(live - ref) <= 1e-6 * np.maximum(1.0, np.abs(ref)))
