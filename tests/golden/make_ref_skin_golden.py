@@ -12,7 +12,7 @@ REPO = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(REPO / "rendering-fw_b200" / "python"))
 sys.path.insert(0, str(REPO / "tests"))
 import scenes as S  # noqa: E402
-from ref_pin_common import ref_camera_get_view, ref_set_pose  # noqa: E402
+from ref_pin_common import OracleScalar, emode_randoms, ref_camera_get_view, ref_generate_from_view, ref_set_pose  # noqa: E402
 
 OUT = Path(__file__).resolve().parent / "ref_skin_vectors.npz"
 
@@ -42,6 +42,14 @@ def main():
         cams.append(row)
         views.append(ref_camera_get_view(row[0:3], row[3:6], float(row[6]), float(row[7]), float(row[8]), int(row[9]), int(row[10])))
     out["camera_in"], out["camera_view"] = np.array(cams, np.float32), np.array(views, np.float32)
+    # Ray::generateFromView (EmbreeRT/src/Ray.cpp:16-47) for pixels of a 96x64 frame under the E-mode random contract
+    orc = OracleScalar()
+    W, H, sample = 96, 64, 3
+    view = views[0].copy()
+    view[12] = 0.05  # a visible aperture so the lens term matters
+    px = rng.choice(W * H, size=128, replace=False)
+    rays = [ref_generate_from_view(view, W, H, int(p % W), int(p // W), emode_randoms(orc.wang, int(p), sample)) for p in px]
+    out["ray_view"], out["ray_dims"], out["ray_pixels"], out["ray_out"] = view, np.array([W, H, sample], np.int32), px.astype(np.int32), np.array(rays, np.float32)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, {k: v.shape for k, v in out.items()})
 

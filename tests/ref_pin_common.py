@@ -27,6 +27,33 @@ def ref_camera_get_view(position, direction, fov, focal_distance, aperture, widt
     return out
 
 
+REF_RAY_LIB = R.REPO_DIR / "oracle" / "_ref" / "librfwref_ray.so"
+
+
+def ref_generate_from_view(view14, width, height, x, y, r):
+    """Ray::generateFromView of the reference (EmbreeRT/src/Ray.cpp:16-47, oracle/ref_build/ref_ray_shim.cpp) -> origin, direction"""
+    lib = C.CDLL(str(REF_RAY_LIB))
+    f = lib.rfwref_generate_from_view
+    f.restype, f.argtypes = None, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_float] * 4 + [C.c_void_p]
+    v = np.ascontiguousarray(view14, np.float32)
+    out = np.zeros(6, np.float32)
+    f(v.ctypes.data, width, height, x, y, float(r[0]), float(r[1]), float(r[2]), float(r[3]), out.ctypes.data)
+    return out
+
+
+def emode_randoms(wang, pixel, sample):
+    """the E-mode determinism contract: first four xor128 outputs with x seeded per (pixel, sample)"""
+    m = 0xFFFFFFFF
+    x, y, z, w = 123456789 ^ wang((pixel * 16789 + sample * 1791) & m), 362436069, 521288629, 88675123
+    out = []
+    for _ in range(4):
+        t = (x ^ (x << 11)) & m
+        x, y, z = y, z, w
+        w = (w ^ (w >> 19) ^ (t ^ (t >> 8))) & m
+        out.append(np.float32(w) * np.float32(2.3283064365387e-10))
+    return np.array(out, np.float32)
+
+
 def ref_set_pose(joint_matrices, base_vertices, base_normals, joints, weights):
     """the reference's own SIMD math around the loop body of gltf/mesh.cpp:30-45 (oracle/ref_build/ref_skin_shim.cpp).
     joint_matrices: (nj, 4, 4) in the mathematical (row, col) convention -> (vertices (nv,4), normals (nv,3))"""

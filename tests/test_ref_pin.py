@@ -203,3 +203,29 @@ def test_camera_get_view_matches_reference_camera_cpp():
         if REF_CAMERA_LIB.exists():
             live = ref_camera_get_view(row[0:3], np.asarray(cam.direction, np.float32), float(row[6]), float(row[7]), float(row[8]), int(row[9]), int(row[10]))
             assert np.all(np.abs(live - ref) <= 1e-6 * np.maximum(1.0, np.abs(ref)))
+
+
+def test_emode_generate_matches_reference_generate_from_view(oracle_lib):
+    """The oracle's E-mode camera rays against the reference's own Ray::generateFromView (EmbreeRT/src/Ray.cpp:16-47, compiled
+    from the reference tree) fed with the randoms of the E-mode determinism contract: origins within 1e-6, directions 2e-6."""
+    from ref_pin_common import REF_RAY_LIB, emode_randoms, ref_generate_from_view
+
+    W, H, sample = (int(v) for v in GS["ray_dims"])
+    view = R.CameraView()
+    v14 = GS["ray_view"]
+    for i in range(3):
+        view.pos[i], view.p1[i], view.p2[i], view.p3[i] = float(v14[i]), float(v14[3 + i]), float(v14[6 + i]), float(v14[9 + i])
+    view.aperture, view.spread_angle = float(v14[12]), float(v14[13])
+    o = R.RenderContext(oracle_lib)
+    S.upload(o, S.cornell_box(unit_scale=True), W, H)
+    o.set_setting("mode", "embree")
+    origins, dirs = o.generate_primary(view, sample)
+    px = GS["ray_pixels"]
+    assert np.abs(origins[px, :3] - GS["ray_out"][:, :3]).max() <= 1e-6 * max(1.0, float(np.abs(GS["ray_out"][:, :3]).max()))
+    assert np.abs(dirs[px, :3] - GS["ray_out"][:, 3:]).max() <= 2e-6
+    assert np.abs(origins[px, :3] - v14[:3]).max() > 1e-3  # the lens offset is exercised
+    if REF_RAY_LIB.exists():
+        orc = OracleScalar()
+        for p, ref in list(zip(px, GS["ray_out"]))[:16]:
+            live = ref_generate_from_view(v14, W, H, int(p % W), int(p // W), emode_randoms(orc.wang, int(p), sample))
+            assert np.array_equal(live, ref)
