@@ -33,8 +33,17 @@ constexpr int MAX_LEAF = 4; // 4-wide layout; the compressed 8-wide layout takes
 constexpr int MAX_DEPTH2 = 31;			// BVH2 depth bound => BVH4 depth <= 31 => stack <= 94 + sentinel <= TRAVERSAL_STACK
 constexpr size_t PAR_THRESHOLD = 16384; // subtrees above this many references become pool tasks
 constexpr float BOX_PAD = 1e-5f;		// reference pads primitive and node boxes by 1e-5 (bvh_tree.cpp:446, bvh_node.h:221)
-constexpr float SPATIAL_ALPHA = 1e-5f;	// overlap / root area above which a spatial split is considered
-constexpr float REF_BUDGET = 0.6f;		// at most this fraction of extra (duplicated) references
+#ifndef RFW_SPATIAL_ALPHA
+#define RFW_SPATIAL_ALPHA 1e-5f
+#endif
+constexpr float SPATIAL_ALPHA = RFW_SPATIAL_ALPHA;	// overlap / root area above which a spatial split is considered
+#ifndef RFW_REF_BUDGET
+#define RFW_REF_BUDGET 0.6f
+#endif
+#ifndef RFW_SAH_CTRAV
+#define RFW_SAH_CTRAV 1.0f
+#endif
+constexpr float REF_BUDGET = RFW_REF_BUDGET;		// at most this fraction of extra (duplicated) references
 
 struct Box
 {
@@ -302,7 +311,7 @@ struct Builder
 		const float node_area = node.box.area();
 		const float leaf_cost = float(count) * node_area;
 		const float best_cost = std::min(obj_cost, sp_cost);
-		const float split_cost = node_area * 1.0f + best_cost; // C_trav = C_isect = 1
+		const float split_cost = node_area * RFW_SAH_CTRAV + best_cost; // C_trav (default 1) relative to C_isect = 1
 		if (count <= uint32_t(max_leaf) && (best_cost >= 3.0e38f || split_cost >= leaf_cost))
 		{
 			make_leaf(node, refs);
