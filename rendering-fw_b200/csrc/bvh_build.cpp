@@ -43,6 +43,9 @@ constexpr float SPATIAL_ALPHA = RFW_SPATIAL_ALPHA;	// overlap / root area above 
 #ifndef RFW_SAH_CTRAV
 #define RFW_SAH_CTRAV 1.0f
 #endif
+#ifndef RFW_COLLAPSE_CTRAV
+#define RFW_COLLAPSE_CTRAV 1.0f // node visit : triangle test cost in the collapse (measured: 1 is best, 2.4 = the kernels' instruction ratio is not)
+#endif
 constexpr float REF_BUDGET = RFW_REF_BUDGET;		// at most this fraction of extra (duplicated) references
 
 struct Box
@@ -553,30 +556,36 @@ void build_bvh4(const BuildTriangle *tris, size_t count, int threads, BvhBuildRe
 
 	// ---- collapse to 4-wide, breadth-first layout; leaves get their slice of the triangle order here ----
 	const std::vector<Node2> &n2 = b.nodes;
-	// SAH-optimal collapse: G(i, k) = cheapest cover of BVH2 subtree i by at most k roots, a root being a leaf or a 4-wide
-	// node (area * C_trav + cheapest cover of its two subtrees by 4 roots).  Against the greedy rule "open the child with
-	// the largest area" (-DRFW_GREEDY_COLLAPSE) on Sponza: 72.7 k instead of 86.0 k nodes, 4.8 % fewer node visits per
-	// bounce ray for 2.7 % more triangle tests.
+	// Optional SAH-optimal collapse (-DRFW_OPTIMAL_COLLAPSE): G(i, k) = cheapest cover of BVH2 subtree i by at most k roots,
+	// a root being a leaf or a 4-wide node (area * C_trav + cheapest cover of its two subtrees by 4 roots); since every
+	// BVH2 leaf ends up as a leaf slot either way, this minimises the summed area of the 4-wide nodes.  Against the greedy
+	// rule "open the child with the largest area" on Sponza: 72.7 k instead of 86.0 k nodes, 4.8 % fewer node visits per
+	// bounce ray for 2.7 % more triangle tests — measured on the B200: frame 13.81 vs 13.88 ms on Sponza, but 10.95 vs
+	// 10.57 ms on the 10 M-triangle scene (profiles/r01b/collapse_sweep.jsonl), so greedy stays the default.
 	struct Dp
 	{
 		float g[5];
 		uint8_t left_share[5]; // roots given to the left subtree when the node is opened with k roots
 		bool as_one[5];		   // with k roots available the node is still cheapest as ONE 4-wide node
+		bool as_leaf;		   // an inner BVH2 node whose <= 4 references are cheapest as one leaf slot of its parent
 	};
-#ifdef RFW_GREEDY_COLLAPSE
-	const bool optimal_collapse = false;
-#else
+#ifdef RFW_OPTIMAL_COLLAPSE
 	const bool optimal_collapse = true;
+#else
+	const bool optimal_collapse = false;
 #endif
 	std::vector<Dp> dp;
 	if (optimal_collapse)
 	{
 		const int32_t nn2 = b.next_node.load();
 		dp.resize(size_t(nn2));
+		std::vector<uint32_t> sub(size_t(nn2), 0);
 		for (int32_t i = nn2; i-- > 0;) // children are allocated after their parents
 		{
 			Dp &d = dp[i];
 			const Node2 &nd = n2[i];
+			d.as_leaf = false;
+			sub[i] = nd.leaf ? uint32_t(std::max<size_t>(nd.prims.size(), 1)) : (sub[nd.left] + sub[nd.right]);
 			if (nd.leaf)
 			{
 				for (int k = 1; k <= 4; k++)
@@ -589,12 +598,48 @@ void build_bvh4(const BuildTriangle *tris, size_t count, int threads, BvhBuildRe
 				for (int a = 1; a < k; a++)
 					if (l.g[a] + r.g[k - a] < f[k])
 						f[k] = l.g[a] + r.g[k - a], d.left_share[k] = uint8_t(a);
-			const float one = nd.box.area() * RFW_SAH_CTRAV + f[4];
+			const float one = nd.box.area() * RFW_COLLAPSE_CTRAV + f[4];
 			d.g[1] = one, d.as_one[1] = true, d.left_share[1] = d.left_share[4];
 			for (int k = 2; k <= 4; k++)
 				d.as_one[k] = one <= f[k], d.g[k] = std::min(one, f[k]);
+#ifndef RFW_NO_LEAF_MERGE
+			// the wide node pays per visit, not per triangle: a small subtree can be cheaper as one leaf slot
+			const float as_leaf_cost = nd.box.area() * float(sub[i]);
+			if (sub[i] <= uint32_t(MAX_LEAF) && as_leaf_cost <= d.g[4])
+			{
+				d.as_leaf = true;
+				for (int k = 1; k <= 4; k++)
+					d.g[k] = as_leaf_cost, d.as_one[k] = true;
+			}
+#endif
 		}
 	}
+	// references of a (merged) leaf: the two halves of a spatially split triangle collapse into one reference
+	std::vector<uint32_t> leaf_prims;
+	std::vector<Box> leaf_boxes;
+	auto gather_leaf = [&](int32_t root) {
+		leaf_prims.clear(), leaf_boxes.clear();
+		int32_t st[16];
+		int sp = 0;
+		st[sp++] = root;
+		while (sp)
+		{
+			const Node2 &c = n2[st[--sp]];
+			if (!c.leaf)
+			{
+				st[sp++] = c.right, st[sp++] = c.left;
+				continue;
+			}
+			for (size_t pi = 0; pi < c.prims.size(); pi++)
+			{
+				const auto it = std::find(leaf_prims.begin(), leaf_prims.end(), c.prims[pi]);
+				if (it == leaf_prims.end())
+					leaf_prims.push_back(c.prims[pi]), leaf_boxes.push_back(c.prim_boxes[pi]);
+				else
+					leaf_boxes[size_t(it - leaf_prims.begin())].grow(c.prim_boxes[pi]);
+			}
+		}
+	};
 	struct Pending
 	{
 		int32_t n2;
@@ -636,7 +681,7 @@ void build_bvh4(const BuildTriangle *tris, size_t count, int threads, BvhBuildRe
 			{
 				const Item it = st[--sp];
 				const Node2 &c = n2[it.n];
-				if (c.leaf || it.k == 1 || dp[it.n].as_one[it.k])
+				if (c.leaf || dp[it.n].as_leaf || it.k == 1 || dp[it.n].as_one[it.k])
 					kids[nk++] = it.n;
 				else
 				{
@@ -676,25 +721,26 @@ void build_bvh4(const BuildTriangle *tris, size_t count, int threads, BvhBuildRe
 			}
 			const Node2 &c = n2[kids[k]];
 			set_child_box(node, k, padded(c.box));
-			if (c.leaf)
+			if (c.leaf || (optimal_collapse && dp[kids[k]].as_leaf))
 			{
+				gather_leaf(kids[k]);
 				const uint32_t first = uint32_t(out.tri_order.size());
-				const uint32_t cnt = uint32_t(std::min<size_t>(std::max<size_t>(c.prims.size(), 1), MAX_LEAF));
-				if (c.prims.empty())
+				const uint32_t cnt = uint32_t(std::min<size_t>(std::max<size_t>(leaf_prims.size(), 1), MAX_LEAF));
+				if (leaf_prims.empty())
 				{
 					out.tri_order.push_back(0);
 					out.ref_boxes.insert(out.ref_boxes.end(), {0.f, 0.f, 0.f, 0.f, 0.f, 0.f});
 				}
-				for (size_t i = 0; i < c.prims.size(); i++)
+				for (size_t i = 0; i < leaf_prims.size(); i++)
 				{
 					if (i >= size_t(MAX_LEAF))
 						break; // cannot happen: leaves are only made at <= MAX_LEAF references
-					out.tri_order.push_back(c.prims[i]);
-					const Box &rb = c.prim_boxes[i];
+					out.tri_order.push_back(leaf_prims[i]);
+					const Box &rb = leaf_boxes[i];
 					out.ref_boxes.insert(out.ref_boxes.end(), {rb.lo[0], rb.lo[1], rb.lo[2], rb.hi[0], rb.hi[1], rb.hi[2]});
 				}
 				node.child[k] = ~int32_t((first << 2) | (cnt - 1));
-				cost += c.box.area() * inv_root_area * float(c.prims.size());
+				cost += c.box.area() * inv_root_area * float(leaf_prims.size());
 			}
 			else
 			{
