@@ -199,7 +199,7 @@ struct rfwb200_context
 	cudaEvent_t ev_fork = nullptr;
 
 	// ---- settings / state ------------------------------------------------------------------------------
-	RenderSettings rs{2, 10.0f, 1e-5f, 1, 0, 16, nullptr, -1, 9, 5}; // bounces: packed nodes + unsorted connect rays; camera rays: fp32 nodes (DESIGN.md sweep) // smem_nodes 0: measured fastest on B200 (DESIGN.md "staging")
+	RenderSettings rs{2, 10.0f, 1e-5f, 1, 0, 16, nullptr, -1, 9, 0, 5}; // bounces: packed nodes + unsorted connect rays; camera rays: fp32 nodes (DESIGN.md sweep) // smem_nodes 0: measured fastest on B200 (DESIGN.md "staging")
 	int spp = 1;
 	bool mode_pt = true;
 	LaunchDims dims{};
@@ -1421,6 +1421,8 @@ extern "C"
 			REQUIRE(n >= 0 && n <= 12, "trace_variant must be in [0, 12]");
 			c->rs.trace_variant = c->rs.primary_variant = n; // one value for both kinds of launch; primary_variant overrides
 		}
+		else if (k == "shadow_cache")
+			c->rs.shadow_cache = (v == "on" || v == "1") ? 1 : 0;
 		else if (k == "primary_variant")
 		{
 			const int n = atoi(v.c_str());
@@ -1466,7 +1468,11 @@ extern "C"
 		REQUIRE(c && buf && buf_size > 0, "bad buffer");
 		const std::string s = "spp=" + std::to_string(c->spp) + "\nmode=pt|embree\nmax_path_length=" +
 							  std::to_string(c->rs.max_path_length) + "\nclamp=" + std::to_string(c->rs.clamp_value) +
-							  "\nsurvival_scale=on|off\nsmem_nodes=" + std::to_string(c->rs.smem_nodes) + "\n";
+							  "\nsurvival_scale=on|off\nsmem_nodes=" + std::to_string(c->rs.smem_nodes) + "\nsample_lanes=" +
+							  std::to_string(c->n_lanes) + "\nfetch_threshold=" + std::to_string(c->rs.fetch_threshold) +
+							  "\ntrace_variant=" + std::to_string(c->rs.trace_variant) + "\nprimary_variant=" +
+							  std::to_string(c->rs.primary_variant) + "\nbvh=4|8\nbuilder=sbvh|lbvh\nspatial_splits=on|off\nrefit=device|host" +
+							  "\nshade_math=fast|ieee\ntiming=on|off\n";
 		snprintf(buf, buf_size, "%s", s.c_str());
 		return RFWB200_OK;
 	}

@@ -163,6 +163,7 @@ struct RenderSettings
 	unsigned long long *debug; // optional per-warp {start ns, end ns, rays} records of one trace launch (tools/diag)
 	int debug_depth;
 	int trace_variant; // which instantiation of k_wavefront_trace runs (kernels.cu launch_trace; tuning)
+	int shadow_cache; // 1: connect rays test the occluder of the lane's previous connect ray before entering the tree
 	int primary_variant; // the same for camera rays (coherent: fp32 nodes measured faster there than packed ones)
 };
 

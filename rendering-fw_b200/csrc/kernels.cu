@@ -567,6 +567,11 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 	constexpr int NO_LEAF = 0;			 // leaf references are negative, so 0 can mean "none postponed"
 	int sp = 0, cur = SENTINEL, leaf = NO_LEAF;
 	int leaf1 = NO_LEAF, leaf2 = NO_LEAF; // further held-back leaves (LQ > 1)
+	// Occluder cache (setting shadow_cache): the triangle record that stopped this lane's previous connect ray is tested
+	// first; lanes take neighbouring queue entries (neighbouring pixels aiming at the same light), so a wall or a roof that
+	// occluded one ray usually occludes the next, which then never enters the tree.  Occlusion is a yes/no answer, so the
+	// result does not depend on which occluder is found.
+	uint32_t occluder = 0xffffffffu;
 	bool exhausted = false; // warp-uniform: the queue has no more items
 	uint32_t acc_count = 0;
 
@@ -619,6 +624,23 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 						const float4 O4 = wf.sO[k], D4 = wf.sD[k];
 						o = mk(O4.x, O4.y, O4.z), d = mk(D4.x, D4.y, D4.z);
 						tmin = rs.geometry_epsilon, tmax = D4.w, shadow = true;
+						if (rs.shadow_cache && occluder != 0xffffffffu)
+						{
+							const float4 a = __ldg(tris + size_t(occluder) * 3 + 0);
+							const float4 b = __ldg(tris + size_t(occluder) * 3 + 1);
+							const float4 c = __ldg(tris + size_t(occluder) * 3 + 2);
+							const V3 p0 = mk(a.x, a.y, a.z), e1 = mk(a.w, b.x, b.y), e2 = mk(b.z, b.w, c.x);
+							const V3 h = cross(d, e2);
+							const float det = dot(e1, h);
+							const float f = 1.0f / det;
+							const V3 s = o - p0;
+							const float u = f * dot(s, h);
+							const V3 q = cross(s, e1);
+							const float vv = f * dot(d, q);
+							const float t = f * dot(e2, q);
+							if (!(det > -c.z && det < c.z) && u >= 0.0f && u <= 1.0f && vv >= 0.0f && u + vv <= 1.0f && t > tmin && tmax > t)
+								valid = false; // occluded: nothing to accumulate, the lane stays idle and takes the next item
+						}
 					}
 					if (valid)
 					{
@@ -813,6 +835,7 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 							{
 								cur = SENTINEL; // any hit ends a connect ray
 								leaf1 = leaf2 = NO_LEAF;
+								occluder = first + i;
 								break;
 							}
 						}
