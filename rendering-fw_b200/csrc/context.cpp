@@ -174,6 +174,8 @@ struct rfwb200_context
 	bool wide8 = false;		 // setting "bvh" = 4 | 8 (compressed 8-wide layout, cwbvh.h)
 	bool lbvh = false;		 // setting "builder" = sbvh (host, SAH + spatial splits) | lbvh (device, lbvh.h)
 	bool device_built = false; // the current tree was built on the device: the host has no copy of its topology
+	bool lbvh_presplit = true; // setting "lbvh_presplit": early split clipping before the Morton sort (lbvh.h step 0)
+	bool device_ref_boxes = false; // d_ref_boxes was written by the device builder
 	int device_depth = 0;
 	DevBuf d_lbvh_scratch;
 	DevBuf d_cw_nodes, d_nodes16;
@@ -556,7 +558,7 @@ void bind_geometry_views(Ctx *c, size_t nn, size_t nr)
 	g.flat_count = uint32_t(c->flat_tri_count);
 	g.nodes = c->d_nodes.as<BvhNode4>(), g.tri_order = c->d_tri_order.as<uint32_t>();
 	g.parent_slot = c->d_parent_slot.as<uint32_t>(), g.arrivals = c->d_arrivals.as<uint32_t>();
-	g.ref_boxes = (c->bvh.ref_boxes.size() == 6 * nr && nr > 0) ? c->d_ref_boxes.as<float>() : nullptr;
+	g.ref_boxes = ((c->bvh.ref_boxes.size() == 6 * nr || c->device_ref_boxes) && nr > 0) ? c->d_ref_boxes.as<float>() : nullptr;
 	g.node_count = uint32_t(nn), g.ref_count = uint32_t(nr);
 	g.out_tris = c->d_tris.as<TriRec>(), g.out_shade = c->d_shade_tris.as<ShadeTri>();
 	c->scene.nodes = c->d_nodes.as<BvhNode4>(), c->scene.tris = c->d_tris.as<TriRec>();
@@ -1084,14 +1086,17 @@ extern "C"
 				return r;
 			if (int r = upload_instances(c, true))
 				return r;
-			const size_t nn_cap = total; // a 4-wide node has at least two children
+			const size_t ref_cap = c->lbvh_presplit ? total + total / 2 + 1024 : total; // early split clipping: up to 50 % more references
+			const size_t nn_cap = ref_cap;													  // a 4-wide node has at least two children
 			CK(c->d_nodes.reserve(nn_cap * sizeof(BvhNode4)));
-			CK(c->d_tris.reserve(total * sizeof(TriRec)));
-			CK(c->d_tri_order.reserve(total * sizeof(uint32_t)));
+			CK(c->d_tris.reserve(ref_cap * sizeof(TriRec)));
+			CK(c->d_tri_order.reserve(ref_cap * sizeof(uint32_t)));
 			CK(c->d_parent_slot.reserve(nn_cap * sizeof(uint32_t)));
 			CK(c->d_arrivals.reserve(nn_cap * sizeof(uint32_t)));
 			CK(c->d_shade_tris.reserve(total * sizeof(ShadeTri)));
-			CK(c->d_lbvh_scratch.reserve(lbvh_scratch_bytes(total)));
+			CK(c->d_ref_boxes.reserve(ref_cap * 6 * sizeof(float)));
+			CK(c->d_lbvh_scratch.reserve(lbvh_scratch_bytes(total, ref_cap)));
+			c->device_ref_boxes = false;
 			bind_geometry_views(c, 0, total);
 			if (!c->ev_geo_a)
 			{
@@ -1100,14 +1105,16 @@ extern "C"
 			}
 			const auto tb0 = std::chrono::steady_clock::now();
 			CK(cudaEventRecord(c->ev_geo_a, c->stream));
-			uint32_t nn = 0;
+			uint32_t nn = 0, nrefs = 0;
 			int depth = 0, launches = 0;
-			CK(lbvh_build(c->geo, c->d_lbvh_scratch.ptr, c->d_lbvh_scratch.bytes, c->d_nodes.as<BvhNode4>(), nn_cap, c->d_tri_order.as<uint32_t>(),
-						  c->d_parent_slot.as<uint32_t>(), &nn, &depth, &launches, c->stream));
+			CK(lbvh_build(c->geo, c->lbvh_presplit ? 1 : 0, c->d_lbvh_scratch.ptr, c->d_lbvh_scratch.bytes, ref_cap, c->d_nodes.as<BvhNode4>(),
+						  c->d_tri_order.as<uint32_t>(), c->d_parent_slot.as<uint32_t>(), c->d_ref_boxes.as<float>(), &nn, &nrefs, &depth,
+						  &launches, c->stream));
 			c->launches += uint64_t(launches);
+			c->device_ref_boxes = true;
 			if (3 * depth + 1 > TRAVERSAL_STACK)
 				return set_error(RFWB200_ERR_INVALID, "LBVH deeper than the traversal stack allows (use builder=sbvh)");
-			bind_geometry_views(c, nn, total);
+			bind_geometry_views(c, nn, nrefs);
 			if (int r = device_generate(c, false, false))
 				return r;
 			CK(cudaStreamSynchronize(c->stream));
@@ -1121,6 +1128,7 @@ extern "C"
 			return RFWB200_OK;
 		}
 		REQUIRE(!(c->lbvh && !c->device_geometry), "builder=lbvh needs the device geometry path (refit=device)");
+		c->device_ref_boxes = false;
 		REQUIRE(!(can_refit && c->device_built && c->bvh.nodes.empty()), "a device-built tree can only be refitted on the device (refit=device)");
 		c->device_built = false;
 		std::vector<ShadeTri> shade;
@@ -1442,6 +1450,16 @@ extern "C"
 			const bool lb = (v == "lbvh");
 			if (lb != c->lbvh)
 				c->lbvh = lb, c->arena_valid = false, c->geometry_dirty = c->topology_dirty = true;
+		}
+		else if (k == "lbvh_presplit")
+		{
+			const bool on = (v == "on" || v == "1");
+			if (on != c->lbvh_presplit)
+			{
+				c->lbvh_presplit = on;
+				if (c->lbvh)
+					c->arena_valid = false, c->geometry_dirty = c->topology_dirty = true;
+			}
 		}
 		else if (k == "bvh")
 		{
@@ -2056,31 +2074,72 @@ extern "C"
 	// Self check of the GPU builder's algorithm without a GPU: the per-element functions of lbvh.h — the very code the
 	// kernels in geometry.cu run one element per thread — executed in loops on the host (std::sort in place of the radix
 	// sort), then walked like any other 4-wide tree.
-	int rfwb200_host_lbvh_check(const float *tris9, size_t n_tris, const float *origins3, const float *dirs3, size_t n_rays, float *t_out,
-								int32_t *tri_out, uint64_t *nodes_out, int32_t *depth_out, uint32_t *visits_out)
+	int rfwb200_host_lbvh_check(const float *tris9, size_t n_tris, int presplit, const float *origins3, const float *dirs3, size_t n_rays,
+								float *t_out, int32_t *tri_out, uint64_t *nodes_out, uint64_t *refs_out, int32_t *depth_out, uint32_t *visits_out)
 	{
 		REQUIRE(tris9 && origins3 && dirs3 && t_out && tri_out, "bad arguments");
-		REQUIRE(n_tris >= 1 && n_tris < (1u << 30), "need 1 .. 2^30 triangles");
-		const int n = int(n_tris);
+		REQUIRE(n_tris >= 1 && n_tris < (1u << 29), "need 1 .. 2^29 triangles");
 		std::vector<BuildTriangle> bt(n_tris);
 		for (size_t i = 0; i < n_tris; i++)
 			memcpy(&bt[i], tris9 + 9 * i, 9 * sizeof(float));
-		std::vector<LbvhBox> boxes(n), leaf_box(n), inner_box(n);
+		auto pad_box = [](LbvhBox &b) {
+			for (int a = 0; a < 3; a++)
+			{
+				const float m = std::max(std::fabs(b.lo[a]), std::fabs(b.hi[a])), pad = std::max(1e-5f, m * 2.4e-7f);
+				b.lo[a] -= pad, b.hi[a] += pad;
+			}
+		};
+		// k_lbvh_bounds
+		std::vector<LbvhBox> full(n_tris);
 		float slo[3] = {3e38f, 3e38f, 3e38f}, shi[3] = {-3e38f, -3e38f, -3e38f};
-		for (int i = 0; i < n; i++)
+		for (size_t i = 0; i < n_tris; i++)
 		{
-			LbvhBox &b = boxes[i];
+			LbvhBox &b = full[i];
 			for (int a = 0; a < 3; a++)
 			{
 				b.lo[a] = std::min(std::min(bt[i].v0[a], bt[i].v1[a]), bt[i].v2[a]);
 				b.hi[a] = std::max(std::max(bt[i].v0[a], bt[i].v1[a]), bt[i].v2[a]);
 				const float c = 0.5f * (b.lo[a] + b.hi[a]);
 				slo[a] = std::min(slo[a], c), shi[a] = std::max(shi[a], c);
-				const float m = std::max(std::fabs(b.lo[a]), std::fabs(b.hi[a])), pad = std::max(1e-5f, m * 2.4e-7f);
-				b.lo[a] -= pad, b.hi[a] += pad;
 			}
 			b.pad0 = b.pad1 = 0;
 		}
+		// k_lbvh_counts / k_lbvh_emit: one reference per piece
+		float cell = presplit ? std::max(std::max(shi[0] - slo[0], shi[1] - slo[1]), shi[2] - slo[2]) * (1.0f / 64.0f) : 0.0f;
+		const size_t ref_cap = n_tris + n_tris / 2 + 1024; // the device orchestrator's capacity rule (context.cpp, lbvh_build)
+		for (int attempt = 0; presplit && attempt < 8 && cell > 0.0f; attempt++, cell *= 2.0f)
+		{
+			size_t total = 0;
+			for (size_t i = 0; i < n_tris; i++)
+				total += size_t(lb_piece_count(full[i], cell));
+			if (total <= ref_cap)
+				break;
+			if (attempt == 7)
+				cell = 0.0f; // gives up: one reference per triangle
+		}
+		std::vector<LbvhBox> boxes;
+		std::vector<uint32_t> ref_tri;
+		for (size_t i = 0; i < n_tris; i++)
+		{
+			const int cnt = presplit ? lb_piece_count(full[i], cell) : 1;
+			for (int j = 0; j < cnt; j++)
+			{
+				LbvhBox b = full[i];
+				if (cnt > 1)
+				{
+					int axis;
+					float lo, hi;
+					lb_piece_slab(full[i], cnt, j, axis, lo, hi);
+					b = lb_clip_to_slab(bt[i].v0, bt[i].v1, bt[i].v2, full[i], axis, lo, hi);
+				}
+				pad_box(b);
+				boxes.push_back(b), ref_tri.push_back(uint32_t(i));
+			}
+		}
+		const int n = int(boxes.size());
+		if (refs_out)
+			*refs_out = uint64_t(n);
+		std::vector<LbvhBox> leaf_box(n), inner_box(n);
 		float inv[3];
 		for (int a = 0; a < 3; a++)
 			inv[a] = shi[a] > slo[a] ? 1.0f / (shi[a] - slo[a]) : 0.0f;
@@ -2094,7 +2153,10 @@ extern "C"
 		BvhBuildResult bvh;
 		bvh.tri_order.resize(n);
 		for (int i = 0; i < n; i++)
-			bvh.tri_order[i] = uint32_t(keys[i] & 0xffffffffull), leaf_box[i] = boxes[bvh.tri_order[i]];
+		{
+			const uint32_t r = uint32_t(keys[i] & 0xffffffffull);
+			bvh.tri_order[i] = ref_tri[r], leaf_box[i] = boxes[r];
+		}
 		std::vector<int32_t> left(n), right(n), first(n), last(n), parent_inner(n), parent_leaf(n);
 		std::vector<uint32_t> arrivals(n, 0u);
 		Lbvh2View t{};

@@ -18,6 +18,7 @@
 #include "lbvh.h"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <cuda_runtime.h>
 #include <math.h>
@@ -392,7 +393,19 @@ __host__ __device__ __forceinline__ float ordered_to_float(int32_t i)
 }
 } // namespace
 
-// per flattened triangle: padded world-space box (the same arithmetic as k_refit) + scene bounds of the centroids
+// per flattened triangle: exact world-space box (the same vertex arithmetic as k_refit) + scene bounds of the centroids
+__device__ __forceinline__ void lbvh_world_triangle(const GeometryView &g, uint32_t src, F3 &v0, F3 &v1, F3 &v2)
+{
+	const uint32_t ii = g.flat_inst[src];
+	const DeviceInstance &in = g.instances[ii];
+	const uint32_t prim = src - in.flat_off;
+	const uint32_t *ix = g.indices + size_t(in.tri_off + prim) * 3;
+	const float4 *vb = g.verts + in.vert_off;
+	v0 = xf_point(in.transform, vb[ix[0]]);
+	v1 = xf_point(in.transform, vb[ix[1]]);
+	v2 = xf_point(in.transform, vb[ix[2]]);
+}
+
 __global__ void __launch_bounds__(256) k_lbvh_bounds(const GeometryView g, LbvhBox *__restrict__ boxes, int32_t *__restrict__ scene_bounds)
 {
 	const uint32_t src = blockIdx.x * blockDim.x + threadIdx.x;
@@ -400,22 +413,13 @@ __global__ void __launch_bounds__(256) k_lbvh_bounds(const GeometryView g, LbvhB
 	const bool live = src < g.flat_count;
 	if (live)
 	{
-		const uint32_t ii = g.flat_inst[src];
-		const DeviceInstance &in = g.instances[ii];
-		const uint32_t prim = src - in.flat_off;
-		const uint32_t *ix = g.indices + size_t(in.tri_off + prim) * 3;
-		const float4 *vb = g.verts + in.vert_off;
-		const F3 v0 = xf_point(in.transform, vb[ix[0]]);
-		const F3 v1 = xf_point(in.transform, vb[ix[1]]);
-		const F3 v2 = xf_point(in.transform, vb[ix[2]]);
+		F3 v0, v1, v2;
+		lbvh_world_triangle(g, src, v0, v1, v2);
 		LbvhBox b;
 		b.lo[0] = fminf(fminf(v0.x, v1.x), v2.x), b.lo[1] = fminf(fminf(v0.y, v1.y), v2.y), b.lo[2] = fminf(fminf(v0.z, v1.z), v2.z);
 		b.hi[0] = fmaxf(fmaxf(v0.x, v1.x), v2.x), b.hi[1] = fmaxf(fmaxf(v0.y, v1.y), v2.y), b.hi[2] = fmaxf(fmaxf(v0.z, v1.z), v2.z);
 		for (int a = 0; a < 3; a++)
-		{
 			c[a] = 0.5f * (b.lo[a] + b.hi[a]);
-			pad_axis(b.lo[a], b.hi[a]);
-		}
 		b.pad0 = b.pad1 = 0.0f;
 		boxes[src] = b;
 	}
@@ -432,7 +436,47 @@ __global__ void __launch_bounds__(256) k_lbvh_bounds(const GeometryView g, LbvhB
 	}
 }
 
-__global__ void __launch_bounds__(256) k_lbvh_keys(const LbvhBox *__restrict__ boxes, uint32_t n, const int32_t *__restrict__ scene_bounds,
+// early split clipping (lbvh.h step 0): pieces per triangle, then one reference per piece
+__global__ void __launch_bounds__(256) k_lbvh_counts(const LbvhBox *__restrict__ boxes, uint32_t n, float cell, uint32_t *__restrict__ counts)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n)
+		counts[i] = uint32_t(lb_piece_count(boxes[i], cell));
+}
+
+__global__ void __launch_bounds__(256) k_lbvh_emit(const GeometryView g, const LbvhBox *__restrict__ boxes, const uint32_t *__restrict__ counts,
+												   const uint32_t *__restrict__ offsets, LbvhBox *__restrict__ ref_box,
+												   uint32_t *__restrict__ ref_tri)
+{
+	const uint32_t src = blockIdx.x * blockDim.x + threadIdx.x;
+	if (src >= g.flat_count)
+		return;
+	const LbvhBox full = boxes[src];
+	const uint32_t cnt = counts ? counts[src] : 1u, off = offsets ? offsets[src] : src;
+	if (cnt <= 1u)
+	{
+		LbvhBox b = full;
+		for (int a = 0; a < 3; a++)
+			pad_axis(b.lo[a], b.hi[a]);
+		ref_box[off] = b, ref_tri[off] = src;
+		return;
+	}
+	F3 v0, v1, v2;
+	lbvh_world_triangle(g, src, v0, v1, v2);
+	const float p0[3] = {v0.x, v0.y, v0.z}, p1[3] = {v1.x, v1.y, v1.z}, p2[3] = {v2.x, v2.y, v2.z};
+	for (uint32_t j = 0; j < cnt; j++)
+	{
+		int axis;
+		float lo, hi;
+		lb_piece_slab(full, int(cnt), int(j), axis, lo, hi);
+		LbvhBox b = lb_clip_to_slab(p0, p1, p2, full, axis, lo, hi);
+		for (int a = 0; a < 3; a++)
+			pad_axis(b.lo[a], b.hi[a]);
+		ref_box[off + j] = b, ref_tri[off + j] = src;
+	}
+}
+
+__global__ void __launch_bounds__(256) k_lbvh_keys(const LbvhBox *__restrict__ ref_box, uint32_t n, const int32_t *__restrict__ scene_bounds,
 												   uint64_t *__restrict__ keys)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -445,21 +489,28 @@ __global__ void __launch_bounds__(256) k_lbvh_keys(const LbvhBox *__restrict__ b
 		const float ext = ordered_to_float(scene_bounds[3 + a]) - lo[a];
 		inv[a] = ext > 0.0f ? 1.0f / ext : 0.0f;
 	}
-	const LbvhBox b = boxes[i];
+	const LbvhBox b = ref_box[i];
 	// centroid of the padded box = centroid of the exact box up to rounding: only the ordering matters
 	const uint32_t m = lb_morton30(0.5f * (b.lo[0] + b.hi[0]), 0.5f * (b.lo[1] + b.hi[1]), 0.5f * (b.lo[2] + b.hi[2]), lo, inv);
 	keys[i] = (uint64_t(m) << 32) | uint64_t(i);
 }
 
-__global__ void __launch_bounds__(256) k_lbvh_gather(const uint64_t *__restrict__ keys, const LbvhBox *__restrict__ boxes, uint32_t n,
-													 LbvhBox *__restrict__ leaf_box, uint32_t *__restrict__ tri_order)
+__global__ void __launch_bounds__(256) k_lbvh_gather(const uint64_t *__restrict__ keys, const LbvhBox *__restrict__ ref_box,
+													 const uint32_t *__restrict__ ref_tri, uint32_t n, LbvhBox *__restrict__ leaf_box,
+													 uint32_t *__restrict__ tri_order, float *__restrict__ ref_boxes_out)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n)
 		return;
-	const uint32_t src = uint32_t(keys[i] & 0xffffffffull);
-	leaf_box[i] = boxes[src];
-	tri_order[i] = src;
+	const uint32_t r = uint32_t(keys[i] & 0xffffffffull);
+	const LbvhBox b = ref_box[r];
+	leaf_box[i] = b;
+	tri_order[i] = ref_tri[r];
+	if (ref_boxes_out) // kept for refits: triangles that do not move keep their clipped boxes (k_refit)
+	{
+		float *o = ref_boxes_out + size_t(i) * 6;
+		o[0] = b.lo[0], o[1] = b.lo[1], o[2] = b.lo[2], o[3] = b.hi[0], o[4] = b.hi[1], o[5] = b.hi[2];
+	}
 }
 
 __global__ void __launch_bounds__(256) k_lbvh_inner(const Lbvh2View t)
@@ -504,22 +555,27 @@ __global__ void __launch_bounds__(128) k_lbvh_collapse(const Lbvh2View t, const 
 					 [next_count] __device__(uint32_t k) { return atomicAdd(next_count, k); });
 }
 
-size_t lbvh_scratch_bytes(size_t n)
+// scratch for `refs` references over `tris` triangles (refs >= tris)
+size_t lbvh_scratch_bytes(size_t tris, size_t refs)
 {
-	size_t sort_tmp = 0;
-	cub::DeviceRadixSort::SortKeys(nullptr, sort_tmp, (const uint64_t *)nullptr, (uint64_t *)nullptr, int(n), 0, 62);
+	size_t sort_tmp = 0, scan_tmp = 0;
+	cub::DeviceRadixSort::SortKeys(nullptr, sort_tmp, (const uint64_t *)nullptr, (uint64_t *)nullptr, int(refs), 0, 62);
+	cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (const uint32_t *)nullptr, (uint32_t *)nullptr, int(tris));
 	auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
-	return al(sort_tmp) + 2 * al(n * 8) + 3 * al(n * sizeof(LbvhBox)) + 6 * al(n * 4) + al(n * 4) + 2 * al(n * sizeof(LbvhPending)) + al(64) + 4096;
+	return al(sort_tmp) + al(scan_tmp) + 2 * al(refs * 8) + al(tris * sizeof(LbvhBox)) + 3 * al(refs * sizeof(LbvhBox)) + 8 * al(refs * 4) +
+		   2 * al(tris * 4) + 2 * al(refs * sizeof(LbvhPending)) + al(64) + 8192;
 }
 
-// Builds nodes[0..*node_count), tri_order[0..flat_count), parent_slot[0..*node_count) on `stream` (synchronises once per
-// tree level to read the size of the next level).
-cudaError_t lbvh_build(const GeometryView &g, void *scratch, size_t scratch_bytes, BvhNode4 *nodes, size_t node_capacity, uint32_t *tri_order,
-					   uint32_t *parent_slot, uint32_t *node_count, int *depth, int *launches, cudaStream_t stream)
+// Builds nodes[0..*node_count), tri_order[0..*ref_count), parent_slot[0..*node_count) (and ref_boxes_out, 6 floats per
+// reference, when given) on `stream`; synchronises once per tree level to read the size of the next level, and once or
+// twice more when `presplit` is on (scene extent, reference count).
+cudaError_t lbvh_build(const GeometryView &g, int presplit, void *scratch, size_t scratch_bytes, size_t ref_capacity, BvhNode4 *nodes,
+					   uint32_t *tri_order, uint32_t *parent_slot, float *ref_boxes_out, uint32_t *node_count, uint32_t *ref_count, int *depth,
+					   int *launches, cudaStream_t stream)
 {
-	const uint32_t n = g.flat_count;
-	*node_count = 0, *depth = 0;
-	if (n == 0 || scratch_bytes < lbvh_scratch_bytes(n))
+	const uint32_t nt = g.flat_count;
+	*node_count = 0, *ref_count = 0, *depth = 0;
+	if (nt == 0 || ref_capacity < nt || scratch_bytes < lbvh_scratch_bytes(nt, ref_capacity))
 		return cudaErrorInvalidValue;
 	auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
 	char *p = static_cast<char *>(scratch);
@@ -528,35 +584,75 @@ cudaError_t lbvh_build(const GeometryView &g, void *scratch, size_t scratch_byte
 		p += al(b);
 		return r;
 	};
-	size_t sort_tmp = 0;
-	cub::DeviceRadixSort::SortKeys(nullptr, sort_tmp, (const uint64_t *)nullptr, (uint64_t *)nullptr, int(n), 0, 62);
-	void *d_sort = take(sort_tmp);
-	uint64_t *keys_a = reinterpret_cast<uint64_t *>(take(size_t(n) * 8)), *keys_b = reinterpret_cast<uint64_t *>(take(size_t(n) * 8));
-	LbvhBox *boxes = reinterpret_cast<LbvhBox *>(take(size_t(n) * sizeof(LbvhBox)));
+	const size_t cap = ref_capacity;
+	size_t sort_tmp = 0, scan_tmp = 0;
+	cub::DeviceRadixSort::SortKeys(nullptr, sort_tmp, (const uint64_t *)nullptr, (uint64_t *)nullptr, int(cap), 0, 62);
+	cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (const uint32_t *)nullptr, (uint32_t *)nullptr, int(nt));
+	void *d_sort = take(sort_tmp), *d_scan = take(scan_tmp);
+	uint64_t *keys_a = reinterpret_cast<uint64_t *>(take(cap * 8)), *keys_b = reinterpret_cast<uint64_t *>(take(cap * 8));
+	LbvhBox *boxes = reinterpret_cast<LbvhBox *>(take(size_t(nt) * sizeof(LbvhBox)));
+	LbvhBox *ref_box = reinterpret_cast<LbvhBox *>(take(cap * sizeof(LbvhBox)));
 	Lbvh2View t{};
-	t.n = int32_t(n);
-	t.leaf_box = reinterpret_cast<LbvhBox *>(take(size_t(n) * sizeof(LbvhBox)));
-	t.inner_box = reinterpret_cast<LbvhBox *>(take(size_t(n) * sizeof(LbvhBox)));
-	t.left = reinterpret_cast<int32_t *>(take(size_t(n) * 4)), t.right = reinterpret_cast<int32_t *>(take(size_t(n) * 4));
-	t.first = reinterpret_cast<int32_t *>(take(size_t(n) * 4)), t.last = reinterpret_cast<int32_t *>(take(size_t(n) * 4));
-	t.parent_inner = reinterpret_cast<int32_t *>(take(size_t(n) * 4)), t.parent_leaf = reinterpret_cast<int32_t *>(take(size_t(n) * 4));
-	t.arrivals = reinterpret_cast<uint32_t *>(take(size_t(n) * 4));
-	LbvhPending *queue_a = reinterpret_cast<LbvhPending *>(take(size_t(n) * sizeof(LbvhPending)));
-	LbvhPending *queue_b = reinterpret_cast<LbvhPending *>(take(size_t(n) * sizeof(LbvhPending)));
+	t.leaf_box = reinterpret_cast<LbvhBox *>(take(cap * sizeof(LbvhBox)));
+	t.inner_box = reinterpret_cast<LbvhBox *>(take(cap * sizeof(LbvhBox)));
+	t.left = reinterpret_cast<int32_t *>(take(cap * 4)), t.right = reinterpret_cast<int32_t *>(take(cap * 4));
+	t.first = reinterpret_cast<int32_t *>(take(cap * 4)), t.last = reinterpret_cast<int32_t *>(take(cap * 4));
+	t.parent_inner = reinterpret_cast<int32_t *>(take(cap * 4)), t.parent_leaf = reinterpret_cast<int32_t *>(take(cap * 4));
+	t.arrivals = reinterpret_cast<uint32_t *>(take(cap * 4));
+	uint32_t *ref_tri = reinterpret_cast<uint32_t *>(take(cap * 4));
+	uint32_t *counts = reinterpret_cast<uint32_t *>(take(size_t(nt) * 4)), *offsets = reinterpret_cast<uint32_t *>(take(size_t(nt) * 4));
+	LbvhPending *queue_a = reinterpret_cast<LbvhPending *>(take(cap * sizeof(LbvhPending)));
+	LbvhPending *queue_b = reinterpret_cast<LbvhPending *>(take(cap * sizeof(LbvhPending)));
 	int32_t *bounds = reinterpret_cast<int32_t *>(take(64)); // 6 ordered ints + the level counter
 	uint32_t *next_count = reinterpret_cast<uint32_t *>(bounds + 8);
-	const uint32_t blocks = (n + 255u) / 256u;
+	const uint32_t tblocks = (nt + 255u) / 256u;
 	cudaError_t e;
 	const int32_t init[12] = {0x7fffffff, 0x7fffffff, 0x7fffffff, int32_t(0x80000000), int32_t(0x80000000), int32_t(0x80000000), 0, 0, 0, 0, 0, 0};
 	if ((e = cudaMemcpyAsync(bounds, init, sizeof(init), cudaMemcpyHostToDevice, stream)) != cudaSuccess)
 		return e;
-	k_lbvh_bounds<<<blocks, 256, 0, stream>>>(g, boxes, bounds);
-	k_lbvh_keys<<<blocks, 256, 0, stream>>>(boxes, n, bounds, keys_a);
+	k_lbvh_bounds<<<tblocks, 256, 0, stream>>>(g, boxes, bounds);
+	*launches += 1;
+	uint32_t n = nt;
+	bool split = false;
+	if (presplit && cap > nt)
+	{
+		int32_t hb[6];
+		if ((e = cudaMemcpyAsync(hb, bounds, sizeof(hb), cudaMemcpyDeviceToHost, stream)) != cudaSuccess)
+			return e;
+		if ((e = cudaStreamSynchronize(stream)) != cudaSuccess)
+			return e;
+		float ext = 0.0f;
+		for (int a = 0; a < 3; a++)
+			ext = fmaxf(ext, ordered_to_float(hb[3 + a]) - ordered_to_float(hb[a]));
+		float cell = ext * (1.0f / 64.0f);
+		for (int attempt = 0; attempt < 8 && cell > 0.0f; attempt++, cell *= 2.0f)
+		{
+			k_lbvh_counts<<<tblocks, 256, 0, stream>>>(boxes, nt, cell, counts);
+			if ((e = cub::DeviceScan::ExclusiveSum(d_scan, scan_tmp, counts, offsets, int(nt), stream)) != cudaSuccess)
+				return e;
+			*launches += 2;
+			uint32_t last_off = 0, last_cnt = 0;
+			if ((e = cudaMemcpyAsync(&last_off, offsets + (nt - 1), 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess)
+				return e;
+			if ((e = cudaMemcpyAsync(&last_cnt, counts + (nt - 1), 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess)
+				return e;
+			if ((e = cudaStreamSynchronize(stream)) != cudaSuccess)
+				return e;
+			if (size_t(last_off) + last_cnt <= cap)
+			{
+				n = last_off + last_cnt, split = true;
+				break;
+			}
+		}
+	}
+	k_lbvh_emit<<<tblocks, 256, 0, stream>>>(g, boxes, split ? counts : nullptr, split ? offsets : nullptr, ref_box, ref_tri);
+	const uint32_t blocks = (n + 255u) / 256u;
+	k_lbvh_keys<<<blocks, 256, 0, stream>>>(ref_box, n, bounds, keys_a);
 	if ((e = cub::DeviceRadixSort::SortKeys(d_sort, sort_tmp, keys_a, keys_b, int(n), 0, 62, stream)) != cudaSuccess)
 		return e;
-	t.keys = keys_b;
-	k_lbvh_gather<<<blocks, 256, 0, stream>>>(keys_b, boxes, n, t.leaf_box, tri_order);
-	*launches += 4 + 3; // + the sort's passes, roughly
+	t.keys = keys_b, t.n = int32_t(n);
+	k_lbvh_gather<<<blocks, 256, 0, stream>>>(keys_b, ref_box, ref_tri, n, t.leaf_box, tri_order, ref_boxes_out);
+	*launches += 3 + 3; // + the sort's passes, roughly
 	LbvhPending root{n == 1 ? ~0 : 0, 0xffffffffu};
 	if (n > 1)
 	{
@@ -573,7 +669,7 @@ cudaError_t lbvh_build(const GeometryView &g, void *scratch, size_t scratch_byte
 	int levels = 0;
 	while (count > 0)
 	{
-		if (size_t(level_base) + count > node_capacity)
+		if (size_t(level_base) + count > cap)
 			return cudaErrorMemoryAllocation;
 		if ((e = cudaMemsetAsync(next_count, 0, 4, stream)) != cudaSuccess)
 			return e;
@@ -590,7 +686,7 @@ cudaError_t lbvh_build(const GeometryView &g, void *scratch, size_t scratch_byte
 		if (levels > 64)
 			return cudaErrorUnknown;
 	}
-	*node_count = level_base, *depth = levels;
+	*node_count = level_base, *ref_count = n, *depth = levels;
 	return cudaGetLastError();
 }
 

@@ -149,6 +149,81 @@ LB_HD float lb_area(const LbvhBox &b)
 	return ex * ey + ey * ez + ez * ex;
 }
 
+// ---- step 0 (optional, setting lbvh_presplit): early split clipping --------------------------------------------------
+// A Morton-ordered tree cannot separate a huge triangle from the small ones around it, and Sponza's floor and walls are
+// exactly that.  Before the sort, a triangle whose box is longer than `cell` along its longest axis is cut into up to
+// LBVH_MAX_PIECES slabs; every slab becomes its own reference (same triangle, box of the clipped polygon), the way the
+// host builder's spatial splits do (bvh_build.cpp split_ref) but decided up front instead of by SAH.
+constexpr int LBVH_MAX_PIECES = 16;
+
+LB_HD int lb_longest_axis(const LbvhBox &b)
+{
+	const float ex = b.hi[0] - b.lo[0], ey = b.hi[1] - b.lo[1], ez = b.hi[2] - b.lo[2];
+	return ex >= ey ? (ex >= ez ? 0 : 2) : (ey >= ez ? 1 : 2);
+}
+
+// number of pieces of a triangle with (unpadded) box b
+LB_HD int lb_piece_count(const LbvhBox &b, float cell)
+{
+	const int a = lb_longest_axis(b);
+	const float len = b.hi[a] - b.lo[a];
+	if (!(cell > 0.0f) || !(len > cell))
+		return 1;
+	const float k = ceilf(len / cell);
+	return k > float(LBVH_MAX_PIECES) ? LBVH_MAX_PIECES : int(k);
+}
+
+// box of the part of triangle (v0, v1, v2) inside the slab lo <= x[axis] <= hi, intersected with the triangle's own box
+LB_HD LbvhBox lb_clip_to_slab(const float *v0, const float *v1, const float *v2, const LbvhBox &full, int axis, float lo, float hi)
+{
+	LbvhBox r;
+	for (int k = 0; k < 3; k++)
+		r.lo[k] = 3.0e38f, r.hi[k] = -3.0e38f;
+	r.pad0 = r.pad1 = 0.0f;
+	const float *v[3] = {v0, v1, v2};
+	for (int i = 0; i < 3; i++)
+	{
+		const float *a = v[i], *b = v[(i + 1) % 3];
+		const float pa = a[axis], pb = b[axis];
+		if (pa >= lo && pa <= hi)
+			for (int k = 0; k < 3; k++)
+				r.lo[k] = fminf(r.lo[k], a[k]), r.hi[k] = fmaxf(r.hi[k], a[k]);
+		for (int side = 0; side < 2; side++)
+		{
+			const float pl = side ? hi : lo;
+			if ((pa < pl && pb > pl) || (pa > pl && pb < pl))
+			{
+				float t = (pl - pa) / (pb - pa);
+				t = t < 0.0f ? 0.0f : (t > 1.0f ? 1.0f : t);
+				for (int k = 0; k < 3; k++)
+				{
+					const float q = k == axis ? pl : a[k] + (b[k] - a[k]) * t;
+					r.lo[k] = fminf(r.lo[k], q), r.hi[k] = fmaxf(r.hi[k], q);
+				}
+			}
+		}
+	}
+	// conservative against rounding of the intersection points: never smaller than the slab says, never larger than the triangle
+	for (int k = 0; k < 3; k++)
+	{
+		if (k == axis)
+			r.lo[k] = fminf(r.lo[k], fmaxf(lo, full.lo[k])), r.hi[k] = fmaxf(r.hi[k], fminf(hi, full.hi[k]));
+		r.lo[k] = fmaxf(r.lo[k], full.lo[k]), r.hi[k] = fminf(r.hi[k], full.hi[k]);
+		if (!(r.lo[k] <= r.hi[k]))
+			r.lo[k] = full.lo[k], r.hi[k] = full.hi[k]; // degenerate piece: fall back to the whole box
+	}
+	return r;
+}
+
+// piece j of `pieces` of a triangle: the slab bounds along the longest axis of its box
+LB_HD void lb_piece_slab(const LbvhBox &full, int pieces, int j, int &axis, float &lo, float &hi)
+{
+	axis = lb_longest_axis(full);
+	const float w = (full.hi[axis] - full.lo[axis]) / float(pieces);
+	lo = j == 0 ? full.lo[axis] : full.lo[axis] + w * float(j);
+	hi = j == pieces - 1 ? full.hi[axis] : full.lo[axis] + w * float(j + 1);
+}
+
 // one entry of the level queue of step 4
 struct LbvhPending
 {
@@ -156,7 +231,10 @@ struct LbvhPending
 	uint32_t parent_slot; // (parent << 2) | slot, root 0xffffffff
 };
 
-constexpr int LBVH_MAX_LEAF = 4;
+#ifndef RFW_LBVH_MAX_LEAF
+#define RFW_LBVH_MAX_LEAF 4
+#endif
+constexpr int LBVH_MAX_LEAF = RFW_LBVH_MAX_LEAF;
 
 LB_HD int lb_count(const Lbvh2View &t, int32_t c) { return c < 0 ? 1 : (t.last[c] - t.first[c] + 1); }
 LB_HD int lb_first(const Lbvh2View &t, int32_t c) { return c < 0 ? ~c : t.first[c]; }

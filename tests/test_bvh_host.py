@@ -172,36 +172,39 @@ def test_cwbvh_empty_and_single_triangle(product_lib):
 
 
 # ---- GPU builder's algorithm, emulated on the host (csrc/lbvh.h) ------------------------------------------------------
-def host_check_lbvh(lib, tris, o, d):
-    f = lib.fn("host_lbvh_check", C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
-                                             C.c_void_p, C.c_void_p, C.c_void_p])
+def host_check_lbvh(lib, tris, o, d, presplit=False):
+    f = lib.fn("host_lbvh_check", C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p])
     t, tri = np.zeros(len(o), np.float32), np.zeros(len(o), np.int32)
-    nodes, depth = C.c_uint64(), C.c_int32()
+    nodes, refs, depth = C.c_uint64(), C.c_uint64(), C.c_int32()
     visits = np.zeros((len(o), 2), np.uint32)
     o, d = np.ascontiguousarray(o, np.float32), np.ascontiguousarray(d, np.float32)
-    rc = f(tris.ctypes.data, len(tris), o.ctypes.data, d.ctypes.data, len(o), t.ctypes.data, tri.ctypes.data, C.byref(nodes),
-           C.byref(depth), visits.ctypes.data)
+    rc = f(tris.ctypes.data, len(tris), int(presplit), o.ctypes.data, d.ctypes.data, len(o), t.ctypes.data, tri.ctypes.data, C.byref(nodes),
+           C.byref(refs), C.byref(depth), visits.ctypes.data)
     assert rc == 0, lib.last_error()
-    return t, tri, {"nodes": nodes.value, "depth": depth.value, "visits": visits}
+    return t, tri, {"nodes": nodes.value, "refs": refs.value, "depth": depth.value, "visits": visits}
 
 
+@pytest.mark.parametrize("presplit", [False, True])
 @pytest.mark.parametrize("scene", ["soup", "cornell", "atrium"])
-def test_lbvh_algorithm_matches_brute_force(product_lib, scene):
+def test_lbvh_algorithm_matches_brute_force(product_lib, scene, presplit):
     """Morton keys -> radix tree (Karras) -> bottom-up boxes -> 4-wide collapse, the per-element functions of the GPU
     builder run on the host: closest hits equal brute force; the tree is shallower than the traversal stack allows."""
     sc = {"soup": lambda: S.feature_soup(1500), "cornell": lambda: S.cornell_box(unit_scale=True), "atrium": lambda: S.atrium(6000)}[scene]()
     tris = flatten(sc)
     ext = float(np.abs(tris).max())
     o, d = rays(300, 3, ext * 0.7)
-    t, tri, info = host_check_lbvh(product_lib, tris, o, d)
+    t, tri, info = host_check_lbvh(product_lib, tris, o, d, presplit)
     bt = brute(tris, o, d)
     hit = bt < 1e33
     assert np.array_equal(t < 1e33, hit)
     assert np.allclose(t[hit], bt[hit], rtol=2e-4, atol=1e-5 * ext)
     assert 3 * info["depth"] + 2 <= 96
-    assert info["nodes"] <= len(tris)
+    assert info["nodes"] <= info["refs"] and len(tris) <= info["refs"] <= 1.5 * len(tris) + 1024
+    if not presplit:
+        assert info["refs"] == len(tris)
     _, _, sbvh = host_check(product_lib, tris, o, d, True)
-    print(scene, "lbvh visits", info["visits"][:, 0].mean(), "sbvh visits", sbvh["visits"][:, 0].mean(), "depth", info["depth"], sbvh["depth"])
+    print(scene, "presplit", presplit, "refs", info["refs"], "lbvh visits", info["visits"][:, 0].mean(), "sbvh visits", sbvh["visits"][:, 0].mean(), "depth", info["depth"], sbvh["depth"])
 
 
 def test_lbvh_degenerate_inputs(product_lib):

@@ -376,19 +376,25 @@ def test_device_geometry_is_bit_identical_to_the_host_path(product_lib):
     assert np.array_equal(d.read_image(), h.read_image())
 
 
-def test_device_lbvh_build_then_device_refit(product_lib, oracle_lib):
+@pytest.mark.parametrize("presplit", ["on", "off"])
+def test_device_lbvh_build_then_device_refit(product_lib, oracle_lib, presplit):
     """builder=lbvh: Morton sort + radix tree + 4-wide collapse as kernels (csrc/lbvh.h, geometry.cu); the tree it makes is
     refitted by the same k_refit as a host-built one.  Hits against the oracle, frame against the host-built frame."""
     W, H = 160, 96
     (g, sc), (o, _) = make_pair(product_lib, oracle_lib, S.feature_soup, W, H)
     ref = R.RenderContext(product_lib)
     S.upload(ref, S.feature_soup(), W, H)
+    g.set_setting("lbvh_presplit", presplit)
     g.set_setting("builder", "lbvh")
     g.update()
     st = g.get_geometry_stats()
     assert (st.on_device, st.was_refit, st.builds, st.refits) == (1, 0, 2, 0) and st.device_ms > 0
     info = g.get_bvh_info()
-    assert info["triangles"] == sc.triangle_count() and 1 <= info["nodes"] <= info["triangles"]
+    assert 1 <= info["nodes"] <= info["triangles"]
+    if presplit == "off":
+        assert info["triangles"] == sc.triangle_count()
+    else:  # early split clipping: long triangles are referenced once per slab
+        assert sc.triangle_count() <= info["triangles"] <= 1.5 * sc.triangle_count() + 1024
     cam = sc.camera(W, H)
     origins, dirs = o.generate_primary(cam, 0)
     _check_hits(g, o, origins, dirs, g.trace_closest(origins, dirs), o.trace_closest(origins, dirs))
