@@ -174,7 +174,7 @@ struct rfwb200_context
 	bool wide8 = false;		 // setting "bvh" = 4 | 8 (compressed 8-wide layout, cwbvh.h)
 	bool lbvh = false;		 // setting "builder" = sbvh (host, SAH + spatial splits) | lbvh (device, lbvh.h)
 	bool device_built = false; // the current tree was built on the device: the host has no copy of its topology
-	bool lbvh_presplit = true; // setting "lbvh_presplit": early split clipping before the Morton sort (lbvh.h step 0)
+	bool lbvh_presplit = false; // setting "lbvh_presplit": early split clipping before the Morton sort (lbvh.h step 0); measured slower
 	bool device_ref_boxes = false; // d_ref_boxes was written by the device builder
 	int device_depth = 0;
 	DevBuf d_lbvh_scratch;

@@ -9,9 +9,9 @@ import rfwb200 as R, scenes as S
 sc = S.sponza_or_standin()
 out = {}
 ref = None
-for builder in ("sbvh", "lbvh", "lbvh-nosplit"):
+for builder in ("sbvh", "lbvh", "lbvh-presplit"):
     ctx = R.RenderContext(R.load_product())
-    ctx.set_setting("lbvh_presplit", "off" if builder.endswith("nosplit") else "on")
+    ctx.set_setting("lbvh_presplit", "on" if builder.endswith("presplit") else "off")
     ctx.set_setting("builder", builder.split("-")[0])
     t0 = time.time(); S.upload(ctx, sc, 1920, 1080); up = time.time() - t0
     g = ctx.get_geometry_stats()
