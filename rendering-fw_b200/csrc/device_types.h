@@ -149,6 +149,7 @@ struct WavefrontView
 	float4 *framebuffer;		// finalised
 	DepthCounters *counters;	// [spp][MAX_DEPTH_SLOTS]
 	ProbeResult *probe;
+	uint32_t *prim_cache;		// per local pixel: triangle record hit by the previous camera ray of that pixel (a bound only)
 	const FrameParams *frame;
 };
 
@@ -163,6 +164,7 @@ struct RenderSettings
 	unsigned long long *debug; // optional per-warp {start ns, end ns, rays} records of one trace launch (tools/diag)
 	int debug_depth;
 	int trace_variant; // which instantiation of k_wavefront_trace runs (kernels.cu launch_trace; tuning)
+	int primary_cache; // 1: a camera ray first tests the triangle its pixel hit last time and starts with that distance as bound
 	int shadow_cache; // 1: connect rays test the occluder of the lane's previous connect ray before entering the tree
 	int primary_variant; // the same for camera rays (coherent: fp32 nodes measured faster there than packed ones)
 };

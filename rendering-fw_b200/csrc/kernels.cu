@@ -572,6 +572,7 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 	// occluded one ray usually occludes the next, which then never enters the tree.  Occlusion is a yes/no answer, so the
 	// result does not depend on which occluder is found.
 	uint32_t occluder = 0xffffffffu;
+	uint32_t hit_pos = 0xffffffffu; // record position of the closest hit (camera rays: remembered per pixel)
 	bool exhausted = false; // warp-uniform: the queue has no more items
 	uint32_t acc_count = 0;
 
@@ -605,6 +606,28 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 							wf.O[0][item] = make_float4(o.x, o.y, o.z, __uint_as_float((item << 8) + 1u));
 							wf.D[0][item] = make_float4(d.x, d.y, d.z, 0.0f);
 							tmin = 1e-5f, tmax = 1e34f, shadow = false;
+							// Bound from the pixel's previous sample: the 8 samples of a pixel differ by a sub-pixel jitter, so
+							// the triangle one of them hit is almost always hit by the next.  Its distance (plus a few ulps) only
+							// LIMITS the search — the triangle is found again by the traversal itself, in the usual order — so the
+							// result is bit-identical with and without the cache, whatever stale value a concurrent lane left here.
+							const uint32_t cand = rs.primary_cache ? wf.prim_cache[item] : 0xffffffffu;
+							if (cand < sc.tri_count)
+							{
+								const float4 a = __ldg(tris + size_t(cand) * 3 + 0);
+								const float4 b = __ldg(tris + size_t(cand) * 3 + 1);
+								const float4 c = __ldg(tris + size_t(cand) * 3 + 2);
+								const V3 p0 = mk(a.x, a.y, a.z), e1 = mk(a.w, b.x, b.y), e2 = mk(b.z, b.w, c.x);
+								const V3 h = cross(d, e2);
+								const float det = dot(e1, h);
+								const float f = 1.0f / det;
+								const V3 s = o - p0;
+								const float u = f * dot(s, h);
+								const V3 q = cross(s, e1);
+								const float vv = f * dot(d, q);
+								const float t = f * dot(e2, q);
+								if (!(det > -c.z && det < c.z) && u >= 0.0f && u <= 1.0f && vv >= 0.0f && u + vv <= 1.0f && t > tmin && t < 1e33f)
+									tmax = t * 1.000004f + 1e-30f;
+							}
 						}
 						else
 						{
@@ -831,6 +854,8 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 						if (t > tmin && tmax > t)
 						{
 							tmax = t, hit_u = u, hit_v = vv, hit_tri = __float_as_uint(c.y);
+							if (PRIMARY)
+								hit_pos = first + i;
 							if (shadow)
 							{
 								cur = SENTINEL; // any hit ends a connect ray
@@ -866,6 +891,8 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 					hit = make_float4(__uint_as_float(uint32_t(65535.0f * hit_u) | (uint32_t(65535.0f * hit_v) << 16)),
 									  __uint_as_float(hit_tri), __int_as_float(0), tmax);
 				wf.hit[item] = hit;
+				if (PRIMARY && rs.primary_cache)
+					wf.prim_cache[item] = hit_tri != 0xffffffffu ? hit_pos : 0xffffffffu;
 			}
 			else if (hit_tri == 0xffffffffu)
 			{

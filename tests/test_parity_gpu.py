@@ -164,6 +164,25 @@ def test_bvh8_refit_and_skinning_fall_back_to_the_host_refit(product_lib, oracle
     _check_hits(g, o, origins, dirs, g.trace_closest(origins, dirs), o.trace_closest(origins, dirs))
 
 
+@pytest.mark.parametrize("scene", ["cornell", "soup"])
+def test_primary_bound_cache_does_not_change_a_single_bit(product_lib, scene):
+    """A camera ray may start with the distance of the triangle its pixel hit in the previous sample as a bound (setting
+    primary_cache); the bound only prunes — the triangle is found again by the traversal — so frames are bit-identical."""
+    W, H = 160, 96
+    imgs = []
+    for cache in ("on", "off"):
+        sc = SCENES[scene]()
+        ctx = R.RenderContext(product_lib)
+        S.upload(ctx, sc, W, H)
+        ctx.set_setting("spp", 8)
+        ctx.set_setting("primary_cache", cache)
+        cam = sc.camera(W, H)
+        ctx.render_frame(cam, R.RESET)
+        ctx.render_frame(cam, R.CONVERGE)  # the second call starts with a warm cache
+        imgs.append(ctx.read_image().copy())
+    assert np.array_equal(imgs[0], imgs[1])
+
+
 def test_extend_random_rays_and_occlusion(product_lib, oracle_lib):
     (g, sc), (o, _) = make_pair(product_lib, oracle_lib, S.feature_soup, 32, 32)
     rng = np.random.default_rng(5)
