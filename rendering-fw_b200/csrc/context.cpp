@@ -178,7 +178,7 @@ struct rfwb200_context
 	bool device_ref_boxes = false; // d_ref_boxes was written by the device builder
 	int device_depth = 0;
 	DevBuf d_lbvh_scratch;
-	DevBuf d_cw_nodes, d_nodes16, d_prim_cache;
+	DevBuf d_cw_nodes, d_nodes16, d_prim_cache, d_occ_cache;
 
 	// ---- wavefront state -----------------------------------------------------------------------------
 	DevBuf d_debug;
@@ -201,7 +201,7 @@ struct rfwb200_context
 	cudaEvent_t ev_fork = nullptr;
 
 	// ---- settings / state ------------------------------------------------------------------------------
-	RenderSettings rs{2, 10.0f, 1e-5f, 1, 0, 16, nullptr, -1, 9, 0, 0, 5}; // bounces: packed nodes + unsorted connect rays; camera rays: fp32 nodes (DESIGN.md sweep) // smem_nodes 0: measured fastest on B200 (DESIGN.md "staging")
+	RenderSettings rs{2, 10.0f, 1e-5f, 1, 0, 16, nullptr, -1, 9, 1, 0, 5}; // bounces: packed nodes + unsorted connect rays; camera rays: fp32 nodes (DESIGN.md sweep) // smem_nodes 0: measured fastest on B200 (DESIGN.md "staging")
 	int spp = 1;
 	bool mode_pt = true;
 	LaunchDims dims{};
@@ -293,6 +293,9 @@ int alloc_wavefront(Ctx *c)
 	CK(c->d_prim_cache.reserve(P * sizeof(uint32_t)));
 	CK(cudaMemsetAsync(c->d_prim_cache.ptr, 0xff, P * sizeof(uint32_t), c->stream));
 	w.prim_cache = c->d_prim_cache.as<uint32_t>();
+	CK(c->d_occ_cache.reserve(2 * P * sizeof(uint32_t)));
+	CK(cudaMemsetAsync(c->d_occ_cache.ptr, 0xff, 2 * P * sizeof(uint32_t), c->stream));
+	w.occ_cache = c->d_occ_cache.as<uint32_t>();
 	w.frame = c->d_frame.as<FrameParams>();
 	w.n_acc_extra = 0;
 	while (int(c->lanes.size()) < c->n_lanes - 1)
@@ -1435,7 +1438,7 @@ extern "C"
 		else if (k == "primary_cache")
 			c->rs.primary_cache = (v == "on" || v == "1") ? 1 : 0;
 		else if (k == "shadow_cache")
-			c->rs.shadow_cache = (v == "on" || v == "1") ? 1 : 0;
+			c->rs.shadow_cache = (v == "pixel" || v == "2") ? 2 : ((v == "on" || v == "lane" || v == "1") ? 1 : 0);
 		else if (k == "primary_variant")
 		{
 			const int n = atoi(v.c_str());

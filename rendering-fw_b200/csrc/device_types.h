@@ -149,6 +149,7 @@ struct WavefrontView
 	float4 *framebuffer;		// finalised
 	DepthCounters *counters;	// [spp][MAX_DEPTH_SLOTS]
 	ProbeResult *probe;
+	uint32_t *occ_cache;		// [2][local pixels]: occluder of the pixel's previous connect ray at this depth parity (shadow_cache = 2)
 	uint32_t *prim_cache;		// per local pixel: triangle record hit by the previous camera ray of that pixel (a bound only)
 	const FrameParams *frame;
 };
@@ -165,7 +166,8 @@ struct RenderSettings
 	int debug_depth;
 	int trace_variant; // which instantiation of k_wavefront_trace runs (kernels.cu launch_trace; tuning)
 	int primary_cache; // 1: a camera ray first tests the triangle its pixel hit last time and starts with that distance as bound
-	int shadow_cache; // 1: connect rays test the occluder of the lane's previous connect ray before entering the tree
+	int shadow_cache; // connect rays first test a remembered occluder: 1 = of the lane's previous connect ray, 2 = of the same pixel's
+					  // previous connect ray at this depth (another sample); occlusion is yes/no, so frames do not change
 	int primary_variant; // the same for camera rays (coherent: fp32 nodes measured faster there than packed ones)
 };
 

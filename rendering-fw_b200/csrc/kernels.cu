@@ -573,6 +573,7 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 	// result does not depend on which occluder is found.
 	uint32_t occluder = 0xffffffffu;
 	uint32_t hit_pos = 0xffffffffu; // record position of the closest hit (camera rays: remembered per pixel)
+	uint32_t occ_slot = 0;			// where this connect ray's occluder is remembered (shadow_cache = 2)
 	bool exhausted = false; // warp-uniform: the queue has no more items
 	uint32_t acc_count = 0;
 
@@ -647,7 +648,12 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 						const float4 O4 = wf.sO[k], D4 = wf.sD[k];
 						o = mk(O4.x, O4.y, O4.z), d = mk(D4.x, D4.y, D4.z);
 						tmin = rs.geometry_epsilon, tmax = D4.w, shadow = true;
-						if (rs.shadow_cache && occluder != 0xffffffffu)
+						if (rs.shadow_cache == 2)
+						{
+							occ_slot = ((depth - 1u) & 1u) * sh.local_pixels + __float_as_uint(wf.sE[k].w);
+							occluder = wf.occ_cache[occ_slot];
+						}
+						if (rs.shadow_cache && occluder < sc.tri_count)
 						{
 							const float4 a = __ldg(tris + size_t(occluder) * 3 + 0);
 							const float4 b = __ldg(tris + size_t(occluder) * 3 + 1);
@@ -861,6 +867,8 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 								cur = SENTINEL; // any hit ends a connect ray
 								leaf1 = leaf2 = NO_LEAF;
 								occluder = first + i;
+								if (!PRIMARY && rs.shadow_cache == 2)
+									wf.occ_cache[occ_slot] = occluder;
 								break;
 							}
 						}

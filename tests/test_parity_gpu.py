@@ -106,7 +106,7 @@ def test_pt_frame_is_independent_of_staging_and_fetch_tunables(product_lib, smem
     assert np.array_equal(imgs[0], imgs[1])
 
 
-@pytest.mark.parametrize("setting,value", [("trace_variant", v) for v in (0, 1, 3, 5, 8, 10)] + [("bvh", 8), ("shadow_cache", "on")])
+@pytest.mark.parametrize("setting,value", [("trace_variant", v) for v in (0, 1, 3, 5, 8, 10)] + [("bvh", 8), ("shadow_cache", "on"), ("shadow_cache", "pixel")])
 def test_trace_kernel_variants_agree(product_lib, oracle_lib, setting, value):
     """Every instantiation of the traversal kernel (held-back leaves LQ = 1..3, unsorted node step, the compressed 8-wide
     BVH) finds the oracle's closest hits, and renders the frame of the default kernel: a different traversal order can

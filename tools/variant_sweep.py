@@ -52,5 +52,5 @@ for var in a.variants.split(";"):
                       "pixels_differing_from_first": float((np.abs(img - ref).max(axis=-1) > 0).mean()),
                       "mean": float(img[..., :3].mean()), "bvh": ctx.get_bvh_info()}), flush=True)
     for k, v in kvs:  # back to the defaults
-        ctx.set_setting(k, {"trace_variant": "9", "primary_variant": "5", "bvh": "4", "shadow_cache": "off", "primary_cache": "off"}.get(k, v))
+        ctx.set_setting(k, {"trace_variant": "9", "primary_variant": "5", "bvh": "4", "shadow_cache": "off", "primary_cache": "on"}.get(k, v))
     ctx.set_setting("primary_variant", "5")
