@@ -164,21 +164,25 @@ def test_bvh8_refit_and_skinning_fall_back_to_the_host_refit(product_lib, oracle
     _check_hits(g, o, origins, dirs, g.trace_closest(origins, dirs), o.trace_closest(origins, dirs))
 
 
+@pytest.mark.parametrize("setting,value", [("primary_cache", "off"), ("shadow_cache", "lane"), ("shadow_cache", "pixel")])
 @pytest.mark.parametrize("scene", ["cornell", "soup"])
-def test_primary_bound_cache_does_not_change_a_single_bit(product_lib, scene):
-    """A camera ray may start with the distance of the triangle its pixel hit in the previous sample as a bound (setting
-    primary_cache); the bound only prunes — the triangle is found again by the traversal — so frames are bit-identical."""
+def test_hit_caches_do_not_change_a_single_bit(product_lib, scene, setting, value):
+    """primary_cache: a camera ray may start with the distance of the triangle its pixel hit in the previous sample as a
+    bound; the bound only prunes — the triangle is found again by the traversal.  shadow_cache: a connect ray may first test
+    a remembered occluder; occlusion is a yes/no answer.  Either way frames are bit-identical to the plain traversal."""
     W, H = 160, 96
     imgs = []
-    for cache in ("on", "off"):
+    for tuned in (False, True):
         sc = SCENES[scene]()
         ctx = R.RenderContext(product_lib)
         S.upload(ctx, sc, W, H)
         ctx.set_setting("spp", 8)
-        ctx.set_setting("primary_cache", cache)
+        ctx.set_setting("primary_cache", "on"), ctx.set_setting("shadow_cache", "off")
+        if tuned:
+            ctx.set_setting(setting, value)
         cam = sc.camera(W, H)
         ctx.render_frame(cam, R.RESET)
-        ctx.render_frame(cam, R.CONVERGE)  # the second call starts with a warm cache
+        ctx.render_frame(cam, R.CONVERGE)  # the second call starts with warm caches
         imgs.append(ctx.read_image().copy())
     assert np.array_equal(imgs[0], imgs[1])
 
