@@ -1829,7 +1829,8 @@ __device__ V3 RandomPointOnLight(const SceneView &sc, float r0, float r1, V3 I, 
 // with warp-aggregated slot allocation.
 // ------------------------------------------------------------------------------------------------
 #ifndef SHADE_MINB
-#define SHADE_MINB 6 // 80 registers: measured 4.94 ms/frame vs 5.67 at 4 and 4.92 at 8 (spilling)
+#define SHADE_MINB 7 // 72 registers (162 B of spills): shade 3.37 ms/frame vs 3.45 at 6 (80 registers) and 3.44 at 5 (96); IEEE build of an
+					 // earlier kernel: 4.94 at 6, 5.67 at 4, 4.92 at 8
 #endif
 __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, const ShardView sh, const WavefrontView wf,
 											  const RenderSettings rs, const uint32_t sample_in_frame,
