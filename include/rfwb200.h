@@ -272,13 +272,17 @@ RFWB200_API int rfwb200_set_mesh_morph_weights(rfwb200_context *ctx, size_t mesh
 											   size_t weight_count);
 RFWB200_API int rfwb200_get_geometry_stats(rfwb200_context *ctx, rfwb200_geometry_stats *out);
 
-/* replaces RenderContext::set_setting (context.h:107). Keys: "spp" (samples per render_frame,
- * default 1), "mode" ("pt" wavefront path tracer | "embree" = image model of the EmbreeRT
- * backend), "max_path_length" (default 2 = settings.h:5), "clamp" (default 10, camera.h:36),
- * "smem_nodes" (BVH nodes staged in shared memory per CTA), "spatial_splits" (on|off), "sample_lanes" (1-4 concurrent samples), "fetch_threshold", "timing" (on|off: per-stage CUDA-event
- * times in get_stats), "survival_scale" (on|off, the 1/p throughput scale of Kernels.cu:783), "refit" (device|host),
- * "shade_math" (fast = the shade kernel built with -use_fast_math like the reference's CUDA backend,
- * CUDART/CMakeLists.txt:7-9 | ieee = the same kernel with IEEE division/sqrt, the arithmetic of the CPU oracle). */
+/* replaces RenderContext::set_setting (context.h:107).  Keys (DESIGN.md §7 has the measured effect of each):
+ *   spp (samples per render_frame, default 1) · mode (pt = wavefront path tracer | embree = image model of the EmbreeRT
+ *   backend) · max_path_length (default 2 = settings.h:5) · clamp (default 10, camera.h:36) · survival_scale (on|off, the 1/p
+ *   throughput scale of Kernels.cu:783) · timing (on|off: per-stage CUDA-event times in get_stats)
+ *   traversal: trace_variant / primary_variant (which instantiation of the trace kernel bounce / camera rays use) ·
+ *   primary_cache (on|off) · shadow_cache (off|lane|pixel) · fetch_threshold · sample_lanes (1-4 concurrent samples) ·
+ *   smem_nodes (BVH nodes staged in shared memory per CTA by TMA)
+ *   acceleration structure: bvh (4|8) · builder (sbvh = host SAH + spatial splits | lbvh = device) · lbvh_presplit (on|off) ·
+ *   spatial_splits (on|off) · refit (device|host)
+ *   shading arithmetic: shade_math (fast = built with -use_fast_math like the reference's CUDA backend,
+ *   CUDART/CMakeLists.txt:7-9 | ieee = the arithmetic of the CPU oracle). */
 RFWB200_API int rfwb200_set_setting(rfwb200_context *ctx, const char *key, const char *value);
 /* replaces RenderContext::get_settings (context.h:106): writes a '\n'-separated "key=v1|v2" list */
 RFWB200_API int rfwb200_get_settings(const rfwb200_context *ctx, char *buf, size_t buf_size);
