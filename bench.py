@@ -159,8 +159,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the ONE JSON line (VERSION prints a banner there); INFO etc. are respected
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")  # these levels print a version banner on stdout; keep stdout to the ONE JSON line (INFO etc. are respected)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     warmup = max(3, args.warmup)
     steps = max(1, args.steps)
