@@ -13,10 +13,16 @@
 // into oracle/_ref/librfwref.so, and tests/test_ref_pin.py checks this oracle against it (live in the build
 // container, and everywhere through the committed vectors tests/golden/ref_vectors.npz): hashes, RNG, normal
 // packing, blue noise, Disney eval/sample/pdf, Moller-Trumbore, MBVH closest/any-hit traversal, getShadingData
-// incl. trilinear texture fetch, light sampling and pick probabilities.  PINNED on reference code: those
-// building blocks.  UNPINNED (restated from source, cited line by line, no executable reference): the glue —
-// generatePrimaryRay, the shade_rays control flow, the host bounce loop, the EmbreeRT frame loop — and the BVH
-// builder (rtbvh is an un-vendored Rust crate; only the in-tree binned-SAH spec exists).
+// incl. trilinear texture fetch, light sampling and pick probabilities.  The glue is pinned as well: the same
+// directory compiles the reference's whole CUDA wavefront file, CUDART/src/Kernels.cu, for the HOST (launch syntax
+// rewritten at build time, CUDA threads run one after the other; ref_kernels_shim.cpp) into
+// oracle/_ref/librfwref_kernels.so, and test_pt_pipeline_matches_reference_cudart_kernels compares this oracle's
+// camera rays (bit-exact), primary hits, per-bounce queue sizes (identical) and accumulated image (1e-5) with it on a
+// scene that keeps D1-D6 below out of play (vectors committed as tests/golden/ref_kernels_vectors.npz).
+// PINNED on reference code: the building blocks and the PT pipeline end to end (generatePrimaryRay, intersect_rays,
+// shade_rays control flow, NEE, connect, the bounce loop).  UNPINNED (restated from source, cited line by line, no
+// executable reference): the EmbreeRT frame loop and the BVH builder (rtbvh is an un-vendored Rust crate; only the
+// in-tree binned-SAH spec exists; the trees are checked against brute force).
 //
 // Two image models are restated:
 //   PT-mode  = the wavefront estimator of backends/CUDART/src/Kernels.cu (+ getShadingData.h,
@@ -1232,11 +1238,17 @@ static vec3 EvaluateBSDF(const ShadingData &sd, const vec3 &iN, const vec3 &wo, 
 	pdf = BSDFPdf(sd, iN, wo, wi);
 	return bsdf;
 }
+// D5 switch (setting "bsdf_random_order" = ltr | rtl): C++ leaves the evaluation order of SampleBSDF's two RandomFloat(seed)
+// arguments unspecified (bsdf/disney.h:278); g++ evaluates them right to left, which is what the host-compiled reference
+// kernels of oracle/ref_build/ref_kernels_shim.cpp do, so the pin test selects rtl.
+static bool g_bsdf_randoms_right_to_left = false;
 static vec3 SampleBSDF(const ShadingData &sd, const vec3 &iN, const vec3 &T, const vec3 &B, const vec3 &wo, float t,
 					   bool backfacing, vec3 &wi, float &pdf, uint32_t &seed)
 {
-	const float r3 = RandomFloat(seed); // D5
-	const float r4 = RandomFloat(seed);
+	float r3 = RandomFloat(seed); // D5
+	float r4 = RandomFloat(seed);
+	if (g_bsdf_randoms_right_to_left) // the order a compiler that evaluates arguments right to left gives the reference
+		std::swap(r3, r4);
 	BSDFSample(sd, T, B, iN, wo, wi, pdf, r3, r4);
 	return BSDFEval(sd, iN, wo, wi, t, backfacing);
 }
@@ -2194,6 +2206,8 @@ extern "C"
 			c->clamp_value = float(atof(v.c_str()));
 		else if (k == "survival_scale")
 			c->survival_scale = (v == "on" || v == "1");
+		else if (k == "bsdf_random_order")
+			g_bsdf_randoms_right_to_left = (v == "rtl");
 		else if (k == "smem_nodes" || k == "threads")
 		{
 			if (k == "threads")
@@ -2336,6 +2350,18 @@ extern "C"
 		if (mesh >= c->meshes.size())
 			return fail("bad mesh");
 		const Bvh &b = c->meshes[mesh].bvh;
+		*n_nodes = b.mnodes.size(), *n_prims = b.prim_indices.size();
+		if (nodes_out && node_cap >= b.mnodes.size())
+			memcpy(nodes_out, b.mnodes.data(), b.mnodes.size() * sizeof(MBVHNode));
+		if (prims_out && prim_cap >= b.prim_indices.size())
+			memcpy(prims_out, b.prim_indices.data(), b.prim_indices.size() * sizeof(uint32_t));
+		return RFWB200_OK;
+	}
+	// the top-level MBVH over the instances, in the reference's node layout (for the host-compiled reference kernels)
+	ORACLE_API int rfworacle_export_tlas_mbvh(rfworacle_context *c, void *nodes_out, size_t node_cap, uint32_t *prims_out,
+											  size_t prim_cap, size_t *n_nodes, size_t *n_prims)
+	{
+		const Bvh &b = c->tlas;
 		*n_nodes = b.mnodes.size(), *n_prims = b.prim_indices.size();
 		if (nodes_out && node_cap >= b.mnodes.size())
 			memcpy(nodes_out, b.mnodes.data(), b.mnodes.size() * sizeof(MBVHNode));

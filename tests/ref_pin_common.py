@@ -303,3 +303,141 @@ def reference_soup_outputs(ref, sc, inp):
     res["li_out"] = np.array(rows, np.float32)
     res["rb_out"] = np.array([ref.random_barycentrics(float(r)) for r in inp["li_r"][:, 0]], np.float32)
     return res
+
+
+# ---- the reference's own CUDA wavefront kernels compiled for the host (oracle/ref_build/ref_kernels_shim.cpp) --------------
+REF_KERNELS_LIB = R.REPO_DIR / "oracle" / "_ref" / "librfwref_kernels.so"
+
+
+class _RefMesh(C.Structure):
+    _fields_ = [("vertices4", C.c_void_p), ("indices3", C.c_void_p), ("triangles160", C.c_void_p), ("mbvh_nodes", C.c_void_p),
+                ("prim_indices", C.c_void_p)]
+
+
+class _RefInstance(C.Structure):
+    _fields_ = [("mesh", C.c_int), ("transform", C.c_float * 16), ("inverse", C.c_float * 16), ("normal", C.c_float * 16)]
+
+
+class _RefScene(C.Structure):
+    _fields_ = [("n_meshes", C.c_int), ("meshes", C.c_void_p), ("n_instances", C.c_int), ("instances", C.c_void_p),
+                ("tlas_nodes", C.c_void_p), ("tlas_prims", C.c_void_p), ("materials192", C.c_void_p), ("uint_texels", C.c_void_p),
+                ("float_texels4", C.c_void_p), ("sky3", C.c_void_p), ("sky_w", C.c_uint), ("sky_h", C.c_uint),
+                ("n_area", C.c_uint), ("n_point", C.c_uint), ("n_spot", C.c_uint), ("n_dir", C.c_uint),
+                ("area", C.c_void_p), ("point", C.c_void_p), ("spot", C.c_void_p), ("dir", C.c_void_p), ("blue_noise", C.c_void_p)]
+
+
+def pin_scene():
+    """A flat-shaded, untextured box that keeps the oracle's documented deviations from CUDART out of play (oracle header D1-D6):
+    ONE emissive triangle whose material is material 0 (D1: the reference reads the material index where the light-triangle
+    index is meant — both are 0 here), no alpha (D2), no textures or smooth normals (D4)."""
+    s = S.Scene(name="pin-box")
+    light = S.add_material(s, (17, 12, 4))  # material 0 = the light
+    white = S.add_material(s, (0.73, 0.73, 0.73))
+    red = S.add_material(s, (0.65, 0.05, 0.05))
+    green = S.add_material(s, (0.12, 0.45, 0.15))
+    glossy = S.add_material(s, (0.8, 0.8, 0.85), roughness=0.25, metallic=0.6, specular=0.5)
+    c = 2.775
+    lp = np.array([[[2.0, 5.549, 2.0], [3.5, 5.549, 2.2], [2.6, 5.549, 3.4]]], np.float32)
+    ln = np.array([[[0, -1, 0]] * 3], np.float32)
+    ltri = S.make_triangles(lp, ln, np.zeros((1, 3, 2), np.float32), light)
+    lmesh = S.SceneMesh(np.concatenate([lp.reshape(3, 3), np.ones((3, 1), np.float32)], 1), ltri, None)
+    s.meshes = [
+        lmesh,  # mesh 0: its only triangle is area light 0
+        S.quad((0, 1, 0), (c, 0, c), 5.55, 5.55, white), S.quad((0, -1, 0), (c, 5.55, c), 5.55, 5.55, white),
+        S.quad((0, 0, -1), (c, c, 5.55), 5.55, 5.55, white), S.quad((1, 0, 0), (0, c, c), 5.55, 5.55, green),
+        S.quad((-1, 0, 0), (5.55, c, c), 5.55, 5.55, red),
+        S.box_mesh((-0.5, 0, -0.5), (0.5, 1, 0.5), white), S.box_mesh((-0.5, 0, -0.5), (0.5, 1, 0.5), glossy),
+    ]
+    I = np.eye(4)
+    s.instances = [(i, I) for i in range(6)]
+    s.instances.append((6, S.translate(1.85, 0, 1.69) @ S.rotate_y(-18) @ S.scale(1.65, 1.65, 1.65)))
+    s.instances.append((7, S.translate(3.68, 0, 3.51) @ S.rotate_y(15) @ S.scale(1.65, 3.30, 1.65)))
+    s.sky = (np.full((1, 3), 0.05, np.float32), 1, 1)
+    s.camera_pos, s.camera_dir, s.fov = (2.78, 2.73, -8.0), (0, 0, 1), 40.0
+    return s
+
+
+def reference_kernels_render(orc_ctx, sc, view14, w, h, first, count, clamp=10.0):
+    """Run the reference's host-compiled CUDA kernels on the scene `sc` (already uploaded to the oracle context `orc_ctx`, whose
+    MBVHs are exported in the reference's node layout).  -> dict(acc (h,w,4), origins, directions, states (w*h,4), counters)"""
+    lib = C.CDLL(str(REF_KERNELS_LIB))
+    P = C.c_void_p
+    exp_mesh = orc_ctx.L.fn("export_mesh_mbvh", C.c_int, [P, C.c_size_t, P, C.c_size_t, P, C.c_size_t, P, P])
+    exp_tlas = orc_ctx.L.fn("export_tlas_mbvh", C.c_int, [P, P, C.c_size_t, P, C.c_size_t, P, P])
+    keep = []
+
+    def arr(a, dt):
+        a = np.ascontiguousarray(a, dt)
+        keep.append(a)
+        return a.ctypes.data
+
+    meshes = (_RefMesh * len(sc.meshes))()
+    for mi, m in enumerate(sc.meshes):
+        nn, npm = C.c_size_t(), C.c_size_t()
+        exp_mesh(orc_ctx._h, mi, None, 0, None, 0, C.byref(nn), C.byref(npm))
+        nodes, prims = np.zeros(nn.value * 32, np.float32), np.zeros(max(npm.value, 1), np.uint32)
+        exp_mesh(orc_ctx._h, mi, nodes.ctypes.data, nn.value, prims.ctypes.data, npm.value, C.byref(nn), C.byref(npm))
+        keep += [nodes, prims]
+        meshes[mi].vertices4 = arr(m.vertices, np.float32)
+        meshes[mi].indices3 = None if m.indices is None else arr(m.indices, np.uint32)
+        meshes[mi].triangles160 = arr(m.triangles, R.TRIANGLE_DTYPE)
+        meshes[mi].mbvh_nodes, meshes[mi].prim_indices = nodes.ctypes.data, prims.ctypes.data
+    insts = (_RefInstance * len(sc.instances))()
+    for ii, (mi, M) in enumerate(sc.instances):
+        M = np.asarray(M, np.float64).reshape(4, 4)
+        nm = np.eye(4)
+        nm[:3, :3] = np.linalg.inv(M[:3, :3]).T
+        insts[ii].mesh = mi
+        for name, mat in (("transform", M), ("inverse", np.linalg.inv(M)), ("normal", nm)):
+            col_major = mat.T.reshape(-1).astype(np.float32)
+            getattr(insts[ii], name)[:] = [float(x) for x in col_major]
+    nn, npm = C.c_size_t(), C.c_size_t()
+    exp_tlas(orc_ctx._h, None, 0, None, 0, C.byref(nn), C.byref(npm))
+    tnodes, tprims = np.zeros(nn.value * 32, np.float32), np.zeros(max(npm.value, 1), np.uint32)
+    exp_tlas(orc_ctx._h, tnodes.ctypes.data, nn.value, tprims.ctypes.data, npm.value, C.byref(nn), C.byref(npm))
+    mats, pool = patched_materials(sc)
+    rs = _RefScene()
+    rs.n_meshes, rs.meshes, rs.n_instances, rs.instances = len(sc.meshes), C.addressof(meshes), len(sc.instances), C.addressof(insts)
+    rs.tlas_nodes, rs.tlas_prims = tnodes.ctypes.data, tprims.ctypes.data
+    rs.materials192 = arr(mats, R.MATERIAL_DTYPE)
+    rs.uint_texels = arr(pool if len(pool) else np.zeros(4, np.uint32), np.uint32)
+    rs.float_texels4 = arr(np.zeros(4, np.float32), np.float32)
+    sky, sw, sh = sc.sky
+    rs.sky3, rs.sky_w, rs.sky_h = arr(np.asarray(sky, np.float32).reshape(-1, 3), np.float32), sw, sh
+    for name, lights, dt in (("area", sc.area_lights, R.AREA_LIGHT_DTYPE), ("point", sc.point_lights, R.POINT_LIGHT_DTYPE),
+                             ("spot", sc.spot_lights, R.SPOT_LIGHT_DTYPE), ("dir", sc.dir_lights, R.DIR_LIGHT_DTYPE)):
+        setattr(rs, "n_" + name, len(lights))
+        setattr(rs, name, arr(lights if len(lights) else np.zeros(1, dt), dt))
+    rs.blue_noise = arr(blue_noise_uint_table(), np.uint32)
+    n = w * h
+    acc, o, d, st = (np.zeros((n, 4), np.float32) for _ in range(4))
+    counters = np.zeros((count, 8, 3), np.uint32)
+    f = lib.rfwref_cudart_render
+    f.restype, f.argtypes = C.c_int, [P, P, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_float, P, P, P, P, P]
+    v = np.ascontiguousarray(view14, np.float32)
+    rc = f(C.addressof(rs), v.ctypes.data, w, h, first, count, clamp, acc.ctypes.data, o.ctypes.data, d.ctypes.data, st.ctypes.data,
+           counters.ctypes.data)
+    assert rc == 0
+    return {"acc": acc.reshape(h, w, 4), "origins": o, "directions": d, "states": st, "counters": counters}
+
+
+def pin_cases():
+    """name -> (width, height, first sample, sample count, lens aperture).  'lens' has a wide lens (the blade sampling of
+    generatePrimaryRay) at a packet-aligned size; 'long' crosses sample 256, where shade_rays switches from the blue-noise table
+    to RandomFloat(seed) for the light sample, at a size that is not a multiple of the 8x8 / 64 / 128 launch shapes."""
+    return {"lens": (64, 48, 0, 4, 0.12), "long": (70, 50, 0, 260, 0.0)}
+
+
+def pin_view14(sc, w, h, aperture):
+    cam = sc.camera(w, h)
+    cam.aperture, cam.focalDistance = np.float32(aperture), np.float32(10.5)
+    v = cam.get_view()
+    return np.array(list(v.pos) + list(v.p1) + list(v.p2) + list(v.p3) + [v.aperture, v.spread_angle], np.float32)
+
+
+def view_from14(v14):
+    view = R.CameraView()
+    for i in range(3):
+        view.pos[i], view.p1[i], view.p2[i], view.p3[i] = float(v14[i]), float(v14[3 + i]), float(v14[6 + i]), float(v14[9 + i])
+    view.aperture, view.spread_angle = float(v14[12]), float(v14[13])
+    return view
