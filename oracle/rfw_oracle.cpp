@@ -46,8 +46,11 @@
 //   D4 barycentrics are the weights of vertex1/vertex2 (Embree/OptiX convention,
 //      OptiX6Context/assets/kernels/getShadingData.h:167,183-184);
 //   D5 SampleBSDF's two RandomFloat(seed) arguments are drawn left to right (r3 then r4);
-//      the C++ order is unspecified (bsdf/disney.h:278);
+//      the C++ order is unspecified (bsdf/disney.h:278) — left to right is what nvcc compiles
+//      (tests/test_ref_pin.py::test_nvcc_draws_samplebsdf_randoms_left_to_right), so this is the
+//      reference's behaviour on a GPU; "bsdf_random_order"=rtl gives g++'s order;
 //   D6 float->int conversions saturate (CUDA semantics) where the operand can be inf/NaN.
+// D1 and D4 can be undone with the setting "cudart_conventions"=on (the pin test's "rich" case).
 // E-mode determinism contract (the reference's shared xor128 is a data race):
 //   r0..r3 of pixel p, sample s = first four outputs of xor128 with
 //   x = 123456789 ^ WangHash(p*16789 + s*1791), y,z,w = reference defaults; shadow rays use
@@ -658,6 +661,12 @@ inline MBVHHit intersect_quad_node(const MBVHNode &n, const vec3 &org, const vec
 	return hit;
 }
 
+// D1 / D4 switch (setting "cudart_conventions" = off | on).  "on" follows CUDART to the letter where the default follows
+// the reference's newer backends: barycentrics are the area ratios of CUDAIntersect.h:82-87 (weights of vertex0, vertex1)
+// and getShadingData.h:123,140-141 weights vertex 0,1,2 with u,v,w; the light index of the MIS pick probability is the
+// material index (device_structs.h:37).  Used by the pin test against the reference's host-compiled kernels.
+static bool g_cudart_conventions = false;
+
 // CUDAIntersect.h:48-94 intersect_triangle (Moller-Trumbore); D4: barycentrics returned are the
 // Moller-Trumbore u,v (weights of vertex1, vertex2) instead of the area ratios of :82-87.
 inline bool intersect_triangle(const vec3 &org, const vec3 &dir, float tmin, float *rayt, const vec3 &p0, const vec3 &p1,
@@ -680,7 +689,16 @@ inline bool intersect_triangle(const vec3 &org, const vec3 &dir, float tmin, flo
 	const float t = f * dot(e2, q);
 	if (t > tmin && *rayt > t)
 	{
-		if (bary)
+		if (bary && g_cudart_conventions) // :82-87
+		{
+			const vec3 p = org + dir * t;
+			const vec3 N = normalize(cross(e1, e2));
+			const float areaABC = dot(N, cross(e1, e2));
+			const float areaPBC = dot(N, cross(p1 - p, p2 - p));
+			const float areaPCA = dot(N, cross(p2 - p, p0 - p));
+			*bary = {areaPBC / areaABC, areaPCA / areaABC};
+		}
+		else if (bary)
 			*bary = {u, v};
 		*rayt = t;
 		return true;
@@ -1319,7 +1337,7 @@ static ShadingData getShadingData(const Ctx &c, const vec3 &D, float u, float v,
 	N = vec3(tri.Nx, tri.Ny, tri.Nz);
 	iN = N;
 	if (has_flag(flags, HasSmoothNormals))
-		iN = normalize(n0 * w + n1 * u + n2 * v);
+		iN = g_cudart_conventions ? normalize(n0 * u + n1 * v + n2 * w) : normalize(n0 * w + n1 * u + n2 * v);
 	N = normalize(invT.mul(N));
 	iN = normalize(invT.mul(iN));
 	createTangentSpace(iN, T, B);
@@ -1330,6 +1348,8 @@ static ShadingData getShadingData(const Ctx &c, const vec3 &D, float u, float v,
 	{
 		tu = w * tri.u0 + u * tri.u1 + v * tri.u2;
 		tv = w * tri.v0 + u * tri.v1 + v * tri.v2;
+		if (g_cudart_conventions)
+			tu = u * tri.u0 + v * tri.u1 + w * tri.u2, tv = u * tri.v0 + v * tri.v1 + w * tri.v2;
 	}
 	if (has_flag(flags, HasDiffuseMap))
 	{
@@ -1722,7 +1742,7 @@ static void shade_path(Ctx &c, const rfwb200_camera_view &view, const PathState 
 			{
 				const vec3 lastN = UnpackNormal(f2u(D4.w));
 				const float lightPdf = CalculateLightPDF(D, hitData.w, triangle.area, N);
-				const int triangleIdx = triangle.light_tri_idx; // D1
+				const int triangleIdx = g_cudart_conventions ? int(triangle.material) : triangle.light_tri_idx; // D1
 				const float pickProb = LightPickProb(c, triangleIdx, O, lastN, I);
 				if ((bsdfPdf + lightPdf * pickProb) <= 0)
 					return;
@@ -2208,6 +2228,8 @@ extern "C"
 			c->survival_scale = (v == "on" || v == "1");
 		else if (k == "bsdf_random_order")
 			g_bsdf_randoms_right_to_left = (v == "rtl");
+		else if (k == "cudart_conventions")
+			g_cudart_conventions = (v == "on" || v == "1");
 		else if (k == "smem_nodes" || k == "threads")
 		{
 			if (k == "threads")

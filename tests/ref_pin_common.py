@@ -326,24 +326,40 @@ class _RefScene(C.Structure):
                 ("area", C.c_void_p), ("point", C.c_void_p), ("spot", C.c_void_p), ("dir", C.c_void_p), ("blue_noise", C.c_void_p)]
 
 
-def pin_scene():
-    """A flat-shaded, untextured box that keeps the oracle's documented deviations from CUDART out of play (oracle header D1-D6):
-    ONE emissive triangle whose material is material 0 (D1: the reference reads the material index where the light-triangle
-    index is meant — both are 0 here), no alpha (D2), no textures or smooth normals (D4)."""
-    s = S.Scene(name="pin-box")
+def pin_scene(rich=False):
+    """A box that keeps the oracle's documented deviations from CUDART out of play (oracle header D1-D6).
+    rich=False: ONE emissive triangle whose material is material 0 (D1: the reference reads the material index where the
+    light-triangle index is meant — both are 0 here), no alpha (D2), untextured, flat normals.
+    rich=True adds what the oracle setting cudart_conventions=on covers: a two-triangle light (material 0 < light count, so the
+    reference's potential[material] is a defined value), an indexed, bumpy, diffuse- and normal-mapped floor with smooth
+    normals (trilinear fetch, LOD, texture coordinates and normals from the reference's area-ratio barycentrics), a smooth
+    textured column and a second, instanced and scaled copy of it."""
+    s = S.Scene(name="pin-box-rich" if rich else "pin-box")
     light = S.add_material(s, (17, 12, 4))  # material 0 = the light
     white = S.add_material(s, (0.73, 0.73, 0.73))
     red = S.add_material(s, (0.65, 0.05, 0.05))
     green = S.add_material(s, (0.12, 0.45, 0.15))
     glossy = S.add_material(s, (0.8, 0.8, 0.85), roughness=0.25, metallic=0.6, specular=0.5)
     c = 2.775
-    lp = np.array([[[2.0, 5.549, 2.0], [3.5, 5.549, 2.2], [2.6, 5.549, 3.4]]], np.float32)
-    ln = np.array([[[0, -1, 0]] * 3], np.float32)
-    ltri = S.make_triangles(lp, ln, np.zeros((1, 3, 2), np.float32), light)
-    lmesh = S.SceneMesh(np.concatenate([lp.reshape(3, 3), np.ones((3, 1), np.float32)], 1), ltri, None)
+    if rich:
+        lmesh = S.quad((0, -1, 0), (2.78, 5.549, 2.6), 1.5, 1.2, light)
+    else:
+        lp = np.array([[[2.0, 5.549, 2.0], [3.5, 5.549, 2.2], [2.6, 5.549, 3.4]]], np.float32)
+        ln = np.array([[[0, -1, 0]] * 3], np.float32)
+        ltri = S.make_triangles(lp, ln, np.zeros((1, 3, 2), np.float32), light)
+        lmesh = S.SceneMesh(np.concatenate([lp.reshape(3, 3), np.ones((3, 1), np.float32)], 1), ltri, None)
+    floor = S.quad((0, 1, 0), (c, 0, c), 5.55, 5.55, white)
+    if rich:
+        t0 = S.add_texture_rgba8(s, S.checker_texture(64, 5))
+        n0 = S.add_texture_rgba8(s, S.normal_texture(64, 6))
+        t1 = S.add_texture_rgba8(s, S.checker_texture(32, 9))
+        tiles = S.add_material(s, (0.9, 0.9, 0.9), roughness=0.7, tex0=t0, nmap0=n0, uvscale=(1.0, 1.0))
+        column = S.add_material(s, (0.85, 0.8, 0.7), roughness=0.45, specular=0.3, tex0=t1)
+        floor = S._grid_quad((0, 0, 0), (0, 0, 5.55), (5.55, 0, 0), 6, 6, tiles, uv_rep=3.0, tex_dims=(64, 64), bump=0.06,
+                             rng=np.random.default_rng(3))
     s.meshes = [
-        lmesh,  # mesh 0: its only triangle is area light 0
-        S.quad((0, 1, 0), (c, 0, c), 5.55, 5.55, white), S.quad((0, -1, 0), (c, 5.55, c), 5.55, 5.55, white),
+        lmesh,  # mesh 0: its triangles are the area lights
+        floor, S.quad((0, -1, 0), (c, 5.55, c), 5.55, 5.55, white),
         S.quad((0, 0, -1), (c, c, 5.55), 5.55, 5.55, white), S.quad((1, 0, 0), (0, c, c), 5.55, 5.55, green),
         S.quad((-1, 0, 0), (5.55, c, c), 5.55, 5.55, red),
         S.box_mesh((-0.5, 0, -0.5), (0.5, 1, 0.5), white), S.box_mesh((-0.5, 0, -0.5), (0.5, 1, 0.5), glossy),
@@ -352,6 +368,10 @@ def pin_scene():
     s.instances = [(i, I) for i in range(6)]
     s.instances.append((6, S.translate(1.85, 0, 1.69) @ S.rotate_y(-18) @ S.scale(1.65, 1.65, 1.65)))
     s.instances.append((7, S.translate(3.68, 0, 3.51) @ S.rotate_y(15) @ S.scale(1.65, 3.30, 1.65)))
+    if rich:
+        s.meshes.append(S._cylinder((0, 0, 0), 0.35, 2.2, 14, 6, column, tex_dims=(32, 32)))
+        s.instances.append((8, S.translate(4.4, 0.02, 1.1)))
+        s.instances.append((8, S.translate(1.0, 0.02, 3.9) @ S.rotate_y(40) @ S.scale(1.4, 0.7, 0.9)))
     s.sky = (np.full((1, 3), 0.05, np.float32), 1, 1)
     s.camera_pos, s.camera_dir, s.fov = (2.78, 2.73, -8.0), (0, 0, 1), 40.0
     return s
@@ -425,7 +445,7 @@ def pin_cases():
     """name -> (width, height, first sample, sample count, lens aperture).  'lens' has a wide lens (the blade sampling of
     generatePrimaryRay) at a packet-aligned size; 'long' crosses sample 256, where shade_rays switches from the blue-noise table
     to RandomFloat(seed) for the light sample, at a size that is not a multiple of the 8x8 / 64 / 128 launch shapes."""
-    return {"lens": (64, 48, 0, 4, 0.12), "long": (70, 50, 0, 260, 0.0)}
+    return {"lens": (64, 48, 0, 4, 0.12), "long": (70, 50, 0, 260, 0.0), "rich": (72, 56, 0, 8, 0.05)}
 
 
 def pin_view14(sc, w, h, aperture):

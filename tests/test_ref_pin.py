@@ -235,7 +235,7 @@ def test_emode_generate_matches_reference_generate_from_view(oracle_lib):
 GK = dict(np.load(Path(__file__).resolve().parent / "golden" / "ref_kernels_vectors.npz"))
 
 
-@pytest.mark.parametrize("case", ["lens", "long"])
+@pytest.mark.parametrize("case", ["lens", "long", "rich"])
 def test_pt_pipeline_matches_reference_cudart_kernels(oracle_lib, case):
     """The oracle end to end — blue-noise camera rays with the lens, two-level MBVH extend, shade_rays control flow (sky,
     emissive termination with MIS, NEE with the blue-noise / RandomFloat switch at sample 256, BSDF sampling, postponed pdf),
@@ -245,13 +245,18 @@ def test_pt_pipeline_matches_reference_cudart_kernels(oracle_lib, case):
     left, so the oracle is told to draw them in that order.
     Bars: camera-ray origins / directions and path ids bit-exact; hit triangle and instance identical, distance within
     2e-6 relative; queue sizes per bounce identical over all samples; accumulated radiance within 1e-5 relative per pixel for
-    all but 0.1 % of the pixels (a last-bit difference can flip one branch of one sample), 1e-3 for those."""
+    all but 0.1 % of the pixels (a last-bit difference can flip one branch of one sample), 1e-3 for those.
+    Case "rich" adds a two-triangle light, an indexed bumpy floor with diffuse and normal maps, smooth textured columns and a
+    scaled instance, with the oracle following CUDART's own barycentric and light-index conventions
+    (cudart_conventions=on, D1 / D4); with the oracle's default conventions the same image differs from the reference's by
+    more than 1e-3 relative in under 1 % of the pixels, which bounds what those two deviations are worth."""
     from ref_pin_common import pin_cases, pin_scene, pin_view14, view_from14
 
     w, h, first, count, aperture = pin_cases()[case]
-    sc = pin_scene()
+    sc = pin_scene(rich=(case == "rich"))
     o = R.RenderContext(oracle_lib)
     S.upload(o, sc, w, h)
+    o.set_setting("cudart_conventions", "on" if case == "rich" else "off")
     v14 = pin_view14(sc, w, h, aperture)
     view = view_from14(v14)
     origins, dirs = o.generate_primary(view, first)
@@ -274,7 +279,7 @@ def test_pt_pipeline_matches_reference_cudart_kernels(oracle_lib, case):
     o.render_frame(view, R.RESET)
     img = o.read_image()
     ref = GK[case + "_acc"] / np.float32(count)
-    assert 0.2 < ref[..., :3].mean() < 0.6
+    assert 0.2 < ref[..., :3].mean() < 0.8
     err = (np.abs(img[..., :3] - ref[..., :3]) / (1.0 + np.abs(ref[..., :3]))).max(-1)
     assert (err > 1e-5).mean() <= 1e-3 and err.max() < 1e-3, (float((err > 1e-5).mean()), float(err.max()))
     # queue sizes: extension rays written and shadow rays queued, summed over bounces and samples (Counters of Kernels.cu)
@@ -284,7 +289,13 @@ def test_pt_pipeline_matches_reference_cudart_kernels(oracle_lib, case):
     assert fc["n_ext_out"] == cnt[:, :, 0].sum()
     # shadow rays queued by the shade pass of the last bounce are never traced: the host loop ends first (Context.cpp:109-116)
     assert fc["n_nee"] == cnt[:, :2, 1].sum() and cnt[:, 2, 1].sum() > 0
-    o.set_setting("bsdf_random_order", "ltr")  # global of the oracle library: restore the default
+    if case == "rich":
+        o.set_setting("cudart_conventions", "off")
+        o.render_frame(view, R.RESET)
+        err = (np.abs(o.read_image()[..., :3] - ref[..., :3]) / (1.0 + np.abs(ref[..., :3]))).max(-1)
+        assert (err > 1e-3).mean() < 0.01 and err.max() < 0.05, (float((err > 1e-3).mean()), float(err.max()))
+    o.set_setting("bsdf_random_order", "ltr")  # globals of the oracle library: restore the defaults
+    o.set_setting("cudart_conventions", "off")
 
 
 @pytest.mark.skipif(not (Path(R.REPO_DIR) / "oracle" / "_ref" / "librfwref_kernels.so").exists(),
@@ -299,3 +310,32 @@ def test_stored_kernel_vectors_are_what_the_live_reference_kernels_produce(oracl
     live = reference_kernels_render(o, sc, pin_view14(sc, w, h, aperture), w, h, first, count)
     for key in ("acc", "origins", "directions", "states", "counters"):
         assert np.array_equal(live[key].view(np.uint32), GK["lens_" + key].view(np.uint32)), key
+
+
+def test_nvcc_draws_samplebsdf_randoms_left_to_right(tmp_path):
+    """D5: `SampleBSDF(..., RandomFloat(seed), RandomFloat(seed))` (bsdf/disney.h:278) leaves the order of the two draws to the
+    compiler.  The reference runs as nvcc-compiled device code, so what counts is nvcc's order: the first PARAMETER receives the
+    first draw (left to right) — the oracle's and the CUDA kernels' default.  (g++ goes right to left, which is why the
+    host-compiled reference kernels above are compared under bsdf_random_order=rtl.)  Checked on constant-folded PTX."""
+    import re
+    import shutil
+    import subprocess
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not Path(nvcc).exists():
+        pytest.skip("nvcc not found")
+    src = tmp_path / "order.cu"
+    src.write_text("""
+typedef unsigned uint;
+__device__ uint RandomInt(uint &s) { s ^= s << 13; s ^= s >> 17; s ^= s << 5; return s; }
+__device__ float RandomFloat(uint &s) { return RandomInt(s) * 2.3283064365387e-10f; }
+__device__ __forceinline__ void two(float first_param, float second_param, float *out) { out[0] = first_param, out[1] = second_param; }
+__global__ void k(float *out) { uint seed = 0x12345u; two(RandomFloat(seed), RandomFloat(seed), out); }
+""")
+    ptx = subprocess.run([nvcc, "-arch=sm_100a", "-ptx", "-o", "-", str(src)], check=True, capture_output=True, text=True).stdout
+    consts = {m.group(1): int(m.group(2)) for m in re.finditer(r"mov\.b32\s+(%r\d+), (\d+);", ptx)}
+    stores = {m.group(1) or "+0": consts[m.group(2)] for m in re.finditer(r"st\.global\.u32\s+\[%rd\d+(\+\d+)?\], (%r\d+);", ptx)}
+    orc = OracleScalar()
+    draws = orc.random_stream(0x12345, 2)  # RandomInt stream of the oracle (pinned bit for bit above)
+    first, second = (int((np.float32(d) * np.float32(2.3283064365387e-10)).view(np.uint32)) for d in draws)
+    assert stores == {"+0": first, "+4": second}
