@@ -377,10 +377,9 @@ def pin_scene(rich=False):
     return s
 
 
-def reference_kernels_render(orc_ctx, sc, view14, w, h, first, count, clamp=10.0):
-    """Run the reference's host-compiled CUDA kernels on the scene `sc` (already uploaded to the oracle context `orc_ctx`, whose
-    MBVHs are exported in the reference's node layout).  -> dict(acc (h,w,4), origins, directions, states (w*h,4), counters)"""
-    lib = C.CDLL(str(REF_KERNELS_LIB))
+def reference_kernels_scene(orc_ctx, sc):
+    """Marshal the scene `sc` (already uploaded to the oracle context `orc_ctx`, whose MBVHs are exported in the reference's node
+    layout) for the reference's host-compiled kernels.  -> (RefScene struct, objects that own its memory)"""
     P = C.c_void_p
     exp_mesh = orc_ctx.L.fn("export_mesh_mbvh", C.c_int, [P, C.c_size_t, P, C.c_size_t, P, C.c_size_t, P, P])
     exp_tlas = orc_ctx.L.fn("export_tlas_mbvh", C.c_int, [P, P, C.c_size_t, P, C.c_size_t, P, P])
@@ -429,16 +428,86 @@ def reference_kernels_render(orc_ctx, sc, view14, w, h, first, count, clamp=10.0
         setattr(rs, "n_" + name, len(lights))
         setattr(rs, name, arr(lights if len(lights) else np.zeros(1, dt), dt))
     rs.blue_noise = arr(blue_noise_uint_table(), np.uint32)
+    keep += [meshes, insts, tnodes, tprims]
+    return rs, keep
+
+
+def reference_kernels_run(rs, view14, w, h, first, count, clamp=10.0, want_rays=True):
+    """Render samples [first, first + count) with the reference's host-compiled kernels.
+    -> dict(acc (h,w,4), origins, directions, states (w*h,4) of sample `first`, counters (count, 8, 3))"""
+    lib = C.CDLL(str(REF_KERNELS_LIB))
+    P = C.c_void_p
     n = w * h
-    acc, o, d, st = (np.zeros((n, 4), np.float32) for _ in range(4))
+    acc = np.zeros((n, 4), np.float32)
+    o, d, st = ((np.zeros((n, 4), np.float32) for _ in range(3)) if want_rays else (None, None, None))
     counters = np.zeros((count, 8, 3), np.uint32)
     f = lib.rfwref_cudart_render
     f.restype, f.argtypes = C.c_int, [P, P, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_float, P, P, P, P, P]
     v = np.ascontiguousarray(view14, np.float32)
-    rc = f(C.addressof(rs), v.ctypes.data, w, h, first, count, clamp, acc.ctypes.data, o.ctypes.data, d.ctypes.data, st.ctypes.data,
-           counters.ctypes.data)
+    ptr = lambda a: None if a is None else a.ctypes.data  # noqa: E731
+    rc = f(C.addressof(rs), v.ctypes.data, w, h, first, count, clamp, acc.ctypes.data, ptr(o), ptr(d), ptr(st), counters.ctypes.data)
     assert rc == 0
     return {"acc": acc.reshape(h, w, 4), "origins": o, "directions": d, "states": st, "counters": counters}
+
+
+def reference_kernels_render(orc_ctx, sc, view14, w, h, first, count, clamp=10.0):
+    rs, keep = reference_kernels_scene(orc_ctx, sc)
+    return reference_kernels_run(rs, view14, w, h, first, count, clamp)
+
+
+def reference_kernels_timed(rs, view14, w, h, spp, procs, timeout_s=240.0):
+    """Time the reference's host-compiled kernels on `spp` samples of a w x h frame, the samples dealt round-robin to `procs`
+    forked processes (the kernels keep their state in globals, so a process is the unit of parallelism; samples of a frame are
+    independent given the sample index).  -> (seconds = slowest process, mean radiance of the frame as a sanity value)"""
+    import os
+    import struct
+    import time
+
+    procs = max(1, min(procs, spp))
+    pipes = []
+    for k in range(procs):
+        r, wfd = os.pipe()
+        pid = os.fork()
+        if pid == 0:
+            code = 1
+            try:
+                os.close(r)
+                t0, total = time.perf_counter(), 0.0
+                for s_ in range(k, spp, procs):
+                    total += float(reference_kernels_run(rs, view14, w, h, s_, 1, want_rays=False)["acc"][..., :3].sum(dtype=np.float64))
+                os.write(wfd, struct.pack("dd", time.perf_counter() - t0, total))
+                code = 0
+            finally:
+                os._exit(code)
+        os.close(wfd)
+        pipes.append((pid, r))
+    import select
+    import signal
+
+    secs, total, deadline, failed = 0.0, 0.0, time.monotonic() + timeout_s, False
+    for pid, r in pipes:
+        buf = b""
+        while len(buf) < 16 and not failed:
+            ready, _, _ = select.select([r], [], [], max(0.0, deadline - time.monotonic()))
+            if not ready:
+                failed = True  # out of time: stop waiting, the workers are killed below (by their exact pids)
+                break
+            chunk = os.read(r, 16 - len(buf))
+            if not chunk:
+                break
+            buf += chunk
+        os.close(r)
+        if failed:
+            os.kill(pid, signal.SIGKILL)
+        _, status = os.waitpid(pid, 0)
+        if failed or status != 0 or len(buf) < 16:
+            failed = True
+            continue
+        dt, tot = struct.unpack("dd", buf)
+        secs, total = max(secs, dt), total + tot
+    if failed:
+        raise RuntimeError("a reference-kernel worker failed or timed out")
+    return secs, total / (spp * w * h * 3)
 
 
 def pin_cases():

@@ -339,3 +339,21 @@ __global__ void k(float *out) { uint seed = 0x12345u; two(RandomFloat(seed), Ran
     draws = orc.random_stream(0x12345, 2)  # RandomInt stream of the oracle (pinned bit for bit above)
     first, second = (int((np.float32(d) * np.float32(2.3283064365387e-10)).view(np.uint32)) for d in draws)
     assert stores == {"+0": first, "+4": second}
+
+
+@pytest.mark.skipif(not (Path(R.REPO_DIR) / "oracle" / "_ref" / "librfwref_kernels.so").exists(),
+                    reason="oracle/_ref is only built where /root/reference exists")
+def test_reference_kernels_sample_parallel_timing_helper(oracle_lib):
+    """bench.py's `reference_kernels_on_host` leg: samples dealt to forked processes give the frame the serial run gives, and a
+    worker that exceeds the time limit is killed and reported instead of hanging the bench."""
+    from ref_pin_common import pin_cases, pin_scene, pin_view14, reference_kernels_scene, reference_kernels_timed
+
+    w, h, first, count, aperture = pin_cases()["lens"]
+    sc = pin_scene()
+    o = R.RenderContext(oracle_lib)
+    S.upload(o, sc, w, h)
+    rs, keep = reference_kernels_scene(o, sc)
+    secs, mean = reference_kernels_timed(rs, pin_view14(sc, w, h, aperture), w, h, count, 2)
+    assert secs > 0 and abs(mean - float(GK["lens_acc"][..., :3].mean(dtype=np.float64)) / count) < 1e-6
+    with pytest.raises(RuntimeError):
+        reference_kernels_timed(rs, pin_view14(sc, 512, 512, aperture), 512, 512, 64, 2, timeout_s=0.05)
