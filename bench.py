@@ -363,15 +363,8 @@ def main():
         cpu = {"value": w * h * SPP / dt / 1e6, "unit": "Msamples/s", "cores": int(olib.fn("num_threads", ctypes.c_int, [])()),
                "kind": "port", "sample": f"{w}x{h} x {SPP} spp (one whole frame of the workload), {dt:.1f} s",
                "note": "CPU restatement of the reference's wavefront estimator (oracle/); the reference's Embree backend is not a "
-                       "path tracer and cannot be built here (DESIGN.md)"}
-        ref_kernels = reference_kernels_on_host(octx, osc)
-        if ref_kernels:
-            if ref_kernels.get("value", 0.0) > cpu["value"]:  # report the stronger CPU baseline, keep the other beside it
-                port = dict(cpu)
-                cpu = {k: ref_kernels[k] for k in ("value", "unit", "cores", "kind", "sample", "note")}
-                cpu["oracle_port"] = port
-            else:
-                cpu["reference_kernels_on_host"] = ref_kernels
+                       "path tracer and cannot be built here (DESIGN.md); `--impl reference` also times the reference's own "
+                       "Kernels.cu compiled for the host (no fork from this CUDA process)"}
 
     if rank == 0:
         bvh = ctx.get_bvh_info()
