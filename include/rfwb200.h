@@ -300,6 +300,20 @@ RFWB200_API void *rfwb200_device_framebuffer(rfwb200_context *ctx);
 RFWB200_API size_t rfwb200_local_pixel_count(const rfwb200_context *ctx);
 /* blocking copy of the finalised framebuffer to host memory (float4 per local pixel) */
 RFWB200_API int rfwb200_read_framebuffer(rfwb200_context *ctx, float *host_rgba, size_t capacity_pixels);
+/* replaces the display pass of rfw::system::render_frame(camera, status, toneMap = true) (system/src/rfw/system.cpp:694-713
+ * running assets/shaders/tone-map.frag over the render target): rgb' = ACESFitted(max(0, rgb - 0.5*contrast + 0.5 +
+ * brightness)) with camera.contrast / camera.brightness (context/camera.h), alpha passed through, packed to RGBA8 (round
+ * to nearest). Source: `device_rgba32f` (float4 per pixel, e.g. the image assembled from shards) or, when null, the
+ * context's finalised framebuffer (then `pixels` is ignored). Destination: `device_rgba8` or, when null, a buffer of the
+ * context (rfwb200_device_display). Rows keep the framebuffer's order (the shader's UV flip belongs to the GL quad).
+ * Asynchronous on the context's stream. */
+RFWB200_API int rfwb200_tone_map(rfwb200_context *ctx, float contrast, float brightness, const void *device_rgba32f,
+                                 void *device_rgba8, size_t pixels);
+RFWB200_API void *rfwb200_device_display(rfwb200_context *ctx);
+/* rfwb200_tone_map of the context's framebuffer + blocking copy of the RGBA8 result to host memory (4 bytes per local pixel:
+ * a quarter of the read_framebuffer traffic for a consumer that only displays) */
+RFWB200_API int rfwb200_read_display(rfwb200_context *ctx, float contrast, float brightness, uint8_t *host_rgba8,
+                                     size_t capacity_pixels);
 /* scatter `world` gathered tile-major shards (as produced by an all-gather of
  * rfwb200_device_framebuffer buffers, each padded to rfwb200_shard_stride pixels) into one
  * row-major image; all pointers are device pointers. */

@@ -183,6 +183,7 @@ struct rfwb200_context
 	// ---- wavefront state -----------------------------------------------------------------------------
 	DevBuf d_debug;
 	DevBuf d_O[2], d_D[2], d_T[2], d_hit, d_sO, d_sD, d_sE, d_acc, d_fb, d_counters, d_probe, d_frame, d_scratch_cursor;
+	DevBuf d_display; // RGBA8 output of the tone-map pass (rfwb200_read_display), allocated on first use
 	WavefrontView wf{};
 	uint32_t counters_capacity_spp = 0;
 	// Sample lanes: sample s of a frame runs on lane s % n_lanes.  Lane 0 is the caller's stream and the buffers above;
@@ -1621,6 +1622,45 @@ extern "C"
 		const size_t n = rfwb200_local_pixel_count(c);
 		REQUIRE(capacity_pixels >= n, "host buffer too small");
 		CK(cudaMemcpyAsync(host_rgba, c->d_fb.ptr, n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+		return RFWB200_OK;
+	}
+
+	int rfwb200_tone_map(rfwb200_context *c, float contrast, float brightness, const void *device_rgba32f, void *device_rgba8,
+						 size_t pixels)
+	{
+		REQUIRE(c != nullptr, "context is null");
+		if (int r = ensure_device(c))
+			return r;
+		const float4 *src = static_cast<const float4 *>(device_rgba32f);
+		if (!src)
+		{
+			src = c->d_fb.as<float4>();
+			pixels = rfwb200_local_pixel_count(c);
+		}
+		REQUIRE(src != nullptr, "no framebuffer: call init first");
+		REQUIRE(pixels <= 0xffffffffull, "too many pixels");
+		uint32_t *dst = static_cast<uint32_t *>(device_rgba8);
+		if (!dst)
+		{
+			CK(c->d_display.reserve(std::max<size_t>(pixels, 1) * sizeof(uint32_t)));
+			dst = c->d_display.as<uint32_t>();
+		}
+		CK(launch_tone_map(src, dst, uint32_t(pixels), contrast, brightness, c->stream));
+		c->launches += 1;
+		return RFWB200_OK;
+	}
+
+	void *rfwb200_device_display(rfwb200_context *c) { return c ? c->d_display.ptr : nullptr; }
+
+	int rfwb200_read_display(rfwb200_context *c, float contrast, float brightness, uint8_t *host_rgba8, size_t capacity_pixels)
+	{
+		REQUIRE(c && host_rgba8, "bad arguments");
+		const size_t n = rfwb200_local_pixel_count(c);
+		REQUIRE(capacity_pixels >= n, "host buffer too small");
+		if (int r = rfwb200_tone_map(c, contrast, brightness, nullptr, nullptr, 0))
+			return r;
+		CK(cudaMemcpyAsync(host_rgba8, c->d_display.ptr, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
 		CK(cudaStreamSynchronize(c->stream));
 		return RFWB200_OK;
 	}

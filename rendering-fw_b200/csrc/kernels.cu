@@ -2140,6 +2140,49 @@ __global__ void k_assemble(const ShardView sh, const float4 *__restrict__ gather
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_tone_map — the display pass of rfw::system::render_frame(camera, status, toneMap = true) (system.cpp:694-713), i.e.
+// assets/shaders/tone-map.frag: rgb' = ACESFitted(max(0, rgb - 0.5 * contrast + 0.5 + brightness)), alpha passed through,
+// written as RGBA8 (round to nearest, the UNORM conversion of an 8-bit GL target) so a display consumer reads back a
+// quarter of the float framebuffer.  Every operation is written out (no contraction: __fmul_rn / __fadd_rn) in the
+// order of the shader, so a float32 restatement of the shader reproduces the bytes exactly (tests).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rrt_odt_fit(float v)
+{
+	const float a = __fadd_rn(__fmul_rn(v, __fadd_rn(v, 0.0245786f)), -0.000090537f);
+	const float b = __fadd_rn(__fmul_rn(v, __fadd_rn(__fmul_rn(0.983729f, v), 0.4329510f)), 0.238081f);
+	return __fdiv_rn(a, b);
+}
+__device__ __forceinline__ float mat_row(float m0, float m1, float m2, float x, float y, float z)
+{
+	return __fadd_rn(__fadd_rn(__fmul_rn(m0, x), __fmul_rn(m1, y)), __fmul_rn(m2, z)); // column sum c0*x + c1*y + c2*z
+}
+__device__ __forceinline__ uint32_t unorm8(float v)
+{
+	v = fminf(fmaxf(v, 0.0f), 1.0f);
+	return uint32_t(__fadd_rn(__fmul_rn(v, 255.0f), 0.5f));
+}
+__global__ void k_tone_map(const float4 *__restrict__ fb, uint32_t *__restrict__ out, const uint32_t n, const float contrast,
+						   const float brightness)
+{
+	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n)
+		return;
+	const float4 c = fb[j];
+	const float half_contrast = __fmul_rn(0.5f, contrast);
+	const float r = fmaxf(0.0f, __fadd_rn(__fadd_rn(__fadd_rn(c.x, -half_contrast), 0.5f), brightness));
+	const float g = fmaxf(0.0f, __fadd_rn(__fadd_rn(__fadd_rn(c.y, -half_contrast), 0.5f), brightness));
+	const float b = fmaxf(0.0f, __fadd_rn(__fadd_rn(__fadd_rn(c.z, -half_contrast), 0.5f), brightness));
+	// ACESInputMat (columns as written in the shader), RRT+ODT fit, ACESOutputMat
+	const float ir = rrt_odt_fit(mat_row(0.59719f, 0.35458f, 0.04823f, r, g, b));
+	const float ig = rrt_odt_fit(mat_row(0.07600f, 0.90834f, 0.01566f, r, g, b));
+	const float ib = rrt_odt_fit(mat_row(0.02840f, 0.13383f, 0.83777f, r, g, b));
+	const float orr = mat_row(1.60475f, -0.53108f, -0.07367f, ir, ig, ib);
+	const float og = mat_row(-0.10208f, 1.10813f, -0.00605f, ir, ig, ib);
+	const float ob = mat_row(-0.00327f, -0.07276f, 1.07602f, ir, ig, ib);
+	out[j] = unorm8(orr) | (unorm8(og) << 8) | (unorm8(ob) << 16) | (unorm8(c.w) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_emode — EmbreeRT/src/Context.cpp:104-300 + retrieve_material :417-476, one thread per pixel
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_emode(const SceneView sc, const ShardView sh, const WavefrontView wf,
@@ -2495,6 +2538,13 @@ cudaError_t launch_finalize(const ShardView &sh, const WavefrontView &wf, float 
 {
 	const uint32_t n = sh.local_pixels;
 	k_finalize<<<(n + 255) / 256, 256, 0, stream>>>(sh, wf, scale);
+	return cudaGetLastError();
+}
+cudaError_t launch_tone_map(const float4 *framebuffer, uint32_t *rgba8_out, uint32_t n, float contrast, float brightness,
+							cudaStream_t stream)
+{
+	if (n)
+		k_tone_map<<<(n + 255) / 256, 256, 0, stream>>>(framebuffer, rgba8_out, n, contrast, brightness);
 	return cudaGetLastError();
 }
 cudaError_t launch_emode(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,

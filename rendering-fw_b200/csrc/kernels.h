@@ -30,6 +30,9 @@ cudaError_t launch_shade_ieee(const SceneView &sc, const ShardView &sh, const Wa
 cudaError_t launch_trace(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
 						 uint32_t sample_in_frame, uint32_t depth, const LaunchDims &dims, cudaStream_t stream);
 cudaError_t launch_finalize(const ShardView &sh, const WavefrontView &wf, float scale, cudaStream_t stream);
+// display pass (assets/shaders/tone-map.frag): ACES fit of the finalised framebuffer, packed to RGBA8
+cudaError_t launch_tone_map(const float4 *framebuffer, uint32_t *rgba8_out, uint32_t n, float contrast, float brightness,
+							cudaStream_t stream);
 
 // --- E-mode (image model of the reference's EmbreeRT backend), one fused kernel ---
 cudaError_t launch_emode(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,

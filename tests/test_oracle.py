@@ -253,3 +253,29 @@ def test_skinning_restatement_known_answers():
     t = K.update_triangles(m.triangles, v, n, m.indices)
     gn = np.stack([t["Nx"], t["Ny"], t["Nz"]], 1)
     assert (np.einsum("ij,ij->i", gn, t["vN0"]) > 0.5).mean() > 0.99
+
+
+def test_tone_map_restatement_against_the_shader_formulas():
+    """oracle/tonemap.py: the float32 restatement of assets/shaders/tone-map.frag stays within half a code value of the float64
+    evaluation of the same formulas; anchors computed by hand from the shader."""
+    import sys
+
+    sys.path.insert(0, str(R.REPO_DIR))
+    from oracle.tonemap import tone_map, tone_map_spec
+
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(0, 6, (4000, 4)), rng.uniform(0, 0.1, (1000, 4)), [[0, 0, 0, 0], [1e9, 1e9, 1e9, 2], [17, 12, 4, 1]]]).astype(np.float32)
+    for contrast, brightness in ((1.0, 0.05), (0.0, 0.0), (1.7, -0.2)):
+        b, s = tone_map(x, contrast, brightness), tone_map_spec(x, contrast, brightness)
+        assert b.dtype == np.uint8 and np.abs(b.astype(np.float64) - s).max() <= 0.5 + 1e-3
+    # black with contrast 1, brightness 0: rgb = 0 -> RRTAndODTFit(0) < 0 -> clamped to 0; alpha passes through
+    assert tone_map(np.array([[0, 0, 0, 0.5]], np.float32), 1.0, 0.0).tolist() == [[0, 0, 0, 128]]
+    # mid grey 0.18 with the camera defaults (contrast 1, brightness 0.05): v = 0.23 per channel -> ACES ~ 0.3217 -> code 82
+    v = 0.23 * (0.59719 + 0.35458 + 0.04823)
+    fit = (v * (v + 0.0245786) - 0.000090537) / (v * (0.983729 * v + 0.4329510) + 0.238081)
+    code = round(255 * fit * (1.60475 - 0.53108 - 0.07367))
+    assert abs(int(tone_map(np.array([[0.18, 0.18, 0.18, 1]], np.float32), 1.0, 0.05)[0, 0]) - code) <= 1
+    # monotone in luminance, saturates at white
+    ramp = np.linspace(0, 50, 256, dtype=np.float32)[:, None].repeat(4, 1)
+    t = tone_map(ramp, 1.0, 0.05)[:, 0].astype(int)
+    assert (np.diff(t) >= 0).all() and t[-1] == 255
