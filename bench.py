@@ -289,6 +289,25 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = float(te.item())
     e2e_value = WIDTH * HEIGHT * SPP / (e2e_ms * 1e-3) / 1e6
+    # the same through the display pass (tone-map to RGBA8 on the device, a quarter of the read-back): informational
+    e2e_display = None
+    if world == 1:
+        pinned8 = torch.empty((WIDTH * HEIGHT, 4), dtype=torch.uint8, pin_memory=True)
+
+        def display_step():
+            step()
+            ctx.read_display(1.0, 0.05, out=pinned8.numpy())  # rfw::Camera's default contrast / brightness
+
+        display_step()
+        fence()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            display_step()
+        fence()
+        d_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        e2e_display = {"value": WIDTH * HEIGHT * SPP / (d_ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": d_ms,
+                       "d2h_bytes_per_step": WIDTH * HEIGHT * 4,
+                       "what": "render_frame + read_display (ACES tone-map to RGBA8 on the device) into pinned host memory"}
     h2d_bytes = 72 + 16  # FrameParams + probe reset (the scene is resident: upload is excluded by the metric)
     d2h_bytes = WIDTH * HEIGHT * 16
 
@@ -381,6 +400,8 @@ def main():
                     "ms_per_step": e2e_ms, "what": "render_frame + read_framebuffer into pinned host memory through the C ABI"},
             "roofline": roofline, "counters": counters,
         }
+        if e2e_display:
+            line["e2e_display"] = e2e_display
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))

@@ -338,10 +338,12 @@ class RenderContext:
     def read_image(self) -> np.ndarray:
         return self.read_framebuffer().reshape(self.height, self.width, 4)
 
-    def read_display(self, contrast: float = 0.0, brightness: float = 0.0) -> np.ndarray:
+    def read_display(self, contrast: float = 0.0, brightness: float = 0.0, out: np.ndarray | None = None) -> np.ndarray:
         """rfwb200_read_display: the tone-map pass of system::render_frame(toneMap=true) -> (local pixels, 4) uint8"""
         n = self.local_pixel_count()
-        out = np.empty((n, 4), np.uint8)
+        if out is None:
+            out = np.empty((n, 4), np.uint8)
+        assert out.dtype == np.uint8 and out.size >= n * 4 and out.flags.c_contiguous
         self._check(self.L.fn("read_display", C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_size_t])(
             self._h, contrast, brightness, out.ctypes.data, n))
         return out
