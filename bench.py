@@ -156,7 +156,7 @@ def run_reference(args):
             line["value"], line["ms_per_step"] = rv, WIDTH * HEIGHT * SPP / rv / 1e3
             line["cpu_baseline"] = {k: ref_kernels[k] for k in ("value", "unit", "cores", "kind", "sample")}
             line["e2e"]["value"] = rv
-    print(json.dumps(line))
+    emit(json.dumps(line))
     return 0
 
 
@@ -171,7 +171,41 @@ class DevPtr:
         self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
 
 
+class OneLineStdout:
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL's version banner, compiler chatter of a
+    first-time build), so for the lifetime of the run file descriptor 1 points at stderr and the line goes to the real stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text: str):
+        sys.stdout.flush()
+        os.write(self.real, (text + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.real, 1)
+        os.close(self.real)
+        return False
+
+
+OUT = None
+
+
+def emit(text: str):
+    OUT.emit(text) if OUT else print(text)
+
+
 def main():
+    global OUT
+    with OneLineStdout() as OUT:
+        return run()
+
+
+def run():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
@@ -404,7 +438,7 @@ def main():
             line["e2e_display"] = e2e_display
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
