@@ -2,7 +2,7 @@
 // RFW/backends/CUDART/src/Kernels.cu (generatePrimaryRay, intersect_rays for the three stages, shade_rays, blit_buffer and
 // every set* symbol upload), compiled for the HOST from the reference tree and run one CUDA thread after the other.  The
 // kernels use no shared memory, barriers or warp intrinsics, so thread-by-thread execution is what a GPU computes up to
-// the order of atomics.  The Makefile writes a transformed copy into the git-ignored output directory in which the six
+// the order of atomics.  The Makefile compiles a transformed copy, kept in a temporary directory for the duration of the compile, in which the six
 // `kernel<<<grid, block>>>(args)` launches read `RFW_LAUNCH(kernel, grid, block, args)` (the only syntax a host compiler
 // cannot parse); shim_inc/cuda_kernels_standin.h supplies the CUDA names the file uses.  What is ours here: the C
 // interface below and the bounce loop of CUDAContext::render_frame (CUDART/src/Context.cpp:83-159), which cannot be
@@ -13,7 +13,7 @@
 // deviations D1-D6 (oracle/rfw_oracle.cpp header) out of play.
 #include <cuda_kernels_standin.h>
 
-#include "kernels_host.inc" // oracle/_ref: Kernels.cu with the launch syntax rewritten
+#include "kernels_host.inc" // temporary: Kernels.cu with the launch syntax rewritten (Makefile)
 
 #include <vector>
 

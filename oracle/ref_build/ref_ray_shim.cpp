@@ -1,8 +1,8 @@
 // ref_ray_shim.cpp — TEST INFRASTRUCTURE.  The reference's scalar specification of the generate stage,
 // Ray::CameraParams::CameraParams and Ray::generateFromView (RFW/backends/EmbreeRT/src/Ray.cpp:3-47), compiled from the
 // reference tree.  Ray.cpp as a whole needs Embree, TBB and the GL window headers through its PCH, so the Makefile
-// extracts exactly those two definitions (lines 3-47, checked) into oracle/_ref/ray_generate_extract.inc at build time — a
-// build output, never committed — and this file supplies the declarations they need: the reference's own Ray.h,
+// extracts exactly those two definitions (lines 3-47, checked) into a temporary directory for the duration of the compile —
+// nothing of the reference's source stays in the tree — and this file supplies the declarations they need: the reference's own Ray.h,
 // device_structs.h and rng.h, plus field-compatible stand-ins for the Embree packet structs Ray.h names.
 #include <cassert>
 #include <cmath>
@@ -34,7 +34,7 @@ using RTCRayHit8 = RTCRayHitNt<8>;
 using RTCRayHit16 = RTCRayHitNt<16>;
 
 #include "Ray.h" // RFW/backends/EmbreeRT/src
-#include "ray_generate_extract.inc" // oracle/_ref, = Ray.cpp:3-47
+#include "ray_generate_extract.inc" // temporary (Makefile), = Ray.cpp:3-47
 
 #define REF_API extern "C" __attribute__((visibility("default")))
 
