@@ -22,7 +22,7 @@ OUT = Path(__file__).resolve().parent / "ref_kernels_vectors.npz"
 def main():
     out = {}
     for name, (w, h, first, count, aperture) in pin_cases().items():
-        sc = pin_scene(rich=(name == "rich"))
+        sc = pin_scene(rich=(name in ("rich", "lights")), lights=(name == "lights"))
         o = R.RenderContext(R.load_oracle())  # only to build and export the MBVHs in the reference's node layout
         S.upload(o, sc, w, h)
         ref = reference_kernels_render(o, sc, pin_view14(sc, w, h, aperture), w, h, first, count)

@@ -326,7 +326,7 @@ class _RefScene(C.Structure):
                 ("area", C.c_void_p), ("point", C.c_void_p), ("spot", C.c_void_p), ("dir", C.c_void_p), ("blue_noise", C.c_void_p)]
 
 
-def pin_scene(rich=False):
+def pin_scene(rich=False, lights=False):
     """A box that keeps the oracle's documented deviations from CUDART out of play (oracle header D1-D6).
     rich=False: ONE emissive triangle whose material is material 0 (D1: the reference reads the material index where the
     light-triangle index is meant — both are 0 here), no alpha (D2), untextured, flat normals.
@@ -373,6 +373,25 @@ def pin_scene(rich=False):
         s.instances.append((8, S.translate(4.4, 0.02, 1.1)))
         s.instances.append((8, S.translate(1.0, 0.02, 3.9) @ S.rotate_y(40) @ S.scale(1.4, 0.7, 0.9)))
     s.sky = (np.full((1, 3), 0.05, np.float32), 1, 1)
+    if lights:  # every light type of lights.h in one pick table, and a sky with texture (the lookup of Kernels.cu:593-600)
+        import math
+
+        pl = np.zeros(1, R.POINT_LIGHT_DTYPE)
+        pl["position"], pl["radiance"] = (1.2, 4.2, 0.8), (5, 4, 3)
+        pl["energy"] = np.linalg.norm(pl["radiance"][0])
+        sl = np.zeros(1, R.SPOT_LIGHT_DTYPE)
+        sl["position"], sl["radiance"], sl["direction"] = (4.6, 4.8, 0.6), (14, 14, 18), (-0.35, -0.8, 0.45)
+        sl["direction"] /= np.linalg.norm(sl["direction"][0])
+        sl["cos_inner"], sl["cos_outer"] = math.cos(math.radians(14)), math.cos(math.radians(32))
+        sl["energy"] = np.linalg.norm(sl["radiance"][0])
+        dl = np.zeros(1, R.DIR_LIGHT_DTYPE)
+        dl["direction"], dl["radiance"] = (0.25, -0.6, 0.75), (0.9, 0.85, 0.7)
+        dl["direction"] /= np.linalg.norm(dl["direction"][0])
+        dl["energy"] = np.linalg.norm(dl["radiance"][0])
+        s.point_lights, s.spot_lights, s.dir_lights = pl, sl, dl
+        sw, sh = 32, 16
+        yy, xx = np.mgrid[0:sh, 0:sw]
+        s.sky = (np.stack([0.2 + 0.5 * xx / sw, 0.3 + 0.4 * yy / sh, 0.9 - 0.4 * yy / sh], -1).astype(np.float32).reshape(-1, 3), sw, sh)
     s.camera_pos, s.camera_dir, s.fov = (2.78, 2.73, -8.0), (0, 0, 1), 40.0
     return s
 
@@ -514,7 +533,8 @@ def pin_cases():
     """name -> (width, height, first sample, sample count, lens aperture).  'lens' has a wide lens (the blade sampling of
     generatePrimaryRay) at a packet-aligned size; 'long' crosses sample 256, where shade_rays switches from the blue-noise table
     to RandomFloat(seed) for the light sample, at a size that is not a multiple of the 8x8 / 64 / 128 launch shapes."""
-    return {"lens": (64, 48, 0, 4, 0.12), "long": (70, 50, 0, 260, 0.0), "rich": (72, 56, 0, 8, 0.05)}
+    return {"lens": (64, 48, 0, 4, 0.12), "long": (70, 50, 0, 260, 0.0), "rich": (72, 56, 0, 8, 0.05),
+            "lights": (64, 40, 0, 258, 0.0)}
 
 
 def pin_view14(sc, w, h, aperture):
