@@ -2380,6 +2380,19 @@ extern "C"
 		return RFWB200_OK;
 	}
 	// the top-level MBVH over the instances, in the reference's node layout (for the host-compiled reference kernels)
+	// test hook: the matrices this context traverses and shades instance i with (column-major mat4 / mat3), so that the
+	// reference's host-compiled kernels (oracle/ref_build/ref_kernels_shim.cpp) can be given exactly the same ones
+	ORACLE_API int rfworacle_export_instance(rfworacle_context *c, size_t i, float transform16[16], float inverse16[16],
+											 float normal9[9])
+	{
+		if (i >= c->instances.size())
+			return fail("unknown instance");
+		const Instance &in = c->instances[i];
+		memcpy(transform16, in.transform.m, sizeof(float) * 16);
+		memcpy(inverse16, in.inverse.m, sizeof(float) * 16);
+		memcpy(normal9, in.normal.m, sizeof(float) * 9);
+		return RFWB200_OK;
+	}
 	ORACLE_API int rfworacle_export_tlas_mbvh(rfworacle_context *c, void *nodes_out, size_t node_cap, uint32_t *prims_out,
 											  size_t prim_cap, size_t *n_nodes, size_t *n_prims)
 	{

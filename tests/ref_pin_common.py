@@ -355,6 +355,11 @@ def pin_scene(rich=False, lights=False):
         t1 = S.add_texture_rgba8(s, S.checker_texture(32, 9))
         tiles = S.add_material(s, (0.9, 0.9, 0.9), roughness=0.7, tex0=t0, nmap0=n0, uvscale=(1.0, 1.0))
         column = S.add_material(s, (0.85, 0.8, 0.7), roughness=0.45, specular=0.3, tex0=t1)
+        # a smooth dielectric (roughness below MIN_ROUGHNESS: the IS_SPECULAR branches — no NEE, emissive hits without MIS,
+        # refraction through SampleBSDF's transmission lobe with absorption) and a clear-coated, tinted metal
+        glass = S.add_material(s, (0.95, 0.97, 1.0), roughness=0.0, transmission=0.9, eta=1.45, specular=0.6, absorption=(0.3, 0.1, 0.05))
+        coated = S.add_material(s, (0.7, 0.25, 0.1), roughness=0.35, metallic=0.8, clearcoat=0.9, clearcoat_gloss=0.7, spec_tint=0.5,
+                                subsurface=0.2)
         floor = S._grid_quad((0, 0, 0), (0, 0, 5.55), (5.55, 0, 0), 6, 6, tiles, uv_rep=3.0, tex_dims=(64, 64), bump=0.06,
                              rng=np.random.default_rng(3))
     s.meshes = [
@@ -362,7 +367,8 @@ def pin_scene(rich=False, lights=False):
         floor, S.quad((0, -1, 0), (c, 5.55, c), 5.55, 5.55, white),
         S.quad((0, 0, -1), (c, c, 5.55), 5.55, 5.55, white), S.quad((1, 0, 0), (0, c, c), 5.55, 5.55, green),
         S.quad((-1, 0, 0), (5.55, c, c), 5.55, 5.55, red),
-        S.box_mesh((-0.5, 0, -0.5), (0.5, 1, 0.5), white), S.box_mesh((-0.5, 0, -0.5), (0.5, 1, 0.5), glossy),
+        S.box_mesh((-0.5, 0, -0.5), (0.5, 1, 0.5), glass if rich else white),
+        S.box_mesh((-0.5, 0, -0.5), (0.5, 1, 0.5), coated if rich else glossy),
     ]
     I = np.eye(4)
     s.instances = [(i, I) for i in range(6)]
@@ -421,14 +427,18 @@ def reference_kernels_scene(orc_ctx, sc):
         meshes[mi].triangles160 = arr(m.triangles, R.TRIANGLE_DTYPE)
         meshes[mi].mbvh_nodes, meshes[mi].prim_indices = nodes.ctypes.data, prims.ctypes.data
     insts = (_RefInstance * len(sc.instances))()
-    for ii, (mi, M) in enumerate(sc.instances):
-        M = np.asarray(M, np.float64).reshape(4, 4)
-        nm = np.eye(4)
-        nm[:3, :3] = np.linalg.inv(M[:3, :3]).T
+    exp_inst = orc_ctx.L.fn("export_instance", C.c_int, [P, C.c_size_t, P, P, P])
+    for ii, (mi, _) in enumerate(sc.instances):
+        # the matrices the oracle itself uses (its float32 inverse restates glm::inverse, top_level_bvh.cpp:309): last-bit
+        # differences in the inverse decide self-intersections at the reference's fixed 1e-5 epsilons
+        t16, i16, n9 = np.zeros(16, np.float32), np.zeros(16, np.float32), np.zeros(9, np.float32)
+        assert exp_inst(orc_ctx._h, ii, t16.ctypes.data, i16.ctypes.data, n9.ctypes.data) == 0
+        n16 = np.eye(4, dtype=np.float32)
+        n16[:3, :3] = n9.reshape(3, 3)  # both column-major: columns stay columns
         insts[ii].mesh = mi
-        for name, mat in (("transform", M), ("inverse", np.linalg.inv(M)), ("normal", nm)):
-            col_major = mat.T.reshape(-1).astype(np.float32)
-            getattr(insts[ii], name)[:] = [float(x) for x in col_major]
+        insts[ii].transform[:] = [float(x) for x in t16]
+        insts[ii].inverse[:] = [float(x) for x in i16]
+        insts[ii].normal[:] = [float(x) for x in n16.reshape(-1)]
     nn, npm = C.c_size_t(), C.c_size_t()
     exp_tlas(orc_ctx._h, None, 0, None, 0, C.byref(nn), C.byref(npm))
     tnodes, tprims = np.zeros(nn.value * 32, np.float32), np.zeros(max(npm.value, 1), np.uint32)
