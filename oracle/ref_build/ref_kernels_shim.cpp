@@ -160,3 +160,16 @@ REF_API int rfwref_cudart_render(const RefScene *sc, const float *view14, unsign
 	memcpy(accumulator_out, acc.data(), size_t(N) * 16);
 	return 0;
 }
+
+// finalize: the reference's own blit_buffer (Kernels.cu:181-203) from an accumulator into an RGBA32F image through the surface
+// stand-in, with the scale CUDAContext::render_frame passes (1 / m_SampleIndex after the increment, Context.cpp:149-152)
+REF_API int rfwref_cudart_blit(const float *accumulator_in, unsigned w, unsigned h, unsigned samples, float *image_out)
+{
+	std::vector<vec4> acc(size_t(w) * h);
+	memcpy(acc.data(), accumulator_in, acc.size() * 16);
+	setAccumulator(acc.data());
+	output.pixels = image_out, output.width = w;
+	blitBuffer(w, h, samples);
+	output.pixels = nullptr;
+	return 0;
+}

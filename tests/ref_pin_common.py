@@ -479,6 +479,18 @@ def reference_kernels_run(rs, view14, w, h, first, count, clamp=10.0, want_rays=
     return {"acc": acc.reshape(h, w, 4), "origins": o, "directions": d, "states": st, "counters": counters}
 
 
+def reference_blit(acc, samples):
+    """The reference's own blit_buffer (Kernels.cu:181-203) on an accumulator (h, w, 4) -> finalised RGBA32F image."""
+    lib = C.CDLL(str(REF_KERNELS_LIB))
+    acc = np.ascontiguousarray(acc, np.float32)
+    h, w = acc.shape[:2]
+    img = np.zeros_like(acc)
+    f = lib.rfwref_cudart_blit
+    f.restype, f.argtypes = C.c_int, [C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_void_p]
+    assert f(acc.ctypes.data, w, h, samples, img.ctypes.data) == 0
+    return img
+
+
 def reference_kernels_render(orc_ctx, sc, view14, w, h, first, count, clamp=10.0):
     rs, keep = reference_kernels_scene(orc_ctx, sc)
     return reference_kernels_run(rs, view14, w, h, first, count, clamp)

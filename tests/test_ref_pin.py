@@ -279,7 +279,7 @@ def test_pt_pipeline_matches_reference_cudart_kernels(oracle_lib, case):
     o.set_setting("spp", count)
     o.render_frame(view, R.RESET)
     img = o.read_image()
-    ref = GK[case + "_acc"] / np.float32(count)
+    ref = GK[case + "_acc"] * (np.float32(1.0) / np.float32(count))  # blit_buffer's scale (checked against the reference's blit below)
     assert 0.2 < ref[..., :3].mean() < 1.2
     err = (np.abs(img[..., :3] - ref[..., :3]) / (1.0 + np.abs(ref[..., :3]))).max(-1)
     assert (err > 1e-5).mean() <= 1e-3 and err.max() < 1e-3, (float((err > 1e-5).mean()), float(err.max()))
@@ -302,7 +302,7 @@ def test_pt_pipeline_matches_reference_cudart_kernels(oracle_lib, case):
 @pytest.mark.skipif(not (Path(R.REPO_DIR) / "oracle" / "_ref" / "librfwref_kernels.so").exists(),
                     reason="oracle/_ref is only built where /root/reference exists")
 def test_stored_kernel_vectors_are_what_the_live_reference_kernels_produce(oracle_lib):
-    from ref_pin_common import pin_cases, pin_scene, pin_view14, reference_kernels_render
+    from ref_pin_common import pin_cases, pin_scene, pin_view14, reference_kernels_render, view_from14
 
     w, h, first, count, aperture = pin_cases()["lens"]
     sc = pin_scene()
@@ -311,6 +311,19 @@ def test_stored_kernel_vectors_are_what_the_live_reference_kernels_produce(oracl
     live = reference_kernels_render(o, sc, pin_view14(sc, w, h, aperture), w, h, first, count)
     for key in ("acc", "origins", "directions", "states", "counters"):
         assert np.array_equal(live[key].view(np.uint32), GK["lens_" + key].view(np.uint32)), key
+    # finalize: the reference's own blit_buffer (Kernels.cu:181-203) is accumulator * (1 / samples) in float32, which is what
+    # the pipeline test divides the stored accumulators by and what the oracle and k_finalize compute
+    from ref_pin_common import reference_blit
+
+    assert np.array_equal(reference_blit(live["acc"], count), live["acc"] * (np.float32(1.0) / np.float32(count)))
+    o.set_setting("mode", "pt")
+    o.set_setting("bsdf_random_order", "rtl")
+    o.set_setting("spp", count)
+    o.render_frame(view_from14(pin_view14(sc, w, h, aperture)), R.RESET)
+    img = o.read_image()
+    o.set_setting("bsdf_random_order", "ltr")
+    ref_img = reference_blit(live["acc"], count)
+    assert np.abs(img - ref_img).max() <= 1e-5 * (1.0 + np.abs(ref_img).max())
 
 
 def test_nvcc_draws_samplebsdf_randoms_left_to_right(tmp_path):
