@@ -43,8 +43,9 @@
 //      rt_shade.comp:155);
 //   D3 counters->samplesTaken equals sampleIndex while a sample renders
 //      (OptiX6Context/src/OptiXContext.cpp:364; CUDART lags one frame after Reset);
-//   D4 barycentrics are the weights of vertex1/vertex2 (Embree/OptiX convention,
-//      OptiX6Context/assets/kernels/getShadingData.h:167,183-184);
+//   D4 the two 16-bit barycentrics of a hit record are the weights of vertex 0 and vertex 1 as in CUDART, but computed
+//      as (1 - u - v, u) from the Moller-Trumbore u, v instead of the area ratios of CUDAIntersect.h:82-87 (the same
+//      weights up to rounding; "cudart_conventions"=on computes the area ratios);
 //   D5 SampleBSDF's two RandomFloat(seed) arguments are drawn left to right (r3 then r4);
 //      the C++ order is unspecified (bsdf/disney.h:278) — left to right is what nvcc compiles
 //      (tests/test_ref_pin.py::test_nvcc_draws_samplebsdf_randoms_left_to_right), so this is the
@@ -661,10 +662,10 @@ inline MBVHHit intersect_quad_node(const MBVHNode &n, const vec3 &org, const vec
 	return hit;
 }
 
-// D1 / D4 switch (setting "cudart_conventions" = off | on).  "on" follows CUDART to the letter where the default follows
-// the reference's newer backends: barycentrics are the area ratios of CUDAIntersect.h:82-87 (weights of vertex0, vertex1)
-// and getShadingData.h:123,140-141 weights vertex 0,1,2 with u,v,w; the light index of the MIS pick probability is the
-// material index (device_structs.h:37).  Used by the pin test against the reference's host-compiled kernels.
+// D1 / D4 switch (setting "cudart_conventions" = off | on).  "on" follows CUDART to the letter: the barycentrics of a hit
+// are computed as the area ratios of CUDAIntersect.h:82-87 (default: the same two weights from Moller-Trumbore's u, v)
+// and the light index of the MIS pick probability is the material index (device_structs.h:37; default: the light
+// index, as the reference's newer backends do).  Used by the pin test against the reference's host-compiled kernels.
 static bool g_cudart_conventions = false;
 
 // CUDAIntersect.h:48-94 intersect_triangle (Moller-Trumbore); D4: barycentrics returned are the
@@ -1319,7 +1320,7 @@ static vec4 FetchTexelTrilinear(const Ctx &c, float lambda, float tcx, float tcy
 	return p0 * (1.0f - f) + p1 * f;
 }
 
-// :100-217 getShadingData (D4: u,v are the weights of vertex1, vertex2; w of vertex0)
+// :100-217 getShadingData (u, v: the weights of vertex 0 and vertex 1 as in the reference; w of vertex 2)
 static ShadingData getShadingData(const Ctx &c, const vec3 &D, float u, float v, float coneWidth,
 								  const rfwb200_triangle &tri, vec3 &N, vec3 &iN, vec3 &T, vec3 &B, const mat3 &invT)
 {
@@ -1337,7 +1338,7 @@ static ShadingData getShadingData(const Ctx &c, const vec3 &D, float u, float v,
 	N = vec3(tri.Nx, tri.Ny, tri.Nz);
 	iN = N;
 	if (has_flag(flags, HasSmoothNormals))
-		iN = g_cudart_conventions ? normalize(n0 * u + n1 * v + n2 * w) : normalize(n0 * w + n1 * u + n2 * v);
+		iN = normalize(n0 * u + n1 * v + n2 * w); // :123
 	N = normalize(invT.mul(N));
 	iN = normalize(invT.mul(iN));
 	createTangentSpace(iN, T, B);
@@ -1346,10 +1347,8 @@ static ShadingData getShadingData(const Ctx &c, const vec3 &D, float u, float v,
 		has_flag(flags, HasRoughnessMap) || has_flag(flags, Has2ndDiffuseMap) || has_flag(flags, Has3rdDiffuseMap) ||
 		has_flag(flags, Has2ndNormalMap) || has_flag(flags, Has3rdNormalMap))
 	{
-		tu = w * tri.u0 + u * tri.u1 + v * tri.u2;
-		tv = w * tri.v0 + u * tri.v1 + v * tri.v2;
-		if (g_cudart_conventions)
-			tu = u * tri.u0 + v * tri.u1 + w * tri.u2, tv = u * tri.v0 + v * tri.v1 + w * tri.v2;
+		tu = u * tri.u0 + v * tri.u1 + w * tri.u2; // :140-141
+		tv = u * tri.v0 + v * tri.v1 + w * tri.v2;
 	}
 	if (has_flag(flags, HasDiffuseMap))
 	{
@@ -1657,8 +1656,14 @@ static vec4 trace_to_state(const Ctx &c, const vec3 &O, const vec3 &D)
 	int inst = 0, prim = -1;
 	vec2 bary = {0, 0};
 	if (intersect_scene(c, O, D, &inst, &prim, &t, &bary, 1e-5f)) // Kernels.cu:455-457
+	{
+		// D4: the hit record holds the weights of vertex 0 and vertex 1 like the reference's; they are taken from the
+		// Moller-Trumbore u, v (1 - u - v, u) unless cudart_conventions asks for the area ratios of CUDAIntersect.h:82-87
+		if (!g_cudart_conventions)
+			bary = {1.0f - bary.x - bary.y, bary.x};
 		return vec4(u2f(cvt_u32(65535.0f * bary.x) | (cvt_u32(65535.0f * bary.y) << 16)), u2f(uint32_t(inst)),
 					u2f(uint32_t(prim)), t);
+	}
 	return vec4(0, 0, u2f(uint32_t(-1)), 0);
 }
 
@@ -2414,7 +2419,8 @@ extern "C"
 		if (prim < 0 || size_t(prim) >= m.triangles.size())
 			return fail("bad prim");
 		vec3 N, iN, T, B;
-		const ShadingData sd = getShadingData(*c, vec3(D), u, v, cone_width, m.triangles[prim], N, iN, T, B, in.normal);
+		// the caller passes Moller-Trumbore u, v (weights of vertex 1, 2); getShadingData takes the weights of vertex 0, 1
+		const ShadingData sd = getShadingData(*c, vec3(D), 1.0f - u - v, u, cone_width, m.triangles[prim], N, iN, T, B, in.normal);
 		color_out[0] = sd.color.x, color_out[1] = sd.color.y, color_out[2] = sd.color.z;
 		*flags_out = sd.flags;
 		N_out[0] = N.x, N_out[1] = N.y, N_out[2] = N.z;

@@ -259,6 +259,14 @@ __device__ __forceinline__ float slab(float lo, float hi, float idir, float ood,
 	}
 #define PICK(KEY) ((((KEY)&3u) == 0u) ? n.child.x : ((((KEY)&3u) == 1u) ? n.child.y : ((((KEY)&3u) == 2u) ? n.child.z : n.child.w)))
 
+// Hit-record barycentrics as CUDART stores them (CUDAIntersect.h:82-87, Kernels.cu:457): 16-bit weights of vertex 0 and
+// vertex 1 (the reference computes them as area ratios; 1 - u - v and u of Moller-Trumbore are the same weights), so the
+// 16-bit quantisation falls on the same two weights as in the reference and shading interpolates as getShadingData.h:123,140.
+__device__ __forceinline__ uint32_t pack_barycentrics(float mt_u, float mt_v)
+{
+	return uint32_t(65535.0f * (1.0f - mt_u - mt_v)) | (uint32_t(65535.0f * mt_u) << 16);
+}
+
 // one ray through the compressed 8-wide BVH (cwbvh.h): the per-thread form of k_wavefront_trace_cw's loop, used by the
 // stage-level kernels and E-mode
 template <bool ANY_HIT>
@@ -896,7 +904,7 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 			{
 				float4 hit = make_float4(0.f, 0.f, __int_as_float(PRIM_MISS), 0.f);
 				if (hit_tri != 0xffffffffu)
-					hit = make_float4(__uint_as_float(uint32_t(65535.0f * hit_u) | (uint32_t(65535.0f * hit_v) << 16)),
+					hit = make_float4(__uint_as_float(pack_barycentrics(hit_u, hit_v)),
 									  __uint_as_float(hit_tri), __int_as_float(0), tmax);
 				wf.hit[item] = hit;
 				if (PRIMARY && rs.primary_cache)
@@ -1157,7 +1165,7 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace_cw(const Sc
 			{
 				float4 hit = make_float4(0.f, 0.f, __int_as_float(PRIM_MISS), 0.f);
 				if (hit_tri != 0xffffffffu)
-					hit = make_float4(__uint_as_float(uint32_t(65535.0f * hit_u) | (uint32_t(65535.0f * hit_v) << 16)),
+					hit = make_float4(__uint_as_float(pack_barycentrics(hit_u, hit_v)),
 									  __uint_as_float(hit_tri), __int_as_float(0), tmax);
 				wf.hit[item] = hit;
 			}
@@ -1560,16 +1568,16 @@ __device__ ShadingData getShadingData(const SceneView &sc, V3 D, float u, float 
 					  __half2float(__ushort_as_half((unsigned short)(base.z & 0xffffu))),
 					  __half2float(__ushort_as_half((unsigned short)(base.z >> 16))));
 	r.p0 = par.x, r.p1 = par.y, r.p2 = par.z;
-	const float w = 1.0f - u - v;
+	const float w = 1.0f - u - v; // u, v: weights of vertex 0 and vertex 1 (the reference's convention), w: of vertex 2
 	N = mk(tri.Nx, tri.Ny, tri.Nz);
 	iN = N;
 	if (has_flag(flags, HasSmoothNormals))
-		iN = normalize(mk(tri.n0x, tri.n0y, tri.n0z) * w + mk(tri.n1x, tri.n1y, tri.n1z) * u + mk(tri.n2x, tri.n2y, tri.n2z) * v);
+		iN = normalize(mk(tri.n0x, tri.n0y, tri.n0z) * u + mk(tri.n1x, tri.n1y, tri.n1z) * v + mk(tri.n2x, tri.n2y, tri.n2z) * w);
 	createTangentSpace(iN, T, B);
 	if (has_flag(flags, HasDiffuseMap))
 	{
-		const float tu = w * tri.u0 + u * tri.u1 + v * tri.u2;
-		const float tv = w * tri.v0 + u * tri.v1 + v * tri.v2;
+		const float tu = u * tri.u0 + v * tri.u1 + w * tri.u2;
+		const float tv = u * tri.v0 + v * tri.v1 + w * tri.v2;
 		const float lambda = tri.lod + log2f(coneWidth * (1.0f / fabsf(dot(-D, N))));
 		const MapDesc m0 = load_map(&mat->tex0);
 		const float4 texel = FetchTexelTrilinear(sc, lambda, m0.us * (m0.uo + tu), m0.vs * (m0.vo + tv), int(m0.addr), m0.w, m0.h);

@@ -248,8 +248,9 @@ def test_pt_pipeline_matches_reference_cudart_kernels(oracle_lib, case):
     all but 0.1 % of the pixels (a last-bit difference can flip one branch of one sample), 1e-3 for those.
     Case "rich" adds a two-triangle light, an indexed bumpy floor with diffuse and normal maps, smooth textured columns and a
     scaled instance, with the oracle following CUDART's own barycentric and light-index conventions
-    (cudart_conventions=on, D1 / D4); with the oracle's default conventions the same image differs from the reference's by
-    more than 1e-3 relative in under 1 % of the pixels, which bounds what those two deviations are worth.
+    (cudart_conventions=on, D1 / D4); with the oracle's default conventions (the light index instead of the material index,
+    the hit's two weights from Moller-Trumbore instead of area ratios) the same image stays within 1e-3 of the reference's
+    (measured: worst pixel 2.8e-4), which bounds what those two deviations are worth.
     Case "lights" adds a point, a spot and a directional light to the pick table of lights.h and a textured sky, 258 samples."""
     from ref_pin_common import pin_cases, pin_scene, pin_view14, view_from14
 
@@ -294,7 +295,7 @@ def test_pt_pipeline_matches_reference_cudart_kernels(oracle_lib, case):
         o.set_setting("cudart_conventions", "off")
         o.render_frame(view, R.RESET)
         err = (np.abs(o.read_image()[..., :3] - ref[..., :3]) / (1.0 + np.abs(ref[..., :3]))).max(-1)
-        assert (err > 1e-3).mean() < 0.01 and err.max() < 0.05, (float((err > 1e-3).mean()), float(err.max()))
+        assert (err > 1e-3).mean() < 0.002 and err.max() < 0.01, (float((err > 1e-3).mean()), float(err.max()))
     o.set_setting("bsdf_random_order", "ltr")  # globals of the oracle library: restore the defaults
     o.set_setting("cudart_conventions", "off")
 
