@@ -372,3 +372,40 @@ def test_reference_kernels_sample_parallel_timing_helper(oracle_lib):
     assert secs > 0 and abs(mean - float(GK["lens_acc"][..., :3].mean(dtype=np.float64)) / count) < 1e-6
     with pytest.raises(RuntimeError):
         reference_kernels_timed(rs, pin_view14(sc, 512, 512, aperture), 512, 512, 64, 2, timeout_s=0.05)
+
+
+@pytest.mark.skipif(not (Path(R.REPO_DIR) / "oracle" / "_ref" / "librfwref_kernels.so").exists(),
+                    reason="oracle/_ref is only built where /root/reference exists")
+def test_alpha_cutouts_are_where_the_oracle_leaves_cudart(oracle_lib):
+    """D2, measured on the reference's own kernels: shade_rays' alpha continuation writes the path's throughput into the
+    hit-record plane instead of the throughput plane (Kernels.cu:634-647, `// TODO: this never gets hit, fix this`), so the
+    next bounce reads whatever that slot held before — zero in the first sample (the pixel stays black), another path's
+    throughput afterwards.  The oracle (and the CUDA kernels) carry the throughput through the cut-out, as the reference's
+    Vulkan backend does (rt_shade.comp:155).  Everything else in a scene with an alpha-mapped surface — including which
+    pixels ARE cut out, i.e. getShadingData's alpha test on the trilinear texel — agrees with the reference kernels."""
+    from ref_pin_common import pin_scene, pin_view14, reference_kernels_render, view_from14
+
+    w, h = 64, 48
+    sc = pin_scene()
+    ta = S.add_texture_rgba8(sc, S.checker_texture(64, 3, alpha_holes=True))
+    leaf = S.add_material(sc, (0.9, 0.9, 0.9), tex0=ta, has_alpha=True)
+    sc.meshes.append(S._grid_quad((1.5, 1.0, -1.0), (2.5, 0, 0), (0, 2.5, 0), 1, 1, leaf, uv_rep=1.0, tex_dims=(64, 64)))
+    sc.instances.append((len(sc.meshes) - 1, np.eye(4)))
+    o = R.RenderContext(oracle_lib)
+    S.upload(o, sc, w, h)
+    v14 = pin_view14(sc, w, h, 0.0)
+    view = view_from14(v14)
+    for k, v in (("cudart_conventions", "on"), ("bsdf_random_order", "rtl"), ("mode", "pt"), ("spp", 1)):
+        o.set_setting(k, v)
+    origins, dirs = o.generate_primary(view, 0)
+    hits = o.trace_closest(origins, dirs)
+    on_quad = (hits["inst_id"] == len(sc.instances) - 1) & (hits["prim_id"] >= 0)
+    ref = reference_kernels_render(o, sc, v14, w, h, 0, 1)["acc"].reshape(-1, 4)
+    o.render_frame(view, R.RESET)
+    img = o.read_image().reshape(-1, 4)
+    o.set_setting("cudart_conventions", "off"), o.set_setting("bsdf_random_order", "ltr")
+    bad = (np.abs(ref[:, :3] - img[:, :3]) / (1.0 + np.abs(ref[:, :3]))).max(-1) > 1e-4
+    assert 300 < on_quad.sum() < 1200 and 50 < (bad & on_quad).sum() < on_quad.sum()  # the holes, not the whole quad
+    assert (bad & ~on_quad).sum() <= 3  # nothing else moves (a path that reaches the quad by a bounce may)
+    assert np.abs(ref[bad & on_quad, :3]).max() == 0.0  # CUDART: black behind a cut-out in the first sample
+    assert img[bad & on_quad, :3].mean() > 0.3  # the scene behind it
