@@ -1903,6 +1903,55 @@ static void render_sample_pt(Ctx &c, const rfwb200_camera_view &view)
 	c.sample_index++;
 }
 
+// EmbreeRT/src/Context.cpp:417-476 retrieve_material: interpolated normal, material colour times the nearest texel of the
+// first diffuse map (no mips, no filtering; the FLOAT4 case falls through into the UINT case)
+static void emode_material(const Ctx &c, const Instance &inst, const rfwb200_triangle &tri, const vec3 &bary, vec3 &color, vec3 &iN)
+{
+	const rfwb200_material &material = c.materials_raw[tri.material];
+	// retrieve_material :417-476
+	const vec3 iNl = vec3(tri.vN0) * bary.x + vec3(tri.vN1) * bary.y + vec3(tri.vN2) * bary.z;
+	iN = normalize(inst.normal.mul(iNl));
+	color = vec3(half2float(material.diffuse[0]), half2float(material.diffuse[1]), half2float(material.diffuse[2]));
+	float tu = 0.0f, tv = 0.0f;
+	if (has_flag(material.flags, HasDiffuseMap) || has_flag(material.flags, HasNormalMap) ||
+		has_flag(material.flags, HasRoughnessMap) || has_flag(material.flags, HasAlphaMap) ||
+		has_flag(material.flags, HasSpecularityMap))
+	{
+		tu = bary.x * tri.u0 + bary.y * tri.u1 + bary.z * tri.u2;
+		tv = bary.x * tri.v0 + bary.y * tri.v1 + bary.z * tri.v2;
+	}
+	if (has_flag(material.flags, HasDiffuseMap) && material.tex0.texaddr < c.textures.size())
+	{
+		const float u = (tu + half2float(material.tex0.uoffs)) * half2float(material.tex0.uscale);
+		const float v = (tv + half2float(material.tex0.voffs)) * half2float(material.tex0.vscale);
+		float txf = std::fmod(u, 1.0f), tyf = std::fmod(v, 1.0f);
+		if (txf < 0.f)
+			txf = 1.f + txf;
+		if (tyf < 0.f)
+			tyf = 1.f + tyf;
+		const TextureDesc &tex = c.textures[material.tex0.texaddr]; // unpatched: texaddr0 = texture id
+		const uint32_t ix = cvt_u32(txf * float(tex.width - 1)), iy = cvt_u32(tyf * float(tex.height - 1));
+		const size_t id = size_t(iy) * tex.width + ix;
+		if (tex.type == RFWB200_TEX_UINT)
+		{
+			const uint32_t tc = c.uint_texels[tex.addr + id];
+			constexpr float sc = 1.0f / 256.0f;
+			color = color * sc * vec3(float(tc & 0xFFu), float((tc >> 8) & 0xFFu), float((tc >> 16) & 0xFFu));
+		}
+		else
+		{
+			// FLOAT4 case falls through into the UINT case (:458-472): the texel is applied, then the word at index `id`
+			// of the same buffer read as uints (float number id of the texture, not texel id) is applied as RGBA8.
+			const vec4 tf = c.float_texels[tex.addr + id];
+			color = color * vec3(tf.x, tf.y, tf.z);
+			const vec4 &wq = c.float_texels[tex.addr + id / 4];
+			const uint32_t tc = f2u(id % 4 == 0 ? wq.x : (id % 4 == 1 ? wq.y : (id % 4 == 2 ? wq.z : wq.w)));
+			constexpr float sc = 1.0f / 256.0f;
+			color = color * sc * vec3(float(tc & 0xFFu), float((tc >> 8) & 0xFFu), float((tc >> 16) & 0xFFu));
+		}
+	}
+}
+
 // ---------------------------------------------------------------------------------------------
 // E-mode frame — EmbreeRT/src/Context.cpp:104-300, retrieve_material :417-476
 // ---------------------------------------------------------------------------------------------
@@ -1944,48 +1993,8 @@ static void render_emode(Ctx &c, const rfwb200_camera_view &view)
 				const rfwb200_triangle &tri = c.meshes[inst.mesh].triangles[primID];
 				const vec3 bary(1.0f - uv.x - uv.y, uv.x, uv.y);
 				const vec3 p = origin + direction * t;
-				const rfwb200_material &material = c.materials_raw[tri.material];
-				// retrieve_material :417-476
-				const vec3 iNl = vec3(tri.vN0) * bary.x + vec3(tri.vN1) * bary.y + vec3(tri.vN2) * bary.z;
-				const vec3 iN = normalize(inst.normal.mul(iNl));
-				vec3 color(half2float(material.diffuse[0]), half2float(material.diffuse[1]), half2float(material.diffuse[2]));
-				float tu = 0.0f, tv = 0.0f;
-				if (has_flag(material.flags, HasDiffuseMap) || has_flag(material.flags, HasNormalMap) ||
-					has_flag(material.flags, HasRoughnessMap) || has_flag(material.flags, HasAlphaMap) ||
-					has_flag(material.flags, HasSpecularityMap))
-				{
-					tu = bary.x * tri.u0 + bary.y * tri.u1 + bary.z * tri.u2;
-					tv = bary.x * tri.v0 + bary.y * tri.v1 + bary.z * tri.v2;
-				}
-				if (has_flag(material.flags, HasDiffuseMap) && material.tex0.texaddr < c.textures.size())
-				{
-					const float u = (tu + half2float(material.tex0.uoffs)) * half2float(material.tex0.uscale);
-					const float v = (tv + half2float(material.tex0.voffs)) * half2float(material.tex0.vscale);
-					float txf = std::fmod(u, 1.0f), tyf = std::fmod(v, 1.0f);
-					if (txf < 0.f)
-						txf = 1.f + txf;
-					if (tyf < 0.f)
-						tyf = 1.f + tyf;
-					const TextureDesc &tex = c.textures[material.tex0.texaddr]; // unpatched: texaddr0 = texture id
-					const uint32_t ix = cvt_u32(txf * float(tex.width - 1)), iy = cvt_u32(tyf * float(tex.height - 1));
-					const size_t id = size_t(iy) * tex.width + ix;
-					if (tex.type == RFWB200_TEX_UINT)
-					{
-						const uint32_t tc = c.uint_texels[tex.addr + id];
-						constexpr float sc = 1.0f / 256.0f;
-						color = color * sc * vec3(float(tc & 0xFFu), float((tc >> 8) & 0xFFu), float((tc >> 16) & 0xFFu));
-					}
-					else
-					{
-						// FLOAT4 case falls through into the UINT case (:458-472): the texel is applied,
-						// then its first float's bit pattern is applied again as RGBA8.
-						const vec4 tf = c.float_texels[tex.addr + id];
-						color = color * vec3(tf.x, tf.y, tf.z);
-						const uint32_t tc = f2u(tf.x);
-						constexpr float sc = 1.0f / 256.0f;
-						color = color * sc * vec3(float(tc & 0xFFu), float((tc >> 8) & 0xFFu), float((tc >> 16) & 0xFFu));
-					}
-				}
+				vec3 color, iN;
+				emode_material(c, inst, tri, bary, color, iN); // retrieve_material :417-476
 				if (color.x > 1 || color.y > 1 || color.z > 1) // :216-220
 				{
 					c.framebuffer[pixel] = vec4(color, 1.0f);
@@ -2396,6 +2405,22 @@ extern "C"
 		memcpy(transform16, in.transform.m, sizeof(float) * 16);
 		memcpy(inverse16, in.inverse.m, sizeof(float) * 16);
 		memcpy(normal9, in.normal.m, sizeof(float) * 9);
+		return RFWB200_OK;
+	}
+	// test hook: the E-mode material step for (instance, primitive) at Embree barycentrics (u, v) = weights of vertex 1, 2
+	ORACLE_API int rfworacle_emode_material(rfworacle_context *c, int inst, int prim, float u, float v, float *color_out,
+											float *iN_out)
+	{
+		if (inst < 0 || size_t(inst) >= c->instances.size())
+			return fail("bad instance");
+		const Instance &in = c->instances[inst];
+		const MeshData &m = c->meshes[in.mesh];
+		if (prim < 0 || size_t(prim) >= m.triangles.size())
+			return fail("bad prim");
+		vec3 color, iN;
+		emode_material(*c, in, m.triangles[prim], vec3(1.0f - u - v, u, v), color, iN);
+		color_out[0] = color.x, color_out[1] = color.y, color_out[2] = color.z;
+		iN_out[0] = iN.x, iN_out[1] = iN.y, iN_out[2] = iN.z;
 		return RFWB200_OK;
 	}
 	ORACLE_API int rfworacle_export_tlas_mbvh(rfworacle_context *c, void *nodes_out, size_t node_cap, uint32_t *prims_out,

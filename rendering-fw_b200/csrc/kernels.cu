@@ -2284,10 +2284,12 @@ __global__ void __launch_bounds__(256) k_emode(const SceneView sc, const ShardVi
 						}
 						else
 						{
-							// FLOAT4 falls through into the UINT case in the reference (Context.cpp:458-472)
+							// FLOAT4 falls through into the UINT case in the reference (Context.cpp:458-472): the texel is
+							// applied, then the 32-bit word at index `id` of the SAME buffer read as uints — float number id
+							// of the texture, not texel id — is applied as RGBA8
 							const float4 tf = __ldg(reinterpret_cast<const float4 *>(sc.float_texels) + taddr + id);
 							color = color * mk(tf.x, tf.y, tf.z);
-							const uint32_t tc = __float_as_uint(tf.x);
+							const uint32_t tc = __ldg(reinterpret_cast<const uint32_t *>(reinterpret_cast<const float4 *>(sc.float_texels) + taddr) + id);
 							color = color * tsc * mk(float(tc & 0xFFu), float((tc >> 8) & 0xFFu), float((tc >> 16) & 0xFFu));
 						}
 					}

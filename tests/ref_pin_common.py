@@ -572,3 +572,48 @@ def view_from14(v14):
         view.pos[i], view.p1[i], view.p2[i], view.p3[i] = float(v14[i]), float(v14[3 + i]), float(v14[6 + i]), float(v14[9 + i])
     view.aperture, view.spread_angle = float(v14[12]), float(v14[13])
     return view
+
+
+# ---- the reference's own E-mode material lookup (EmbreeRT/src/Context.cpp:417-476 via oracle/ref_build/ref_emat_shim.cpp) -------
+REF_EMAT_LIB = R.REPO_DIR / "oracle" / "_ref" / "librfwref_emat.so"
+
+
+class _RefTexture(C.Structure):
+    _fields_ = [("type", C.c_int), ("width", C.c_uint), ("height", C.c_uint), ("data", C.c_void_p)]
+
+
+def ref_emode_material(sc, inst, prim, u, v):
+    """retrieve_material of the reference for (instance, primitive) of scene `sc` at Embree barycentrics (u, v).
+    -> (color3, N3, iN3).  Materials keep the texture ID in texaddr0, as the CPU backend's do."""
+    lib = C.CDLL(str(REF_EMAT_LIB))
+    mesh_idx, M = sc.instances[inst]
+    tri = sc.meshes[mesh_idx].triangles[prim:prim + 1].copy()
+    mat = sc.materials[int(tri["material"][0]):int(tri["material"][0]) + 1].copy()
+    keep, texs = [], (_RefTexture * max(len(sc.textures), 1))()
+    for i, t in enumerate(sc.textures):
+        data = np.ascontiguousarray(t["data"])
+        keep.append(data)
+        texs[i].type, texs[i].width, texs[i].height, texs[i].data = (1 if t["type"] == R.TEX_UINT else 0), t["width"], t["height"], data.ctypes.data
+    nm = np.eye(4)
+    nm[:3, :3] = np.linalg.inv(np.asarray(M, np.float64)[:3, :3]).T
+    nm16 = np.ascontiguousarray(nm.T.reshape(-1), np.float32)
+    bary = np.array([1.0 - u - v, u, v], np.float32)
+    color, N, iN = (np.zeros(3, np.float32) for _ in range(3))
+    P = C.c_void_p
+    f = lib.rfwref_emode_material
+    f.restype, f.argtypes = None, [P, P, P, C.c_int, P, P, P, P, P]
+    f(tri.ctypes.data, mat.ctypes.data, C.addressof(texs), len(sc.textures), bary.ctypes.data, nm16.ctypes.data, color.ctypes.data,
+      N.ctypes.data, iN.ctypes.data)
+    return color, N, iN
+
+
+def emat_scene():
+    """feature soup + a quad whose diffuse map is a FLOAT4 texture: retrieve_material's FLOAT4 case falls through into the
+    UINT case (EmbreeRT/src/Context.cpp:458-472, no `break`), which the oracle restates."""
+    sc = soup_scene()
+    rng = np.random.default_rng(12)
+    tf = S.add_texture_float4(sc, rng.uniform(0.2, 1.0, (16, 16, 4)).astype(np.float32))
+    m = S.add_material(sc, (0.9, 0.8, 0.7), tex0=tf, uvscale=(2.0, 1.5), uvoffs=(0.25, -0.5))
+    sc.meshes.append(S._grid_quad((0, 0, 0), (1, 0, 0), (0, 1, 0), 2, 2, m, uv_rep=1.0, tex_dims=(16, 16)))
+    sc.instances.append((len(sc.meshes) - 1, S.translate(0.5, 0.5, -3.0) @ S.rotate_y(20) @ S.scale(1.5, 0.7, 1.0)))
+    return sc

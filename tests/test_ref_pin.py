@@ -409,3 +409,29 @@ def test_alpha_cutouts_are_where_the_oracle_leaves_cudart(oracle_lib):
     assert (bad & ~on_quad).sum() <= 3  # nothing else moves (a path that reaches the quad by a bounce may)
     assert np.abs(ref[bad & on_quad, :3]).max() == 0.0  # CUDART: black behind a cut-out in the first sample
     assert img[bad & on_quad, :3].mean() > 0.3  # the scene behind it
+
+
+GE = dict(np.load(Path(__file__).resolve().parent / "golden" / "ref_emat_vectors.npz"))
+
+
+def test_emode_material_matches_reference_retrieve_material(oracle_lib):
+    """The material step of the oracle's E-mode image (interpolated normal through the normal matrix, material colour times the
+    nearest texel of the first diffuse map, the FLOAT4-falls-through-into-UINT quirk) against the reference's own
+    Context::retrieve_material (EmbreeRT/src/Context.cpp:417-476, compiled from the reference tree): within 2e-6."""
+    from ref_pin_common import REF_EMAT_LIB, emat_scene, ref_emode_material
+
+    sc = emat_scene()
+    o = R.RenderContext(oracle_lib)
+    S.upload(o, sc, 8, 8)
+    f = o.L.fn("emode_material", C.c_int, [P, I, I, F, F, P, P])
+    kinds = GE["emat_kind"]
+    assert (kinds == 0).sum() > 100 and (kinds == 1).sum() > 100 and (kinds == 2).sum() > 50
+    for k, (row, ref) in enumerate(zip(GE["emat_in"], GE["emat_out"])):
+        inst, prim, u, v = int(row[0]), int(row[1]), float(row[2]), float(row[3])
+        color, iN = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        assert f(o._h, inst, prim, u, v, color.ctypes.data, iN.ctypes.data) == 0
+        assert np.abs(color - ref[:3]).max() <= 2e-6 * (1.0 + np.abs(ref[:3]).max()), (k, color, ref[:3])
+        assert np.abs(iN - ref[6:9]).max() <= 2e-6, (k, iN, ref[6:9])
+        if REF_EMAT_LIB.exists() and k % 16 == 0:  # the stored vectors cannot go stale where the reference is present
+            live = np.concatenate(ref_emode_material(sc, inst, prim, u, v))
+            assert np.array_equal(live, ref)
