@@ -237,6 +237,11 @@ def rotate_y(deg):
 # system::update_area_lights (system.cpp:967-1032)
 # ------------------------------------------------------------------------------------------------
 def extract_area_lights(scene: Scene):
+    """Caller-side stand-in for system::update_area_lights (system/src/rfw/system.cpp:985-1025): one AreaLight per emissive
+    triangle of every instance, position = centroid, radiance = material colour, energy = |colour|.  Two choices differ from
+    the reference for SCALED emissive instances (none of BASELINE's configs has one; the Sponza light is only translated):
+    the normal is normalised and the area is the world-space area, where the reference keeps the unnormalised
+    inverse-transpose product and the object-space `triangle.area` — inconsistent with its own world-space distances."""
     emissive = np.array([bool(np.any(m["diffuse"].astype(np.float32) > 1.0)) for m in scene.materials], bool)
     lights = []
     for inst_idx, (mesh_idx, M) in enumerate(scene.instances):
