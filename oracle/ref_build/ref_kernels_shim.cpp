@@ -50,6 +50,17 @@ struct RefScene
 	const unsigned *blue_noise; // 5 x 65536 uints (createBlueNoiseBuffer)
 };
 
+// probe pixel of the next render (RenderContext::set_probe_index) and what shade_rays stored for it at path length 0
+// (Kernels.cu:626-631), read back as CUDAContext::render_frame does for the first sample (Context.cpp:103-109)
+static unsigned g_probe_index = 0xffffffffu;
+static int g_probed_instance = -1, g_probed_prim = -1;
+static float g_probed_distance = -1.0f;
+REF_API void rfwref_set_probe_index(unsigned index) { g_probe_index = index; }
+REF_API void rfwref_get_probe_results(int *instance, int *prim, float *distance)
+{
+	*instance = g_probed_instance, *prim = g_probed_prim, *distance = g_probed_distance;
+}
+
 static mat4 load_mat4(const float *m)
 {
 	mat4 r;
@@ -90,7 +101,7 @@ REF_API int rfwref_cudart_render(const RefScene *sc, const float *view14, unsign
 	std::vector<Counters> counter_store(1); // on the heap, like the mapped host copy CUDAContext reads (m_Counters)
 	Counters &cnt = counter_store[0];
 	memset(&cnt, 0, sizeof(cnt));
-	cnt.probeIdx = 0xffffffffu;
+	cnt.probeIdx = g_probe_index; // counters->probeIdx = probe.x + probe.y * width (Context.cpp:70)
 	std::vector<vec4> acc(N, vec4(0.0f)), states(2 * N), origins(2 * N), directions(2 * N), throughputs(2 * N);
 	std::vector<PotentialContribution> connect(N);
 
@@ -141,6 +152,8 @@ REF_API int rfwref_cudart_render(const RefScene *sc, const float *view14, unsign
 		}
 		shadeRays(pathLength, pathCount);
 		unsigned activePaths = cnt.extensionRays;
+		if (s == 0) // Context.cpp:103-109 (m_SampleIndex == 0)
+			g_probed_instance = cnt.probedInstanceId, g_probed_prim = cnt.probedPrimId, g_probed_distance = cnt.probedDistance;
 		unsigned *rec = counters_out ? counters_out + size_t(s - first) * 8 * 3 : nullptr;
 		if (rec)
 			rec[0] = cnt.extensionRays, rec[1] = cnt.shadowRays, rec[2] = pathCount;

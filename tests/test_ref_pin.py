@@ -312,6 +312,24 @@ def test_stored_kernel_vectors_are_what_the_live_reference_kernels_produce(oracl
     live = reference_kernels_render(o, sc, pin_view14(sc, w, h, aperture), w, h, first, count)
     for key in ("acc", "origins", "directions", "states", "counters"):
         assert np.array_equal(live[key].view(np.uint32), GK["lens_" + key].view(np.uint32)), key
+    # probe: what shade_rays stores for counters->probeIdx at path length 0 (Kernels.cu:626-631) = get_probe_results
+    ref_lib = C.CDLL(str(Path(R.REPO_DIR) / "oracle" / "_ref" / "librfwref_kernels.so"))
+    probes_hit = 0
+    for px, py in ((w // 2, h // 2), (10, 30), (1, 1)):
+        ref_lib.rfwref_set_probe_index(C.c_uint(py * w + px))
+        reference_kernels_render(o, sc, pin_view14(sc, w, h, aperture), w, h, 0, 1)
+        ri, rp, rd = C.c_int(), C.c_int(), C.c_float()
+        ref_lib.rfwref_get_probe_results(C.byref(ri), C.byref(rp), C.byref(rd))
+        o.set_probe_index(px, py)
+        o.set_setting("mode", "pt"), o.set_setting("spp", 1)
+        o.render_frame(view_from14(pin_view14(sc, w, h, aperture)), R.RESET)
+        inst, prim, dist = o.get_probe_results()
+        if ri.value >= 0 and rd.value > 0:  # the probe pixel hit something
+            assert (inst, prim) == (ri.value, rp.value) and abs(dist - rd.value) <= 2e-6 * rd.value, (px, py)
+            probes_hit += 1
+    assert probes_hit >= 2
+    ref_lib.rfwref_set_probe_index(C.c_uint(0xFFFFFFFF))
+    o.set_probe_index(0, 0)
     # finalize: the reference's own blit_buffer (Kernels.cu:181-203) is accumulator * (1 / samples) in float32, which is what
     # the pipeline test divides the stored accumulators by and what the oracle and k_finalize compute
     from ref_pin_common import reference_blit
