@@ -55,7 +55,11 @@ struct RefScene
 static unsigned g_probe_index = 0xffffffffu;
 static int g_probed_instance = -1, g_probed_prim = -1;
 static float g_probed_distance = -1.0f;
-REF_API void rfwref_set_probe_index(unsigned index) { g_probe_index = index; }
+REF_API void rfwref_set_probe_index(unsigned index)
+{
+	g_probe_index = index;
+	g_probed_instance = g_probed_prim = -1, g_probed_distance = -1.0f;
+}
 REF_API void rfwref_get_probe_results(int *instance, int *prim, float *distance)
 {
 	*instance = g_probed_instance, *prim = g_probed_prim, *distance = g_probed_distance;
