@@ -119,9 +119,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    if not R.ORACLE_FAST_LIB.exists():
+    from oracle.oracle_lib import ORACLE_FAST_LIB, load_oracle  # the reference arm is the one place bench.py times oracle/
+
+    if not ORACLE_FAST_LIB.exists():
         g.build()
-    lib = R.load_oracle(fast=True)
+    lib = load_oracle(fast=True)
     sc = S.sponza_or_standin()
     w, h = CPU_SAMPLE
     ctx = R.RenderContext(lib)
@@ -400,7 +402,9 @@ def run():
     # ---- CPU baseline beside it (rank 0, N = 1 only) ------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        olib = R.load_oracle(fast=True)
+        from oracle.oracle_lib import load_oracle  # cpu_baseline leg only, after the timed region
+
+        olib = load_oracle(fast=True)
         octx = R.RenderContext(olib)
         w, h = CPU_SAMPLE
         osc = S.sponza_or_standin()

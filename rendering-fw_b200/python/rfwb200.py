@@ -1,9 +1,7 @@
 """ctypes binding of the C ABI in include/rfwb200.h, used by tests/, bench.py and __graft_entry__.py.
 
-The same wrapper class drives two libraries with identical call shapes:
-  * librfwb200.so            (product: hand-written sm_100a kernels)   prefix ``rfwb200_``
-  * oracle/librfworacle*.so  (CPU oracle, test infrastructure only)    prefix ``rfworacle_``
-so a parity test uploads one scene to both and compares the results.
+`Library` is a (path, symbol prefix) pair, so the test infrastructure can drive a second library with the same call
+shapes through the same wrapper class (the CPU checker is loaded by oracle/oracle_lib.py, never from this package).
 
 `RenderContext` mirrors the method names of the reference's plugin interface
 rfw::RenderContext (RFW/system/context/rfw/context/context.h:74-111); `Camera.get_view` restates
@@ -21,8 +19,6 @@ import numpy as np
 PKG_DIR = Path(__file__).resolve().parent.parent
 REPO_DIR = PKG_DIR.parent
 PRODUCT_LIB = Path(os.environ.get("RFWB200_LIB", PKG_DIR / "librfwb200.so"))  # override: tuning experiments only
-ORACLE_LIB = REPO_DIR / "oracle" / "librfworacle.so"
-ORACLE_FAST_LIB = REPO_DIR / "oracle" / "librfworacle_fast.so"
 BLUENOISE_BIN = PKG_DIR / "data" / "bluenoise_256spp.bin"
 
 RESET, CONVERGE = 0, 1
@@ -150,7 +146,7 @@ class Library:
         self.path = Path(path)
         self.prefix = prefix
         self.lib = C.CDLL(str(path))
-        self.is_oracle = prefix == "rfworacle_"
+        self.post_create = None  # optional callable(RenderContext) run after create (set by whoever loaded the library)
 
     def fn(self, name, restype=C.c_int, argtypes=None):
         f = getattr(self.lib, self.prefix + name)
@@ -166,10 +162,6 @@ class Library:
 
 def load_product() -> Library:
     return Library(PRODUCT_LIB, "rfwb200_")
-
-
-def load_oracle(fast: bool = False) -> Library:
-    return Library(ORACLE_FAST_LIB if fast else ORACLE_LIB, "rfworacle_")
 
 
 class Camera:
@@ -216,11 +208,9 @@ class RenderContext:
         self._h = C.c_void_p()
         self._keep = []  # arrays borrowed by the last upload calls (API contract: caller keeps them alive during the call)
         self._check(self.L.fn("create", C.c_int, [C.c_int, C.POINTER(C.c_void_p)])(device, C.byref(self._h)))
-        if self.L.is_oracle:
-            table = np.fromfile(BLUENOISE_BIN, dtype=np.uint8)
-            self._check(self.L.fn("set_blue_noise", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t])(
-                self._h, table.ctypes.data, table.size))
         self.width = self.height = 0
+        if self.L.post_create is not None:
+            self.L.post_create(self)
 
     # -- plumbing --
     def _check(self, rc: int):
@@ -465,7 +455,7 @@ class RenderContext:
             self._h, C.byref(view), sample_index, o.ctypes.data, d.ctypes.data, n))
         return o, d
 
-    # -- oracle-only --
+    # -- entry points librfwb200.so does not export (a checker library may) --
     def intersect_prim(self, origin, direction, inst: int, prim: int, t_min: float = 1e-5) -> float:
         o, d = _f32(origin, (-1,)), _f32(direction, (-1,))
         t = C.c_float()

@@ -23,9 +23,9 @@ def built():
 
 @pytest.fixture(scope="session")
 def oracle_lib(built):
-    import rfwb200 as R
+    from oracle.oracle_lib import load_oracle
 
-    return R.load_oracle()
+    return load_oracle()
 
 
 @pytest.fixture(scope="session")

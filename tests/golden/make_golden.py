@@ -18,6 +18,7 @@ sys.path.insert(0, str(REPO))
 import ctypes as C  # noqa: E402
 
 import rfwb200 as R  # noqa: E402
+from oracle.oracle_lib import load_oracle  # noqa: E402
 import scenes as S  # noqa: E402
 
 OUT = Path(__file__).resolve().parent
@@ -47,7 +48,7 @@ def scalar_kats(lib):
 
 
 def main():
-    lib = R.load_oracle()
+    lib = load_oracle()
     np.savez_compressed(OUT / "scalar_kats.npz", **scalar_kats(lib))
 
     W, H = 64, 48

@@ -13,6 +13,8 @@ REPO = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(REPO / "rendering-fw_b200" / "python"))
 sys.path.insert(0, str(REPO / "tests"))
 import rfwb200 as R  # noqa: E402
+sys.path.insert(0, str(REPO))
+from oracle.oracle_lib import load_oracle  # noqa: E402
 import scenes as S  # noqa: E402
 from ref_pin_common import pin_cases, pin_scene, pin_view14, reference_kernels_render  # noqa: E402
 
@@ -23,7 +25,7 @@ def main():
     out = {}
     for name, (w, h, first, count, aperture) in pin_cases().items():
         sc = pin_scene(rich=(name in ("rich", "lights")), lights=(name == "lights"))
-        o = R.RenderContext(R.load_oracle())  # only to build and export the MBVHs in the reference's node layout
+        o = R.RenderContext(load_oracle())  # only to build and export the MBVHs in the reference's node layout
         S.upload(o, sc, w, h)
         ref = reference_kernels_render(o, sc, pin_view14(sc, w, h, aperture), w, h, first, count)
         out[name + "_acc"] = ref["acc"]

@@ -6,6 +6,7 @@ from pathlib import Path
 import numpy as np
 
 import rfwb200 as R
+from oracle.oracle_lib import load_oracle
 import scenes as S
 
 REF_LIB = R.REPO_DIR / "oracle" / "_ref" / "librfwref.so"
@@ -155,7 +156,7 @@ class OracleScalar(RefLib):
     prefix = "rfworacle_"
 
     def __init__(self):
-        self.L = R.load_oracle()
+        self.L = load_oracle()
         self.lib = self.L.lib
         self.ctx = R.RenderContext(self.L)
 
@@ -250,7 +251,7 @@ def soup_inputs(rng, ref=None):
 def reference_soup_outputs(ref, sc, inp):
     """run the soup queries through the reference headers"""
     res = {}
-    orc = R.RenderContext(R.load_oracle())
+    orc = R.RenderContext(load_oracle())
     S.upload(orc, sc, 16, 16)
     trav = ref.f("traverse_mbvh", I, [P, P, P, P, P, P, F, P, P, P])
     occl = ref.f("occluded_mbvh", I, [P, P, P, P, P, P, F, F])

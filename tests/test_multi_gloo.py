@@ -24,13 +24,15 @@ def _worker(rank, world, port, w, h, ret):
     import torch
     import torch.distributed as dist
 
+    sys.path.insert(0, str(REPO))
     import rfwb200 as R
+    from oracle.oracle_lib import load_oracle
     import scenes as S
 
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     sc = S.cornell_box(unit_scale=True)
-    ctx = R.RenderContext(R.load_oracle())
+    ctx = R.RenderContext(load_oracle())
     S.upload(ctx, sc, w, h)
     ctx.render_frame(sc.camera(w, h), R.RESET)
     full = ctx.read_framebuffer().reshape(-1, 4)

@@ -12,6 +12,7 @@ import numpy as np
 import pytest
 
 import rfwb200 as R
+from oracle.oracle_lib import load_oracle
 import scenes as S
 from ref_pin_common import REF_LIB, OracleScalar, RefLib, fp, patched_materials, reference_soup_outputs, soup_scene
 
@@ -85,7 +86,7 @@ def _single_mesh_context(sc, mi):
     s2.materials, s2.tex_ids, s2.textures = sc.materials, sc.tex_ids, sc.textures
     s2.meshes = [sc.meshes[mi]]
     s2.instances = [(0, np.eye(4))]
-    ctx = R.RenderContext(R.load_oracle())
+    ctx = R.RenderContext(load_oracle())
     S.upload(ctx, s2, 8, 8)
     return ctx
 
@@ -110,7 +111,7 @@ def test_mbvh_traversal_matches_reference(mi):
 
 def test_get_shading_data_matches_reference():
     sc = soup_scene()
-    ctx = R.RenderContext(R.load_oracle())
+    ctx = R.RenderContext(load_oracle())
     S.upload(ctx, sc, 8, 8)
     f = ctx.L.fn("shading_data", C.c_int, [P, I, I, P, F, F, F, P, P, P, P])
     got = []
@@ -130,7 +131,7 @@ def test_get_shading_data_matches_reference():
 
 def test_light_sampling_matches_reference():
     sc = soup_scene()
-    ctx = R.RenderContext(R.load_oracle())
+    ctx = R.RenderContext(load_oracle())
     S.upload(ctx, sc, 8, 8)
     rpl = ctx.L.fn("random_point_on_light", None, [P, F, F, P, P, P, P, P, P])
     lpp = ctx.L.fn("light_pick_prob", F, [P, I, P, P, P])
