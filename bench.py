@@ -373,7 +373,8 @@ def run():
     total_alg = fc.algorithmic_bytes()
     alg_sum = sum(alg.values())
     alg["acc_rmw"] = total_alg - alg_sum
-    launches_per_frame = {"primary": SPP, "trace": SPP * MAX_PATH, "shade": SPP * (MAX_PATH + 1), "finalize": 1}
+    nb = max(1, int(st.wavefronts)) if hasattr(st, "wavefronts") else 1  # wavefronts per frame (all samples travel in one when they fit)
+    launches_per_frame = {"primary": nb, "trace": nb * MAX_PATH, "shade": nb * (MAX_PATH + 1), "finalize": nb}
     dominant = max(("primary", "trace", "shade"), key=lambda k: stage[k])
     peak, peak_src = load_peaks()
     dom_ms_per_launch = stage[dominant] / launches_per_frame[dominant]

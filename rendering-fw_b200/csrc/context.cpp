@@ -181,35 +181,29 @@ struct rfwb200_context
 	DevBuf d_cw_nodes, d_nodes16, d_prim_cache, d_occ_cache;
 
 	// ---- wavefront state -----------------------------------------------------------------------------
+	// One wavefront carries up to `batch_spp` samples of every local pixel (BatchView); the planes hold local_pixels *
+	// batch_spp work items.  A frame of spp samples is ceil(spp / batch_spp) wavefronts run one after the other on the
+	// context's stream: 3 + 4 * bounces launches each, no host synchronisation.
 	DevBuf d_debug;
-	DevBuf d_O[2], d_D[2], d_T[2], d_hit, d_sO, d_sD, d_sE, d_acc, d_fb, d_counters, d_probe, d_frame, d_scratch_cursor;
+	DevBuf d_O[2], d_D[2], d_T[2], d_hit, d_sO, d_sD, d_sE, d_sample_acc, d_acc, d_fb, d_counters, d_ext_seen, d_probe, d_frame,
+		d_scratch_cursor;
+	DevBuf d_sort_key, d_sort_hist, d_sort_base, d_sort_chunk, d_sort_grid;
 	DevBuf d_display; // RGBA8 output of the tone-map pass (rfwb200_read_display), allocated on first use
 	WavefrontView wf{};
-	uint32_t counters_capacity_spp = 0;
-	// Sample lanes: sample s of a frame runs on lane s % n_lanes.  Lane 0 is the caller's stream and the buffers above;
-	// every further lane owns a CUDA stream and a full set of wavefront planes + accumulator, so the tail of one
-	// sample's launch (a single long ray can keep one warp busy for 200+ us, profiles/r01) overlaps with the next
-	// sample's work.  finalize sums the lane accumulators in lane order, so the result is deterministic.
-	struct Lane
-	{
-		DevBuf O[2], D[2], T[2], hit, sO, sD, sE, acc;
-		WavefrontView wf{};
-		cudaStream_t stream = nullptr;
-		cudaEvent_t done = nullptr;
-	};
-	std::vector<std::unique_ptr<Lane>> lanes; // lanes 1..n_lanes-1
-	int n_lanes = 4; // measured on Sponza 1080p 8 spp: 17.20 ms (1 lane), 15.84 (2), 15.76 (3), 15.68 (4)
-	cudaEvent_t ev_fork = nullptr;
+	uint32_t counters_capacity = 0; // wavefronts per frame the counter rows are allocated for
+	size_t items_capacity = 0;		// work items the wavefront planes are allocated for
+	int spp_batch = 0;				// setting "spp_batch": samples per wavefront, 0 = as many as fit (<= MAX_BATCH_SPP, <= 2^24 items)
+	uint32_t sort_bins_allocated = 0;
 
 	// ---- settings / state ------------------------------------------------------------------------------
-	RenderSettings rs{2, 10.0f, 1e-5f, 1, 0, 8, nullptr, -1, 9, 1, 0, 5}; // bounces: packed nodes + unsorted connect rays; camera rays: fp32 nodes (DESIGN.md sweep) // smem_nodes 0: measured fastest on B200 (DESIGN.md "staging")
+	RenderSettings rs{2, 10.0f, 1e-5f, 1, 0, 8, nullptr, -1, 9, 1, 0, 5, 1, 5, 0}; // bounces: packed nodes + unsorted connect rays; camera rays: fp32 nodes (DESIGN.md sweep) // smem_nodes 0: measured fastest on B200 (DESIGN.md "staging")
 	int spp = 1;
 	bool mode_pt = true;
 	LaunchDims dims{};
 	bool dims_valid = false;
 	uint32_t sample_index = 0;
 	uint32_t probe_x = 0, probe_y = 0;
-	uint32_t last_spp = 0, last_first_sample = 0;
+	uint32_t last_spp = 0, last_first_sample = 0, last_batches = 0;
 	uint64_t launches = 0;
 	rfwb200_render_stats stats{};
 	cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
@@ -218,7 +212,7 @@ struct rfwb200_context
 	bool timing = false;
 	struct StageEvent
 	{
-		int category; // 0 primary, 1 secondary (trace depth 1), 2 deep (trace depth >= 2), 3 shade, 4 finalize
+		int category; // 0 primary, 1 secondary (trace depth 1), 2 deep (trace depth >= 2), 3 shade, 4 finalize, 5 re-ordering
 		cudaEvent_t a, b;
 	};
 	std::vector<StageEvent> stage_events;
@@ -263,31 +257,29 @@ size_t shard_stride_pixels(const ShardView &s)
 	return size_t((total + s.world - 1) / s.world) * s.tile_w * s.tile_h;
 }
 
+// samples of a frame of `spp` samples that travel in one wavefront
+uint32_t batch_spp_for(const Ctx *c, uint32_t spp)
+{
+	const uint32_t P = std::max<uint32_t>(c->shard.local_pixels, 32);
+	uint32_t b = std::min<uint32_t>(spp, MAX_BATCH_SPP);
+	if (c->spp_batch > 0)
+		b = std::min<uint32_t>(b, uint32_t(c->spp_batch));
+	b = std::min<uint32_t>(b, std::max<uint32_t>(1u, (1u << 24) / P)); // the path index is a 24-bit field of the state word
+	return std::max<uint32_t>(b, 1u);
+}
+
+// per-pixel state: accumulator, framebuffer, hit caches
 int alloc_wavefront(Ctx *c)
 {
 	const size_t P = std::max<size_t>(c->shard.local_pixels, 32);
-	const size_t plane = P * sizeof(float4);
-	for (int i = 0; i < 2; i++)
-	{
-		CK(c->d_O[i].reserve(plane));
-		CK(c->d_D[i].reserve(plane));
-		CK(c->d_T[i].reserve(plane));
-	}
-	CK(c->d_hit.reserve(plane));
-	CK(c->d_sO.reserve(plane));
-	CK(c->d_sD.reserve(plane));
-	CK(c->d_sE.reserve(plane));
-	CK(c->d_acc.reserve(plane));
+	CK(c->d_acc.reserve(P * sizeof(float4)));
 	const size_t fb_pixels = c->shard.world == 1 ? size_t(c->width) * c->height : shard_stride_pixels(c->shard);
 	CK(c->d_fb.reserve(std::max(fb_pixels, P) * sizeof(float4)));
 	CK(c->d_probe.reserve(sizeof(ProbeResult)));
 	CK(c->d_frame.reserve(sizeof(FrameParams)));
+	CK(c->d_sort_grid.reserve(sizeof(SortGrid)));
 	CK(c->d_scratch_cursor.reserve(256));
 	WavefrontView &w = c->wf;
-	for (int i = 0; i < 2; i++)
-		w.O[i] = c->d_O[i].as<float4>(), w.D[i] = c->d_D[i].as<float4>(), w.T[i] = c->d_T[i].as<float4>();
-	w.hit = c->d_hit.as<float4>();
-	w.sO = c->d_sO.as<float4>(), w.sD = c->d_sD.as<float4>(), w.sE = c->d_sE.as<float4>();
 	w.accumulator = c->d_acc.as<float4>();
 	w.framebuffer = c->d_fb.as<float4>();
 	w.probe = c->d_probe.as<ProbeResult>();
@@ -298,52 +290,64 @@ int alloc_wavefront(Ctx *c)
 	CK(cudaMemsetAsync(c->d_occ_cache.ptr, 0xff, 2 * P * sizeof(uint32_t), c->stream));
 	w.occ_cache = c->d_occ_cache.as<uint32_t>();
 	w.frame = c->d_frame.as<FrameParams>();
-	w.n_acc_extra = 0;
-	while (int(c->lanes.size()) < c->n_lanes - 1)
-	{
-		std::unique_ptr<Ctx::Lane> l(new Ctx::Lane());
-		CK(cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking));
-		CK(cudaEventCreateWithFlags(&l->done, cudaEventDisableTiming));
-		c->lanes.push_back(std::move(l));
-	}
-	if (!c->ev_fork)
-		CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-	for (int li = 0; li < c->n_lanes - 1; li++)
-	{
-		Ctx::Lane &l = *c->lanes[li];
-		for (int i = 0; i < 2; i++)
-		{
-			CK(l.O[i].reserve(plane));
-			CK(l.D[i].reserve(plane));
-			CK(l.T[i].reserve(plane));
-		}
-		CK(l.hit.reserve(plane));
-		CK(l.sO.reserve(plane));
-		CK(l.sD.reserve(plane));
-		CK(l.sE.reserve(plane));
-		CK(l.acc.reserve(plane));
-		l.wf = w;
-		for (int i = 0; i < 2; i++)
-			l.wf.O[i] = l.O[i].as<float4>(), l.wf.D[i] = l.D[i].as<float4>(), l.wf.T[i] = l.T[i].as<float4>();
-		l.wf.hit = l.hit.as<float4>();
-		l.wf.sO = l.sO.as<float4>(), l.wf.sD = l.sD.as<float4>(), l.wf.sE = l.sE.as<float4>();
-		l.wf.accumulator = l.acc.as<float4>();
-		w.acc_extra[li] = l.acc.as<float4>();
-		w.n_acc_extra = li + 1;
-	}
+	w.grid = c->d_sort_grid.as<SortGrid>();
 	return RFWB200_OK;
 }
 
-int ensure_counters(Ctx *c, uint32_t spp)
+// per-work-item state of a wavefront of `bspp` samples per pixel, and the bins of the re-ordering pass
+int ensure_wavefront(Ctx *c, uint32_t bspp)
 {
-	if (spp > c->counters_capacity_spp)
+	const size_t items = std::max<size_t>(size_t(c->shard.local_pixels) * bspp, 32);
+	if (items > c->items_capacity)
 	{
-		CK(c->d_counters.reserve(size_t(spp) * MAX_DEPTH_SLOTS * sizeof(DepthCounters)));
-		c->counters_capacity_spp = spp;
+		CK(cudaStreamSynchronize(c->stream));
+		const size_t plane = items * sizeof(float4);
+		for (int i = 0; i < 2; i++)
+		{
+			CK(c->d_O[i].reserve(plane));
+			CK(c->d_D[i].reserve(plane));
+			CK(c->d_T[i].reserve(plane));
+		}
+		CK(c->d_hit.reserve(plane));
+		CK(c->d_sO.reserve(plane));
+		CK(c->d_sD.reserve(plane));
+		CK(c->d_sE.reserve(plane));
+		CK(c->d_sample_acc.reserve(plane));
+		CK(c->d_sort_key.reserve(items * sizeof(uint2)));
+		c->items_capacity = items;
+	}
+	const uint32_t bins = 1u << (3 * c->rs.sort_cell_bits + 3);
+	if (bins > c->sort_bins_allocated)
+	{
+		CK(cudaStreamSynchronize(c->stream));
+		CK(c->d_sort_hist.reserve(size_t(bins) * sizeof(uint32_t)));
+		CK(c->d_sort_base.reserve(size_t(bins) * sizeof(uint32_t)));
+		CK(c->d_sort_chunk.reserve(size_t(std::max<uint32_t>(bins / SORT_CHUNK, 1)) * sizeof(uint32_t)));
+		CK(cudaMemsetAsync(c->d_sort_hist.ptr, 0, c->d_sort_hist.bytes, c->stream)); // k_sort_scan leaves the counts at zero again
+		c->sort_bins_allocated = bins;
+	}
+	WavefrontView &w = c->wf;
+	for (int i = 0; i < 2; i++)
+		w.O[i] = c->d_O[i].as<float4>(), w.D[i] = c->d_D[i].as<float4>(), w.T[i] = c->d_T[i].as<float4>();
+	w.hit = c->d_hit.as<float4>();
+	w.sO = c->d_sO.as<float4>(), w.sD = c->d_sD.as<float4>(), w.sE = c->d_sE.as<float4>();
+	w.sample_acc = c->d_sample_acc.as<float4>();
+	w.sort_key = c->d_sort_key.as<uint2>();
+	w.sort_hist = c->d_sort_hist.as<uint32_t>(), w.sort_base = c->d_sort_base.as<uint32_t>(), w.sort_chunk = c->d_sort_chunk.as<uint32_t>();
+	return RFWB200_OK;
+}
+
+int ensure_counters(Ctx *c, uint32_t batches)
+{
+	if (batches > c->counters_capacity)
+	{
+		CK(cudaStreamSynchronize(c->stream));
+		CK(c->d_counters.reserve(size_t(batches) * MAX_DEPTH_SLOTS * sizeof(DepthCounters)));
+		CK(c->d_ext_seen.reserve(size_t(batches) * MAX_DEPTH_SLOTS * MAX_BATCH_SPP * sizeof(uint32_t)));
+		c->counters_capacity = batches;
 	}
 	c->wf.counters = c->d_counters.as<DepthCounters>();
-	for (auto &l : c->lanes)
-		l->wf.counters = c->wf.counters;
+	c->wf.ext_seen = c->d_ext_seen.as<uint32_t>();
 	return RFWB200_OK;
 }
 
@@ -809,10 +813,6 @@ extern "C"
 			cudaEventDestroy(c->ev_end);
 		for (auto &e : c->stage_events)
 			cudaEventDestroy(e.a), cudaEventDestroy(e.b);
-		for (auto &l : c->lanes)
-			cudaStreamDestroy(l->stream), cudaEventDestroy(l->done);
-		if (c->ev_fork)
-			cudaEventDestroy(c->ev_fork);
 		if (c->ev_geo_a)
 			cudaEventDestroy(c->ev_geo_a), cudaEventDestroy(c->ev_geo_b);
 		delete c;
@@ -823,16 +823,23 @@ extern "C"
 	{
 		REQUIRE(c != nullptr, "context is null");
 		REQUIRE(width > 0 && height > 0, "width and height must be positive");
-		REQUIRE(uint64_t(width) * height < (1u << 24), "more than 2^24 pixels: path index no longer fits the state word");
+		REQUIRE(uint64_t(width) * height < (1ull << 31), "more than 2^31 pixels");
 		if (int r = ensure_device(c))
 			return r;
+		const uint32_t old_w = c->width, old_h = c->height;
 		c->width = width, c->height = height;
 		recompute_shard(c);
+		// the 24-bit path index of the state word addresses the tile-padded local work items of this shard
+		if (uint64_t(c->shard.local_tiles) * c->shard.tile_w * c->shard.tile_h > (1ull << 24))
+		{
+			c->width = old_w, c->height = old_h;
+			recompute_shard(c);
+			return set_error(RFWB200_ERR_INVALID, "more than 2^24 (tile-padded) pixels in this shard: path index no longer fits the state word; "
+												  "shard the frame over more ranks (rfwb200_set_shard)");
+		}
 		if (int r = alloc_wavefront(c))
 			return r;
 		CK(cudaMemsetAsync(c->d_acc.ptr, 0, c->d_acc.bytes, c->stream));
-		for (int li = 0; li < c->n_lanes - 1; li++)
-			CK(cudaMemsetAsync(c->lanes[li]->acc.ptr, 0, c->lanes[li]->acc.bytes, c->stream));
 		CK(cudaMemsetAsync(c->d_fb.ptr, 0, c->d_fb.bytes, c->stream));
 		c->sample_index = 0;
 		c->initialised = true;
@@ -1402,20 +1409,32 @@ extern "C"
 		}
 		else if (k == "sample_lanes")
 		{
+			// Round 1 ran the samples of a frame as separate 1-spp wavefronts on up to four streams; all samples now travel
+			// in one wavefront (spp_batch), so the setting is accepted and has no effect.
 			const int n = atoi(v.c_str());
 			REQUIRE(n >= 1 && n <= 4, "sample_lanes must be in [1, 4]");
-			if (n != c->n_lanes)
-			{
-				CK(cudaDeviceSynchronize());
-				c->n_lanes = n;
-				while (int(c->lanes.size()) > n - 1)
-				{
-					cudaStreamDestroy(c->lanes.back()->stream), cudaEventDestroy(c->lanes.back()->done);
-					c->lanes.pop_back();
-				}
-				if (c->initialised)
-					return rfwb200_init(c, c->width, c->height);
-			}
+		}
+		else if (k == "spp_batch")
+		{
+			const int n = atoi(v.c_str());
+			REQUIRE(n >= 0 && n <= MAX_BATCH_SPP, "spp_batch must be in [0, 64] (0 = as many samples per wavefront as fit)");
+			c->spp_batch = n;
+		}
+		else if (k == "sort")
+		{
+			REQUIRE(v == "on" || v == "off" || v == "1" || v == "0", "sort must be on or off");
+			c->rs.sort_mode = (v == "on" || v == "1") ? 1 : 0;
+		}
+		else if (k == "sort_cell_bits")
+		{
+			const int n = atoi(v.c_str());
+			REQUIRE(n >= 3 && n <= 6, "sort_cell_bits must be in [3, 6] (grid cells per axis = 2^bits)");
+			c->rs.sort_cell_bits = n;
+		}
+		else if (k == "sort_major")
+		{
+			REQUIRE(v == "cell" || v == "octant", "sort_major must be 'cell' or 'octant'");
+			c->rs.sort_dir_major = (v == "octant") ? 1 : 0;
 		}
 		else if (k == "spatial_splits")
 		{
@@ -1495,8 +1514,9 @@ extern "C"
 		REQUIRE(c && buf && buf_size > 0, "bad buffer");
 		const std::string s = "spp=" + std::to_string(c->spp) + "\nmode=pt|embree\nmax_path_length=" +
 							  std::to_string(c->rs.max_path_length) + "\nclamp=" + std::to_string(c->rs.clamp_value) +
-							  "\nsurvival_scale=on|off\nsmem_nodes=" + std::to_string(c->rs.smem_nodes) + "\nsample_lanes=" +
-							  std::to_string(c->n_lanes) + "\nfetch_threshold=" + std::to_string(c->rs.fetch_threshold) +
+							  "\nsurvival_scale=on|off\nsmem_nodes=" + std::to_string(c->rs.smem_nodes) + "\nspp_batch=" +
+							  std::to_string(c->spp_batch) + "\nsort=on|off\nsort_cell_bits=" + std::to_string(c->rs.sort_cell_bits) +
+							  "\nsort_major=cell|octant\nfetch_threshold=" + std::to_string(c->rs.fetch_threshold) +
 							  "\ntrace_variant=" + std::to_string(c->rs.trace_variant) + "\nprimary_variant=" +
 							  std::to_string(c->rs.primary_variant) + "\nbvh=4|8\nbuilder=sbvh|lbvh\nspatial_splits=on|off\nrefit=device|host" +
 							  "\nshade_math=fast|ieee\ntiming=on|off\n";
@@ -1514,18 +1534,21 @@ extern "C"
 		if (int r = ensure_dims(c))
 			return r;
 		const uint32_t spp = c->mode_pt ? uint32_t(c->spp) : 1u;
-		if (int r = ensure_counters(c, spp))
+		const uint32_t bspp = batch_spp_for(c, spp), batches = (spp + bspp - 1) / bspp;
+		if (int r = ensure_counters(c, batches))
 			return r;
+		if (c->mode_pt)
+			if (int r = ensure_wavefront(c, bspp))
+				return r;
 		cudaStream_t st = c->stream;
 		CK(cudaEventRecord(c->ev_begin, st));
 		if (status == RFWB200_RESET)
 		{
 			CK(cudaMemsetAsync(c->d_acc.ptr, 0, size_t(c->shard.local_pixels) * sizeof(float4), st));
-			for (int li = 0; li < c->n_lanes - 1; li++)
-				CK(cudaMemsetAsync(c->lanes[li]->acc.ptr, 0, size_t(c->shard.local_pixels) * sizeof(float4), st));
 			c->sample_index = 0;
 		}
-		CK(cudaMemsetAsync(c->d_counters.ptr, 0, size_t(spp) * MAX_DEPTH_SLOTS * sizeof(DepthCounters), st));
+		CK(cudaMemsetAsync(c->d_counters.ptr, 0, size_t(batches) * MAX_DEPTH_SLOTS * sizeof(DepthCounters), st));
+		CK(cudaMemsetAsync(c->d_ext_seen.ptr, 0, size_t(batches) * MAX_DEPTH_SLOTS * MAX_BATCH_SPP * sizeof(uint32_t), st));
 		if (c->sample_index == 0)
 		{
 			const ProbeResult none{0, 0, 0.f, 0};
@@ -1538,55 +1561,57 @@ extern "C"
 		if (c->mode_pt)
 		{
 			const uint32_t maxd = uint32_t(c->rs.max_path_length);
-			// per-stage timing wants undisturbed kernels: it runs every sample on lane 0
-			const int lanes = c->timing ? 1 : c->n_lanes;
-			if (lanes > 1)
+			const bool sort = c->rs.sort_mode != 0 && maxd > 0;
+			auto shade = c->shade_ieee ? launch_shade_ieee : launch_shade;
+			if (sort)
 			{
-				CK(cudaEventRecord(c->ev_fork, st)); // lanes start after the frame's clears / parameter upload
-				for (int li = 0; li < lanes - 1; li++)
-					CK(cudaStreamWaitEvent(c->lanes[li]->stream, c->ev_fork, 0));
+				CK(launch_sort_setup(c->scene, c->wf, c->rs, st)); // grid of the bins from the root of the current tree
+				c->launches += 1;
 			}
-			for (uint32_t s = 0; s < spp; s++)
+			for (uint32_t b = 0; b < batches; b++)
 			{
-				// the lane is a function of the GLOBAL sample index, so Converge sequences and one multi-spp call
-				// accumulate every sample into the same lane in the same order (bit-identical frames)
-				const int lane = int((c->sample_index + s) % uint32_t(lanes));
-				const WavefrontView &wf = lane == 0 ? c->wf : c->lanes[lane - 1]->wf;
-				cudaStream_t ls = lane == 0 ? st : c->lanes[lane - 1]->stream;
+				BatchView bv;
+				bv.spp = std::min(bspp, spp - b * bspp), bv.first_sample = b * bspp, bv.index = b;
+				bv.items = c->shard.local_pixels * bv.spp;
 				{
 					StageTimer t(c, 0);
-					CK(launch_primary(c->scene, c->shard, wf, c->rs, s, c->dims, ls));
+					CK(launch_primary(c->scene, c->shard, c->wf, c->rs, bv, c->dims, st));
 				}
 				{
 					StageTimer t(c, 3);
-					CK((c->shade_ieee ? launch_shade_ieee : launch_shade)(c->scene, c->shard, wf, c->rs, s, 0, c->dims, ls));
+					CK(shade(c->scene, c->shard, c->wf, c->rs, bv, 0, 0, 1, c->dims, st));
 				}
 				c->launches += 2;
 				for (uint32_t d = 1; d <= maxd; d++)
 				{
+					// re-ordering on: shade appends to planes [1], the sort moves them into planes [0], trace and shade read [0];
+					// off: the planes alternate per depth (Kernels.cu:578-584)
+					const uint32_t in = sort ? 0u : (d & 1u), out = sort ? 1u : (in ^ 1u);
+					if (sort)
+					{
+						StageTimer t(c, 5);
+						CK(launch_sort(c->wf, c->rs, bv, d, c->dims, st));
+						c->launches += 2;
+					}
 					{
 						StageTimer t(c, d == 1 ? 1 : 2);
-						CK(launch_trace(c->scene, c->shard, wf, c->rs, s, d, c->dims, ls));
+						CK(launch_trace(c->scene, c->shard, c->wf, c->rs, bv, d, in, c->dims, st));
 					}
 					{
 						StageTimer t(c, 3);
-						CK((c->shade_ieee ? launch_shade_ieee : launch_shade)(c->scene, c->shard, wf, c->rs, s, d, c->dims, ls));
+						CK(shade(c->scene, c->shard, c->wf, c->rs, bv, d, in, out, c->dims, st));
 					}
 					c->launches += 2;
 				}
-			}
-			if (lanes > 1)
-				for (int li = 0; li < lanes - 1; li++)
+				const bool last = b + 1 == batches;
 				{
-					CK(cudaEventRecord(c->lanes[li]->done, c->lanes[li]->stream));
-					CK(cudaStreamWaitEvent(st, c->lanes[li]->done, 0)); // join before finalize
+					StageTimer t(c, 4);
+					// blit_buffer, Kernels.cu:181-203
+					CK(launch_fold(c->shard, c->wf, bv, 1.0f / float(c->sample_index + spp), last ? 1 : 0, st));
 				}
-			c->sample_index += spp;
-			{
-				StageTimer t(c, 4);
-				CK(launch_finalize(c->shard, c->wf, 1.0f / float(c->sample_index), st)); // blit_buffer, Kernels.cu:181-203
+				c->launches += 1;
 			}
-			c->launches += 1;
+			c->sample_index += spp;
 		}
 		else
 		{
@@ -1598,7 +1623,7 @@ extern "C"
 			c->sample_index += 1;
 		}
 		CK(cudaEventRecord(c->ev_end, st));
-		c->last_spp = spp;
+		c->last_spp = spp, c->last_batches = batches;
 		c->frame_in_flight = true;
 		return RFWB200_OK;
 	}
@@ -1709,7 +1734,7 @@ extern "C"
 
 	static int fetch_counters(Ctx *c)
 	{
-		const size_t n = size_t(c->last_spp) * MAX_DEPTH_SLOTS;
+		const size_t n = size_t(c->last_batches) * MAX_DEPTH_SLOTS;
 		c->host_counters.assign(n, DepthCounters{});
 		if (n == 0)
 			return RFWB200_OK;
@@ -1748,10 +1773,10 @@ extern "C"
 			return RFWB200_OK;
 		}
 		const uint32_t maxd = uint32_t(c->rs.max_path_length);
-		for (uint32_t s = 0; s < c->last_spp; s++)
+		out->n_gen = out->n_ext = out->n_shade = live * c->last_spp;
+		for (uint32_t s = 0; s < c->last_batches; s++)
 		{
 			const DepthCounters *dc = &c->host_counters[size_t(s) * MAX_DEPTH_SLOTS];
-			out->n_gen += live, out->n_ext += live, out->n_shade += live;
 			for (uint32_t d = 0; d <= maxd; d++)
 			{
 				out->n_ext_out += dc[d].ext;
@@ -1794,6 +1819,8 @@ extern "C"
 			case 1: out->secondary_time += t; break;
 			case 2: out->deep_time += t; break;
 			case 3: out->shade_time += t; break;
+			case 5: out->animation_time += t; break; // no field of the reference's RenderStats fits the re-ordering pass; its
+													 // device time is reported in the one field this backend otherwise leaves 0
 			default: out->finalize_time += t; break;
 			}
 		}
@@ -1804,7 +1831,7 @@ extern "C"
 		if (c->mode_pt && c->last_spp)
 		{
 			uint64_t sec = 0, deep = 0, shadow = 0;
-			for (uint32_t s = 0; s < c->last_spp; s++)
+			for (uint32_t s = 0; s < c->last_batches; s++)
 			{
 				const DepthCounters *dc = &c->host_counters[size_t(s) * MAX_DEPTH_SLOTS];
 				for (uint32_t d = 1; d <= uint32_t(c->rs.max_path_length); d++)
@@ -1950,7 +1977,7 @@ extern "C"
 		if (int r = ensure_device(c))
 			return r;
 		const DevBuf *planes[11] = {&c->d_O[0], &c->d_O[1], &c->d_D[0], &c->d_D[1], &c->d_T[0], &c->d_T[1],
-									&c->d_hit,	&c->d_sO,	&c->d_sD,	&c->d_sE,	&c->d_acc};
+									&c->d_hit,	&c->d_sO,	&c->d_sD,	&c->d_sE,	&c->d_sample_acc};
 		REQUIRE(which >= 0 && which < 11, "bad plane");
 		REQUIRE(n * 16 <= planes[which]->bytes, "plane smaller than requested");
 		CK(cudaMemcpyAsync(host, planes[which]->ptr, n * 16, cudaMemcpyDeviceToHost, c->stream));
@@ -1986,7 +2013,7 @@ extern "C"
 		REQUIRE(c && out8_per_depth, "bad arguments");
 		if (int r = ensure_device(c))
 			return r;
-		REQUIRE(depth_slots <= size_t(c->counters_capacity_spp) * MAX_DEPTH_SLOTS, "more slots than allocated");
+		REQUIRE(depth_slots <= size_t(c->counters_capacity) * MAX_DEPTH_SLOTS, "more slots than allocated");
 		CK(cudaMemcpyAsync(out8_per_depth, c->d_counters.ptr, depth_slots * sizeof(DepthCounters), cudaMemcpyDeviceToHost, c->stream));
 		CK(cudaStreamSynchronize(c->stream));
 		return RFWB200_OK;

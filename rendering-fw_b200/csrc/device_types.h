@@ -69,7 +69,7 @@ struct alignas(16) ShadeTri
 };
 static_assert(sizeof(ShadeTri) == 96, "shading triangle is 6 x 16 bytes");
 
-// per (sample, depth) queue sizes and per-launch work cursors; zeroed once per frame.
+// per (wavefront batch, depth) queue sizes and per-launch work cursors; zeroed once per frame.
 struct DepthCounters
 {
 	uint32_t ext;		  // extension rays emitted by shade(depth)          (counters->extensionRays)
@@ -78,11 +78,33 @@ struct DepthCounters
 	uint32_t shade_cursor; // work cursor of the shade launch at this depth
 	uint32_t acc;		  // accumulator read-modify-writes at this depth
 	uint32_t shadow_traced; // shadow rays actually traced by connect (reference drops some)
-	uint32_t pad0, pad1;
+	uint32_t move_cursor;  // work cursor of the re-ordering pass in front of the trace launch at this depth
+	uint32_t pad1;
 };
 static_assert(sizeof(DepthCounters) == 32, "");
 
 constexpr int MAX_DEPTH_SLOTS = 8; // max_path_length + 1 <= 8
+constexpr int MAX_BATCH_SPP = 64;  // samples of a frame that travel in one wavefront (BatchView)
+
+// One wavefront carries `spp` samples of every local pixel: work item = ((block * spp + s) << 5) | lane, where block is
+// an 8x4-pixel block of the shard (32 consecutive local pixels) — so a warp of camera rays is one sample of one compact
+// block, the samples of a block are neighbours in the queue (they walk the same part of the tree right after each
+// other), and a frame is 3 + 4 * bounces launches however many samples it has.  The reference renders one sample per
+// render_frame call (CUDART/src/Context.cpp:75-80,149).
+struct BatchView
+{
+	uint32_t spp;		   // samples in this wavefront (<= MAX_BATCH_SPP)
+	uint32_t first_sample; // index within the frame of its first sample
+	uint32_t index;		   // wavefront number within the frame: selects the DepthCounters row
+	uint32_t items;		   // local_pixels * spp
+};
+
+// uniform grid over the scene box the bounce rays are binned in before they are traced (k_shade emits the key)
+struct SortGrid
+{
+	float lo[3];
+	float scale[3]; // cells per unit length
+};
 
 struct ProbeResult
 {
@@ -140,18 +162,26 @@ struct ShardView
 
 struct WavefrontView
 {
-	float4 *O[2], *D[2], *T[2]; // ping-pong planes: origin|pathIdx<<8|flags, direction|packed normal, throughput|pdf
+	float4 *O[2], *D[2], *T[2]; // ray planes: origin|pathIdx<<8|flags, direction|packed normal, throughput|pdf.  With re-ordering
+								// on, [0] is the queue the trace / shade launches read and [1] the staging queue shade appends
+								// to; with it off the two alternate per depth like Kernels.cu:578-584
 	float4 *hit;				// bits(u16|v16<<16), bits(shade_idx), bits(prim or -1), t
-	float4 *sO, *sD, *sE;		// connect queue: origin, direction|tmax, contribution|bits(local pixel)
-	float4 *accumulator;		// per local pixel (of this sample lane)
-	float4 *acc_extra[3];		// accumulators of the other sample lanes, summed by finalize in fixed order
-	int n_acc_extra;
+	float4 *sO, *sD, *sE;		// connect queue: origin, direction|tmax, contribution|bits(path index)
+	float4 *sample_acc;			// per work item (= per pixel and sample of the wavefront): radiance of that one sample
+	float4 *accumulator;		// per local pixel: sum over all samples since the last Reset (k_fold adds the wavefront's samples in order)
 	float4 *framebuffer;		// finalised
-	DepthCounters *counters;	// [spp][MAX_DEPTH_SLOTS]
+	DepthCounters *counters;	// [wavefront][MAX_DEPTH_SLOTS]
+	uint32_t *ext_seen;			// [wavefront][MAX_DEPTH_SLOTS][MAX_BATCH_SPP]: sample s emitted an extension ray at that depth
 	ProbeResult *probe;
 	uint32_t *occ_cache;		// [2][local pixels]: occluder of the pixel's previous connect ray at this depth parity (shadow_cache = 2)
 	uint32_t *prim_cache;		// per local pixel: triangle record hit by the previous camera ray of that pixel (a bound only)
 	const FrameParams *frame;
+	// re-ordering of the bounce queue (counting sort by origin cell + direction octant)
+	uint2 *sort_key;	 // per staging slot: (bin, rank inside the bin)
+	uint32_t *sort_hist; // per bin: rays emitted into it (zeroed again by k_sort_scan)
+	uint32_t *sort_base; // per bin: exclusive prefix inside its 4096-bin chunk
+	uint32_t *sort_chunk; // per chunk: rays in the chunk
+	const SortGrid *grid;
 };
 
 struct RenderSettings
@@ -169,6 +199,10 @@ struct RenderSettings
 	int shadow_cache; // connect rays first test a remembered occluder: 1 = of the lane's previous connect ray, 2 = of the same pixel's
 					  // previous connect ray at this depth (another sample); occlusion is yes/no, so frames do not change
 	int primary_variant; // the same for camera rays (coherent: fp32 nodes measured faster there than packed ones)
+	int sort_mode;		 // 1: bounce rays are re-ordered by (origin cell, direction octant) before they are traced
+	int sort_cell_bits;	 // grid resolution per axis: 2^bits cells (3..6)
+	int sort_dir_major;	 // 1: the octant is the most significant part of the key, 0: the cell is
 };
+constexpr int SORT_CHUNK = 4096; // bins scanned by one CTA of k_sort_scan
 
 } // namespace rfwb200

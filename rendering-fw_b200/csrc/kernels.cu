@@ -159,6 +159,40 @@ __device__ __forceinline__ bool local_to_pixel(const ShardView &sh, uint32_t j, 
 	return (x < sh.width) & (y < sh.height) & (ty < sh.tiles_y);
 }
 
+// work item of a wavefront -> (local pixel, sample of the wavefront); see BatchView (device_types.h)
+__device__ __forceinline__ void item_to_pixel_sample(const BatchView &bv, uint32_t item, uint32_t &j, uint32_t &s)
+{
+	const uint32_t grp = item >> 5, blk = grp / bv.spp;
+	s = grp - blk * bv.spp;
+	j = (blk << 5) | (item & 31u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// bin of a bounce ray for the re-ordering pass: Morton code of the origin's grid cell + direction octant.
+// Rays of one bin start in the same part of the scene and run towards the same octant, so the lanes of a warp walk
+// the same nodes (Garanzha & Loop 2010, "Fast ray sorting and breadth-first packet traversal"; the reference traces
+// its extension rays in the order shade happened to append them, Kernels.cu:788-793).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t spread3(uint32_t x)
+{
+	x = (x | (x << 16)) & 0x030000FFu;
+	x = (x | (x << 8)) & 0x0300F00Fu;
+	x = (x | (x << 4)) & 0x030C30C3u;
+	x = (x | (x << 2)) & 0x09249249u;
+	return x;
+}
+__device__ __forceinline__ uint32_t ray_bin(const SortGrid &g, int cell_bits, int dir_major, float ox, float oy, float oz, float dx,
+											float dy, float dz)
+{
+	const int hi = (1 << cell_bits) - 1;
+	const int cx = min(max(__float2int_rd((ox - g.lo[0]) * g.scale[0]), 0), hi);
+	const int cy = min(max(__float2int_rd((oy - g.lo[1]) * g.scale[1]), 0), hi);
+	const int cz = min(max(__float2int_rd((oz - g.lo[2]) * g.scale[2]), 0), hi);
+	const uint32_t cell = spread3(uint32_t(cx)) | (spread3(uint32_t(cy)) << 1) | (spread3(uint32_t(cz)) << 2);
+	const uint32_t oct = (dx < 0.0f ? 1u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 4u : 0u);
+	return dir_major ? ((oct << (3 * cell_bits)) | cell) : ((cell << 3) | oct);
+}
+
 // ------------------------------------------------------------------------------------------------
 // TMA bulk staging of the BVH prefix into shared memory
 // ------------------------------------------------------------------------------------------------
@@ -516,10 +550,174 @@ extern __shared__ __align__(128) unsigned char g_dyn_smem[];
 // PACKED = read the 80-byte BvhNode4Packed form of a node (five 128-bit loads per visit instead of seven, bfloat16
 // planes decoded with one shift / mask each); the staged shared-memory prefix (setting smem_nodes) exists only in
 // the <LQ 1, LEAN 0, !PACKED> variant.
+// What one trace launch reads: queue sizes (device-resident, written by the shade launch in front of it) and planes.
+struct TraceQueue
+{
+	uint32_t n_ext, n_shadow, total;
+	const float4 *Oin, *Din;
+	const uint32_t *seen; // ext_seen row of the depth that emitted these rays
+};
+template <bool PRIMARY>
+__device__ __forceinline__ TraceQueue open_queue(const ShardView &sh, const WavefrontView &wf, const BatchView &bv, uint32_t depth,
+												 uint32_t in_buf)
+{
+	TraceQueue q;
+	q.Oin = wf.O[in_buf], q.Din = wf.D[in_buf];
+	q.seen = nullptr;
+	if (PRIMARY)
+		q.n_ext = bv.items, q.n_shadow = 0;
+	else
+	{
+		const DepthCounters *prev = &wf.counters[bv.index * MAX_DEPTH_SLOTS + depth - 1];
+		q.n_ext = prev->ext;
+		q.n_shadow = prev->shadow;
+		q.seen = wf.ext_seen + size_t(bv.index * MAX_DEPTH_SLOTS + depth - 1) * MAX_BATCH_SPP;
+	}
+	q.total = q.n_ext + q.n_shadow;
+	return q;
+}
+
+// Moller-Trumbore against one triangle record, all conditions folded into one predicate (used for the cached candidates)
+__device__ __forceinline__ bool hits_record(const float4 *__restrict__ tris, uint32_t rec, V3 o, V3 d, float tmin, float tmax, float &t)
+{
+	const float4 a = __ldg(tris + size_t(rec) * 3 + 0);
+	const float4 b = __ldg(tris + size_t(rec) * 3 + 1);
+	const float4 c = __ldg(tris + size_t(rec) * 3 + 2);
+	const V3 p0 = mk(a.x, a.y, a.z), e1 = mk(a.w, b.x, b.y), e2 = mk(b.z, b.w, c.x);
+	const V3 h = cross(d, e2);
+	const float det = dot(e1, h);
+	const float f = 1.0f / det;
+	const V3 s = o - p0;
+	const float u = f * dot(s, h);
+	const V3 q = cross(s, e1);
+	const float vv = f * dot(d, q);
+	t = f * dot(e2, q);
+	return !(det > -c.z && det < c.z) && u >= 0.0f && u <= 1.0f && vv >= 0.0f && u + vv <= 1.0f && t > tmin && tmax > t;
+}
+
+// One work item of a trace launch becomes a ray.  Returns false when the item needs no traversal (padded pixel, connect
+// ray the reference never traces, connect ray stopped by a remembered occluder).
+//   camera ray  : item = ((block * spp + s) << 5) | lane; generates the ray (Kernels.cu:383-426), writes O/D
+//   extension   : item < n_ext, reads O/D
+//   connect     : item - n_ext indexes the connect queue; `pidx` is the path index its contribution goes to
+template <bool PRIMARY>
+__device__ __forceinline__ bool fetch_ray(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
+										  const BatchView &bv, const FrameParams &fp, const TraceQueue &q, uint32_t depth, uint32_t in_buf,
+										  uint32_t item, V3 &o, V3 &d, float &tmin, float &tmax, bool &shadow, uint32_t &pidx,
+										  uint32_t &occluder, uint32_t &occ_slot, uint32_t &n_traced)
+{
+	const float4 *__restrict__ tris = reinterpret_cast<const float4 *>(sc.tris);
+	if (PRIMARY)
+	{
+		uint32_t j, s, x, y;
+		item_to_pixel_sample(bv, item, j, s);
+		pidx = j;
+		if (!local_to_pixel(sh, j, x, y))
+		{
+			wf.hit[item] = make_float4(0.f, 0.f, __int_as_float(PRIM_DEAD), 0.f);
+			return false;
+		}
+		generate_pt(sc, fp, sh, x, y, fp.sample_base + bv.first_sample + s, o, d);
+		wf.O[in_buf][item] = make_float4(o.x, o.y, o.z, __uint_as_float((item << 8) + 1u));
+		wf.D[in_buf][item] = make_float4(d.x, d.y, d.z, 0.0f);
+		tmin = 1e-5f, tmax = 1e34f, shadow = false;
+		// Bound from an earlier sample of the pixel: the samples of a pixel differ by a sub-pixel jitter, so the triangle
+		// one of them hit is almost always hit by the next.  Its distance (plus a few ulps) only LIMITS the search — the
+		// triangle is found again by the traversal itself, in the usual order — so the result is bit-identical with and
+		// without the cache, whatever stale value a concurrent lane left here.
+		const uint32_t cand = rs.primary_cache ? wf.prim_cache[j] : 0xffffffffu;
+		float t;
+		if (cand < sc.tri_count && hits_record(tris, cand, o, d, tmin, 1e33f, t))
+			tmax = t * 1.000004f + 1e-30f;
+		return true;
+	}
+	if (item < q.n_ext)
+	{
+		const float4 O4 = q.Oin[item], D4 = q.Din[item];
+		o = mk(O4.x, O4.y, O4.z), d = mk(D4.x, D4.y, D4.z);
+		tmin = 1e-5f, tmax = 1e34f, shadow = false;
+		return true;
+	}
+	const uint32_t k = item - q.n_ext;
+	pidx = __float_as_uint(wf.sE[k].w);
+	// the reference only traces the connect queue of a sample when its bounce loop continues, i.e. when that sample
+	// emitted at least one extension ray at this depth (CUDART/src/Context.cpp:109-120)
+	if (q.seen[(pidx >> 5) % bv.spp] == 0u)
+		return false;
+	n_traced++;
+	const float4 O4 = wf.sO[k], D4 = wf.sD[k];
+	o = mk(O4.x, O4.y, O4.z), d = mk(D4.x, D4.y, D4.z);
+	tmin = rs.geometry_epsilon, tmax = D4.w, shadow = true;
+	if (rs.shadow_cache == 2)
+	{
+		uint32_t j, s;
+		item_to_pixel_sample(bv, pidx, j, s);
+		occ_slot = ((depth - 1u) & 1u) * sh.local_pixels + j;
+		occluder = wf.occ_cache[occ_slot];
+	}
+	float t;
+	if (rs.shadow_cache && occluder < sc.tri_count && hits_record(tris, occluder, o, d, tmin, tmax, t))
+		return false; // occluded: nothing to accumulate, the lane stays idle and takes the next item
+	return true;
+}
+
+// end of a ray: hit record of a closest-hit ray, or accumulator[path] += (contribution, 1) of an unoccluded connect ray
+// (Kernels.cu:457-459, 495-497).  Every path of a wavefront owns its accumulator slot (one per pixel and sample), so the
+// read-modify-write needs no atomic, exactly like the reference's one-sample-per-launch `+=`.
+__device__ __forceinline__ void retire_ray(const WavefrontView &wf, const TraceQueue &q, uint32_t item, bool shadow, uint32_t hit_tri,
+										   float hit_u, float hit_v, float tmax, uint32_t pidx, uint32_t &acc_count)
+{
+	if (!shadow)
+	{
+		float4 hit = make_float4(0.f, 0.f, __int_as_float(PRIM_MISS), 0.f);
+		if (hit_tri != 0xffffffffu)
+			hit = make_float4(__uint_as_float(pack_barycentrics(hit_u, hit_v)), __uint_as_float(hit_tri), __int_as_float(0), tmax);
+		wf.hit[item] = hit;
+	}
+	else if (hit_tri == 0xffffffffu)
+	{
+		const float4 E = wf.sE[item - q.n_ext];
+		float4 a = wf.sample_acc[pidx];
+		a.x += E.x, a.y += E.y, a.z += E.z, a.w += 1.0f;
+		wf.sample_acc[pidx] = a;
+		acc_count++;
+	}
+}
+
+// per-warp {start, end, rays, smid} record of the debug timeline + the launch's bookkeeping counters
+__device__ __forceinline__ void close_launch(const RenderSettings &rs, DepthCounters *curc, bool primary, bool dbg, unsigned long long dbg_t0,
+											 unsigned long long dbg_rays, uint32_t acc_count, uint32_t n_traced)
+{
+	const uint32_t lane = threadIdx.x & 31u;
+	if (dbg)
+	{
+		unsigned long long t1;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+		const unsigned long long n = __reduce_add_sync(0xffffffffu, uint32_t(dbg_rays));
+		if (lane == 0)
+		{
+			unsigned long long *rec = rs.debug + size_t(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4;
+			uint32_t smid;
+			asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+			rec[0] = dbg_t0, rec[1] = t1, rec[2] = n, rec[3] = smid;
+		}
+	}
+	if (!primary)
+	{
+		// bookkeeping for the algorithmic-bytes formula: one atomic per warp
+		acc_count = __reduce_add_sync(0xffffffffu, acc_count);
+		n_traced = __reduce_add_sync(0xffffffffu, n_traced);
+		if (lane == 0 && acc_count)
+			atomicAdd(&curc->acc, acc_count);
+		if (lane == 0 && n_traced)
+			atomicAdd(&curc->shadow_traced, n_traced);
+	}
+}
+
 template <bool PRIMARY, int LQ, int LEAN, bool PACKED>
 __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const SceneView sc, const ShardView sh, const WavefrontView wf,
-															const RenderSettings rs, const uint32_t sample_in_frame,
-															const uint32_t depth)
+															const RenderSettings rs, const BatchView bv, const uint32_t depth,
+															const uint32_t in_buf)
 {
 	constexpr bool STAGED = (LQ == 1 && LEAN == 0 && !PACKED);
 	__shared__ uint64_t mbar;
@@ -528,33 +726,16 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 	if (STAGED)
 		stage_nodes(snodes, sc.nodes, n_smem, &mbar);
 
-	DepthCounters *curc = &wf.counters[sample_in_frame * MAX_DEPTH_SLOTS + depth];
-	uint32_t n_ext, n_shadow;
-	if (PRIMARY)
-		n_ext = sh.local_pixels, n_shadow = 0;
-	else
-	{
-		const DepthCounters *prev = &wf.counters[sample_in_frame * MAX_DEPTH_SLOTS + depth - 1];
-		n_ext = prev->ext;
-		// the reference only traces the connect queue when the bounce loop continues, i.e. when at least
-		// one extension ray exists (CUDART/src/Context.cpp:109-120)
-		n_shadow = n_ext > 0 ? prev->shadow : 0u;
-	}
-	const uint32_t total = n_ext + n_shadow;
-	const uint32_t buf = depth & 1u;
-	const float4 *__restrict__ Oin = wf.O[buf];
-	const float4 *__restrict__ Din = wf.D[buf];
+	DepthCounters *curc = &wf.counters[bv.index * MAX_DEPTH_SLOTS + depth];
+	const TraceQueue q = open_queue<PRIMARY>(sh, wf, bv, depth, in_buf);
+	const uint32_t total = q.total;
 	const float4 *__restrict__ tris = reinterpret_cast<const float4 *>(sc.tris);
 	uint32_t *cursor = &curc->trace_cursor;
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t lt_mask = (1u << lane) - 1u;
 	FrameParams fp;
-	uint32_t sampleIndex = 0;
 	if (PRIMARY)
-	{
 		fp = *wf.frame;
-		sampleIndex = fp.sample_base + sample_in_frame;
-	}
 
 	unsigned long long dbg_t0 = 0, dbg_rays = 0;
 	const bool dbg = !PRIMARY && rs.debug != nullptr && int(depth) == rs.debug_depth;
@@ -582,8 +763,9 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 	uint32_t occluder = 0xffffffffu;
 	uint32_t hit_pos = 0xffffffffu; // record position of the closest hit (camera rays: remembered per pixel)
 	uint32_t occ_slot = 0;			// where this connect ray's occluder is remembered (shadow_cache = 2)
+	uint32_t pidx = 0;				// camera ray: local pixel; connect ray: path index its contribution belongs to
 	bool exhausted = false; // warp-uniform: the queue has no more items
-	uint32_t acc_count = 0;
+	uint32_t acc_count = 0, n_traced = 0;
 
 	for (;;)
 	{
@@ -603,95 +785,19 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 			if (!alive)
 			{
 				item = base + __popc(idle_mask & lt_mask);
-				if (item < total)
+				if (item < total &&
+					fetch_ray<PRIMARY>(sc, sh, wf, rs, bv, fp, q, depth, in_buf, item, o, d, tmin, tmax, shadow, pidx, occluder, occ_slot, n_traced))
 				{
-					bool valid = true;
-					if (PRIMARY)
-					{
-						uint32_t x, y;
-						if (local_to_pixel(sh, item, x, y))
-						{
-							generate_pt(sc, fp, sh, x, y, sampleIndex, o, d);
-							wf.O[0][item] = make_float4(o.x, o.y, o.z, __uint_as_float((item << 8) + 1u));
-							wf.D[0][item] = make_float4(d.x, d.y, d.z, 0.0f);
-							tmin = 1e-5f, tmax = 1e34f, shadow = false;
-							// Bound from the pixel's previous sample: the 8 samples of a pixel differ by a sub-pixel jitter, so
-							// the triangle one of them hit is almost always hit by the next.  Its distance (plus a few ulps) only
-							// LIMITS the search — the triangle is found again by the traversal itself, in the usual order — so the
-							// result is bit-identical with and without the cache, whatever stale value a concurrent lane left here.
-							const uint32_t cand = rs.primary_cache ? wf.prim_cache[item] : 0xffffffffu;
-							if (cand < sc.tri_count)
-							{
-								const float4 a = __ldg(tris + size_t(cand) * 3 + 0);
-								const float4 b = __ldg(tris + size_t(cand) * 3 + 1);
-								const float4 c = __ldg(tris + size_t(cand) * 3 + 2);
-								const V3 p0 = mk(a.x, a.y, a.z), e1 = mk(a.w, b.x, b.y), e2 = mk(b.z, b.w, c.x);
-								const V3 h = cross(d, e2);
-								const float det = dot(e1, h);
-								const float f = 1.0f / det;
-								const V3 s = o - p0;
-								const float u = f * dot(s, h);
-								const V3 q = cross(s, e1);
-								const float vv = f * dot(d, q);
-								const float t = f * dot(e2, q);
-								if (!(det > -c.z && det < c.z) && u >= 0.0f && u <= 1.0f && vv >= 0.0f && u + vv <= 1.0f && t > tmin && t < 1e33f)
-									tmax = t * 1.000004f + 1e-30f;
-							}
-						}
-						else
-						{
-							wf.hit[item] = make_float4(0.f, 0.f, __int_as_float(PRIM_DEAD), 0.f);
-							valid = false;
-						}
-					}
-					else if (item < n_ext)
-					{
-						const float4 O4 = Oin[item], D4 = Din[item];
-						o = mk(O4.x, O4.y, O4.z), d = mk(D4.x, D4.y, D4.z);
-						tmin = 1e-5f, tmax = 1e34f, shadow = false;
-					}
-					else
-					{
-						const uint32_t k = item - n_ext;
-						const float4 O4 = wf.sO[k], D4 = wf.sD[k];
-						o = mk(O4.x, O4.y, O4.z), d = mk(D4.x, D4.y, D4.z);
-						tmin = rs.geometry_epsilon, tmax = D4.w, shadow = true;
-						if (rs.shadow_cache == 2)
-						{
-							occ_slot = ((depth - 1u) & 1u) * sh.local_pixels + __float_as_uint(wf.sE[k].w);
-							occluder = wf.occ_cache[occ_slot];
-						}
-						if (rs.shadow_cache && occluder < sc.tri_count)
-						{
-							const float4 a = __ldg(tris + size_t(occluder) * 3 + 0);
-							const float4 b = __ldg(tris + size_t(occluder) * 3 + 1);
-							const float4 c = __ldg(tris + size_t(occluder) * 3 + 2);
-							const V3 p0 = mk(a.x, a.y, a.z), e1 = mk(a.w, b.x, b.y), e2 = mk(b.z, b.w, c.x);
-							const V3 h = cross(d, e2);
-							const float det = dot(e1, h);
-							const float f = 1.0f / det;
-							const V3 s = o - p0;
-							const float u = f * dot(s, h);
-							const V3 q = cross(s, e1);
-							const float vv = f * dot(d, q);
-							const float t = f * dot(e2, q);
-							if (!(det > -c.z && det < c.z) && u >= 0.0f && u <= 1.0f && vv >= 0.0f && u + vv <= 1.0f && t > tmin && tmax > t)
-								valid = false; // occluded: nothing to accumulate, the lane stays idle and takes the next item
-						}
-					}
-					if (valid)
-					{
-						dbg_rays++;
-						const float tiny = 1e-30f;
-						idx = 1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));
-						idy = 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));
-						idz = 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
-						oodx = o.x * idx, oody = o.y * idy, oodz = o.z * idz;
-						sgx = idx < 0.0f ? 1u : 0u, sgy = idy < 0.0f ? 1u : 0u, sgz = idz < 0.0f ? 1u : 0u;
-						stack[0] = SENTINEL;
-						sp = 1, cur = 0, leaf = leaf1 = leaf2 = NO_LEAF, hit_tri = 0xffffffffu, hit_u = 0.f, hit_v = 0.f;
-						alive = true;
-					}
+					dbg_rays++;
+					const float tiny = 1e-30f;
+					idx = 1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));
+					idy = 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));
+					idz = 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
+					oodx = o.x * idx, oody = o.y * idy, oodz = o.z * idz;
+					sgx = idx < 0.0f ? 1u : 0u, sgy = idy < 0.0f ? 1u : 0u, sgz = idz < 0.0f ? 1u : 0u;
+					stack[0] = SENTINEL;
+					sp = 1, cur = 0, leaf = leaf1 = leaf2 = NO_LEAF, hit_tri = 0xffffffffu, hit_u = 0.f, hit_v = 0.f;
+					alive = true;
 				}
 			}
 		}
@@ -900,50 +1006,12 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 		if (alive && finished)
 		{
 			alive = false;
-			if (!shadow)
-			{
-				float4 hit = make_float4(0.f, 0.f, __int_as_float(PRIM_MISS), 0.f);
-				if (hit_tri != 0xffffffffu)
-					hit = make_float4(__uint_as_float(pack_barycentrics(hit_u, hit_v)),
-									  __uint_as_float(hit_tri), __int_as_float(0), tmax);
-				wf.hit[item] = hit;
-				if (PRIMARY && rs.primary_cache)
-					wf.prim_cache[item] = hit_tri != 0xffffffffu ? hit_pos : 0xffffffffu;
-			}
-			else if (hit_tri == 0xffffffffu)
-			{
-				// unoccluded: accumulator[pixel] += (contribution, 1)  (Kernels.cu:495-497)
-				const float4 E = wf.sE[item - n_ext];
-				const uint32_t pixel = __float_as_uint(E.w);
-				float4 a = wf.accumulator[pixel];
-				a.x += E.x, a.y += E.y, a.z += E.z, a.w += 1.0f;
-				wf.accumulator[pixel] = a;
-				acc_count++;
-			}
+			retire_ray(wf, q, item, shadow, hit_tri, hit_u, hit_v, tmax, pidx, acc_count);
+			if (PRIMARY && rs.primary_cache)
+				wf.prim_cache[pidx] = hit_tri != 0xffffffffu ? hit_pos : 0xffffffffu;
 		}
 	}
-	if (dbg)
-	{
-		unsigned long long t1;
-		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-		const unsigned long long n = __reduce_add_sync(0xffffffffu, uint32_t(dbg_rays));
-		if (lane == 0)
-		{
-			unsigned long long *rec = rs.debug + size_t(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4;
-			uint32_t smid;
-			asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-			rec[0] = dbg_t0, rec[1] = t1, rec[2] = n, rec[3] = smid;
-		}
-	}
-	if (!PRIMARY)
-	{
-		// bookkeeping for the algorithmic-bytes formula: one atomic per warp
-		acc_count = __reduce_add_sync(0xffffffffu, acc_count);
-		if (lane == 0 && acc_count)
-			atomicAdd(&curc->acc, acc_count);
-		if (blockIdx.x == 0 && threadIdx.x == 0)
-			curc->shadow_traced = n_shadow;
-	}
+	close_launch(rs, curc, PRIMARY, dbg, dbg_t0, dbg_rays, acc_count, n_traced);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -953,38 +1021,21 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 // ------------------------------------------------------------------------------------------------
 template <bool PRIMARY>
 __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace_cw(const SceneView sc, const ShardView sh, const WavefrontView wf,
-															const RenderSettings rs, const uint32_t sample_in_frame,
-															const uint32_t depth)
+															const RenderSettings rs, const BatchView bv, const uint32_t depth,
+															const uint32_t in_buf)
 {
 	const uint4 *__restrict__ cwn = sc.cw_nodes;
 
-	DepthCounters *curc = &wf.counters[sample_in_frame * MAX_DEPTH_SLOTS + depth];
-	uint32_t n_ext, n_shadow;
-	if (PRIMARY)
-		n_ext = sh.local_pixels, n_shadow = 0;
-	else
-	{
-		const DepthCounters *prev = &wf.counters[sample_in_frame * MAX_DEPTH_SLOTS + depth - 1];
-		n_ext = prev->ext;
-		// the reference only traces the connect queue when the bounce loop continues, i.e. when at least
-		// one extension ray exists (CUDART/src/Context.cpp:109-120)
-		n_shadow = n_ext > 0 ? prev->shadow : 0u;
-	}
-	const uint32_t total = n_ext + n_shadow;
-	const uint32_t buf = depth & 1u;
-	const float4 *__restrict__ Oin = wf.O[buf];
-	const float4 *__restrict__ Din = wf.D[buf];
+	DepthCounters *curc = &wf.counters[bv.index * MAX_DEPTH_SLOTS + depth];
+	const TraceQueue q = open_queue<PRIMARY>(sh, wf, bv, depth, in_buf);
+	const uint32_t total = q.total;
 	const float4 *__restrict__ tris = reinterpret_cast<const float4 *>(sc.tris);
 	uint32_t *cursor = &curc->trace_cursor;
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t lt_mask = (1u << lane) - 1u;
 	FrameParams fp;
-	uint32_t sampleIndex = 0;
 	if (PRIMARY)
-	{
 		fp = *wf.frame;
-		sampleIndex = fp.sample_base + sample_in_frame;
-	}
 
 	unsigned long long dbg_t0 = 0, dbg_rays = 0;
 	const bool dbg = !PRIMARY && rs.debug != nullptr && int(depth) == rs.debug_depth;
@@ -1007,7 +1058,7 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace_cw(const Sc
 	int sp = 0;
 	bool trav_done = true;
 	bool exhausted = false; // warp-uniform: the queue has no more items
-	uint32_t acc_count = 0;
+	uint32_t acc_count = 0, n_traced = 0, pidx = 0, occluder = 0xffffffffu, occ_slot = 0;
 
 	for (;;)
 	{
@@ -1027,51 +1078,19 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace_cw(const Sc
 			if (!alive)
 			{
 				item = base + __popc(idle_mask & lt_mask);
-				if (item < total)
+				if (item < total &&
+					fetch_ray<PRIMARY>(sc, sh, wf, rs, bv, fp, q, depth, in_buf, item, o, d, tmin, tmax, shadow, pidx, occluder, occ_slot, n_traced))
 				{
-					bool valid = true;
-					if (PRIMARY)
-					{
-						uint32_t x, y;
-						if (local_to_pixel(sh, item, x, y))
-						{
-							generate_pt(sc, fp, sh, x, y, sampleIndex, o, d);
-							wf.O[0][item] = make_float4(o.x, o.y, o.z, __uint_as_float((item << 8) + 1u));
-							wf.D[0][item] = make_float4(d.x, d.y, d.z, 0.0f);
-							tmin = 1e-5f, tmax = 1e34f, shadow = false;
-						}
-						else
-						{
-							wf.hit[item] = make_float4(0.f, 0.f, __int_as_float(PRIM_DEAD), 0.f);
-							valid = false;
-						}
-					}
-					else if (item < n_ext)
-					{
-						const float4 O4 = Oin[item], D4 = Din[item];
-						o = mk(O4.x, O4.y, O4.z), d = mk(D4.x, D4.y, D4.z);
-						tmin = 1e-5f, tmax = 1e34f, shadow = false;
-					}
-					else
-					{
-						const uint32_t k = item - n_ext;
-						const float4 O4 = wf.sO[k], D4 = wf.sD[k];
-						o = mk(O4.x, O4.y, O4.z), d = mk(D4.x, D4.y, D4.z);
-						tmin = rs.geometry_epsilon, tmax = D4.w, shadow = true;
-					}
-					if (valid)
-					{
-						dbg_rays++;
-						const float tiny = 1e-30f;
-						ray.ox = o.x, ray.oy = o.y, ray.oz = o.z;
-						ray.idx = 1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));
-						ray.idy = 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));
-						ray.idz = 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
-						ray.octinv = cw_octinv(ray.idx, ray.idy, ray.idz);
-						ng = make_uint2(0u, 0x80000000u), held = tg = make_uint2(0u, 0u); // the root is "child 7 ^ octinv of nothing"
-						sp = 0, trav_done = false, hit_tri = 0xffffffffu, hit_u = 0.f, hit_v = 0.f;
-						alive = true;
-					}
+					dbg_rays++;
+					const float tiny = 1e-30f;
+					ray.ox = o.x, ray.oy = o.y, ray.oz = o.z;
+					ray.idx = 1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));
+					ray.idy = 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));
+					ray.idz = 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
+					ray.octinv = cw_octinv(ray.idx, ray.idy, ray.idz);
+					ng = make_uint2(0u, 0x80000000u), held = tg = make_uint2(0u, 0u); // the root is "child 7 ^ octinv of nothing"
+					sp = 0, trav_done = false, hit_tri = 0xffffffffu, hit_u = 0.f, hit_v = 0.f;
+					alive = true;
 				}
 			}
 		}
@@ -1161,48 +1180,10 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace_cw(const Sc
 		if (alive && finished)
 		{
 			alive = false;
-			if (!shadow)
-			{
-				float4 hit = make_float4(0.f, 0.f, __int_as_float(PRIM_MISS), 0.f);
-				if (hit_tri != 0xffffffffu)
-					hit = make_float4(__uint_as_float(pack_barycentrics(hit_u, hit_v)),
-									  __uint_as_float(hit_tri), __int_as_float(0), tmax);
-				wf.hit[item] = hit;
-			}
-			else if (hit_tri == 0xffffffffu)
-			{
-				// unoccluded: accumulator[pixel] += (contribution, 1)  (Kernels.cu:495-497)
-				const float4 E = wf.sE[item - n_ext];
-				const uint32_t pixel = __float_as_uint(E.w);
-				float4 a = wf.accumulator[pixel];
-				a.x += E.x, a.y += E.y, a.z += E.z, a.w += 1.0f;
-				wf.accumulator[pixel] = a;
-				acc_count++;
-			}
+			retire_ray(wf, q, item, shadow, hit_tri, hit_u, hit_v, tmax, pidx, acc_count);
 		}
 	}
-	if (dbg)
-	{
-		unsigned long long t1;
-		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-		const unsigned long long n = __reduce_add_sync(0xffffffffu, uint32_t(dbg_rays));
-		if (lane == 0)
-		{
-			unsigned long long *rec = rs.debug + size_t(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4;
-			uint32_t smid;
-			asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-			rec[0] = dbg_t0, rec[1] = t1, rec[2] = n, rec[3] = smid;
-		}
-	}
-	if (!PRIMARY)
-	{
-		// bookkeeping for the algorithmic-bytes formula: one atomic per warp
-		acc_count = __reduce_add_sync(0xffffffffu, acc_count);
-		if (lane == 0 && acc_count)
-			atomicAdd(&curc->acc, acc_count);
-		if (blockIdx.x == 0 && threadIdx.x == 0)
-			curc->shadow_traced = n_shadow;
-	}
+	close_launch(rs, curc, PRIMARY, dbg, dbg_t0, dbg_rays, acc_count, n_traced);
 }
 
 
@@ -1841,16 +1822,20 @@ __device__ V3 RandomPointOnLight(const SceneView &sc, float r0, float r1, V3 I, 
 					 // earlier kernel: 4.94 at 6, 5.67 at 4, 4.92 at 8
 #endif
 __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, const ShardView sh, const WavefrontView wf,
-											  const RenderSettings rs, const uint32_t sample_in_frame,
-											  const uint32_t pathLength)
+											  const RenderSettings rs, const BatchView bv, const uint32_t pathLength,
+											  const uint32_t buf, const uint32_t nbuf)
 {
-	DepthCounters *curc = &wf.counters[sample_in_frame * MAX_DEPTH_SLOTS + pathLength];
-	const uint32_t n_paths = pathLength == 0 ? sh.local_pixels : wf.counters[sample_in_frame * MAX_DEPTH_SLOTS + pathLength - 1].ext;
+	DepthCounters *curc = &wf.counters[bv.index * MAX_DEPTH_SLOTS + pathLength];
+	const uint32_t n_paths = pathLength == 0 ? bv.items : wf.counters[bv.index * MAX_DEPTH_SLOTS + pathLength - 1].ext;
 	const FrameParams fp = *wf.frame;
-	const uint32_t samplesTaken = fp.sample_base + sample_in_frame;
-	const uint32_t buf = pathLength & 1u, nbuf = buf ^ 1u;
 	const uint32_t lane = threadIdx.x & 31u;
 	uint32_t acc_count = 0;
+	// extension rays leave with the bin they are re-ordered by before the next trace launch (ray_bin)
+	const bool binning = rs.sort_mode != 0 && int(pathLength) < rs.max_path_length;
+	SortGrid grid{};
+	if (binning)
+		grid = *wf.grid;
+	uint32_t *seen = wf.ext_seen + size_t(bv.index * MAX_DEPTH_SLOTS + pathLength) * MAX_BATCH_SPP;
 	for (;;)
 	{
 		uint32_t base = 0;
@@ -1861,9 +1846,9 @@ __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, c
 			break;
 		const uint32_t job = base + lane;
 
-		bool do_acc = false, do_shadow = false, do_ext = false;
+		bool do_acc = false, do_shadow = false, do_ext = false, dead = false;
 		V3 accv = mk(0.f);
-		uint32_t pathIndex = 0;
+		uint32_t pathIndex = 0, pixelIndex = 0, sampleInBatch = 0;
 		float4 eO, eD, eT, cO, cD, cE;
 		eO = eD = eT = cO = cD = cE = make_float4(0.f, 0.f, 0.f, 0.f);
 
@@ -1871,7 +1856,8 @@ __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, c
 		{
 			const float4 hitData = wf.hit[job];
 			const int primIdx = __float_as_int(hitData.z);
-			if (primIdx != PRIM_DEAD)
+			dead = primIdx == PRIM_DEAD;
+			if (!dead)
 			{
 				const float4 O4 = wf.O[buf][job];
 				const float4 D4 = wf.D[buf][job];
@@ -1880,7 +1866,9 @@ __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, c
 				V3 throughput = mk(T4.x, T4.y, T4.z);
 				const float bsdfPdf = T4.w;
 				const V3 D = mk(D4.x, D4.y, D4.z);
-				pathIndex = __float_as_uint(O4.w) >> 8; // local pixel index
+				pathIndex = __float_as_uint(O4.w) >> 8; // work item the path started as: (local pixel, sample) of the wavefront
+				item_to_pixel_sample(bv, pathIndex, pixelIndex, sampleInBatch);
+				const uint32_t samplesTaken = fp.sample_base + bv.first_sample + sampleInBatch;
 				if (primIdx == PRIM_MISS)
 				{
 					// Kernels.cu:593-610
@@ -1921,8 +1909,8 @@ __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, c
 					if (pathLength == 0)
 					{
 						uint32_t px, py;
-						local_to_pixel(sh, pathIndex, px, py);
-						if (py * sh.width + px == fp.probe_pixel) // Kernels.cu:626-631
+						local_to_pixel(sh, pixelIndex, px, py);
+						if (py * sh.width + px == fp.probe_pixel && sampleInBatch == 0u) // Kernels.cu:626-631
 						{
 							wf.probe->inst = int(tri.inst_id), wf.probe->prim = int(tri.prim_id), wf.probe->dist = hitData.w;
 						}
@@ -1979,7 +1967,7 @@ __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, c
 						else
 							flags &= ~IS_SPECULAR;
 						uint32_t gx, gy;
-						local_to_pixel(sh, pathIndex, gx, gy);
+						local_to_pixel(sh, pixelIndex, gx, gy);
 						const uint32_t globalPixel = gy * sh.width + gx;
 						uint32_t seed = WangHash(globalPixel * 16789u + samplesTaken * 1791u + pathLength * 720898027u);
 						const float flip = (dot(D, N) > 0) ? -1.0f : 1.0f;
@@ -2062,13 +2050,22 @@ __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, c
 		}
 
 		// ---- converged commit: warp-aggregated compaction --------------------------------------
-		if (do_acc)
+		// accumulator[path] += contribution (Kernels.cu:607,690).  A path owns its slot (one per pixel and sample of the
+		// wavefront); the first shade launch of a wavefront visits every live path exactly once and initialises the slot,
+		// so no clear is needed between frames.
+		if (pathLength == 0)
 		{
-			float4 a = wf.accumulator[pathIndex];
-			a.x += accv.x, a.y += accv.y, a.z += accv.z;
-			wf.accumulator[pathIndex] = a;
-			acc_count++;
+			if (job < n_paths && !dead)
+				wf.sample_acc[job] = make_float4(accv.x, accv.y, accv.z, 0.0f);
 		}
+		else if (do_acc)
+		{
+			float4 a = wf.sample_acc[pathIndex];
+			a.x += accv.x, a.y += accv.y, a.z += accv.z;
+			wf.sample_acc[pathIndex] = a;
+		}
+		if (do_acc)
+			acc_count++;
 		const uint32_t lt_mask = (1u << lane) - 1u;
 		const uint32_t m_sh = __ballot_sync(0xffffffffu, do_shadow);
 		if (m_sh)
@@ -2094,6 +2091,21 @@ __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, c
 			{
 				const uint32_t slot = ebase + __popc(m_ex & lt_mask);
 				wf.O[nbuf][slot] = eO, wf.D[nbuf][slot] = eD, wf.T[nbuf][slot] = eT;
+				if (seen[sampleInBatch] == 0u) // this sample's bounce loop continues (CUDART/src/Context.cpp:109-120)
+					seen[sampleInBatch] = 1u;
+				if (binning)
+				{
+					// counting sort, first half: the lanes of the warp that emit into the same bin are found with one
+					// match instruction and take consecutive ranks from ONE atomic on the bin's counter
+					const uint32_t bin = ray_bin(grid, rs.sort_cell_bits, rs.sort_dir_major, eO.x, eO.y, eO.z, eD.x, eD.y, eD.z);
+					const uint32_t peers = __match_any_sync(m_ex, bin);
+					const int leader = __ffs(peers) - 1;
+					uint32_t rank = 0;
+					if (int(lane) == leader)
+						rank = atomicAdd(&wf.sort_hist[bin], uint32_t(__popc(peers)));
+					rank = __shfl_sync(m_ex, rank, leader) + __popc(peers & lt_mask);
+					wf.sort_key[slot] = make_uint2(bin, rank);
+				}
 			}
 		}
 	}
@@ -2106,29 +2118,156 @@ __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, c
 
 #if RFW_PART != 2 // ---- trace part ----
 // ------------------------------------------------------------------------------------------------
-// k_finalize — Kernels.cu:181-203: framebuffer = accumulator * 1/samples.  world == 1 writes the
-// row-major image; world > 1 keeps the tile-major shard for the gather.
+// k_fold — Kernels.cu:181-203: accumulator += the wavefront's samples (in sample order, so a frame does not depend on how
+// its samples were split into wavefronts or render_frame calls), framebuffer = accumulator * 1/samples.  world == 1
+// writes the row-major image; world > 1 keeps the tile-major shard for the gather.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_finalize(const ShardView sh, const WavefrontView wf, const float scale)
+__global__ void k_fold(const ShardView sh, const WavefrontView wf, const BatchView bv, const float scale, const int write_fb)
 {
 	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (j >= sh.local_pixels)
 		return;
-	float4 a = wf.accumulator[j];
-	for (int k = 0; k < wf.n_acc_extra; k++) // sample lanes: fixed summation order keeps the frame deterministic
+	uint32_t x, y;
+	const bool live = local_to_pixel(sh, j, x, y);
+	float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+	if (live)
 	{
-		const float4 b = wf.acc_extra[k][j];
-		a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+		a = wf.accumulator[j];
+		const uint32_t blk = j >> 5, lane = j & 31u;
+		for (uint32_t s = 0; s < bv.spp; s++)
+		{
+			const float4 b = wf.sample_acc[((blk * bv.spp + s) << 5) | lane];
+			a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+		}
+		wf.accumulator[j] = a;
 	}
+	if (!write_fb)
+		return;
 	a.x *= scale, a.y *= scale, a.z *= scale, a.w *= scale;
 	if (sh.world == 1)
 	{
-		uint32_t x, y;
-		if (local_to_pixel(sh, j, x, y))
+		if (live)
 			wf.framebuffer[size_t(y) * sh.width + x] = a;
 	}
 	else
 		wf.framebuffer[j] = a;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Re-ordering of the bounce queue: a counting sort whose first half (bin + rank inside the bin, one warp-aggregated
+// atomic per bin and warp) is done by k_shade while it appends the rays.
+//   k_sort_setup  the grid the bins are cells of, from the root of the current tree (runs once per frame: one warp)
+//   k_sort_scan   exclusive prefix of the bin counts inside 4096-bin chunks + the chunk totals; clears the counts
+//   k_sort_move   ray i of the staging queue goes to position chunk_prefix + base[bin] + rank of the trace queue
+// ------------------------------------------------------------------------------------------------
+__global__ void k_sort_setup(const SceneView sc, SortGrid *grid, const int cell_bits)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0)
+		return;
+	float lo[3] = {0.f, 0.f, 0.f}, hi[3] = {1.f, 1.f, 1.f};
+	if (sc.cw_nodes != nullptr && sc.cw_node_count > 0)
+	{
+		// compressed 8-wide root: grid origin p and step 2^(e - 127) per axis, 256 steps span the node
+		const uint4 q0 = sc.cw_nodes[0];
+		const float p[3] = {__uint_as_float(q0.x), __uint_as_float(q0.y), __uint_as_float(q0.z)};
+		for (int a = 0; a < 3; a++)
+		{
+			const uint32_t e = (q0.w >> (8 * a)) & 255u;
+			lo[a] = p[a], hi[a] = p[a] + 256.0f * __uint_as_float(e << 23);
+		}
+	}
+	else if (sc.node_count > 0)
+	{
+		const BvhNode4 &n = sc.nodes[0];
+		for (int a = 0; a < 3; a++)
+			lo[a] = 3e38f, hi[a] = -3e38f;
+		for (int k = 0; k < 4; k++) // fminf / fmaxf drop the NaN boxes of unused slots
+		{
+			lo[0] = fminf(lo[0], n.minx[k]), lo[1] = fminf(lo[1], n.miny[k]), lo[2] = fminf(lo[2], n.minz[k]);
+			hi[0] = fmaxf(hi[0], n.maxx[k]), hi[1] = fmaxf(hi[1], n.maxy[k]), hi[2] = fmaxf(hi[2], n.maxz[k]);
+		}
+	}
+	for (int a = 0; a < 3; a++)
+	{
+		const float ext = hi[a] - lo[a];
+		grid->lo[a] = lo[a];
+		grid->scale[a] = (ext > 0.0f && ext < 3e38f) ? float(1 << cell_bits) / ext : 0.0f;
+	}
+}
+
+__global__ void __launch_bounds__(1024) k_sort_scan(const WavefrontView wf)
+{
+	__shared__ uint32_t warp_sum[32];
+	const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+	uint4 *hist = reinterpret_cast<uint4 *>(wf.sort_hist + size_t(blockIdx.x) * SORT_CHUNK) + t;
+	const uint4 c = *hist;
+	*hist = make_uint4(0u, 0u, 0u, 0u);
+	const uint32_t mine = c.x + c.y + c.z + c.w;
+	uint32_t incl = mine;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1)
+	{
+		const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+		if (int(lane) >= o)
+			incl += v;
+	}
+	if (lane == 31u)
+		warp_sum[warp] = incl;
+	__syncthreads();
+	if (warp == 0)
+	{
+		const uint32_t w = warp_sum[lane];
+		uint32_t wi = w;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
+			if (int(lane) >= o)
+				wi += v;
+		}
+		warp_sum[lane] = wi - w; // exclusive
+		if (lane == 31u)
+			wf.sort_chunk[blockIdx.x] = wi;
+	}
+	__syncthreads();
+	const uint32_t excl = warp_sum[warp] + incl - mine;
+	reinterpret_cast<uint4 *>(wf.sort_base + size_t(blockIdx.x) * SORT_CHUNK)[t] = make_uint4(excl, excl + c.x, excl + c.x + c.y, excl + c.x + c.y + c.z);
+}
+
+__global__ void __launch_bounds__(256) k_sort_move(const WavefrontView wf, const BatchView bv, const uint32_t depth, const uint32_t n_chunks)
+{
+	// prefix of the chunk totals (at most 2^21 bins / 4096 = 512 chunks), recomputed by every CTA: cheaper than a third launch
+	__shared__ uint32_t chunk_prefix[512];
+	if (threadIdx.x < 32)
+	{
+		uint32_t carry = 0;
+		for (uint32_t b0 = 0; b0 < n_chunks; b0 += 32)
+		{
+			const uint32_t i = b0 + threadIdx.x;
+			const uint32_t v = i < n_chunks ? wf.sort_chunk[i] : 0u;
+			uint32_t incl = v;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1)
+			{
+				const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+				if (int(threadIdx.x) >= o)
+					incl += u;
+			}
+			if (i < n_chunks)
+				chunk_prefix[i] = carry + incl - v;
+			carry += __shfl_sync(0xffffffffu, incl, 31);
+		}
+	}
+	__syncthreads();
+	DepthCounters *row = &wf.counters[bv.index * MAX_DEPTH_SLOTS];
+	const uint32_t n = row[depth - 1].ext;
+	const float4 *__restrict__ sO = wf.O[1], *__restrict__ sD = wf.D[1], *__restrict__ sT = wf.T[1];
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+	{
+		const uint2 kr = wf.sort_key[i];
+		const uint32_t dst = chunk_prefix[kr.x / SORT_CHUNK] + wf.sort_base[kr.x] + kr.y;
+		wf.O[0][dst] = sO[i], wf.D[0][dst] = sD[i], wf.T[0][dst] = sT[i];
+	}
 }
 
 __global__ void k_assemble(const ShardView sh, const float4 *__restrict__ gathered, const size_t stride,
@@ -2483,15 +2622,16 @@ cudaError_t configure_launches(const RenderSettings &rs, uint32_t node_count, La
 	if (shade_per_sm < 1)
 		shade_per_sm = 1;
 	dims.shade_grid = sms * shade_per_sm;
+	dims.move_grid = sms * 8; // k_sort_move: 8 CTAs of 256 threads per SM, grid-stride over the device-resident queue size
 	return cudaSuccess;
 }
 
 cudaError_t launch_primary(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
-						   uint32_t sample_in_frame, const LaunchDims &dims, cudaStream_t stream)
+						   const BatchView &bv, const LaunchDims &dims, cudaStream_t stream)
 {
 	if (sc.cw_nodes != nullptr)
 	{
-		k_wavefront_trace_cw<true><<<dims.trace_grid, dims.trace_block, 0, stream>>>(sc, sh, wf, rs, sample_in_frame, 0u);
+		k_wavefront_trace_cw<true><<<dims.trace_grid, dims.trace_block, 0, stream>>>(sc, sh, wf, rs, bv, 0u, 0u);
 		return cudaGetLastError();
 	}
 	switch (rs.smem_nodes > 0 ? 0 : rs.primary_variant) // the staged prefix only exists in variant 0
@@ -2499,7 +2639,7 @@ cudaError_t launch_primary(const SceneView &sc, const ShardView &sh, const Wavef
 #define RFW_TRACE_CASE(V, LQ, LEAN, PACKED)                                                                                     \
 	case V:                                                                                                             \
 		k_wavefront_trace<true, LQ, LEAN, PACKED><<<dims.trace_grid, dims.trace_block, (LQ == 1 && LEAN == 0 && !PACKED) ? dims.trace_smem : 0, stream>>>( \
-			sc, sh, wf, rs, sample_in_frame, 0u);                                                                       \
+			sc, sh, wf, rs, bv, 0u, 0u);                                                                                \
 		break;
 		RFW_TRACE_CASE(1, 2, 0, false)
 		RFW_TRACE_CASE(3, 1, 1, false)
@@ -2516,11 +2656,11 @@ cudaError_t launch_primary(const SceneView &sc, const ShardView &sh, const Wavef
 	return cudaGetLastError();
 }
 cudaError_t launch_trace(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
-						 uint32_t sample_in_frame, uint32_t depth, const LaunchDims &dims, cudaStream_t stream)
+						 const BatchView &bv, uint32_t depth, uint32_t in_buf, const LaunchDims &dims, cudaStream_t stream)
 {
 	if (sc.cw_nodes != nullptr)
 	{
-		k_wavefront_trace_cw<false><<<dims.trace_grid, dims.trace_block, 0, stream>>>(sc, sh, wf, rs, sample_in_frame, depth);
+		k_wavefront_trace_cw<false><<<dims.trace_grid, dims.trace_block, 0, stream>>>(sc, sh, wf, rs, bv, depth, in_buf);
 		return cudaGetLastError();
 	}
 	switch (rs.smem_nodes > 0 ? 0 : rs.trace_variant)
@@ -2528,7 +2668,7 @@ cudaError_t launch_trace(const SceneView &sc, const ShardView &sh, const Wavefro
 #define RFW_TRACE_CASE(V, LQ, LEAN, PACKED)                                                                                     \
 	case V:                                                                                                             \
 		k_wavefront_trace<false, LQ, LEAN, PACKED><<<dims.trace_grid, dims.trace_block, (LQ == 1 && LEAN == 0 && !PACKED) ? dims.trace_smem : 0, stream>>>( \
-			sc, sh, wf, rs, sample_in_frame, depth);                                                                    \
+			sc, sh, wf, rs, bv, depth, in_buf);                                                                         \
 		break;
 		RFW_TRACE_CASE(1, 2, 0, false)
 		RFW_TRACE_CASE(3, 1, 1, false)
@@ -2544,10 +2684,26 @@ cudaError_t launch_trace(const SceneView &sc, const ShardView &sh, const Wavefro
 	}
 	return cudaGetLastError();
 }
-cudaError_t launch_finalize(const ShardView &sh, const WavefrontView &wf, float scale, cudaStream_t stream)
+cudaError_t launch_fold(const ShardView &sh, const WavefrontView &wf, const BatchView &bv, float scale, int write_fb, cudaStream_t stream)
 {
 	const uint32_t n = sh.local_pixels;
-	k_finalize<<<(n + 255) / 256, 256, 0, stream>>>(sh, wf, scale);
+	k_fold<<<(n + 255) / 256, 256, 0, stream>>>(sh, wf, bv, scale, write_fb);
+	return cudaGetLastError();
+}
+cudaError_t launch_sort_setup(const SceneView &sc, const WavefrontView &wf, const RenderSettings &rs, cudaStream_t stream)
+{
+	k_sort_setup<<<1, 32, 0, stream>>>(sc, const_cast<SortGrid *>(wf.grid), rs.sort_cell_bits);
+	return cudaGetLastError();
+}
+cudaError_t launch_sort(const WavefrontView &wf, const RenderSettings &rs, const BatchView &bv, uint32_t depth, const LaunchDims &dims,
+						cudaStream_t stream)
+{
+	const uint32_t bins = 1u << (3 * rs.sort_cell_bits + 3), n_chunks = bins / SORT_CHUNK;
+	k_sort_scan<<<n_chunks, 1024, 0, stream>>>(wf);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess)
+		return e;
+	k_sort_move<<<dims.move_grid, 256, 0, stream>>>(wf, bv, depth, n_chunks);
 	return cudaGetLastError();
 }
 cudaError_t launch_tone_map(const float4 *framebuffer, uint32_t *rgba8_out, uint32_t n, float contrast, float brightness,
@@ -2601,9 +2757,9 @@ cudaError_t launch_assemble(const ShardView &sh, const float4 *gathered, size_t 
 
 #if RFW_PART != 1 // ---- shade part ----
 cudaError_t LAUNCH_SHADE(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
-						 uint32_t sample_in_frame, uint32_t depth, const LaunchDims &dims, cudaStream_t stream)
+						 const BatchView &bv, uint32_t depth, uint32_t in_buf, uint32_t out_buf, const LaunchDims &dims, cudaStream_t stream)
 {
-	K_SHADE<<<dims.shade_grid, dims.shade_block, 0, stream>>>(sc, sh, wf, rs, sample_in_frame, depth);
+	K_SHADE<<<dims.shade_grid, dims.shade_block, 0, stream>>>(sc, sh, wf, rs, bv, depth, in_buf, out_buf);
 	return cudaGetLastError();
 }
 cudaError_t SHADE_OCCUPANCY(int block, int *per_sm)

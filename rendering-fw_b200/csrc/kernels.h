@@ -12,6 +12,7 @@ struct LaunchDims
 {
 	int trace_grid = 0, trace_block = 256;
 	int shade_grid = 0, shade_block = 128;
+	int move_grid = 0;
 	size_t trace_smem = 0; // dynamic shared memory of the trace kernels (staged BVH prefix)
 };
 
@@ -19,17 +20,24 @@ struct LaunchDims
 cudaError_t shade_occupancy(int block, int *per_sm); // defined next to k_shade
 cudaError_t configure_launches(const RenderSettings &rs, uint32_t node_count, LaunchDims &dims);
 
-// --- PT-mode stages (one sample = primary, shade(0), [trace(d), shade(d)] for d = 1..max) ---
+// --- PT-mode stages.  One wavefront (BatchView: up to MAX_BATCH_SPP samples of every local pixel) =
+//     primary, shade(0), [sort, trace(d), shade(d)] for d = 1..max, fold ---
 cudaError_t launch_primary(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
-						   uint32_t sample_in_frame, const LaunchDims &dims, cudaStream_t stream);
+						   const BatchView &bv, const LaunchDims &dims, cudaStream_t stream);
+// in_buf: ray planes the paths are read from; out_buf: planes the extension rays are appended to
 cudaError_t launch_shade(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
-						 uint32_t sample_in_frame, uint32_t depth, const LaunchDims &dims, cudaStream_t stream);
+						 const BatchView &bv, uint32_t depth, uint32_t in_buf, uint32_t out_buf, const LaunchDims &dims, cudaStream_t stream);
 // the same kernel built without -use_fast_math (setting "shade_math" = "ieee")
 cudaError_t launch_shade_ieee(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
-							  uint32_t sample_in_frame, uint32_t depth, const LaunchDims &dims, cudaStream_t stream);
+							  const BatchView &bv, uint32_t depth, uint32_t in_buf, uint32_t out_buf, const LaunchDims &dims, cudaStream_t stream);
 cudaError_t launch_trace(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
-						 uint32_t sample_in_frame, uint32_t depth, const LaunchDims &dims, cudaStream_t stream);
-cudaError_t launch_finalize(const ShardView &sh, const WavefrontView &wf, float scale, cudaStream_t stream);
+						 const BatchView &bv, uint32_t depth, uint32_t in_buf, const LaunchDims &dims, cudaStream_t stream);
+// accumulator += samples of the wavefront; write_fb: framebuffer = accumulator * scale (Kernels.cu:181-203)
+cudaError_t launch_fold(const ShardView &sh, const WavefrontView &wf, const BatchView &bv, float scale, int write_fb, cudaStream_t stream);
+// re-ordering of the extension rays shade(depth - 1) appended (planes [1] -> planes [0]): bin scan + move
+cudaError_t launch_sort_setup(const SceneView &sc, const WavefrontView &wf, const RenderSettings &rs, cudaStream_t stream);
+cudaError_t launch_sort(const WavefrontView &wf, const RenderSettings &rs, const BatchView &bv, uint32_t depth, const LaunchDims &dims,
+						cudaStream_t stream);
 // display pass (assets/shaders/tone-map.frag): ACES fit of the finalised framebuffer, packed to RGBA8
 cudaError_t launch_tone_map(const float4 *framebuffer, uint32_t *rgba8_out, uint32_t n, float contrast, float brightness,
 							cudaStream_t stream);

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
-"""A/B of the traversal-kernel instantiations on BASELINE.json configs[1] (Sponza 1920x1080 8 spp): frame time (all sample
-lanes, CUDA events) and per-stage times (one lane, `timing`) per setting.  One JSON line per variant."""
+"""A/B of the traversal-kernel instantiations on BASELINE.json configs[1] (Sponza 1920x1080 8 spp): frame time (CUDA events)
+and per-stage times (`timing`) per setting.  One JSON line per variant."""
 import argparse
 import json
 import sys
@@ -48,9 +48,11 @@ for var in a.variants.split(";"):
     st = ctx.get_stats()
     print(json.dumps({"variant": var, "frame_ms_median": float(np.median(ms[2:])), "frame_ms_min": float(np.min(ms[2:])),
                       "msamples_per_s": a.width * a.height * a.spp / (float(np.median(ms[2:])) * 1e3),
-                      "one_lane": {"primary": st.primary_time, "trace_d1": st.secondary_time, "trace_d2": st.deep_time, "shade": st.shade_time},
+                      "stages": {"primary": st.primary_time, "trace_d1": st.secondary_time, "trace_d2": st.deep_time, "shade": st.shade_time,
+                                 "sort": st.animation_time, "fold": st.finalize_time},
                       "pixels_differing_from_first": float((np.abs(img - ref).max(axis=-1) > 0).mean()),
                       "mean": float(img[..., :3].mean()), "bvh": ctx.get_bvh_info()}), flush=True)
     for k, v in kvs:  # back to the defaults
-        ctx.set_setting(k, {"trace_variant": "9", "primary_variant": "5", "bvh": "4", "shadow_cache": "off", "primary_cache": "on"}.get(k, v))
+        ctx.set_setting(k, {"trace_variant": "9", "primary_variant": "5", "bvh": "4", "shadow_cache": "off", "primary_cache": "on", "sort": "on",
+                               "sort_cell_bits": "5", "sort_major": "cell", "spp_batch": "0", "fetch_threshold": "8"}.get(k, v))
     ctx.set_setting("primary_variant", "5")
