@@ -196,7 +196,7 @@ struct rfwb200_context
 	uint32_t sort_bins_allocated = 0;
 
 	// ---- settings / state ------------------------------------------------------------------------------
-	RenderSettings rs{2, 10.0f, 1e-5f, 1, 0, 8, nullptr, -1, 9, 1, 0, 5, 1, 5, 0}; // bounces: packed nodes + unsorted connect rays; camera rays: fp32 nodes (DESIGN.md sweep) // smem_nodes 0: measured fastest on B200 (DESIGN.md "staging")
+	RenderSettings rs{2, 10.0f, 1e-5f, 1, 0, 8, nullptr, -1, 9, 1, 0, 9, 1, 5, 0, 0}; // bounces: packed nodes + unsorted connect rays; camera rays: fp32 nodes (DESIGN.md sweep) // smem_nodes 0: measured fastest on B200 (DESIGN.md "staging")
 	int spp = 1;
 	bool mode_pt = true;
 	LaunchDims dims{};
@@ -249,6 +249,8 @@ void recompute_shard(Ctx *c)
 	s.tiles_y = (s.height + s.tile_h - 1) / s.tile_h;
 	s.local_tiles = local_tile_count(s);
 	s.local_pixels = s.local_tiles * s.tile_w * s.tile_h;
+	s.inv_tile_pixels = 1.0f / float(s.tile_w * s.tile_h), s.inv_tiles_x = 1.0f / float(s.tiles_x);
+	s.inv_blocks_per_row = 1.0f / float(s.tile_w >> 3);
 }
 
 size_t shard_stride_pixels(const ShardView &s)
@@ -851,6 +853,7 @@ extern "C"
 		REQUIRE(c != nullptr, "context is null");
 		REQUIRE(world >= 1 && rank < world, "rank must be < world");
 		REQUIRE(tile_w >= 8 && tile_w % 8 == 0 && tile_h >= 4 && tile_h % 4 == 0, "tile must be a multiple of 8x4 pixels");
+		REQUIRE(tile_w <= 1024 && tile_h <= 1024, "tile must be at most 1024x1024 pixels");
 		c->shard.rank = rank, c->shard.world = world, c->shard.tile_w = tile_w, c->shard.tile_h = tile_h;
 		if (c->initialised)
 			return rfwb200_init(c, c->width, c->height);
@@ -1447,6 +1450,12 @@ extern "C"
 			REQUIRE(n >= 1 && n <= 32, "fetch_threshold must be in [1, 32]");
 			c->rs.fetch_threshold = n;
 		}
+		else if (k == "fetch_chunk")
+		{
+			const int n = atoi(v.c_str());
+			REQUIRE(n == 0 || (n >= 32 && n <= (1 << 20)), "fetch_chunk must be 0 (one shared front) or in [32, 2^20]");
+			c->rs.fetch_chunk = n;
+		}
 		else if (k == "timing")
 			c->timing = (v == "on" || v == "1");
 		else if (k == "trace_variant")
@@ -1516,7 +1525,7 @@ extern "C"
 							  std::to_string(c->rs.max_path_length) + "\nclamp=" + std::to_string(c->rs.clamp_value) +
 							  "\nsurvival_scale=on|off\nsmem_nodes=" + std::to_string(c->rs.smem_nodes) + "\nspp_batch=" +
 							  std::to_string(c->spp_batch) + "\nsort=on|off\nsort_cell_bits=" + std::to_string(c->rs.sort_cell_bits) +
-							  "\nsort_major=cell|octant\nfetch_threshold=" + std::to_string(c->rs.fetch_threshold) +
+							  "\nsort_major=cell|octant\nfetch_chunk=" + std::to_string(c->rs.fetch_chunk) + "\nfetch_threshold=" + std::to_string(c->rs.fetch_threshold) +
 							  "\ntrace_variant=" + std::to_string(c->rs.trace_variant) + "\nprimary_variant=" +
 							  std::to_string(c->rs.primary_variant) + "\nbvh=4|8\nbuilder=sbvh|lbvh\nspatial_splits=on|off\nrefit=device|host" +
 							  "\nshade_math=fast|ieee\ntiming=on|off\n";
@@ -1572,7 +1581,7 @@ extern "C"
 			{
 				BatchView bv;
 				bv.spp = std::min(bspp, spp - b * bspp), bv.first_sample = b * bspp, bv.index = b;
-				bv.items = c->shard.local_pixels * bv.spp;
+				bv.items = c->shard.local_pixels * bv.spp, bv.inv_spp = 1.0f / float(bv.spp);
 				{
 					StageTimer t(c, 0);
 					CK(launch_primary(c->scene, c->shard, c->wf, c->rs, bv, c->dims, st));

@@ -97,6 +97,7 @@ struct BatchView
 	uint32_t first_sample; // index within the frame of its first sample
 	uint32_t index;		   // wavefront number within the frame: selects the DepthCounters row
 	uint32_t items;		   // local_pixels * spp
+	float inv_spp;		   // 1 / spp (fast_div)
 };
 
 // uniform grid over the scene box the bounce rays are binned in before they are traced (k_shade emits the key)
@@ -158,6 +159,7 @@ struct ShardView
 	uint32_t tiles_x, tiles_y;	// tile grid of the full image
 	uint32_t local_tiles;		// tiles owned by this rank
 	uint32_t local_pixels;		// local_tiles * tile_w * tile_h (padded: edge tiles carry dead pixels)
+	float inv_tile_pixels, inv_tiles_x, inv_blocks_per_row; // reciprocals for the index divisions of local_to_pixel (fast_div)
 };
 
 struct WavefrontView
@@ -202,6 +204,7 @@ struct RenderSettings
 	int sort_mode;		 // 1: bounce rays are re-ordered by (origin cell, direction octant) before they are traced
 	int sort_cell_bits;	 // grid resolution per axis: 2^bits cells (3..6)
 	int sort_dir_major;	 // 1: the octant is the most significant part of the key, 0: the cell is
+	int fetch_chunk;	 // 0: idle lanes take the next entries of one shared front; > 0: a warp claims a private run of that many entries
 };
 constexpr int SORT_CHUNK = 4096; // bins scanned by one CTA of k_sort_scan
 

@@ -164,11 +164,14 @@ __global__ void __launch_bounds__(256) k_refit(const GeometryView g)
 // k_pack_nodes — BvhNode4 (128 B, fp32 planes) -> BvhNode4Packed (80 B, bfloat16 planes relative to the node's min
 // corner, rounded outwards).  One thread per node.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t bf16_down(float v, float p, float exact_lo)
+// The trace kernel decodes the plane in the LOWER half of a word exactly (bits << 16) and uses the one in the UPPER half
+// as the word stands, i.e. with up to 0xffff of foreign mantissa bits below it (kernels.cu CHILD_P): `slack` is that
+// worst case, and the rounding loops make sure the box still contains the exact one with it.
+__device__ __forceinline__ uint32_t bf16_down(float v, float p, float exact_lo, uint32_t slack)
 {
 	// largest bfloat16 <= v (v >= 0: truncation), then make sure p + decoded <= the exact plane
 	uint32_t b = __float_as_uint(v) >> 16;
-	while (b > 0u && p + __uint_as_float(b << 16) > exact_lo)
+	while (b > 0u && p + __uint_as_float((b << 16) | slack) > exact_lo)
 		b -= 1u;
 	return b;
 }
@@ -196,16 +199,17 @@ __global__ void __launch_bounds__(256) k_pack_nodes(const BvhNode4 *__restrict__
 		float p = 3.0e38f;
 		for (int k = 0; k < used; k++)
 			p = fminf(p, lo[a][k]);
-		if (used == 0)
-			p = 0.0f;
+		// the corner sits a hair below the smallest plane, so that an offset of zero with foreign low bits (a denormal)
+		// still decodes to a plane at or below the exact one
+		p = used == 0 ? 0.0f : p - (fabsf(p) * 1.2e-7f + 1e-30f);
 		o.p[a] = p;
 		uint32_t l[4], h[4];
 		for (int k = 0; k < 4; k++)
 		{
 			if (k < used)
-				l[k] = bf16_down(lo[a][k] - p, p, lo[a][k]), h[k] = bf16_up(hi[a][k] - p, p, hi[a][k]);
+				l[k] = bf16_down(lo[a][k] - p, p, lo[a][k], (k & 1) ? 0xffffu : 0u), h[k] = bf16_up(hi[a][k] - p, p, hi[a][k]);
 			else
-				l[k] = h[k] = 0x7fc0u; // NaN: an unused slot never passes the hit test
+				l[k] = 0x7f7fu, h[k] = 0xff7fu; // unused slot: inverted box (+3.4e38, -3.4e38), empty for every ray direction
 		}
 		o.plane[a][0] = l[0] | (l[1] << 16), o.plane[a][1] = l[2] | (l[3] << 16);
 		o.plane[a][2] = h[0] | (h[1] << 16), o.plane[a][3] = h[2] | (h[3] << 16);

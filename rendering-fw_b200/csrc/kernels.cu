@@ -145,15 +145,27 @@ __device__ __forceinline__ float blueNoiseSampler(const uint8_t *__restrict__ bn
 // round-robin to ranks, and inside a tile consecutive 32 indices form an 8x4 pixel block so one
 // warp traces a compact bundle of camera rays.
 // ------------------------------------------------------------------------------------------------
+// n / d for n, d < 2^24 with the reciprocal of d computed once on the host: the float estimate is within one of the
+// quotient and is corrected by the remainder (a 32-bit division by a run-time divisor is ~20 instructions, and the index
+// arithmetic below runs several of them per path)
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t d, float inv_d)
+{
+	uint32_t q = __float2uint_rz(__uint2float_rn(n) * inv_d);
+	const int32_t r = int32_t(n - q * d);
+	q += r >= int32_t(d) ? 1u : 0u;
+	q -= r < 0 ? 1u : 0u;
+	return q;
+}
+
 __device__ __forceinline__ bool local_to_pixel(const ShardView &sh, uint32_t j, uint32_t &x, uint32_t &y)
 {
 	const uint32_t tp = sh.tile_w * sh.tile_h;
-	const uint32_t lt = j / tp, w = j - lt * tp;
+	const uint32_t lt = fast_div(j, tp, sh.inv_tile_pixels), w = j - lt * tp;
 	const uint32_t gt = lt * sh.world + sh.rank;
-	const uint32_t ty = gt / sh.tiles_x, tx = gt - ty * sh.tiles_x;
+	const uint32_t ty = fast_div(gt, sh.tiles_x, sh.inv_tiles_x), tx = gt - ty * sh.tiles_x;
 	const uint32_t blk = w >> 5, lane = w & 31u;
 	const uint32_t bpr = sh.tile_w >> 3;
-	const uint32_t by = blk / bpr, bx = blk - by * bpr;
+	const uint32_t by = fast_div(blk, bpr, sh.inv_blocks_per_row), bx = blk - by * bpr;
 	x = tx * sh.tile_w + bx * 8u + (lane & 7u);
 	y = ty * sh.tile_h + by * 4u + (lane >> 3);
 	return (x < sh.width) & (y < sh.height) & (ty < sh.tiles_y);
@@ -162,7 +174,7 @@ __device__ __forceinline__ bool local_to_pixel(const ShardView &sh, uint32_t j, 
 // work item of a wavefront -> (local pixel, sample of the wavefront); see BatchView (device_types.h)
 __device__ __forceinline__ void item_to_pixel_sample(const BatchView &bv, uint32_t item, uint32_t &j, uint32_t &s)
 {
-	const uint32_t grp = item >> 5, blk = grp / bv.spp;
+	const uint32_t grp = item >> 5, blk = fast_div(grp, bv.spp, bv.inv_spp);
 	s = grp - blk * bv.spp;
 	j = (blk << 5) | (item & 31u);
 }
@@ -269,7 +281,6 @@ __device__ __forceinline__ float slab(float lo, float hi, float idir, float ood,
 		const float nz = slab(n.minz.C, n.maxz.C, idz, oodz, fz);                                                       \
 		const float tn = fmaxf(fmaxf(nx, ny), nz), tf = fminf(fminf(fx, fy), fz);                                       \
 		const bool h = (tf >= tn) & (tn < tmax) & (tf >= tmin);                                                         \
-		nh += h ? 1 : 0;                                                                                                \
 		key##K = h ? ((__float_as_uint(fmaxf(tn, 0.0f)) & 0xFFFFFFFCu) | uint32_t(K)) : MISSKEY(K);      \
 	}
 // Sort keys are the BIT PATTERNS of the clamped (>= 0) entry distances compared as unsigned integers — monotonic for
@@ -283,9 +294,9 @@ __device__ __forceinline__ float slab(float lo, float hi, float idir, float ood,
 		const float tn = fmaxf(fmaxf(fmaf(nearx.C, idx, -oodx), fmaf(neary.C, idy, -oody)), fmaf(nearz.C, idz, -oodz));  \
 		const float tf = fminf(fminf(fmaf(farx.C, idx, -oodx), fmaf(fary.C, idy, -oody)), fmaf(farz.C, idz, -oodz));     \
 		const bool h = (tf >= tn) & (tn < tmax) & (tf >= tmin);                                                         \
-		nh += h ? 1 : 0;                                                                                                \
 		key##K = h ? ((__float_as_uint(fmaxf(tn, 0.0f)) & 0xFFFFFFFCu) | uint32_t(K)) : MISSKEY(K);      \
 	}
+#define NO_CHILD_HIT(K0, K1, K2, K3) (min(min(K0, K1), min(K2, K3)) >= 0x7f000000u) // MISSKEY is the largest key
 #define CSWAP(A, B)                                                                                                     \
 	{                                                                                                                   \
 		const uint32_t lo_ = min(A, B), hi_ = max(A, B);                                                                \
@@ -399,12 +410,11 @@ __device__ __forceinline__ bool traverse(const SceneView &sc, const float4 *__re
 		{
 			const NodeRegs n = load_node(sc, snodes, n_smem, uint32_t(cur));
 			uint32_t key0, key1, key2, key3;
-			int nh = 0;
 			CHILD_T(0, x)
 			CHILD_T(1, y)
 			CHILD_T(2, z)
 			CHILD_T(3, w)
-			if (nh == 0)
+			if (NO_CHILD_HIT(key0, key1, key2, key3))
 			{
 				if (sp == 0)
 					break;
@@ -417,11 +427,11 @@ __device__ __forceinline__ bool traverse(const SceneView &sc, const float4 *__re
 			CSWAP(key1, key3)
 			CSWAP(key1, key2)
 			cur = PICK(key0);
-			if (nh > 1)
+			if (key1 < 0x7f000000u) // sorted: misses are last
 			{
-				if (nh > 3)
+				if (key3 < 0x7f000000u)
 					stack[sp++] = PICK(key3);
-				if (nh > 2)
+				if (key2 < 0x7f000000u)
 					stack[sp++] = PICK(key2);
 				stack[sp++] = PICK(key1);
 			}
@@ -642,7 +652,7 @@ __device__ __forceinline__ bool fetch_ray(const SceneView &sc, const ShardView &
 	pidx = __float_as_uint(wf.sE[k].w);
 	// the reference only traces the connect queue of a sample when its bounce loop continues, i.e. when that sample
 	// emitted at least one extension ray at this depth (CUDART/src/Context.cpp:109-120)
-	if (q.seen[(pidx >> 5) % bv.spp] == 0u)
+	if (q.seen[(pidx >> 5) - fast_div(pidx >> 5, bv.spp, bv.inv_spp) * bv.spp] == 0u)
 		return false;
 	n_traced++;
 	const float4 O4 = wf.sO[k], D4 = wf.sD[k];
@@ -766,6 +776,8 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 	uint32_t pidx = 0;				// camera ray: local pixel; connect ray: path index its contribution belongs to
 	bool exhausted = false; // warp-uniform: the queue has no more items
 	uint32_t acc_count = 0, n_traced = 0;
+	uint32_t chunk_pos = 0, chunk_end = 0; // warp-uniform: the run of queue entries this warp is working through
+	const uint32_t chunk_len = uint32_t(rs.fetch_chunk);
 
 	for (;;)
 	{
@@ -776,16 +788,29 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 		const int n_idle = __popc(idle_mask);
 		if (!exhausted && (n_idle >= rs.fetch_threshold))
 		{
-			uint32_t base = 0;
-			if (lane == 0)
-				base = atomicAdd(cursor, uint32_t(n_idle));
-			base = __shfl_sync(0xffffffffu, base, 0);
-			if (base + uint32_t(n_idle) >= total)
-				exhausted = true;
+			// Default (fetch_chunk = 0): the idle lanes take the next n_idle queue entries with one atomic, so all warps of the
+			// GPU work on one narrow front of the queue and share its nodes in L1 / L2.  fetch_chunk > 0 gives each warp a
+			// private run of that many consecutive entries instead (its lanes then hold neighbours of the queue, but the
+			// warps of an SM are spread over 4,736 runs): measured slower at every run length, profiles/r02.
+			if (chunk_pos >= chunk_end)
+			{
+				const uint32_t want = chunk_len ? chunk_len : uint32_t(n_idle);
+				uint32_t base = 0;
+				if (lane == 0)
+					base = atomicAdd(cursor, want);
+				base = __shfl_sync(0xffffffffu, base, 0);
+				chunk_pos = min(base, total), chunk_end = min(base + want, total);
+				if (base + want >= total)
+					exhausted = chunk_len == 0u || base >= total;
+			}
+			const uint32_t take = min(uint32_t(n_idle), chunk_end - chunk_pos);
+			const uint32_t mine = __popc(idle_mask & lt_mask);
+			const uint32_t first = chunk_pos;
+			chunk_pos += take;
 			if (!alive)
 			{
-				item = base + __popc(idle_mask & lt_mask);
-				if (item < total &&
+				item = first + mine;
+				if (mine < take &&
 					fetch_ray<PRIMARY>(sc, sh, wf, rs, bv, fp, q, depth, in_buf, item, o, d, tmin, tmax, shadow, pidx, occluder, occ_slot, n_traced))
 				{
 					dbg_rays++;
@@ -817,7 +842,6 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 						int4 child;
 					} n;
 					uint32_t key0, key1, key2, key3;
-					int nh = 0;
 					if (PACKED)
 					{
 						// five 16-byte pieces: min corner, three axes of bfloat16 planes (lo0 lo1 | lo2 lo3 | hi0 hi1 | hi2 hi3), children
@@ -830,15 +854,19 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 						const uint32_t nx01 = sgx ? px.z : px.x, nx23 = sgx ? px.w : px.y, fx01 = sgx ? px.x : px.z, fx23 = sgx ? px.y : px.w;
 						const uint32_t ny01 = sgy ? py.z : py.x, ny23 = sgy ? py.w : py.y, fy01 = sgy ? py.x : py.z, fy23 = sgy ? py.y : py.w;
 						const uint32_t nz01 = sgz ? pz.z : pz.x, nz23 = sgz ? pz.w : pz.y, fz01 = sgz ? pz.x : pz.z, fz23 = sgz ? pz.y : pz.w;
+						// The plane in the upper half of a word is used as it stands: the lower half (its neighbour's bits) only
+						// extends the mantissa, i.e. makes the offset larger by less than one bfloat16 step, and k_pack_nodes
+						// (geometry.cu) rounds the planes stored there with that step to spare.  The interval test is folded into
+						// the min / max chain: [max(tn, tmin), min(tf, tmax)] non-empty — a superset of the fp32 kernel's test
+						// (it admits tn == tmax), so no node is skipped that the exact test enters; unused slots are inverted
+						// boxes of +-3e38 here (not NaN boxes: fmaxf(NaN, tmin) would admit them).
 #define BF_LO(W) __uint_as_float((W) << 16)
-#define BF_HI(W) __uint_as_float((W)&0xffff0000u)
+#define BF_HI(W) __uint_as_float(W)
 #define CHILD_P(K, NX, FX, NY, FY, NZ, FZ)                                                                              \
 	{                                                                                                                   \
-		const float tn = fmaxf(fmaxf(fmaf(NX, idx, cx), fmaf(NY, idy, cy)), fmaf(NZ, idz, cz));                         \
-		const float tf = fminf(fminf(fmaf(FX, idx, cx), fmaf(FY, idy, cy)), fmaf(FZ, idz, cz));                         \
-		const bool h = (tf >= tn) & (tn < tmax) & (tf >= tmin);                                                         \
-		nh += h ? 1 : 0;                                                                                                \
-		key##K = h ? ((__float_as_uint(fmaxf(tn, 0.0f)) & 0xFFFFFFFCu) | uint32_t(K)) : MISSKEY(K);                     \
+		const float tn = fmaxf(fmaxf(fmaxf(fmaf(NX, idx, cx), fmaf(NY, idy, cy)), fmaf(NZ, idz, cz)), tmin);            \
+		const float tf = fminf(fminf(fminf(fmaf(FX, idx, cx), fmaf(FY, idy, cy)), fmaf(FZ, idz, cz)), tmax);            \
+		key##K = tn <= tf ? ((__float_as_uint(tn) & 0xFFFFFFFCu) | uint32_t(K)) : MISSKEY(K);                           \
 	}
 						CHILD_P(0, BF_LO(nx01), BF_LO(fx01), BF_LO(ny01), BF_LO(fy01), BF_LO(nz01), BF_LO(fz01))
 						CHILD_P(1, BF_HI(nx01), BF_HI(fx01), BF_HI(ny01), BF_HI(fy01), BF_HI(nz01), BF_HI(fz01))
@@ -865,7 +893,7 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 					if (LEAN == 1 || ((LEAN == 2 || LEAN == 3) && shadow))
 					{
 						const uint32_t km = min(min(key0, key1), min(key2, key3));
-						if (nh == 0)
+						if (km >= 0x7f000000u)
 							cur = stack[--sp];
 						else
 						{
@@ -899,6 +927,8 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 						CSWAP2(key1, key3, c1, c3)
 						CSWAP2(key1, key2, c1, c2)
 #undef CSWAP2
+						const int nh = (key0 < 0x7f000000u ? 1 : 0) + (key1 < 0x7f000000u ? 1 : 0) + (key2 < 0x7f000000u ? 1 : 0) +
+									   (key3 < 0x7f000000u ? 1 : 0);
 						if (nh > 3)
 							stack[sp++] = c3;
 						if (nh > 2)
@@ -908,7 +938,7 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 						cur = nh > 0 ? c0 : stack[sp - 1];
 						sp -= nh > 0 ? 0 : 1;
 					}
-					else if (nh == 0)
+					else if (NO_CHILD_HIT(key0, key1, key2, key3))
 						cur = stack[--sp];
 					else
 					{
@@ -918,11 +948,11 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 						CSWAP(key1, key3)
 						CSWAP(key1, key2)
 						cur = PICK(key0);
-						if (nh > 1)
+						if (key1 < 0x7f000000u) // sorted: misses are last
 						{
-							if (nh > 3)
+							if (key3 < 0x7f000000u)
 								stack[sp++] = PICK(key3);
-							if (nh > 2)
+							if (key2 < 0x7f000000u)
 								stack[sp++] = PICK(key2);
 							stack[sp++] = PICK(key1);
 						}
@@ -1059,6 +1089,8 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace_cw(const Sc
 	bool trav_done = true;
 	bool exhausted = false; // warp-uniform: the queue has no more items
 	uint32_t acc_count = 0, n_traced = 0, pidx = 0, occluder = 0xffffffffu, occ_slot = 0;
+	uint32_t chunk_pos = 0, chunk_end = 0; // warp-uniform: the run of queue entries this warp is working through
+	const uint32_t chunk_len = uint32_t(rs.fetch_chunk);
 
 	for (;;)
 	{
@@ -1069,16 +1101,29 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace_cw(const Sc
 		const int n_idle = __popc(idle_mask);
 		if (!exhausted && (n_idle >= rs.fetch_threshold))
 		{
-			uint32_t base = 0;
-			if (lane == 0)
-				base = atomicAdd(cursor, uint32_t(n_idle));
-			base = __shfl_sync(0xffffffffu, base, 0);
-			if (base + uint32_t(n_idle) >= total)
-				exhausted = true;
+			// Default (fetch_chunk = 0): the idle lanes take the next n_idle queue entries with one atomic, so all warps of the
+			// GPU work on one narrow front of the queue and share its nodes in L1 / L2.  fetch_chunk > 0 gives each warp a
+			// private run of that many consecutive entries instead (its lanes then hold neighbours of the queue, but the
+			// warps of an SM are spread over 4,736 runs): measured slower at every run length, profiles/r02.
+			if (chunk_pos >= chunk_end)
+			{
+				const uint32_t want = chunk_len ? chunk_len : uint32_t(n_idle);
+				uint32_t base = 0;
+				if (lane == 0)
+					base = atomicAdd(cursor, want);
+				base = __shfl_sync(0xffffffffu, base, 0);
+				chunk_pos = min(base, total), chunk_end = min(base + want, total);
+				if (base + want >= total)
+					exhausted = chunk_len == 0u || base >= total;
+			}
+			const uint32_t take = min(uint32_t(n_idle), chunk_end - chunk_pos);
+			const uint32_t mine = __popc(idle_mask & lt_mask);
+			const uint32_t first = chunk_pos;
+			chunk_pos += take;
 			if (!alive)
 			{
-				item = base + __popc(idle_mask & lt_mask);
-				if (item < total &&
+				item = first + mine;
+				if (mine < take &&
 					fetch_ray<PRIMARY>(sc, sh, wf, rs, bv, fp, q, depth, in_buf, item, o, d, tmin, tmax, shadow, pidx, occluder, occ_slot, n_traced))
 				{
 					dbg_rays++;
@@ -1476,15 +1521,19 @@ __device__ float4 FetchTexel(const SceneView &sc, float tcx, float tcy, int o, i
 	if (w <= 0 || h <= 0)
 		return make_float4(0.f, 0.f, 0.f, 0.f);
 	const float tx = (fmaxf(tcx + 1000, 0.0f) * float(w)) - 0.5f, ty = (fmaxf(tcy + 1000, 0.0f) * float(h)) - 0.5f;
-	const int iu = __float2int_rz(tx) % w;
-	const int iv = __float2int_rz(ty) % h;
+	// wrap: tx, ty >= -0.5 so the truncated coordinates are >= 0 and `%` is a mask for power-of-two sizes (every mip of
+	// a power-of-two texture); other sizes take the division
+	const bool pow2 = ((w & (w - 1)) | (h & (h - 1))) == 0;
+	const int iu = pow2 ? (__float2int_rz(tx) & (w - 1)) : (__float2int_rz(tx) % w);
+	const int iv = pow2 ? (__float2int_rz(ty) & (h - 1)) : (__float2int_rz(ty) % h);
 	const float fu = tx - floorf(tx);
 	const float fv = ty - floorf(ty);
 	const float w0 = (1 - fu) * (1 - fv);
 	const float w1 = fu * (1 - fv);
 	const float w2 = (1 - fu) * fv;
 	const float w3 = 1 - (w0 + w1 + w2);
-	const uint32_t iu1 = uint32_t(iu + 1) % uint32_t(w), iv1 = uint32_t(iv + 1) % uint32_t(h);
+	const uint32_t iu1 = pow2 ? (uint32_t(iu + 1) & uint32_t(w - 1)) : (uint32_t(iu + 1) % uint32_t(w));
+	const uint32_t iv1 = pow2 ? (uint32_t(iv + 1) & uint32_t(h - 1)) : (uint32_t(iv + 1) % uint32_t(h));
 	const float4 p0 = texel_rgba8(sc, uint32_t(o) + iu + uint32_t(iv) * w), p1 = texel_rgba8(sc, uint32_t(o) + iu1 + uint32_t(iv) * w);
 	const float4 p2 = texel_rgba8(sc, uint32_t(o) + iu + iv1 * w), p3 = texel_rgba8(sc, uint32_t(o) + iu1 + iv1 * w);
 	return make_float4(p0.x * w0 + p1.x * w1 + p2.x * w2 + p3.x * w3, p0.y * w0 + p1.y * w1 + p2.y * w2 + p3.y * w3,
@@ -1684,27 +1733,27 @@ __device__ float LightPickProb(const SceneView &sc, int idx, V3 O, V3 N, V3 I) /
 		return 0;
 	return mine / sum;
 }
-__device__ V3 RandomBarycentrics(float r0) // :119-157
+// lights.h:119-157 subdivides the unit triangle A=(1,0) B=(0,1) C=(0,0) sixteen times — digit d of r0 (two bits, most
+// significant first) keeps corner d's sub-triangle (d = 0: the middle one) — and returns the centroid of what is left.
+// Every step is linear in the corners, so the sum of the final corners is w . (A,B,C) with the row vector
+// w = [1 1 1] T(d15) ... T(d0); with h = w / 2 and H = hA + hB + hC (constant: the components always sum to 3):
+//   d = 0: w' = H - h      d = 1: w' = h + (H,0,0)      d = 2: w' = h + (0,H,0)      d = 3: w' = h + (0,0,H)
+// All corner coordinates of the reference's loop are dyadic rationals with at most 16 fractional bits, i.e. exact in
+// float, so the same sums in 16.16 fixed point give the identical centroid — without a 16-trip loop around a four-way
+// branch (17 % of k_shade's instructions at depth 0, profiles/r02).
+__device__ __forceinline__ V3 RandomBarycentrics(float r0)
 {
-	const uint32_t uf = __float2uint_rz(r0 * 4294967295.0f);
-	float Ax = 1.f, Ay = 0.f, Bx = 0.f, By = 1.f, Cx = 0.f, Cy = 0.f;
-#pragma unroll 1
-	for (int i = 0; i < 16; ++i)
+	uint32_t uf = __float2uint_rz(r0 * 4294967295.0f);
+	constexpr uint32_t H = 3u << 15;
+	uint32_t wA = 1u << 16, wB = 1u << 16;
+#pragma unroll
+	for (int i = 0; i < 16; ++i, uf >>= 2) // least significant digit first: it is the last subdivision
 	{
-		const int d = int((uf >> (2 * (15 - i))) & 0x3);
-		float Anx, Any, Bnx, Bny, Cnx, Cny;
-		if (d == 0)
-			Anx = (Bx + Cx) * 0.5f, Any = (By + Cy) * 0.5f, Bnx = (Ax + Cx) * 0.5f, Bny = (Ay + Cy) * 0.5f,
-			Cnx = (Ax + Bx) * 0.5f, Cny = (Ay + By) * 0.5f;
-		else if (d == 1)
-			Anx = Ax, Any = Ay, Bnx = (Ax + Bx) * 0.5f, Bny = (Ay + By) * 0.5f, Cnx = (Ax + Cx) * 0.5f, Cny = (Ay + Cy) * 0.5f;
-		else if (d == 2)
-			Anx = (Bx + Ax) * 0.5f, Any = (By + Ay) * 0.5f, Bnx = Bx, Bny = By, Cnx = (Bx + Cx) * 0.5f, Cny = (By + Cy) * 0.5f;
-		else
-			Anx = (Cx + Ax) * 0.5f, Any = (Cy + Ay) * 0.5f, Bnx = (Cx + Bx) * 0.5f, Bny = (Cy + By) * 0.5f, Cnx = Cx, Cny = Cy;
-		Ax = Anx, Ay = Any, Bx = Bnx, By = Bny, Cx = Cnx, Cy = Cny;
+		const uint32_t d = uf & 3u, hA = wA >> 1, hB = wB >> 1;
+		wA = d == 0u ? H - hA : (d == 1u ? hA + H : hA);
+		wB = d == 0u ? H - hB : (d == 2u ? hB + H : hB);
 	}
-	const float rx = (Ax + Bx + Cx) * 0.3333333f, ry = (Ay + By + Cy) * 0.3333333f;
+	const float rx = (float(wA) * (1.0f / 65536.0f)) * 0.3333333f, ry = (float(wB) * (1.0f / 65536.0f)) * 0.3333333f;
 	return mk(rx, ry, 1.0f - rx - ry);
 }
 __device__ V3 RandomPointOnLight(const SceneView &sc, float r0, float r1, V3 I, V3 N, float &pickProb, float &lightPdf,

@@ -116,3 +116,28 @@ def test_atrium_standin_is_well_formed():
     assert len(sc.area_lights) == 2
     for m in sc.meshes:
         assert np.isfinite(m.vertices).all() and np.isfinite(m.triangles["LOD"]).all()
+
+
+def test_closed_form_random_barycentrics_equals_the_reference_loop(oracle_lib):
+    """k_shade's RandomBarycentrics replaces the sixteen-trip subdivision loop of lights.h:119-157 by the weights of the
+    final corners in 16.16 fixed point (csrc/kernels.cu).  This numpy restatement of those integer sums must give the
+    oracle's loop (pinned on the reference's own lights.h, test_ref_pin) bit for bit — every float of the loop is exact."""
+    import ctypes as C
+
+    f = oracle_lib.fn("random_barycentrics", None, [C.c_float, C.c_void_p])
+    rng = np.random.default_rng(7)
+    r0s = np.concatenate([rng.random(4000, dtype=np.float32), np.float32([0.0, 0.25, 0.5, 0.75, 1.0 - 2 ** -24, 1e-9, 0.3333333])])
+    for r0 in r0s:
+        out = np.zeros(3, np.float32)
+        f(float(r0), out.ctypes.data)
+        uf = min(int(np.float32(r0) * np.float32(4294967295.0)), 0xFFFFFFFF)  # __float2uint_rz saturates
+        H, wA, wB = 3 << 15, 1 << 16, 1 << 16
+        for _ in range(16):
+            d, hA, hB = uf & 3, wA >> 1, wB >> 1
+            wA = H - hA if d == 0 else (hA + H if d == 1 else hA)
+            wB = H - hB if d == 0 else (hB + H if d == 2 else hB)
+            uf >>= 2
+        rx = np.float32(np.float32(wA) * np.float32(1.0 / 65536.0)) * np.float32(0.3333333)
+        ry = np.float32(np.float32(wB) * np.float32(1.0 / 65536.0)) * np.float32(0.3333333)
+        mine = np.float32([rx, ry, np.float32(np.float32(1.0) - rx) - ry])
+        assert np.array_equal(mine, out), (r0, mine, out)

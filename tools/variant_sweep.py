@@ -53,6 +53,6 @@ for var in a.variants.split(";"):
                       "pixels_differing_from_first": float((np.abs(img - ref).max(axis=-1) > 0).mean()),
                       "mean": float(img[..., :3].mean()), "bvh": ctx.get_bvh_info()}), flush=True)
     for k, v in kvs:  # back to the defaults
-        ctx.set_setting(k, {"trace_variant": "9", "primary_variant": "5", "bvh": "4", "shadow_cache": "off", "primary_cache": "on", "sort": "on",
-                               "sort_cell_bits": "5", "sort_major": "cell", "spp_batch": "0", "fetch_threshold": "8"}.get(k, v))
-    ctx.set_setting("primary_variant", "5")
+        ctx.set_setting(k, {"trace_variant": "9", "primary_variant": "9", "bvh": "4", "shadow_cache": "off", "primary_cache": "on", "sort": "on",
+                               "sort_cell_bits": "5", "sort_major": "cell", "spp_batch": "0", "fetch_threshold": "8", "fetch_chunk": "0"}.get(k, v))
+    ctx.set_setting("primary_variant", "9")
