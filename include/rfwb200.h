@@ -210,6 +210,15 @@ RFWB200_API int rfwb200_destroy(rfwb200_context *ctx);
 /* message of the calling thread's last failing call */
 RFWB200_API const char *rfwb200_last_error(void);
 
+/* The same factory for a box with several GPUs: ONE context that owns `count` devices (CUDA ordinals) in
+ * this process.  Every set_* / update / set_setting call is applied to all of them (the scene is replicated; the host-built
+ * BVH is built once and shared), rfwb200_render_frame renders the frame tile-sharded over the devices — one host thread per
+ * device enqueues its share — and each device's fold kernel writes its tiles straight into the image of devices[0] over
+ * NVLink peer access (no collective, no de-tiling pass), so rfwb200_read_framebuffer / rfwb200_device_framebuffer present
+ * the assembled row-major frame exactly as a single-device context does.  The frame is bit-identical for every count.
+ * The reference calls one render_frame per frame (RFW/system/src/rfw/system.cpp:682-718); this is that call on N GPUs. */
+RFWB200_API int rfwb200_create_group(const int *devices, size_t count, rfwb200_context **out);
+
 /* replaces RenderContext::init(GLuint*, w, h) (context.h:88) with a BUFFER target
  * (RenderTarget::BUFFER, context.h:27-34): linear-HDR RGBA32F, row-major, row 0 first. */
 RFWB200_API int rfwb200_init(rfwb200_context *ctx, uint32_t width, uint32_t height);
@@ -300,6 +309,12 @@ RFWB200_API void *rfwb200_device_framebuffer(rfwb200_context *ctx);
 RFWB200_API size_t rfwb200_local_pixel_count(const rfwb200_context *ctx);
 /* blocking copy of the finalised framebuffer to host memory (float4 per local pixel) */
 RFWB200_API int rfwb200_read_framebuffer(rfwb200_context *ctx, float *host_rgba, size_t capacity_pixels);
+/* The same copy without blocking the caller: enqueued on a second stream behind the frame just rendered, into PINNED host
+ * memory; rfwb200_read_wait blocks until the latest such copy has landed.  The next render_frame may be issued right away —
+ * its kernels run beside the copy, and only its last launch (the one that overwrites the framebuffer) waits for it — so a
+ * host that consumes every frame pays max(render, copy) per frame instead of their sum. */
+RFWB200_API int rfwb200_read_framebuffer_async(rfwb200_context *ctx, float *pinned_host_rgba, size_t capacity_pixels);
+RFWB200_API int rfwb200_read_wait(rfwb200_context *ctx);
 /* replaces the display pass of rfw::system::render_frame(camera, status, toneMap = true) (system/src/rfw/system.cpp:694-713
  * running assets/shaders/tone-map.frag over the render target): rgb' = ACESFitted(max(0, rgb - 0.5*contrast + 0.5 +
  * brightness)) with camera.contrast / camera.brightness (context/camera.h), alpha passed through, packed to RGBA8 (round
@@ -319,6 +334,25 @@ RFWB200_API int rfwb200_read_display(rfwb200_context *ctx, float contrast, float
  * row-major image; all pointers are device pointers. */
 RFWB200_API int rfwb200_assemble_shards(rfwb200_context *ctx, const void *gathered, void *image_out);
 RFWB200_API size_t rfwb200_shard_stride(const rfwb200_context *ctx);
+
+/* ---- display image of a sharded frame: one rank per PROCESS (torchrun) --------------------------------------------------
+ * The display rank allocates ONE row-major image (float4[width * height]) plus two flow-control counters in its device
+ * memory (rfwb200_display_create) and hands the 64-byte CUDA IPC handle of that allocation to the other ranks
+ * (rfwb200_display_export -> any byte transport -> rfwb200_display_import; ranks living in the same process use
+ * rfwb200_display_attach, which is what rfwb200_create_group does).  From then on the last launch of every rank's
+ * render_frame (k_fold) writes that rank's finalised tiles into the image — peer stores over NVLink — and adds one arrival
+ * to the counter; rfwb200_display_wait makes the display rank's stream wait until all `world` ranks of its latest frame
+ * have arrived.  A rank overwrites the image with frame f + 1 only after the display rank's next render_frame has been
+ * enqueued behind whatever read frame f on its stream.  All waits give up after 4 s and make rfwb200_synchronize fail
+ * instead of hanging the device.  This replaces the NCCL gather + de-tiling pass of SURVEY.md §8e. */
+RFWB200_API int rfwb200_display_create(rfwb200_context *ctx, void **image_dev_out /* may be NULL */);
+RFWB200_API int rfwb200_display_export(rfwb200_context *ctx, unsigned char handle_out[64]);
+RFWB200_API int rfwb200_display_import(rfwb200_context *ctx, const unsigned char handle[64]);
+RFWB200_API int rfwb200_display_attach(rfwb200_context *ctx, rfwb200_context *display_rank);
+RFWB200_API int rfwb200_display_wait(rfwb200_context *ctx);
+RFWB200_API void *rfwb200_display_image(rfwb200_context *ctx);
+/* test hook: blocking copy of `bytes` from a device pointer valid on this context's device, ordered after its stream */
+RFWB200_API int rfwb200_debug_read_device(rfwb200_context *ctx, const void *device_ptr, void *host, size_t bytes);
 /* wait for all enqueued work of this context */
 RFWB200_API int rfwb200_synchronize(rfwb200_context *ctx);
 

@@ -21,6 +21,9 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -119,10 +122,74 @@ inline void mul_mat3(const float *m, const float *p, float *o)
 }
 } // namespace
 
+// One host thread per further device of an in-process group: it enqueues that device's frame while the calling thread
+// enqueues its own (a frame is ~20 asynchronous API calls per device; issued one device after the other they would
+// stagger the start of eight GPUs by half a millisecond).
+class DeviceWorker
+{
+  public:
+	DeviceWorker() : th([this] { loop(); }) {}
+	~DeviceWorker()
+	{
+		{
+			std::lock_guard<std::mutex> l(m);
+			quit = true;
+		}
+		cv.notify_all();
+		th.join();
+	}
+	void submit(std::function<int(std::string &)> f)
+	{
+		{
+			std::lock_guard<std::mutex> l(m);
+			job = std::move(f), busy = true;
+		}
+		cv.notify_all();
+	}
+	int wait(std::string &msg)
+	{
+		std::unique_lock<std::mutex> l(m);
+		cv.wait(l, [this] { return !busy; });
+		msg = message;
+		return code;
+	}
+
+  private:
+	void loop()
+	{
+		for (;;)
+		{
+			std::function<int(std::string &)> f;
+			{
+				std::unique_lock<std::mutex> l(m);
+				cv.wait(l, [this] { return quit || (busy && job); });
+				if (quit)
+					return;
+				f = std::move(job), job = nullptr;
+			}
+			std::string msg;
+			const int r = f(msg);
+			{
+				std::lock_guard<std::mutex> l(m);
+				code = r, message = msg, busy = false;
+			}
+			cv.notify_all();
+		}
+	}
+	std::mutex m;
+	std::condition_variable cv;
+	std::function<int(std::string &)> job;
+	bool busy = false, quit = false;
+	int code = 0;
+	std::string message;
+	std::thread th;
+};
+
 struct rfwb200_context
 {
 	int device = 0;
 	cudaStream_t stream = nullptr;
+	bool owns_stream = false;
 	bool initialised = false;
 	uint32_t width = 0, height = 0;
 	ShardView shard{};
@@ -194,6 +261,24 @@ struct rfwb200_context
 	size_t items_capacity = 0;		// work items the wavefront planes are allocated for
 	int spp_batch = 0;				// setting "spp_batch": samples per wavefront, 0 = as many as fit (<= MAX_BATCH_SPP, <= 2^24 items)
 	uint32_t sort_bins_allocated = 0;
+
+	// ---- display target of a sharded frame (DisplayTarget, device_types.h) and in-process device groups ----
+	struct Display
+	{
+		void *base = nullptr; // [float4 image[w * h]] [arrivals @ +0, consumed @ +128 of the 256-byte tail]
+		size_t image_bytes = 0;
+		bool owner = false, ipc = false;
+		float4 *image = nullptr;
+		uint32_t *arrivals = nullptr, *consumed = nullptr;
+		uint32_t frames = 0; // sharded frames this context has folded into the image
+	} display;
+	cudaStream_t copy_stream = nullptr;			 // rfwb200_read_framebuffer_async: the read-back runs beside the next frame's kernels
+	cudaEvent_t ev_frame_done = nullptr, ev_copy_done = nullptr;
+	bool copy_pending = false;
+	DevBuf d_display_local;						 // [0] CTA counter of k_fold, [1] error word of the flow-control kernels
+	std::vector<rfwb200_context *> peers;		 // ranks 1..n-1 of an in-process group; this context is rank 0 = the display rank
+	std::vector<std::unique_ptr<DeviceWorker>> workers; // one per peer
+	const rfwb200_context *build_donor = nullptr; // rank 0 of the group: its host-built tree is adopted instead of built again
 
 	// ---- settings / state ------------------------------------------------------------------------------
 	RenderSettings rs{2, 10.0f, 1e-5f, 1, 0, 8, nullptr, -1, 9, 1, 0, 9, 1, 5, 0, 0}; // bounces: packed nodes + unsorted connect rays; camera rays: fp32 nodes (DESIGN.md sweep) // smem_nodes 0: measured fastest on B200 (DESIGN.md "staging")
@@ -743,6 +828,52 @@ struct StageTimer
 	}
 };
 
+#define FORWARD(call)                                                                                                   \
+	do                                                                                                                  \
+	{                                                                                                                   \
+		for (rfwb200_context * p_ : c->peers)                                                                           \
+			if (int r_ = (call))                                                                                        \
+				return r_;                                                                                              \
+	} while (0)
+
+void display_detach(Ctx *c)
+{
+	Ctx::Display &d = c->display;
+	if (d.base)
+	{
+		cudaSetDevice(c->device);
+		cudaStreamSynchronize(c->stream);
+		if (d.owner)
+			cudaFree(d.base);
+		else if (d.ipc)
+			cudaIpcCloseMemHandle(d.base);
+	}
+	d = Ctx::Display{};
+}
+
+// lays the pointers of a display allocation out for an image of this context's size
+int display_bind(Ctx *c, void *base, bool owner, bool ipc)
+{
+	Ctx::Display &d = c->display;
+	d.base = base, d.owner = owner, d.ipc = ipc;
+	d.image_bytes = (size_t(c->width) * c->height * sizeof(float4) + 255) & ~size_t(255);
+	d.image = static_cast<float4 *>(base);
+	d.arrivals = reinterpret_cast<uint32_t *>(static_cast<char *>(base) + d.image_bytes);
+	d.consumed = d.arrivals + 32;
+	d.frames = 0;
+	CK(c->d_display_local.reserve(256));
+	CK(cudaMemsetAsync(c->d_display_local.ptr, 0, 256, c->stream));
+	return RFWB200_OK;
+}
+
+DisplayTarget display_target(const Ctx *c)
+{
+	DisplayTarget t{};
+	if (c->display.image)
+		t.image = c->display.image, t.arrivals = c->display.arrivals, t.local_done = c->d_display_local.as<uint32_t>();
+	return t;
+}
+
 int check_ready(Ctx *c)
 {
 	if (!c->initialised)
@@ -799,6 +930,8 @@ extern "C"
 	{
 		if (!c)
 			return RFWB200_OK;
+		for (rfwb200_context *p : c->peers)
+			rfwb200_cleanup(p);
 		cudaSetDevice(c->device);
 		cudaStreamSynchronize(c->stream);
 		return RFWB200_OK;
@@ -809,6 +942,16 @@ extern "C"
 		if (!c)
 			return RFWB200_OK;
 		rfwb200_cleanup(c);
+		c->workers.clear(); // joins the per-device host threads
+		for (rfwb200_context *p : c->peers)
+			rfwb200_destroy(p); // peers drop their mapping of the display image before its owner frees it
+		c->peers.clear();
+		cudaSetDevice(c->device);
+		display_detach(c);
+		if (c->copy_stream)
+			cudaStreamDestroy(c->copy_stream), cudaEventDestroy(c->ev_frame_done), cudaEventDestroy(c->ev_copy_done);
+		if (c->owns_stream && c->stream)
+			cudaStreamDestroy(c->stream);
 		if (c->ev_begin)
 			cudaEventDestroy(c->ev_begin);
 		if (c->ev_end)
@@ -845,6 +988,23 @@ extern "C"
 		CK(cudaMemsetAsync(c->d_fb.ptr, 0, c->d_fb.bytes, c->stream));
 		c->sample_index = 0;
 		c->initialised = true;
+		c->items_capacity = 0; // the wavefront planes are sized per frame (ensure_wavefront)
+		if ((c->display.base && !c->display.owner) || (c->display.owner && (old_w != width || old_h != height)))
+			display_detach(c); // a display image of another size: the caller attaches again
+		if (!c->peers.empty())
+		{
+			// group: rank 0 owns the display image every rank folds into
+			for (rfwb200_context *p : c->peers)
+				display_detach(p);
+			FORWARD(rfwb200_init(p_, width, height));
+			if (int r = ensure_device(c))
+				return r;
+			if (int r = rfwb200_display_create(c, nullptr))
+				return r;
+			FORWARD(rfwb200_display_attach(p_, c));
+			if (int r = ensure_device(c))
+				return r;
+		}
 		return RFWB200_OK;
 	}
 
@@ -854,6 +1014,7 @@ extern "C"
 		REQUIRE(world >= 1 && rank < world, "rank must be < world");
 		REQUIRE(tile_w >= 8 && tile_w % 8 == 0 && tile_h >= 4 && tile_h % 4 == 0, "tile must be a multiple of 8x4 pixels");
 		REQUIRE(tile_w <= 1024 && tile_h <= 1024, "tile must be at most 1024x1024 pixels");
+		REQUIRE(c->peers.empty() && c->build_donor == nullptr, "the ranks of an in-process group are assigned by rfwb200_create_group");
 		c->shard.rank = rank, c->shard.world = world, c->shard.tile_w = tile_w, c->shard.tile_h = tile_h;
 		if (c->initialised)
 			return rfwb200_init(c, c->width, c->height);
@@ -870,6 +1031,7 @@ extern "C"
 	int rfwb200_set_sky(rfwb200_context *c, const float *rgb, size_t width, size_t height)
 	{
 		REQUIRE(c && rgb && width > 0 && height > 0, "bad sky");
+		FORWARD(rfwb200_set_sky(p_, rgb, width, height));
 		if (int r = ensure_device(c))
 			return r;
 		std::vector<float> tmp(width * height * 4);
@@ -885,6 +1047,7 @@ extern "C"
 	int rfwb200_set_textures(rfwb200_context *c, const rfwb200_texture_data *tex, size_t count)
 	{
 		REQUIRE(c && (tex || count == 0), "bad textures");
+		FORWARD(rfwb200_set_textures(p_, tex, count));
 		if (int r = ensure_device(c))
 			return r;
 		// one linear uint array and one float4 array with per-texture offsets (CUDART/src/Context.cpp:201-268)
@@ -934,6 +1097,7 @@ extern "C"
 							  size_t count)
 	{
 		REQUIRE(c && (mats || count == 0), "bad materials");
+		FORWARD(rfwb200_set_materials(p_, mats, ids, count));
 		if (int r = ensure_device(c))
 			return r;
 		c->materials.assign(mats, mats + count);
@@ -972,6 +1136,7 @@ extern "C"
 		REQUIRE(c && mesh, "bad mesh");
 		REQUIRE(mesh->vertices && mesh->triangles, "mesh needs vertices and triangles");
 		REQUIRE(index < (1u << 24), "mesh index too large");
+		FORWARD(rfwb200_set_mesh(p_, index, mesh));
 		if (index >= c->meshes.size())
 			c->meshes.resize(index + 1), c->topology_dirty = true;
 		HostMesh &m = c->meshes[index];
@@ -1008,6 +1173,7 @@ extern "C"
 		REQUIRE(c && transform && normal_matrix, "bad instance");
 		REQUIRE(mesh_index < c->meshes.size(), "instance references a mesh that was not set");
 		REQUIRE(i <= c->instances.size() + (1u << 20), "instance index too large");
+		FORWARD(rfwb200_set_instance(p_, i, mesh_index, transform, normal_matrix));
 		if (i >= c->instances.size())
 			c->instances.resize(i + 1), c->topology_dirty = true;
 		HostInstance &in = c->instances[i];
@@ -1028,6 +1194,7 @@ extern "C"
 		REQUIRE(c != nullptr, "context is null");
 		REQUIRE((n.area == 0 || a) && (n.point == 0 || p) && (n.spot == 0 || s) && (n.directional == 0 || d),
 				"light count without array");
+		FORWARD(rfwb200_set_lights(p_, n, a, p, s, d));
 		if (int r = ensure_device(c))
 			return r;
 		CK(cudaStreamSynchronize(c->stream));
@@ -1049,9 +1216,22 @@ extern "C"
 		return RFWB200_OK;
 	}
 
+	static int update_one(rfwb200_context *c);
+
 	int rfwb200_update(rfwb200_context *c)
 	{
 		REQUIRE(c != nullptr, "context is null");
+		// rank 0 of a group builds (or refits) on the host once; the other ranks adopt its tree and only run the uploads
+		// and the device kernels on their own GPU — every device traverses the SAME tree, so the frame does not depend on
+		// the number of devices
+		if (int r = update_one(c))
+			return r;
+		FORWARD(update_one(p_));
+		return ensure_device(c);
+	}
+
+	static int update_one(rfwb200_context *c)
+	{
 		if (int r = ensure_device(c))
 			return r;
 		if (!c->geometry_dirty && c->scene.nodes)
@@ -1153,7 +1333,17 @@ extern "C"
 		if (int r = flatten_scene(c, device ? nullptr : &shade, device ? nullptr : &det_eps))
 			return r;
 		const auto t0 = std::chrono::steady_clock::now();
-		if (can_refit && c->bvh.wide8 == c->wide8)
+		const rfwb200_context *donor = c->build_donor;
+		if (donor && !donor->device_built && donor->built_layout == layout && donor->bvh.wide8 == c->wide8 &&
+			donor->built_tri_count == c->build_tris.size() && (!donor->bvh.nodes.empty() || !donor->bvh.cw_nodes.empty()))
+		{
+			c->bvh = donor->bvh; // topology + boxes as rank 0 built / refitted them
+			c->built_tri_count = c->build_tris.size();
+			if (!can_refit)
+				c->inst_moved.assign(c->instances.size(), 0);
+			(can_refit ? c->refits : c->builds)++;
+		}
+		else if (can_refit && c->bvh.wide8 == c->wide8)
 		{
 			c->tri_moved.clear();
 			c->inst_moved.resize(c->instances.size(), 0);
@@ -1222,6 +1412,7 @@ extern "C"
 	{
 		REQUIRE(c && base_vertices && base_normals && joints && weights, "bad skin");
 		REQUIRE(mesh_index < c->meshes.size(), "skin references a mesh that was not set");
+		FORWARD(rfwb200_set_mesh_skin(p_, mesh_index, base_vertices, base_normals, joints, weights, vertex_count));
 		REQUIRE(c->meshes[mesh_index].vertices.size() == vertex_count * 4, "skin and mesh vertex counts differ");
 		if (int r = ensure_device(c))
 			return r;
@@ -1253,6 +1444,7 @@ extern "C"
 	{
 		REQUIRE(c && pose_positions && pose_normals && target_count >= 1, "bad morph targets");
 		REQUIRE(mesh_index < c->meshes.size(), "morph targets reference a mesh that was not set");
+		FORWARD(rfwb200_set_mesh_morph_targets(p_, mesh_index, pose_positions, pose_normals, target_count, vertex_count));
 		REQUIRE(c->meshes[mesh_index].vertices.size() == vertex_count * 4, "morph target and mesh vertex counts differ");
 		if (int r = ensure_device(c))
 			return r;
@@ -1276,6 +1468,7 @@ extern "C"
 		REQUIRE(c && weights, "bad morph weights");
 		REQUIRE(mesh_index < c->skins.size() && c->skins[mesh_index] && c->skins[mesh_index]->n_targets > 0,
 				"mesh has no morph targets (rfwb200_set_mesh_morph_targets)");
+		FORWARD(rfwb200_set_mesh_morph_weights(p_, mesh_index, weights, weight_count));
 		if (int r = ensure_device(c))
 			return r;
 		Ctx::Skin &sk = *c->skins[mesh_index];
@@ -1309,6 +1502,7 @@ extern "C"
 	{
 		REQUIRE(c && joint_matrices && joint_count > 0, "bad pose");
 		REQUIRE(mesh_index < c->skins.size() && c->skins[mesh_index] && c->skins[mesh_index]->has_skin, "mesh has no skin (rfwb200_set_mesh_skin)");
+		FORWARD(rfwb200_set_mesh_pose(p_, mesh_index, joint_matrices, joint_count));
 		if (int r = ensure_device(c))
 			return r;
 		Ctx::Skin &sk = *c->skins[mesh_index];
@@ -1381,6 +1575,7 @@ extern "C"
 	int rfwb200_set_setting(rfwb200_context *c, const char *key, const char *value)
 	{
 		REQUIRE(c && key && value, "bad setting");
+		FORWARD(rfwb200_set_setting(p_, key, value));
 		const std::string k = key, v = value;
 		if (k == "spp")
 		{
@@ -1533,9 +1728,45 @@ extern "C"
 		return RFWB200_OK;
 	}
 
+	static int render_one(rfwb200_context *c, const rfwb200_camera_view *view, int status);
+
 	int rfwb200_render_frame(rfwb200_context *c, const rfwb200_camera_view *view, int status)
 	{
 		REQUIRE(c && view, "bad arguments");
+		if (c->peers.empty())
+			return render_one(c, view, status);
+		// in-process group: every further device's frame is enqueued by its own host thread while this thread enqueues
+		// rank 0's; all ranks write their tiles into rank 0's display image, and rank 0's stream then waits for the
+		// arrivals, so whatever the caller enqueues next on this context sees the complete frame
+		const rfwb200_camera_view v = *view;
+		for (size_t i = 0; i < c->peers.size(); i++)
+		{
+			rfwb200_context *p = c->peers[i];
+			c->workers[i]->submit([p, v, status](std::string &msg) {
+				const int r = render_one(p, &v, status);
+				if (r)
+					msg = g_last_error;
+				return r;
+			});
+		}
+		int rc = render_one(c, view, status);
+		std::string first_msg = rc ? g_last_error : std::string();
+		for (size_t i = 0; i < c->peers.size(); i++)
+		{
+			std::string msg;
+			const int r = c->workers[i]->wait(msg);
+			if (r && !rc)
+				rc = r, first_msg = "device " + std::to_string(c->peers[i]->device) + ": " + msg;
+		}
+		if (rc)
+			return set_error(rc, first_msg);
+		if (c->mode_pt)
+			return rfwb200_display_wait(c);
+		return RFWB200_OK;
+	}
+
+	static int render_one(rfwb200_context *c, const rfwb200_camera_view *view, int status)
+	{
 		if (int r = ensure_device(c))
 			return r;
 		if (int r = check_ready(c))
@@ -1558,6 +1789,7 @@ extern "C"
 		}
 		CK(cudaMemsetAsync(c->d_counters.ptr, 0, size_t(batches) * MAX_DEPTH_SLOTS * sizeof(DepthCounters), st));
 		CK(cudaMemsetAsync(c->d_ext_seen.ptr, 0, size_t(batches) * MAX_DEPTH_SLOTS * MAX_BATCH_SPP * sizeof(uint32_t), st));
+		const bool to_display = c->mode_pt && c->display.image != nullptr;
 		if (c->sample_index == 0)
 		{
 			const ProbeResult none{0, 0, 0.f, 0};
@@ -1613,12 +1845,34 @@ extern "C"
 					c->launches += 2;
 				}
 				const bool last = b + 1 == batches;
+				if (last && c->copy_pending) // an asynchronous read-back of the previous frame: the image is overwritten only after it
+				{
+					CK(cudaStreamWaitEvent(st, c->ev_copy_done, 0));
+					c->copy_pending = false;
+				}
+				if (last && to_display && c->display.owner)
+				{
+					// everything that read the previous frame on this stream (or the asynchronous read-back) has run: the other
+					// ranks may overwrite the image.  Placed in front of the fold, not of the frame, so that all ranks trace the
+					// next frame while the previous one is still being read.
+					CK(launch_display_release(c->display.consumed, c->display.frames, st));
+					c->launches += 1;
+				}
+				if (last && to_display && !c->display.owner && c->display.frames > 0)
+				{
+					// the display rank must have released the previous frame before this rank's tiles overwrite it
+					CK(launch_display_spin(c->display.consumed, c->display.frames, c->d_display_local.as<uint32_t>() + 1, st));
+					c->launches += 1;
+				}
 				{
 					StageTimer t(c, 4);
 					// blit_buffer, Kernels.cu:181-203
-					CK(launch_fold(c->shard, c->wf, bv, 1.0f / float(c->sample_index + spp), last ? 1 : 0, st));
+					CK(launch_fold(c->shard, c->wf, bv, 1.0f / float(c->sample_index + spp), last ? 1 : 0,
+								   (last && to_display) ? display_target(c) : DisplayTarget{}, st));
 				}
 				c->launches += 1;
+				if (last && to_display)
+					c->display.frames++;
 			}
 			c->sample_index += spp;
 		}
@@ -1637,13 +1891,22 @@ extern "C"
 		return RFWB200_OK;
 	}
 
-	void *rfwb200_device_framebuffer(rfwb200_context *c) { return c ? c->d_fb.ptr : nullptr; }
+	// the display rank of a sharded frame (rank 0 of an in-process group, or the owner of an exported display image) presents the
+	// assembled frame exactly like a single-device context
+	static bool presents_display(const rfwb200_context *c) { return c && c->display.owner && c->display.image && c->mode_pt && c->shard.world > 1; }
+
+	void *rfwb200_device_framebuffer(rfwb200_context *c)
+	{
+		if (presents_display(c))
+			return c->display.image;
+		return c ? c->d_fb.ptr : nullptr;
+	}
 
 	size_t rfwb200_local_pixel_count(const rfwb200_context *c)
 	{
 		if (!c)
 			return 0;
-		return c->shard.world == 1 ? size_t(c->width) * c->height : size_t(c->shard.local_pixels);
+		return (c->shard.world == 1 || presents_display(c)) ? size_t(c->width) * c->height : size_t(c->shard.local_pixels);
 	}
 
 	size_t rfwb200_shard_stride(const rfwb200_context *c) { return c ? shard_stride_pixels(c->shard) : 0; }
@@ -1655,8 +1918,39 @@ extern "C"
 			return r;
 		const size_t n = rfwb200_local_pixel_count(c);
 		REQUIRE(capacity_pixels >= n, "host buffer too small");
-		CK(cudaMemcpyAsync(host_rgba, c->d_fb.ptr, n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaMemcpyAsync(host_rgba, rfwb200_device_framebuffer(c), n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
 		CK(cudaStreamSynchronize(c->stream));
+		return RFWB200_OK;
+	}
+
+	int rfwb200_read_framebuffer_async(rfwb200_context *c, float *pinned_host_rgba, size_t capacity_pixels)
+	{
+		REQUIRE(c && pinned_host_rgba, "bad arguments");
+		if (int r = ensure_device(c))
+			return r;
+		const size_t n = rfwb200_local_pixel_count(c);
+		REQUIRE(capacity_pixels >= n, "host buffer too small");
+		if (!c->copy_stream)
+		{
+			CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+			CK(cudaEventCreateWithFlags(&c->ev_frame_done, cudaEventDisableTiming));
+			CK(cudaEventCreateWithFlags(&c->ev_copy_done, cudaEventDisableTiming));
+		}
+		CK(cudaEventRecord(c->ev_frame_done, c->stream));
+		CK(cudaStreamWaitEvent(c->copy_stream, c->ev_frame_done, 0));
+		CK(cudaMemcpyAsync(pinned_host_rgba, rfwb200_device_framebuffer(c), n * sizeof(float4), cudaMemcpyDeviceToHost, c->copy_stream));
+		CK(cudaEventRecord(c->ev_copy_done, c->copy_stream));
+		c->copy_pending = true;
+		return RFWB200_OK;
+	}
+
+	int rfwb200_read_wait(rfwb200_context *c)
+	{
+		REQUIRE(c != nullptr, "context is null");
+		if (int r = ensure_device(c))
+			return r;
+		if (c->ev_copy_done)
+			CK(cudaEventSynchronize(c->ev_copy_done));
 		return RFWB200_OK;
 	}
 
@@ -1669,7 +1963,7 @@ extern "C"
 		const float4 *src = static_cast<const float4 *>(device_rgba32f);
 		if (!src)
 		{
-			src = c->d_fb.as<float4>();
+			src = static_cast<const float4 *>(rfwb200_device_framebuffer(c));
 			pixels = rfwb200_local_pixel_count(c);
 		}
 		REQUIRE(src != nullptr, "no framebuffer: call init first");
@@ -1710,18 +2004,162 @@ extern "C"
 		return RFWB200_OK;
 	}
 
-	int rfwb200_synchronize(rfwb200_context *c)
+	// ---- display target of a sharded frame ------------------------------------------------------------------------
+	int rfwb200_display_create(rfwb200_context *c, void **image_out)
 	{
 		REQUIRE(c != nullptr, "context is null");
 		if (int r = ensure_device(c))
 			return r;
+		if (!c->initialised)
+			return set_error(RFWB200_ERR_STATE, "rfwb200_init has not been called");
+		display_detach(c);
+		void *base = nullptr;
+		const size_t image_bytes = (size_t(c->width) * c->height * sizeof(float4) + 255) & ~size_t(255);
+		CK(cudaMalloc(&base, image_bytes + 256));
+		CK(cudaMemset(base, 0, image_bytes + 256));
+		if (int r = display_bind(c, base, true, false))
+			return r;
+		if (image_out)
+			*image_out = c->display.image;
+		return RFWB200_OK;
+	}
+
+	int rfwb200_display_export(rfwb200_context *c, unsigned char handle_out[64])
+	{
+		REQUIRE(c && handle_out, "bad arguments");
+		REQUIRE(c->display.owner, "this context does not own a display image (rfwb200_display_create)");
+		if (int r = ensure_device(c))
+			return r;
+		static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+		cudaIpcMemHandle_t h;
+		CK(cudaIpcGetMemHandle(&h, c->display.base));
+		memcpy(handle_out, &h, 64);
+		return RFWB200_OK;
+	}
+
+	int rfwb200_display_import(rfwb200_context *c, const unsigned char handle[64])
+	{
+		REQUIRE(c && handle, "bad arguments");
+		if (int r = ensure_device(c))
+			return r;
+		if (!c->initialised)
+			return set_error(RFWB200_ERR_STATE, "rfwb200_init has not been called");
+		display_detach(c);
+		cudaIpcMemHandle_t h;
+		memcpy(&h, handle, 64);
+		void *base = nullptr;
+		CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+		return display_bind(c, base, false, true);
+	}
+
+	int rfwb200_display_attach(rfwb200_context *c, rfwb200_context *display_rank)
+	{
+		REQUIRE(c && display_rank && c != display_rank, "bad arguments");
+		REQUIRE(display_rank->display.owner, "the display rank owns no display image (rfwb200_display_create)");
+		REQUIRE(c->initialised && c->width == display_rank->width && c->height == display_rank->height,
+				"both contexts must be initialised with the same frame size");
+		if (int r = ensure_device(c))
+			return r;
+		display_detach(c);
+		if (c->device != display_rank->device)
+		{
+			int can = 0;
+			CK(cudaDeviceCanAccessPeer(&can, c->device, display_rank->device));
+			REQUIRE(can, "no peer access between the two devices");
+			const cudaError_t e = cudaDeviceEnablePeerAccess(display_rank->device, 0);
+			if (e == cudaErrorPeerAccessAlreadyEnabled)
+				cudaGetLastError();
+			else
+				CK(e);
+		}
+		return display_bind(c, display_rank->display.base, false, false);
+	}
+
+	int rfwb200_display_wait(rfwb200_context *c)
+	{
+		REQUIRE(c != nullptr, "context is null");
+		REQUIRE(c->display.owner, "only the display rank waits for a frame");
+		if (int r = ensure_device(c))
+			return r;
+		CK(launch_display_spin(c->display.arrivals, c->display.frames * c->shard.world, c->d_display_local.as<uint32_t>() + 1, c->stream));
+		c->launches += 1;
+		return RFWB200_OK;
+	}
+
+	void *rfwb200_display_image(rfwb200_context *c) { return c ? c->display.image : nullptr; }
+	// test hook: blocking copy from a device pointer valid on this context's device, ordered after its stream
+	int rfwb200_debug_read_device(rfwb200_context *c, const void *device_ptr, void *host, size_t bytes)
+	{
+		REQUIRE(c && device_ptr && host, "bad arguments");
+		if (int r = ensure_device(c))
+			return r;
+		CK(cudaMemcpyAsync(host, device_ptr, bytes, cudaMemcpyDeviceToHost, c->stream));
 		CK(cudaStreamSynchronize(c->stream));
+		return RFWB200_OK;
+	}
+
+	// ---- in-process device group -----------------------------------------------------------------------------------
+	int rfwb200_create_group(const int *devices, size_t count, rfwb200_context **out)
+	{
+		REQUIRE(devices && out && count >= 1 && count <= 64, "bad device list");
+		*out = nullptr;
+		rfwb200_context *master = nullptr;
+		if (int r = rfwb200_create(devices[0], &master))
+			return r;
+		for (size_t i = 1; i < count; i++)
+		{
+			rfwb200_context *p = nullptr;
+			int r = rfwb200_create(devices[i], &p);
+			if (!r)
+			{
+				cudaSetDevice(p->device);
+				const cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+				if (e != cudaSuccess)
+					r = set_error(RFWB200_ERR_CUDA, cudaGetErrorString(e));
+			}
+			if (r)
+			{
+				const std::string msg = g_last_error;
+				if (p)
+					rfwb200_destroy(p);
+				rfwb200_destroy(master);
+				return set_error(r, msg);
+			}
+			p->owns_stream = true;
+			p->build_donor = master;
+			p->shard.rank = uint32_t(i), p->shard.world = uint32_t(count);
+			master->peers.push_back(p);
+			master->workers.emplace_back(new DeviceWorker());
+		}
+		master->shard.rank = 0, master->shard.world = uint32_t(count);
+		*out = master;
+		return RFWB200_OK;
+	}
+
+	int rfwb200_synchronize(rfwb200_context *c)
+	{
+		REQUIRE(c != nullptr, "context is null");
+		FORWARD(rfwb200_synchronize(p_));
+		if (int r = ensure_device(c))
+			return r;
+		CK(cudaStreamSynchronize(c->stream));
+		if (c->d_display_local.ptr && c->display.image)
+		{
+			uint32_t words[2] = {0, 0};
+			CK(cudaMemcpy(words, c->d_display_local.ptr, sizeof(words), cudaMemcpyDeviceToHost));
+			if (words[1])
+			{
+				CK(cudaMemset(c->d_display_local.as<uint32_t>() + 1, 0, 4));
+				return set_error(RFWB200_ERR_STATE, "display flow control timed out: a rank of the sharded frame did not arrive / release within 4 s");
+			}
+		}
 		return RFWB200_OK;
 	}
 
 	int rfwb200_set_probe_index(rfwb200_context *c, uint32_t x, uint32_t y)
 	{
 		REQUIRE(c != nullptr, "context is null");
+		FORWARD(rfwb200_set_probe_index(p_, x, y));
 		c->probe_x = x, c->probe_y = y;
 		return RFWB200_OK;
 	}
@@ -1738,7 +2176,17 @@ extern "C"
 			CK(cudaStreamSynchronize(c->stream));
 		}
 		*inst = uint32_t(p.inst), *prim = uint32_t(p.prim), *dist = p.dist;
-		return RFWB200_OK;
+		// in a group the probed pixel belongs to one rank's shard; the others report the cleared record
+		for (rfwb200_context *q : c->peers)
+		{
+			uint32_t qi = 0, qp = 0;
+			float qd = 0.f;
+			if (int r = rfwb200_get_probe_results(q, &qi, &qp, &qd))
+				return r;
+			if (qd > 0.f && *dist == 0.f)
+				*inst = qi, *prim = qp, *dist = qd;
+		}
+		return ensure_device(c);
 	}
 
 	static int fetch_counters(Ctx *c)
@@ -1753,9 +2201,26 @@ extern "C"
 		return RFWB200_OK;
 	}
 
+	static int frame_counters_one(rfwb200_context *c, rfwb200_frame_counters *out);
+
 	int rfwb200_get_frame_counters(rfwb200_context *c, rfwb200_frame_counters *out)
 	{
 		REQUIRE(c && out, "bad arguments");
+		if (int r = frame_counters_one(c, out))
+			return r;
+		for (rfwb200_context *q : c->peers) // a group reports the whole frame
+		{
+			rfwb200_frame_counters o;
+			if (int r = frame_counters_one(q, &o))
+				return r;
+			out->n_gen += o.n_gen, out->n_ext += o.n_ext, out->n_shade += o.n_shade, out->n_ext_out += o.n_ext_out;
+			out->n_nee += o.n_nee, out->n_acc += o.n_acc, out->pixels += o.pixels;
+		}
+		return ensure_device(c);
+	}
+
+	static int frame_counters_one(rfwb200_context *c, rfwb200_frame_counters *out)
+	{
 		if (int r = ensure_device(c))
 			return r;
 		memset(out, 0, sizeof(*out));
@@ -1840,21 +2305,32 @@ extern "C"
 		if (c->mode_pt && c->last_spp)
 		{
 			uint64_t sec = 0, deep = 0, shadow = 0;
-			for (uint32_t s = 0; s < c->last_batches; s++)
-			{
-				const DepthCounters *dc = &c->host_counters[size_t(s) * MAX_DEPTH_SLOTS];
-				for (uint32_t d = 1; d <= uint32_t(c->rs.max_path_length); d++)
+			std::vector<const rfwb200_context *> ranks(1, c);
+			ranks.insert(ranks.end(), c->peers.begin(), c->peers.end());
+			for (const rfwb200_context *q : ranks) // host_counters of every rank were fetched by get_frame_counters above
+				for (uint32_t s = 0; s < q->last_batches && size_t(s + 1) * MAX_DEPTH_SLOTS <= q->host_counters.size(); s++)
 				{
-					(d == 1 ? sec : deep) += dc[d - 1].ext;
-					shadow += dc[d].shadow_traced;
+					const DepthCounters *dc = &q->host_counters[size_t(s) * MAX_DEPTH_SLOTS];
+					for (uint32_t d = 1; d <= uint32_t(c->rs.max_path_length); d++)
+					{
+						(d == 1 ? sec : deep) += dc[d - 1].ext;
+						shadow += dc[d].shadow_traced;
+					}
 				}
-			}
 			out->secondary_count = uint32_t(sec), out->deep_count = uint32_t(deep), out->shadow_count = uint32_t(shadow);
 		}
 		return RFWB200_OK;
 	}
 
-	uint64_t rfwb200_launch_count(const rfwb200_context *c) { return c ? c->launches : 0; }
+	uint64_t rfwb200_launch_count(const rfwb200_context *c)
+	{
+		if (!c)
+			return 0;
+		uint64_t n = c->launches;
+		for (const rfwb200_context *q : c->peers)
+			n += q->launches;
+		return n;
+	}
 
 	int rfwb200_get_bvh_info(const rfwb200_context *c, uint64_t *nodes, uint64_t *triangles, float *sah_cost, float *build_ms)
 	{

@@ -100,6 +100,16 @@ struct BatchView
 	float inv_spp;		   // 1 / spp (fast_div)
 };
 
+// Display target of a tile-sharded frame: ONE row-major image in the display rank's memory that the fold
+// kernel of every rank writes its pixels into — peer stores over NVLink for the other ranks — followed by one arrival per
+// rank and frame on a counter beside it.  No collective and no de-tiling pass.
+struct DisplayTarget
+{
+	float4 *image;		  // float4[width * height], row-major (local or peer-mapped); null = no display target
+	uint32_t *arrivals;	  // in the display rank's memory: += 1 by every rank when its tiles of a frame are written
+	uint32_t *local_done; // this rank's CTA counter for the last-CTA-signals pattern
+};
+
 // uniform grid over the scene box the bounce rays are binned in before they are traced (k_shade emits the key)
 struct SortGrid
 {

@@ -650,9 +650,12 @@ __device__ __forceinline__ bool fetch_ray(const SceneView &sc, const ShardView &
 	}
 	const uint32_t k = item - q.n_ext;
 	pidx = __float_as_uint(wf.sE[k].w);
-	// the reference only traces the connect queue of a sample when its bounce loop continues, i.e. when that sample
-	// emitted at least one extension ray at this depth (CUDART/src/Context.cpp:109-120)
-	if (q.seen[(pidx >> 5) - fast_div(pidx >> 5, bv.spp, bv.inv_spp) * bv.spp] == 0u)
+	// The reference only traces the connect queue of a sample when its bounce loop continues, i.e. when that sample
+	// emitted at least one extension ray at this depth anywhere in the frame (CUDART/src/Context.cpp:109-120: the host
+	// loop leaves before the pending shadow rays are traced).  A rank of a sharded frame only knows about its own tiles,
+	// so it always traces: the two agree whenever some path of the sample continues somewhere in the frame — every frame
+	// of more than a handful of pixels — and the assembled frame does not depend on how it was sharded.
+	if (sh.world == 1u && q.seen[(pidx >> 5) - fast_div(pidx >> 5, bv.spp, bv.inv_spp) * bv.spp] == 0u)
 		return false;
 	n_traced++;
 	const float4 O4 = wf.sO[k], D4 = wf.sD[k];
@@ -2171,35 +2174,82 @@ __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, c
 // its samples were split into wavefronts or render_frame calls), framebuffer = accumulator * 1/samples.  world == 1
 // writes the row-major image; world > 1 keeps the tile-major shard for the gather.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_fold(const ShardView sh, const WavefrontView wf, const BatchView bv, const float scale, const int write_fb)
+__global__ void k_fold(const ShardView sh, const WavefrontView wf, const BatchView bv, const float scale, const int write_fb,
+					   const DisplayTarget dt)
 {
 	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= sh.local_pixels)
-		return;
-	uint32_t x, y;
-	const bool live = local_to_pixel(sh, j, x, y);
-	float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-	if (live)
+	if (j < sh.local_pixels)
 	{
-		a = wf.accumulator[j];
-		const uint32_t blk = j >> 5, lane = j & 31u;
-		for (uint32_t s = 0; s < bv.spp; s++)
-		{
-			const float4 b = wf.sample_acc[((blk * bv.spp + s) << 5) | lane];
-			a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
-		}
-		wf.accumulator[j] = a;
-	}
-	if (!write_fb)
-		return;
-	a.x *= scale, a.y *= scale, a.z *= scale, a.w *= scale;
-	if (sh.world == 1)
-	{
+		uint32_t x, y;
+		const bool live = local_to_pixel(sh, j, x, y);
+		float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 		if (live)
-			wf.framebuffer[size_t(y) * sh.width + x] = a;
+		{
+			a = wf.accumulator[j];
+			const uint32_t blk = j >> 5, lane = j & 31u;
+			for (uint32_t s = 0; s < bv.spp; s++)
+			{
+				const float4 b = wf.sample_acc[((blk * bv.spp + s) << 5) | lane];
+				a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+			}
+			wf.accumulator[j] = a;
+		}
+		if (write_fb)
+		{
+			a.x *= scale, a.y *= scale, a.z *= scale, a.w *= scale;
+			if (sh.world == 1)
+			{
+				if (live)
+					wf.framebuffer[size_t(y) * sh.width + x] = a;
+			}
+			else
+				wf.framebuffer[j] = a;
+			if (dt.image != nullptr && live)
+				dt.image[size_t(y) * sh.width + x] = a; // the display rank's image: a peer store over NVLink on the other ranks
+		}
 	}
-	else
-		wf.framebuffer[j] = a;
+	if (write_fb && dt.image != nullptr)
+	{
+		// the last CTA of the launch tells the display rank that this rank's tiles of the frame are in place
+		__threadfence_system();
+		__syncthreads();
+		if (threadIdx.x == 0)
+		{
+			const uint32_t done = atomicAdd(dt.local_done, 1u);
+			if (done == gridDim.x - 1u)
+			{
+				*dt.local_done = 0u;
+				__threadfence_system();
+				atomicAdd_system(dt.arrivals, 1u);
+			}
+		}
+	}
+}
+
+// Flow control of the display image, one thread each.  Counters only grow: frame f is complete when arrivals reaches
+// f * world; a rank may overwrite the image with frame f + 1 once the display rank has released frame f (consumed >= f).
+// Every wait gives up after four seconds and raises *err instead of hanging the device.
+__global__ void k_display_spin(const volatile uint32_t *counter, const uint32_t need, uint32_t *err)
+{
+	unsigned long long t0, t1;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+	while (*counter < need)
+	{
+		__nanosleep(200);
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+		if (t1 - t0 > 4000000000ull)
+		{
+			*err = 1u;
+			break;
+		}
+	}
+	__threadfence_system();
+}
+__global__ void k_display_release(uint32_t *consumed, const uint32_t value)
+{
+	__threadfence_system();
+	*reinterpret_cast<volatile uint32_t *>(consumed) = value;
+	__threadfence_system();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2733,10 +2783,21 @@ cudaError_t launch_trace(const SceneView &sc, const ShardView &sh, const Wavefro
 	}
 	return cudaGetLastError();
 }
-cudaError_t launch_fold(const ShardView &sh, const WavefrontView &wf, const BatchView &bv, float scale, int write_fb, cudaStream_t stream)
+cudaError_t launch_fold(const ShardView &sh, const WavefrontView &wf, const BatchView &bv, float scale, int write_fb, const DisplayTarget &dt,
+						cudaStream_t stream)
 {
-	const uint32_t n = sh.local_pixels;
-	k_fold<<<(n + 255) / 256, 256, 0, stream>>>(sh, wf, bv, scale, write_fb);
+	const uint32_t n = sh.local_pixels > 0 ? sh.local_pixels : 1u; // a rank without tiles still reports its arrival
+	k_fold<<<(n + 255) / 256, 256, 0, stream>>>(sh, wf, bv, scale, write_fb, dt);
+	return cudaGetLastError();
+}
+cudaError_t launch_display_spin(const uint32_t *counter, uint32_t need, uint32_t *err, cudaStream_t stream)
+{
+	k_display_spin<<<1, 1, 0, stream>>>(counter, need, err);
+	return cudaGetLastError();
+}
+cudaError_t launch_display_release(uint32_t *consumed, uint32_t value, cudaStream_t stream)
+{
+	k_display_release<<<1, 1, 0, stream>>>(consumed, value);
 	return cudaGetLastError();
 }
 cudaError_t launch_sort_setup(const SceneView &sc, const WavefrontView &wf, const RenderSettings &rs, cudaStream_t stream)

@@ -33,7 +33,13 @@ cudaError_t launch_shade_ieee(const SceneView &sc, const ShardView &sh, const Wa
 cudaError_t launch_trace(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
 						 const BatchView &bv, uint32_t depth, uint32_t in_buf, const LaunchDims &dims, cudaStream_t stream);
 // accumulator += samples of the wavefront; write_fb: framebuffer = accumulator * scale (Kernels.cu:181-203)
-cudaError_t launch_fold(const ShardView &sh, const WavefrontView &wf, const BatchView &bv, float scale, int write_fb, cudaStream_t stream);
+// dt.image != null: the finalised pixels also go, row-major, into the display rank's image, and the last CTA adds one arrival
+cudaError_t launch_fold(const ShardView &sh, const WavefrontView &wf, const BatchView &bv, float scale, int write_fb, const DisplayTarget &dt,
+						cudaStream_t stream);
+// one-thread flow-control kernels of the display image: wait until *counter >= need (gives up after 4 s and sets *err),
+// publish a counter value
+cudaError_t launch_display_spin(const uint32_t *counter, uint32_t need, uint32_t *err, cudaStream_t stream);
+cudaError_t launch_display_release(uint32_t *consumed, uint32_t value, cudaStream_t stream);
 // re-ordering of the extension rays shade(depth - 1) appended (planes [1] -> planes [0]): bin scan + move
 cudaError_t launch_sort_setup(const SceneView &sc, const WavefrontView &wf, const RenderSettings &rs, cudaStream_t stream);
 cudaError_t launch_sort(const WavefrontView &wf, const RenderSettings &rs, const BatchView &bv, uint32_t depth, const LaunchDims &dims,

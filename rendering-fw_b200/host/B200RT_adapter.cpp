@@ -10,7 +10,10 @@
 
 #include "../../include/rfwb200.h"
 
+#include <dlfcn.h>
+
 #include <cmath>
+#include <cstdlib>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -36,29 +39,70 @@ void check(int rc, const char *what)
 		throw std::runtime_error(std::string("B200RT: ") + what + ": " + rfwb200_last_error());
 }
 
+// The three GL entry points the texture target needs, resolved from the host process at run time: rfw::system created
+// the GL context and the texture (RFW/system/src/rfw/system.cpp:204-211), so libGL is already loaded there.  The plugin
+// itself links no GL library (a headless host has none); without these symbols only RenderTarget::BUFFER is advertised.
+struct GLApi
+{
+	void (*BindTexture)(unsigned, unsigned) = nullptr;
+	void (*TexSubImage2D)(unsigned, int, int, int, int, int, unsigned, unsigned, const void *) = nullptr;
+	unsigned (*GetError)() = nullptr;
+	bool ok() const { return BindTexture && TexSubImage2D; }
+	static GLApi load()
+	{
+		GLApi g;
+		g.BindTexture = reinterpret_cast<decltype(g.BindTexture)>(dlsym(RTLD_DEFAULT, "glBindTexture"));
+		g.TexSubImage2D = reinterpret_cast<decltype(g.TexSubImage2D)>(dlsym(RTLD_DEFAULT, "glTexSubImage2D"));
+		g.GetError = reinterpret_cast<decltype(g.GetError)>(dlsym(RTLD_DEFAULT, "glGetError"));
+		return g;
+	}
+};
+
 class B200Context final : public rfw::RenderContext
 {
   public:
-	B200Context()
+	B200Context() : m_GL(GLApi::load())
 	{
-		const char *dev = std::getenv("RFWB200_DEVICE");
-		check(rfwb200_create(dev ? std::atoi(dev) : 0, &m_Ctx), "create");
+		// RFWB200_DEVICES="0,1,2,3": one context that owns several GPUs of the box and shards every frame over them
+		// (rfwb200_create_group); RFWB200_DEVICE=n / nothing: one GPU
+		std::vector<int> devices;
+		if (const char *list = std::getenv("RFWB200_DEVICES"))
+		{
+			std::stringstream ss(list);
+			std::string tok;
+			while (std::getline(ss, tok, ','))
+				if (!tok.empty())
+					devices.push_back(std::atoi(tok.c_str()));
+		}
+		if (devices.size() > 1)
+			check(rfwb200_create_group(devices.data(), devices.size(), &m_Ctx), "create_group");
+		else
+		{
+			const char *dev = std::getenv("RFWB200_DEVICE");
+			check(rfwb200_create(devices.size() == 1 ? devices[0] : (dev ? std::atoi(dev) : 0), &m_Ctx), "create");
+		}
 	}
 	~B200Context() override { cleanup(); }
 
 	[[nodiscard]] std::vector<rfw::RenderTarget> get_supported_targets() const override
 	{
-		return {rfw::RenderTarget::BUFFER, rfw::RenderTarget::OPENGL_TEXTURE};
+		if (m_GL.ok())
+			return {rfw::RenderTarget::BUFFER, rfw::RenderTarget::OPENGL_TEXTURE};
+		return {rfw::RenderTarget::BUFFER};
 	}
 
-	// The frame is rendered into a linear-HDR RGBA32F device buffer (RenderTarget::BUFFER, context.h:27-34).  With a GL
-	// texture the host application copies it with read_pixels()/glTexSubImage2D exactly as EmbreeRT does
-	// (EmbreeRT/src/Context.cpp:289-297); CUDA-GL interop is listed as follow-up work in DESIGN.md.
+	// The frame is rendered into a linear-HDR RGBA32F device buffer.  With a GL texture target the finished frame is
+	// copied into the texture at the end of render_frame, RGBA / FLOAT rows in framebuffer order, as EmbreeRT fills its
+	// target (EmbreeRT/src/Context.cpp:289-297: PBO + glTexSubImage2D) — rfw::system only draws that texture.
 	void init(GLuint *glTextureID, uint width, uint height) override
 	{
 		m_Texture = glTextureID ? *glTextureID : 0;
+		if (m_Texture != 0 && !m_GL.ok())
+			throw std::runtime_error("B200RT: init(GLuint*) needs glBindTexture / glTexSubImage2D in the host process (no GL library is loaded)");
 		m_Width = width, m_Height = height;
 		check(rfwb200_init(m_Ctx, width, height), "init");
+		if (m_Texture != 0)
+			m_Staging.assign(size_t(width) * height * 4, 0.0f);
 	}
 
 	void cleanup() override
@@ -72,6 +116,17 @@ class B200Context final : public rfw::RenderContext
 	{
 		const rfwb200_camera_view view = get_view(camera);
 		check(rfwb200_render_frame(m_Ctx, &view, status == rfw::Reset ? RFWB200_RESET : RFWB200_CONVERGE), "render_frame");
+		if (m_Texture != 0)
+		{
+			constexpr unsigned GL_TEXTURE_2D_ = 0x0DE1, GL_RGBA_ = 0x1908, GL_FLOAT_ = 0x1406;
+			read_pixels(m_Staging.data());
+			m_GL.BindTexture(GL_TEXTURE_2D_, m_Texture);
+			m_GL.TexSubImage2D(GL_TEXTURE_2D_, 0, 0, 0, int(m_Width), int(m_Height), GL_RGBA_, GL_FLOAT_, m_Staging.data());
+			m_GL.BindTexture(GL_TEXTURE_2D_, 0);
+			if (m_GL.GetError)
+				if (const unsigned e = m_GL.GetError())
+					throw std::runtime_error("B200RT: glTexSubImage2D failed with GL error " + std::to_string(e));
+		}
 	}
 
 	void set_materials(const std::vector<rfw::DeviceMaterial> &materials, const std::vector<rfw::MaterialTexIds> &texDescriptors) override
@@ -155,6 +210,8 @@ class B200Context final : public rfw::RenderContext
 	}
 
 	rfwb200_context *m_Ctx = nullptr;
+	GLApi m_GL;
+	std::vector<float> m_Staging;
 	GLuint m_Texture = 0;
 	uint m_Width = 0, m_Height = 0;
 };

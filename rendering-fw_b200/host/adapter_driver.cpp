@@ -15,6 +15,23 @@ const float rfw::Camera::DEFAULT_CONTRAST = 0.0f;
 const glm::vec3 rfw::Camera::DEFAULT_POSITION = glm::vec3(0.0f);
 const glm::vec3 rfw::Camera::DEFAULT_DIRECTION = glm::vec3(0.0f, 0.0f, 1.0f);
 
+// Stand-ins for the three GL entry points the plugin resolves from its host process (the driver is linked -rdynamic):
+// with `--gl` the driver hands the plugin a texture id like rfw::system does, and checks that render_frame uploaded the
+// frame into "the texture" (EmbreeRT/src/Context.cpp:289-297 is the behaviour being mirrored).
+static unsigned g_bound = 0, g_uploads = 0, g_upload_w = 0, g_upload_h = 0, g_upload_tex = 0;
+static std::vector<float> g_texture;
+extern "C" __attribute__((visibility("default"))) void glBindTexture(unsigned target, unsigned tex) { g_bound = tex; }
+extern "C" __attribute__((visibility("default"))) void glTexSubImage2D(unsigned target, int level, int x, int y, int w, int h, unsigned format,
+																   unsigned type, const void *data)
+{
+	if (target == 0x0DE1 && level == 0 && x == 0 && y == 0 && format == 0x1908 && type == 0x1406 && data)
+	{
+		g_texture.assign(static_cast<const float *>(data), static_cast<const float *>(data) + size_t(w) * h * 4);
+		g_uploads++, g_upload_w = unsigned(w), g_upload_h = unsigned(h), g_upload_tex = g_bound;
+	}
+}
+extern "C" __attribute__((visibility("default"))) unsigned glGetError() { return 0; }
+
 typedef rfw::RenderContext *(*CreateFn)();
 typedef void (*DestroyFn)(rfw::RenderContext *);
 typedef void (*ReadFn)(rfw::RenderContext *, float *);
@@ -35,6 +52,7 @@ static rfw::Triangle make_tri(glm::vec3 a, glm::vec3 b, glm::vec3 c, uint mat)
 int main(int argc, char **argv)
 {
 	const char *lib = argc > 1 ? argv[1] : "./B200RT.so";
+	const bool with_gl = argc > 2 && strcmp(argv[2], "--gl") == 0;
 	void *h = dlopen(lib, RTLD_NOW);
 	if (!h)
 	{
@@ -63,7 +81,7 @@ int main(int argc, char **argv)
 	try
 	{
 		printf("targets %zu\n", ctx->get_supported_targets().size());
-		GLuint tex = 0;
+		GLuint tex = with_gl ? 7 : 0;
 		ctx->init(&tex, W, H);
 		ctx->set_sky({glm::vec3(0.2f, 0.3f, 0.4f)}, 1, 1);
 		ctx->set_textures({});
@@ -132,6 +150,16 @@ int main(int argc, char **argv)
 		ctx->get_probe_results(&inst, &prim, &dist);
 		const rfw::RenderStats st = ctx->get_stats();
 		printf("mean %.6f probe %u %u %.4f primary_count %u\n", sum / (3.0 * W * H), inst, prim, dist, st.primaryCount);
+		if (with_gl)
+		{
+			const bool same = g_texture.size() == px.size() && memcmp(g_texture.data(), px.data(), px.size() * sizeof(float)) == 0;
+			printf("gl uploads %u tex %u size %ux%u identical_to_read_pixels %d\n", g_uploads, g_upload_tex, g_upload_w, g_upload_h, same ? 1 : 0);
+			if (g_uploads != 2 || g_upload_tex != 7 || !same)
+			{
+				destroy(ctx);
+				return 5;
+			}
+		}
 	}
 	catch (const std::exception &e)
 	{

@@ -203,11 +203,17 @@ class Camera:
 class RenderContext:
     """Python mirror of rfw::RenderContext over the C ABI; method names follow context.h:78-110."""
 
-    def __init__(self, library: Library, device: int = 0):
+    def __init__(self, library: Library, device: int = 0, devices=None):
+        """devices=[0, 1, ...]: one context that owns several GPUs in this process (rfwb200_create_group) and shards every
+        frame over them; otherwise `device` is the single CUDA ordinal."""
         self.L = library
         self._h = C.c_void_p()
         self._keep = []  # arrays borrowed by the last upload calls (API contract: caller keeps them alive during the call)
-        self._check(self.L.fn("create", C.c_int, [C.c_int, C.POINTER(C.c_void_p)])(device, C.byref(self._h)))
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            self._check(self.L.fn("create_group", C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)])(arr, len(devices), C.byref(self._h)))
+        else:
+            self._check(self.L.fn("create", C.c_int, [C.c_int, C.POINTER(C.c_void_p)])(device, C.byref(self._h)))
         self.width = self.height = 0
         if self.L.post_create is not None:
             self.L.post_create(self)
@@ -325,6 +331,13 @@ class RenderContext:
         self._check(self.L.fn("read_framebuffer", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t])(self._h, out.ctypes.data, n))
         return out
 
+    def read_framebuffer_async(self, pinned_ptr: int, capacity_pixels: int):
+        """rfwb200_read_framebuffer_async into pinned host memory at `pinned_ptr` (e.g. a torch pin_memory tensor's data_ptr)"""
+        self._check(self.L.fn("read_framebuffer_async", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t])(self._h, pinned_ptr, capacity_pixels))
+
+    def read_wait(self):
+        self._check(self.L.fn("read_wait", C.c_int, [C.c_void_p])(self._h))
+
     def read_image(self) -> np.ndarray:
         return self.read_framebuffer().reshape(self.height, self.width, 4)
 
@@ -361,6 +374,37 @@ class RenderContext:
 
     def shard_stride(self) -> int:
         return int(self.L.fn("shard_stride", C.c_size_t, [C.c_void_p])(self._h))
+
+    # -- display image of a sharded frame, one rank per process (rfwb200_display_*) --
+    def display_create(self) -> int:
+        ptr = C.c_void_p()
+        self._check(self.L.fn("display_create", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)])(self._h, C.byref(ptr)))
+        return int(ptr.value or 0)
+
+    def display_export(self) -> bytes:
+        buf = (C.c_ubyte * 64)()
+        self._check(self.L.fn("display_export", C.c_int, [C.c_void_p, C.c_void_p])(self._h, buf))
+        return bytes(buf)
+
+    def display_import(self, handle: bytes):
+        assert len(handle) == 64
+        buf = (C.c_ubyte * 64)(*handle)
+        self._check(self.L.fn("display_import", C.c_int, [C.c_void_p, C.c_void_p])(self._h, buf))
+
+    def display_attach(self, display_rank: "RenderContext"):
+        self._check(self.L.fn("display_attach", C.c_int, [C.c_void_p, C.c_void_p])(self._h, display_rank._h))
+
+    def display_wait(self):
+        self._check(self.L.fn("display_wait", C.c_int, [C.c_void_p])(self._h))
+
+    def display_image(self) -> int:
+        return int(self.L.fn("display_image", C.c_void_p, [C.c_void_p])(self._h) or 0)
+
+    def read_device(self, ptr: int, n_pixels: int) -> np.ndarray:
+        """blocking copy of n_pixels float4 at a device pointer of this context's device (tests)"""
+        out = np.empty((n_pixels, 4), np.float32)
+        self._check(self.L.fn("debug_read_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t])(self._h, ptr, out.ctypes.data, out.nbytes))
+        return out
 
     def assemble_shards(self, gathered_ptr: int, image_ptr: int):
         self._check(self.L.fn("assemble_shards", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p])(self._h, gathered_ptr, image_ptr))

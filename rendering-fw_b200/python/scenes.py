@@ -47,6 +47,7 @@ class Scene:
     dir_lights: np.ndarray = field(default_factory=lambda: np.zeros(0, R.DIR_LIGHT_DTYPE))
     area_lights: np.ndarray = field(default_factory=lambda: np.zeros(0, R.AREA_LIGHT_DTYPE))
     sky: tuple = (np.zeros((1, 3), np.float32), 1, 1)
+    sky_rgbe: np.ndarray | None = None  # (h, w, 4) uint8: the Radiance RGBE texels `sky` was decoded from (kept for the bake)
     camera_pos: tuple = (0, 0, 0)
     camera_dir: tuple = (0, 0, 1)
     fov: float = 40.0
@@ -667,6 +668,43 @@ def atrium(target_tris=262_000, seed=11) -> Scene:
 BAKE_MAGIC = b"RFWB200S"
 
 
+def decode_rgbe(rgbe: np.ndarray) -> np.ndarray:
+    """Radiance RGBE texels -> float32 RGB the way FreeImage's HDR reader does for the reference's skybox
+    (rfw::skybox::load, RFW/system/src/rfw/skybox.cpp:112-133, via FreeImage_ConvertToRGBAF): mantissa * 2^(e - 136), 0 when e == 0."""
+    e = rgbe[..., 3].astype(np.int32)
+    f = np.where(e > 0, np.ldexp(np.float32(1.0), e - 136), np.float32(0.0)).astype(np.float32)
+    return (rgbe[..., :3].astype(np.float32) * f[..., None]).astype(np.float32)
+
+
+def read_radiance_hdr(path) -> np.ndarray:
+    """-> (h, w, 4) uint8 RGBE texels of a Radiance .hdr file (header '-Y h +X w', new-style run-length scanlines), top row first"""
+    blob = Path(path).read_bytes()
+    end = blob.index(b"\n\n") + 2
+    nl = blob.index(b"\n", end)
+    res = blob[end:nl].split()
+    assert res[0] == b"-Y" and res[2] == b"+X", res
+    h, w = int(res[1]), int(res[3])
+    data = np.frombuffer(blob, np.uint8, offset=nl + 1)
+    out = np.empty((h, w, 4), np.uint8)
+    pos = 0
+    for y in range(h):
+        assert data[pos] == 2 and data[pos + 1] == 2 and (int(data[pos + 2]) << 8 | int(data[pos + 3])) == w, "only new-style RLE scanlines"
+        pos += 4
+        for c in range(4):
+            x = 0
+            while x < w:
+                n = int(data[pos])
+                if n > 128:
+                    out[y, x:x + n - 128, c] = data[pos + 1]
+                    x += n - 128
+                    pos += 2
+                else:
+                    out[y, x:x + n, c] = data[pos + 1:pos + 1 + n]
+                    x += n
+                    pos += 1 + n
+    return out
+
+
 def save_baked(scene: Scene, path: Path):
     parts = []
 
@@ -698,8 +736,13 @@ def save_baked(scene: Scene, path: Path):
             data = level0
         put(data)
     sky, sw, sh = scene.sky
-    parts.append(struct.pack("<II", sw, sh))
-    put(np.asarray(sky, np.float32))
+    if scene.sky_rgbe is not None:  # the asset's own RGBE texels (4 bytes per texel instead of 12); bit 31 of the width marks them
+        assert scene.sky_rgbe.shape == (sh, sw, 4) and np.array_equal(decode_rgbe(scene.sky_rgbe).reshape(-1, 3), np.asarray(sky, np.float32).reshape(-1, 3))
+        parts.append(struct.pack("<II", sw | 0x80000000, sh))
+        put(scene.sky_rgbe.astype(np.uint8))
+    else:
+        parts.append(struct.pack("<II", sw, sh))
+        put(np.asarray(sky, np.float32))
     put(scene.point_lights), put(scene.spot_lights), put(scene.dir_lights)
     raw = b"".join(parts)
     Path(path).parent.mkdir(parents=True, exist_ok=True)
@@ -752,7 +795,12 @@ def load_baked(path: Path) -> Scene:
             data = build_mips(data.reshape(h, w))
         s.textures.append({"type": ty, "width": w, "height": h, "data": data})
     sw, sh = take("<II")
-    s.sky = (get(np.float32).reshape(-1, 3), sw, sh)
+    if sw & 0x80000000:
+        sw &= 0x7FFFFFFF
+        s.sky_rgbe = get(np.uint8).reshape(sh, sw, 4)
+        s.sky = (decode_rgbe(s.sky_rgbe).reshape(-1, 3), sw, sh)
+    else:
+        s.sky = (get(np.float32).reshape(-1, 3), sw, sh)
     s.point_lights, s.spot_lights, s.dir_lights = get(R.POINT_LIGHT_DTYPE), get(R.SPOT_LIGHT_DTYPE), get(R.DIR_LIGHT_DTYPE)
     return s
 
@@ -765,3 +813,48 @@ def sponza_or_standin() -> Scene:
     if BAKED_SPONZA.exists():
         return load_baked(BAKED_SPONZA)
     return atrium()
+
+
+def sponza_instanced(copies: int = 38, seed: int = 1234) -> Scene:
+    """BASELINE.json configs[2] stand-in (San Miguel is not in the reference repository): the
+    config-2 scene instanced `copies` times on a jittered 3-D lattice with a rotation about Y per copy — 38 copies of
+    Sponza's 262 k triangles are 10 M triangles behind one instance table, with the triangle-size distribution and the
+    occlusion depth of the real asset.  Copy 0 is the config-2 scene itself (same light, same camera inside it)."""
+    base = sponza_or_standin()
+    if copies <= 1:
+        return base
+    rng = np.random.default_rng(seed)
+    lo, hi = np.full(3, np.inf), np.full(3, -np.inf)
+    for mi, M in base.instances:
+        v = base.meshes[mi].vertices[:, :3].astype(np.float64)
+        w = v @ np.asarray(M, np.float64)[:3, :3].T + np.asarray(M, np.float64)[:3, 3]
+        lo, hi = np.minimum(lo, w.min(0)), np.maximum(hi, w.max(0))
+    size = (hi - lo) * 1.05
+    nx = int(np.ceil(copies ** (1 / 3) * 1.3))
+    nz = int(np.ceil(np.sqrt(copies / nx * 1.5)))
+    ny = int(np.ceil(copies / (nx * nz)))
+    cells = [(x, y, z) for y in range(ny) for z in range(nz) for x in range(nx)]
+    base_instances = list(base.instances)
+    n_light = 1  # the light quad is the last instance of the baked scene and stays with copy 0 only
+    for c in range(1, copies):
+        x, y, z = cells[c]
+        jitter = (rng.random(3) - 0.5) * 0.1 * size
+        T = translate(*(np.array([x, y, z]) * size + jitter)) @ rotate_y(float(rng.integers(0, 4)) * 90.0 + float(rng.random() * 10 - 5))
+        for mi, M in base_instances[: len(base_instances) - n_light]:
+            base.instances.append((mi, T @ np.asarray(M, np.float64)))
+    base.name = f"{base.name} x{copies} (instanced lattice, seed {seed})"
+    return base
+
+
+def add_config5_lights(scene: Scene, scene_scale: float = 0.2) -> Scene:
+    """BASELINE.json configs[4]: add_point_light((-15, 10, -5) * s, (20, 20, 20)) and
+    add_directional_light(normalize(-0.3, -1, 0.2), (3, 3, 3)) with energy = |radiance| (RFW/system/src/rfw/system.cpp:720-758)."""
+    pl = np.zeros(1, R.POINT_LIGHT_DTYPE)
+    pl["position"], pl["radiance"] = (-15 * scene_scale, 10 * scene_scale, -5 * scene_scale), (20, 20, 20)
+    pl["energy"] = np.linalg.norm(pl["radiance"][0])
+    dl = np.zeros(1, R.DIR_LIGHT_DTYPE)
+    d = np.array([-0.3, -1.0, 0.2])
+    dl["direction"], dl["radiance"] = d / np.linalg.norm(d), (3, 3, 3)
+    dl["energy"] = np.linalg.norm(dl["radiance"][0])
+    scene.point_lights, scene.dir_lights = pl, dl
+    return scene

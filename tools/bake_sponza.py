@@ -63,6 +63,12 @@ def load_tga(path: Path, max_dim: int):
 
 
 def load_hdr(path: Path, out_w: int, out_h: int):
+    """(0, 0): the asset as shipped — its RGBE texels are kept and decoded like FreeImage does (scenes.decode_rgbe); any other
+    size: area-resampled with OpenCV (smaller snapshot, stated in the scene name)."""
+    if out_w == 0:
+        rgbe = S.read_radiance_hdr(path)
+        h, w = rgbe.shape[:2]
+        return S.decode_rgbe(rgbe).reshape(-1, 3), w, h, "sky_15.hdr %dx%d as shipped" % (w, h), rgbe
     try:
         import cv2
 
@@ -71,16 +77,16 @@ def load_hdr(path: Path, out_w: int, out_h: int):
             raise RuntimeError("cv2 could not read the HDR")
         img = img[..., ::-1].astype(np.float32)  # BGR -> RGB
         img = cv2.resize(img, (out_w, out_h), interpolation=cv2.INTER_AREA)
-        return img.reshape(-1, 3), out_w, out_h, "sky_15.hdr (area-resampled to %dx%d)" % (out_w, out_h)
+        return img.reshape(-1, 3), out_w, out_h, "sky_15.hdr (area-resampled to %dx%d)" % (out_w, out_h), None
     except Exception as e:  # constant sky, as SURVEY.md §8d allows — stated in the scene name
         print("HDR decode unavailable (%s): constant sky (0.5,0.6,0.8)" % e, file=sys.stderr)
-        return np.tile(np.array([[0.5, 0.6, 0.8]], np.float32), (1, 1)), 1, 1, "constant sky"
+        return np.tile(np.array([[0.5, 0.6, 0.8]], np.float32), (1, 1)), 1, 1, "constant sky", None
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--max-dim", type=int, default=1024, help="textures larger than this are box-downsampled")
-    ap.add_argument("--sky", type=int, nargs=2, default=(2048, 1024))
+    ap.add_argument("--max-dim", type=int, default=4096, help="textures larger than this are box-downsampled (the asset's largest are 2048: default = as shipped)")
+    ap.add_argument("--sky", type=int, nargs=2, default=(0, 0), help="resample the sky to this size; 0 0 = as shipped")
     ap.add_argument("--out", type=Path, default=S.BAKED_SPONZA)
     args = ap.parse_args()
     obj = ASSETS / "models" / "sponza" / "sponza.obj"
@@ -167,10 +173,12 @@ def main():
     scene.meshes.append(S.quad((0, -1, 0), (0, 0, 0), 20.0, 100.0, light_mat))
     scene.instances.append((len(scene.meshes) - 1, S.translate(0, 60.0, 0)))
 
-    sky, sw, sh, sky_note = load_hdr(ASSETS / "envmaps" / "sky_15.hdr", *args.sky)
+    sky, sw, sh, sky_note, rgbe = load_hdr(ASSETS / "envmaps" / "sky_15.hdr", *args.sky)
     scene.sky = (sky, sw, sh)
+    scene.sky_rgbe = rgbe
     scene.camera_pos, scene.camera_dir, scene.fov = (0.0, 10.0, 0.0), (1.0, 0.0, 0.05), 40.0
-    scene.name = "sponza (262k tris, %d meshes, textures<=%d, %s)" % (len(scene.meshes), args.max_dim, sky_note)
+    tex_note = "textures as shipped" if args.max_dim >= 2048 else "textures<=%d" % args.max_dim
+    scene.name = "sponza (262k tris, %d meshes, %s, %s)" % (len(scene.meshes), tex_note, sky_note)
     S.save_baked(scene, args.out)
     print("wrote %s: %.1f MiB in %.1fs" % (args.out, args.out.stat().st_size / 2 ** 20, time.time() - t0))
     return 0
