@@ -265,12 +265,14 @@ struct rfwb200_context
 	// ---- display target of a sharded frame (DisplayTarget, device_types.h) and in-process device groups ----
 	struct Display
 	{
-		void *base = nullptr; // [float4 image[w * h]] [arrivals @ +0, consumed @ +128 of the 256-byte tail]
+		void *base = nullptr; // [float4 image[w * h]] [tail: arrivals @ +0, consumed @ +128, sync arrivals @ +256, seen flags @ +512]
 		size_t image_bytes = 0;
 		bool owner = false, ipc = false;
 		float4 *image = nullptr;
-		uint32_t *arrivals = nullptr, *consumed = nullptr;
+		uint32_t *arrivals = nullptr, *consumed = nullptr, *sync_arrivals = nullptr, *sync_seen = nullptr;
 		uint32_t frames = 0; // sharded frames this context has folded into the image
+		uint32_t syncs = 0;	 // k_shard_sync launches so far (every rank issues the same sequence)
+		uint32_t stamp = 0;	 // wavefronts started so far
 	} display;
 	cudaStream_t copy_stream = nullptr;			 // rfwb200_read_framebuffer_async: the read-back runs beside the next frame's kernels
 	cudaEvent_t ev_frame_done = nullptr, ev_copy_done = nullptr;
@@ -836,6 +838,10 @@ struct StageTimer
 				return r_;                                                                                              \
 	} while (0)
 
+// counters + two sets of flag rows (wavefronts alternate between them, so a rank that is one wavefront ahead never
+// overwrites flags another rank has not read yet)
+constexpr size_t DISPLAY_TAIL_BYTES = 512 + 2 * MAX_DEPTH_SLOTS * MAX_BATCH_SPP * sizeof(uint32_t);
+
 void display_detach(Ctx *c)
 {
 	Ctx::Display &d = c->display;
@@ -859,8 +865,8 @@ int display_bind(Ctx *c, void *base, bool owner, bool ipc)
 	d.image_bytes = (size_t(c->width) * c->height * sizeof(float4) + 255) & ~size_t(255);
 	d.image = static_cast<float4 *>(base);
 	d.arrivals = reinterpret_cast<uint32_t *>(static_cast<char *>(base) + d.image_bytes);
-	d.consumed = d.arrivals + 32;
-	d.frames = 0;
+	d.consumed = d.arrivals + 32, d.sync_arrivals = d.arrivals + 64, d.sync_seen = d.arrivals + 128;
+	d.frames = 0, d.syncs = 0, d.stamp = 0;
 	CK(c->d_display_local.reserve(256));
 	CK(cudaMemsetAsync(c->d_display_local.ptr, 0, 256, c->stream));
 	return RFWB200_OK;
@@ -1804,6 +1810,7 @@ extern "C"
 			const uint32_t maxd = uint32_t(c->rs.max_path_length);
 			const bool sort = c->rs.sort_mode != 0 && maxd > 0;
 			auto shade = c->shade_ieee ? launch_shade_ieee : launch_shade;
+			const bool shard_sync = to_display && c->shard.world > 1;
 			if (sort)
 			{
 				CK(launch_sort_setup(c->scene, c->wf, c->rs, st)); // grid of the bins from the root of the current tree
@@ -1814,15 +1821,39 @@ extern "C"
 				BatchView bv;
 				bv.spp = std::min(bspp, spp - b * bspp), bv.first_sample = b * bspp, bv.index = b;
 				bv.items = c->shard.local_pixels * bv.spp, bv.inv_spp = 1.0f / float(bv.spp);
+				ShardSync sync{};
+				if (shard_sync)
+				{
+					sync.stamp = ++c->display.stamp;
+					sync.seen = c->display.sync_seen + size_t(sync.stamp & 1u) * MAX_DEPTH_SLOTS * MAX_BATCH_SPP;
+					sync.arrivals = c->display.sync_arrivals;
+				}
+				// ranks of a sharded frame merge their "sample s still has extension rays" flags behind every shade launch
+				// whose connect rays are traced (k_shard_sync): one arrival + one short wait per bounce
+				auto merge_flags = [&](uint32_t depth) -> int {
+					if (!shard_sync || depth >= maxd)
+						return RFWB200_OK;
+					c->display.syncs++;
+					// every rank issues the same sequence of syncs (maxd per wavefront); the lag of maxd - 1 syncs means "all ranks
+					// have arrived at the first sync of the wavefront before this one's last", see k_shard_sync
+					const uint32_t lag = maxd - 1u;
+					const uint32_t lagged = c->display.syncs > lag ? (c->display.syncs - lag) * c->shard.world : 0u;
+					CK(launch_shard_sync(sync, depth, c->display.syncs * c->shard.world, lagged, bv.spp,
+										 c->wf.ext_seen + size_t(b * MAX_DEPTH_SLOTS + depth) * MAX_BATCH_SPP, c->d_display_local.as<uint32_t>() + 1, st));
+					c->launches += 1;
+					return RFWB200_OK;
+				};
 				{
 					StageTimer t(c, 0);
 					CK(launch_primary(c->scene, c->shard, c->wf, c->rs, bv, c->dims, st));
 				}
 				{
 					StageTimer t(c, 3);
-					CK(shade(c->scene, c->shard, c->wf, c->rs, bv, 0, 0, 1, c->dims, st));
+					CK(shade(c->scene, c->shard, c->wf, c->rs, bv, 0, 0, 1, sync, c->dims, st));
 				}
 				c->launches += 2;
+				if (int r = merge_flags(0))
+					return r;
 				for (uint32_t d = 1; d <= maxd; d++)
 				{
 					// re-ordering on: shade appends to planes [1], the sort moves them into planes [0], trace and shade read [0];
@@ -1840,9 +1871,11 @@ extern "C"
 					}
 					{
 						StageTimer t(c, 3);
-						CK(shade(c->scene, c->shard, c->wf, c->rs, bv, d, in, out, c->dims, st));
+						CK(shade(c->scene, c->shard, c->wf, c->rs, bv, d, in, out, sync, c->dims, st));
 					}
 					c->launches += 2;
+					if (int r = merge_flags(d))
+						return r;
 				}
 				const bool last = b + 1 == batches;
 				if (last && c->copy_pending) // an asynchronous read-back of the previous frame: the image is overwritten only after it
@@ -2015,8 +2048,8 @@ extern "C"
 		display_detach(c);
 		void *base = nullptr;
 		const size_t image_bytes = (size_t(c->width) * c->height * sizeof(float4) + 255) & ~size_t(255);
-		CK(cudaMalloc(&base, image_bytes + 256));
-		CK(cudaMemset(base, 0, image_bytes + 256));
+		CK(cudaMalloc(&base, image_bytes + DISPLAY_TAIL_BYTES));
+		CK(cudaMemset(base, 0, image_bytes + DISPLAY_TAIL_BYTES));
 		if (int r = display_bind(c, base, true, false))
 			return r;
 		if (image_out)

@@ -110,6 +110,17 @@ struct DisplayTarget
 	uint32_t *local_done; // this rank's CTA counter for the last-CTA-signals pattern
 };
 
+// What the ranks of a sharded frame agree on inside a frame (all of it in the display rank's memory, beside the image): whether
+// sample s of the wavefront emitted an extension ray at depth d ANYWHERE in the frame — the reference's host loop leaves a
+// sample's bounce loop, without tracing its pending shadow rays, as soon as a bounce emits none (CUDART/src/Context.cpp:109-120),
+// and a rank only sees its own tiles.  A flag is set by writing the wavefront's stamp (no clearing between frames).
+struct ShardSync
+{
+	uint32_t *seen;		// [MAX_DEPTH_SLOTS][MAX_BATCH_SPP]; null = this context renders alone (or has no display target)
+	uint32_t *arrivals; // += 1 by every rank after each shade launch below the last depth
+	uint32_t stamp;		// value that means "set" for the wavefront in flight
+};
+
 // uniform grid over the scene box the bounce rays are binned in before they are traced (k_shade emits the key)
 struct SortGrid
 {

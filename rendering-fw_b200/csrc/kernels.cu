@@ -38,12 +38,14 @@
 #define K_SHADE k_shade_ieee
 #define LAUNCH_SHADE launch_shade_ieee
 #define SHADE_OCCUPANCY shade_occupancy_ieee
+#define SHADE_PRELOAD shade_preload_ieee
 #undef RFW_PART
 #define RFW_PART 2
 #else
 #define K_SHADE k_shade
 #define LAUNCH_SHADE launch_shade
 #define SHADE_OCCUPANCY shade_occupancy
+#define SHADE_PRELOAD shade_preload_fast
 #endif
 
 namespace rfwb200
@@ -652,10 +654,9 @@ __device__ __forceinline__ bool fetch_ray(const SceneView &sc, const ShardView &
 	pidx = __float_as_uint(wf.sE[k].w);
 	// The reference only traces the connect queue of a sample when its bounce loop continues, i.e. when that sample
 	// emitted at least one extension ray at this depth anywhere in the frame (CUDART/src/Context.cpp:109-120: the host
-	// loop leaves before the pending shadow rays are traced).  A rank of a sharded frame only knows about its own tiles,
-	// so it always traces: the two agree whenever some path of the sample continues somewhere in the frame — every frame
-	// of more than a handful of pixels — and the assembled frame does not depend on how it was sharded.
-	if (sh.world == 1u && q.seen[(pidx >> 5) - fast_div(pidx >> 5, bv.spp, bv.inv_spp) * bv.spp] == 0u)
+	// loop leaves before the pending shadow rays are traced).  The ranks of a sharded frame merge their flags between the
+	// shade launch and this one (k_shard_sync), so the assembled frame does not depend on how it was sharded.
+	if (q.seen[(pidx >> 5) - fast_div(pidx >> 5, bv.spp, bv.inv_spp) * bv.spp] == 0u)
 		return false;
 	n_traced++;
 	const float4 O4 = wf.sO[k], D4 = wf.sD[k];
@@ -1875,7 +1876,7 @@ __device__ V3 RandomPointOnLight(const SceneView &sc, float r0, float r1, V3 I, 
 #endif
 __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, const ShardView sh, const WavefrontView wf,
 											  const RenderSettings rs, const BatchView bv, const uint32_t pathLength,
-											  const uint32_t buf, const uint32_t nbuf)
+											  const uint32_t buf, const uint32_t nbuf, const ShardSync sync)
 {
 	DepthCounters *curc = &wf.counters[bv.index * MAX_DEPTH_SLOTS + pathLength];
 	const uint32_t n_paths = pathLength == 0 ? bv.items : wf.counters[bv.index * MAX_DEPTH_SLOTS + pathLength - 1].ext;
@@ -2049,8 +2050,12 @@ __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, c
 								V3 lightColor = mk(0.f);
 								float pickProb = 0, lightPdf = 0;
 								V3 L = RandomPointOnLight(sc, r0, r1, I, iN, pickProb, lightPdf, lightColor) - I;
-								const float dist = length(L);
-								L = L * (1.0f / dist);
+								// The connect ray's direction and length decide whether it stops 2e-5 short of the light it aims at or
+								// inside it (one float ulp at Sponza scale is larger than that, DESIGN.md "Epsilons"): they are computed
+								// with correctly rounded sqrt / division in the fast-math build too, so both builds and the CPU oracle
+								// aim the same ray; everything else of the shade kernel keeps -use_fast_math.
+								const float dist = __fsqrt_rn(dot(L, L));
+								L = L * __fdiv_rn(1.0f, dist);
 								const float NdotL = dot(L, iN);
 								if (NdotL > 0 && lightPdf > 0)
 								{
@@ -2144,7 +2149,11 @@ __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, c
 				const uint32_t slot = ebase + __popc(m_ex & lt_mask);
 				wf.O[nbuf][slot] = eO, wf.D[nbuf][slot] = eD, wf.T[nbuf][slot] = eT;
 				if (seen[sampleInBatch] == 0u) // this sample's bounce loop continues (CUDART/src/Context.cpp:109-120)
+				{
 					seen[sampleInBatch] = 1u;
+					if (sync.seen != nullptr) // tell the other ranks of a sharded frame (a handful of peer stores per sample and depth)
+						*reinterpret_cast<volatile uint32_t *>(sync.seen + pathLength * MAX_BATCH_SPP + sampleInBatch) = sync.stamp;
+				}
 				if (binning)
 				{
 					// counting sort, first half: the lanes of the warp that emit into the same bin are found with one
@@ -2245,6 +2254,50 @@ __global__ void k_display_spin(const volatile uint32_t *counter, const uint32_t 
 	}
 	__threadfence_system();
 }
+// Between shade(depth) and trace(depth + 1) of a sharded frame: this rank arrives (its own flags were published by the
+// shade launch) and takes over the merged "sample s emitted an extension ray" flags (ShardSync).  It only has to WAIT for
+// the other ranks' shade launches when one of its own flags is still clear — a set flag cannot be unset by anybody — so
+// in an ordinary frame the ranks do not run in lockstep.  `need_lagged` (arrivals of an earlier sync) is waited for in
+// any case: it bounds how far a rank may run ahead, so that the flag rows of the wavefront after next (same rows, see
+// DISPLAY_TAIL_BYTES) are not written while a slower rank still reads this wavefront's.
+__global__ void k_shard_sync(const ShardSync sync, const uint32_t depth, const uint32_t need_full, const uint32_t need_lagged,
+							 const uint32_t spp, uint32_t *local_seen_row, uint32_t *err)
+{
+	__shared__ uint32_t any_clear;
+	if (threadIdx.x == 0)
+		any_clear = 0u;
+	__syncthreads();
+	if (threadIdx.x < spp && local_seen_row[threadIdx.x] == 0u)
+		any_clear = 1u;
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		__threadfence_system();
+		atomicAdd_system(sync.arrivals, 1u);
+		const uint32_t need = any_clear ? need_full : need_lagged;
+		unsigned long long t0, t1;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+		while (*reinterpret_cast<const volatile uint32_t *>(sync.arrivals) < need)
+		{
+			__nanosleep(200);
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+			if (t1 - t0 > 4000000000ull)
+			{
+				*err = 1u; // the frame goes on with this rank's own flags
+				break;
+			}
+		}
+		__threadfence_system();
+	}
+	__syncthreads();
+	if (any_clear && threadIdx.x < spp)
+	{
+		const uint32_t g = *reinterpret_cast<const volatile uint32_t *>(sync.seen + depth * MAX_BATCH_SPP + threadIdx.x);
+		if (g == sync.stamp)
+			local_seen_row[threadIdx.x] = 1u;
+	}
+}
+
 __global__ void k_display_release(uint32_t *consumed, const uint32_t value)
 {
 	__threadfence_system();
@@ -2669,6 +2722,14 @@ __global__ void k_generate_only(const SceneView sc, const ShardView sh, const Wa
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
+cudaError_t shade_preload_fast();
+cudaError_t shade_preload_ieee();
+static cudaError_t shade_preload()
+{
+	const cudaError_t e = shade_preload_fast();
+	return e != cudaSuccess ? e : shade_preload_ieee();
+}
+
 cudaError_t configure_launches(const RenderSettings &rs, uint32_t node_count, LaunchDims &dims)
 {
 	int dev = 0, sms = 0;
@@ -2706,6 +2767,21 @@ cudaError_t configure_launches(const RenderSettings &rs, uint32_t node_count, La
 			if (e != cudaSuccess)
 				return e;
 		}
+	}
+	// Load every kernel of the frame now.  With CUDA's lazy module loading the first launch of a kernel may have to wait
+	// for the device to drain, and the ranks of a sharded frame wait for each other INSIDE kernels (k_display_spin,
+	// k_shard_sync): a first frame would sit in that wait until its time-out.
+	{
+		const void *all[] = {(const void *)k_fold,		   (const void *)k_sort_setup,		(const void *)k_sort_scan,	  (const void *)k_sort_move,
+							 (const void *)k_display_spin, (const void *)k_display_release, (const void *)k_shard_sync, (const void *)k_assemble,
+							 (const void *)k_tone_map,	   (const void *)k_generate_only,	(const void *)k_emode,		  (const void *)k_trace_closest,
+							 (const void *)k_trace_occluded};
+		cudaFuncAttributes fa;
+		for (const void *k : all)
+			if ((e = cudaFuncGetAttributes(&fa, k)) != cudaSuccess)
+				return e;
+		if ((e = shade_preload()) != cudaSuccess)
+			return e;
 	}
 	int per_sm = 0;
 	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wavefront_trace<false, 1, 0, false>, dims.trace_block, dims.trace_smem);
@@ -2795,6 +2871,12 @@ cudaError_t launch_display_spin(const uint32_t *counter, uint32_t need, uint32_t
 	k_display_spin<<<1, 1, 0, stream>>>(counter, need, err);
 	return cudaGetLastError();
 }
+cudaError_t launch_shard_sync(const ShardSync &sync, uint32_t depth, uint32_t need_full, uint32_t need_lagged, uint32_t spp,
+							  uint32_t *local_seen_row, uint32_t *err, cudaStream_t stream)
+{
+	k_shard_sync<<<1, MAX_BATCH_SPP, 0, stream>>>(sync, depth, need_full, need_lagged, spp, local_seen_row, err);
+	return cudaGetLastError();
+}
 cudaError_t launch_display_release(uint32_t *consumed, uint32_t value, cudaStream_t stream)
 {
 	k_display_release<<<1, 1, 0, stream>>>(consumed, value);
@@ -2867,14 +2949,20 @@ cudaError_t launch_assemble(const ShardView &sh, const float4 *gathered, size_t 
 
 #if RFW_PART != 1 // ---- shade part ----
 cudaError_t LAUNCH_SHADE(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
-						 const BatchView &bv, uint32_t depth, uint32_t in_buf, uint32_t out_buf, const LaunchDims &dims, cudaStream_t stream)
+						 const BatchView &bv, uint32_t depth, uint32_t in_buf, uint32_t out_buf, const ShardSync &sync, const LaunchDims &dims,
+						 cudaStream_t stream)
 {
-	K_SHADE<<<dims.shade_grid, dims.shade_block, 0, stream>>>(sc, sh, wf, rs, bv, depth, in_buf, out_buf);
+	K_SHADE<<<dims.shade_grid, dims.shade_block, 0, stream>>>(sc, sh, wf, rs, bv, depth, in_buf, out_buf, sync);
 	return cudaGetLastError();
 }
 cudaError_t SHADE_OCCUPANCY(int block, int *per_sm)
 {
 	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, K_SHADE, block, 0);
+}
+cudaError_t SHADE_PRELOAD()
+{
+	cudaFuncAttributes fa;
+	return cudaFuncGetAttributes(&fa, K_SHADE);
 }
 #endif // RFW_PART != 1 (shade part)
 

@@ -26,10 +26,12 @@ cudaError_t launch_primary(const SceneView &sc, const ShardView &sh, const Wavef
 						   const BatchView &bv, const LaunchDims &dims, cudaStream_t stream);
 // in_buf: ray planes the paths are read from; out_buf: planes the extension rays are appended to
 cudaError_t launch_shade(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
-						 const BatchView &bv, uint32_t depth, uint32_t in_buf, uint32_t out_buf, const LaunchDims &dims, cudaStream_t stream);
+						 const BatchView &bv, uint32_t depth, uint32_t in_buf, uint32_t out_buf, const ShardSync &sync, const LaunchDims &dims,
+						 cudaStream_t stream);
 // the same kernel built without -use_fast_math (setting "shade_math" = "ieee")
 cudaError_t launch_shade_ieee(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
-							  const BatchView &bv, uint32_t depth, uint32_t in_buf, uint32_t out_buf, const LaunchDims &dims, cudaStream_t stream);
+							  const BatchView &bv, uint32_t depth, uint32_t in_buf, uint32_t out_buf, const ShardSync &sync, const LaunchDims &dims,
+							  cudaStream_t stream);
 cudaError_t launch_trace(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
 						 const BatchView &bv, uint32_t depth, uint32_t in_buf, const LaunchDims &dims, cudaStream_t stream);
 // accumulator += samples of the wavefront; write_fb: framebuffer = accumulator * scale (Kernels.cu:181-203)
@@ -40,6 +42,10 @@ cudaError_t launch_fold(const ShardView &sh, const WavefrontView &wf, const Batc
 // publish a counter value
 cudaError_t launch_display_spin(const uint32_t *counter, uint32_t need, uint32_t *err, cudaStream_t stream);
 cudaError_t launch_display_release(uint32_t *consumed, uint32_t value, cudaStream_t stream);
+// sharded frame, between shade(depth) and trace(depth + 1): arrive; wait for `need_full` arrivals and merge the ranks' ext-seen
+// flags if one of this rank's `spp` flags is clear, else only for `need_lagged`
+cudaError_t launch_shard_sync(const ShardSync &sync, uint32_t depth, uint32_t need_full, uint32_t need_lagged, uint32_t spp,
+							  uint32_t *local_seen_row, uint32_t *err, cudaStream_t stream);
 // re-ordering of the extension rays shade(depth - 1) appended (planes [1] -> planes [0]): bin scan + move
 cudaError_t launch_sort_setup(const SceneView &sc, const WavefrontView &wf, const RenderSettings &rs, cudaStream_t stream);
 cudaError_t launch_sort(const WavefrontView &wf, const RenderSettings &rs, const BatchView &bv, uint32_t depth, const LaunchDims &dims,

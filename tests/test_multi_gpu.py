@@ -21,6 +21,15 @@ def unit_cornell():
     return S.cornell_box(unit_scale=True)
 
 
+def dying_wavefront():
+    """the adapter driver's scene: no path continues after the first bounce, so the reference's loop leaves every sample
+    before its depth-1 shadow rays are traced (CUDART/src/Context.cpp:109-120) — the ranks of a sharded frame have to agree
+    on that (k_shard_sync), although each of them only sees a few tiles"""
+    from test_adapter import _driver_scene
+
+    return _driver_scene()
+
+
 def _single(product_lib, scene_fn, W, H, spp, frames=1, **settings):
     sc = scene_fn()
     ctx = R.RenderContext(product_lib)
@@ -38,7 +47,7 @@ def _single(product_lib, scene_fn, W, H, spp, frames=1, **settings):
 
 
 @pytest.mark.parametrize("world", [2, 3, 8])
-@pytest.mark.parametrize("scene", [unit_cornell, S.feature_soup])
+@pytest.mark.parametrize("scene", [unit_cornell, S.feature_soup, dying_wavefront])
 def test_device_group_frame_is_bit_identical_to_one_device(product_lib, scene, world):
     """rfwb200_create_group: one context, `world` ranks (here all on device 0), one render_frame call; every rank's fold
     kernel writes its tiles into rank 0's display image.  Frame, counters and probe equal the single-device context's."""

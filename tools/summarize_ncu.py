@@ -62,8 +62,13 @@ def full(rep, out):
                     d[label] = float(r[h.index(m)].replace(",", ""))
                 except ValueError:
                     pass
-        if "dram_read_MB" in d and u[h.index("dram__bytes_read.sum")].lower().startswith("g"):
-            d["dram_read_MB"] *= 1e3
+        for m, label in (("dram__bytes_read.sum", "dram_read_MB"), ("dram__bytes_write.sum", "dram_write_MB")):
+            if label in d:  # ncu picks a unit per column: normalise to MB
+                unit = u[h.index(m)].lower()
+                d[label] *= {"g": 1e3, "m": 1.0, "k": 1e-3, "b": 1e-6}.get(unit[:1], 1.0)
+        if "gpu_time_us" in d:
+            unit = u[h.index("gpu__time_duration.sum")].lower()
+            d["gpu_time_us"] *= {"ms": 1e3, "us": 1.0, "ns": 1e-3, "s": 1e6}.get(unit.replace("econd", ""), 1.0)
         res.append(d)
     json.dump({"source": rep, "launches": res}, open(out, "w"), indent=1)
     for d in res:
