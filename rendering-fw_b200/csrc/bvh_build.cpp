@@ -108,6 +108,10 @@ struct Task
 	int32_t node;
 	std::vector<Ref> refs;
 	int32_t depth;
+	int64_t budget = 0; // references spatial splits below this node may still duplicate.  The budget travels with the task
+						// (a split hands what is left to its children in proportion to their reference counts) instead of
+						// living in one shared counter, so the tree does not depend on which worker thread splits first:
+						// every build of the same triangles — on every rank of a sharded frame — gives the same tree.
 };
 
 inline int ceil_log2(uint32_t v)
@@ -152,7 +156,6 @@ struct Builder
 	const BuildTriangle *tris = nullptr;
 	std::vector<Node2> nodes;
 	std::atomic<int32_t> next_node{1};
-	std::atomic<int64_t> spare_refs{0}; // remaining duplication budget
 	float root_area = 1.0f;
 	bool spatial = true;
 	int max_leaf = MAX_LEAF;
@@ -251,7 +254,8 @@ struct Builder
 		// ---- spatial split: chopped binning over the node box ---------------------------------------------
 		int sp_axis = -1;
 		float sp_pos = 0.0f, sp_cost = 3.0e38f;
-		if (spatial && !force_median && count > uint32_t(max_leaf) && spare_refs.load(std::memory_order_relaxed) > 0 &&
+		int64_t budget_left = t.budget;
+		if (spatial && !force_median && count > uint32_t(max_leaf) && t.budget > 0 &&
 			(obj_axis < 0 || obj_overlap > SPATIAL_ALPHA * root_area))
 		{
 			for (int axis = 0; axis < 3; axis++)
@@ -345,10 +349,11 @@ struct Builder
 						right.push_back(r);
 				}
 			}
+			const int64_t extra = int64_t(left.size() + right.size()) - int64_t(count);
 			if (!left.empty() && !right.empty() && left.size() < count + count / 2 && right.size() < count + count / 2 &&
-				(left.size() < count || right.size() < count))
+				(left.size() < count || right.size() < count) && extra <= t.budget)
 			{
-				spare_refs.fetch_sub(int64_t(left.size() + right.size()) - int64_t(count), std::memory_order_relaxed);
+				budget_left = t.budget - extra;
 				done = true;
 			}
 			else
@@ -387,7 +392,16 @@ struct Builder
 		std::vector<Ref>().swap(refs);
 
 		const int32_t l = next_node.fetch_add(2), r = l + 1;
+		if (size_t(r) >= nodes.size()) // cannot happen while the budget holds (nodes are sized for it); never write past the array
+		{
+			t.refs.swap(left);
+			t.refs.insert(t.refs.end(), right.begin(), right.end());
+			make_leaf(node, t.refs);
+			return false;
+		}
 		node.left = l, node.right = r;
+		lt.budget = int64_t(double(budget_left) * double(left.size()) / double(left.size() + right.size()));
+		rt.budget = budget_left - lt.budget;
 		Box lb, rb;
 		lb.reset(), rb.reset();
 		for (const Ref &x : left)
@@ -516,7 +530,7 @@ static size_t build_tree2(Builder &b, const BuildTriangle *tris, size_t count, i
 	b.tris = tris;
 	b.spatial = spatial_splits;
 	b.root_area = std::max(root_box.area(), 1e-30f);
-	b.spare_refs.store(int64_t(double(count) * REF_BUDGET));
+	root->budget = int64_t(double(count) * REF_BUDGET);
 	const size_t max_refs = count + size_t(double(count) * REF_BUDGET) + 64;
 	b.nodes.resize(2 * max_refs + 2);
 	b.nodes[0].box = root_box;

@@ -198,6 +198,7 @@ struct rfwb200_context
 	std::vector<HostMesh> meshes;
 	std::vector<HostInstance> instances;
 	std::vector<rfwb200_material> materials, materials_raw;
+	std::vector<rfwb200_material_tex_ids> material_tex_ids;
 	std::vector<HostTexture> textures;
 	bool geometry_dirty = true, topology_dirty = true;
 	std::vector<std::pair<int, size_t>> built_layout; // (mesh, tri count) per instance at last build
@@ -1050,6 +1051,8 @@ extern "C"
 		return RFWB200_OK;
 	}
 
+	static int resolve_and_upload_materials(rfwb200_context *c);
+
 	int rfwb200_set_textures(rfwb200_context *c, const rfwb200_texture_data *tex, size_t count)
 	{
 		REQUIRE(c && (tex || count == 0), "bad textures");
@@ -1096,6 +1099,15 @@ extern "C"
 		CK(cudaMemcpy(c->d_tex_desc.ptr, desc.data(), desc.size() * 4, cudaMemcpyHostToDevice));
 		c->scene.uint_texels = c->d_uint_tex.as<uint32_t>(), c->scene.uint_texel_count = uint32_t(upool.size());
 		c->scene.float_texels = c->d_float_tex.as<float>(), c->scene.float_texel_count = uint32_t(fpool.size() / 4);
+		if (!c->materials_raw.empty()) // materials uploaded earlier keep texture ids: point them at the new pool
+		{
+			bool all_known = true;
+			for (const rfwb200_material_tex_ids &t : c->material_tex_ids)
+				for (int k = 0; k < 11; k++)
+					all_known &= t.texture[k] < int(count);
+			if (all_known) // otherwise the caller is about to send matching materials (set_textures precedes set_materials)
+				return resolve_and_upload_materials(c);
+		}
 		return RFWB200_OK;
 	}
 
@@ -1106,8 +1118,21 @@ extern "C"
 		FORWARD(rfwb200_set_materials(p_, mats, ids, count));
 		if (int r = ensure_device(c))
 			return r;
-		c->materials.assign(mats, mats + count);
 		c->materials_raw.assign(mats, mats + count);
+		if (ids)
+			c->material_tex_ids.assign(ids, ids + count);
+		else
+			c->material_tex_ids.clear();
+		return resolve_and_upload_materials(c);
+	}
+
+	// texaddr fields of the uploaded materials <- texel offsets of the current texture pool (CUDART/src/Context.cpp:167-191);
+	// runs again when the textures change, so materials never point at the offsets of an older pool
+	static int resolve_and_upload_materials(rfwb200_context *c)
+	{
+		const size_t count = c->materials_raw.size();
+		c->materials = c->materials_raw;
+		const rfwb200_material_tex_ids *ids = c->material_tex_ids.empty() ? nullptr : c->material_tex_ids.data();
 		for (size_t i = 0; i < count && ids; i++)
 		{
 			// CUDART/src/Context.cpp:167-191 (slot 8 = ROUGHNESS1 has no descriptor)
@@ -1251,6 +1276,14 @@ extern "C"
 			layout.emplace_back(in.mesh, ok ? c->meshes[in.mesh].triangles.size() : 0);
 			total += layout.back().second;
 		}
+		// a triangle's material index is used unchecked by the shade kernel: validate the meshes that changed
+		c->mesh_dirty.resize(c->meshes.size(), 1);
+		for (size_t mi = 0; mi < c->meshes.size(); mi++)
+			if (c->mesh_dirty[mi])
+				for (const rfwb200_triangle &t : c->meshes[mi].triangles)
+					if (t.material >= c->materials_raw.size())
+						return set_error(RFWB200_ERR_INVALID, "mesh " + std::to_string(mi) + " references material " + std::to_string(t.material) +
+																  " but only " + std::to_string(c->materials_raw.size()) + " materials were set");
 		const bool can_refit = !c->topology_dirty && layout == c->built_layout && (!c->bvh.nodes.empty() || !c->bvh.cw_nodes.empty() || c->device_built) && c->built_tri_count == total;
 		const bool device = c->device_geometry && total > 0;
 		c->mesh_dirty.resize(c->meshes.size(), 1);
@@ -1662,7 +1695,7 @@ extern "C"
 		else if (k == "trace_variant")
 		{
 			const int n = atoi(v.c_str());
-			REQUIRE(n >= 0 && n <= 12, "trace_variant must be in [0, 12]");
+			REQUIRE(n >= 0 && n <= 13, "trace_variant must be in [0, 13]");
 			c->rs.trace_variant = c->rs.primary_variant = n; // one value for both kinds of launch; primary_variant overrides
 		}
 		else if (k == "primary_cache")
@@ -1672,7 +1705,7 @@ extern "C"
 		else if (k == "primary_variant")
 		{
 			const int n = atoi(v.c_str());
-			REQUIRE(n >= 0 && n <= 12, "primary_variant must be in [0, 12]");
+			REQUIRE(n >= 0 && n <= 13, "primary_variant must be in [0, 13]");
 			c->rs.primary_variant = n;
 		}
 		else if (k == "refit")

@@ -212,8 +212,18 @@ __device__ __forceinline__ uint32_t ray_bin(const SortGrid &g, int cell_bits, in
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
 
+__device__ __forceinline__ void stage_bytes(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *mbar);
 __device__ __forceinline__ void stage_nodes(float4 *smem_nodes, const BvhNode4 *gnodes, uint32_t n_stage, uint64_t *mbar)
 {
+	stage_bytes(smem_nodes, gnodes, n_stage * uint32_t(sizeof(BvhNode4)), mbar);
+}
+// one TMA bulk copy (cp.async.bulk, SASS: UBLKCP) of `bytes` (a multiple of 16) from global to shared memory, completion on an
+// mbarrier every thread of the CTA then waits on
+__device__ __forceinline__ void stage_bytes(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *mbar)
+{
+	float4 *smem_nodes = static_cast<float4 *>(smem_dst);
+	const void *gnodes = gsrc;
+	const uint32_t n_stage = bytes;
 	if (n_stage == 0)
 		return;
 	const uint32_t bar = smem_u32(mbar);
@@ -225,7 +235,6 @@ __device__ __forceinline__ void stage_nodes(float4 *smem_nodes, const BvhNode4 *
 	__syncthreads();
 	if (threadIdx.x == 0)
 	{
-		const uint32_t bytes = n_stage * uint32_t(sizeof(BvhNode4));
 		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
 						 smem_u32(smem_nodes)),
@@ -728,7 +737,10 @@ __device__ __forceinline__ void close_launch(const RenderSettings &rs, DepthCoun
 	}
 }
 
-template <bool PRIMARY, int LQ, int LEAN, bool PACKED>
+// STAGE_P: the first rs.smem_nodes PACKED nodes (80 B each: 256 nodes = 20 KB) are staged into shared memory with one TMA bulk copy
+// per CTA, and node fetches below that index read shared memory (setting smem_nodes with the packed variants; measured in
+// profiles/r02 against the L1-only default).
+template <bool PRIMARY, int LQ, int LEAN, bool PACKED, bool STAGE_P = false>
 __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const SceneView sc, const ShardView sh, const WavefrontView wf,
 															const RenderSettings rs, const BatchView bv, const uint32_t depth,
 															const uint32_t in_buf)
@@ -736,9 +748,12 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 	constexpr bool STAGED = (LQ == 1 && LEAN == 0 && !PACKED);
 	__shared__ uint64_t mbar;
 	float4 *snodes = reinterpret_cast<float4 *>(g_dyn_smem);
-	const uint32_t n_smem = STAGED ? min(uint32_t(rs.smem_nodes), sc.node_count) : 0u;
+	const uint4 *snodes16 = reinterpret_cast<const uint4 *>(g_dyn_smem);
+	const uint32_t n_smem = (STAGED || STAGE_P) ? min(uint32_t(rs.smem_nodes), sc.node_count) : 0u;
 	if (STAGED)
 		stage_nodes(snodes, sc.nodes, n_smem, &mbar);
+	if (STAGE_P)
+		stage_bytes(g_dyn_smem, sc.nodes16, n_smem * 80u, &mbar);
 
 	DepthCounters *curc = &wf.counters[bv.index * MAX_DEPTH_SLOTS + depth];
 	const TraceQueue q = open_queue<PRIMARY>(sh, wf, bv, depth, in_buf);
@@ -849,7 +864,7 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 					if (PACKED)
 					{
 						// five 16-byte pieces: min corner, three axes of bfloat16 planes (lo0 lo1 | lo2 lo3 | hi0 hi1 | hi2 hi3), children
-						const uint4 *np_ = sc.nodes16 + size_t(cur) * 5;
+						const uint4 *np_ = (STAGE_P && uint32_t(cur) < n_smem) ? snodes16 + size_t(cur) * 5 : sc.nodes16 + size_t(cur) * 5;
 						const uint4 hp = np_[0], px = np_[1], py = np_[2], pz = np_[3];
 						n.child = *reinterpret_cast<const int4 *>(np_ + 4);
 						// t = plane * idir - o * idir with plane = p + v:  v * idir + (p * idir - o * idir)
@@ -2783,6 +2798,18 @@ cudaError_t configure_launches(const RenderSettings &rs, uint32_t node_count, La
 		if ((e = shade_preload()) != cudaSuccess)
 			return e;
 	}
+	{
+		dims.trace_smem16 = size_t(staged) * 80;
+		const void *ks[] = {(const void *)k_wavefront_trace<true, 1, 2, true, true>, (const void *)k_wavefront_trace<false, 1, 2, true, true>};
+		for (const void *k : ks)
+			if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dims.trace_smem16))) != cudaSuccess)
+				return e;
+		int p16 = 0;
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p16, k_wavefront_trace<false, 1, 2, true, true>, dims.trace_block, dims.trace_smem16);
+		if (e != cudaSuccess)
+			return e;
+		dims.trace_grid_staged16 = sms * (p16 < 1 ? 1 : p16);
+	}
 	int per_sm = 0;
 	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wavefront_trace<false, 1, 0, false>, dims.trace_block, dims.trace_smem);
 	if (e != cudaSuccess)
@@ -2809,7 +2836,7 @@ cudaError_t launch_primary(const SceneView &sc, const ShardView &sh, const Wavef
 		k_wavefront_trace_cw<true><<<dims.trace_grid, dims.trace_block, 0, stream>>>(sc, sh, wf, rs, bv, 0u, 0u);
 		return cudaGetLastError();
 	}
-	switch (rs.smem_nodes > 0 ? 0 : rs.primary_variant) // the staged prefix only exists in variant 0
+	switch ((rs.smem_nodes > 0 && rs.primary_variant != 13) ? 0 : rs.primary_variant) // the staged fp32 prefix only exists in variant 0, the staged packed one in 13
 	{
 #define RFW_TRACE_CASE(V, LQ, LEAN, PACKED)                                                                                     \
 	case V:                                                                                                             \
@@ -2824,6 +2851,9 @@ cudaError_t launch_primary(const SceneView &sc, const ShardView &sh, const Wavef
 		RFW_TRACE_CASE(10, 1, 1, true)
 		RFW_TRACE_CASE(11, 1, 3, true)
 		RFW_TRACE_CASE(12, 1, 4, true)
+	case 13: // packed nodes with the TMA-staged prefix
+		k_wavefront_trace<true, 1, 2, true, true><<<dims.trace_grid_staged16, dims.trace_block, dims.trace_smem16, stream>>>(sc, sh, wf, rs, bv, 0u, 0u);
+		break;
 	default:
 		RFW_TRACE_CASE(0, 1, 0, false)
 #undef RFW_TRACE_CASE
@@ -2838,7 +2868,7 @@ cudaError_t launch_trace(const SceneView &sc, const ShardView &sh, const Wavefro
 		k_wavefront_trace_cw<false><<<dims.trace_grid, dims.trace_block, 0, stream>>>(sc, sh, wf, rs, bv, depth, in_buf);
 		return cudaGetLastError();
 	}
-	switch (rs.smem_nodes > 0 ? 0 : rs.trace_variant)
+	switch ((rs.smem_nodes > 0 && rs.trace_variant != 13) ? 0 : rs.trace_variant)
 	{
 #define RFW_TRACE_CASE(V, LQ, LEAN, PACKED)                                                                                     \
 	case V:                                                                                                             \
@@ -2853,6 +2883,9 @@ cudaError_t launch_trace(const SceneView &sc, const ShardView &sh, const Wavefro
 		RFW_TRACE_CASE(10, 1, 1, true)
 		RFW_TRACE_CASE(11, 1, 3, true)
 		RFW_TRACE_CASE(12, 1, 4, true)
+	case 13: // packed nodes with the TMA-staged prefix
+		k_wavefront_trace<false, 1, 2, true, true><<<dims.trace_grid_staged16, dims.trace_block, dims.trace_smem16, stream>>>(sc, sh, wf, rs, bv, depth, in_buf);
+		break;
 	default:
 		RFW_TRACE_CASE(0, 1, 0, false)
 #undef RFW_TRACE_CASE

@@ -14,6 +14,8 @@ struct LaunchDims
 	int shade_grid = 0, shade_block = 128;
 	int move_grid = 0;
 	size_t trace_smem = 0; // dynamic shared memory of the trace kernels (staged BVH prefix)
+	size_t trace_smem16 = 0; // the same for the packed-node variant (80 B per staged node)
+	int trace_grid_staged16 = 0;
 };
 
 // queries occupancy for the current device and smem_nodes setting, sets function attributes

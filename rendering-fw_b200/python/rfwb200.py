@@ -407,15 +407,6 @@ class RenderContext:
         self._check(self.L.fn("debug_read_plane", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t])(self._h, which, out.ctypes.data, n))
         return out
 
-    def debug_read_scene(self, which: int) -> np.ndarray:
-        """committed device scene (rfwb200_debug_read_scene): 0 BVH nodes (128 B), 1 triangle records (48 B), 2 shading triangles (96 B) as bytes"""
-        n = C.c_size_t()
-        f = self.L.fn("debug_read_scene", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)])
-        self._check(f(self._h, which, None, 0, C.byref(n)))
-        out = np.empty(n.value, np.uint8)
-        self._check(f(self._h, which, out.ctypes.data, out.nbytes, C.byref(n)))
-        return out
-
     def read_device(self, ptr: int, n_pixels: int) -> np.ndarray:
         """blocking copy of n_pixels float4 at a device pointer of this context's device (tests)"""
         out = np.empty((n_pixels, 4), np.float32)

@@ -214,3 +214,23 @@ def test_lbvh_degenerate_inputs(product_lib):
     for k in (1, 2, 3, 5, 9):  # identical triangles: identical Morton codes, ties broken by the index bits of the key
         t, tri, info = host_check_lbvh(product_lib, np.repeat(one, k, axis=0), o, d)
         assert tri[0] >= 0 and abs(t[0] - 2) < 1e-5 and info["nodes"] >= 1
+
+
+def test_parallel_sbvh_build_is_deterministic(product_lib):
+    """The SAH + spatial-split builder runs large subtrees on a pool of host threads; the duplication budget travels with the
+    tasks (not in one shared counter), so two builds of the same triangles — e.g. on two ranks of a sharded frame — give
+    the same tree whatever the thread timing: same node / reference counts, same SAH cost, same walk for every ray."""
+    rng = np.random.default_rng(5)
+    n = 150_000  # above the threshold that makes the build parallel
+    c = rng.uniform(-10, 10, size=(n, 1, 3))
+    # long thin triangles mixed with small ones: plenty of spatial splits competing for the budget
+    e = rng.normal(size=(n, 3, 3)) * np.where(rng.random((n, 1, 1)) < 0.3, [[[3.0, 0.05, 0.05]]], 0.15)
+    tris = np.ascontiguousarray((c + e).reshape(n, 9), np.float32)
+    o, d = rays(3000, 9, 10.0)
+    runs = [host_check(product_lib, tris, o, d, True) for _ in range(3)]
+    t0, tri0, i0 = runs[0]
+    assert i0["refs"] > n  # spatial splits happened
+    for t, tri, info in runs[1:]:
+        assert (info["nodes"], info["refs"], info["depth"]) == (i0["nodes"], i0["refs"], i0["depth"])
+        assert info["sah"] == i0["sah"]
+        assert np.array_equal(info["visits"], i0["visits"]) and np.array_equal(tri, tri0) and np.array_equal(t, t0)

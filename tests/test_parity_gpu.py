@@ -767,3 +767,28 @@ def test_wavefront_batching_and_reordering_do_not_change_a_single_bit(product_li
         ctx.close()
     assert np.array_equal(imgs[0], imgs[1])
     assert counters[0] == counters[1]
+
+
+def test_material_indices_are_validated_and_textures_can_be_resent(product_lib):
+    """update() rejects a triangle whose material index was never set (the shade kernel uses it unchecked), and
+    re-sending the textures after the materials re-resolves the materials' texel offsets instead of leaving stale ones."""
+    W, H = 96, 64
+    sc = S.feature_soup()
+    ctx = R.RenderContext(product_lib)
+    S.upload(ctx, sc, W, H)
+    ctx.set_setting("spp", 2)
+    cam = sc.camera(W, H)
+    ctx.render_frame(cam, R.RESET)
+    ref = ctx.read_image().copy()
+    m = sc.meshes[0]
+    bad = m.triangles.copy()
+    bad["material"][0] = len(sc.materials) + 5
+    ctx.set_mesh(0, m.vertices, bad, m.indices)
+    with pytest.raises(R.Rfwb200Error, match="material"):
+        ctx.update()
+    ctx.set_mesh(0, m.vertices, m.triangles, m.indices)
+    ctx.update()
+    # the same textures with one more appended in FRONT of nothing: ids keep their meaning, the pool is rebuilt
+    ctx.set_textures(list(sc.textures) + [{"type": R.TEX_UINT, "width": 4, "height": 4, "data": S.build_mips(np.zeros((4, 4), np.uint32))}])
+    ctx.render_frame(cam, R.RESET)
+    assert np.array_equal(ctx.read_image(), ref)
