@@ -403,6 +403,7 @@ def run():
     if rank == 0:
         sampler.start()
         time.sleep(0.15)
+    fence()  # all ranks start the timed region together (rank 0 has just spent 150 ms starting the sampler)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_begin = time.perf_counter()
     e0.record(stream)

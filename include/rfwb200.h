@@ -329,6 +329,15 @@ RFWB200_API void *rfwb200_device_display(rfwb200_context *ctx);
  * a quarter of the read_framebuffer traffic for a consumer that only displays) */
 RFWB200_API int rfwb200_read_display(rfwb200_context *ctx, float contrast, float brightness, uint8_t *host_rgba8,
                                      size_t capacity_pixels);
+/* Feature planes for a denoiser (extension; the reference's OptiX backend fills them when built with ALLOW_DENOISER,
+ * OptiX6Context/assets/kernels/kernels.cu:122-133,206-221,316-330): with setting "aov" = on, every sample's depth-0 vertex adds
+ * its albedo (sky as seen / min(emission, 1) / material colour * |cos| of the sampled direction) and its shading normal,
+ * multiplied by the 3x3 matrix of rfwb200_set_aov_transform (column-major; the reference passes
+ * transpose(inverse(camera matrix)), OptiXContext.cpp:398; default identity = world space), to two per-pixel sums.
+ * rfwb200_read_aov copies sum / samples to the host: which = 0 albedo, 1 normal; float4 per local pixel, row-major for a
+ * single shard.  A sharded context returns its own tiles (tile-major), a device group is not assembled. */
+RFWB200_API int rfwb200_set_aov_transform(rfwb200_context *ctx, const float m[9]);
+RFWB200_API int rfwb200_read_aov(rfwb200_context *ctx, int which, float *host_rgba, size_t capacity_pixels);
 /* scatter `world` gathered tile-major shards (as produced by an all-gather of
  * rfwb200_device_framebuffer buffers, each padded to rfwb200_shard_stride pixels) into one
  * row-major image; all pointers are device pointers. */

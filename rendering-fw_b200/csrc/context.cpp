@@ -256,6 +256,9 @@ struct rfwb200_context
 	DevBuf d_O[2], d_D[2], d_T[2], d_hit, d_sO, d_sD, d_sE, d_sample_acc, d_acc, d_fb, d_counters, d_ext_seen, d_probe, d_frame,
 		d_scratch_cursor;
 	DevBuf d_sort_key, d_sort_hist, d_sort_base, d_sort_chunk, d_sort_grid;
+	DevBuf d_sample_albedo, d_sample_normal, d_albedo, d_normal, d_aov_out; // setting "aov": depth-0 feature planes
+	bool aov = false;
+	float to_eye[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
 	DevBuf d_display; // RGBA8 output of the tone-map pass (rfwb200_read_display), allocated on first use
 	WavefrontView wf{};
 	uint32_t counters_capacity = 0; // wavefronts per frame the counter rows are allocated for
@@ -406,6 +409,24 @@ int ensure_wavefront(Ctx *c, uint32_t bspp)
 		CK(c->d_sort_key.reserve(items * sizeof(uint2)));
 		c->items_capacity = items;
 	}
+	if (c->aov)
+	{
+		const size_t P = std::max<size_t>(c->shard.local_pixels, 32);
+		if (c->d_sample_albedo.bytes < items * sizeof(float4) || c->d_albedo.bytes < P * sizeof(float4))
+		{
+			CK(cudaStreamSynchronize(c->stream));
+			CK(c->d_sample_albedo.reserve(items * sizeof(float4)));
+			CK(c->d_sample_normal.reserve(items * sizeof(float4)));
+			const bool fresh = c->d_albedo.bytes < P * sizeof(float4);
+			CK(c->d_albedo.reserve(P * sizeof(float4)));
+			CK(c->d_normal.reserve(P * sizeof(float4)));
+			if (fresh)
+			{
+				CK(cudaMemsetAsync(c->d_albedo.ptr, 0, c->d_albedo.bytes, c->stream));
+				CK(cudaMemsetAsync(c->d_normal.ptr, 0, c->d_normal.bytes, c->stream));
+			}
+		}
+	}
 	const uint32_t bins = 1u << (3 * c->rs.sort_cell_bits + 3);
 	if (bins > c->sort_bins_allocated)
 	{
@@ -422,6 +443,8 @@ int ensure_wavefront(Ctx *c, uint32_t bspp)
 	w.hit = c->d_hit.as<float4>();
 	w.sO = c->d_sO.as<float4>(), w.sD = c->d_sD.as<float4>(), w.sE = c->d_sE.as<float4>();
 	w.sample_acc = c->d_sample_acc.as<float4>();
+	w.sample_albedo = c->aov ? c->d_sample_albedo.as<float4>() : nullptr, w.sample_normal = c->aov ? c->d_sample_normal.as<float4>() : nullptr;
+	w.albedo_acc = c->aov ? c->d_albedo.as<float4>() : nullptr, w.normal_acc = c->aov ? c->d_normal.as<float4>() : nullptr;
 	w.sort_key = c->d_sort_key.as<uint2>();
 	w.sort_hist = c->d_sort_hist.as<uint32_t>(), w.sort_base = c->d_sort_base.as<uint32_t>(), w.sort_chunk = c->d_sort_chunk.as<uint32_t>();
 	return RFWB200_OK;
@@ -789,6 +812,7 @@ int upload_frame_params(Ctx *c, const rfwb200_camera_view *view, uint32_t sample
 	}
 	fp.aperture = view->aperture, fp.spread_angle = view->spread_angle;
 	fp.sample_base = sample_base;
+	memcpy(fp.to_eye, c->to_eye, sizeof(fp.to_eye));
 	fp.probe_pixel = (c->probe_x < c->width && c->probe_y < c->height) ? c->probe_y * c->width + c->probe_x : 0xffffffffu;
 	CK(cudaMemcpyAsync(c->d_frame.ptr, &fp, sizeof(fp), cudaMemcpyHostToDevice, c->stream));
 	return RFWB200_OK;
@@ -1684,6 +1708,11 @@ extern "C"
 			REQUIRE(n >= 1 && n <= 32, "fetch_threshold must be in [1, 32]");
 			c->rs.fetch_threshold = n;
 		}
+		else if (k == "aov")
+		{
+			REQUIRE(v == "on" || v == "off" || v == "1" || v == "0", "aov must be on or off");
+			c->aov = (v == "on" || v == "1"); // takes effect with the next Reset frame
+		}
 		else if (k == "fetch_chunk")
 		{
 			const int n = atoi(v.c_str());
@@ -1759,7 +1788,7 @@ extern "C"
 							  std::to_string(c->rs.max_path_length) + "\nclamp=" + std::to_string(c->rs.clamp_value) +
 							  "\nsurvival_scale=on|off\nsmem_nodes=" + std::to_string(c->rs.smem_nodes) + "\nspp_batch=" +
 							  std::to_string(c->spp_batch) + "\nsort=on|off\nsort_cell_bits=" + std::to_string(c->rs.sort_cell_bits) +
-							  "\nsort_major=cell|octant\nfetch_chunk=" + std::to_string(c->rs.fetch_chunk) + "\nfetch_threshold=" + std::to_string(c->rs.fetch_threshold) +
+							  "\nsort_major=cell|octant\naov=on|off\nfetch_chunk=" + std::to_string(c->rs.fetch_chunk) + "\nfetch_threshold=" + std::to_string(c->rs.fetch_threshold) +
 							  "\ntrace_variant=" + std::to_string(c->rs.trace_variant) + "\nprimary_variant=" +
 							  std::to_string(c->rs.primary_variant) + "\nbvh=4|8\nbuilder=sbvh|lbvh\nspatial_splits=on|off\nrefit=device|host" +
 							  "\nshade_math=fast|ieee\ntiming=on|off\n";
@@ -1824,6 +1853,11 @@ extern "C"
 		if (status == RFWB200_RESET)
 		{
 			CK(cudaMemsetAsync(c->d_acc.ptr, 0, size_t(c->shard.local_pixels) * sizeof(float4), st));
+			if (c->aov && c->d_albedo.ptr)
+			{
+				CK(cudaMemsetAsync(c->d_albedo.ptr, 0, size_t(c->shard.local_pixels) * sizeof(float4), st));
+				CK(cudaMemsetAsync(c->d_normal.ptr, 0, size_t(c->shard.local_pixels) * sizeof(float4), st));
+			}
 			c->sample_index = 0;
 		}
 		CK(cudaMemsetAsync(c->d_counters.ptr, 0, size_t(batches) * MAX_DEPTH_SLOTS * sizeof(DepthCounters), st));
@@ -2017,6 +2051,30 @@ extern "C"
 			return r;
 		if (c->ev_copy_done)
 			CK(cudaEventSynchronize(c->ev_copy_done));
+		return RFWB200_OK;
+	}
+
+	int rfwb200_set_aov_transform(rfwb200_context *c, const float m[9])
+	{
+		REQUIRE(c && m, "bad arguments");
+		FORWARD(rfwb200_set_aov_transform(p_, m));
+		memcpy(c->to_eye, m, sizeof(c->to_eye));
+		return RFWB200_OK;
+	}
+
+	int rfwb200_read_aov(rfwb200_context *c, int which, float *host_rgba, size_t capacity_pixels)
+	{
+		REQUIRE(c && host_rgba && (which == 0 || which == 1), "bad arguments (which: 0 = albedo, 1 = normal)");
+		if (int r = ensure_device(c))
+			return r;
+		REQUIRE(c->aov && c->d_albedo.ptr && c->sample_index > 0, "no feature planes: set \"aov\" = on and render a Reset frame first");
+		const size_t n = c->shard.world == 1 ? size_t(c->width) * c->height : size_t(c->shard.local_pixels);
+		REQUIRE(capacity_pixels >= n, "host buffer too small");
+		CK(c->d_aov_out.reserve(std::max<size_t>(n, c->shard.local_pixels) * sizeof(float4)));
+		CK(launch_aov_finalize(c->shard, (which == 0 ? c->d_albedo : c->d_normal).as<float4>(), 1.0f / float(c->sample_index), c->d_aov_out.as<float4>(), c->stream));
+		c->launches += 1;
+		CK(cudaMemcpyAsync(host_rgba, c->d_aov_out.ptr, n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
 		return RFWB200_OK;
 	}
 

@@ -142,6 +142,7 @@ struct FrameParams
 	float aperture, spread_angle;
 	uint32_t sample_base; // sample index of the first sample of this frame
 	uint32_t probe_pixel; // global pixel id, 0xffffffff = none
+	float to_eye[9];	  // column-major mat3 applied to the normal AOV (OptiX6Context: transpose(inverse(camera matrix))); identity by default
 };
 
 struct LightCounts
@@ -199,6 +200,9 @@ struct WavefrontView
 	uint32_t *occ_cache;		// [2][local pixels]: occluder of the pixel's previous connect ray at this depth parity (shadow_cache = 2)
 	uint32_t *prim_cache;		// per local pixel: triangle record hit by the previous camera ray of that pixel (a bound only)
 	const FrameParams *frame;
+	// depth-0 feature planes for a denoiser (OptiX6Context/assets/kernels/kernels.cu:122-133,206-221,316-330), setting "aov":
+	// per work item like sample_acc, folded into per-pixel sums by k_fold; null when the setting is off
+	float4 *sample_albedo, *sample_normal, *albedo_acc, *normal_acc;
 	// re-ordering of the bounce queue (counting sort by origin cell + direction octant)
 	uint2 *sort_key;	 // per staging slot: (bin, rank inside the bin)
 	uint32_t *sort_hist; // per bin: rays emitted into it (zeroed again by k_sort_scan)

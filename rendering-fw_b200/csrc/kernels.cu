@@ -1916,6 +1916,7 @@ __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, c
 
 		bool do_acc = false, do_shadow = false, do_ext = false, dead = false;
 		V3 accv = mk(0.f);
+		V3 aov_albedo = mk(0.f), aov_normal = mk(0.f); // depth 0 only (setting "aov")
 		uint32_t pathIndex = 0, pixelIndex = 0, sampleInBatch = 0;
 		float4 eO, eD, eT, cO, cD, cE;
 		eO = eD = eT = cO = cD = cE = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1952,6 +1953,7 @@ __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, c
 					V3 contribution = throughput * (1.0f / bsdfPdf) * sky;
 					if (!any_nan(contribution))
 					{
+						aov_albedo = contribution; // OptiX6 kernels.cu:122-133: the sky as seen, no normal
 						clampIntensity(contribution, rs.clamp_value);
 						do_acc = true, accv = contribution;
 					}
@@ -2024,6 +2026,8 @@ __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, c
 						{
 							if (any_nan(contribution))
 								contribution = mk(0.f);
+							aov_albedo = mk(fminf(contribution.x, 1.0f), fminf(contribution.y, 1.0f), fminf(contribution.z, 1.0f)); // :206-221
+							aov_normal = iN;
 							clampIntensity(contribution, rs.clamp_value);
 							do_acc = true, accv = contribution;
 						}
@@ -2102,6 +2106,7 @@ __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, c
 							const float r4 = RandomFloat(seed);
 							BSDFSample(sd, T, B, iN, wo, R, newBsdfPdf, r3, r4);
 							const V3 bsdf = BSDFEval(sd, iN, wo, R, hitData.w, flip < 0);
+							aov_albedo = sd.color * fabsf(dot(iN, R)), aov_normal = iN; // :316-330
 							if (rs.survival_scale) // Kernels.cu:783
 								throughput = throughput * 1.0f / SurvivalProbability(throughput) * bsdf * fabsf(dot(iN, R));
 							else
@@ -2128,7 +2133,17 @@ __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, c
 		if (pathLength == 0)
 		{
 			if (job < n_paths && !dead)
+			{
 				wf.sample_acc[job] = make_float4(accv.x, accv.y, accv.z, 0.0f);
+				if (wf.sample_albedo != nullptr)
+				{
+					const float *m = fp.to_eye;
+					wf.sample_albedo[job] = make_float4(aov_albedo.x, aov_albedo.y, aov_albedo.z, 0.0f);
+					wf.sample_normal[job] = make_float4(m[0] * aov_normal.x + m[3] * aov_normal.y + m[6] * aov_normal.z,
+														m[1] * aov_normal.x + m[4] * aov_normal.y + m[7] * aov_normal.z,
+														m[2] * aov_normal.x + m[5] * aov_normal.y + m[8] * aov_normal.z, 0.0f);
+				}
+			}
 		}
 		else if (do_acc)
 		{
@@ -2217,6 +2232,16 @@ __global__ void k_fold(const ShardView sh, const WavefrontView wf, const BatchVi
 				a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
 			}
 			wf.accumulator[j] = a;
+			if (wf.sample_albedo != nullptr)
+			{
+				float4 al = wf.albedo_acc[j], no = wf.normal_acc[j];
+				for (uint32_t s = 0; s < bv.spp; s++)
+				{
+					const float4 b = wf.sample_albedo[((blk * bv.spp + s) << 5) | lane], c = wf.sample_normal[((blk * bv.spp + s) << 5) | lane];
+					al.x += b.x, al.y += b.y, al.z += b.z, no.x += c.x, no.y += c.y, no.z += c.z;
+				}
+				wf.albedo_acc[j] = al, wf.normal_acc[j] = no;
+			}
 		}
 		if (write_fb)
 		{
@@ -2451,6 +2476,25 @@ __global__ void k_assemble(const ShardView sh, const float4 *__restrict__ gather
 	uint32_t x, y;
 	if (local_to_pixel(s, j, x, y))
 		image[size_t(y) * s.width + x] = gathered[size_t(r) * stride + j];
+}
+
+// feature plane / samples, row-major for a single shard (tile-major otherwise, like the framebuffer)
+__global__ void k_aov_finalize(const ShardView sh, const float4 *__restrict__ acc, const float scale, float4 *__restrict__ out)
+{
+	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= sh.local_pixels)
+		return;
+	uint32_t x, y;
+	const bool live = local_to_pixel(sh, j, x, y);
+	float4 a = live ? acc[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+	a.x *= scale, a.y *= scale, a.z *= scale, a.w = 0.f;
+	if (sh.world == 1)
+	{
+		if (live)
+			out[size_t(y) * sh.width + x] = a;
+	}
+	else
+		out[j] = a;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2929,6 +2973,12 @@ cudaError_t launch_sort(const WavefrontView &wf, const RenderSettings &rs, const
 	if (e != cudaSuccess)
 		return e;
 	k_sort_move<<<dims.move_grid, 256, 0, stream>>>(wf, bv, depth, n_chunks);
+	return cudaGetLastError();
+}
+cudaError_t launch_aov_finalize(const ShardView &sh, const float4 *acc, float scale, float4 *out, cudaStream_t stream)
+{
+	if (sh.local_pixels)
+		k_aov_finalize<<<(sh.local_pixels + 255) / 256, 256, 0, stream>>>(sh, acc, scale, out);
 	return cudaGetLastError();
 }
 cudaError_t launch_tone_map(const float4 *framebuffer, uint32_t *rgba8_out, uint32_t n, float contrast, float brightness,

@@ -52,6 +52,8 @@ cudaError_t launch_shard_sync(const ShardSync &sync, uint32_t depth, uint32_t ne
 cudaError_t launch_sort_setup(const SceneView &sc, const WavefrontView &wf, const RenderSettings &rs, cudaStream_t stream);
 cudaError_t launch_sort(const WavefrontView &wf, const RenderSettings &rs, const BatchView &bv, uint32_t depth, const LaunchDims &dims,
 						cudaStream_t stream);
+// feature plane (albedo / normal sums of the depth-0 vertices) * scale -> out (row-major for a single shard)
+cudaError_t launch_aov_finalize(const ShardView &sh, const float4 *acc, float scale, float4 *out, cudaStream_t stream);
 // display pass (assets/shaders/tone-map.frag): ACES fit of the finalised framebuffer, packed to RGBA8
 cudaError_t launch_tone_map(const float4 *framebuffer, uint32_t *rgba8_out, uint32_t n, float contrast, float brightness,
 							cudaStream_t stream);

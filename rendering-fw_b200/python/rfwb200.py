@@ -338,6 +338,17 @@ class RenderContext:
     def read_wait(self):
         self._check(self.L.fn("read_wait", C.c_int, [C.c_void_p])(self._h))
 
+    def read_aov(self, which: int) -> np.ndarray:
+        """rfwb200_read_aov: 0 = albedo, 1 = normal (depth-0 feature planes, setting "aov")"""
+        n = self.width * self.height
+        out = np.empty((n, 4), np.float32)
+        self._check(self.L.fn("read_aov", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t])(self._h, which, out.ctypes.data, n))
+        return out.reshape(self.height, self.width, 4)
+
+    def set_aov_transform(self, m3: np.ndarray):
+        m = _f32(np.asarray(m3, np.float64).reshape(3, 3).T.reshape(-1))
+        self._check(self.L.fn("set_aov_transform", C.c_int, [C.c_void_p, C.c_void_p])(self._h, m.ctypes.data))
+
     def read_image(self) -> np.ndarray:
         return self.read_framebuffer().reshape(self.height, self.width, 4)
 

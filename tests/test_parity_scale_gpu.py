@@ -32,21 +32,24 @@ def wavefront_primary_hits(g, cam, W, H):
     bound cache, dynamic fetch) -> per-pixel arrays like trace_closest's"""
     g.set_setting("spp", 1)
     g.render_frame(cam, R.RESET)
-    rec = g.debug_read_plane(6, W * H).view(np.uint32)
+    pix = np.asarray(R.shard_pixel_map(W, H, 0, 1))  # work item (spp = 1: local pixel, tile-padded) -> y * W + x, -1 = padding
+    n = len(pix)
+    rec = np.ascontiguousarray(g.debug_read_plane(6, n)).view(np.uint32).reshape(n, 4)
     shade = g.debug_read_scene("shade")
-    pix = R.shard_pixel_map(W, H, 0, 1)  # work item (spp = 1: local pixel) -> y * W + x
     ok = pix >= 0
-    t = rec[:, 3].view(np.float32)
-    miss = rec[:, 2].view(np.int32) != 0
-    sid = np.minimum(rec[:, 1], len(shade) - 1)
+    t = np.ascontiguousarray(rec[:, 3]).view(np.float32)
+    miss = np.ascontiguousarray(rec[:, 2]).view(np.int32) != 0
+    sid = np.minimum(rec[:, 1], len(shade) - 1).astype(np.int64)
     w0 = (rec[:, 0] & 65535).astype(np.float32) / 65535.0
     w1 = (rec[:, 0] >> 16).astype(np.float32) / 65535.0
+    assert t.shape == miss.shape == sid.shape == ok.shape == (n,), (t.shape, miss.shape, sid.shape, ok.shape, n)
+    dst = pix[ok]
     hits = np.zeros(W * H, R.HIT_DTYPE)
-    hits["t"][pix[ok]] = np.where(miss, 1e34, t)[ok]
-    hits["inst_id"][pix[ok]] = np.where(miss, -1, shade["inst_id"][sid].astype(np.int64))[ok]
-    hits["prim_id"][pix[ok]] = np.where(miss, -1, shade["prim_id"][sid].astype(np.int64))[ok]
-    hits["u"][pix[ok]] = np.where(miss, 0, w1)[ok]            # Moller-Trumbore u = weight of vertex 1
-    hits["v"][pix[ok]] = np.where(miss, 0, 1.0 - w0 - w1)[ok]  # v = weight of vertex 2
+    hits["t"][dst] = np.where(miss, np.float32(1e34), t)[ok]
+    hits["inst_id"][dst] = np.where(miss, -1, shade["inst_id"][sid].astype(np.int64))[ok]
+    hits["prim_id"][dst] = np.where(miss, -1, shade["prim_id"][sid].astype(np.int64))[ok]
+    hits["u"][dst] = np.where(miss, 0, w1)[ok]            # Moller-Trumbore u = weight of vertex 1
+    hits["v"][dst] = np.where(miss, 0, 1.0 - w0 - w1)[ok]  # v = weight of vertex 2
     return hits
 
 
