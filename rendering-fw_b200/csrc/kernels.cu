@@ -1904,14 +1904,19 @@ __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, c
 	if (binning)
 		grid = *wf.grid;
 	uint32_t *seen = wf.ext_seen + size_t(bv.index * MAX_DEPTH_SLOTS + pathLength) * MAX_BATCH_SPP;
+	// work is pulled 32 paths at a time from a device cursor; the atomic for the NEXT chunk is issued before the current one is
+	// shaded, so its round trip to L2 (a tenth of the kernel's stall samples when it sat in front of the shading, profiles/r02)
+	// is hidden behind ~2,500 instructions of work
+	uint32_t next_base = 0;
+	if (lane == 0)
+		next_base = atomicAdd(&curc->shade_cursor, 32u);
 	for (;;)
 	{
-		uint32_t base = 0;
-		if (lane == 0)
-			base = atomicAdd(&curc->shade_cursor, 32u);
-		base = __shfl_sync(0xffffffffu, base, 0);
+		const uint32_t base = __shfl_sync(0xffffffffu, next_base, 0);
 		if (base >= n_paths)
 			break;
+		if (lane == 0)
+			next_base = atomicAdd(&curc->shade_cursor, 32u);
 		const uint32_t job = base + lane;
 
 		bool do_acc = false, do_shadow = false, do_ext = false, dead = false;

@@ -103,6 +103,29 @@ def add_material(scene: Scene, color, roughness=1.0, metallic=0.0, specular=0.0,
     return len(scene.materials) - 1
 
 
+def material_rule(emissive, diffuse, transparent, opacity, shininess, shininess_strength, eta, reflectivity) -> dict:
+    """What rfw::material_list::add(aiMaterial*) makes of the values assimp hands over (RFW/system/src/rfw/material_list.cpp:54-78;
+    for an OBJ/MTL: Ke, Kd, Tf, d, Ns, -, Ni, -): emissive colour wins over diffuse, roughness = 1 - sqrt(min(Ns, 1024) / 1024),
+    specular only from a shininess strength inside (0, 1), eta only when > 1, transmission = 1 - opacity when opacity != 0.
+    Untouched fields keep the HostMaterial defaults (material_list.h:50-62).  Pinned on the reference's own lines by
+    tests/test_ref_pin_ingest.py."""
+    f = np.float32
+    emissive, diffuse, transparent = (np.asarray(x, f) for x in (emissive, diffuse, transparent))
+    m = {"metallic": f(0), "subsurface": f(0), "specular": f(0.5), "roughness": f(0.5), "eta": f(1), "transmission": f(0)}
+    m["color"] = np.maximum(emissive if np.any(emissive != 0) else diffuse, f(0))
+    m["absorption"] = np.maximum(transparent, f(0))
+    m["metallic"] = max(f(reflectivity), f(0))
+    if reflectivity > 0:
+        m["metallic"] = f(reflectivity)
+    m["specular"] = f(shininess_strength) if 0 < shininess_strength < 1 else f(0)
+    m["roughness"] = max(f(0), f(1) - np.sqrt(min(f(shininess), f(1024)) / f(1024))) if shininess > 0 else f(1)
+    if eta > 1:
+        m["eta"] = f(eta)
+    if opacity != 0:
+        m["transmission"] = f(1) - max(f(opacity), f(0))
+    return m
+
+
 def build_mips(rgba8: np.ndarray) -> np.ndarray:
     """rgba8: (h, w) uint32 packed r|g<<8|b<<16|a<<24 -> 5 concatenated levels (texture.cpp:163-225)."""
     levels = [rgba8.astype(np.uint32)]

@@ -161,6 +161,7 @@ inline bool any(const bvec3 &b) { return b.x || b.y || b.z; }
 inline bool any(const bvec4 &b) { return b.x || b.y || b.z || b.w; }
 inline bvec3 greaterThan(const vec3 &a, const vec3 &b) { return {a.x > b.x, a.y > b.y, a.z > b.z}; }
 inline bvec3 lessThan(const vec3 &a, const vec3 &b) { return {a.x < b.x, a.y < b.y, a.z < b.z}; }
+inline bvec3 notEqual(const vec3 &a, const vec3 &b) { return {a.x != b.x, a.y != b.y, a.z != b.z}; }
 inline bvec4 lessThan(const vec4 &a, const vec4 &b) { return {a.x < b.x, a.y < b.y, a.z < b.z, a.w < b.w}; }
 inline bvec4 greaterThanEqual(const vec4 &a, const vec4 &b) { return {a.x >= b.x, a.y >= b.y, a.z >= b.z, a.w >= b.w}; }
 inline uint floatBitsToUint(float f)

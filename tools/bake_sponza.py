@@ -110,16 +110,13 @@ def main():
                 tex_index[f] = S.add_texture_rgba8(scene, rgba)
                 tex_alpha[f] = aflag
             tex0, has_alpha = tex_index[f], tex_alpha[f]
-        ke = m["Ke"]
-        color = ke if any(c != 0 for c in ke) else m["Kd"]
+        # what assimp's OBJ importer hands to the reference's material rule: Ke, Kd, Tf (absent: 0), d (absent: 0 = "not set"),
+        # Ns, no shininess strength, Ni, no reflectivity
+        r = S.material_rule(m["Ke"], m["Kd"], (0.0, 0.0, 0.0), m["d"] if m["d"] is not None else 0.0, m["Ns"], 0.0, m["Ni"], 0.0)
+        color = tuple(float(c) for c in r["color"])
         if tex0 >= 0 and all(c == 0 for c in color):
-            color = (1.0, 1.0, 1.0)
-        ns = m["Ns"]
-        rough = max(0.0, 1.0 - (min(ns, 1024.0) / 1024.0) ** 0.5) if ns > 0 else 1.0
-        transmission = 0.0
-        if m["d"] is not None and m["d"] != 0.0:
-            transmission = 1.0 - max(m["d"], 0.0)
-        eta = m["Ni"] if m["Ni"] > 1.0 else 1.0  # HostMaterial::eta default, material_list.h:62
+            color = (1.0, 1.0, 1.0)  # material_list.cpp:84-86: a black diffuse colour under a diffuse map becomes white
+        rough, transmission, eta = float(r["roughness"]), float(r["transmission"]), float(r["eta"])
         mat_index[name] = S.add_material(scene, color, roughness=rough, transmission=transmission, eta=eta, tex0=tex0,
                                          smooth=True, has_alpha=has_alpha)
     light_mat = S.add_material(scene, (100, 100, 100), roughness=1.0)
