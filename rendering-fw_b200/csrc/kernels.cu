@@ -1904,19 +1904,16 @@ __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, c
 	if (binning)
 		grid = *wf.grid;
 	uint32_t *seen = wf.ext_seen + size_t(bv.index * MAX_DEPTH_SLOTS + pathLength) * MAX_BATCH_SPP;
-	// work is pulled 32 paths at a time from a device cursor; the atomic for the NEXT chunk is issued before the current one is
-	// shaded, so its round trip to L2 (a tenth of the kernel's stall samples when it sat in front of the shading, profiles/r02)
-	// is hidden behind ~2,500 instructions of work
-	uint32_t next_base = 0;
-	if (lane == 0)
-		next_base = atomicAdd(&curc->shade_cursor, 32u);
 	for (;;)
 	{
-		const uint32_t base = __shfl_sync(0xffffffffu, next_base, 0);
+		// (issuing the atomic for the NEXT chunk before shading the current one was measured: one more live register, 430
+		// instead of 274 bytes of spills, shade 3.13 instead of 3.00 ms per frame — profiles/r02/sweep6)
+		uint32_t base = 0;
+		if (lane == 0)
+			base = atomicAdd(&curc->shade_cursor, 32u);
+		base = __shfl_sync(0xffffffffu, base, 0);
 		if (base >= n_paths)
 			break;
-		if (lane == 0)
-			next_base = atomicAdd(&curc->shade_cursor, 32u);
 		const uint32_t job = base + lane;
 
 		bool do_acc = false, do_shadow = false, do_ext = false, dead = false;
@@ -2142,6 +2139,11 @@ __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, c
 				wf.sample_acc[job] = make_float4(accv.x, accv.y, accv.z, 0.0f);
 				if (wf.sample_albedo != nullptr)
 				{
+					// a BSDF sample can be NaN (the path is then dropped, Kernels.cu:785); a feature plane must stay finite
+					if (any_nan(aov_albedo))
+						aov_albedo = mk(0.f);
+					if (any_nan(aov_normal))
+						aov_normal = mk(0.f);
 					const float *m = fp.to_eye;
 					wf.sample_albedo[job] = make_float4(aov_albedo.x, aov_albedo.y, aov_albedo.z, 0.0f);
 					wf.sample_normal[job] = make_float4(m[0] * aov_normal.x + m[3] * aov_normal.y + m[6] * aov_normal.z,
