@@ -70,10 +70,21 @@ def check_hits(o, origins, dirs, hg, ho, max_frac=2e-3):
     assert (duv > 1e-3).sum() <= max(2, 5e-5 * len(duv)) and duv.max() < 2e-2, info
     diff = np.nonzero(~same)[0]
     assert len(diff) <= max(4, max_frac * len(origins)), f"{len(diff)} of {len(origins)} rays disagree"
-    for i in diff[:4000]:  # every disagreement must be a tie (shared edge, coplanar duplicate)
+    cracks = 0
+    for i in diff[:4000]:
         if hg["prim_id"][i] >= 0 and ho["prim_id"][i] >= 0:
+            # every disagreement must be a tie (shared edge, coplanar duplicate): the GPU's triangle, intersected by the oracle,
+            # is as close as the oracle's own hit ...
             t_alt = o.intersect_prim(origins[i, :3], dirs[i, :3], int(hg["inst_id"][i]), int(hg["prim_id"][i]))
-            assert abs(t_alt - ho["t"][i]) <= 2e-4 * max(1.0, ho["t"][i]) or t_alt > 1e33, (i, t_alt, ho["t"][i])
+            tie = abs(t_alt - ho["t"][i]) <= 2e-4 * max(1.0, ho["t"][i]) or t_alt > 1e33
+            # ... or an edge crack: Moller-Trumbore is not watertight, so a ray through the shared edge of two triangles can miss
+            # both in one arithmetic (fp32 world space here, object space in the oracle and the reference) and hit in the other;
+            # then the nearer of the two hits lies within 2e-4 (barycentric) of an edge of its triangle
+            near = ho[i] if ho["t"][i] <= hg["t"][i] else hg[i]
+            on_edge = min(near["u"], near["v"], 1.0 - near["u"] - near["v"]) < 2e-4
+            cracks += 0 if tie else 1
+            assert tie or on_edge, (i, t_alt, ho[i], hg[i])
+    assert cracks <= max(2, 1e-5 * len(origins)), f"{cracks} rays fell through an edge"
     return len(diff)
 
 
