@@ -435,6 +435,14 @@ RFWB200_API int rfwb200_host_lbvh_check(const float *tris9, size_t n_tris, int p
 										const float *dirs3, size_t n_rays, float *t_out, int32_t *tri_out, uint64_t *nodes_out,
 										uint64_t *refs_out, int32_t *depth_out, uint32_t *visits_out);
 
+/* The same for the top level of two-level scenes (setting "levels" = 2 | auto; the reference's top level:
+ * RFW/system/bvh/src/top_level_bvh.cpp:17-102): builds the 4-wide tree over n_boxes boxes (float[6]: lo, hi), checks that every
+ * box is named by exactly one leaf slot and that every slot box contains its subtree (structure_errors_out), and, for every
+ * ray, that the boxes reached through the tree are the boxes a loop over all of them finds (ray_mismatches_out). */
+RFWB200_API int rfwb200_host_tlas_check(const float *boxes6, size_t n_boxes, const float *origins3, const float *dirs3,
+										size_t n_rays, uint64_t *nodes_out, int32_t *depth_out, uint64_t *structure_errors_out,
+										uint64_t *ray_mismatches_out, uint64_t *boxes_hit_out);
+
 #ifdef __cplusplus
 } /* extern "C" */
 

@@ -1036,4 +1036,159 @@ void refit_cwbvh(const BuildTriangle *tris, size_t count, BvhBuildResult &bvh, c
 	}
 }
 
+// ---- top level of a two-level scene ---------------------------------------------------------------------------------------
+// A 4-wide tree over item boxes (instances) whose leaf slots name ONE item each (leaf word ~(item << 2)): binned SAH on the
+// box centres, two binary splits per node.  The reference builds its top level the same way over instance boxes
+// (RFW/system/bvh/src/top_level_bvh.cpp:17-102), with one instance per leaf as well.
+namespace
+{
+struct TlasBuild
+{
+	const float *boxes;
+	std::vector<BvhNode4> *nodes;
+	int depth = 0;
+
+	Box item_box(uint32_t i) const
+	{
+		Box b;
+		for (int a = 0; a < 3; a++)
+			b.lo[a] = boxes[6 * i + a], b.hi[a] = boxes[6 * i + 3 + a];
+		return b;
+	}
+	// splits items[lo, hi) in two non-empty halves, returns the split position
+	size_t split(std::vector<uint32_t> &items, size_t lo, size_t hi) const
+	{
+		const size_t n = hi - lo;
+		Box cb;
+		cb.reset();
+		for (size_t i = lo; i < hi; i++)
+		{
+			const Box b = item_box(items[i]);
+			const float c[3] = {0.5f * (b.lo[0] + b.hi[0]), 0.5f * (b.lo[1] + b.hi[1]), 0.5f * (b.lo[2] + b.hi[2])};
+			cb.grow(c);
+		}
+		constexpr int BINS = 16;
+		float best = 3.0e38f;
+		int best_axis = -1, best_bin = 0;
+		for (int a = 0; a < 3; a++)
+		{
+			const float ext = cb.hi[a] - cb.lo[a];
+			if (!(ext > 0.0f))
+				continue;
+			Box bb[BINS];
+			size_t bc[BINS] = {};
+			for (int k = 0; k < BINS; k++)
+				bb[k].reset();
+			const float sc = float(BINS) / ext;
+			for (size_t i = lo; i < hi; i++)
+			{
+				const Box b = item_box(items[i]);
+				const int k = std::min(BINS - 1, std::max(0, int((0.5f * (b.lo[a] + b.hi[a]) - cb.lo[a]) * sc)));
+				bb[k].grow(b), bc[k]++;
+			}
+			float right_area[BINS];
+			Box acc;
+			acc.reset();
+			size_t cnt = 0;
+			for (int k = BINS - 1; k > 0; k--)
+				acc.grow(bb[k]), right_area[k] = acc.area();
+			acc.reset();
+			size_t right = n;
+			for (int k = 0; k < BINS - 1; k++)
+			{
+				acc.grow(bb[k]), cnt += bc[k], right = n - cnt;
+				if (cnt == 0 || right == 0)
+					continue;
+				const float cost = acc.area() * float(cnt) + right_area[k + 1] * float(right);
+				if (cost < best)
+					best = cost, best_axis = a, best_bin = k;
+			}
+		}
+		if (best_axis < 0) // all centres coincide: split the run in the middle
+			return lo + n / 2;
+		const int a = best_axis;
+		const float sc = float(BINS) / (cb.hi[a] - cb.lo[a]);
+		const auto mid = std::partition(items.begin() + lo, items.begin() + hi, [&](uint32_t it) {
+			const Box b = item_box(it);
+			return std::min(BINS - 1, std::max(0, int((0.5f * (b.lo[a] + b.hi[a]) - cb.lo[a]) * sc))) <= best_bin;
+		});
+		const size_t m = size_t(mid - items.begin());
+		return (m == lo || m == hi) ? lo + n / 2 : m;
+	}
+	uint32_t build(std::vector<uint32_t> &items, size_t lo, size_t hi, int level)
+	{
+		depth = std::max(depth, level);
+		const uint32_t me = uint32_t(nodes->size());
+		nodes->emplace_back();
+		// up to four groups: split once, then the larger-area halves again
+		size_t cut[5] = {lo, hi, hi, hi, hi};
+		int groups = 1;
+		while (groups < 4)
+		{
+			int pick = -1;
+			float pick_area = -1.0f;
+			for (int g = 0; g < groups; g++)
+			{
+				if (cut[g + 1] - cut[g] < 2)
+					continue;
+				Box b;
+				b.reset();
+				for (size_t i = cut[g]; i < cut[g + 1]; i++)
+					b.grow(item_box(items[i]));
+				if (b.area() > pick_area)
+					pick_area = b.area(), pick = g;
+			}
+			if (pick < 0)
+				break;
+			const size_t m = split(items, cut[pick], cut[pick + 1]);
+			for (int g = groups; g > pick; g--)
+				cut[g + 1] = cut[g];
+			cut[pick + 1] = m;
+			groups++;
+		}
+		BvhNode4 n;
+		memset(&n, 0, sizeof(n));
+		for (int s = 0; s < 4; s++)
+			set_child_empty(n, s);
+		for (int g = 0; g < groups; g++)
+		{
+			Box b;
+			b.reset();
+			for (size_t i = cut[g]; i < cut[g + 1]; i++)
+				b.grow(item_box(items[i]));
+			n.minx[g] = b.lo[0], n.miny[g] = b.lo[1], n.minz[g] = b.lo[2];
+			n.maxx[g] = b.hi[0], n.maxy[g] = b.hi[1], n.maxz[g] = b.hi[2];
+			if (cut[g + 1] - cut[g] == 1)
+				n.child[g] = ~int32_t(items[cut[g]] << 2);
+			else
+				n.child[g] = int32_t(build(items, cut[g], cut[g + 1], level + 1));
+		}
+		n.pad[0] = groups;
+		(*nodes)[me] = n;
+		return me;
+	}
+};
+} // namespace
+
+int build_tlas4(const float *boxes, size_t count, std::vector<BvhNode4> &nodes)
+{
+	nodes.clear();
+	TlasBuild b;
+	b.boxes = boxes, b.nodes = &nodes;
+	if (count == 0)
+	{
+		BvhNode4 root;
+		memset(&root, 0, sizeof(root));
+		for (int s = 0; s < 4; s++)
+			set_child_empty(root, s);
+		nodes.push_back(root);
+		return 1;
+	}
+	std::vector<uint32_t> items(count);
+	for (size_t i = 0; i < count; i++)
+		items[i] = uint32_t(i);
+	b.build(items, 0, count, 1);
+	return b.depth;
+}
+
 } // namespace rfwb200

@@ -52,6 +52,10 @@ void refit_bvh4(const BuildTriangle *tris, size_t count, BvhBuildResult &bvh, co
 void build_cwbvh(const BuildTriangle *tris, size_t count, int threads, BvhBuildResult &out, bool spatial_splits = true);
 void refit_cwbvh(const BuildTriangle *tris, size_t count, BvhBuildResult &bvh, const uint8_t *tri_moved = nullptr);
 
+// Top level of a two-level scene: a 4-wide tree over `count` boxes (6 floats each: lo, hi) whose leaf slots name one box each
+// (child word ~(index << 2)); nodes[0] is the root.  Returns the depth of the tree.
+int build_tlas4(const float *boxes, size_t count, std::vector<BvhNode4> &nodes);
+
 constexpr int TRAVERSAL_STACK = 96; // ints per thread in the kernels; builder keeps 3*depth+1 below this
 
 } // namespace rfwb200

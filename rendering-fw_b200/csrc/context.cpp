@@ -247,6 +247,14 @@ struct rfwb200_context
 	int device_depth = 0;
 	DevBuf d_lbvh_scratch;
 	DevBuf d_cw_nodes, d_nodes16, d_prim_cache, d_occ_cache;
+	// ---- two-level scene (TlInstance, device_types.h): setting "levels" = 1 (flatten, default) | 2 | auto ----
+	int levels_setting = 1;				   // 0 = auto: two levels when the flattened scene would exceed flatten_budget triangles
+	uint64_t flatten_budget = 1ull << 26;  // setting "flatten_budget" (flattened triangles; 2^26 of them are ~15 GB of records and nodes)
+	bool two_level = false;				   // the committed device scene is two-level
+	std::vector<BvhBuildResult> blas;	   // one object-space tree per mesh (kept across updates: only changed meshes are rebuilt)
+	std::vector<uint8_t> blas_valid;
+	DevBuf d_tl_instances;
+	int tl_depth = 0; // top-level depth + deepest mesh tree
 
 	// ---- wavefront state -----------------------------------------------------------------------------
 	// One wavefront carries up to `batch_spp` samples of every local pixel (BatchView); the planes hold local_pixels *
@@ -1285,12 +1293,29 @@ extern "C"
 		return ensure_device(c);
 	}
 
+	static int update_two_level(rfwb200_context *c);
+
 	static int update_one(rfwb200_context *c)
 	{
 		if (int r = ensure_device(c))
 			return r;
 		if (!c->geometry_dirty && c->scene.nodes)
 			return RFWB200_OK;
+		{
+			uint64_t flattened = 0;
+			for (const HostInstance &in : c->instances)
+				if (in.mesh >= 0 && size_t(in.mesh) < c->meshes.size())
+					flattened += c->meshes[in.mesh].triangles.size();
+			if (c->levels_setting == 2 || (c->levels_setting == 0 && flattened > c->flatten_budget))
+				return update_two_level(c);
+			if (c->two_level) // back to the flattened form: nothing of the two-level scene is reused
+			{
+				c->two_level = false, c->scene.tl_instances = nullptr, c->scene.tl_instance_count = 0;
+				c->bvh = BvhBuildResult();
+				c->arena_valid = false, c->topology_dirty = true, c->device_built = false;
+				c->built_layout.clear();
+			}
+		}
 		// topology unchanged since the last build => refit (bvh_tree.cpp:104-114)
 		std::vector<std::pair<int, size_t>> layout;
 		size_t total = 0;
@@ -1466,6 +1491,221 @@ extern "C"
 				return r;
 		c->geometry_dirty = false, c->topology_dirty = false;
 		c->dims_valid = false; // node count may have changed the staged prefix
+		return RFWB200_OK;
+	}
+
+	// Two-level commit (setting "levels"): one object-space tree per mesh (host SBVH, rebuilt only for meshes that changed), a
+	// top-level tree over the instances' world boxes, per-mesh intersection and shading records, and the instance table
+	// with the inverse transforms.  Memory is that of the unique meshes plus 96 B + a share of a node per instance —
+	// what the reference keeps (CUDART/src/Context.cpp:270-311,394-456), and the fallback for scenes whose flattened
+	// form would not fit.  A moved instance costs a top-level rebuild on the host (microseconds per thousand instances).
+	static int update_two_level(rfwb200_context *c)
+	{
+		REQUIRE(!c->wide8, "bvh=8 is a flattened layout: use levels=1");
+		for (const auto &sk : c->skins)
+			REQUIRE(!sk, "device skinning / morph targets write the flattened scene's arena: use levels=1 for animated meshes");
+		CK(cudaStreamSynchronize(c->stream));
+		const size_t nm = c->meshes.size();
+		c->mesh_dirty.resize(nm, 1);
+		c->blas.resize(nm);
+		c->blas_valid.resize(nm, 0);
+		for (size_t mi = 0; mi < nm; mi++)
+			if (c->mesh_dirty[mi] || !c->blas_valid[mi])
+				for (const rfwb200_triangle &t : c->meshes[mi].triangles)
+					if (t.material >= c->materials_raw.size())
+						return set_error(RFWB200_ERR_INVALID, "mesh " + std::to_string(mi) + " references material " + std::to_string(t.material) +
+																  " but only " + std::to_string(c->materials_raw.size()) + " materials were set");
+		const auto t0 = std::chrono::steady_clock::now();
+		const int threads = int(std::max(1u, std::thread::hardware_concurrency()));
+		std::vector<BuildTriangle> bt;
+		for (size_t mi = 0; mi < nm; mi++)
+		{
+			if (!c->mesh_dirty[mi] && c->blas_valid[mi])
+				continue;
+			const HostMesh &m = c->meshes[mi];
+			const size_t nt = m.triangles.size(), nv = m.vertices.size() / 4;
+			bt.resize(nt);
+			for (size_t t = 0; t < nt; t++)
+				for (int k = 0; k < 3; k++)
+				{
+					const uint32_t vi = m.indices.empty() ? uint32_t(t * 3 + k) : m.indices[t * 3 + k];
+					if (vi >= nv)
+						return set_error(RFWB200_ERR_INVALID, "mesh index out of range");
+					float *dst = k == 0 ? bt[t].v0 : (k == 1 ? bt[t].v1 : bt[t].v2);
+					dst[0] = m.vertices[4 * vi], dst[1] = m.vertices[4 * vi + 1], dst[2] = m.vertices[4 * vi + 2];
+				}
+			build_bvh4(bt.data(), nt, threads, c->blas[mi], c->spatial_splits);
+			c->blas_valid[mi] = 1, c->mesh_dirty[mi] = 0;
+			c->builds++;
+		}
+		// ---- layout: [top-level nodes][mesh 0 nodes][mesh 1 nodes]... ; records and shading records per mesh, back to back
+		std::vector<uint32_t> valid_ids;
+		std::vector<float> boxes;
+		std::vector<float> mesh_box(nm * 6);
+		std::vector<uint8_t> mesh_empty(nm, 1);
+		int deepest = 0;
+		for (size_t mi = 0; mi < nm; mi++)
+		{
+			float *b = &mesh_box[6 * mi];
+			for (int a = 0; a < 3; a++)
+				b[a] = 3.0e38f, b[3 + a] = -3.0e38f;
+			if (c->meshes[mi].triangles.empty() || c->blas[mi].nodes.empty())
+				continue;
+			const BvhNode4 &root = c->blas[mi].nodes[0];
+			for (int s = 0; s < root.pad[0]; s++)
+			{
+				b[0] = std::min(b[0], root.minx[s]), b[1] = std::min(b[1], root.miny[s]), b[2] = std::min(b[2], root.minz[s]);
+				b[3] = std::max(b[3], root.maxx[s]), b[4] = std::max(b[4], root.maxy[s]), b[5] = std::max(b[5], root.maxz[s]);
+			}
+			mesh_empty[mi] = b[0] <= b[3] ? 0 : 1;
+			deepest = std::max(deepest, c->blas[mi].depth);
+		}
+		for (size_t ii = 0; ii < c->instances.size(); ii++)
+		{
+			const HostInstance &in = c->instances[ii];
+			if (in.mesh < 0 || size_t(in.mesh) >= nm || mesh_empty[in.mesh])
+				continue;
+			const float *b = &mesh_box[6 * size_t(in.mesh)];
+			float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+			for (int corner = 0; corner < 8; corner++)
+			{
+				const float p[3] = {b[(corner & 1) ? 3 : 0], b[(corner & 2) ? 4 : 1], b[(corner & 4) ? 5 : 2]};
+				float w[3];
+				mul_point(in.transform, p, w);
+				for (int a = 0; a < 3; a++)
+					lo[a] = std::min(lo[a], w[a]), hi[a] = std::max(hi[a], w[a]);
+			}
+			// one float step of slack per coordinate: the object-space walk rounds differently from a world-space box test
+			for (int a = 0; a < 3; a++)
+			{
+				const float pad = 4e-7f * std::max(std::fabs(lo[a]), std::fabs(hi[a])) + 1e-30f;
+				boxes.push_back(lo[a] - pad);
+			}
+			for (int a = 0; a < 3; a++)
+			{
+				const float pad = 4e-7f * std::max(std::fabs(lo[a]), std::fabs(hi[a])) + 1e-30f;
+				boxes.push_back(hi[a] + pad);
+			}
+			valid_ids.push_back(uint32_t(ii));
+		}
+		std::vector<BvhNode4> nodes;
+		const int top_depth = build_tlas4(boxes.data(), valid_ids.size(), nodes);
+		for (BvhNode4 &n : nodes)
+			for (int s = 0; s < n.pad[0]; s++)
+				if (n.child[s] < 0)
+					n.child[s] = ~int32_t(valid_ids[uint32_t(~n.child[s]) >> 2] << 2);
+		const size_t top_nodes = nodes.size();
+		std::vector<uint32_t> node_base(nm, 0), ref_base(nm, 0), tri_base(nm, 0);
+		size_t nn = top_nodes, nr = 0, ntri = 0;
+		for (size_t mi = 0; mi < nm; mi++)
+		{
+			node_base[mi] = uint32_t(nn), ref_base[mi] = uint32_t(nr), tri_base[mi] = uint32_t(ntri);
+			nn += c->blas[mi].nodes.size(), nr += c->blas[mi].tri_order.size(), ntri += c->meshes[mi].triangles.size();
+		}
+		REQUIRE(nn < (1ull << 30) && nr < (1ull << 29) && ntri < (1ull << 31), "two-level scene exceeds the 32-bit node / reference encoding");
+		REQUIRE(c->instances.size() < (1ull << 29), "too many instances");
+		if (3 * (top_depth + deepest) + 3 > TRAVERSAL_STACK)
+			return set_error(RFWB200_ERR_INVALID, "two-level scene deeper than the traversal stack allows");
+		nodes.resize(nn);
+		std::vector<TriRec> recs(std::max<size_t>(nr, 1));
+		std::vector<ShadeTri> shade(std::max<size_t>(ntri, 1));
+		memset(recs.data(), 0, recs.size() * sizeof(TriRec));
+		memset(shade.data(), 0, shade.size() * sizeof(ShadeTri));
+		for (size_t mi = 0; mi < nm; mi++)
+		{
+			const BvhBuildResult &b = c->blas[mi];
+			const HostMesh &m = c->meshes[mi];
+			for (size_t k = 0; k < b.nodes.size(); k++)
+			{
+				BvhNode4 n = b.nodes[k];
+				for (int s = 0; s < n.pad[0]; s++)
+				{
+					if (n.child[s] >= 0)
+						n.child[s] += int32_t(node_base[mi]);
+					else
+					{
+						const uint32_t v = uint32_t(~n.child[s]);
+						n.child[s] = ~int32_t((((v >> 2) + ref_base[mi]) << 2) | (v & 3u));
+					}
+				}
+				nodes[node_base[mi] + k] = n;
+			}
+			for (size_t i = 0; i < b.tri_order.size(); i++)
+			{
+				const uint32_t t = b.tri_order[i];
+				uint32_t vi[3];
+				for (int k = 0; k < 3; k++)
+					vi[k] = m.indices.empty() ? uint32_t(t * 3 + k) : m.indices[t * 3 + k];
+				const float *v0 = &m.vertices[4 * vi[0]], *v1 = &m.vertices[4 * vi[1]], *v2 = &m.vertices[4 * vi[2]];
+				TriRec &r = recs[ref_base[mi] + i];
+				r.p0x = v0[0], r.p0y = v0[1], r.p0z = v0[2];
+				r.e1x = v1[0] - v0[0], r.e1y = v1[1] - v0[1], r.e1z = v1[2] - v0[2];
+				r.e2x = v2[0] - v0[0], r.e2y = v2[1] - v0[1], r.e2z = v2[2] - v0[2];
+				r.shade_idx = tri_base[mi] + t;
+				r.det_eps = 1e-6f; // T_EPSILON, tested in object space like the reference (CUDAIntersect.h:61-63)
+			}
+			for (size_t t = 0; t < m.triangles.size(); t++)
+			{
+				const rfwb200_triangle &src = m.triangles[t];
+				ShadeTri &st = shade[tri_base[mi] + t];
+				st.u0 = src.u0, st.u1 = src.u1, st.u2 = src.u2, st.light_tri_idx = src.light_tri_idx;
+				st.v0 = src.v0, st.v1 = src.v1, st.v2 = src.v2, st.material = src.material;
+				st.n0x = src.vN0[0], st.n0y = src.vN0[1], st.n0z = src.vN0[2];
+				st.n1x = src.vN1[0], st.n1y = src.vN1[1], st.n1z = src.vN1[2];
+				st.n2x = src.vN2[0], st.n2y = src.vN2[1], st.n2z = src.vN2[2];
+				st.Nx = src.Nx, st.Ny = src.Ny, st.Nz = src.Nz; // the instance's normal matrix is applied when the hit is shaded
+				st.area = src.area, st.lod = src.LOD;
+				st.inst_id = 0, st.prim_id = uint32_t(t);
+			}
+		}
+		std::vector<TlInstance> table(std::max<size_t>(c->instances.size(), 1));
+		memset(table.data(), 0, table.size() * sizeof(TlInstance));
+		for (uint32_t ii : valid_ids)
+		{
+			const HostInstance &in = c->instances[ii];
+			TlInstance &ti = table[ii];
+			// inverse of the affine transform (column-major M), in double, rounded once
+			const float *M = in.transform;
+			const double a = M[0], b = M[4], cc = M[8], d = M[1], e = M[5], f = M[9], g = M[2], h = M[6], k = M[10];
+			const double det = a * (e * k - f * h) - b * (d * k - f * g) + cc * (d * h - e * g);
+			REQUIRE(det != 0.0, "instance " + std::to_string(ii) + " has a singular transform");
+			const double id = 1.0 / det;
+			const double r[3][3] = {{(e * k - f * h) * id, (cc * h - b * k) * id, (b * f - cc * e) * id},
+									{(f * g - d * k) * id, (a * k - cc * g) * id, (cc * d - a * f) * id},
+									{(d * h - e * g) * id, (b * g - a * h) * id, (a * e - b * d) * id}};
+			const double tx = M[12], ty = M[13], tz = M[14];
+			for (int row = 0; row < 3; row++)
+			{
+				ti.inv[4 * row + 0] = float(r[row][0]), ti.inv[4 * row + 1] = float(r[row][1]), ti.inv[4 * row + 2] = float(r[row][2]);
+				ti.inv[4 * row + 3] = float(-(r[row][0] * tx + r[row][1] * ty + r[row][2] * tz));
+			}
+			memcpy(ti.normal, in.normal, sizeof(ti.normal));
+			ti.blas_root = node_base[in.mesh];
+		}
+		CK(c->d_nodes.reserve(nodes.size() * sizeof(BvhNode4)));
+		CK(c->d_tris.reserve(recs.size() * sizeof(TriRec)));
+		CK(c->d_shade_tris.reserve(shade.size() * sizeof(ShadeTri)));
+		CK(c->d_tl_instances.reserve(table.size() * sizeof(TlInstance)));
+		CK(cudaMemcpyAsync(c->d_nodes.ptr, nodes.data(), nodes.size() * sizeof(BvhNode4), cudaMemcpyHostToDevice, c->stream));
+		CK(cudaMemcpyAsync(c->d_tris.ptr, recs.data(), recs.size() * sizeof(TriRec), cudaMemcpyHostToDevice, c->stream));
+		CK(cudaMemcpyAsync(c->d_shade_tris.ptr, shade.data(), shade.size() * sizeof(ShadeTri), cudaMemcpyHostToDevice, c->stream));
+		CK(cudaMemcpyAsync(c->d_tl_instances.ptr, table.data(), table.size() * sizeof(TlInstance), cudaMemcpyHostToDevice, c->stream));
+		CK(cudaStreamSynchronize(c->stream)); // the staging vectors die here
+		c->scene.nodes = c->d_nodes.as<BvhNode4>(), c->scene.tris = c->d_tris.as<TriRec>(), c->scene.shade_tris = c->d_shade_tris.as<ShadeTri>();
+		c->scene.node_count = uint32_t(nn), c->scene.tri_count = uint32_t(nr);
+		c->scene.nodes16 = nullptr, c->scene.cw_nodes = nullptr, c->scene.cw_node_count = 0;
+		c->scene.tl_instances = c->d_tl_instances.as<TlInstance>(), c->scene.tl_instance_count = uint32_t(c->instances.size());
+		c->flat_tri_count = ntri;
+		c->two_level = true, c->tl_depth = top_depth + deepest;
+		c->bvh = BvhBuildResult();
+		c->bvh.depth = c->tl_depth;
+		c->bvh.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+		c->device_built = true; // get_bvh_info reads the counts from the device scene
+		c->arena_valid = false, c->built_layout.clear(), c->built_tri_count = 0;
+		c->inst_moved.assign(c->instances.size(), 0);
+		c->last_update_on_device = false, c->last_update_was_refit = false, c->geo_timed = false;
+		c->geometry_dirty = false, c->topology_dirty = false;
+		c->dims_valid = false;
 		return RFWB200_OK;
 	}
 
@@ -1773,6 +2013,21 @@ extern "C"
 			REQUIRE(v == "fast" || v == "ieee", "shade_math must be 'fast' or 'ieee'");
 			c->shade_ieee = (v == "ieee");
 		}
+		else if (k == "levels")
+		{
+			REQUIRE(v == "1" || v == "2" || v == "auto", "levels must be 1 (instances flattened into one tree), 2 (top level over per-mesh trees) or auto");
+			const int n = v == "auto" ? 0 : atoi(v.c_str());
+			if (n != c->levels_setting)
+				c->levels_setting = n, c->geometry_dirty = c->topology_dirty = true;
+		}
+		else if (k == "flatten_budget")
+		{
+			const long long n = atoll(v.c_str());
+			REQUIRE(n >= 0, "flatten_budget is a number of flattened triangles");
+			c->flatten_budget = uint64_t(n);
+			if (c->levels_setting == 0)
+				c->geometry_dirty = c->topology_dirty = true;
+		}
 		else if (k == "threads")
 		{
 		}
@@ -1791,7 +2046,7 @@ extern "C"
 							  "\nsort_major=cell|octant\naov=on|off\nfetch_chunk=" + std::to_string(c->rs.fetch_chunk) + "\nfetch_threshold=" + std::to_string(c->rs.fetch_threshold) +
 							  "\ntrace_variant=" + std::to_string(c->rs.trace_variant) + "\nprimary_variant=" +
 							  std::to_string(c->rs.primary_variant) + "\nbvh=4|8\nbuilder=sbvh|lbvh\nspatial_splits=on|off\nrefit=device|host" +
-							  "\nshade_math=fast|ieee\ntiming=on|off\n";
+							  "\nshade_math=fast|ieee\ntiming=on|off\nlevels=1|2|auto\nflatten_budget=" + std::to_string(c->flatten_budget) + "\nlevels_in_use=" + (c->two_level ? "2" : "1") + "\n";
 		snprintf(buf, buf_size, "%s", s.c_str());
 		return RFWB200_OK;
 	}
@@ -1863,6 +2118,10 @@ extern "C"
 		CK(cudaMemsetAsync(c->d_counters.ptr, 0, size_t(batches) * MAX_DEPTH_SLOTS * sizeof(DepthCounters), st));
 		CK(cudaMemsetAsync(c->d_ext_seen.ptr, 0, size_t(batches) * MAX_DEPTH_SLOTS * MAX_BATCH_SPP * sizeof(uint32_t), st));
 		const bool to_display = c->mode_pt && c->display.image != nullptr;
+		// the hit caches remember positions in the flattened record array; a two-level scene has none
+		RenderSettings rs_frame = c->rs;
+		if (c->two_level)
+			rs_frame.primary_cache = 0, rs_frame.shadow_cache = 0;
 		if (c->sample_index == 0)
 		{
 			const ProbeResult none{0, 0, 0.f, 0};
@@ -1880,7 +2139,7 @@ extern "C"
 			const bool shard_sync = to_display && c->shard.world > 1;
 			if (sort)
 			{
-				CK(launch_sort_setup(c->scene, c->wf, c->rs, st)); // grid of the bins from the root of the current tree
+				CK(launch_sort_setup(c->scene, c->wf, rs_frame, st)); // grid of the bins from the root of the current tree
 				c->launches += 1;
 			}
 			for (uint32_t b = 0; b < batches; b++)
@@ -1912,11 +2171,11 @@ extern "C"
 				};
 				{
 					StageTimer t(c, 0);
-					CK(launch_primary(c->scene, c->shard, c->wf, c->rs, bv, c->dims, st));
+					CK(launch_primary(c->scene, c->shard, c->wf, rs_frame, bv, c->dims, st));
 				}
 				{
 					StageTimer t(c, 3);
-					CK(shade(c->scene, c->shard, c->wf, c->rs, bv, 0, 0, 1, sync, c->dims, st));
+					CK(shade(c->scene, c->shard, c->wf, rs_frame, bv, 0, 0, 1, sync, c->dims, st));
 				}
 				c->launches += 2;
 				if (int r = merge_flags(0))
@@ -1929,16 +2188,16 @@ extern "C"
 					if (sort)
 					{
 						StageTimer t(c, 5);
-						CK(launch_sort(c->wf, c->rs, bv, d, c->dims, st));
+						CK(launch_sort(c->wf, rs_frame, bv, d, c->dims, st));
 						c->launches += 2;
 					}
 					{
 						StageTimer t(c, d == 1 ? 1 : 2);
-						CK(launch_trace(c->scene, c->shard, c->wf, c->rs, bv, d, in, c->dims, st));
+						CK(launch_trace(c->scene, c->shard, c->wf, rs_frame, bv, d, in, c->dims, st));
 					}
 					{
 						StageTimer t(c, 3);
-						CK(shade(c->scene, c->shard, c->wf, c->rs, bv, d, in, out, sync, c->dims, st));
+						CK(shade(c->scene, c->shard, c->wf, rs_frame, bv, d, in, out, sync, c->dims, st));
 					}
 					c->launches += 2;
 					if (int r = merge_flags(d))
@@ -1980,7 +2239,7 @@ extern "C"
 		{
 			// EmbreeRT renders one un-accumulated sample per call (Context.cpp:104-300)
 			StageTimer t(c, 0);
-			CK(launch_emode(c->scene, c->shard, c->wf, c->rs, c->d_materials_raw.ptr, c->d_tex_desc.as<uint32_t>(),
+			CK(launch_emode(c->scene, c->shard, c->wf, rs_frame, c->d_materials_raw.ptr, c->d_tex_desc.as<uint32_t>(),
 							uint32_t(c->textures.size()), c->dims, st));
 			c->launches += 1;
 			c->sample_index += 1;
@@ -2486,19 +2745,24 @@ extern "C"
 		if (n == 0)
 			return RFWB200_OK;
 		CK(c->d_scratch_cursor.reserve(256));
-		DevBuf dO, dD, dH;
+		DevBuf dO, dD, dH, dI;
 		CK(dO.reserve(n * 16));
 		CK(dD.reserve(n * 16));
 		CK(dH.reserve(n * 16));
+		if (c->two_level)
+			CK(dI.reserve(n * 4));
 		cudaStream_t st = c->stream;
 		CK(cudaMemcpyAsync(dO.ptr, origins, n * 16, cudaMemcpyHostToDevice, st));
 		CK(cudaMemcpyAsync(dD.ptr, directions, n * 16, cudaMemcpyHostToDevice, st));
 		CK(cudaMemsetAsync(c->d_scratch_cursor.ptr, 0, 4, st));
 		CK(launch_trace_closest(c->scene, c->rs, dO.as<float4>(), dD.as<float4>(), uint32_t(n), t_min, dH.as<float4>(),
-								c->d_scratch_cursor.as<uint32_t>(), c->dims, st));
+								c->d_scratch_cursor.as<uint32_t>(), c->dims, st, c->two_level ? dI.as<uint32_t>() : nullptr));
 		c->launches += 1;
 		std::vector<float> raw(n * 4);
+		std::vector<uint32_t> hit_inst(c->two_level ? n : 0);
 		CK(cudaMemcpyAsync(raw.data(), dH.ptr, n * 16, cudaMemcpyDeviceToHost, st));
+		if (c->two_level)
+			CK(cudaMemcpyAsync(hit_inst.data(), dI.ptr, n * 4, cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
 		// translate shading-record indices back to (instance, primitive)
 		std::vector<ShadeTri> shade(c->flat_tri_count);
@@ -2512,7 +2776,7 @@ extern "C"
 			if (tri == 0xffffffffu || tri >= shade.size())
 				hits_out[i].inst_id = -1, hits_out[i].prim_id = -1, hits_out[i].u = 0, hits_out[i].v = 0;
 			else
-				hits_out[i].inst_id = int32_t(shade[tri].inst_id), hits_out[i].prim_id = int32_t(shade[tri].prim_id);
+				hits_out[i].inst_id = int32_t(c->two_level ? hit_inst[i] : shade[tri].inst_id), hits_out[i].prim_id = int32_t(shade[tri].prim_id);
 		}
 		return RFWB200_OK;
 	}
@@ -2742,6 +3006,113 @@ extern "C"
 		if (sah_out)
 			*sah_out = bvh.sah_cost;
 		return walk_bvh4_host(bvh, bt, origins3, dirs3, n_rays, t_out, tri_out, visits_out);
+	}
+
+	// Self check of the top-level builder of two-level scenes without a GPU: every box is named by exactly one leaf slot, every
+	// node's slot boxes contain what is below them, and for every ray the set of boxes reached through the tree equals the
+	// set a loop over all boxes finds with the same slab test.
+	int rfwb200_host_tlas_check(const float *boxes6, size_t n_boxes, const float *origins3, const float *dirs3, size_t n_rays,
+								uint64_t *nodes_out, int32_t *depth_out, uint64_t *structure_errors_out, uint64_t *ray_mismatches_out,
+								uint64_t *boxes_hit_out)
+	{
+		REQUIRE((boxes6 || n_boxes == 0) && (n_rays == 0 || (origins3 && dirs3)) && structure_errors_out && ray_mismatches_out, "bad arguments");
+		std::vector<BvhNode4> nodes;
+		const int depth = build_tlas4(boxes6, n_boxes, nodes);
+		if (nodes_out)
+			*nodes_out = nodes.size();
+		if (depth_out)
+			*depth_out = depth;
+		uint64_t bad = 0;
+		std::vector<uint32_t> named(n_boxes, 0);
+		std::vector<uint8_t> visited(nodes.size(), 0);
+		// bounds of a subtree, checked against the slot box that covers it
+		std::function<void(uint32_t, float *)> bound = [&](uint32_t ni, float *out6) {
+			for (int a = 0; a < 3; a++)
+				out6[a] = 3.0e38f, out6[3 + a] = -3.0e38f;
+			if (ni >= nodes.size() || visited[ni]++)
+			{
+				bad++;
+				return;
+			}
+			const BvhNode4 &n = nodes[ni];
+			if (n.pad[0] < (n_boxes ? 1 : 0) || n.pad[0] > 4)
+				bad++;
+			for (int s = 0; s < n.pad[0] && s < 4; s++)
+			{
+				float sub[6];
+				if (n.child[s] >= 0)
+					bound(uint32_t(n.child[s]), sub);
+				else
+				{
+					const uint32_t item = uint32_t(~n.child[s]) >> 2;
+					if (item >= n_boxes || (uint32_t(~n.child[s]) & 3u) != 0u)
+					{
+						bad++;
+						continue;
+					}
+					named[item]++;
+					memcpy(sub, boxes6 + 6 * item, sizeof(sub));
+				}
+				const float slot[6] = {n.minx[s], n.miny[s], n.minz[s], n.maxx[s], n.maxy[s], n.maxz[s]};
+				for (int a = 0; a < 3; a++)
+				{
+					if (!(slot[a] <= sub[a]) || !(slot[3 + a] >= sub[3 + a]))
+						bad++;
+					out6[a] = std::min(out6[a], slot[a]), out6[3 + a] = std::max(out6[3 + a], slot[3 + a]);
+				}
+			}
+		};
+		float all[6];
+		bound(0, all);
+		for (size_t i = 0; i < n_boxes; i++)
+			if (named[i] != 1)
+				bad++;
+		*structure_errors_out = bad;
+		auto slab_hit = [](const float *lo, const float *hi, const float *o, const float *id) {
+			float tn = 0.0f, tf = 3.0e38f;
+			for (int a = 0; a < 3; a++)
+			{
+				const float t1 = (lo[a] - o[a]) * id[a], t2 = (hi[a] - o[a]) * id[a];
+				tn = std::max(tn, std::min(t1, t2)), tf = std::min(tf, std::max(t1, t2));
+			}
+			return tn <= tf;
+		};
+		uint64_t mismatches = 0, total_hit = 0;
+		std::vector<uint32_t> via_tree, direct, stack;
+		for (size_t r = 0; r < n_rays; r++)
+		{
+			const float *o = origins3 + 3 * r, *d = dirs3 + 3 * r;
+			float id[3];
+			for (int a = 0; a < 3; a++)
+				id[a] = 1.0f / (std::fabs(d[a]) > 1e-30f ? d[a] : std::copysign(1e-30f, d[a]));
+			via_tree.clear(), direct.clear(), stack.assign(1, 0u);
+			while (!stack.empty())
+			{
+				const BvhNode4 &n = nodes[stack.back()];
+				stack.pop_back();
+				for (int s = 0; s < n.pad[0] && s < 4; s++)
+				{
+					const float lo[3] = {n.minx[s], n.miny[s], n.minz[s]}, hi[3] = {n.maxx[s], n.maxy[s], n.maxz[s]};
+					if (!slab_hit(lo, hi, o, id))
+						continue;
+					if (n.child[s] >= 0)
+						stack.push_back(uint32_t(n.child[s]));
+					else if (slab_hit(boxes6 + 6 * (uint32_t(~n.child[s]) >> 2), boxes6 + 6 * (uint32_t(~n.child[s]) >> 2) + 3, o, id))
+						via_tree.push_back(uint32_t(~n.child[s]) >> 2);
+				}
+			}
+			for (size_t i = 0; i < n_boxes; i++)
+				if (slab_hit(boxes6 + 6 * i, boxes6 + 6 * i + 3, o, id))
+					direct.push_back(uint32_t(i));
+			std::sort(via_tree.begin(), via_tree.end());
+			if (via_tree != direct)
+				mismatches++;
+			total_hit += direct.size();
+		}
+		*ray_mismatches_out = mismatches;
+		if (boxes_hit_out)
+			*boxes_hit_out = total_hit;
+		return RFWB200_OK;
 	}
 
 	struct SerialAlloc // what atomicAdd on the level counter does, for one "thread" at a time

@@ -145,6 +145,20 @@ struct FrameParams
 	float to_eye[9];	  // column-major mat3 applied to the normal AOV (OptiX6Context: transpose(inverse(camera matrix))); identity by default
 };
 
+// Two-level scene (setting "levels" = 2, or "auto" when the flattened triangle count exceeds "flatten_budget"): instances
+// stay instances — a top-level tree over their world boxes whose leaves name ONE instance each, and one object-space tree
+// per mesh, all in SceneView::nodes (top-level nodes first).  The reference traverses exactly this shape
+// (CUDART/src/Kernels.cu:226-303: ray moved into object space with the instance's inverse transform, un-normalised, so
+// distances stay world distances) and applies the normal matrix at shading time (getShadingData.h:129-130).
+struct alignas(16) TlInstance
+{
+	float inv[12];		// object = inv * world: rows (m00 m01 m02 m03), (m10 ...), (m20 ...)
+	float normal[9];	// column-major normal matrix
+	uint32_t blas_root; // node index of the mesh's tree
+	uint32_t pad[2];
+};
+static_assert(sizeof(TlInstance) == 96, "");
+
 struct LightCounts
 {
 	uint32_t area, point, spot, directional;
@@ -171,6 +185,10 @@ struct SceneView
 	const void *area_lights, *point_lights, *spot_lights, *dir_lights;
 	LightCounts lights;
 	const uint8_t *blue_noise; // 327,680 table bytes at the offsets of createBlueNoiseBuffer (blue_noise.h:8204-8219)
+	// two-level scene (null = flattened, the default): `tris` / `shade_tris` are then per MESH triangle in object space and a
+	// hit carries the instance it was found in
+	const TlInstance *tl_instances;
+	uint32_t tl_instance_count;
 };
 
 struct ShardView

@@ -399,10 +399,153 @@ __device__ bool traverse_cw(const SceneView &sc, V3 o, V3 d, float tmin, float &
 	return found;
 }
 
+// One ray through a two-level scene (TlInstance, device_types.h): the top-level tree in world space; a top-level leaf names one
+// instance, whose inverse transform moves the ray into object space (direction NOT re-normalised: t stays the world distance,
+// Kernels.cu:229-232,270-272) for the walk of that mesh's tree; a marker on the stack brings the world ray back when the
+// instance's subtree is exhausted.  One stack serves both levels.
+template <bool ANY_HIT>
+__device__ __noinline__ bool traverse_tl(const SceneView &sc, const V3 wo, const V3 wd, const float tmin, float &tmax, uint32_t &hit_tri,
+										 float &hit_u, float &hit_v, uint32_t &hit_inst)
+{
+	constexpr int RETURN_TO_WORLD = 0x7ffffffe;
+	constexpr uint32_t NO_INSTANCE = 0xffffffffu;
+	const float tiny = 1e-30f;
+	V3 o = wo, d = wd;
+	float idx, idy, idz, oodx, oody, oodz;
+#define RFW_RAY_SETUP()                                                                                                 \
+	idx = 1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));                                                      \
+	idy = 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));                                                      \
+	idz = 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));                                                      \
+	oodx = o.x * idx, oody = o.y * idy, oodz = o.z * idz;
+	RFW_RAY_SETUP()
+	int stack[TRAVERSAL_STACK];
+	int sp = 0;
+	int cur = 0;
+	uint32_t inst = NO_INSTANCE; // the instance whose tree is being walked
+	bool found = false;
+	const float4 *__restrict__ tris = reinterpret_cast<const float4 *>(sc.tris);
+	if (sc.node_count == 0)
+		return false;
+	for (;;)
+	{
+		if (cur == RETURN_TO_WORLD)
+		{
+			o = wo, d = wd, inst = NO_INSTANCE;
+			RFW_RAY_SETUP()
+			if (sp == 0)
+				break;
+			cur = stack[--sp];
+		}
+		else if (cur >= 0)
+		{
+			const NodeRegs n = load_node(sc, nullptr, 0u, uint32_t(cur));
+			uint32_t key0, key1, key2, key3;
+			CHILD_T(0, x)
+			CHILD_T(1, y)
+			CHILD_T(2, z)
+			CHILD_T(3, w)
+			if (NO_CHILD_HIT(key0, key1, key2, key3))
+			{
+				if (sp == 0)
+					break;
+				cur = stack[--sp];
+				continue;
+			}
+			CSWAP(key0, key1)
+			CSWAP(key2, key3)
+			CSWAP(key0, key2)
+			CSWAP(key1, key3)
+			CSWAP(key1, key2)
+			cur = PICK(key0);
+			if (key1 < 0x7f000000u) // sorted: misses are last
+			{
+				if (key3 < 0x7f000000u)
+					stack[sp++] = PICK(key3);
+				if (key2 < 0x7f000000u)
+					stack[sp++] = PICK(key2);
+				stack[sp++] = PICK(key1);
+			}
+		}
+		else if (inst == NO_INSTANCE)
+		{
+			// top-level leaf: enter the instance
+			inst = uint32_t(~cur) >> 2;
+			const float4 *ip = reinterpret_cast<const float4 *>(sc.tl_instances + inst);
+			const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2);
+			o = mk(r0.x * wo.x + r0.y * wo.y + r0.z * wo.z + r0.w, r1.x * wo.x + r1.y * wo.y + r1.z * wo.z + r1.w,
+				   r2.x * wo.x + r2.y * wo.y + r2.z * wo.z + r2.w);
+			d = mk(r0.x * wd.x + r0.y * wd.y + r0.z * wd.z, r1.x * wd.x + r1.y * wd.y + r1.z * wd.z, r2.x * wd.x + r2.y * wd.y + r2.z * wd.z);
+			RFW_RAY_SETUP()
+			stack[sp++] = RETURN_TO_WORLD;
+			cur = int(__ldg(&sc.tl_instances[inst].blas_root));
+		}
+		else
+		{
+			const uint32_t v = uint32_t(~cur), first = v >> 2, cnt = (v & 3u) + 1u;
+			for (uint32_t i = 0; i < cnt; i++)
+			{
+				const float4 a = __ldg(tris + size_t(first + i) * 3 + 0);
+				const float4 b = __ldg(tris + size_t(first + i) * 3 + 1);
+				const float4 c = __ldg(tris + size_t(first + i) * 3 + 2);
+				const V3 p0 = mk(a.x, a.y, a.z), e1 = mk(a.w, b.x, b.y), e2 = mk(b.z, b.w, c.x);
+				const V3 h = cross(d, e2);
+				const float det = dot(e1, h);
+				const float eps = c.z;
+				if (det > -eps && det < eps)
+					continue;
+				const float f = 1.0f / det;
+				const V3 s = o - p0;
+				const float u = f * dot(s, h);
+				if (u < 0.0f || u > 1.0f)
+					continue;
+				const V3 q = cross(s, e1);
+				const float vv = f * dot(d, q);
+				if (vv < 0.0f || u + vv > 1.0f)
+					continue;
+				const float t = f * dot(e2, q);
+				if (t > tmin && tmax > t)
+				{
+					if (ANY_HIT)
+						return true;
+					tmax = t, hit_u = u, hit_v = vv, hit_tri = __float_as_uint(c.y), hit_inst = inst;
+					found = true;
+				}
+			}
+			cur = stack[--sp]; // at least the marker is below
+		}
+	}
+#undef RFW_RAY_SETUP
+	return found;
+}
+
+// the normals of a mesh's shading record taken to world space with the instance's normal matrix, in the arithmetic of the
+// flattening pass (context.cpp flatten_scene / geometry.cu k_flatten_shade), so both scene forms shade alike
+__device__ __forceinline__ void apply_instance_normals(const SceneView &sc, uint32_t inst, ShadeTri &tri)
+{
+	const float *m = sc.tl_instances[inst].normal;
+	const float m0 = __ldg(m), m1 = __ldg(m + 1), m2 = __ldg(m + 2), m3 = __ldg(m + 3), m4 = __ldg(m + 4), m5 = __ldg(m + 5), m6 = __ldg(m + 6),
+				m7 = __ldg(m + 7), m8 = __ldg(m + 8);
+#define RFW_NMUL(X, Y, Z)                                                                                               \
+	{                                                                                                                   \
+		const float x_ = m0 * X + m3 * Y + m6 * Z, y_ = m1 * X + m4 * Y + m7 * Z, z_ = m2 * X + m5 * Y + m8 * Z;           \
+		X = x_, Y = y_, Z = z_;                                                                                         \
+	}
+	RFW_NMUL(tri.n0x, tri.n0y, tri.n0z)
+	RFW_NMUL(tri.n1x, tri.n1y, tri.n1z)
+	RFW_NMUL(tri.n2x, tri.n2y, tri.n2z)
+	RFW_NMUL(tri.Nx, tri.Ny, tri.Nz)
+#undef RFW_NMUL
+	const float il = 1.0f / sqrtf(tri.Nx * tri.Nx + tri.Ny * tri.Ny + tri.Nz * tri.Nz);
+	tri.Nx *= il, tri.Ny *= il, tri.Nz *= il;
+	tri.inst_id = inst;
+}
+
 template <bool ANY_HIT>
 __device__ __forceinline__ bool traverse(const SceneView &sc, const float4 *__restrict__ snodes, uint32_t n_smem, V3 o,
-										 V3 d, float tmin, float &tmax, uint32_t &hit_tri, float &hit_u, float &hit_v)
+										 V3 d, float tmin, float &tmax, uint32_t &hit_tri, float &hit_u, float &hit_v, uint32_t &hit_inst)
 {
+	if (sc.tl_instances != nullptr)
+		return traverse_tl<ANY_HIT>(sc, o, d, tmin, tmax, hit_tri, hit_u, hit_v, hit_inst);
 	if (sc.cw_nodes != nullptr)
 		return traverse_cw<ANY_HIT>(sc, o, d, tmin, tmax, hit_tri, hit_u, hit_v);
 	const float tiny = 1e-30f;
@@ -485,6 +628,13 @@ __device__ __forceinline__ bool traverse(const SceneView &sc, const float4 *__re
 		}
 	}
 	return found;
+}
+template <bool ANY_HIT>
+__device__ __forceinline__ bool traverse(const SceneView &sc, const float4 *__restrict__ snodes, uint32_t n_smem, V3 o,
+										 V3 d, float tmin, float &tmax, uint32_t &hit_tri, float &hit_u, float &hit_v)
+{
+	uint32_t inst = 0;
+	return traverse<ANY_HIT>(sc, snodes, n_smem, o, d, tmin, tmax, hit_tri, hit_u, hit_v, inst);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -687,14 +837,15 @@ __device__ __forceinline__ bool fetch_ray(const SceneView &sc, const ShardView &
 // end of a ray: hit record of a closest-hit ray, or accumulator[path] += (contribution, 1) of an unoccluded connect ray
 // (Kernels.cu:457-459, 495-497).  Every path of a wavefront owns its accumulator slot (one per pixel and sample), so the
 // read-modify-write needs no atomic, exactly like the reference's one-sample-per-launch `+=`.
+// (hit.z of a hit: 0 in a flattened scene, the instance index in a two-level scene — any value >= 0 means "hit")
 __device__ __forceinline__ void retire_ray(const WavefrontView &wf, const TraceQueue &q, uint32_t item, bool shadow, uint32_t hit_tri,
-										   float hit_u, float hit_v, float tmax, uint32_t pidx, uint32_t &acc_count)
+										   float hit_u, float hit_v, float tmax, uint32_t pidx, uint32_t &acc_count, uint32_t hit_inst = 0u)
 {
 	if (!shadow)
 	{
 		float4 hit = make_float4(0.f, 0.f, __int_as_float(PRIM_MISS), 0.f);
 		if (hit_tri != 0xffffffffu)
-			hit = make_float4(__uint_as_float(pack_barycentrics(hit_u, hit_v)), __uint_as_float(hit_tri), __int_as_float(0), tmax);
+			hit = make_float4(__uint_as_float(pack_barycentrics(hit_u, hit_v)), __uint_as_float(hit_tri), __int_as_float(int(hit_inst)), tmax);
 		wf.hit[item] = hit;
 	}
 	else if (hit_tri == 0xffffffffu)
@@ -1061,6 +1212,54 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 		}
 	}
 	close_launch(rs, curc, PRIMARY, dbg, dbg_t0, dbg_rays, acc_count, n_traced);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_wavefront_trace_tl — the trace stages over a two-level scene (TlInstance): the fallback for scenes that are not
+// flattened.  Persistent CTAs, 32 queue entries per warp and fetch, one ray per lane walked by traverse_tl; the same
+// queue semantics, hit records and accumulator updates as k_wavefront_trace.
+// ------------------------------------------------------------------------------------------------
+template <bool PRIMARY>
+__global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace_tl(const SceneView sc, const ShardView sh, const WavefrontView wf,
+															   const RenderSettings rs, const BatchView bv, const uint32_t depth,
+															   const uint32_t in_buf)
+{
+	DepthCounters *curc = &wf.counters[bv.index * MAX_DEPTH_SLOTS + depth];
+	const TraceQueue q = open_queue<PRIMARY>(sh, wf, bv, depth, in_buf);
+	const uint32_t total = q.total;
+	uint32_t *cursor = &curc->trace_cursor;
+	const uint32_t lane = threadIdx.x & 31u;
+	FrameParams fp;
+	if (PRIMARY)
+		fp = *wf.frame;
+	uint32_t acc_count = 0, n_traced = 0;
+	for (;;)
+	{
+		uint32_t base = 0;
+		if (lane == 0)
+			base = atomicAdd(cursor, 32u);
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (base >= total)
+			break;
+		const uint32_t item = base + lane;
+		if (item >= total)
+			continue;
+		V3 o = mk(0.f), d = mk(0.f);
+		float tmin = 0.f, tmax = 0.f, hit_u = 0.f, hit_v = 0.f;
+		bool shadow = false;
+		uint32_t pidx = 0, occluder = 0xffffffffu, occ_slot = 0, hit_tri = 0xffffffffu, hit_inst = 0;
+		if (!fetch_ray<PRIMARY>(sc, sh, wf, rs, bv, fp, q, depth, in_buf, item, o, d, tmin, tmax, shadow, pidx, occluder, occ_slot, n_traced))
+			continue;
+		if (shadow)
+		{
+			if (traverse_tl<true>(sc, o, d, tmin, tmax, hit_tri, hit_u, hit_v, hit_inst))
+				hit_tri = 0u; // occluded: anything but "no hit"
+		}
+		else
+			traverse_tl<false>(sc, o, d, tmin, tmax, hit_tri, hit_u, hit_v, hit_inst);
+		retire_ray(wf, q, item, shadow, hit_tri, hit_u, hit_v, tmax, pidx, acc_count, hit_inst);
+	}
+	close_launch(rs, curc, PRIMARY, false, 0ull, 0ull, acc_count, n_traced);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1974,6 +2173,8 @@ __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, c
 						for (int k = 0; k < 6; k++)
 							dst[k] = __ldg(tp + k);
 					}
+					if (sc.tl_instances != nullptr) // two-level scene: the record is the mesh's, hit.z names the instance
+						apply_instance_normals(sc, uint32_t(primIdx), tri);
 					const float bu = float(ub & 65535u) * (1.0f / 65535.0f), bv = float((ub >> 16) & 65535u) * (1.0f / 65535.0f);
 					V3 N, iN, T, B;
 					const ShadingData sd = getShadingData(sc, D, bu, bv, fp.spread_angle * hitData.w, tri, N, iN, T, B);
@@ -2550,7 +2751,7 @@ __global__ void k_tone_map(const float4 *__restrict__ fb, uint32_t *__restrict__
 // ------------------------------------------------------------------------------------------------
 // k_emode — EmbreeRT/src/Context.cpp:104-300 + retrieve_material :417-476, one thread per pixel
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_emode(const SceneView sc, const ShardView sh, const WavefrontView wf,
+__global__ void __launch_bounds__(256, 3) k_emode(const SceneView sc, const ShardView sh, const WavefrontView wf,
 											  const RenderSettings rs, const rfwb200_material *__restrict__ raw_materials,
 											  const uint32_t *__restrict__ tex_desc, const uint32_t tex_count)
 {
@@ -2582,8 +2783,8 @@ __global__ void __launch_bounds__(256) k_emode(const SceneView sc, const ShardVi
 			V3 O, D;
 			generate_emode(fp, sh, x, y, fp.sample_base, O, D);
 			float t = 1e34f, u = 0.f, v = 0.f;
-			uint32_t triIdx = 0;
-			if (!traverse<false>(sc, snodes, n_smem, O, D, 1e-5f, t, triIdx, u, v))
+			uint32_t triIdx = 0, hitInst = 0;
+			if (!traverse<false>(sc, snodes, n_smem, O, D, 1e-5f, t, triIdx, u, v, hitInst))
 			{
 				const float su = 0.5f * (1.0f + atan2f(D.x, -D.z) * INVPI);
 				const float sv = acosf(D.y) * INVPI;
@@ -2605,6 +2806,8 @@ __global__ void __launch_bounds__(256) k_emode(const SceneView sc, const ShardVi
 					for (int k = 0; k < 6; k++)
 						dst[k] = __ldg(tp + k);
 				}
+				if (sc.tl_instances != nullptr)
+					apply_instance_normals(sc, hitInst, tri);
 				if (y * sh.width + x == fp.probe_pixel)
 					wf.probe->inst = int(tri.inst_id), wf.probe->prim = int(tri.prim_id), wf.probe->dist = t;
 				const float b0 = 1.0f - u - v;
@@ -2707,7 +2910,7 @@ __global__ void __launch_bounds__(256) k_emode(const SceneView sc, const ShardVi
 __global__ void __launch_bounds__(256) k_trace_closest(const SceneView sc, const RenderSettings rs,
 													  const float4 *__restrict__ origins, const float4 *__restrict__ dirs,
 													  const uint32_t n, const float t_min, float4 *__restrict__ hits,
-													  uint32_t *cursor)
+													  uint32_t *cursor, uint32_t *__restrict__ inst_out)
 {
 	__shared__ uint64_t mbar;
 	float4 *snodes = reinterpret_cast<float4 *>(g_dyn_smem);
@@ -2727,9 +2930,11 @@ __global__ void __launch_bounds__(256) k_trace_closest(const SceneView sc, const
 			continue;
 		const float4 O4 = origins[i], D4 = dirs[i];
 		float t = 1e34f, u = 0.f, v = 0.f;
-		uint32_t tri = 0xffffffffu;
-		const bool h = traverse<false>(sc, snodes, n_smem, mk(O4.x, O4.y, O4.z), mk(D4.x, D4.y, D4.z), t_min, t, tri, u, v);
+		uint32_t tri = 0xffffffffu, inst = 0;
+		const bool h = traverse<false>(sc, snodes, n_smem, mk(O4.x, O4.y, O4.z), mk(D4.x, D4.y, D4.z), t_min, t, tri, u, v, inst);
 		hits[i] = make_float4(h ? t : 1e34f, u, v, __uint_as_float(h ? tri : 0xffffffffu));
+		if (inst_out != nullptr) // two-level scene: the instance the hit was found in
+			inst_out[i] = inst;
 	}
 }
 
@@ -2826,7 +3031,8 @@ cudaError_t configure_launches(const RenderSettings &rs, uint32_t node_count, La
 									(const void *)k_wavefront_trace<true, 1, 1, true>,	 (const void *)k_wavefront_trace<false, 1, 1, true>,
 									(const void *)k_wavefront_trace<true, 1, 3, true>,	 (const void *)k_wavefront_trace<false, 1, 3, true>,
 									(const void *)k_wavefront_trace<true, 1, 4, true>,	 (const void *)k_wavefront_trace<false, 1, 4, true>,
-									(const void *)k_wavefront_trace_cw<true>,			 (const void *)k_wavefront_trace_cw<false>};
+									(const void *)k_wavefront_trace_cw<true>,			 (const void *)k_wavefront_trace_cw<false>,
+									(const void *)k_wavefront_trace_tl<true>,			 (const void *)k_wavefront_trace_tl<false>};
 		for (const void *k : l1_kernels)
 		{
 			e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
@@ -2882,6 +3088,11 @@ cudaError_t configure_launches(const RenderSettings &rs, uint32_t node_count, La
 cudaError_t launch_primary(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
 						   const BatchView &bv, const LaunchDims &dims, cudaStream_t stream)
 {
+	if (sc.tl_instances != nullptr)
+	{
+		k_wavefront_trace_tl<true><<<dims.trace_grid, dims.trace_block, 0, stream>>>(sc, sh, wf, rs, bv, 0u, 0u);
+		return cudaGetLastError();
+	}
 	if (sc.cw_nodes != nullptr)
 	{
 		k_wavefront_trace_cw<true><<<dims.trace_grid, dims.trace_block, 0, stream>>>(sc, sh, wf, rs, bv, 0u, 0u);
@@ -2914,6 +3125,11 @@ cudaError_t launch_primary(const SceneView &sc, const ShardView &sh, const Wavef
 cudaError_t launch_trace(const SceneView &sc, const ShardView &sh, const WavefrontView &wf, const RenderSettings &rs,
 						 const BatchView &bv, uint32_t depth, uint32_t in_buf, const LaunchDims &dims, cudaStream_t stream)
 {
+	if (sc.tl_instances != nullptr)
+	{
+		k_wavefront_trace_tl<false><<<dims.trace_grid, dims.trace_block, 0, stream>>>(sc, sh, wf, rs, bv, depth, in_buf);
+		return cudaGetLastError();
+	}
 	if (sc.cw_nodes != nullptr)
 	{
 		k_wavefront_trace_cw<false><<<dims.trace_grid, dims.trace_block, 0, stream>>>(sc, sh, wf, rs, bv, depth, in_buf);
@@ -3005,10 +3221,10 @@ cudaError_t launch_emode(const SceneView &sc, const ShardView &sh, const Wavefro
 }
 cudaError_t launch_trace_closest(const SceneView &sc, const RenderSettings &rs, const float4 *origins, const float4 *directions,
 								 uint32_t n, float t_min, float4 *hits_out, uint32_t *cursor, const LaunchDims &dims,
-								 cudaStream_t stream)
+								 cudaStream_t stream, uint32_t *inst_out)
 {
 	k_trace_closest<<<dims.trace_grid, dims.trace_block, dims.trace_smem, stream>>>(sc, rs, origins, directions, n, t_min,
-																				   hits_out, cursor);
+																				   hits_out, cursor, inst_out);
 	return cudaGetLastError();
 }
 cudaError_t launch_trace_occluded(const SceneView &sc, const RenderSettings &rs, const float4 *origins,

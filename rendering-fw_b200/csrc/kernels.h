@@ -66,7 +66,7 @@ cudaError_t launch_emode(const SceneView &sc, const ShardView &sh, const Wavefro
 // --- stage-level entry points on caller rays ---
 cudaError_t launch_trace_closest(const SceneView &sc, const RenderSettings &rs, const float4 *origins,
 								 const float4 *directions, uint32_t n, float t_min, float4 *hits_out, uint32_t *cursor,
-								 const LaunchDims &dims, cudaStream_t stream);
+								 const LaunchDims &dims, cudaStream_t stream, uint32_t *inst_out = nullptr /* two-level scenes */);
 cudaError_t launch_trace_occluded(const SceneView &sc, const RenderSettings &rs, const float4 *origins,
 								  const float4 *directions_tmax, uint32_t n, float t_min, uint8_t *occluded_out,
 								  uint32_t *cursor, const LaunchDims &dims, cudaStream_t stream);

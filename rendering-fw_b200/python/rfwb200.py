@@ -316,6 +316,12 @@ class RenderContext:
         self._check(self.L.fn("set_setting", C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p])(
             self._h, key.encode(), str(value).encode()))
 
+    def get_settings(self) -> str:
+        """key=value lines (RenderContext::get_settings, context.h:96) + `levels_in_use`: the form of the committed scene"""
+        buf = C.create_string_buffer(4096)
+        self._check(self.L.fn("get_settings", C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t])(self._h, buf, len(buf)))
+        return buf.value.decode()
+
     def render_frame(self, camera, status: int = RESET):
         view = camera.get_view() if hasattr(camera, "get_view") else camera
         self._check(self.L.fn("render_frame", C.c_int, [C.c_void_p, C.POINTER(CameraView), C.c_int])(

@@ -3,6 +3,14 @@ from pathlib import Path
 
 import pytest
 
+import os
+
+# The device-group tests put up to 8 ranks of a sharded frame on ONE GPU.  The ranks wait for each other inside tiny kernels
+# (k_shard_sync, k_display_spin); with CUDA's default of 8 hardware work queues per device two ranks' streams can share a
+# queue, and a waiting kernel at its head then blocks the very kernel it waits for until the 4 s time-out.  On a real
+# multi-GPU box every rank has its own device and queues.  Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 REPO = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(REPO / "rendering-fw_b200" / "python"))
 sys.path.insert(0, str(REPO))

@@ -234,3 +234,53 @@ def test_parallel_sbvh_build_is_deterministic(product_lib):
         assert (info["nodes"], info["refs"], info["depth"]) == (i0["nodes"], i0["refs"], i0["depth"])
         assert info["sah"] == i0["sah"]
         assert np.array_equal(info["visits"], i0["visits"]) and np.array_equal(tri, tri0) and np.array_equal(t, t0)
+
+
+# ---- top level of two-level scenes (csrc/bvh_build.cpp build_tlas4) ------------------------------------------------------
+def host_check_tlas(lib, boxes, o, d):
+    f = lib.fn("host_tlas_check", C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p])
+    boxes = np.ascontiguousarray(boxes, np.float32).reshape(-1, 6)
+    o, d = np.ascontiguousarray(o, np.float32), np.ascontiguousarray(d, np.float32)
+    nodes, depth, bad, mism, hit = C.c_uint64(), C.c_int32(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+    rc = f(boxes.ctypes.data if len(boxes) else None, len(boxes), o.ctypes.data, d.ctypes.data, len(o), C.byref(nodes), C.byref(depth), C.byref(bad),
+           C.byref(mism), C.byref(hit))
+    assert rc == 0, lib.last_error()
+    return {"nodes": nodes.value, "depth": depth.value, "structure_errors": bad.value, "ray_mismatches": mism.value, "boxes_hit": hit.value}
+
+
+@pytest.mark.parametrize("n,layout", [(1, "random"), (2, "random"), (3, "random"), (5, "random"), (394, "random"), (5000, "random"), (1000, "line"),
+                                      (64, "coincident"), (4096, "lattice")])
+def test_top_level_tree_names_every_box_once_and_finds_what_a_loop_finds(product_lib, n, layout):
+    rng = np.random.default_rng(n)
+    if layout == "random":  # overlapping boxes of very different sizes (Sponza's 394 instance boxes look like this)
+        c = rng.uniform(-50, 50, size=(n, 3))
+        h = np.exp(rng.uniform(-3, 3, size=(n, 3)))
+    elif layout == "line":  # one axis only: the other two offer no split
+        c = np.zeros((n, 3))
+        c[:, 1] = np.arange(n) * 2.0
+        h = np.full((n, 3), 0.9)
+    elif layout == "coincident":  # identical centres: no plane separates them, the builder must still terminate
+        c = np.zeros((n, 3))
+        h = np.tile(rng.uniform(0.5, 2.0, size=(1, 3)), (n, 1))
+    else:  # config 3: copies on a jittered lattice
+        g = np.stack(np.meshgrid(*[np.arange(16)] * 3, indexing="ij"), -1).reshape(-1, 3)[:n]
+        c = g * 40.0 + rng.uniform(-5, 5, size=(n, 3))
+        h = np.full((n, 3), 18.0)
+    boxes = np.concatenate([c - h, c + h], axis=1).astype(np.float32)
+    ext = float(np.abs(boxes).max())
+    o, d = rays(400, n, ext * 0.8)
+    aim = c[rng.integers(0, n, size=200)].astype(np.float32) - o[200:]  # half of the rays are aimed at a box
+    d[200:] = aim / np.maximum(np.linalg.norm(aim, axis=1, keepdims=True), 1e-20)
+    info = host_check_tlas(product_lib, boxes, o, d)
+    assert info["structure_errors"] == 0 and info["ray_mismatches"] == 0, info
+    assert info["boxes_hit"] >= 190
+    assert info["nodes"] <= max(1, n - 1)  # every node has at least two children, except a root over a single box
+    if layout != "coincident":
+        assert info["depth"] <= 2 * int(np.ceil(np.log(max(n, 2)) / np.log(4))) + 4, info  # close to balanced
+
+
+def test_top_level_tree_of_nothing(product_lib):
+    o, d = rays(4, 0, 1.0)
+    info = host_check_tlas(product_lib, np.zeros((0, 6), np.float32), o, d)
+    assert info == {"nodes": 1, "depth": 1, "structure_errors": 0, "ray_mismatches": 0, "boxes_hit": 0}
