@@ -429,9 +429,10 @@ RFWB200_API int rfwb200_host_cwbvh_check(const float *tris9, size_t n_tris, int 
 										 int32_t *tri_out, uint64_t *nodes_out, uint64_t *refs_out, int32_t *depth_out,
 										 float *sah_out, uint32_t *visits_out, float *tris9_out);
 
-/* The same check for the GPU builder's algorithm (csrc/lbvh.h, setting builder=lbvh): its per-element functions run in
- * host loops (presplit != 0: with early split clipping of long triangles), the resulting 4-wide tree is walked on the CPU. */
-RFWB200_API int rfwb200_host_lbvh_check(const float *tris9, size_t n_tris, int presplit, const float *origins3,
+/* The same check for the GPU builders' algorithms (csrc/lbvh.h, setting builder = lbvh | ploc): their per-element functions
+ * run in host loops, the resulting 4-wide tree is walked on the CPU.  presplit_and_flags: bit 0 = early split clipping of
+ * long triangles, bit 1 = parallel locally-ordered clustering (builder=ploc) instead of the radix tree. */
+RFWB200_API int rfwb200_host_lbvh_check(const float *tris9, size_t n_tris, int presplit_and_flags, const float *origins3,
 										const float *dirs3, size_t n_rays, float *t_out, int32_t *tri_out, uint64_t *nodes_out,
 										uint64_t *refs_out, int32_t *depth_out, uint32_t *visits_out);
 

@@ -240,7 +240,8 @@ struct rfwb200_context
 	uint64_t refits = 0, builds = 0;
 	bool shade_ieee = false; // setting "shade_math" = fast | ieee
 	bool wide8 = false;		 // setting "bvh" = 4 | 8 (compressed 8-wide layout, cwbvh.h)
-	bool lbvh = false;		 // setting "builder" = sbvh (host, SAH + spatial splits) | lbvh (device, lbvh.h)
+	bool lbvh = false;		 // setting "builder" = sbvh (host, SAH + spatial splits) | lbvh | ploc (device, lbvh.h)
+	bool ploc = false;		 // device builder: parallel locally-ordered clustering instead of the radix tree
 	bool device_built = false; // the current tree was built on the device: the host has no copy of its topology
 	bool lbvh_presplit = false; // setting "lbvh_presplit": early split clipping before the Morton sort (lbvh.h step 0); measured slower
 	bool device_ref_boxes = false; // d_ref_boxes was written by the device builder
@@ -1392,7 +1393,7 @@ extern "C"
 			CK(cudaEventRecord(c->ev_geo_a, c->stream));
 			uint32_t nn = 0, nrefs = 0;
 			int depth = 0, launches = 0;
-			CK(lbvh_build(c->geo, c->lbvh_presplit ? 1 : 0, c->d_lbvh_scratch.ptr, c->d_lbvh_scratch.bytes, ref_cap, c->d_nodes.as<BvhNode4>(),
+			CK(lbvh_build(c->geo, (c->lbvh_presplit ? 1 : 0) | (c->ploc ? 2 : 0), c->d_lbvh_scratch.ptr, c->d_lbvh_scratch.bytes, ref_cap, c->d_nodes.as<BvhNode4>(),
 						  c->d_tri_order.as<uint32_t>(), c->d_parent_slot.as<uint32_t>(), c->d_ref_boxes.as<float>(), &nn, &nrefs, &depth,
 						  &launches, c->stream));
 			c->launches += uint64_t(launches);
@@ -1986,10 +1987,10 @@ extern "C"
 		}
 		else if (k == "builder")
 		{
-			REQUIRE(v == "sbvh" || v == "lbvh", "builder must be 'sbvh' (host) or 'lbvh' (device)");
-			const bool lb = (v == "lbvh");
-			if (lb != c->lbvh)
-				c->lbvh = lb, c->arena_valid = false, c->geometry_dirty = c->topology_dirty = true;
+			REQUIRE(v == "sbvh" || v == "lbvh" || v == "ploc", "builder must be 'sbvh' (host), 'lbvh' or 'ploc' (device)");
+			const bool lb = (v == "lbvh" || v == "ploc"), pl = (v == "ploc");
+			if (lb != c->lbvh || pl != c->ploc)
+				c->lbvh = lb, c->ploc = pl, c->arena_valid = false, c->geometry_dirty = c->topology_dirty = true;
 		}
 		else if (k == "lbvh_presplit")
 		{
@@ -2045,7 +2046,7 @@ extern "C"
 							  std::to_string(c->spp_batch) + "\nsort=on|off\nsort_cell_bits=" + std::to_string(c->rs.sort_cell_bits) +
 							  "\nsort_major=cell|octant\naov=on|off\nfetch_chunk=" + std::to_string(c->rs.fetch_chunk) + "\nfetch_threshold=" + std::to_string(c->rs.fetch_threshold) +
 							  "\ntrace_variant=" + std::to_string(c->rs.trace_variant) + "\nprimary_variant=" +
-							  std::to_string(c->rs.primary_variant) + "\nbvh=4|8\nbuilder=sbvh|lbvh\nspatial_splits=on|off\nrefit=device|host" +
+							  std::to_string(c->rs.primary_variant) + "\nbvh=4|8\nbuilder=sbvh|lbvh|ploc\nspatial_splits=on|off\nrefit=device|host" +
 							  "\nshade_math=fast|ieee\ntiming=on|off\nlevels=1|2|auto\nflatten_budget=" + std::to_string(c->flatten_budget) + "\nlevels_in_use=" + (c->two_level ? "2" : "1") + "\n";
 		snprintf(buf, buf_size, "%s", s.c_str());
 		return RFWB200_OK;
@@ -3115,6 +3116,11 @@ extern "C"
 		return RFWB200_OK;
 	}
 
+	struct SerialAlloc1 // atomicAdd(counter, 1)
+	{
+		uint32_t *next;
+		uint32_t operator()() const { return (*next)++; }
+	};
 	struct SerialAlloc // what atomicAdd on the level counter does, for one "thread" at a time
 	{
 		uint32_t *next;
@@ -3129,9 +3135,11 @@ extern "C"
 	// Self check of the GPU builder's algorithm without a GPU: the per-element functions of lbvh.h — the very code the
 	// kernels in geometry.cu run one element per thread — executed in loops on the host (std::sort in place of the radix
 	// sort), then walked like any other 4-wide tree.
-	int rfwb200_host_lbvh_check(const float *tris9, size_t n_tris, int presplit, const float *origins3, const float *dirs3, size_t n_rays,
+	int rfwb200_host_lbvh_check(const float *tris9, size_t n_tris, int presplit_and_flags, const float *origins3, const float *dirs3, size_t n_rays,
 								float *t_out, int32_t *tri_out, uint64_t *nodes_out, uint64_t *refs_out, int32_t *depth_out, uint32_t *visits_out)
 	{
+		const int presplit = presplit_and_flags & 1;
+		const bool ploc = (presplit_and_flags & 2) != 0; // builder=ploc: clustering instead of the radix tree
 		REQUIRE(tris9 && origins3 && dirs3 && t_out && tri_out, "bad arguments");
 		REQUIRE(n_tris >= 1 && n_tris < (1u << 29), "need 1 .. 2^29 triangles");
 		std::vector<BuildTriangle> bt(n_tris);
@@ -3219,9 +3227,62 @@ extern "C"
 		t.left = left.data(), t.right = right.data(), t.first = first.data(), t.last = last.data();
 		t.parent_inner = parent_inner.data(), t.parent_leaf = parent_leaf.data();
 		t.inner_box = inner_box.data(), t.leaf_box = leaf_box.data(), t.arrivals = arrivals.data();
-		for (int i = 0; i < n - 1; i++)
+		std::vector<int32_t> counts(n, 0), position(n, 0);
+		int ploc_rounds = 0;
+		if (ploc && n > 1)
+		{
+			// k_ploc_nearest / k_ploc_merge / compaction, one "thread" after the other (geometry.cu ploc rounds)
+			std::vector<int32_t> id_a(n), id_b(n), nn(n);
+			std::vector<LbvhBox> box_a(leaf_box), box_b(n);
+			std::vector<uint32_t> keep(n);
+			for (int i = 0; i < n; i++)
+				id_a[i] = ~i;
+			uint32_t made = 0;
+			int c = n;
+			while (c > 1)
+			{
+				PlocRound pr{c, id_a.data(), box_a.data(), nn.data(), id_b.data(), box_b.data(), keep.data()};
+				for (int i = 0; i < c; i++)
+					ploc_nearest(pr, i, PLOC_RADIUS);
+				for (int i = 0; i < c; i++)
+					ploc_merge(pr, t, counts.data(), i, SerialAlloc1{&made});
+				int c2 = 0;
+				for (int i = 0; i < c; i++)
+					if (keep[i])
+						id_a[c2] = id_b[i], box_a[c2] = box_b[i], c2++;
+				REQUIRE(c2 < c, "a clustering round merged nothing");
+				c = c2, ploc_rounds++;
+			}
+			REQUIRE(made == uint32_t(n - 1), "clustering did not produce n - 1 inner nodes");
+			for (int i = 0; i < n; i++)
+				position[i] = ploc_leaf_position(t, counts.data(), i);
+			for (int k = 0; k < n - 1; k++)
+				ploc_node_range(t, counts.data(), position.data(), k);
+			// permute the per-reference arrays to depth-first order and relabel the leaf children (k_ploc_permute)
+			std::vector<LbvhBox> lb2(n);
+			std::vector<uint32_t> to2(n);
+			std::vector<int32_t> pl2(n);
+			for (int i = 0; i < n; i++)
+				lb2[position[i]] = leaf_box[i], to2[position[i]] = bvh.tri_order[i], pl2[position[i]] = parent_leaf[i];
+			for (int k = 0; k < n - 1; k++)
+			{
+				if (left[k] < 0)
+					left[k] = ~position[~left[k]];
+				if (right[k] < 0)
+					right[k] = ~position[~right[k]];
+			}
+			leaf_box.swap(lb2), bvh.tri_order.swap(to2), parent_leaf.swap(pl2);
+			t.leaf_box = leaf_box.data(), t.parent_leaf = parent_leaf.data();
+			std::vector<uint8_t> seen(n, 0);
+			for (int i = 0; i < n; i++)
+				seen[position[i]]++;
+			for (int i = 0; i < n; i++)
+				REQUIRE(seen[i] == 1, "depth-first positions are not a permutation");
+			std::fill(arrivals.begin(), arrivals.begin() + (n - 1), 2u);
+		}
+		for (int i = 0; i < n - 1 && !ploc; i++)
 			lb_build_inner(t, i);
-		for (int i = 0; i < n && n > 1; i++) // k_lbvh_boxes, one "thread" after the other
+		for (int i = 0; i < n && n > 1 && !ploc; i++) // k_lbvh_boxes, one "thread" after the other
 		{
 			int cur = parent_leaf[i];
 			while (cur >= 0)

@@ -548,6 +548,70 @@ __global__ void __launch_bounds__(256) k_lbvh_boxes(const Lbvh2View t)
 	}
 }
 
+// ---- builder=ploc: parallel locally-ordered clustering (lbvh.h ploc_*), one launch per step and round -----------------------
+__global__ void __launch_bounds__(256) k_ploc_init(int32_t *__restrict__ id, LbvhBox *__restrict__ box, const LbvhBox *__restrict__ leaf_box, int n)
+{
+	const int i = int(blockIdx.x * blockDim.x + threadIdx.x);
+	if (i < n)
+		id[i] = ~i, box[i] = leaf_box[i];
+}
+__global__ void __launch_bounds__(256) k_ploc_nearest(const PlocRound p)
+{
+	const int i = int(blockIdx.x * blockDim.x + threadIdx.x);
+	if (i < p.c)
+		ploc_nearest(p, i, PLOC_RADIUS);
+}
+__global__ void __launch_bounds__(256) k_ploc_merge(const PlocRound p, const Lbvh2View t, int32_t *counts, uint32_t *made)
+{
+	const int i = int(blockIdx.x * blockDim.x + threadIdx.x);
+	if (i < p.c)
+		ploc_merge(p, t, counts, i, [made] __device__() { return atomicAdd(made, 1u); });
+}
+__global__ void __launch_bounds__(256) k_ploc_compact(const PlocRound p, const uint32_t *__restrict__ offsets, int32_t *__restrict__ id_next,
+													  LbvhBox *__restrict__ box_next)
+{
+	const int i = int(blockIdx.x * blockDim.x + threadIdx.x);
+	if (i < p.c && p.keep[i])
+		id_next[offsets[i]] = p.out_id[i], box_next[offsets[i]] = p.out_box[i];
+}
+__global__ void __launch_bounds__(256) k_ploc_positions(const Lbvh2View t, const int32_t *__restrict__ counts, int32_t *__restrict__ position)
+{
+	const int i = int(blockIdx.x * blockDim.x + threadIdx.x);
+	if (i < t.n)
+		position[i] = ploc_leaf_position(t, counts, i);
+}
+__global__ void __launch_bounds__(256) k_ploc_ranges(const Lbvh2View t, const int32_t *__restrict__ counts, const int32_t *__restrict__ position)
+{
+	const int k = int(blockIdx.x * blockDim.x + threadIdx.x);
+	if (k < t.n - 1)
+		ploc_node_range(t, counts, position, k);
+}
+// references to depth-first order (the leaf encoding needs a subtree's references contiguous), leaf children relabelled
+__global__ void __launch_bounds__(256) k_ploc_permute(const Lbvh2View t, const int32_t *__restrict__ position, const uint32_t *__restrict__ tri_order_in,
+													  LbvhBox *__restrict__ leaf_box_out, uint32_t *__restrict__ tri_order_out,
+													  int32_t *__restrict__ parent_leaf_out, float *__restrict__ ref_boxes_out)
+{
+	const int i = int(blockIdx.x * blockDim.x + threadIdx.x);
+	if (i >= t.n)
+		return;
+	const int32_t q = position[i];
+	const LbvhBox b = t.leaf_box[i];
+	leaf_box_out[q] = b, tri_order_out[q] = tri_order_in[i], parent_leaf_out[q] = t.parent_leaf[i];
+	if (ref_boxes_out)
+	{
+		float *o = ref_boxes_out + size_t(q) * 6;
+		o[0] = b.lo[0], o[1] = b.lo[1], o[2] = b.lo[2], o[3] = b.hi[0], o[4] = b.hi[1], o[5] = b.hi[2];
+	}
+	if (i < t.n - 1)
+	{
+		const int32_t l = t.left[i], r = t.right[i];
+		if (l < 0)
+			t.left[i] = ~position[~l];
+		if (r < 0)
+			t.right[i] = ~position[~r];
+	}
+}
+
 __global__ void __launch_bounds__(128) k_lbvh_collapse(const Lbvh2View t, const LbvhPending *__restrict__ queue, uint32_t count, uint32_t level_base,
 													   uint32_t next_level_base, BvhNode4 *nodes, uint32_t *parent_slot, LbvhPending *next_queue,
 													   uint32_t *next_count)
@@ -564,19 +628,22 @@ size_t lbvh_scratch_bytes(size_t tris, size_t refs)
 {
 	size_t sort_tmp = 0, scan_tmp = 0;
 	cub::DeviceRadixSort::SortKeys(nullptr, sort_tmp, (const uint64_t *)nullptr, (uint64_t *)nullptr, int(refs), 0, 62);
-	cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (const uint32_t *)nullptr, (uint32_t *)nullptr, int(tris));
+	cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (const uint32_t *)nullptr, (uint32_t *)nullptr, int(refs));
 	auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
 	return al(sort_tmp) + al(scan_tmp) + 2 * al(refs * 8) + al(tris * sizeof(LbvhBox)) + 3 * al(refs * sizeof(LbvhBox)) + 8 * al(refs * 4) +
-		   2 * al(tris * 4) + 2 * al(refs * sizeof(LbvhPending)) + al(64) + 8192;
+		   2 * al(tris * 4) + 2 * al(refs * sizeof(LbvhPending)) + al(64) + 8192 +
+		   2 * al(refs * sizeof(LbvhBox)) + 8 * al(refs * 4); // builder=ploc: cluster ids / boxes (double-buffered), partner, keep, offsets, counts, positions, parent links
 }
 
 // Builds nodes[0..*node_count), tri_order[0..*ref_count), parent_slot[0..*node_count) (and ref_boxes_out, 6 floats per
 // reference, when given) on `stream`; synchronises once per tree level to read the size of the next level, and once or
 // twice more when `presplit` is on (scene extent, reference count).
-cudaError_t lbvh_build(const GeometryView &g, int presplit, void *scratch, size_t scratch_bytes, size_t ref_capacity, BvhNode4 *nodes,
+cudaError_t lbvh_build(const GeometryView &g, int presplit_and_flags, void *scratch, size_t scratch_bytes, size_t ref_capacity, BvhNode4 *nodes,
 					   uint32_t *tri_order, uint32_t *parent_slot, float *ref_boxes_out, uint32_t *node_count, uint32_t *ref_count, int *depth,
 					   int *launches, cudaStream_t stream)
 {
+	const int presplit = presplit_and_flags & 1;
+	const bool ploc = (presplit_and_flags & 2) != 0;
 	const uint32_t nt = g.flat_count;
 	*node_count = 0, *ref_count = 0, *depth = 0;
 	if (nt == 0 || ref_capacity < nt || scratch_bytes < lbvh_scratch_bytes(nt, ref_capacity))
@@ -591,7 +658,7 @@ cudaError_t lbvh_build(const GeometryView &g, int presplit, void *scratch, size_
 	const size_t cap = ref_capacity;
 	size_t sort_tmp = 0, scan_tmp = 0;
 	cub::DeviceRadixSort::SortKeys(nullptr, sort_tmp, (const uint64_t *)nullptr, (uint64_t *)nullptr, int(cap), 0, 62);
-	cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (const uint32_t *)nullptr, (uint32_t *)nullptr, int(nt));
+	cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (const uint32_t *)nullptr, (uint32_t *)nullptr, int(cap));
 	void *d_sort = take(sort_tmp), *d_scan = take(scan_tmp);
 	uint64_t *keys_a = reinterpret_cast<uint64_t *>(take(cap * 8)), *keys_b = reinterpret_cast<uint64_t *>(take(cap * 8));
 	LbvhBox *boxes = reinterpret_cast<LbvhBox *>(take(size_t(nt) * sizeof(LbvhBox)));
@@ -607,8 +674,9 @@ cudaError_t lbvh_build(const GeometryView &g, int presplit, void *scratch, size_
 	uint32_t *counts = reinterpret_cast<uint32_t *>(take(size_t(nt) * 4)), *offsets = reinterpret_cast<uint32_t *>(take(size_t(nt) * 4));
 	LbvhPending *queue_a = reinterpret_cast<LbvhPending *>(take(cap * sizeof(LbvhPending)));
 	LbvhPending *queue_b = reinterpret_cast<LbvhPending *>(take(cap * sizeof(LbvhPending)));
-	int32_t *bounds = reinterpret_cast<int32_t *>(take(64)); // 6 ordered ints + the level counter
+	int32_t *bounds = reinterpret_cast<int32_t *>(take(64)); // 6 ordered ints + the level counter + the clustering's node counter
 	uint32_t *next_count = reinterpret_cast<uint32_t *>(bounds + 8);
+	uint32_t *made = reinterpret_cast<uint32_t *>(bounds + 9);
 	const uint32_t tblocks = (nt + 255u) / 256u;
 	cudaError_t e;
 	const int32_t init[12] = {0x7fffffff, 0x7fffffff, 0x7fffffff, int32_t(0x80000000), int32_t(0x80000000), int32_t(0x80000000), 0, 0, 0, 0, 0, 0};
@@ -658,7 +726,50 @@ cudaError_t lbvh_build(const GeometryView &g, int presplit, void *scratch, size_
 	k_lbvh_gather<<<blocks, 256, 0, stream>>>(keys_b, ref_box, ref_tri, n, t.leaf_box, tri_order, ref_boxes_out);
 	*launches += 3 + 3; // + the sort's passes, roughly
 	LbvhPending root{n == 1 ? ~0 : 0, 0xffffffffu};
-	if (n > 1)
+	if (n > 1 && ploc)
+	{
+		int32_t *id_a = reinterpret_cast<int32_t *>(take(cap * 4)), *id_b = reinterpret_cast<int32_t *>(take(cap * 4));
+		LbvhBox *box_a = reinterpret_cast<LbvhBox *>(take(cap * sizeof(LbvhBox))), *box_b = reinterpret_cast<LbvhBox *>(take(cap * sizeof(LbvhBox)));
+		int32_t *nn = reinterpret_cast<int32_t *>(take(cap * 4));
+		uint32_t *keep = reinterpret_cast<uint32_t *>(take(cap * 4)), *offs = reinterpret_cast<uint32_t *>(take(cap * 4));
+		int32_t *cnts = reinterpret_cast<int32_t *>(take(cap * 4)), *position = reinterpret_cast<int32_t *>(take(cap * 4));
+		int32_t *parent_leaf2 = reinterpret_cast<int32_t *>(take(cap * 4));
+		k_ploc_init<<<blocks, 256, 0, stream>>>(id_a, box_a, t.leaf_box, int(n));
+		*launches += 1;
+		// out_id / out_box of a round: the round's own scratch (id_b / box_b); the compaction writes back into id_a / box_a only
+		// after every thread of the merge kernel has read them (separate launches)
+		int c = int(n), rounds = 0;
+		while (c > 1)
+		{
+			const PlocRound pr{c, id_a, box_a, nn, id_b, box_b, keep};
+			const uint32_t cb = (uint32_t(c) + 255u) / 256u;
+			k_ploc_nearest<<<cb, 256, 0, stream>>>(pr);
+			k_ploc_merge<<<cb, 256, 0, stream>>>(pr, t, cnts, made);
+			if ((e = cub::DeviceScan::ExclusiveSum(d_scan, scan_tmp, keep, offs, c, stream)) != cudaSuccess)
+				return e;
+			k_ploc_compact<<<cb, 256, 0, stream>>>(pr, offs, id_a, box_a);
+			*launches += 5;
+			uint32_t last_off = 0, last_keep = 0;
+			if ((e = cudaMemcpyAsync(&last_off, offs + (c - 1), 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess)
+				return e;
+			if ((e = cudaMemcpyAsync(&last_keep, keep + (c - 1), 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess)
+				return e;
+			if ((e = cudaStreamSynchronize(stream)) != cudaSuccess)
+				return e;
+			const int c2 = int(last_off + last_keep);
+			if (c2 >= c || ++rounds > 4096)
+				return cudaErrorUnknown; // a round always merges the globally closest pair
+			c = c2;
+		}
+		k_ploc_positions<<<blocks, 256, 0, stream>>>(t, cnts, position);
+		k_ploc_ranges<<<blocks, 256, 0, stream>>>(t, cnts, position);
+		if ((e = cudaMemcpyAsync(ref_tri, tri_order, size_t(n) * 4, cudaMemcpyDeviceToDevice, stream)) != cudaSuccess)
+			return e;
+		k_ploc_permute<<<blocks, 256, 0, stream>>>(t, position, ref_tri, ref_box, tri_order, parent_leaf2, ref_boxes_out);
+		t.leaf_box = ref_box, t.parent_leaf = parent_leaf2;
+		*launches += 3;
+	}
+	else if (n > 1)
 	{
 		if ((e = cudaMemsetAsync(t.arrivals, 0, size_t(n) * 4, stream)) != cudaSuccess)
 			return e;

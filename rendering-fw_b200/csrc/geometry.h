@@ -62,7 +62,7 @@ cudaError_t launch_refit(const GeometryView &g, cudaStream_t stream);
 // geometry arena; outputs are sized for ref_capacity references (>= triangles; > triangles enables early split clipping);
 // *launches is incremented
 size_t lbvh_scratch_bytes(size_t triangles, size_t ref_capacity);
-cudaError_t lbvh_build(const GeometryView &g, int presplit, void *scratch, size_t scratch_bytes, size_t ref_capacity, BvhNode4 *nodes,
+cudaError_t lbvh_build(const GeometryView &g, int presplit_and_flags /* bit 0: early split clipping, bit 1: clustering (builder=ploc) */, void *scratch, size_t scratch_bytes, size_t ref_capacity, BvhNode4 *nodes,
 					   uint32_t *tri_order, uint32_t *parent_slot, float *ref_boxes_out, uint32_t *node_count, uint32_t *ref_count, int *depth,
 					   int *launches, cudaStream_t stream);
 cudaError_t launch_pack_nodes(const BvhNode4 *nodes, BvhNode4Packed *out, uint32_t n, cudaStream_t stream);

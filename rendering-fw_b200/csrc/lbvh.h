@@ -9,6 +9,8 @@
 //   2. binary radix tree over the sorted keys (Karras, "Maximizing Parallelism in the Construction of BVHs, Octrees, and
 //      k-d Trees", HPG 2012): every inner node finds its range and split independently
 //   3. boxes bottom-up with one arrival counter per inner node
+//      (setting "builder" = ploc replaces 2-3 by parallel locally-ordered clustering over the same sorted references:
+//      a bottom-up build that pairs clusters by the surface area of their union, see ploc_* below)
 //   4. collapse to the 4-wide BvhNode4 layout level by level (a subtree of <= 4 triangles becomes a leaf: its triangles
 //      are contiguous in the sorted order), children allocated contiguously -> the same node format, leaf encoding and
 //      parent links as the host builder's output, so the refit / pack / trace kernels do not care who built the tree.
@@ -147,6 +149,106 @@ LB_HD float lb_area(const LbvhBox &b)
 {
 	const float ex = b.hi[0] - b.lo[0], ey = b.hi[1] - b.lo[1], ez = b.hi[2] - b.lo[2];
 	return ex * ey + ey * ez + ez * ex;
+}
+
+// ---- steps 2-3, SAH-aware variant (setting "builder" = ploc): parallel locally-ordered clustering ------------------------------
+// Meister & Bittner, "Parallel Locally-Ordered Clustering for Bounding Volume Hierarchy Construction" (TVCG 2018).  The
+// Morton-sorted references start as one cluster each.  Per round every cluster looks `radius` neighbours to either side in
+// the (Morton-ordered) cluster array for the partner with which it forms the smallest box (surface area — the SAH's
+// measure); two clusters that chose each other merge into a new inner node; the array is compacted and the round repeats
+// until one cluster — the root — is left.  Unlike the radix tree this is a bottom-up agglomerative build driven by box area,
+// so a large triangle is paired late with a large cluster instead of wherever its centroid's Morton prefix puts it.
+// The merged tree no longer keeps the references of a subtree contiguous in Morton order, which the leaf encoding
+// (first, count) needs: afterwards every reference gets its position in a depth-first walk (ploc_leaf_position) and the
+// per-reference arrays are permuted to it.
+#ifndef RFW_PLOC_RADIUS
+#define RFW_PLOC_RADIUS 16
+#endif
+constexpr int PLOC_RADIUS = RFW_PLOC_RADIUS;
+
+struct PlocRound
+{
+	int32_t c;			   // clusters at the start of the round
+	const int32_t *id;	   // [c] BVH2 node of the cluster: ~reference or inner node
+	const LbvhBox *box;	   // [c]
+	int32_t *nn;		   // [c] chosen partner
+	int32_t *out_id;	   // [c] the round's result before compaction
+	LbvhBox *out_box;	   // [c]
+	uint32_t *keep;		   // [c] 1: the entry survives the round (merged pairs survive once, at the lower index)
+};
+
+LB_HD void ploc_nearest(const PlocRound &p, int i, int radius)
+{
+	const LbvhBox me = p.box[i];
+	const int lo = i - radius < 0 ? 0 : i - radius, hi = i + radius > p.c - 1 ? p.c - 1 : i + radius;
+	float best = 3.0e38f;
+	int best_j = -1;
+	for (int j = lo; j <= hi; j++)
+	{
+		if (j == i)
+			continue;
+		const float a = lb_area(lb_union(me, p.box[j]));
+		if (a < best) // ties go to the lower index: both sides of a pair see the same order
+			best = a, best_j = j;
+	}
+	p.nn[i] = best_j;
+}
+
+// counts[k]: references below inner node k.  `alloc()` returns how many inner nodes were made before this one (atomicAdd on
+// the device); node indices run downwards from n - 2 so that the last merge, the root, is node 0 like in the radix tree.
+template <typename Alloc>
+LB_HD void ploc_merge(const PlocRound &p, const Lbvh2View &t, int32_t *counts, int i, Alloc alloc)
+{
+	const int j = p.nn[i];
+	if (j >= 0 && p.nn[j] == i)
+	{
+		if (i > j)
+		{
+			p.keep[i] = 0u; // the pair lives on at index j
+			return;
+		}
+		const int32_t k = int32_t(t.n - 2) - int32_t(alloc());
+		const int32_t l = p.id[i], r = p.id[j];
+		t.left[k] = l, t.right[k] = r;
+		if (l >= 0)
+			t.parent_inner[l] = k;
+		else
+			t.parent_leaf[~l] = k;
+		if (r >= 0)
+			t.parent_inner[r] = k;
+		else
+			t.parent_leaf[~r] = k;
+		const LbvhBox u = lb_union(p.box[i], p.box[j]);
+		t.inner_box[k] = u;
+		counts[k] = (l < 0 ? 1 : counts[l]) + (r < 0 ? 1 : counts[r]);
+		if (k == 0)
+			t.parent_inner[0] = -1;
+		p.out_id[i] = k, p.out_box[i] = u, p.keep[i] = 1u;
+		return;
+	}
+	p.out_id[i] = p.id[i], p.out_box[i] = p.box[i], p.keep[i] = 1u;
+}
+
+// position of reference `leaf` in a depth-first, left-to-right walk of the finished tree
+LB_HD int32_t ploc_leaf_position(const Lbvh2View &t, const int32_t *counts, int leaf)
+{
+	int32_t pos = 0, child = ~leaf, cur = t.parent_leaf[leaf];
+	while (cur >= 0)
+	{
+		if (t.right[cur] == child)
+			pos += t.left[cur] < 0 ? 1 : counts[t.left[cur]];
+		child = cur, cur = t.parent_inner[cur];
+	}
+	return pos;
+}
+
+// reference range of inner node k once the references are in depth-first order (children still carry the old labels)
+LB_HD void ploc_node_range(const Lbvh2View &t, const int32_t *counts, const int32_t *position, int k)
+{
+	int32_t c = k;
+	while (c >= 0)
+		c = t.left[c];
+	t.first[k] = position[~c], t.last[k] = position[~c] + counts[k] - 1;
 }
 
 // ---- step 0 (optional, setting lbvh_presplit): early split clipping --------------------------------------------------

@@ -399,16 +399,18 @@ def test_device_geometry_is_bit_identical_to_the_host_path(product_lib):
     assert np.array_equal(d.read_image(), h.read_image())
 
 
+@pytest.mark.parametrize("builder", ["lbvh", "ploc"])
 @pytest.mark.parametrize("presplit", ["on", "off"])
-def test_device_lbvh_build_then_device_refit(product_lib, oracle_lib, presplit):
-    """builder=lbvh: Morton sort + radix tree + 4-wide collapse as kernels (csrc/lbvh.h, geometry.cu); the tree it makes is
-    refitted by the same k_refit as a host-built one.  Hits against the oracle, frame against the host-built frame."""
+def test_device_lbvh_build_then_device_refit(product_lib, oracle_lib, presplit, builder):
+    """builder=lbvh: Morton sort + radix tree + 4-wide collapse as kernels (csrc/lbvh.h, geometry.cu); builder=ploc: the same
+    sort and collapse around parallel locally-ordered clustering; the tree they make is refitted by the same k_refit as a
+    host-built one.  Hits against the oracle, frame against the host-built frame."""
     W, H = 160, 96
     (g, sc), (o, _) = make_pair(product_lib, oracle_lib, S.feature_soup, W, H)
     ref = R.RenderContext(product_lib)
     S.upload(ref, S.feature_soup(), W, H)
     g.set_setting("lbvh_presplit", presplit)
-    g.set_setting("builder", "lbvh")
+    g.set_setting("builder", builder)
     g.update()
     st = g.get_geometry_stats()
     assert (st.on_device, st.was_refit, st.builds, st.refits) == (1, 0, 2, 0) and st.device_ms > 0

@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Sponza with the device LBVH builder vs the host SBVH: build time, tree size, frame time (configs[1] camera, 8 spp)."""
+"""Sponza with the device builders (lbvh: radix tree, ploc: locally-ordered clustering) vs the host SBVH: build time, tree size,
+frame time (configs[1] camera, 8 spp)."""
 import json, sys, time
 from pathlib import Path
 REPO = Path(__file__).resolve().parent.parent
@@ -9,7 +10,7 @@ import rfwb200 as R, scenes as S
 sc = S.sponza_or_standin()
 out = {}
 ref = None
-for builder in ("sbvh", "lbvh", "lbvh-presplit"):
+for builder in ("sbvh", "lbvh", "lbvh-presplit", "ploc", "ploc-presplit"):
     ctx = R.RenderContext(R.load_product())
     ctx.set_setting("lbvh_presplit", "on" if builder.endswith("presplit") else "off")
     ctx.set_setting("builder", builder.split("-")[0])
