@@ -76,10 +76,13 @@ def data_note(sc):
     return "synthetic (procedural stand-in)" if "atrium" in sc.name else "reference assets baked as shipped (geometry, textures, sky) + deterministic seeds"
 
 
-def base_config(sc, cfg, n):
-    """the keys both arms print (the GPU arm adds its own under `config.gpu`)"""
+def base_config(sc, cfg, n, gpus):
+    """`config` of the JSON line: the same dictionary in both arms (the GPU arm's own details go under the top-level key `gpu`)"""
     return {"workload": workload_name(sc, cfg), "config": n, "width": cfg["width"], "height": cfg["height"], "spp": cfg["spp"],
-            "max_path_length": MAX_PATH if cfg["mode"] == "pt" else 0, "mode": cfg["mode"]}
+            "max_path_length": MAX_PATH if cfg["mode"] == "pt" else 0, "mode": cfg["mode"],
+            "parallelism": "single" if gpus <= 1 or cfg["mode"] != "pt" else f"tile{gpus}",
+            "l2": "inputs larger than L2: the wavefront state of a step (~3 GB at config 2) streams through HBM; the BVH and triangles "
+                  "(~50 MB for Sponza) are meant to stay in the 126 MB L2; no flush between steps"}
 
 
 def load_peaks():
@@ -244,7 +247,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "Msamples/s", "value": val, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": done,
         "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": data_note(sc), "config": base_config(sc, cfg, args.config),
+        "data": data_note(sc), "config": base_config(sc, cfg, args.config, args.gpus),
         "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": threads, "kind": "port", "sample": f"{what}, {done} frame(s) of {dt:.2f} s"},
         "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "steps_requested": args.steps, "warmup_requested": args.warmup,
@@ -597,18 +600,16 @@ def run():
 
     if rank == 0:
         bvh = ctx.get_bvh_info()
-        conf = base_config(sc, cfg, cfg_no)
-        conf["gpu"] = {"parallelism": f"tile{world}" if world > 1 else "single", "tile": [32, 8], "wavefronts_per_frame": nb,
+        conf = base_config(sc, cfg, cfg_no, world)
+        gpu_conf =    {"tile": [32, 8], "wavefronts_per_frame": nb,
                        "assembly": "peer stores into rank 0's image over CUDA IPC (no collective)" if sharded else "none",
-                       "l2": "inputs larger than L2: the wavefront state of a step (~3 GB at config 2) streams through HBM; the BVH and "
-                             "triangles (~50 MB for Sponza) are meant to stay in the 126 MB L2",
                        "triangles": bvh["triangles"], "bvh_nodes": bvh["nodes"], "bvh_build_ms": bvh["build_ms"], "scene_upload_s": upload_s,
                        "settings": args.set,
                        "frames_in_flight": INFLIGHT if sharded else "not bounded (one device, nothing to drift apart)"}
         line = {
             "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": data_note(sc), "config": conf, "clocks": clocks, "gpu_launches": int(launches),
+            "data": data_note(sc), "config": conf, "gpu": gpu_conf, "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms, "steps": e2e_steps, "checksum": checksum[0],
                     "what": "render_frame + read_framebuffer_async into pinned host memory through the C ABI, every frame read back; the "
