@@ -248,8 +248,8 @@ struct rfwb200_context
 	int device_depth = 0;
 	DevBuf d_lbvh_scratch;
 	DevBuf d_cw_nodes, d_nodes16, d_prim_cache, d_occ_cache;
-	// ---- two-level scene (TlInstance, device_types.h): setting "levels" = 1 (flatten, default) | 2 | auto ----
-	int levels_setting = 1;				   // 0 = auto: two levels when the flattened scene would exceed flatten_budget triangles
+	// ---- two-level scene (TlInstance, device_types.h): setting "levels" = 1 (flatten) | 2 | auto (default) ----
+	int levels_setting = 0;				   // 0 = auto (default): two levels when the flattened scene would exceed flatten_budget triangles
 	uint64_t flatten_budget = 1ull << 26;  // setting "flatten_budget" (flattened triangles; 2^26 of them are ~15 GB of records and nodes)
 	bool two_level = false;				   // the committed device scene is two-level
 	std::vector<BvhBuildResult> blas;	   // one object-space tree per mesh (kept across updates: only changed meshes are rebuilt)
