@@ -185,6 +185,26 @@ def cpu_frame_runner(cfg):
     return one, w * h * cfg["spp"], threads, what, ctx, sc
 
 
+def embree_probe():
+    """BASELINE.md §3 "real Embree (conditional)": is Intel Embree (and TBB, which the reference's EmbreeRT backend needs beside it)
+    installed on this box?  Reported, never assumed; when absent the CPU rows are the restatement's."""
+    found = {"libembree": [], "libtbb": []}
+    try:
+        out = subprocess.run(["ldconfig", "-p"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=10).stdout
+        for l in out.splitlines():
+            name = l.strip().split(" ")[0]
+            if name.startswith("libembree"):
+                found["libembree"].append(name)
+            if name.startswith("libtbb"):
+                found["libtbb"].append(name)
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+    usable = bool(found["libembree"]) and bool(found["libtbb"])
+    return {"libembree": sorted(set(found["libembree"])), "libtbb": sorted(set(found["libtbb"])), "usable": usable,
+            "note": "the reference's EmbreeRT backend could be timed directly" if usable else
+                    "Intel Embree is not installed on this box: the CPU rows are the restatement's (a scalar port; real Embree would be faster)"}
+
+
 def time_cpu(one, budget_s, warmup, steps):
     """`warmup` untimed frames, then up to `steps` timed ones, stopping early once `budget_s` is spent (at least one)."""
     for _ in range(warmup):
@@ -254,6 +274,7 @@ def run_reference(args):
         "protocol_note": f"a CPU frame takes seconds: at most {budget:.0f} s of timed frames after one warm-up frame are run "
                          "(`steps` / `warmup` are what was run); the value is the mean frame, so the ratio compares per-frame throughput",
     }
+    line["embree_probe"] = embree_probe()
     if args.config == 2:
         ref_kernels = reference_kernels_on_host(octx, sc, cfg["spp"])
         if ref_kernels:
@@ -598,6 +619,30 @@ def run():
                        "renderers cannot be built here (DESIGN.md §4) and real Embree would be faster than a scalar restatement"}
         octx.close()
 
+    # ---- E-mode of config 2 (the "Embree image" of the headline scene), outside the timed region ---------------
+    emode = None
+    if cfg_no == 2 and world == 1 and rank == 0 and not args.no_cpu_baseline:
+        ctx.set_setting("mode", "embree")
+        for _ in range(3):
+            ctx.render_frame(view, R.RESET)
+        torch.cuda.synchronize()
+        n_e = 50
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(n_e):
+            ctx.render_frame(view, R.RESET)
+        a1.record(stream)
+        torch.cuda.synchronize()
+        e_ms = a0.elapsed_time(a1) / n_e
+        ctx.set_setting("mode", "pt")
+        e_cfg = dict(cfg, mode="embree", spp=1)
+        one_e, samples_e, threads_e, what_e, octx_e, _ = cpu_frame_runner(e_cfg)
+        dt_e, done_e = time_cpu(one_e, 10.0, 1, 3)
+        octx_e.close()
+        emode = {"what": "E-mode (primary visibility + direct light of the reference's EmbreeRT backend, one sample per frame) of the same scene and camera",
+                 "ms_per_frame": e_ms, "mpixels_per_s": W * H / (e_ms * 1e-3) / 1e6,
+                 "cpu_port": {"mpixels_per_s": samples_e / dt_e / 1e6, "cores": threads_e, "sample": f"{what_e}, {done_e} frame(s) of {dt_e:.2f} s"}}
+
     if rank == 0:
         bvh = ctx.get_bvh_info()
         conf = base_config(sc, cfg, cfg_no, world)
@@ -625,6 +670,9 @@ def run():
             line["image_check"] = image_check
         if cpu:
             line["cpu_baseline"] = cpu
+            line["embree_probe"] = embree_probe()
+        if emode:
+            line["emode_of_config2"] = emode
         emit(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -185,3 +185,21 @@ def test_config5_three_light_types_against_the_oracle(product_lib, oracle_lib):
     g2.set_setting("spp", 16)
     g2.render_frame(cam, R.RESET)
     assert abs(g2.read_image()[..., :3].mean() - a[..., :3].mean()) > 0.02 * a[..., :3].mean()
+
+
+def test_config2_emode_image_against_the_oracle(product_lib, oracle_lib):
+    """The "Embree image" (E-mode: primary visibility + direct light) of the headline scene and camera at
+    480x270, pixel by pixel: no bounce, so no epsilon-scale self-intersection decides a pixel and the per-pixel tolerance of the
+    unit-scale tests applies; the pixels that may differ are those whose camera ray or shadow ray grazes an edge."""
+    W, H = 480, 270
+    (g, sc), (o, _) = pair(product_lib, oracle_lib, S.sponza_or_standin, W, H, mode="embree")
+    cam = sc.camera(W, H)
+    g.render_frame(cam, R.RESET), o.render_frame(cam, R.RESET)
+    a, b = g.read_image()[..., :3], o.read_image()[..., :3]
+    assert np.isfinite(a).all()
+    err = (np.abs(a - b) / (1.0 + np.abs(b))).max(axis=-1)
+    bad = float((err > 2e-3).mean())
+    mean_err = abs(float(a.mean()) - float(b.mean())) / float(b.mean())
+    print(f"config 2 E-mode: pixels off {bad:.4f}, mean error {mean_err:.5f}")
+    assert bad < 0.03, bad
+    assert mean_err < 5e-3, mean_err
