@@ -1,6 +1,7 @@
 // device_types.h — HBM-resident data layouts shared by the host side (context.cpp, bvh_build.cpp)
 // and the kernels (kernels.cu).  See DESIGN.md "Data layout in HBM".
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 #include <vector_types.h>
 
@@ -82,6 +83,8 @@ struct DepthCounters
 	uint32_t pad1;
 };
 static_assert(sizeof(DepthCounters) == 32, "");
+static_assert(offsetof(DepthCounters, ext) % 8 == 0 && offsetof(DepthCounters, shadow) == offsetof(DepthCounters, ext) + 4,
+			  "k_shade advances ext and shadow with one 64-bit atomic");
 
 constexpr int MAX_DEPTH_SLOTS = 8; // max_path_length + 1 <= 8
 constexpr int MAX_BATCH_SPP = 64;  // samples of a frame that travel in one wavefront (BatchView)

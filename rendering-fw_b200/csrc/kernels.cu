@@ -112,6 +112,27 @@ enum MatFlagBits
 };
 __device__ __forceinline__ bool has_flag(uint32_t f, int b) { return (f >> b) & 1u; }
 
+// Wavefront state is written once and read once per bounce — gigabytes per frame streaming past a BVH of a few tens of
+// megabytes that should stay in the 126 MB L2.  RFW_STREAM_HINTS marks those accesses evict-first (ld / st .cs):
+// 1 = in the trace kernels, 2 = also in k_shade and the re-ordering pass.  Measured in profiles/r02 (sweep8).
+#ifndef RFW_STREAM_HINTS
+#define RFW_STREAM_HINTS 2
+#endif
+#if RFW_STREAM_HINTS >= 1
+#define LD_TS(p) __ldcs(p)
+#define ST_TS(p, v) __stcs((p), (v))
+#else
+#define LD_TS(p) (*(p))
+#define ST_TS(p, v) (*(p) = (v))
+#endif
+#if RFW_STREAM_HINTS >= 2
+#define LD_SS(p) __ldcs(p)
+#define ST_SS(p, v) __stcs((p), (v))
+#else
+#define LD_SS(p) (*(p))
+#define ST_SS(p, v) (*(p) = (v))
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // hashing / samplers — bsdf/tools.h:218-235, Kernels.cu:205-224, utils/xor128.h:20-27
 // ------------------------------------------------------------------------------------------------
@@ -785,12 +806,12 @@ __device__ __forceinline__ bool fetch_ray(const SceneView &sc, const ShardView &
 		pidx = j;
 		if (!local_to_pixel(sh, j, x, y))
 		{
-			wf.hit[item] = make_float4(0.f, 0.f, __int_as_float(PRIM_DEAD), 0.f);
+			ST_TS(&wf.hit[item], make_float4(0.f, 0.f, __int_as_float(PRIM_DEAD), 0.f));
 			return false;
 		}
 		generate_pt(sc, fp, sh, x, y, fp.sample_base + bv.first_sample + s, o, d);
-		wf.O[in_buf][item] = make_float4(o.x, o.y, o.z, __uint_as_float((item << 8) + 1u));
-		wf.D[in_buf][item] = make_float4(d.x, d.y, d.z, 0.0f);
+		ST_TS(&wf.O[in_buf][item], make_float4(o.x, o.y, o.z, __uint_as_float((item << 8) + 1u)));
+		ST_TS(&wf.D[in_buf][item], make_float4(d.x, d.y, d.z, 0.0f));
 		tmin = 1e-5f, tmax = 1e34f, shadow = false;
 		// Bound from an earlier sample of the pixel: the samples of a pixel differ by a sub-pixel jitter, so the triangle
 		// one of them hit is almost always hit by the next.  Its distance (plus a few ulps) only LIMITS the search — the
@@ -804,13 +825,13 @@ __device__ __forceinline__ bool fetch_ray(const SceneView &sc, const ShardView &
 	}
 	if (item < q.n_ext)
 	{
-		const float4 O4 = q.Oin[item], D4 = q.Din[item];
+		const float4 O4 = LD_TS(&q.Oin[item]), D4 = LD_TS(&q.Din[item]);
 		o = mk(O4.x, O4.y, O4.z), d = mk(D4.x, D4.y, D4.z);
 		tmin = 1e-5f, tmax = 1e34f, shadow = false;
 		return true;
 	}
 	const uint32_t k = item - q.n_ext;
-	pidx = __float_as_uint(wf.sE[k].w);
+	pidx = __float_as_uint(LD_TS(&wf.sE[k].w));
 	// The reference only traces the connect queue of a sample when its bounce loop continues, i.e. when that sample
 	// emitted at least one extension ray at this depth anywhere in the frame (CUDART/src/Context.cpp:109-120: the host
 	// loop leaves before the pending shadow rays are traced).  The ranks of a sharded frame merge their flags between the
@@ -818,7 +839,7 @@ __device__ __forceinline__ bool fetch_ray(const SceneView &sc, const ShardView &
 	if (q.seen[(pidx >> 5) - fast_div(pidx >> 5, bv.spp, bv.inv_spp) * bv.spp] == 0u)
 		return false;
 	n_traced++;
-	const float4 O4 = wf.sO[k], D4 = wf.sD[k];
+	const float4 O4 = LD_TS(&wf.sO[k]), D4 = LD_TS(&wf.sD[k]);
 	o = mk(O4.x, O4.y, O4.z), d = mk(D4.x, D4.y, D4.z);
 	tmin = rs.geometry_epsilon, tmax = D4.w, shadow = true;
 	if (rs.shadow_cache == 2)
@@ -846,14 +867,14 @@ __device__ __forceinline__ void retire_ray(const WavefrontView &wf, const TraceQ
 		float4 hit = make_float4(0.f, 0.f, __int_as_float(PRIM_MISS), 0.f);
 		if (hit_tri != 0xffffffffu)
 			hit = make_float4(__uint_as_float(pack_barycentrics(hit_u, hit_v)), __uint_as_float(hit_tri), __int_as_float(int(hit_inst)), tmax);
-		wf.hit[item] = hit;
+		ST_TS(&wf.hit[item], hit);
 	}
 	else if (hit_tri == 0xffffffffu)
 	{
-		const float4 E = wf.sE[item - q.n_ext];
-		float4 a = wf.sample_acc[pidx];
+		const float4 E = LD_TS(&wf.sE[item - q.n_ext]);
+		float4 a = LD_TS(&wf.sample_acc[pidx]);
 		a.x += E.x, a.y += E.y, a.z += E.z, a.w += 1.0f;
-		wf.sample_acc[pidx] = a;
+		ST_TS(&wf.sample_acc[pidx], a);
 		acc_count++;
 	}
 }
@@ -2124,14 +2145,14 @@ __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, c
 
 		if (job < n_paths)
 		{
-			const float4 hitData = wf.hit[job];
+			const float4 hitData = LD_SS(&wf.hit[job]);
 			const int primIdx = __float_as_int(hitData.z);
 			dead = primIdx == PRIM_DEAD;
 			if (!dead)
 			{
-				const float4 O4 = wf.O[buf][job];
-				const float4 D4 = wf.D[buf][job];
-				const float4 T4 = pathLength == 0 ? make_float4(1.f, 1.f, 1.f, 1.f) : wf.T[buf][job];
+				const float4 O4 = LD_SS(&wf.O[buf][job]);
+				const float4 D4 = LD_SS(&wf.D[buf][job]);
+				const float4 T4 = pathLength == 0 ? make_float4(1.f, 1.f, 1.f, 1.f) : LD_SS(&wf.T[buf][job]);
 				uint32_t flags = __float_as_uint(O4.w) & 0xFFu;
 				V3 throughput = mk(T4.x, T4.y, T4.z);
 				const float bsdfPdf = T4.w;
@@ -2337,7 +2358,7 @@ __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, c
 		{
 			if (job < n_paths && !dead)
 			{
-				wf.sample_acc[job] = make_float4(accv.x, accv.y, accv.z, 0.0f);
+				ST_SS(&wf.sample_acc[job], make_float4(accv.x, accv.y, accv.z, 0.0f));
 				if (wf.sample_albedo != nullptr)
 				{
 					// a BSDF sample can be NaN (the path is then dropped, Kernels.cu:785); a feature plane must stay finite
@@ -2355,37 +2376,42 @@ __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, c
 		}
 		else if (do_acc)
 		{
-			float4 a = wf.sample_acc[pathIndex];
+			float4 a = LD_SS(&wf.sample_acc[pathIndex]);
 			a.x += accv.x, a.y += accv.y, a.z += accv.z;
-			wf.sample_acc[pathIndex] = a;
+			ST_SS(&wf.sample_acc[pathIndex], a);
 		}
 		if (do_acc)
 			acc_count++;
 		const uint32_t lt_mask = (1u << lane) - 1u;
 		const uint32_t m_sh = __ballot_sync(0xffffffffu, do_shadow);
+		const uint32_t m_ex = __ballot_sync(0xffffffffu, do_ext);
+		// slots in both queues from ONE atomic: DepthCounters::ext and ::shadow are the two halves of an aligned 64-bit word
+		// (neither half can carry into the other: a queue holds fewer than 2^32 entries), so the warp waits for one round
+		// trip to L2 instead of two in a row
+		uint32_t ebase = 0, sbase = 0;
+		if (m_sh | m_ex)
+		{
+			unsigned long long both = 0ull;
+			if (lane == 0)
+				both = atomicAdd(reinterpret_cast<unsigned long long *>(&curc->ext),
+								 (unsigned long long)(__popc(m_ex)) | ((unsigned long long)(__popc(m_sh)) << 32));
+			both = __shfl_sync(0xffffffffu, both, 0);
+			ebase = uint32_t(both), sbase = uint32_t(both >> 32);
+		}
 		if (m_sh)
 		{
-			uint32_t sbase = 0;
-			if (lane == 0)
-				sbase = atomicAdd(&curc->shadow, __popc(m_sh));
-			sbase = __shfl_sync(0xffffffffu, sbase, 0);
 			if (do_shadow)
 			{
 				const uint32_t slot = sbase + __popc(m_sh & lt_mask);
-				wf.sO[slot] = cO, wf.sD[slot] = cD, wf.sE[slot] = cE;
+				ST_SS(&wf.sO[slot], cO), ST_SS(&wf.sD[slot], cD), ST_SS(&wf.sE[slot], cE);
 			}
 		}
-		const uint32_t m_ex = __ballot_sync(0xffffffffu, do_ext);
 		if (m_ex)
 		{
-			uint32_t ebase = 0;
-			if (lane == 0)
-				ebase = atomicAdd(&curc->ext, __popc(m_ex));
-			ebase = __shfl_sync(0xffffffffu, ebase, 0);
 			if (do_ext)
 			{
 				const uint32_t slot = ebase + __popc(m_ex & lt_mask);
-				wf.O[nbuf][slot] = eO, wf.D[nbuf][slot] = eD, wf.T[nbuf][slot] = eT;
+				ST_SS(&wf.O[nbuf][slot], eO), ST_SS(&wf.D[nbuf][slot], eD), ST_SS(&wf.T[nbuf][slot], eT);
 				if (seen[sampleInBatch] == 0u) // this sample's bounce loop continues (CUDART/src/Context.cpp:109-120)
 				{
 					seen[sampleInBatch] = 1u;
@@ -2403,7 +2429,7 @@ __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, c
 					if (int(lane) == leader)
 						rank = atomicAdd(&wf.sort_hist[bin], uint32_t(__popc(peers)));
 					rank = __shfl_sync(m_ex, rank, leader) + __popc(peers & lt_mask);
-					wf.sort_key[slot] = make_uint2(bin, rank);
+					ST_SS(&wf.sort_key[slot], make_uint2(bin, rank));
 				}
 			}
 		}
@@ -2664,9 +2690,9 @@ __global__ void __launch_bounds__(256) k_sort_move(const WavefrontView wf, const
 	const float4 *__restrict__ sO = wf.O[1], *__restrict__ sD = wf.D[1], *__restrict__ sT = wf.T[1];
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
 	{
-		const uint2 kr = wf.sort_key[i];
+		const uint2 kr = LD_SS(&wf.sort_key[i]);
 		const uint32_t dst = chunk_prefix[kr.x / SORT_CHUNK] + wf.sort_base[kr.x] + kr.y;
-		wf.O[0][dst] = sO[i], wf.D[0][dst] = sD[i], wf.T[0][dst] = sT[i];
+		ST_SS(&wf.O[0][dst], LD_SS(&sO[i])), ST_SS(&wf.D[0][dst], LD_SS(&sD[i])), ST_SS(&wf.T[0][dst], LD_SS(&sT[i]));
 	}
 }
 

@@ -1,6 +1,9 @@
 #!/usr/bin/env python3
 """The short command compute-sanitizer wraps: a Cornell box 128x128, 4 spp, PT-mode frame + one Converge frame +
-an E-mode frame through the C ABI, single context and a 2-rank in-process group (peer stores, flow-control kernels)."""
+an E-mode frame through the C ABI, single context and a 2-rank in-process group (peer stores, flow-control kernels); then the
+feature soup (textures, all light types, instancing) as a two-level scene (k_wavefront_trace_tl, instance normals at shading
+time) and on trees built by the device builders (lbvh, ploc: clustering rounds, depth-first re-ordering, collapse) with a
+device refit behind them."""
 import sys
 from pathlib import Path
 
@@ -24,5 +27,25 @@ for devs in (None, [0, 0]):
         ctx.set_setting("mode", "embree")
         ctx.render_frame(cam, R.RESET)
         print("emode", float(ctx.read_image()[..., :3].mean()))
+    ctx.close()
+for label, settings in (("two-level", {"levels": 2}), ("lbvh", {"builder": "lbvh"}), ("ploc", {"builder": "ploc"}), ("ploc+presplit", {"builder": "ploc", "lbvh_presplit": "on"})):
+    sc = S.feature_soup(600)
+    ctx = R.RenderContext(lib)
+    for k, v in settings.items():
+        ctx.set_setting(k, v)
+    S.upload(ctx, sc, 96, 64)
+    ctx.set_setting("spp", 2)
+    cam = sc.camera(96, 64)
+    ctx.render_frame(cam, R.RESET)
+    img = ctx.read_image()
+    print(label, float(img[..., :3].mean()))
+    mesh, M = sc.instances[1]
+    ctx.set_instance(1, mesh, S.translate(0.05, 0.0, 0.02) @ M)  # two-level: top-level rebuild; device-built trees: device refit
+    ctx.update()
+    ctx.render_frame(cam, R.RESET)
+    if label == "two-level":
+        ctx.set_setting("mode", "embree")
+        ctx.render_frame(cam, R.RESET)
+    print(label, "after a moved instance", float(ctx.read_image()[..., :3].mean()))
     ctx.close()
 print("sanitize_frame ok")
