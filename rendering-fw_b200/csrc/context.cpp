@@ -1694,7 +1694,9 @@ extern "C"
 		CK(cudaStreamSynchronize(c->stream)); // the staging vectors die here
 		c->scene.nodes = c->d_nodes.as<BvhNode4>(), c->scene.tris = c->d_tris.as<TriRec>(), c->scene.shade_tris = c->d_shade_tris.as<ShadeTri>();
 		c->scene.node_count = uint32_t(nn), c->scene.tri_count = uint32_t(nr);
-		c->scene.nodes16 = nullptr, c->scene.cw_nodes = nullptr, c->scene.cw_node_count = 0;
+		c->scene.cw_nodes = nullptr, c->scene.cw_node_count = 0;
+		if (int r = pack_nodes(c)) // the 80-byte form of every tree (top level and meshes alike) for the wavefront kernel
+			return r;
 		c->scene.tl_instances = c->d_tl_instances.as<TlInstance>(), c->scene.tl_instance_count = uint32_t(c->instances.size());
 		c->flat_tri_count = ntri;
 		c->two_level = true, c->tl_depth = top_depth + deepest;

@@ -912,7 +912,11 @@ __device__ __forceinline__ void close_launch(const RenderSettings &rs, DepthCoun
 // STAGE_P: the first rs.smem_nodes PACKED nodes (80 B each: 256 nodes = 20 KB) are staged into shared memory with one TMA bulk copy
 // per CTA, and node fetches below that index read shared memory (setting smem_nodes with the packed variants; measured in
 // profiles/r02 against the L1-only default).
-template <bool PRIMARY, int LQ, int LEAN, bool PACKED, bool STAGE_P = false>
+// TL: the scene is two-level (TlInstance, device_types.h).  A top-level leaf names one instance; "intersecting" it means moving
+// the ray into the instance's object space, pushing a marker that brings the world ray back, and descending the mesh's tree —
+// all in the same while-while loop, on the same stack.  A lane that holds a postponed leaf of an instance stops at that
+// instance's marker (the leaf's triangles must be tested with the object-space ray), exactly as it stops at a second leaf.
+template <bool PRIMARY, int LQ, int LEAN, bool PACKED, bool STAGE_P = false, bool TL = false>
 __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const SceneView sc, const ShardView sh, const WavefrontView wf,
 															const RenderSettings rs, const BatchView bv, const uint32_t depth,
 															const uint32_t in_buf)
@@ -967,6 +971,9 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 	uint32_t pidx = 0;				// camera ray: local pixel; connect ray: path index its contribution belongs to
 	bool exhausted = false; // warp-uniform: the queue has no more items
 	uint32_t acc_count = 0, n_traced = 0;
+	constexpr int TL_MARKER = 0x7ffffffe;		// stack entry: back to the world ray (below SENTINEL, so the node loop sees it)
+	constexpr uint32_t NO_INSTANCE = 0xffffffffu;
+	uint32_t inst = NO_INSTANCE, hit_inst = 0; // TL: instance whose tree the lane is in; instance of the closest hit
 	uint32_t chunk_pos = 0, chunk_end = 0; // warp-uniform: the run of queue entries this warp is working through
 	const uint32_t chunk_len = uint32_t(rs.fetch_chunk);
 
@@ -1005,13 +1012,18 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 					fetch_ray<PRIMARY>(sc, sh, wf, rs, bv, fp, q, depth, in_buf, item, o, d, tmin, tmax, shadow, pidx, occluder, occ_slot, n_traced))
 				{
 					dbg_rays++;
-					const float tiny = 1e-30f;
-					idx = 1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));
-					idy = 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));
-					idz = 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
-					oodx = o.x * idx, oody = o.y * idy, oodz = o.z * idz;
-					sgx = idx < 0.0f ? 1u : 0u, sgy = idy < 0.0f ? 1u : 0u, sgz = idz < 0.0f ? 1u : 0u;
+#define RFW_LANE_RAY_SETUP()                                                                                            \
+	{                                                                                                                   \
+		const float tiny = 1e-30f;                                                                                      \
+		idx = 1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));                                                  \
+		idy = 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));                                                  \
+		idz = 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));                                                  \
+		oodx = o.x * idx, oody = o.y * idy, oodz = o.z * idz;                                                           \
+		sgx = idx < 0.0f ? 1u : 0u, sgy = idy < 0.0f ? 1u : 0u, sgz = idz < 0.0f ? 1u : 0u;                             \
+	}
+					RFW_LANE_RAY_SETUP()
 					stack[0] = SENTINEL;
+					inst = NO_INSTANCE, hit_inst = 0;
 					sp = 1, cur = 0, leaf = leaf1 = leaf2 = NO_LEAF, hit_tri = 0xffffffffu, hit_u = 0.f, hit_v = 0.f;
 					alive = true;
 				}
@@ -1026,8 +1038,25 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 			{
 				// descend inner nodes; the first leaf a lane meets is postponed and the lane keeps descending
 				// (speculatively) so it stays useful until every lane of the warp holds a leaf
-				while (uint32_t(cur) < uint32_t(SENTINEL))
+				while (uint32_t(cur) < uint32_t(SENTINEL) && !(TL && cur == TL_MARKER && leaf != NO_LEAF))
 				{
+					if (TL && cur == TL_MARKER)
+					{
+						// the instance's subtree is exhausted: the world ray again, from the queue entry it came from
+						float4 O4, D4;
+						if (PRIMARY)
+							O4 = wf.O[in_buf][item], D4 = wf.D[in_buf][item];
+						else if (!shadow)
+							O4 = q.Oin[item], D4 = q.Din[item];
+						else
+							O4 = wf.sO[item - q.n_ext], D4 = wf.sD[item - q.n_ext];
+						o = mk(O4.x, O4.y, O4.z), d = mk(D4.x, D4.y, D4.z);
+						RFW_LANE_RAY_SETUP()
+						inst = NO_INSTANCE;
+						cur = stack[--sp];
+					}
+					else
+					{
 					struct
 					{
 						int4 child;
@@ -1148,6 +1177,7 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 							stack[sp++] = PICK(key1);
 						}
 					}
+					} // node step
 					// hold back up to LQ leaves and keep descending
 					if (cur < 0 && leaf == NO_LEAF)
 					{
@@ -1171,6 +1201,25 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 				while (leaf != NO_LEAF)
 				{
 					const uint32_t v = uint32_t(~leaf), first = v >> 2, cnt = (v & 3u) + 1u;
+					if (TL && inst == NO_INSTANCE)
+					{
+						// top-level leaf: enter the instance (Kernels.cu:229-232,270-272: the direction is not re-normalised, so t
+						// stays the world distance).  What the lane had lined up next waits below the marker.
+						inst = first;
+						const float4 *ip = reinterpret_cast<const float4 *>(sc.tl_instances + inst);
+						const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2);
+						const V3 wo = o, wd = d;
+						o = mk(r0.x * wo.x + r0.y * wo.y + r0.z * wo.z + r0.w, r1.x * wo.x + r1.y * wo.y + r1.z * wo.z + r1.w,
+							   r2.x * wo.x + r2.y * wo.y + r2.z * wo.z + r2.w);
+						d = mk(r0.x * wd.x + r0.y * wd.y + r0.z * wd.z, r1.x * wd.x + r1.y * wd.y + r1.z * wd.z,
+							   r2.x * wd.x + r2.y * wd.y + r2.z * wd.z);
+						RFW_LANE_RAY_SETUP()
+						stack[sp++] = cur;
+						stack[sp++] = TL_MARKER;
+						cur = int(__ldg(&sc.tl_instances[inst].blas_root));
+						leaf = NO_LEAF;
+						break;
+					}
 					for (uint32_t i = 0; i < cnt; i++)
 					{
 						const float4 a = __ldg(tris + size_t(first + i) * 3 + 0);
@@ -1195,6 +1244,8 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 						if (t > tmin && tmax > t)
 						{
 							tmax = t, hit_u = u, hit_v = vv, hit_tri = __float_as_uint(c.y);
+							if (TL)
+								hit_inst = inst;
 							if (PRIMARY)
 								hit_pos = first + i;
 							if (shadow)
@@ -1227,7 +1278,7 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 		if (alive && finished)
 		{
 			alive = false;
-			retire_ray(wf, q, item, shadow, hit_tri, hit_u, hit_v, tmax, pidx, acc_count);
+			retire_ray(wf, q, item, shadow, hit_tri, hit_u, hit_v, tmax, pidx, acc_count, hit_inst);
 			if (PRIMARY && rs.primary_cache)
 				wf.prim_cache[pidx] = hit_tri != 0xffffffffu ? hit_pos : 0xffffffffu;
 		}
@@ -3058,7 +3109,8 @@ cudaError_t configure_launches(const RenderSettings &rs, uint32_t node_count, La
 									(const void *)k_wavefront_trace<true, 1, 3, true>,	 (const void *)k_wavefront_trace<false, 1, 3, true>,
 									(const void *)k_wavefront_trace<true, 1, 4, true>,	 (const void *)k_wavefront_trace<false, 1, 4, true>,
 									(const void *)k_wavefront_trace_cw<true>,			 (const void *)k_wavefront_trace_cw<false>,
-									(const void *)k_wavefront_trace_tl<true>,			 (const void *)k_wavefront_trace_tl<false>};
+									(const void *)k_wavefront_trace_tl<true>,			 (const void *)k_wavefront_trace_tl<false>,
+									(const void *)k_wavefront_trace<true, 1, 2, true, false, true>, (const void *)k_wavefront_trace<false, 1, 2, true, false, true>};
 		for (const void *k : l1_kernels)
 		{
 			e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
@@ -3116,7 +3168,12 @@ cudaError_t launch_primary(const SceneView &sc, const ShardView &sh, const Wavef
 {
 	if (sc.tl_instances != nullptr)
 	{
-		k_wavefront_trace_tl<true><<<dims.trace_grid, dims.trace_block, 0, stream>>>(sc, sh, wf, rs, bv, 0u, 0u);
+		// two-level scene: the while-while kernel with the instance step (packed nodes), or — primary_variant 0 — the plain
+		// one-ray-per-lane kernel around traverse_tl
+		if (rs.primary_variant == 0 || sc.nodes16 == nullptr)
+			k_wavefront_trace_tl<true><<<dims.trace_grid, dims.trace_block, 0, stream>>>(sc, sh, wf, rs, bv, 0u, 0u);
+		else
+			k_wavefront_trace<true, 1, 2, true, false, true><<<dims.trace_grid, dims.trace_block, 0, stream>>>(sc, sh, wf, rs, bv, 0u, 0u);
 		return cudaGetLastError();
 	}
 	if (sc.cw_nodes != nullptr)
@@ -3153,7 +3210,10 @@ cudaError_t launch_trace(const SceneView &sc, const ShardView &sh, const Wavefro
 {
 	if (sc.tl_instances != nullptr)
 	{
-		k_wavefront_trace_tl<false><<<dims.trace_grid, dims.trace_block, 0, stream>>>(sc, sh, wf, rs, bv, depth, in_buf);
+		if (rs.trace_variant == 0 || sc.nodes16 == nullptr)
+			k_wavefront_trace_tl<false><<<dims.trace_grid, dims.trace_block, 0, stream>>>(sc, sh, wf, rs, bv, depth, in_buf);
+		else
+			k_wavefront_trace<false, 1, 2, true, false, true><<<dims.trace_grid, dims.trace_block, 0, stream>>>(sc, sh, wf, rs, bv, depth, in_buf);
 		return cudaGetLastError();
 	}
 	if (sc.cw_nodes != nullptr)

@@ -124,6 +124,23 @@ def test_two_level_settings_do_not_change_the_frame(product_lib):
         assert np.array_equal(img, ref), extra
 
 
+@pytest.mark.parametrize("scene", ["cornell", "soup"])
+def test_both_two_level_kernels_render_the_same_frame(product_lib, scene):
+    """Default: the while-while wavefront kernel with the instance step (packed nodes).  trace_variant 0: the plain
+    one-ray-per-lane kernel around traverse_tl (fp32 nodes).  Same rays, same object-space triangle tests; packed boxes only
+    contain the exact ones, so the frames differ at most where two triangles tie."""
+    W, H, spp = 192, 128, 4
+    a, sc = product(product_lib, SCENES[scene], W, H, levels=2, spp=spp)
+    b, _ = product(product_lib, SCENES[scene], W, H, levels=2, spp=spp, trace_variant=0)
+    cam = sc.camera(W, H)
+    a.render_frame(cam, R.RESET), b.render_frame(cam, R.RESET)
+    ia, ib = a.read_image(), b.read_image()
+    assert (np.abs(ia - ib).max(axis=-1) > 0).mean() < 2e-3
+    ca, cb = a.get_frame_counters().as_dict(), b.get_frame_counters().as_dict()
+    for k in ("n_ext", "n_shade", "n_nee"):
+        assert abs(ca[k] - cb[k]) <= 1e-3 * cb[k] + 2
+
+
 def test_moving_an_instance_rebuilds_the_top_level_only(product_lib, oracle_lib):
     W, H = 160, 120
     g, sc = product(product_lib, SCENES["cornell"], W, H, levels=2)
