@@ -252,10 +252,18 @@ struct rfwb200_context
 	int levels_setting = 0;				   // 0 = auto (default): two levels when the flattened scene would exceed flatten_budget triangles
 	uint64_t flatten_budget = 1ull << 26;  // setting "flatten_budget" (flattened triangles; 2^26 of them are ~15 GB of records and nodes)
 	bool two_level = false;				   // the committed device scene is two-level
-	std::vector<BvhBuildResult> blas;	   // one object-space tree per mesh (kept across updates: only changed meshes are rebuilt)
-	std::vector<uint8_t> blas_valid;
-	DevBuf d_tl_instances;
-	int tl_depth = 0; // top-level depth + deepest mesh tree
+	struct GroupTree // one object-space tree over all meshes that share their list of placements (update_two_level)
+	{
+		std::vector<uint32_t> members;				   // mesh indices, ascending
+		std::vector<uint32_t> tri_mesh_rank, tri_index; // group triangle -> (member rank, triangle of that mesh)
+		BvhBuildResult bvh;
+	};
+	std::vector<GroupTree> group_trees; // kept across updates: a group is rebuilt only when its members or their geometry change
+	std::vector<TlInstance> tl_table;	// host copies for the stage-level entry points
+	std::vector<uint32_t> tl_inst_map;
+	DevBuf d_tl_instances, d_tl_inst_map;
+	int tl_depth = 0; // top-level depth + deepest group tree
+	uint32_t tl_groups = 0;
 
 	// ---- wavefront state -----------------------------------------------------------------------------
 	// One wavefront carries up to `batch_spp` samples of every local pixel (BatchView); the planes hold local_pixels *
@@ -274,6 +282,7 @@ struct rfwb200_context
 	size_t items_capacity = 0;		// work items the wavefront planes are allocated for
 	int spp_batch = 0;				// setting "spp_batch": samples per wavefront, 0 = as many as fit (<= MAX_BATCH_SPP, <= 2^24 items)
 	uint32_t sort_bins_allocated = 0;
+	bool sort_grid_dirty = true; // the bin grid (k_sort_setup: from the root of the current tree) is computed once per scene change, not per frame
 
 	// ---- display target of a sharded frame (DisplayTarget, device_types.h) and in-process device groups ----
 	struct Display
@@ -393,6 +402,7 @@ int alloc_wavefront(Ctx *c)
 	w.occ_cache = c->d_occ_cache.as<uint32_t>();
 	w.frame = c->d_frame.as<FrameParams>();
 	w.grid = c->d_sort_grid.as<SortGrid>();
+	c->sort_grid_dirty = true;
 	return RFWB200_OK;
 }
 
@@ -1311,7 +1321,8 @@ extern "C"
 				return update_two_level(c);
 			if (c->two_level) // back to the flattened form: nothing of the two-level scene is reused
 			{
-				c->two_level = false, c->scene.tl_instances = nullptr, c->scene.tl_instance_count = 0;
+				c->two_level = false, c->scene.tl_instances = nullptr, c->scene.tl_instance_count = 0, c->scene.tl_inst_map = nullptr;
+				c->group_trees.clear(), c->tl_table.clear(), c->tl_inst_map.clear();
 				c->bvh = BvhBuildResult();
 				c->arena_valid = false, c->topology_dirty = true, c->device_built = false;
 				c->built_layout.clear();
@@ -1354,7 +1365,7 @@ extern "C"
 			if (int r = device_generate(c, true))
 				return r;
 			c->refits++, c->last_update_on_device = true, c->last_update_was_refit = true;
-			c->geometry_dirty = false;
+			c->geometry_dirty = false, c->sort_grid_dirty = true;
 			return RFWB200_OK;
 		}
 		CK(cudaStreamSynchronize(c->stream));
@@ -1409,7 +1420,7 @@ extern "C"
 			c->device_built = true, c->device_depth = depth;
 			c->built_layout = layout, c->built_tri_count = total;
 			c->builds++, c->last_update_on_device = true, c->last_update_was_refit = false;
-			c->geometry_dirty = false, c->topology_dirty = false;
+			c->geometry_dirty = false, c->topology_dirty = false, c->sort_grid_dirty = true;
 			c->dims_valid = false;
 			return RFWB200_OK;
 		}
@@ -1490,16 +1501,22 @@ extern "C"
 		if (!device)
 			if (int r = pack_nodes(c))
 				return r;
-		c->geometry_dirty = false, c->topology_dirty = false;
+		c->geometry_dirty = false, c->topology_dirty = false, c->sort_grid_dirty = true;
 		c->dims_valid = false; // node count may have changed the staged prefix
 		return RFWB200_OK;
 	}
 
-	// Two-level commit (setting "levels"): one object-space tree per mesh (host SBVH, rebuilt only for meshes that changed), a
-	// top-level tree over the instances' world boxes, per-mesh intersection and shading records, and the instance table
-	// with the inverse transforms.  Memory is that of the unique meshes plus 96 B + a share of a node per instance —
-	// what the reference keeps (CUDART/src/Context.cpp:270-311,394-456), and the fallback for scenes whose flattened
-	// form would not fit.  A moved instance costs a top-level rebuild on the host (microseconds per thousand instances).
+	// Two-level commit (setting "levels"): object-space trees below a top-level tree over instances — what the reference keeps
+	// (CUDART/src/Context.cpp:270-311,394-456), and the fallback for scenes whose flattened form would not fit.
+	//
+	// The reference builds one tree per MESH, so a model of 394 meshes instanced 38 times is 14,972 overlapping instance boxes
+	// a ray has to enter one after the other.  Here the unit below the top level is a GROUP: all meshes that are instanced
+	// with exactly the same list of (transform, normal matrix) pairs share one object space, so their triangles go into ONE
+	// tree and every entry of the list becomes ONE top-level instance (the 394 x 38 model: one tree of 262 k triangles, 38
+	// instances; a model loaded once under a common transform: one tree, one instance — the speed of the flattened form at
+	// the memory of the unique meshes).  A hit names (top-level instance, mesh triangle); the (instance, primitive) pair the
+	// caller knows is looked up in a small table (tl_inst_map).  Group trees are cached by their member meshes: moving an
+	// instance rebuilds the top level only, on the host (microseconds per thousand instances).
 	static int update_two_level(rfwb200_context *c)
 	{
 		REQUIRE(!c->wide8, "bvh=8 is a flattened layout: use levels=1");
@@ -1508,198 +1525,285 @@ extern "C"
 		CK(cudaStreamSynchronize(c->stream));
 		const size_t nm = c->meshes.size();
 		c->mesh_dirty.resize(nm, 1);
-		c->blas.resize(nm);
-		c->blas_valid.resize(nm, 0);
 		for (size_t mi = 0; mi < nm; mi++)
-			if (c->mesh_dirty[mi] || !c->blas_valid[mi])
+			if (c->mesh_dirty[mi])
 				for (const rfwb200_triangle &t : c->meshes[mi].triangles)
 					if (t.material >= c->materials_raw.size())
 						return set_error(RFWB200_ERR_INVALID, "mesh " + std::to_string(mi) + " references material " + std::to_string(t.material) +
 																  " but only " + std::to_string(c->materials_raw.size()) + " materials were set");
 		const auto t0 = std::chrono::steady_clock::now();
 		const int threads = int(std::max(1u, std::thread::hardware_concurrency()));
-		std::vector<BuildTriangle> bt;
-		for (size_t mi = 0; mi < nm; mi++)
+
+		// ---- groups: meshes with identical sorted lists of (transform, normal matrix) -----------------------------------------
+		struct Placement
 		{
-			if (!c->mesh_dirty[mi] && c->blas_valid[mi])
+			float m[25]; // transform[16] + normal[9]
+			uint32_t instance;
+		};
+		std::vector<std::vector<Placement>> placed(nm);
+		for (size_t ii = 0; ii < c->instances.size(); ii++)
+		{
+			const HostInstance &in = c->instances[ii];
+			if (in.mesh < 0 || size_t(in.mesh) >= nm || c->meshes[in.mesh].triangles.empty())
 				continue;
-			const HostMesh &m = c->meshes[mi];
-			const size_t nt = m.triangles.size(), nv = m.vertices.size() / 4;
-			bt.resize(nt);
-			for (size_t t = 0; t < nt; t++)
-				for (int k = 0; k < 3; k++)
+			Placement pl;
+			memcpy(pl.m, in.transform, sizeof(float) * 16);
+			memcpy(pl.m + 16, in.normal, sizeof(float) * 9);
+			pl.instance = uint32_t(ii);
+			placed[in.mesh].push_back(pl);
+		}
+		auto less_pl = [](const Placement &x, const Placement &y) {
+			const int r = memcmp(x.m, y.m, sizeof(x.m));
+			return r != 0 ? r < 0 : x.instance < y.instance;
+		};
+		for (auto &v : placed)
+			std::sort(v.begin(), v.end(), less_pl);
+		std::vector<size_t> order; // meshes that are placed at all, grouped
+		for (size_t mi = 0; mi < nm; mi++)
+			if (!placed[mi].empty())
+				order.push_back(mi);
+		auto same_list = [&](size_t x, size_t y) {
+			if (placed[x].size() != placed[y].size())
+				return false;
+			for (size_t k = 0; k < placed[x].size(); k++)
+				if (memcmp(placed[x][k].m, placed[y][k].m, sizeof(placed[x][k].m)) != 0)
+					return false;
+			return true;
+		};
+		auto less_list = [&](size_t x, size_t y) {
+			if (placed[x].size() != placed[y].size())
+				return placed[x].size() < placed[y].size();
+			for (size_t k = 0; k < placed[x].size(); k++)
+			{
+				const int r = memcmp(placed[x][k].m, placed[y][k].m, sizeof(placed[x][k].m));
+				if (r != 0)
+					return r < 0;
+			}
+			return x < y;
+		};
+		std::sort(order.begin(), order.end(), less_list);
+		std::vector<std::vector<uint32_t>> groups; // member meshes, ascending
+		for (size_t k = 0; k < order.size(); k++)
+		{
+			if (k == 0 || !same_list(order[k - 1], order[k]))
+				groups.emplace_back();
+			groups.back().push_back(uint32_t(order[k]));
+		}
+		std::sort(groups.begin(), groups.end(), [](const std::vector<uint32_t> &x, const std::vector<uint32_t> &y) { return x[0] < y[0]; });
+
+		// ---- one tree per group, cached by its member list -----------------------------------------------------------------------
+		std::vector<Ctx::GroupTree> trees(groups.size());
+		std::vector<BuildTriangle> bt;
+		for (size_t g = 0; g < groups.size(); g++)
+		{
+			bool reuse = false;
+			for (Ctx::GroupTree &old : c->group_trees)
+				if (old.members == groups[g])
 				{
-					const uint32_t vi = m.indices.empty() ? uint32_t(t * 3 + k) : m.indices[t * 3 + k];
-					if (vi >= nv)
-						return set_error(RFWB200_ERR_INVALID, "mesh index out of range");
-					float *dst = k == 0 ? bt[t].v0 : (k == 1 ? bt[t].v1 : bt[t].v2);
-					dst[0] = m.vertices[4 * vi], dst[1] = m.vertices[4 * vi + 1], dst[2] = m.vertices[4 * vi + 2];
+					reuse = true;
+					for (uint32_t mi : groups[g])
+						reuse = reuse && !c->mesh_dirty[mi];
+					if (reuse)
+						trees[g] = std::move(old), old.members.clear();
+					break;
 				}
-			build_bvh4(bt.data(), nt, threads, c->blas[mi], c->spatial_splits);
-			c->blas_valid[mi] = 1, c->mesh_dirty[mi] = 0;
+			if (reuse)
+				continue;
+			Ctx::GroupTree &gt = trees[g];
+			gt.members = groups[g];
+			size_t total = 0;
+			for (uint32_t mi : groups[g])
+				total += c->meshes[mi].triangles.size();
+			bt.resize(total);
+			gt.tri_mesh_rank.resize(total), gt.tri_index.resize(total);
+			size_t at = 0;
+			for (size_t r = 0; r < groups[g].size(); r++)
+			{
+				const HostMesh &m = c->meshes[groups[g][r]];
+				const size_t nt = m.triangles.size(), nv = m.vertices.size() / 4;
+				for (size_t t = 0; t < nt; t++, at++)
+				{
+					for (int k = 0; k < 3; k++)
+					{
+						const uint32_t vi = m.indices.empty() ? uint32_t(t * 3 + k) : m.indices[t * 3 + k];
+						if (vi >= nv)
+							return set_error(RFWB200_ERR_INVALID, "mesh index out of range");
+						float *dst = k == 0 ? bt[at].v0 : (k == 1 ? bt[at].v1 : bt[at].v2);
+						dst[0] = m.vertices[4 * vi], dst[1] = m.vertices[4 * vi + 1], dst[2] = m.vertices[4 * vi + 2];
+					}
+					gt.tri_mesh_rank[at] = uint32_t(r), gt.tri_index[at] = uint32_t(t);
+				}
+			}
+			build_bvh4(bt.data(), total, threads, gt.bvh, c->spatial_splits);
 			c->builds++;
 		}
-		// ---- layout: [top-level nodes][mesh 0 nodes][mesh 1 nodes]... ; records and shading records per mesh, back to back
-		std::vector<uint32_t> valid_ids;
-		std::vector<float> boxes;
-		std::vector<float> mesh_box(nm * 6);
-		std::vector<uint8_t> mesh_empty(nm, 1);
-		int deepest = 0;
+		c->group_trees = std::move(trees);
+		std::fill(c->mesh_dirty.begin(), c->mesh_dirty.end(), uint8_t(0));
+
+		// ---- layout: [top-level nodes][group 0 nodes][group 1 nodes]...; records per group reference; shading records per mesh triangle
+		std::vector<uint32_t> tri_base(nm, 0);
+		size_t ntri = 0;
 		for (size_t mi = 0; mi < nm; mi++)
+			tri_base[mi] = uint32_t(ntri), ntri += c->meshes[mi].triangles.size();
+		std::vector<float> boxes;
+		std::vector<TlInstance> table;
+		std::vector<uint32_t> inst_map;
+		std::vector<uint32_t> table_group;
+		int deepest = 0;
+		for (size_t g = 0; g < groups.size(); g++)
 		{
-			float *b = &mesh_box[6 * mi];
-			for (int a = 0; a < 3; a++)
-				b[a] = 3.0e38f, b[3 + a] = -3.0e38f;
-			if (c->meshes[mi].triangles.empty() || c->blas[mi].nodes.empty())
-				continue;
-			const BvhNode4 &root = c->blas[mi].nodes[0];
+			const Ctx::GroupTree &gt = c->group_trees[g];
+			deepest = std::max(deepest, gt.bvh.depth);
+			float b[6] = {3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};
+			const BvhNode4 &root = gt.bvh.nodes[0];
 			for (int s = 0; s < root.pad[0]; s++)
 			{
 				b[0] = std::min(b[0], root.minx[s]), b[1] = std::min(b[1], root.miny[s]), b[2] = std::min(b[2], root.minz[s]);
 				b[3] = std::max(b[3], root.maxx[s]), b[4] = std::max(b[4], root.maxy[s]), b[5] = std::max(b[5], root.maxz[s]);
 			}
-			mesh_empty[mi] = b[0] <= b[3] ? 0 : 1;
-			deepest = std::max(deepest, c->blas[mi].depth);
-		}
-		for (size_t ii = 0; ii < c->instances.size(); ii++)
-		{
-			const HostInstance &in = c->instances[ii];
-			if (in.mesh < 0 || size_t(in.mesh) >= nm || mesh_empty[in.mesh])
-				continue;
-			const float *b = &mesh_box[6 * size_t(in.mesh)];
-			float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-			for (int corner = 0; corner < 8; corner++)
+			const std::vector<Placement> &list = placed[groups[g][0]];
+			for (size_t j = 0; j < list.size(); j++)
 			{
-				const float p[3] = {b[(corner & 1) ? 3 : 0], b[(corner & 2) ? 4 : 1], b[(corner & 4) ? 5 : 2]};
-				float w[3];
-				mul_point(in.transform, p, w);
+				const float *M = list[j].m;
+				float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+				for (int corner = 0; corner < 8; corner++)
+				{
+					const float p[3] = {b[(corner & 1) ? 3 : 0], b[(corner & 2) ? 4 : 1], b[(corner & 4) ? 5 : 2]};
+					float w[3];
+					mul_point(M, p, w);
+					for (int a = 0; a < 3; a++)
+						lo[a] = std::min(lo[a], w[a]), hi[a] = std::max(hi[a], w[a]);
+				}
+				// a float step of slack per coordinate: the object-space walk rounds differently from a world-space box test
 				for (int a = 0; a < 3; a++)
-					lo[a] = std::min(lo[a], w[a]), hi[a] = std::max(hi[a], w[a]);
+					boxes.push_back(lo[a] - (4e-7f * std::max(std::fabs(lo[a]), std::fabs(hi[a])) + 1e-30f));
+				for (int a = 0; a < 3; a++)
+					boxes.push_back(hi[a] + (4e-7f * std::max(std::fabs(lo[a]), std::fabs(hi[a])) + 1e-30f));
+				TlInstance ti;
+				memset(&ti, 0, sizeof(ti));
+				// inverse of the affine transform (column-major M), in double, rounded once
+				const double a = M[0], bb = M[4], cc = M[8], d = M[1], e = M[5], f = M[9], gg = M[2], h = M[6], k = M[10];
+				const double det = a * (e * k - f * h) - bb * (d * k - f * gg) + cc * (d * h - e * gg);
+				REQUIRE(det != 0.0, "instance " + std::to_string(list[j].instance) + " has a singular transform");
+				const double id = 1.0 / det;
+				const double r[3][3] = {{(e * k - f * h) * id, (cc * h - bb * k) * id, (bb * f - cc * e) * id},
+										{(f * gg - d * k) * id, (a * k - cc * gg) * id, (cc * d - a * f) * id},
+										{(d * h - e * gg) * id, (bb * gg - a * h) * id, (a * e - bb * d) * id}};
+				const double tx = M[12], ty = M[13], tz = M[14];
+				for (int row = 0; row < 3; row++)
+				{
+					ti.inv[4 * row + 0] = float(r[row][0]), ti.inv[4 * row + 1] = float(r[row][1]), ti.inv[4 * row + 2] = float(r[row][2]);
+					ti.inv[4 * row + 3] = float(-(r[row][0] * tx + r[row][1] * ty + r[row][2] * tz));
+				}
+				memcpy(ti.normal, M + 16, sizeof(ti.normal));
+				ti.pad[0] = uint32_t(inst_map.size()); // first entry of this instance's (mesh rank -> caller's instance) row
+				for (uint32_t mi : groups[g])
+					inst_map.push_back(placed[mi][j].instance);
+				table.push_back(ti);
+				table_group.push_back(uint32_t(g));
 			}
-			// one float step of slack per coordinate: the object-space walk rounds differently from a world-space box test
-			for (int a = 0; a < 3; a++)
-			{
-				const float pad = 4e-7f * std::max(std::fabs(lo[a]), std::fabs(hi[a])) + 1e-30f;
-				boxes.push_back(lo[a] - pad);
-			}
-			for (int a = 0; a < 3; a++)
-			{
-				const float pad = 4e-7f * std::max(std::fabs(lo[a]), std::fabs(hi[a])) + 1e-30f;
-				boxes.push_back(hi[a] + pad);
-			}
-			valid_ids.push_back(uint32_t(ii));
 		}
 		std::vector<BvhNode4> nodes;
-		const int top_depth = build_tlas4(boxes.data(), valid_ids.size(), nodes);
-		for (BvhNode4 &n : nodes)
-			for (int s = 0; s < n.pad[0]; s++)
-				if (n.child[s] < 0)
-					n.child[s] = ~int32_t(valid_ids[uint32_t(~n.child[s]) >> 2] << 2);
+		const int top_depth = build_tlas4(boxes.data(), table.size(), nodes);
 		const size_t top_nodes = nodes.size();
-		std::vector<uint32_t> node_base(nm, 0), ref_base(nm, 0), tri_base(nm, 0);
-		size_t nn = top_nodes, nr = 0, ntri = 0;
-		for (size_t mi = 0; mi < nm; mi++)
+		std::vector<uint32_t> node_base(groups.size(), 0), ref_base(groups.size(), 0);
+		size_t nn = top_nodes, nr = 0;
+		for (size_t g = 0; g < groups.size(); g++)
 		{
-			node_base[mi] = uint32_t(nn), ref_base[mi] = uint32_t(nr), tri_base[mi] = uint32_t(ntri);
-			nn += c->blas[mi].nodes.size(), nr += c->blas[mi].tri_order.size(), ntri += c->meshes[mi].triangles.size();
+			node_base[g] = uint32_t(nn), ref_base[g] = uint32_t(nr);
+			nn += c->group_trees[g].bvh.nodes.size(), nr += c->group_trees[g].bvh.tri_order.size();
 		}
 		REQUIRE(nn < (1ull << 30) && nr < (1ull << 29) && ntri < (1ull << 31), "two-level scene exceeds the 32-bit node / reference encoding");
-		REQUIRE(c->instances.size() < (1ull << 29), "too many instances");
+		REQUIRE(table.size() < (1ull << 29), "too many instances");
 		if (3 * (top_depth + deepest) + 3 > TRAVERSAL_STACK)
 			return set_error(RFWB200_ERR_INVALID, "two-level scene deeper than the traversal stack allows");
+		for (size_t i = 0; i < table.size(); i++)
+			table[i].blas_root = node_base[table_group[i]];
 		nodes.resize(nn);
 		std::vector<TriRec> recs(std::max<size_t>(nr, 1));
 		std::vector<ShadeTri> shade(std::max<size_t>(ntri, 1));
 		memset(recs.data(), 0, recs.size() * sizeof(TriRec));
 		memset(shade.data(), 0, shade.size() * sizeof(ShadeTri));
-		for (size_t mi = 0; mi < nm; mi++)
+		for (size_t g = 0; g < groups.size(); g++)
 		{
-			const BvhBuildResult &b = c->blas[mi];
-			const HostMesh &m = c->meshes[mi];
+			const Ctx::GroupTree &gt = c->group_trees[g];
+			const BvhBuildResult &b = gt.bvh;
 			for (size_t k = 0; k < b.nodes.size(); k++)
 			{
 				BvhNode4 n = b.nodes[k];
 				for (int s = 0; s < n.pad[0]; s++)
 				{
 					if (n.child[s] >= 0)
-						n.child[s] += int32_t(node_base[mi]);
+						n.child[s] += int32_t(node_base[g]);
 					else
 					{
 						const uint32_t v = uint32_t(~n.child[s]);
-						n.child[s] = ~int32_t((((v >> 2) + ref_base[mi]) << 2) | (v & 3u));
+						n.child[s] = ~int32_t((((v >> 2) + ref_base[g]) << 2) | (v & 3u));
 					}
 				}
-				nodes[node_base[mi] + k] = n;
+				nodes[node_base[g] + k] = n;
 			}
 			for (size_t i = 0; i < b.tri_order.size(); i++)
 			{
-				const uint32_t t = b.tri_order[i];
+				const uint32_t gt_tri = b.tri_order[i];
+				const uint32_t mi = groups[g][gt.tri_mesh_rank[gt_tri]], t = gt.tri_index[gt_tri];
+				const HostMesh &m = c->meshes[mi];
 				uint32_t vi[3];
 				for (int k = 0; k < 3; k++)
 					vi[k] = m.indices.empty() ? uint32_t(t * 3 + k) : m.indices[t * 3 + k];
 				const float *v0 = &m.vertices[4 * vi[0]], *v1 = &m.vertices[4 * vi[1]], *v2 = &m.vertices[4 * vi[2]];
-				TriRec &r = recs[ref_base[mi] + i];
+				TriRec &r = recs[ref_base[g] + i];
 				r.p0x = v0[0], r.p0y = v0[1], r.p0z = v0[2];
 				r.e1x = v1[0] - v0[0], r.e1y = v1[1] - v0[1], r.e1z = v1[2] - v0[2];
 				r.e2x = v2[0] - v0[0], r.e2y = v2[1] - v0[1], r.e2z = v2[2] - v0[2];
 				r.shade_idx = tri_base[mi] + t;
 				r.det_eps = 1e-6f; // T_EPSILON, tested in object space like the reference (CUDAIntersect.h:61-63)
 			}
-			for (size_t t = 0; t < m.triangles.size(); t++)
+			for (size_t rank = 0; rank < groups[g].size(); rank++)
 			{
-				const rfwb200_triangle &src = m.triangles[t];
-				ShadeTri &st = shade[tri_base[mi] + t];
-				st.u0 = src.u0, st.u1 = src.u1, st.u2 = src.u2, st.light_tri_idx = src.light_tri_idx;
-				st.v0 = src.v0, st.v1 = src.v1, st.v2 = src.v2, st.material = src.material;
-				st.n0x = src.vN0[0], st.n0y = src.vN0[1], st.n0z = src.vN0[2];
-				st.n1x = src.vN1[0], st.n1y = src.vN1[1], st.n1z = src.vN1[2];
-				st.n2x = src.vN2[0], st.n2y = src.vN2[1], st.n2z = src.vN2[2];
-				st.Nx = src.Nx, st.Ny = src.Ny, st.Nz = src.Nz; // the instance's normal matrix is applied when the hit is shaded
-				st.area = src.area, st.lod = src.LOD;
-				st.inst_id = 0, st.prim_id = uint32_t(t);
+				const uint32_t mi = groups[g][rank];
+				const HostMesh &m = c->meshes[mi];
+				for (size_t t = 0; t < m.triangles.size(); t++)
+				{
+					const rfwb200_triangle &src = m.triangles[t];
+					ShadeTri &st = shade[tri_base[mi] + t];
+					st.u0 = src.u0, st.u1 = src.u1, st.u2 = src.u2, st.light_tri_idx = src.light_tri_idx;
+					st.v0 = src.v0, st.v1 = src.v1, st.v2 = src.v2, st.material = src.material;
+					st.n0x = src.vN0[0], st.n0y = src.vN0[1], st.n0z = src.vN0[2];
+					st.n1x = src.vN1[0], st.n1y = src.vN1[1], st.n1z = src.vN1[2];
+					st.n2x = src.vN2[0], st.n2y = src.vN2[1], st.n2z = src.vN2[2];
+					st.Nx = src.Nx, st.Ny = src.Ny, st.Nz = src.Nz; // the instance's normal matrix is applied when the hit is shaded
+					st.area = src.area, st.lod = src.LOD;
+					st.inst_id = uint32_t(rank); // column of the instance's row in tl_inst_map
+					st.prim_id = uint32_t(t);
+				}
 			}
 		}
-		std::vector<TlInstance> table(std::max<size_t>(c->instances.size(), 1));
-		memset(table.data(), 0, table.size() * sizeof(TlInstance));
-		for (uint32_t ii : valid_ids)
-		{
-			const HostInstance &in = c->instances[ii];
-			TlInstance &ti = table[ii];
-			// inverse of the affine transform (column-major M), in double, rounded once
-			const float *M = in.transform;
-			const double a = M[0], b = M[4], cc = M[8], d = M[1], e = M[5], f = M[9], g = M[2], h = M[6], k = M[10];
-			const double det = a * (e * k - f * h) - b * (d * k - f * g) + cc * (d * h - e * g);
-			REQUIRE(det != 0.0, "instance " + std::to_string(ii) + " has a singular transform");
-			const double id = 1.0 / det;
-			const double r[3][3] = {{(e * k - f * h) * id, (cc * h - b * k) * id, (b * f - cc * e) * id},
-									{(f * g - d * k) * id, (a * k - cc * g) * id, (cc * d - a * f) * id},
-									{(d * h - e * g) * id, (b * g - a * h) * id, (a * e - b * d) * id}};
-			const double tx = M[12], ty = M[13], tz = M[14];
-			for (int row = 0; row < 3; row++)
-			{
-				ti.inv[4 * row + 0] = float(r[row][0]), ti.inv[4 * row + 1] = float(r[row][1]), ti.inv[4 * row + 2] = float(r[row][2]);
-				ti.inv[4 * row + 3] = float(-(r[row][0] * tx + r[row][1] * ty + r[row][2] * tz));
-			}
-			memcpy(ti.normal, in.normal, sizeof(ti.normal));
-			ti.blas_root = node_base[in.mesh];
-		}
+		if (table.empty())
+			table.emplace_back(), memset(&table[0], 0, sizeof(TlInstance));
+		if (inst_map.empty())
+			inst_map.push_back(0);
 		CK(c->d_nodes.reserve(nodes.size() * sizeof(BvhNode4)));
 		CK(c->d_tris.reserve(recs.size() * sizeof(TriRec)));
 		CK(c->d_shade_tris.reserve(shade.size() * sizeof(ShadeTri)));
 		CK(c->d_tl_instances.reserve(table.size() * sizeof(TlInstance)));
+		CK(c->d_tl_inst_map.reserve(inst_map.size() * sizeof(uint32_t)));
 		CK(cudaMemcpyAsync(c->d_nodes.ptr, nodes.data(), nodes.size() * sizeof(BvhNode4), cudaMemcpyHostToDevice, c->stream));
 		CK(cudaMemcpyAsync(c->d_tris.ptr, recs.data(), recs.size() * sizeof(TriRec), cudaMemcpyHostToDevice, c->stream));
 		CK(cudaMemcpyAsync(c->d_shade_tris.ptr, shade.data(), shade.size() * sizeof(ShadeTri), cudaMemcpyHostToDevice, c->stream));
 		CK(cudaMemcpyAsync(c->d_tl_instances.ptr, table.data(), table.size() * sizeof(TlInstance), cudaMemcpyHostToDevice, c->stream));
+		CK(cudaMemcpyAsync(c->d_tl_inst_map.ptr, inst_map.data(), inst_map.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
 		CK(cudaStreamSynchronize(c->stream)); // the staging vectors die here
+		c->tl_table = std::move(table), c->tl_inst_map = std::move(inst_map);
 		c->scene.nodes = c->d_nodes.as<BvhNode4>(), c->scene.tris = c->d_tris.as<TriRec>(), c->scene.shade_tris = c->d_shade_tris.as<ShadeTri>();
 		c->scene.node_count = uint32_t(nn), c->scene.tri_count = uint32_t(nr);
 		c->scene.cw_nodes = nullptr, c->scene.cw_node_count = 0;
-		if (int r = pack_nodes(c)) // the 80-byte form of every tree (top level and meshes alike) for the wavefront kernel
+		if (int r = pack_nodes(c)) // the 80-byte form of every tree (top level and groups alike) for the wavefront kernel
 			return r;
-		c->scene.tl_instances = c->d_tl_instances.as<TlInstance>(), c->scene.tl_instance_count = uint32_t(c->instances.size());
+		c->scene.tl_instances = c->d_tl_instances.as<TlInstance>(), c->scene.tl_instance_count = uint32_t(c->tl_table.size());
+		c->scene.tl_inst_map = c->d_tl_inst_map.as<uint32_t>();
 		c->flat_tri_count = ntri;
-		c->two_level = true, c->tl_depth = top_depth + deepest;
+		c->two_level = true, c->tl_depth = top_depth + deepest, c->tl_groups = uint32_t(groups.size());
 		c->bvh = BvhBuildResult();
 		c->bvh.depth = c->tl_depth;
 		c->bvh.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -1707,7 +1811,7 @@ extern "C"
 		c->arena_valid = false, c->built_layout.clear(), c->built_tri_count = 0;
 		c->inst_moved.assign(c->instances.size(), 0);
 		c->last_update_on_device = false, c->last_update_was_refit = false, c->geo_timed = false;
-		c->geometry_dirty = false, c->topology_dirty = false;
+		c->geometry_dirty = false, c->topology_dirty = false, c->sort_grid_dirty = true;
 		c->dims_valid = false;
 		return RFWB200_OK;
 	}
@@ -1933,7 +2037,7 @@ extern "C"
 		{
 			const int n = atoi(v.c_str());
 			REQUIRE(n >= 3 && n <= 6, "sort_cell_bits must be in [3, 6] (grid cells per axis = 2^bits)");
-			c->rs.sort_cell_bits = n;
+			c->rs.sort_cell_bits = n, c->sort_grid_dirty = true;
 		}
 		else if (k == "sort_major")
 		{
@@ -2049,7 +2153,8 @@ extern "C"
 							  "\nsort_major=cell|octant\naov=on|off\nfetch_chunk=" + std::to_string(c->rs.fetch_chunk) + "\nfetch_threshold=" + std::to_string(c->rs.fetch_threshold) +
 							  "\ntrace_variant=" + std::to_string(c->rs.trace_variant) + "\nprimary_variant=" +
 							  std::to_string(c->rs.primary_variant) + "\nbvh=4|8\nbuilder=sbvh|lbvh|ploc\nspatial_splits=on|off\nrefit=device|host" +
-							  "\nshade_math=fast|ieee\ntiming=on|off\nlevels=1|2|auto\nflatten_budget=" + std::to_string(c->flatten_budget) + "\nlevels_in_use=" + (c->two_level ? "2" : "1") + "\n";
+							  "\nshade_math=fast|ieee\ntiming=on|off\nlevels=1|2|auto\nflatten_budget=" + std::to_string(c->flatten_budget) + "\nlevels_in_use=" + (c->two_level ? "2" : "1") + "\ntop_level_instances=" + std::to_string(c->two_level ? c->tl_table.size() : 0) +
+							  "\ninstance_groups=" + std::to_string(c->two_level ? c->tl_groups : 0) + "\n";
 		snprintf(buf, buf_size, "%s", s.c_str());
 		return RFWB200_OK;
 	}
@@ -2140,10 +2245,11 @@ extern "C"
 			const bool sort = c->rs.sort_mode != 0 && maxd > 0;
 			auto shade = c->shade_ieee ? launch_shade_ieee : launch_shade;
 			const bool shard_sync = to_display && c->shard.world > 1;
-			if (sort)
+			if (sort && c->sort_grid_dirty)
 			{
 				CK(launch_sort_setup(c->scene, c->wf, rs_frame, st)); // grid of the bins from the root of the current tree
 				c->launches += 1;
+				c->sort_grid_dirty = false;
 			}
 			for (uint32_t b = 0; b < batches; b++)
 			{
@@ -2779,7 +2885,13 @@ extern "C"
 			if (tri == 0xffffffffu || tri >= shade.size())
 				hits_out[i].inst_id = -1, hits_out[i].prim_id = -1, hits_out[i].u = 0, hits_out[i].v = 0;
 			else
-				hits_out[i].inst_id = int32_t(c->two_level ? hit_inst[i] : shade[tri].inst_id), hits_out[i].prim_id = int32_t(shade[tri].prim_id);
+			{
+				hits_out[i].prim_id = int32_t(shade[tri].prim_id);
+				if (!c->two_level)
+					hits_out[i].inst_id = int32_t(shade[tri].inst_id);
+				else // (top-level instance, member rank of the triangle's mesh) -> the caller's instance
+					hits_out[i].inst_id = hit_inst[i] < c->tl_table.size() ? int32_t(c->tl_inst_map[c->tl_table[hit_inst[i]].pad[0] + shade[tri].inst_id]) : -1;
+			}
 		}
 		return RFWB200_OK;
 	}

@@ -157,8 +157,8 @@ struct alignas(16) TlInstance
 {
 	float inv[12];		// object = inv * world: rows (m00 m01 m02 m03), (m10 ...), (m20 ...)
 	float normal[9];	// column-major normal matrix
-	uint32_t blas_root; // node index of the mesh's tree
-	uint32_t pad[2];
+	uint32_t blas_root; // node index of the tree below this instance
+	uint32_t pad[2];	// pad[0]: first entry of this instance's row in SceneView::tl_inst_map
 };
 static_assert(sizeof(TlInstance) == 96, "");
 
@@ -192,6 +192,7 @@ struct SceneView
 	// hit carries the instance it was found in
 	const TlInstance *tl_instances;
 	uint32_t tl_instance_count;
+	const uint32_t *tl_inst_map; // [tl_instances[i].pad[0] + ShadeTri::inst_id (rank of the triangle's mesh in its group)] -> the caller's instance index
 };
 
 struct ShardView

@@ -558,7 +558,8 @@ __device__ __forceinline__ void apply_instance_normals(const SceneView &sc, uint
 #undef RFW_NMUL
 	const float il = 1.0f / sqrtf(tri.Nx * tri.Nx + tri.Ny * tri.Ny + tri.Nz * tri.Nz);
 	tri.Nx *= il, tri.Ny *= il, tri.Nz *= il;
-	tri.inst_id = inst;
+	// the caller's instance index: row of the top-level instance, column of the triangle's mesh (context.cpp update_two_level)
+	tri.inst_id = __ldg(sc.tl_inst_map + __ldg(&sc.tl_instances[inst].pad[0]) + tri.inst_id);
 }
 
 template <bool ANY_HIT>
@@ -912,10 +913,11 @@ __device__ __forceinline__ void close_launch(const RenderSettings &rs, DepthCoun
 // STAGE_P: the first rs.smem_nodes PACKED nodes (80 B each: 256 nodes = 20 KB) are staged into shared memory with one TMA bulk copy
 // per CTA, and node fetches below that index read shared memory (setting smem_nodes with the packed variants; measured in
 // profiles/r02 against the L1-only default).
-// TL: the scene is two-level (TlInstance, device_types.h).  A top-level leaf names one instance; "intersecting" it means moving
-// the ray into the instance's object space, pushing a marker that brings the world ray back, and descending the mesh's tree —
-// all in the same while-while loop, on the same stack.  A lane that holds a postponed leaf of an instance stops at that
-// instance's marker (the leaf's triangles must be tested with the object-space ray), exactly as it stops at a second leaf.
+// TL: the scene is two-level (TlInstance, device_types.h).  A top-level leaf names one instance; reaching it means moving the
+// ray into the instance's object space, pushing a marker that brings the world ray back, and descending the tree below —
+// all in the node phase of the same while-while loop, on the same stack.  A lane that holds a postponed leaf of an instance
+// stops at that instance's marker (the leaf's triangles must be tested with the object-space ray), exactly as it stops at
+// a second leaf.
 template <bool PRIMARY, int LQ, int LEAN, bool PACKED, bool STAGE_P = false, bool TL = false>
 __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const SceneView sc, const ShardView sh, const WavefrontView wf,
 															const RenderSettings rs, const BatchView bv, const uint32_t depth,
@@ -974,6 +976,8 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 	constexpr int TL_MARKER = 0x7ffffffe;		// stack entry: back to the world ray (below SENTINEL, so the node loop sees it)
 	constexpr uint32_t NO_INSTANCE = 0xffffffffu;
 	uint32_t inst = NO_INSTANCE, hit_inst = 0; // TL: instance whose tree the lane is in; instance of the closest hit
+	float world_ray[TL ? 6 : 1];			   // TL: the world ray while the lane is inside an instance (indexed dynamically nowhere: registers
+											   // would do, but the kernel has none to spare — the compiler keeps it in local memory, L1)
 	uint32_t chunk_pos = 0, chunk_end = 0; // warp-uniform: the run of queue entries this warp is working through
 	const uint32_t chunk_len = uint32_t(rs.fetch_chunk);
 
@@ -1042,18 +1046,15 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 				{
 					if (TL && cur == TL_MARKER)
 					{
-						// the instance's subtree is exhausted: the world ray again, from the queue entry it came from
-						float4 O4, D4;
-						if (PRIMARY)
-							O4 = wf.O[in_buf][item], D4 = wf.D[in_buf][item];
-						else if (!shadow)
-							O4 = q.Oin[item], D4 = q.Din[item];
-						else
-							O4 = wf.sO[item - q.n_ext], D4 = wf.sD[item - q.n_ext];
-						o = mk(O4.x, O4.y, O4.z), d = mk(D4.x, D4.y, D4.z);
-						RFW_LANE_RAY_SETUP()
+						// the instance's subtree is exhausted: back to the world ray — if the top level has anything left for it
+						// (the ray was parked in thread-local memory when it entered the instance: an L1 hit, not a trip to the queue)
 						inst = NO_INSTANCE;
 						cur = stack[--sp];
+						if (cur != SENTINEL)
+						{
+							o = mk(world_ray[0], world_ray[1], world_ray[2]), d = mk(world_ray[3], world_ray[4], world_ray[5]);
+							RFW_LANE_RAY_SETUP()
+						}
 					}
 					else
 					{
@@ -1178,6 +1179,25 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 						}
 					}
 					} // node step
+					if (TL && cur < 0 && inst == NO_INSTANCE)
+					{
+						// top-level leaf: enter the instance right here, in the node phase (Kernels.cu:229-232,270-272: the direction
+						// is not re-normalised, so t stays the world distance).  A lane in world space never holds a postponed leaf
+						// (it cannot pop an instance's marker while it holds one), so nothing has to wait for the warp's leaf phase —
+						// a freshly fetched ray would otherwise idle from its first node visit to the next leaf phase of its warp.
+						inst = uint32_t(~cur) >> 2;
+						const float4 *ip = reinterpret_cast<const float4 *>(sc.tl_instances + inst);
+						const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2);
+						const V3 wo = o, wd = d;
+						world_ray[0] = wo.x, world_ray[1] = wo.y, world_ray[2] = wo.z, world_ray[3] = wd.x, world_ray[4] = wd.y, world_ray[5] = wd.z;
+						o = mk(r0.x * wo.x + r0.y * wo.y + r0.z * wo.z + r0.w, r1.x * wo.x + r1.y * wo.y + r1.z * wo.z + r1.w,
+							   r2.x * wo.x + r2.y * wo.y + r2.z * wo.z + r2.w);
+						d = mk(r0.x * wd.x + r0.y * wd.y + r0.z * wd.z, r1.x * wd.x + r1.y * wd.y + r1.z * wd.z,
+							   r2.x * wd.x + r2.y * wd.y + r2.z * wd.z);
+						RFW_LANE_RAY_SETUP()
+						stack[sp++] = TL_MARKER;
+						cur = int(__ldg(&sc.tl_instances[inst].blas_root));
+					}
 					// hold back up to LQ leaves and keep descending
 					if (cur < 0 && leaf == NO_LEAF)
 					{
@@ -1201,25 +1221,6 @@ __global__ void __launch_bounds__(256, TRACE_MINB) k_wavefront_trace(const Scene
 				while (leaf != NO_LEAF)
 				{
 					const uint32_t v = uint32_t(~leaf), first = v >> 2, cnt = (v & 3u) + 1u;
-					if (TL && inst == NO_INSTANCE)
-					{
-						// top-level leaf: enter the instance (Kernels.cu:229-232,270-272: the direction is not re-normalised, so t
-						// stays the world distance).  What the lane had lined up next waits below the marker.
-						inst = first;
-						const float4 *ip = reinterpret_cast<const float4 *>(sc.tl_instances + inst);
-						const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2);
-						const V3 wo = o, wd = d;
-						o = mk(r0.x * wo.x + r0.y * wo.y + r0.z * wo.z + r0.w, r1.x * wo.x + r1.y * wo.y + r1.z * wo.z + r1.w,
-							   r2.x * wo.x + r2.y * wo.y + r2.z * wo.z + r2.w);
-						d = mk(r0.x * wd.x + r0.y * wd.y + r0.z * wd.z, r1.x * wd.x + r1.y * wd.y + r1.z * wd.z,
-							   r2.x * wd.x + r2.y * wd.y + r2.z * wd.z);
-						RFW_LANE_RAY_SETUP()
-						stack[sp++] = cur;
-						stack[sp++] = TL_MARKER;
-						cur = int(__ldg(&sc.tl_instances[inst].blas_root));
-						leaf = NO_LEAF;
-						break;
-					}
 					for (uint32_t i = 0; i < cnt; i++)
 					{
 						const float4 a = __ldg(tris + size_t(first + i) * 3 + 0);

@@ -203,3 +203,48 @@ def test_config2_emode_image_against_the_oracle(product_lib, oracle_lib):
     print(f"config 2 E-mode: pixels off {bad:.4f}, mean error {mean_err:.5f}")
     assert bad < 0.03, bad
     assert mean_err < 5e-3, mean_err
+
+
+def test_config4_cesiumman_frames_against_the_oracle(product_lib, oracle_lib):
+    """BASELINE.json configs[3]: the reference's own CesiumMan asset (baked by tools/bake_cesiumman.py: mesh, 19 joints, the
+    sampled animation) at the bench's camera, three frames of the animation.  GPU route: 64 bytes per joint -> k_skin_vertices +
+    k_update_triangles -> k_refit.  Oracle route (the reference's): skin on the CPU (oracle/skinning.py, pinned on the
+    reference's math.h), re-send the mesh, refit.  Camera rays hit by hit at 640x360, then the PT frame as statistics."""
+    sc, skins = S.animated_config4(1)
+    if "cesiumman" not in sc.name:
+        pytest.skip("the baked CesiumMan asset is absent (tools/bake_cesiumman.py needs /root/reference)")
+    from oracle import skinning as K
+
+    W, H = 640, 360
+    g = R.RenderContext(product_lib)
+    S.upload(g, sc, W, H)
+    o = R.RenderContext(oracle_lib)
+    S.upload(o, S.animated_config4(1)[0], W, H)
+    for sk in skins:
+        g.set_mesh_skin(sk.mesh_index, sk.base_vertices, sk.base_normals, sk.joints, sk.weights)
+    cam = sc.camera(W, H)
+    man = {i for i, (mi, _) in enumerate(sc.instances) if mi in {sk.mesh_index for sk in skins}}
+    for n_frame, k in enumerate((0, 11, 37)):
+        for sk in skins:
+            g.set_mesh_pose(sk.mesh_index, sk.joint_matrices(k))
+            m = sc.meshes[sk.mesh_index]
+            v, n = K.set_pose(sk.base_vertices, sk.base_normals, sk.joints, sk.weights, sk.joint_matrices(k))
+            o.set_mesh(sk.mesh_index, v, K.update_triangles(m.triangles, v, n, m.indices), m.indices)
+        g.update(), o.update()
+        st = g.get_geometry_stats()
+        assert (st.on_device, st.was_refit) == (1, 1) and st.refits == n_frame + 1
+        origins, dirs = o.generate_primary(cam, k)
+        hg, ho = g.trace_closest(origins, dirs), o.trace_closest(origins, dirs)
+        assert np.isin(ho["inst_id"], list(man)).mean() > 0.03  # the figure is in view
+        check_hits(o, origins, dirs, hg, ho)
+    for ctx in (g, o):
+        ctx.set_setting("spp", 4)
+        ctx.render_frame(cam, R.RESET)
+    a, b = g.read_image()[..., :3], o.read_image()[..., :3]
+    assert np.isfinite(a).all()
+    mean_err = abs(float(a.mean()) - float(b.mean())) / float(b.mean())
+    blocks = lambda im: im[: H // 8 * 8, : W // 8 * 8].reshape(H // 8, 8, W // 8, 8, 3).mean(axis=(1, 3, 4))
+    ba, bb = blocks(a), blocks(b)
+    within = float((np.abs(ba - bb) <= 0.15 * bb + 0.02).mean())
+    print(f"config 4 statistics: mean error {mean_err:.4f}, blocks within 15 %: {within:.4f}")
+    assert mean_err < 0.01 and within > 0.95

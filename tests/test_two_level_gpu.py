@@ -145,6 +145,9 @@ def test_moving_an_instance_rebuilds_the_top_level_only(product_lib, oracle_lib)
     W, H = 160, 120
     g, sc = product(product_lib, SCENES["cornell"], W, H, levels=2)
     o = oracle(oracle_lib, SCENES["cornell"], W, H)
+    # the six quads share one transform (one group, one top-level instance); the two blocks have their own
+    info = dict(l.split("=", 1) for l in g.get_settings().splitlines() if "=" in l)
+    assert int(info["instance_groups"]) == 3 and int(info["top_level_instances"]) == 3, info
     builds0 = g.get_geometry_stats().builds
     mesh, M = sc.instances[6]  # the short block
     M2 = S.translate(0.4, 0.3, -0.2) @ np.asarray(M)
@@ -206,3 +209,37 @@ def test_config3_instanced_sponza_two_level_against_flattened_and_oracle(product
     assert (np.abs(ba - bb) <= 0.15 * bb + 1e-3).mean() > 0.95
     i2, i1 = g2.get_bvh_info(), g1.get_bvh_info()
     assert i2["triangles"] < 0.4 * i1["triangles"]  # one copy of the records instead of four
+    # the 393 meshes of the model are placed by the same four transforms: ONE tree below FOUR top-level instances (+ the light
+    # quad), not 1,573 overlapping instance boxes
+    info = dict(l.split("=", 1) for l in g2.get_settings().splitlines() if "=" in l)
+    assert int(info["instance_groups"]) == 2 and int(info["top_level_instances"]) == 5, info
+
+
+def test_groups_follow_the_placements(product_lib, oracle_lib):
+    """Meshes placed by the same list of transforms share a tree; a mesh that is moved on its own leaves its group (both
+    trees are rebuilt), and a mesh instanced twice gets two top-level instances over one tree.  Hits keep naming the caller's
+    (instance, primitive) pairs."""
+    W, H = 160, 120
+    g, sc = product(product_lib, SCENES["cornell"], W, H, levels=2)
+    o = oracle(oracle_lib, SCENES["cornell"], W, H)
+    cam = sc.camera(W, H)
+    mesh, M = sc.instances[2]  # the back wall, until now in the group of the six quads
+    M2 = S.translate(0.0, 0.0, -0.5) @ np.asarray(M)
+    extra = len(sc.instances)
+    blk_mesh, blk_M = sc.instances[6]
+    for ctx in (g, o):
+        ctx.set_instance(2, mesh, M2)
+        ctx.set_instance(extra, blk_mesh, S.translate(1.5, 0.0, -0.8) @ np.asarray(blk_M))  # the short block a second time
+        ctx.update()
+    info = dict(l.split("=", 1) for l in g.get_settings().splitlines() if "=" in l)
+    assert int(info["instance_groups"]) == 4 and int(info["top_level_instances"]) == 5, info
+    origins, dirs = o.generate_primary(cam, 0)
+    hg, ho = g.trace_closest(origins, dirs), o.trace_closest(origins, dirs)
+    assert ((ho["inst_id"] == extra) & (ho["prim_id"] >= 0)).sum() > 20 and ((ho["inst_id"] == 2) & (ho["prim_id"] >= 0)).sum() > 50
+    _check_hits(g, o, origins, dirs, hg, ho)
+    for ctx in (g, o):
+        ctx.set_setting("spp", 1)
+        ctx.set_probe_index(W // 2, H // 2)
+        ctx.render_frame(cam, R.RESET)
+    assert frac_bad(g.read_image(), o.read_image()) < 8e-3
+    assert g.get_probe_results()[:2] == o.get_probe_results()[:2]
