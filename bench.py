@@ -326,6 +326,7 @@ def run():
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--set", nargs="*", default=[], help="extra key=value settings (tuning experiments)")
+    ap.add_argument("--inflight", type=int, default=2, help="N > 1: frames a rank may have enqueued ahead of the device")
     ap.add_argument("--no-check-image", action="store_true", help="N > 1: skip the comparison of the assembled frame with a single-rank render")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -397,7 +398,7 @@ def run():
     # the bound the host of each rank runs hundreds of frames ahead and the ranks' launch queues drift apart; the sharded frame
     # (ranks meet twice per bounce and once per image) then measured 2.53 ms at 8 GPUs in the free-running loop against 2.05 ms
     # in the e2e loop, which is paced by its read-back (profiles/r02/r02_bench8_c2.json).
-    INFLIGHT = 2
+    INFLIGHT = max(1, args.inflight)
     pace = [torch.cuda.Event() for _ in range(INFLIGHT)]
     paced = [0]
 
