@@ -282,6 +282,7 @@ struct rfwb200_context
 	size_t items_capacity = 0;		// work items the wavefront planes are allocated for
 	int spp_batch = 0;				// setting "spp_batch": samples per wavefront, 0 = as many as fit (<= MAX_BATCH_SPP, <= 2^24 items)
 	uint32_t sort_bins_allocated = 0;
+	bool sample_minor = false; // setting "sample_layout" = planes | pixel (BatchView::sample_minor)
 	bool sort_grid_dirty = true; // the bin grid (k_sort_setup: from the root of the current tree) is computed once per scene change, not per frame
 
 	// ---- display target of a sharded frame (DisplayTarget, device_types.h) and in-process device groups ----
@@ -2033,6 +2034,11 @@ extern "C"
 			REQUIRE(v == "on" || v == "off" || v == "1" || v == "0", "sort must be on or off");
 			c->rs.sort_mode = (v == "on" || v == "1") ? 1 : 0;
 		}
+		else if (k == "sample_layout")
+		{
+			REQUIRE(v == "planes" || v == "pixel", "sample_layout must be 'planes' (a warp = one sample of 32 pixels) or 'pixel' (a warp = all samples of 32 / spp pixels)");
+			c->sample_minor = (v == "pixel");
+		}
 		else if (k == "sort_cell_bits")
 		{
 			const int n = atoi(v.c_str());
@@ -2256,6 +2262,7 @@ extern "C"
 				BatchView bv;
 				bv.spp = std::min(bspp, spp - b * bspp), bv.first_sample = b * bspp, bv.index = b;
 				bv.items = c->shard.local_pixels * bv.spp, bv.inv_spp = 1.0f / float(bv.spp);
+				bv.sample_minor = c->sample_minor ? 1u : 0u;
 				ShardSync sync{};
 				if (shard_sync)
 				{

@@ -101,6 +101,8 @@ struct BatchView
 	uint32_t index;		   // wavefront number within the frame: selects the DepthCounters row
 	uint32_t items;		   // local_pixels * spp
 	float inv_spp;		   // 1 / spp (fast_div)
+	uint32_t sample_minor; // 1 (setting sample_layout=pixel): item = block * 32 * spp + pixel_in_block * spp + s instead — the
+						   // samples of a pixel sit next to each other, a warp of camera rays is 32 / spp pixels x spp samples
 };
 
 // Display target of a tile-sharded frame: ONE row-major image in the display rank's memory that the fold

@@ -198,8 +198,22 @@ __device__ __forceinline__ bool local_to_pixel(const ShardView &sh, uint32_t j, 
 __device__ __forceinline__ void item_to_pixel_sample(const BatchView &bv, uint32_t item, uint32_t &j, uint32_t &s)
 {
 	const uint32_t grp = item >> 5, blk = fast_div(grp, bv.spp, bv.inv_spp);
+	if (bv.sample_minor)
+	{
+		// the samples of a pixel are neighbours: a warp of camera rays is 32 / spp pixels x spp samples
+		const uint32_t l = item - ((blk * bv.spp) << 5), pix = fast_div(l, bv.spp, bv.inv_spp);
+		s = l - pix * bv.spp;
+		j = (blk << 5) | pix;
+		return;
+	}
 	s = grp - blk * bv.spp;
 	j = (blk << 5) | (item & 31u);
+}
+// where sample s of local pixel j lives (the inverse of item_to_pixel_sample)
+__device__ __forceinline__ uint32_t pixel_sample_to_item(const BatchView &bv, uint32_t j, uint32_t s)
+{
+	const uint32_t blk = j >> 5, lane = j & 31u;
+	return bv.sample_minor ? (((blk * bv.spp) << 5) + lane * bv.spp + s) : ((((blk * bv.spp) + s) << 5) | lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -837,8 +851,12 @@ __device__ __forceinline__ bool fetch_ray(const SceneView &sc, const ShardView &
 	// emitted at least one extension ray at this depth anywhere in the frame (CUDART/src/Context.cpp:109-120: the host
 	// loop leaves before the pending shadow rays are traced).  The ranks of a sharded frame merge their flags between the
 	// shade launch and this one (k_shard_sync), so the assembled frame does not depend on how it was sharded.
-	if (q.seen[(pidx >> 5) - fast_div(pidx >> 5, bv.spp, bv.inv_spp) * bv.spp] == 0u)
-		return false;
+	{
+		uint32_t pj, ps;
+		item_to_pixel_sample(bv, pidx, pj, ps);
+		if (q.seen[ps] == 0u)
+			return false;
+	}
 	n_traced++;
 	const float4 O4 = LD_TS(&wf.sO[k]), D4 = LD_TS(&wf.sD[k]);
 	o = mk(O4.x, O4.y, O4.z), d = mk(D4.x, D4.y, D4.z);
@@ -2511,10 +2529,9 @@ __global__ void k_fold(const ShardView sh, const WavefrontView wf, const BatchVi
 		if (live)
 		{
 			a = wf.accumulator[j];
-			const uint32_t blk = j >> 5, lane = j & 31u;
 			for (uint32_t s = 0; s < bv.spp; s++)
 			{
-				const float4 b = wf.sample_acc[((blk * bv.spp + s) << 5) | lane];
+				const float4 b = wf.sample_acc[pixel_sample_to_item(bv, j, s)];
 				a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
 			}
 			wf.accumulator[j] = a;
@@ -2523,7 +2540,8 @@ __global__ void k_fold(const ShardView sh, const WavefrontView wf, const BatchVi
 				float4 al = wf.albedo_acc[j], no = wf.normal_acc[j];
 				for (uint32_t s = 0; s < bv.spp; s++)
 				{
-					const float4 b = wf.sample_albedo[((blk * bv.spp + s) << 5) | lane], c = wf.sample_normal[((blk * bv.spp + s) << 5) | lane];
+					const uint32_t it = pixel_sample_to_item(bv, j, s);
+					const float4 b = wf.sample_albedo[it], c = wf.sample_normal[it];
 					al.x += b.x, al.y += b.y, al.z += b.z, no.x += c.x, no.y += c.y, no.z += c.z;
 				}
 				wf.albedo_acc[j] = al, wf.normal_acc[j] = no;

@@ -618,3 +618,115 @@ def emat_scene():
     sc.meshes.append(S._grid_quad((0, 0, 0), (1, 0, 0), (0, 1, 0), 2, 2, m, uv_rep=1.0, tex_dims=(16, 16)))
     sc.instances.append((len(sc.meshes) - 1, S.translate(0.5, 0.5, -3.0) @ S.rotate_y(20) @ S.scale(1.5, 0.7, 1.0)))
     return sc
+
+
+# ---- the reference's own E-mode frame loop body (EmbreeRT/src/Context.cpp:179-282 via oracle/ref_build/ref_eframe_shim.cpp) ------
+REF_EFRAME_LIB = R.REPO_DIR / "oracle" / "_ref" / "librfwref_eframe.so"
+
+
+class _RTCRay8(C.Structure):
+    _fields_ = [(n, C.c_float * 8) for n in ("org_x", "org_y", "org_z", "tnear", "dir_x", "dir_y", "dir_z", "time", "tfar")] + \
+               [("mask", C.c_uint * 8), ("id", C.c_int * 8), ("flags", C.c_uint * 8)]
+
+
+class _RTCHit8(C.Structure):
+    _fields_ = [(n, C.c_float * 8) for n in ("Ng_x", "Ng_y", "Ng_z", "u", "v")] + \
+               [("primID", C.c_uint * 8), ("geomID", C.c_uint * 8), ("instID", (C.c_uint * 8) * 1)]
+
+
+class _RTCRayHit8(C.Structure):
+    _fields_ = [("ray", _RTCRay8), ("hit", _RTCHit8)]
+
+
+class _RefEScene(C.Structure):
+    _fields_ = [("materials192", C.c_void_p), ("n_materials", C.c_int), ("textures", C.c_void_p), ("n_textures", C.c_int),
+                ("mesh_triangles160", C.c_void_p), ("n_meshes", C.c_int), ("instance_mesh", C.c_void_p), ("instance_normal16", C.c_void_p),
+                ("n_instances", C.c_int), ("area_lights96", C.c_void_p), ("n_area", C.c_int), ("point_lights32", C.c_void_p), ("n_point", C.c_int),
+                ("sky3", C.c_void_p), ("sky_w", C.c_int), ("sky_h", C.c_int)]
+
+
+_OCCLUDED_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float)
+
+
+def ref_emode_frame(sc, o, W, H, probe=None, sample_index=0):
+    """One E-mode frame of scene `sc` the way the reference's CPU renderer computes it AROUND Embree: the camera rays of the
+    oracle context `o` (E-mode determinism contract) and their closest hits (the oracle's traversal in Embree's place) are put
+    into Embree's ray / hit packets, eight pixels at a time, and handed to the reference's own per-pixel loop body
+    (Context.cpp:179-282) — sky lookup, probe, retrieve_material, light loops, pixel write.  rtcOccluded1 is answered by the
+    oracle's any-hit query with the oracle's stated shadow interval (t_min = the ray's tnear, t_max = tfar * (1 - 1e-4): a
+    light's own triangle cannot shadow its centroid; DESIGN.md "E-mode determinism contract").
+    -> (pixels (H, W, 4) float32, probe (instance, triangle, distance) or None)"""
+    lib = C.CDLL(str(REF_EFRAME_LIB))
+    S.extract_area_lights(sc)
+    cam = sc.camera(W, H)
+    o.set_setting("mode", "embree")
+    origins, dirs = o.generate_primary(cam, sample_index)
+    hits = o.trace_closest(origins, dirs)
+    keep = []
+    texs = (_RefTexture * max(len(sc.textures), 1))()
+    for i, t in enumerate(sc.textures):
+        data = np.ascontiguousarray(t["data"])
+        keep.append(data)
+        texs[i].type, texs[i].width, texs[i].height, texs[i].data = (1 if t["type"] == R.TEX_UINT else 0), t["width"], t["height"], data.ctypes.data
+    mats = np.ascontiguousarray(sc.materials)
+    tri_arrays = [np.ascontiguousarray(m.triangles) for m in sc.meshes]
+    tri_ptrs = (C.c_void_p * len(tri_arrays))(*[a.ctypes.data for a in tri_arrays])
+    inst_mesh = np.array([mi for mi, _ in sc.instances], np.uint32)
+    nms = []
+    for _, M in sc.instances:
+        nm = np.eye(4)
+        nm[:3, :3] = np.linalg.inv(np.asarray(M, np.float64)[:3, :3]).T
+        nms.append(nm.T.reshape(-1))
+    nm16 = np.ascontiguousarray(np.array(nms), np.float32)
+    area = np.ascontiguousarray(sc.area_lights) if sc.area_lights is not None else np.zeros(0, R.AREA_LIGHT_DTYPE)
+    point = np.ascontiguousarray(sc.point_lights) if sc.point_lights is not None else np.zeros(0, R.POINT_LIGHT_DTYPE)
+    sky, sw, sh = sc.sky
+    sky = np.ascontiguousarray(sky, np.float32)
+    es = _RefEScene(mats.ctypes.data, len(mats), C.addressof(texs), len(sc.textures), C.addressof(tri_ptrs), len(tri_arrays), inst_mesh.ctypes.data,
+                    nm16.ctypes.data, len(inst_mesh), area.ctypes.data if len(area) else None, len(area), point.ctypes.data if len(point) else None,
+                    len(point), sky.ctypes.data, int(sw), int(sh))
+
+    def occluded(_user, org, dr, tnear, tfar):
+        oo = np.array([[org[0], org[1], org[2], 0.0]], np.float32)
+        dd = np.array([[dr[0], dr[1], dr[2], 0.0]], np.float32)
+        return int(o.trace_occluded(oo, dd, np.array([tfar * (1.0 - 1e-4)], np.float32), t_min=float(tnear))[0])
+
+    cb = _OCCLUDED_FN(occluded)
+    f = lib.rfwref_emode_shade_packet
+    f.restype, f.argtypes = None, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, _OCCLUDED_FN, C.c_void_p, C.c_void_p, C.c_void_p]
+    pixels = np.zeros((W * H, 4), np.float32)
+    probe_out = np.array([0.0, 0.0, -1.0], np.float32)
+    probe_id = probe[1] * W + probe[0] if probe is not None else -1
+    n = W * H
+    for base in range(0, n, 8):
+        pk = _RTCRayHit8()
+        for j in range(8):
+            i = min(base + j, n - 1)
+            pk.ray.org_x[j], pk.ray.org_y[j], pk.ray.org_z[j] = origins[i, 0], origins[i, 1], origins[i, 2]
+            pk.ray.dir_x[j], pk.ray.dir_y[j], pk.ray.dir_z[j] = dirs[i, 0], dirs[i, 1], dirs[i, 2]
+            pk.ray.tnear[j], pk.ray.tfar[j] = 1e-5, hits["t"][i]
+            pk.ray.id[j] = base + j if base + j < n else n  # >= maxPixelID: skipped by the loop body
+            hit = hits["prim_id"][i] >= 0
+            pk.hit.geomID[j] = 0 if hit else 0xFFFFFFFF
+            pk.hit.instID[0][j] = int(hits["inst_id"][i]) if hit else 0xFFFFFFFF
+            pk.hit.primID[j] = int(hits["prim_id"][i]) if hit else 0xFFFFFFFF
+            pk.hit.u[j], pk.hit.v[j] = hits["u"][i], hits["v"][i]
+        f(C.addressof(es), C.addressof(pk), n, probe_id, cb, None, pixels.ctypes.data, probe_out.ctypes.data)
+    got_probe = (int(probe_out[0]), int(probe_out[1]), float(probe_out[2])) if probe is not None else None
+    return pixels.reshape(H, W, 4), got_probe
+
+
+def _eframe_lights_scene():
+    """the feature soup with the FLOAT4-textured quad, under a textured sky and with a second point light: every branch of the
+    frame loop body (sky lookup, emissive early-out, both light loops, occluded and unoccluded shadow rays)"""
+    sc = emat_scene()
+    rng = np.random.default_rng(3)
+    sc.sky = (rng.uniform(0.1, 2.0, (32 * 16, 3)).astype(np.float32), 32, 16)
+    return sc
+
+
+# name -> (scene, width, height, probe pixel); widths / heights are multiples of the reference's 4x2 packet tiles
+EFRAME_CASES = {
+    "soup": (_eframe_lights_scene, 96, 64, (48, 40)),
+    "cornell": (lambda: S.cornell_box(unit_scale=True), 64, 48, (20, 30)),
+}

@@ -256,6 +256,30 @@ def test_emode_image_parity(product_lib, oracle_lib, scene):
     assert pg[:2] == po[:2] and abs(pg[2] - po[2]) <= 1e-4 * max(1.0, po[2])
 
 
+@pytest.mark.parametrize("case", ["soup", "cornell"])
+def test_emode_frame_against_the_reference_frame_loop(product_lib, case):
+    """k_emode against frames made by the reference's OWN per-pixel frame loop body (EmbreeRT/src/Context.cpp:179-282, compiled
+    from the reference tree; Embree's two calls answered by the oracle's traversal): tests/golden/ref_eframe_vectors.npz, pinned
+    bit for bit on the oracle by tests/test_ref_pin.py."""
+    from pathlib import Path
+
+    from ref_pin_common import EFRAME_CASES
+
+    gf = np.load(Path(__file__).resolve().parent / "golden" / "ref_eframe_vectors.npz")
+    scene_fn, W, H, probe = EFRAME_CASES[case]
+    sc = scene_fn()
+    g = R.RenderContext(product_lib)
+    S.upload(g, sc, W, H)
+    g.set_setting("mode", "embree")
+    g.set_probe_index(*probe)
+    g.render_frame(sc.camera(W, H), R.RESET)
+    a, ref = g.read_image(), gf[f"{case}_image"]
+    assert np.isfinite(a).all()
+    assert frac_bad(a, ref) < (2e-3 if case == "cornell" else 8e-3), frac_bad(a, ref)
+    pr, rp = g.get_probe_results(), gf[f"{case}_probe"]
+    assert pr[:2] == (int(rp[0]), int(rp[1])) and abs(pr[2] - rp[2]) <= 1e-4 * max(1.0, rp[2])
+
+
 def test_config1_cornell_512_emode(product_lib, oracle_lib):
     """BASELINE.json configs[0]: Cornell box 512x512 1 spp, the Embree image model."""
     W = H = 512
@@ -745,7 +769,8 @@ def test_config5_lights_sharded_4k_tile_layout(product_lib):
 
 # ---- wavefront batching and re-ordering ---------------------------------------------------------------------
 @pytest.mark.parametrize("settings", [{"spp_batch": 1}, {"spp_batch": 3}, {"sort": "off"}, {"sort_cell_bits": 3, "sort_major": "octant"},
-                                      {"sort_cell_bits": 6}, {"sort": "off", "spp_batch": 2}])
+                                      {"sort_cell_bits": 6}, {"sort": "off", "spp_batch": 2}, {"sample_layout": "pixel"},
+                                      {"sample_layout": "pixel", "spp_batch": 3}, {"sample_layout": "pixel", "sort": "off", "spp_batch": 5}])
 @pytest.mark.parametrize("scene", ["cornell", "soup"])
 def test_wavefront_batching_and_reordering_do_not_change_a_single_bit(product_lib, scene, settings):
     """All samples of a frame travel in one wavefront (spp_batch) and the bounce queue is re-ordered by origin cell and

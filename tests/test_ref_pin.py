@@ -454,3 +454,37 @@ def test_emode_material_matches_reference_retrieve_material(oracle_lib):
         if REF_EMAT_LIB.exists() and k % 16 == 0:  # the stored vectors cannot go stale where the reference is present
             live = np.concatenate(ref_emode_material(sc, inst, prim, u, v))
             assert np.array_equal(live, ref)
+
+
+GF = dict(np.load(Path(__file__).resolve().parent / "golden" / "ref_eframe_vectors.npz"))
+
+
+@pytest.mark.parametrize("case", ["soup", "cornell"])
+def test_emode_frame_matches_the_reference_frame_loop(oracle_lib, case):
+    """The oracle's E-mode frame against the reference's OWN per-pixel frame loop body (EmbreeRT/src/Context.cpp:179-282 with
+    retrieve_material :417-476, compiled from the reference tree by oracle/ref_build/ref_eframe_shim.cpp): sky lookup on a miss,
+    probe, the material step, the colour > 1 early-out, the area-light and point-light loops, 0.1 ambient, the pixel write.
+    Embree itself is absent: its two calls are answered by the oracle's traversal (closest hits go in through Embree's hit
+    record, rtcOccluded1 is a callback), with the oracle's stated shadow interval.  Everything around them must agree bit for
+    bit; the frames are committed (tests/golden/ref_eframe_vectors.npz, generator make_ref_eframe_golden.py) and re-made live
+    where the reference is present."""
+    from ref_pin_common import EFRAME_CASES, REF_EFRAME_LIB, ref_emode_frame
+
+    scene_fn, W, H, probe = EFRAME_CASES[case]
+    sc = scene_fn()
+    o = R.RenderContext(oracle_lib)
+    S.upload(o, sc, W, H)
+    o.set_setting("mode", "embree")
+    o.set_probe_index(*probe)
+    o.render_frame(sc.camera(W, H), R.RESET)
+    img = o.read_image()
+    ref, ref_probe = GF[f"{case}_image"], GF[f"{case}_probe"]
+    assert ref.shape == img.shape and (ref[..., 3] > 0).mean() > 0.3  # geometry in view ...
+    assert ((ref[..., 3] == 0) & (ref[..., :3].sum(-1) > 0)).sum() >= (50 if case == "soup" else 0)  # ... and textured sky (soup)
+    assert (ref[..., :3].max(-1) > 1).sum() > 10  # light sources seen directly: the early-out
+    assert np.array_equal(img, ref)
+    pr = o.get_probe_results()
+    assert (pr[0], pr[1]) == (int(ref_probe[0]), int(ref_probe[1])) and pr[2] == np.float32(ref_probe[2])
+    if REF_EFRAME_LIB.exists():  # the stored frames cannot go stale where the reference is present
+        live, live_probe = ref_emode_frame(scene_fn(), o, W, H, probe=probe)
+        assert np.array_equal(live, ref) and live_probe[:2] == (int(ref_probe[0]), int(ref_probe[1]))
