@@ -89,11 +89,13 @@ static_assert(offsetof(DepthCounters, ext) % 8 == 0 && offsetof(DepthCounters, s
 constexpr int MAX_DEPTH_SLOTS = 8; // max_path_length + 1 <= 8
 constexpr int MAX_BATCH_SPP = 64;  // samples of a frame that travel in one wavefront (BatchView)
 
-// One wavefront carries `spp` samples of every local pixel: work item = ((block * spp + s) << 5) | lane, where block is
-// an 8x4-pixel block of the shard (32 consecutive local pixels) — so a warp of camera rays is one sample of one compact
-// block, the samples of a block are neighbours in the queue (they walk the same part of the tree right after each
-// other), and a frame is 3 + 4 * bounces launches however many samples it has.  The reference renders one sample per
-// render_frame call (CUDART/src/Context.cpp:75-80,149).
+// One wavefront carries `spp` samples of every local pixel.  Work item (default, sample_minor = 1) = block * 32 * spp +
+// pixel_in_block * spp + s, where block is an 8x4-pixel block of the shard (32 consecutive local pixels): the samples of a
+// pixel are neighbours, so a warp of camera rays is 32 / spp pixels x spp samples — rays that differ by a sub-pixel jitter
+// and walk the same nodes (measured against one sample of 32 pixels per warp, sample_minor = 0: work item =
+// ((block * spp + s) << 5) | lane: camera-ray launch -7 %, frame -2 %, bit-identical frames).  A frame is 3 + 4 * bounces
+// launches however many samples it has.  The reference renders one sample per render_frame call
+// (CUDART/src/Context.cpp:75-80,149).
 struct BatchView
 {
 	uint32_t spp;		   // samples in this wavefront (<= MAX_BATCH_SPP)
