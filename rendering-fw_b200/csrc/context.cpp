@@ -306,7 +306,7 @@ struct rfwb200_context
 	const rfwb200_context *build_donor = nullptr; // rank 0 of the group: its host-built tree is adopted instead of built again
 
 	// ---- settings / state ------------------------------------------------------------------------------
-	RenderSettings rs{2, 10.0f, 1e-5f, 1, 0, 8, nullptr, -1, 9, 1, 0, 9, 1, 5, 0, 0}; // bounces: packed nodes + unsorted connect rays; camera rays: fp32 nodes (DESIGN.md sweep) // smem_nodes 0: measured fastest on B200 (DESIGN.md "staging")
+	RenderSettings rs{2, 10.0f, 1e-5f, 1, 0, 8, nullptr, -1, 9, 1, 0, 9, 1, 5, 0, 0, 5}; // bounces: packed nodes + unsorted connect rays; camera rays: fp32 nodes (DESIGN.md sweep) // smem_nodes 0: measured fastest on B200 (DESIGN.md "staging")
 	int spp = 1;
 	bool mode_pt = true;
 	LaunchDims dims{};
@@ -447,7 +447,8 @@ int ensure_wavefront(Ctx *c, uint32_t bspp)
 			}
 		}
 	}
-	const uint32_t bins = 1u << (3 * c->rs.sort_cell_bits + 3);
+	REQUIRE(3 * c->rs.sort_cell_bits + c->rs.sort_dir_bits <= 21, "sort_cell_bits = 6 needs sort_dir_bits = 3 (at most 2^21 bins)");
+	const uint32_t bins = 1u << (3 * c->rs.sort_cell_bits + c->rs.sort_dir_bits);
 	if (bins > c->sort_bins_allocated)
 	{
 		CK(cudaStreamSynchronize(c->stream));
@@ -2044,6 +2045,12 @@ extern "C"
 			const int n = atoi(v.c_str());
 			REQUIRE(n >= 3 && n <= 6, "sort_cell_bits must be in [3, 6] (grid cells per axis = 2^bits)");
 			c->rs.sort_cell_bits = n, c->sort_grid_dirty = true;
+		}
+		else if (k == "sort_dir_bits")
+		{
+			const int n = atoi(v.c_str());
+			REQUIRE(n == 3 || n == 5, "sort_dir_bits must be 3 (octant) or 5 (octant x dominant axis)");
+			c->rs.sort_dir_bits = n;
 		}
 		else if (k == "sort_major")
 		{

@@ -256,6 +256,7 @@ struct RenderSettings
 	int sort_cell_bits;	 // grid resolution per axis: 2^bits cells (3..6)
 	int sort_dir_major;	 // 1: the octant is the most significant part of the key, 0: the cell is
 	int fetch_chunk;	 // 0: idle lanes take the next entries of one shared front; > 0: a warp claims a private run of that many entries
+	int sort_dir_bits;	 // direction part of the re-ordering key: 3 = octant, 5 = octant x dominant axis (24 bins)
 };
 constexpr int SORT_CHUNK = 4096; // bins scanned by one CTA of k_sort_scan
 

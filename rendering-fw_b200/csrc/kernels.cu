@@ -230,16 +230,21 @@ __device__ __forceinline__ uint32_t spread3(uint32_t x)
 	x = (x | (x << 2)) & 0x09249249u;
 	return x;
 }
-__device__ __forceinline__ uint32_t ray_bin(const SortGrid &g, int cell_bits, int dir_major, float ox, float oy, float oz, float dx,
-											float dy, float dz)
+__device__ __forceinline__ uint32_t ray_bin(const SortGrid &g, int cell_bits, int dir_major, int dir_bits, float ox, float oy, float oz,
+											float dx, float dy, float dz)
 {
 	const int hi = (1 << cell_bits) - 1;
 	const int cx = min(max(__float2int_rd((ox - g.lo[0]) * g.scale[0]), 0), hi);
 	const int cy = min(max(__float2int_rd((oy - g.lo[1]) * g.scale[1]), 0), hi);
 	const int cz = min(max(__float2int_rd((oz - g.lo[2]) * g.scale[2]), 0), hi);
 	const uint32_t cell = spread3(uint32_t(cx)) | (spread3(uint32_t(cy)) << 1) | (spread3(uint32_t(cz)) << 2);
-	const uint32_t oct = (dx < 0.0f ? 1u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 4u : 0u);
-	return dir_major ? ((oct << (3 * cell_bits)) | cell) : ((cell << 3) | oct);
+	uint32_t oct = (dx < 0.0f ? 1u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 4u : 0u);
+	if (dir_bits == 5) // octant x dominant axis: 24 direction bins
+	{
+		const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+		oct |= (ax >= ay ? (ax >= az ? 0u : 2u) : (ay >= az ? 1u : 2u)) << 3;
+	}
+	return dir_major ? ((oct << (3 * cell_bits)) | cell) : ((cell << dir_bits) | oct);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2492,7 +2497,7 @@ __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, c
 				{
 					// counting sort, first half: the lanes of the warp that emit into the same bin are found with one
 					// match instruction and take consecutive ranks from ONE atomic on the bin's counter
-					const uint32_t bin = ray_bin(grid, rs.sort_cell_bits, rs.sort_dir_major, eO.x, eO.y, eO.z, eD.x, eD.y, eD.z);
+					const uint32_t bin = ray_bin(grid, rs.sort_cell_bits, rs.sort_dir_major, rs.sort_dir_bits, eO.x, eO.y, eO.z, eD.x, eD.y, eD.z);
 					const uint32_t peers = __match_any_sync(m_ex, bin);
 					const int leader = __ffs(peers) - 1;
 					uint32_t rank = 0;
@@ -3310,7 +3315,7 @@ cudaError_t launch_sort_setup(const SceneView &sc, const WavefrontView &wf, cons
 cudaError_t launch_sort(const WavefrontView &wf, const RenderSettings &rs, const BatchView &bv, uint32_t depth, const LaunchDims &dims,
 						cudaStream_t stream)
 {
-	const uint32_t bins = 1u << (3 * rs.sort_cell_bits + 3), n_chunks = bins / SORT_CHUNK;
+	const uint32_t bins = 1u << (3 * rs.sort_cell_bits + rs.sort_dir_bits), n_chunks = bins / SORT_CHUNK;
 	k_sort_scan<<<n_chunks, 1024, 0, stream>>>(wf);
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess)

@@ -54,7 +54,7 @@ def test_feature_planes_of_the_first_vertex(product_lib, oracle_lib):
     assert alb[..., :3][same_surface].mean() > 0.05
 
 
-@pytest.mark.parametrize("settings", [{"spp_batch": 1}, {"sort": "off"}, {"spp_batch": 3, "sort_cell_bits": 4}, {"sample_layout": "pixel"}])
+@pytest.mark.parametrize("settings", [{"spp_batch": 1}, {"sort": "off"}, {"spp_batch": 3, "sort_cell_bits": 4}, {"sample_layout": "planes"}])
 def test_feature_planes_do_not_depend_on_the_schedule(product_lib, settings):
     W, H, spp = 200, 100, 8
     a, _, _ = render(product_lib, W, H, spp, frames=2, aov="on")

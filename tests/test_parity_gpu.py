@@ -769,8 +769,8 @@ def test_config5_lights_sharded_4k_tile_layout(product_lib):
 
 # ---- wavefront batching and re-ordering ---------------------------------------------------------------------
 @pytest.mark.parametrize("settings", [{"spp_batch": 1}, {"spp_batch": 3}, {"sort": "off"}, {"sort_cell_bits": 3, "sort_major": "octant"},
-                                      {"sort_cell_bits": 6}, {"sort": "off", "spp_batch": 2}, {"sample_layout": "pixel"},
-                                      {"sample_layout": "pixel", "spp_batch": 3}, {"sample_layout": "pixel", "sort": "off", "spp_batch": 5}])
+                                      {"sort_cell_bits": 6, "sort_dir_bits": 3}, {"sort": "off", "spp_batch": 2}, {"sample_layout": "planes"},
+                                      {"sample_layout": "planes", "spp_batch": 3}, {"sample_layout": "planes", "sort": "off", "spp_batch": 5}, {"sort_dir_bits": 3}, {"sample_layout": "planes", "sort_dir_bits": 3}])
 @pytest.mark.parametrize("scene", ["cornell", "soup"])
 def test_wavefront_batching_and_reordering_do_not_change_a_single_bit(product_lib, scene, settings):
     """All samples of a frame travel in one wavefront (spp_batch) and the bounce queue is re-ordered by origin cell and
