@@ -2,19 +2,24 @@
 //
 // Stage map (reference semantics in parentheses; paths relative to /root/reference/RFW):
 //   k_wavefront_trace<true>   generate + extend for camera rays (backends/CUDART/src/Kernels.cu:383-460)
-//   k_shade     material eval + NEE + BSDF sample + compaction (Kernels.cu:571-794,
+//   k_shade     material eval + NEE + BSDF sample + compaction + sort-bin ranks (Kernels.cu:571-794,
 //               CUDART/src/getShadingData.h, CUDART/src/lights.h, system/context/rfw/bsdf/*.h)
+//   k_sort_scan / k_sort_move  re-ordering of the bounce queue by (origin cell, direction bin) — no counterpart in the reference
 //   k_wavefront_trace<false>  extend (closest hit) for extension rays and connect (any hit) for shadow
-//               rays of one bounce in ONE persistent launch (Kernels.cu:461-498, CUDAIntersect.h)
-//   k_finalize  accumulator / samples (Kernels.cu:181-203)
+//               rays of one bounce in ONE persistent launch (Kernels.cu:461-498, CUDAIntersect.h);
+//               <..., TL> the same over a two-level scene (Kernels.cu:226-303)
+//   k_fold      per-sample radiance folded into the accumulator in sample order, accumulator / samples, and — for a
+//               tile-sharded frame — the peer stores into the display device's image (Kernels.cu:181-203)
 //   k_emode     the image model of backends/EmbreeRT/src/Context.cpp:104-300 as one fused kernel
 //
-// B200 design: persistent CTAs sized from the occupancy API (multiples of 148 SMs)
-// pull 32-ray chunks from a device cursor, so no launch depends on a host-read count; the
-// breadth-first prefix of the BVH is staged into shared memory once per CTA with one TMA bulk copy
-// (cp.async.bulk + mbarrier; SASS: UBLKCP); ray / hit / throughput state is float4 SoA moved with
-// 128-bit coalesced loads and stores; queue compaction is warp-aggregated (ballot + popc, one
-// atomic per warp); tensor cores are not used (no dense contraction on this path).
+// B200 design: persistent CTAs sized from the occupancy API (multiples of 148 SMs) pull work from
+// device-resident cursors and queue sizes, so no launch depends on a host-read count and a frame never synchronises with
+// the host; all samples of a frame travel in one wavefront; ray / hit / throughput state is float4 SoA moved with 128-bit
+// coalesced loads and stores (marked evict-first: it streams past a BVH that should stay in L2); the traversal reads
+// 80-byte packed nodes through L1 (a TMA-staged shared-memory prefix — cp.async.bulk + mbarrier, UBLKCP in the SASS —
+// exists for both node formats, setting smem_nodes, and was measured slower than L1 on the default kernels: DESIGN.md
+// 3a); queue compaction is warp-aggregated (ballot + popc, one 64-bit atomic per warp for both queues), the sort-bin ranks
+// use __match_any_sync; tensor cores are not used (no dense contraction on this path).
 #include "kernels.h"
 
 #include "../../include/rfwb200.h"
