@@ -243,3 +243,24 @@ def test_groups_follow_the_placements(product_lib, oracle_lib):
         ctx.render_frame(cam, R.RESET)
     assert frac_bad(g.read_image(), o.read_image()) < 8e-3
     assert g.get_probe_results()[:2] == o.get_probe_results()[:2]
+
+
+def test_two_level_scene_in_a_device_group(product_lib):
+    """The in-process device group (here two ranks on device 0) over a two-level scene: every rank commits its own copy of the
+    group trees; the sharded frame is bit-identical to the single-device two-level frame."""
+    W, H = 200, 100
+    one, sc = product(product_lib, SCENES["soup"], W, H, levels=2, spp=4)
+    grp = R.RenderContext(product_lib, devices=[0, 0])
+    grp.set_setting("levels", 2)
+    S.upload(grp, SCENES["soup"](), W, H)
+    grp.set_setting("spp", 4)
+    assert "levels_in_use=2" in grp.get_settings()
+    cam = sc.camera(W, H)
+    for ctx in (one, grp):
+        ctx.set_probe_index(W // 2, H // 2)
+        ctx.render_frame(cam, R.RESET)
+        ctx.render_frame(cam, R.CONVERGE)
+    assert np.array_equal(one.read_image(), grp.read_image())
+    assert one.get_probe_results() == grp.get_probe_results()
+    assert one.get_frame_counters().as_dict() == grp.get_frame_counters().as_dict()
+    grp.close()
