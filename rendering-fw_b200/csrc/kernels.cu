@@ -194,8 +194,10 @@ __device__ __forceinline__ bool local_to_pixel(const ShardView &sh, uint32_t j, 
 	const uint32_t blk = w >> 5, lane = w & 31u;
 	const uint32_t bpr = sh.tile_w >> 3;
 	const uint32_t by = fast_div(blk, bpr, sh.inv_blocks_per_row), bx = blk - by * bpr;
-	x = tx * sh.tile_w + bx * 8u + (lane & 7u);
-	y = ty * sh.tile_h + by * 4u + (lane >> 3);
+	// inside the 8x4 block the 32 pixels follow a Z curve (bits x0 y0 x1 y1 x2): any aligned run of 4 / 8 / 16 consecutive pixels
+	// is a compact 2x2 / 4x2 / 4x4 patch — the pixels a warp of camera rays holds when the samples of a pixel are neighbours
+	x = tx * sh.tile_w + bx * 8u + ((lane & 1u) | ((lane >> 1) & 2u) | ((lane >> 2) & 4u));
+	y = ty * sh.tile_h + by * 4u + (((lane >> 1) & 1u) | ((lane >> 2) & 2u));
 	return (x < sh.width) & (y < sh.height) & (ty < sh.tiles_y);
 }
 

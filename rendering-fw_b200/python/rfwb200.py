@@ -549,8 +549,8 @@ def shard_pixel_map(width: int, height: int, rank: int, world: int, tile_w: int 
     blk, lane = w >> 5, w & 31
     bpr = tile_w >> 3
     by, bx = blk // bpr, blk % bpr
-    x = tx * tile_w + bx * 8 + (lane & 7)
-    y = ty * tile_h + by * 4 + (lane >> 3)
+    x = tx * tile_w + bx * 8 + ((lane & 1) | ((lane >> 1) & 2) | ((lane >> 2) & 4))  # Z curve inside the 8x4 block (kernels.cu local_to_pixel)
+    y = ty * tile_h + by * 4 + (((lane >> 1) & 1) | ((lane >> 2) & 2))
     ok = (x < width) & (y < height) & (ty < tiles_y)
     return np.where(ok, y * width + x, -1)
 
