@@ -19,10 +19,16 @@
 // oracle/_ref/librfwref_kernels.so, and test_pt_pipeline_matches_reference_cudart_kernels compares this oracle's
 // camera rays (bit-exact), primary hits, per-bounce queue sizes (identical) and accumulated image (1e-5) with it on a
 // scene that keeps D1-D6 below out of play (vectors committed as tests/golden/ref_kernels_vectors.npz).
-// PINNED on reference code: the building blocks and the PT pipeline end to end (generatePrimaryRay, intersect_rays,
-// shade_rays control flow, NEE, connect, the bounce loop).  UNPINNED (restated from source, cited line by line, no
-// executable reference): the EmbreeRT frame loop and the BVH builder (rtbvh is an un-vendored Rust crate; only the
-// in-tree binned-SAH spec exists; the trees are checked against brute force).
+// The E-mode image is pinned the same way: oracle/_ref/librfwref_eframe.so is the per-pixel body of the reference's own
+// EmbreeRT frame loop (Context::render_frame, EmbreeRT/src/Context.cpp:179-282, with retrieve_material :417-476) compiled
+// from the reference tree; Embree's two calls on that path are answered by this oracle's traversal (ref_eframe_shim.cpp),
+// everything around them runs as the reference wrote it, and this oracle's E-mode frame equals it bit for bit
+// (test_emode_frame_matches_the_reference_frame_loop, vectors tests/golden/ref_eframe_vectors.npz).
+// PINNED on reference code: the building blocks, the PT pipeline end to end (generatePrimaryRay, intersect_rays,
+// shade_rays control flow, NEE, connect, the bounce loop) and the E-mode frame around Embree's intersection calls.
+// UNPINNED (restated from source, cited line by line, no executable reference): Embree's own traversal (absent; this
+// oracle's two-level MBVH stands in its place) and the BVH builder (rtbvh is an un-vendored Rust crate; only the in-tree
+// binned-SAH spec exists; the trees are checked against brute force).
 //
 // Two image models are restated:
 //   PT-mode  = the wavefront estimator of backends/CUDART/src/Kernels.cu (+ getShadingData.h,

@@ -6,8 +6,11 @@ Follows RFW/system/src/rfw/geometry/gltf/mesh.cpp:
   * set_pose(weights)   :126-148 morph targets: v = pose0 + sum_j w_j pose_j (normals likewise, not renormalised)
   * update_triangles()  :428-449 vertex0..2 / vN0..2 from the indexed vertices, N = normalize(cross(v1-v0, v2-v0))
   * joint matrices      node.cpp:97-104  J[j] = inverse(meshNode.combined) * jointNode.combined * inverseBind[j]
-Parity of this restatement is unpinned (the reference has no tests or vectors for it); the GPU kernels
-(rendering-fw_b200/csrc/geometry.cu) are compared against it within 2e-5 relative.
+Parity: the skinning step is pinned on the reference's own SIMD math (RFW/system/math/src/rfw/math.h compiled from the reference
+tree around the loop body of mesh.cpp:30-45, oracle/_ref/librfwref_skin.so; vectors tests/golden/ref_skin_vectors.npz —
+vertices bit for bit, normals within 1 ulp); morph targets and update_triangles are restated from source, unpinned (the
+reference has no tests or vectors for them).  The GPU kernels (rendering-fw_b200/csrc/geometry.cu) are compared
+against this file within 2e-5 relative and against the same reference vectors.
 """
 from __future__ import annotations
 
