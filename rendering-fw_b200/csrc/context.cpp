@@ -2049,7 +2049,7 @@ extern "C"
 		else if (k == "sort_dir_bits")
 		{
 			const int n = atoi(v.c_str());
-			REQUIRE(n == 3 || n == 5, "sort_dir_bits must be 3 (octant) or 5 (octant x dominant axis)");
+			REQUIRE(n == 3 || n == 5 || n == 6, "sort_dir_bits must be 3 (octant), 5 (octant x dominant axis) or 6 (8 x 8 octahedral map)");
 			c->rs.sort_dir_bits = n;
 		}
 		else if (k == "sort_major")

@@ -251,6 +251,19 @@ __device__ __forceinline__ uint32_t ray_bin(const SortGrid &g, int cell_bits, in
 		const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
 		oct |= (ax >= ay ? (ax >= az ? 0u : 2u) : (ay >= az ? 1u : 2u)) << 3;
 	}
+	if (dir_bits == 6) // octahedral map of the direction, 8 x 8 bins
+	{
+		const float inv = 1.0f / (fabsf(dx) + fabsf(dy) + fabsf(dz) + 1e-30f);
+		float u = dx * inv, v = dy * inv;
+		if (dz < 0.0f)
+		{
+			const float tu = (1.0f - fabsf(v)) * (u < 0.0f ? -1.0f : 1.0f);
+			v = (1.0f - fabsf(u)) * (v < 0.0f ? -1.0f : 1.0f);
+			u = tu;
+		}
+		const int iu = min(max(int((u * 0.5f + 0.5f) * 8.0f), 0), 7), iv = min(max(int((v * 0.5f + 0.5f) * 8.0f), 0), 7);
+		oct = uint32_t(iu) | (uint32_t(iv) << 3);
+	}
 	return dir_major ? ((oct << (3 * cell_bits)) | cell) : ((cell << dir_bits) | oct);
 }
 
