@@ -73,7 +73,11 @@ def workload_name(sc, cfg):
 
 
 def data_note(sc):
-    return "synthetic (procedural stand-in)" if "atrium" in sc.name else "reference assets baked as shipped (geometry, textures, sky) + deterministic seeds"
+    if "atrium" in sc.name or sc.name == "config4":
+        return "synthetic (procedural stand-in: the baked reference asset is absent)"
+    if "cornell" in sc.name:
+        return "synthetic (the procedural Cornell box of SURVEY.md §8d config 1) + deterministic seeds"
+    return "reference assets baked as shipped (geometry, textures, sky; config 4: the CesiumMan mesh, skin and animation) + deterministic seeds"
 
 
 def base_config(sc, cfg, n, gpus):
