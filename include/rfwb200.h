@@ -444,6 +444,17 @@ RFWB200_API int rfwb200_host_tlas_check(const float *boxes6, size_t n_boxes, con
 										size_t n_rays, uint64_t *nodes_out, int32_t *depth_out, uint64_t *structure_errors_out,
 										uint64_t *ray_mismatches_out, uint64_t *boxes_hit_out);
 
+/* The grouping rule of two-level scenes (rfwb200_update with "levels" = 2 | auto): meshes placed by exactly the same list of
+ * (transform, normal matrix) pairs share ONE tree, and every entry of that list is ONE top-level instance (the reference keeps one
+ * tree per mesh, RFW/system/bvh/src/top_level_bvh.cpp:17-102).  Inputs: per instance its mesh (or -1), column-major mat4 and mat3.
+ * Outputs: the group of every mesh (-1: not placed), the number of groups and of top-level instances, and the table the kernels read:
+ * for top-level instance i = 0, 1, ... (groups in order, list entries in order) one row with the caller's instance index of every
+ * member mesh (inst_map_size_out entries in all; the first inst_map_capacity are written). */
+RFWB200_API int rfwb200_host_group_check(const int32_t *mesh_of_instance, const float *transforms16, const float *normals9,
+										 size_t n_instances, size_t n_meshes, int32_t *group_of_mesh_out, uint64_t *groups_out,
+										 uint64_t *top_level_instances_out, uint32_t *inst_map_out, size_t inst_map_capacity,
+										 uint64_t *inst_map_size_out);
+
 #ifdef __cplusplus
 } /* extern "C" */
 

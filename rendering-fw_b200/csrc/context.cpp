@@ -122,6 +122,73 @@ inline void mul_mat3(const float *m, const float *p, float *o)
 }
 } // namespace
 
+namespace
+{
+// Two-level scenes: the unit below the top level is a GROUP of meshes that are placed by exactly the same list of (transform,
+// normal matrix) pairs (update_two_level).  placed[mesh] = that mesh's placements sorted bytewise (ties by instance index);
+// groups = member meshes (ascending) of every group, groups ordered by their first member.  Entry j of every member's list is
+// the same matrix: it becomes top-level instance j of the group.
+struct Placement
+{
+	float m[25]; // transform[16] + normal[9]
+	uint32_t instance;
+};
+void group_by_placement(const std::vector<HostInstance> &instances, const std::vector<uint8_t> &mesh_has_triangles,
+						std::vector<std::vector<Placement>> &placed, std::vector<std::vector<uint32_t>> &groups)
+{
+	const size_t nm = mesh_has_triangles.size();
+	placed.assign(nm, {});
+	groups.clear();
+	for (size_t ii = 0; ii < instances.size(); ii++)
+	{
+		const HostInstance &in = instances[ii];
+		if (in.mesh < 0 || size_t(in.mesh) >= nm || !mesh_has_triangles[in.mesh])
+			continue;
+		Placement pl;
+		memcpy(pl.m, in.transform, sizeof(float) * 16);
+		memcpy(pl.m + 16, in.normal, sizeof(float) * 9);
+		pl.instance = uint32_t(ii);
+		placed[in.mesh].push_back(pl);
+	}
+	for (auto &v : placed)
+		std::sort(v.begin(), v.end(), [](const Placement &x, const Placement &y) {
+			const int r = memcmp(x.m, y.m, sizeof(x.m));
+			return r != 0 ? r < 0 : x.instance < y.instance;
+		});
+	std::vector<size_t> order; // meshes that are placed at all
+	for (size_t mi = 0; mi < nm; mi++)
+		if (!placed[mi].empty())
+			order.push_back(mi);
+	auto same_list = [&](size_t x, size_t y) {
+		if (placed[x].size() != placed[y].size())
+			return false;
+		for (size_t k = 0; k < placed[x].size(); k++)
+			if (memcmp(placed[x][k].m, placed[y][k].m, sizeof(placed[x][k].m)) != 0)
+				return false;
+		return true;
+	};
+	std::sort(order.begin(), order.end(), [&](size_t x, size_t y) {
+		if (placed[x].size() != placed[y].size())
+			return placed[x].size() < placed[y].size();
+		for (size_t k = 0; k < placed[x].size(); k++)
+		{
+			const int r = memcmp(placed[x][k].m, placed[y][k].m, sizeof(placed[x][k].m));
+			if (r != 0)
+				return r < 0;
+		}
+		return x < y;
+	});
+	for (size_t k = 0; k < order.size(); k++)
+	{
+		if (k == 0 || !same_list(order[k - 1], order[k]))
+			groups.emplace_back();
+		groups.back().push_back(uint32_t(order[k]));
+	}
+	std::sort(groups.begin(), groups.end(), [](const std::vector<uint32_t> &x, const std::vector<uint32_t> &y) { return x[0] < y[0]; });
+}
+
+} // namespace
+
 // One host thread per further device of an in-process group: it enqueues that device's frame while the calling thread
 // enqueues its own (a frame is ~20 asynchronous API calls per device; issued one device after the other they would
 // stagger the start of eight GPUs by half a millisecond).
@@ -1537,61 +1604,14 @@ extern "C"
 		const int threads = int(std::max(1u, std::thread::hardware_concurrency()));
 
 		// ---- groups: meshes with identical sorted lists of (transform, normal matrix) -----------------------------------------
-		struct Placement
-		{
-			float m[25]; // transform[16] + normal[9]
-			uint32_t instance;
-		};
-		std::vector<std::vector<Placement>> placed(nm);
-		for (size_t ii = 0; ii < c->instances.size(); ii++)
-		{
-			const HostInstance &in = c->instances[ii];
-			if (in.mesh < 0 || size_t(in.mesh) >= nm || c->meshes[in.mesh].triangles.empty())
-				continue;
-			Placement pl;
-			memcpy(pl.m, in.transform, sizeof(float) * 16);
-			memcpy(pl.m + 16, in.normal, sizeof(float) * 9);
-			pl.instance = uint32_t(ii);
-			placed[in.mesh].push_back(pl);
-		}
-		auto less_pl = [](const Placement &x, const Placement &y) {
-			const int r = memcmp(x.m, y.m, sizeof(x.m));
-			return r != 0 ? r < 0 : x.instance < y.instance;
-		};
-		for (auto &v : placed)
-			std::sort(v.begin(), v.end(), less_pl);
-		std::vector<size_t> order; // meshes that are placed at all, grouped
-		for (size_t mi = 0; mi < nm; mi++)
-			if (!placed[mi].empty())
-				order.push_back(mi);
-		auto same_list = [&](size_t x, size_t y) {
-			if (placed[x].size() != placed[y].size())
-				return false;
-			for (size_t k = 0; k < placed[x].size(); k++)
-				if (memcmp(placed[x][k].m, placed[y][k].m, sizeof(placed[x][k].m)) != 0)
-					return false;
-			return true;
-		};
-		auto less_list = [&](size_t x, size_t y) {
-			if (placed[x].size() != placed[y].size())
-				return placed[x].size() < placed[y].size();
-			for (size_t k = 0; k < placed[x].size(); k++)
-			{
-				const int r = memcmp(placed[x][k].m, placed[y][k].m, sizeof(placed[x][k].m));
-				if (r != 0)
-					return r < 0;
-			}
-			return x < y;
-		};
-		std::sort(order.begin(), order.end(), less_list);
+		std::vector<std::vector<Placement>> placed;
 		std::vector<std::vector<uint32_t>> groups; // member meshes, ascending
-		for (size_t k = 0; k < order.size(); k++)
 		{
-			if (k == 0 || !same_list(order[k - 1], order[k]))
-				groups.emplace_back();
-			groups.back().push_back(uint32_t(order[k]));
+			std::vector<uint8_t> has_tris(nm, 0);
+			for (size_t mi = 0; mi < nm; mi++)
+				has_tris[mi] = c->meshes[mi].triangles.empty() ? 0 : 1;
+			group_by_placement(c->instances, has_tris, placed, groups);
 		}
-		std::sort(groups.begin(), groups.end(), [](const std::vector<uint32_t> &x, const std::vector<uint32_t> &y) { return x[0] < y[0]; });
 
 		// ---- one tree per group, cached by its member list -----------------------------------------------------------------------
 		std::vector<Ctx::GroupTree> trees(groups.size());
@@ -3135,6 +3155,44 @@ extern "C"
 		if (sah_out)
 			*sah_out = bvh.sah_cost;
 		return walk_bvh4_host(bvh, bt, origins3, dirs3, n_rays, t_out, tri_out, visits_out);
+	}
+
+	// Self check of the grouping rule of two-level scenes without a GPU: which meshes share a tree, how many top-level instances
+	// the scene has, and which caller instance stands behind (top-level instance, member) — the table the kernels read.
+	int rfwb200_host_group_check(const int32_t *mesh_of_instance, const float *transforms16, const float *normals9, size_t n_instances,
+								 size_t n_meshes, int32_t *group_of_mesh_out, uint64_t *groups_out, uint64_t *top_level_instances_out,
+								 uint32_t *inst_map_out, size_t inst_map_capacity, uint64_t *inst_map_size_out)
+	{
+		REQUIRE((mesh_of_instance && transforms16 && normals9) || n_instances == 0, "bad arguments");
+		REQUIRE(group_of_mesh_out && groups_out && top_level_instances_out && inst_map_size_out, "bad arguments");
+		std::vector<HostInstance> inst(n_instances);
+		for (size_t i = 0; i < n_instances; i++)
+		{
+			inst[i].mesh = mesh_of_instance[i];
+			memcpy(inst[i].transform, transforms16 + 16 * i, sizeof(float) * 16);
+			memcpy(inst[i].normal, normals9 + 9 * i, sizeof(float) * 9);
+		}
+		std::vector<std::vector<Placement>> placed;
+		std::vector<std::vector<uint32_t>> groups;
+		group_by_placement(inst, std::vector<uint8_t>(n_meshes, 1), placed, groups);
+		for (size_t m = 0; m < n_meshes; m++)
+			group_of_mesh_out[m] = -1;
+		uint64_t tl = 0, map_size = 0;
+		for (size_t g = 0; g < groups.size(); g++)
+		{
+			for (uint32_t m : groups[g])
+				group_of_mesh_out[m] = int32_t(g);
+			const size_t k = placed[groups[g][0]].size();
+			for (size_t j = 0; j < k; j++, tl++)
+				for (uint32_t m : groups[g])
+				{
+					if (inst_map_out && map_size < inst_map_capacity)
+						inst_map_out[map_size] = placed[m][j].instance;
+					map_size++;
+				}
+		}
+		*groups_out = groups.size(), *top_level_instances_out = tl, *inst_map_size_out = map_size;
+		return RFWB200_OK;
 	}
 
 	// Self check of the top-level builder of two-level scenes without a GPU: every box is named by exactly one leaf slot, every

@@ -314,3 +314,54 @@ def test_clustering_builds_a_better_sponza_tree_than_the_radix_tree(product_lib)
     assert np.array_equal(t < 1e33, t_ref < 1e33) and np.allclose(t[t < 1e33], t_ref[t < 1e33], rtol=2e-4, atol=1e-5 * ext)
     print("cost per ray", cost)
     assert cost["ploc"] < 0.85 * cost["lbvh"], cost
+
+
+# ---- grouping rule of two-level scenes (csrc/context.cpp group_by_placement) ------------------------------------------------
+def host_group_check(lib, mesh_of_instance, transforms, normals, n_meshes):
+    f = lib.fn("host_group_check", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_size_t, C.c_void_p])
+    moi = np.ascontiguousarray(mesh_of_instance, np.int32)
+    T = np.ascontiguousarray(np.asarray(transforms, np.float32).transpose(0, 2, 1).reshape(len(moi), 16))  # column-major, as set_instance takes it
+    N = np.ascontiguousarray(np.asarray(normals, np.float32).transpose(0, 2, 1).reshape(len(moi), 9))
+    group = np.zeros(n_meshes, np.int32)
+    groups, tl, size = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    table = np.zeros(max(1, len(moi) * 4), np.uint32)
+    rc = f(moi.ctypes.data, T.ctypes.data, N.ctypes.data, len(moi), n_meshes, group.ctypes.data, C.byref(groups), C.byref(tl), table.ctypes.data, len(table),
+           C.byref(size))
+    assert rc == 0, lib.last_error()
+    return group, groups.value, tl.value, table[: size.value]
+
+
+def test_meshes_placed_by_the_same_transforms_share_a_tree(product_lib):
+    """config 3's construction in small: a model of 5 meshes placed by the same 7 transforms (in a different instance order per mesh),
+    one mesh of the model moved on its own in one copy, a light placed once, a mesh that is never instanced."""
+    rng = np.random.default_rng(4)
+    copies = [S.translate(*rng.uniform(-50, 50, 3)) @ S.rotate_y(float(rng.uniform(0, 360))) @ S.scale(0.2) for _ in range(7)]
+    inst = []  # (mesh, matrix)
+    for m in range(5):
+        for k in rng.permutation(7):
+            inst.append((m, copies[k]))
+    inst.append((5, S.translate(0, 60, 0)))  # the light
+    rng.shuffle(inst)
+    moi = [m for m, _ in inst]
+    T = np.array([np.asarray(M, np.float64) for _, M in inst])
+    Nm = np.array([np.linalg.inv(M[:3, :3]).T for M in T])
+    group, n_groups, n_tl, table = host_group_check(product_lib, moi, T, Nm, 7)
+    assert n_groups == 2 and n_tl == 7 + 1
+    assert len(set(group[:5])) == 1 and group[5] not in (group[0], -1) and group[6] == -1  # mesh 6 is never placed
+    assert len(table) == 7 * 5 + 1
+    rows = table[: 35].reshape(7, 5)  # top-level instance j of the model: the caller's instance of every member mesh
+    for row in rows:
+        assert [moi[i] for i in row] == [0, 1, 2, 3, 4]  # members in ascending mesh order
+        assert all(np.array_equal(T[i].astype(np.float32), T[row[0]].astype(np.float32)) for i in row)  # all placed by the same matrix
+    assert sorted(rows.reshape(-1).tolist() + [int(table[35])]) == list(range(len(inst)))  # every instance is named exactly once
+    # one mesh of one copy nudged by one float step: it leaves the group, the other four stay together
+    victim = int(rows[3][2])
+    T2 = T.copy()
+    T2[victim, 0, 3] = np.nextafter(np.float32(T2[victim, 0, 3]), np.float32(1e9))
+    group2, n_groups2, n_tl2, _ = host_group_check(product_lib, moi, T2, Nm, 7)
+    assert n_groups2 == 3 and n_tl2 == 7 + 7 + 1
+    assert group2[2] != group2[0] and len({group2[0], group2[1], group2[3], group2[4]}) == 1
+    # no instances at all
+    g0, n0, t0, tab0 = host_group_check(product_lib, [], np.zeros((0, 4, 4)), np.zeros((0, 3, 3)), 3)
+    assert n0 == 0 and t0 == 0 and len(tab0) == 0 and (g0 == -1).all()
