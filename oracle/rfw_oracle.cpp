@@ -2383,6 +2383,50 @@ extern "C"
 		});
 		return RFWB200_OK;
 	}
+	// Stage-level shade (Kernels.cu:571-794 over a caller-supplied wavefront): path i = (O, D, T, hit) in the layout of
+	// the reference's path buffers — O.w = (pathIndex << 8) | flags with pathIndex = y * width + x, D.w = packed normal of
+	// the previous vertex, T.w = pdf of the sampled direction, hit = (bits(w0_16 | w1_16 << 16), bits(instance),
+	// bits(primitive) or -1 for a miss, t).  Runs shade_path — the very function the oracle's frames run — on every path
+	// and returns its three outputs per path, unset ones zeroed: flags_out bit 0 = extension ray written (ext_O/D/T),
+	// bit 1 = connect entry written (con_O/D/E), bit 2 = contribution accumulated (acc, xyz).  The context's own
+	// max_path_length decides whether a path of this length may continue; the probe is left alone.
+	ORACLE_API int rfworacle_shade_stage(rfworacle_context *c, const rfwb200_camera_view *view, const float *O, const float *D,
+										 const float *T, const float *hit, size_t n, uint32_t path_length, uint32_t samples_taken,
+										 uint32_t *flags_out, float *ext_O, float *ext_D, float *ext_T, float *con_O, float *con_D,
+										 float *con_E, float *acc)
+	{
+		if (!c || !view || !O || !D || !T || !hit || !flags_out || !ext_O || !ext_D || !ext_T || !con_O || !con_D || !con_E || !acc)
+			return fail("bad arguments");
+		for (size_t i = 0; i < n; i++)
+		{
+			const int prim = int(f2u(hit[4 * i + 2]));
+			if (prim < 0)
+				continue;
+			const uint32_t inst = f2u(hit[4 * i + 1]);
+			if (inst >= c->instances.size() || size_t(prim) >= c->meshes[c->instances[inst].mesh].triangles.size())
+				return fail("hit record names an unknown instance or primitive");
+		}
+		const uint32_t px = c->probe_x, py = c->probe_y;
+		c->probe_x = c->probe_y = 0x7fffffffu; // no path index equals the probe pixel
+		parallel_for(int64_t(n), 256, [&](int64_t i) {
+			PathState p;
+			p.O = vec4(O[4 * i], O[4 * i + 1], O[4 * i + 2], O[4 * i + 3]);
+			p.D = vec4(D[4 * i], D[4 * i + 1], D[4 * i + 2], D[4 * i + 3]);
+			p.T = vec4(T[4 * i], T[4 * i + 1], T[4 * i + 2], T[4 * i + 3]);
+			p.hit = vec4(hit[4 * i], hit[4 * i + 1], hit[4 * i + 2], hit[4 * i + 3]);
+			ShadeOut out;
+			shade_path(*c, *view, p, path_length, samples_taken, out);
+			const auto put = [i](float *dst, const vec4 &v) { dst[4 * i] = v.x, dst[4 * i + 1] = v.y, dst[4 * i + 2] = v.z, dst[4 * i + 3] = v.w; };
+			const vec4 zero(0, 0, 0, 0);
+			flags_out[i] = (out.has_ext ? 1u : 0u) | (out.has_shadow ? 2u : 0u) | (out.acc ? 4u : 0u);
+			put(ext_O, out.has_ext ? out.ext.O : zero), put(ext_D, out.has_ext ? out.ext.D : zero), put(ext_T, out.has_ext ? out.ext.T : zero);
+			put(con_O, out.has_shadow ? out.shadow.O : zero), put(con_D, out.has_shadow ? out.shadow.D : zero);
+			put(con_E, out.has_shadow ? out.shadow.E : zero);
+			put(acc, out.acc ? vec4(out.acc_value, 0.0f) : zero);
+		});
+		c->probe_x = px, c->probe_y = py;
+		return RFWB200_OK;
+	}
 
 
 	// ---- hooks for pinning against the reference's own headers (oracle/ref_build, tests/test_ref_pin.py) ----

@@ -308,3 +308,40 @@ def test_config2_bounce_rays_of_the_wavefront_kernel_at_1920x1080(product_lib, o
         else:
             unexplained += 1  # hit on one side, miss on the other: an edge crack (Moller-Trumbore is not watertight)
     assert unexplained <= max(5, 2e-4 * n), unexplained
+
+
+
+
+def test_config2_shade_stage_per_path_at_1920x1080(product_lib, oracle_lib):
+    """k_shade per PATH at the benchmarked resolution.  Whole images of this scene are only comparable statistically (DESIGN.md
+    "Epsilons": which bounce rays re-hit the surface they leave is decided by rounding, in the reference too) — but shading is a
+    function of (ray, hit), so the stage itself can be checked path by path at full scale: the oracle's shade_path
+    (rfworacle_shade_stage; pinned on the reference's kernels through the oracle's frames, tests/test_shade_stage.py) is given the
+    very rays and hit records the product's frame held — all 2,073,600 camera rays with the hits the wavefront kernel found, then the
+    ~1 M depth-1 rays with theirs — and every output is compared per path: extension ray (origin, direction, throughput, pdf, flags),
+    connect entry (origin, direction, length, contribution), accumulated radiance; finally the per-pixel radiance of a one-bounce frame
+    against the oracle's outputs put together with the product's own visibility decisions.  Both builds of the kernel: IEEE and the
+    bench's fast-math one.
+    Tolerances: positions 1e-5 relative to the coordinate magnitude, connect-ray length 1e-5 relative; directions and radiometric values
+    |d| <= tol (values: relative, + 1e-2 absolute floor) with tol = 1e-4 for the IEEE build and 2e-3 for the fast-math build (the
+    unit-scale image tolerance, IMG_TOL); required on >= 99.5 % / 99 % of the paths (a lobe choice or a texel index that flips on a
+    rounding changes the whole entry); paths that emit an entry on one side only <= 1e-3; the flag byte equal on >= 99.99 %."""
+    from stage_common import check_shade_stage_per_path
+
+    W, H = 1920, 1080
+    (g, sc), (o, _) = pair(product_lib, oracle_lib, S.sponza_or_standin, W, H, spp=1)
+    o.set_setting("max_path_length", 2)  # the oracle's stage may continue paths of length 0 and 1 (and emits their connect entries)
+    cam = sc.camera(W, H)
+    results = {}
+    for math_mode, tol, need in (("ieee", 1e-4, 0.995), ("fast", 2e-3, 0.99)):
+        g.set_setting("shade_math", math_mode)
+        fr, report = check_shade_stage_per_path(g, o, cam, W, H, tol, 500_000)
+        print(f"\nshade stage per path at {W}x{H} [{math_mode}, tol {tol:.0e}]")
+        for k, v in report.items():
+            print(f"  {k}: {v}")
+        for k, v in fr.items():
+            print(f"  => {k}: {v:.5f} within tolerance")
+        results[math_mode] = (fr, need)
+    for math_mode, (fr, need) in results.items():
+        for k, v in fr.items():
+            assert v >= (0.9999 if k == "shade(0) flag byte" else need), (math_mode, k, v, need)
