@@ -137,7 +137,8 @@ def _quantiles(e):
 
 def _compare_queue(tag, P, in_pixel, want_mask, want, got_pixel, got, tol, report):
     """`want[k]` = oracle outputs per INPUT path (rows where want_mask), `got` = the product's queue entries (any order, one per
-    path); joined on the pixel.  Returns the fraction of common entries whose every component is within tolerance."""
+    path); joined on the pixel.  Returns (fraction of the common entries whose every component is within tolerance, entries present on
+    one side only as a fraction of the input paths)."""
     row_of = np.full(P, -1, np.int64)
     row_of[in_pixel] = np.arange(len(in_pixel))
     assert (got_pixel >= 0).all() and len(np.unique(got_pixel)) == len(got_pixel), f"{tag}: a path wrote two queue entries"
@@ -147,7 +148,7 @@ def _compare_queue(tag, P, in_pixel, want_mask, want, got_pixel, got, tol, repor
     only_product = int((~both).sum())
     only_oracle = int(want_mask.sum() - both.sum())
     report[f"{tag}: entries"] = f"{len(got_pixel)} (oracle {int(want_mask.sum())}; only product {only_product}, only oracle {only_oracle})"
-    assert only_product + only_oracle <= 1e-3 * max(len(in_pixel), 1) + 4, (tag, only_product, only_oracle)
+    one_sided = (only_product + only_oracle) / max(len(in_pixel), 1)
     r = rows[both]
     ok = np.ones(len(r), bool)
     for k, (ref, val, kind) in got.items():
@@ -168,13 +169,13 @@ def _compare_queue(tag, P, in_pixel, want_mask, want, got_pixel, got, tol, repor
         e = np.where(np.isfinite(e), e, np.inf)
         report[f"{tag}: {k}"] = _quantiles(e) + f"; within {lim:.0e}: {(e <= lim).mean():.5f}"
         ok &= e <= lim
-    return float(ok.mean()) if len(ok) else 1.0
+    return (float(ok.mean()) if len(ok) else 1.0), one_sided
 
 
 def check_shade_stage_per_path(g, o, cam, W, H, tol, min_queue):
     """Renders three 1-sample frames on the product `g` (path length 0, 1, 2), reads the planes its shade launches read and wrote,
     runs the oracle's shade_path on the same (ray, hit) pairs and compares every output per path.  Returns ({what: fraction of the
-    paths within tolerance}, {what: description}).  `o` must hold the same scene with max_path_length >= 2."""
+    paths within tolerance — keys ending in "one-sided": fraction of the paths with an entry on one side only}, {what: description}).  `o` must hold the same scene with max_path_length >= 2."""
     P = W * H
     pix = np.asarray(R.shard_pixel_map(W, H, 0, 1))
     n_items = len(pix)
@@ -211,9 +212,9 @@ def check_shade_stage_per_path(g, o, cam, W, H, tol, min_queue):
     assert live0.sum() == P and np.array_equal(np.sort(pixel0[live0]), np.arange(P))
     s0 = shade_stage(o, cam, O0o[live0], D0[live0], np.ones_like(O0[live0]), hit0o[live0], 0, 0)
     in_pixel0 = pixel0[live0]
-    fr["shade(0) extension"] = _compare_queue("shade(0) extension", P, in_pixel0, (s0["flags"] & 1) != 0, s0, item_pixel(bits(E_O[:, 3]) >> 8),
+    fr["shade(0) extension"], fr["shade(0) extension: one-sided"] = _compare_queue("shade(0) extension", P, in_pixel0, (s0["flags"] & 1) != 0, s0, item_pixel(bits(E_O[:, 3]) >> 8),
                                               ext_spec(E_O, E_D, E_T), tol, report)
-    fr["shade(0) connect"] = _compare_queue("shade(0) connect", P, in_pixel0, (s0["flags"] & 2) != 0, s0, item_pixel(bits(C_E[:, 3])),
+    fr["shade(0) connect"], fr["shade(0) connect: one-sided"] = _compare_queue("shade(0) connect", P, in_pixel0, (s0["flags"] & 2) != 0, s0, item_pixel(bits(C_E[:, 3])),
                                             con_spec(C_O, C_D, C_E), tol, report)
     # flags of the extension rays (specular bit) and the packed normal they carry
     rows = np.full(P, -1, np.int64)
@@ -237,9 +238,9 @@ def check_shade_stage_per_path(g, o, cam, W, H, tol, min_queue):
     E_Oo, hit1o, pixel1, live1 = to_oracle_paths(E_O, hit1, pix, shade)
     assert live1.all()
     s1 = shade_stage(o, cam, E_Oo, E_D, E_T, hit1o, 1, 0)
-    fr["shade(1) extension"] = _compare_queue("shade(1) extension", P, pixel1, (s1["flags"] & 1) != 0, s1, item_pixel(bits(F_O[:, 3]) >> 8),
+    fr["shade(1) extension"], fr["shade(1) extension: one-sided"] = _compare_queue("shade(1) extension", P, pixel1, (s1["flags"] & 1) != 0, s1, item_pixel(bits(F_O[:, 3]) >> 8),
                                               ext_spec(F_O, F_D, F_T), tol, report)
-    fr["shade(1) connect"] = _compare_queue("shade(1) connect", P, pixel1, (s1["flags"] & 2) != 0, s1, item_pixel(bits(G_E[:, 3])),
+    fr["shade(1) connect"], fr["shade(1) connect: one-sided"] = _compare_queue("shade(1) connect", P, pixel1, (s1["flags"] & 2) != 0, s1, item_pixel(bits(G_E[:, 3])),
                                             con_spec(G_O, G_D, G_E), tol, report)
 
     # ---- the one-bounce frame per pixel: oracle outputs + the product's own visibility decisions (the sample slot's .w counts the

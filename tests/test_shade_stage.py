@@ -184,7 +184,7 @@ def test_per_path_checker_on_an_emulated_product(oracle_lib, size):
     o.set_setting("max_path_length", 2)
     cam = sc.camera(W, H)
     fr, report = check_shade_stage_per_path(EmulatedProduct(o, sc, W, H), o, cam, W, H, 1e-6, 100)
-    assert all(v == 1.0 for v in fr.values()), (fr, report)
+    assert all(v == (0.0 if k.endswith("one-sided") else 1.0) for k, v in fr.items()), (fr, report)
     assert "only product 0, only oracle 0" in report["shade(0) extension: entries"] and "only product 0, only oracle 0" in report["shade(1) connect: entries"]
     fr, report = check_shade_stage_per_path(EmulatedProduct(o, sc, W, H, spoil=1.01), o, cam, W, H, 1e-3, 100)
     # (shade(1) is then given the spoiled throughputs on both sides, so only the stage that wrote them stands out)
