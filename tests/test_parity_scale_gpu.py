@@ -320,7 +320,7 @@ def _shade_stage_per_path(product_lib, oracle_lib, scene_fn, what):
     o.set_setting("max_path_length", 2)  # the oracle's stage may continue paths of length 0 and 1 (and emits their connect entries)
     cam = sc.camera(W, H)
     results = {}
-    for math_mode, tol, need in (("ieee", 1e-4, 0.995), ("fast", 2e-3, 0.99)):
+    for math_mode, tol, need in (("ieee", 1e-4, 0.998), ("fast", 2e-3, 0.9985)):
         g.set_setting("shade_math", math_mode)
         fr, report = check_shade_stage_per_path(g, o, cam, W, H, tol, 500_000)
         print(f"\n{what}: shade stage per path at {W}x{H} [{math_mode}, tol {tol:.0e}]")
@@ -332,7 +332,7 @@ def _shade_stage_per_path(product_lib, oracle_lib, scene_fn, what):
     for math_mode, (fr, need) in results.items():
         for k, v in fr.items():
             if k.endswith("one-sided"):
-                assert v <= 1e-3, (math_mode, k, v)
+                assert v <= 1e-4, (math_mode, k, v)
             else:
                 assert v >= (0.9999 if k == "shade(0) flag byte" else need), (math_mode, k, v, need)
 
@@ -349,8 +349,15 @@ def test_config2_shade_stage_per_path_at_1920x1080(product_lib, oracle_lib):
     bench's fast-math one.
     Tolerances: positions 1e-5 relative to the coordinate magnitude, connect-ray length 1e-5 relative; directions and radiometric values
     |d| <= tol (values: relative, + 1e-2 absolute floor) with tol = 1e-4 for the IEEE build and 2e-3 for the fast-math build (the
-    unit-scale image tolerance, IMG_TOL); required on >= 99.5 % / 99 % of the paths (a lobe choice or a texel index that flips on a
-    rounding changes the whole entry); paths that emit an entry on one side only <= 1e-3; the flag byte equal on >= 99.99 %."""
+    unit-scale image tolerance, IMG_TOL); required on >= 99.8 % / 99.85 % of the paths; paths that emit an entry on one side only
+    <= 1e-4; the flag byte equal on >= 99.99 %.
+    Measured (profiles/r02/r02_shade_stage_per_path.log): the SAME 977,140 / 1,778,666 / 532,996 / 576,303 paths emit an extension ray /
+    connect entry at depth 0 / 1 on both sides (none on one side only), flag bytes all equal; origins, directions and connect lengths of
+    ALL of them within 4e-7 / 2e-6 (IEEE) and 4e-5 (fast-math directions); throughputs, pdfs and contributions: median 1e-7, 99th
+    percentile 1e-6 — and 0.09-0.15 % of the paths with another colour (up to 0.8 relative).  Those are the reference's own texel
+    fetch: (tc + 1000) * width in float32 quantises the footprint to 1/8 texel, so the last bit of the interpolated texture coordinate
+    picks the colour — the strict and the FMA-contracted build of the ORACLE differ in the same 0.15 % on identical inputs
+    (tests/test_shade_stage.py::test_texel_fetch_is_decided_by_the_last_bit_in_the_reference_formula)."""
     _shade_stage_per_path(product_lib, oracle_lib, S.sponza_or_standin, "config 2")
 
 
