@@ -373,7 +373,7 @@ struct rfwb200_context
 	const rfwb200_context *build_donor = nullptr; // rank 0 of the group: its host-built tree is adopted instead of built again
 
 	// ---- settings / state ------------------------------------------------------------------------------
-	RenderSettings rs{2, 10.0f, 1e-5f, 1, 0, 8, nullptr, -1, 9, 1, 0, 9, 1, 5, 0, 0, 5}; // bounces: packed nodes + unsorted connect rays; camera rays: fp32 nodes (DESIGN.md sweep) // smem_nodes 0: measured fastest on B200 (DESIGN.md "staging")
+	RenderSettings rs{2, 10.0f, 1e-5f, 1, 0, 8, nullptr, -1, 9, 1, 0, 9, 1, 5, 0, 0, 5, 0}; // bounces: packed nodes + unsorted connect rays; camera rays: fp32 nodes (DESIGN.md sweep) // smem_nodes 0: measured fastest on B200 (DESIGN.md "staging")
 	int spp = 1;
 	bool mode_pt = true;
 	LaunchDims dims{};
@@ -2072,6 +2072,11 @@ extern "C"
 			REQUIRE(n == 3 || n == 5 || n == 6, "sort_dir_bits must be 3 (octant), 5 (octant x dominant axis) or 6 (8 x 8 octahedral map)");
 			c->rs.sort_dir_bits = n;
 		}
+		else if (k == "shade_loop")
+		{
+			REQUIRE(v == "cursor" || v == "static", "shade_loop must be 'cursor' (32 paths per warp from a device cursor) or 'static' (grid strides, next job prefetched)");
+			c->rs.shade_static = (v == "static") ? 1 : 0;
+		}
 		else if (k == "sort_major")
 		{
 			REQUIRE(v == "cell" || v == "octant", "sort_major must be 'cell' or 'octant'");
@@ -2186,7 +2191,7 @@ extern "C"
 							  "\nsort_major=cell|octant\naov=on|off\nfetch_chunk=" + std::to_string(c->rs.fetch_chunk) + "\nfetch_threshold=" + std::to_string(c->rs.fetch_threshold) +
 							  "\ntrace_variant=" + std::to_string(c->rs.trace_variant) + "\nprimary_variant=" +
 							  std::to_string(c->rs.primary_variant) + "\nbvh=4|8\nbuilder=sbvh|lbvh|ploc\nspatial_splits=on|off\nrefit=device|host" +
-							  "\nshade_math=fast|ieee\ntiming=on|off\nlevels=1|2|auto\nflatten_budget=" + std::to_string(c->flatten_budget) + "\nlevels_in_use=" + (c->two_level ? "2" : "1") + "\ntop_level_instances=" + std::to_string(c->two_level ? c->tl_table.size() : 0) +
+							  "\nshade_math=fast|ieee\nshade_loop=" + (c->rs.shade_static ? "static" : "cursor") + "\ntiming=on|off\nlevels=1|2|auto\nflatten_budget=" + std::to_string(c->flatten_budget) + "\nlevels_in_use=" + (c->two_level ? "2" : "1") + "\ntop_level_instances=" + std::to_string(c->two_level ? c->tl_table.size() : 0) +
 							  "\ninstance_groups=" + std::to_string(c->two_level ? c->tl_groups : 0) + "\n";
 		snprintf(buf, buf_size, "%s", s.c_str());
 		return RFWB200_OK;

@@ -257,6 +257,7 @@ struct RenderSettings
 	int sort_dir_major;	 // 1: the octant is the most significant part of the key, 0: the cell is
 	int fetch_chunk;	 // 0: idle lanes take the next entries of one shared front; > 0: a warp claims a private run of that many entries
 	int sort_dir_bits;	 // direction part of the re-ordering key: 3 = octant, 5 = octant x dominant axis (24 bins)
+	int shade_static;	 // 1: k_shade walks the queue in grid strides and prefetches the next job's state (no work cursor)
 };
 constexpr int SORT_CHUNK = 4096; // bins scanned by one CTA of k_sort_scan
 

@@ -2219,17 +2219,41 @@ __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, c
 	if (binning)
 		grid = *wf.grid;
 	uint32_t *seen = wf.ext_seen + size_t(bv.index * MAX_DEPTH_SLOTS + pathLength) * MAX_BATCH_SPP;
-	for (;;)
+	// rs.shade_static (setting shade_loop=static): no work cursor — warp w of the grid shades jobs [32 w, 32 w + 32), then the same
+	// 32 jobs one grid further on, and so on.  The queue size is known when the launch starts and paths cost about the same, so
+	// nothing needs balancing; what goes away is one L2 round trip (the cursor's atomic) in front of every 32 paths of a kernel
+	// that waits on memory most of the time, and knowing the next job early lets the warp pull that job's state lines towards L2
+	// while it shades this one (prefetch: no register held across the body).
+	const uint32_t stride = gridDim.x * blockDim.x;
+	uint32_t job = blockIdx.x * blockDim.x + threadIdx.x;
+	for (;; job += stride)
 	{
 		// (issuing the atomic for the NEXT chunk before shading the current one was measured: one more live register, 430
 		// instead of 274 bytes of spills, shade 3.13 instead of 3.00 ms per frame — profiles/r02/sweep6)
-		uint32_t base = 0;
-		if (lane == 0)
-			base = atomicAdd(&curc->shade_cursor, 32u);
-		base = __shfl_sync(0xffffffffu, base, 0);
-		if (base >= n_paths)
-			break;
-		const uint32_t job = base + lane;
+		if (rs.shade_static)
+		{
+			if (job - lane >= n_paths)
+				break;
+			const uint32_t nj = job + stride;
+			if (nj < n_paths)
+			{
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(&wf.hit[nj]));
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(&wf.O[buf][nj]));
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(&wf.D[buf][nj]));
+				if (pathLength != 0)
+					asm volatile("prefetch.global.L2 [%0];" ::"l"(&wf.T[buf][nj]));
+			}
+		}
+		else
+		{
+			uint32_t base = 0;
+			if (lane == 0)
+				base = atomicAdd(&curc->shade_cursor, 32u);
+			base = __shfl_sync(0xffffffffu, base, 0);
+			if (base >= n_paths)
+				break;
+			job = base + lane;
+		}
 
 		bool do_acc = false, do_shadow = false, do_ext = false, dead = false;
 		V3 accv = mk(0.f);
@@ -2241,13 +2265,25 @@ __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, c
 		if (job < n_paths)
 		{
 			const float4 hitData = LD_SS(&wf.hit[job]);
+			// shade_static: the path's state is requested together with its hit record (one trip to memory instead of two in a
+			// row; a padded work item's state is allocated like any other, so the loads need not wait for the test below)
+			float4 O4, D4, T4 = make_float4(1.f, 1.f, 1.f, 1.f);
+			if (rs.shade_static)
+			{
+				O4 = LD_SS(&wf.O[buf][job]), D4 = LD_SS(&wf.D[buf][job]);
+				if (pathLength != 0)
+					T4 = LD_SS(&wf.T[buf][job]);
+			}
 			const int primIdx = __float_as_int(hitData.z);
 			dead = primIdx == PRIM_DEAD;
 			if (!dead)
 			{
-				const float4 O4 = LD_SS(&wf.O[buf][job]);
-				const float4 D4 = LD_SS(&wf.D[buf][job]);
-				const float4 T4 = pathLength == 0 ? make_float4(1.f, 1.f, 1.f, 1.f) : LD_SS(&wf.T[buf][job]);
+				if (!rs.shade_static)
+				{
+					O4 = LD_SS(&wf.O[buf][job]), D4 = LD_SS(&wf.D[buf][job]);
+					if (pathLength != 0)
+						T4 = LD_SS(&wf.T[buf][job]);
+				}
 				uint32_t flags = __float_as_uint(O4.w) & 0xFFu;
 				V3 throughput = mk(T4.x, T4.y, T4.z);
 				const float bsdfPdf = T4.w;

@@ -54,5 +54,5 @@ for var in a.variants.split(";"):
                       "mean": float(img[..., :3].mean()), "bvh": ctx.get_bvh_info()}), flush=True)
     for k, v in kvs:  # back to the defaults
         ctx.set_setting(k, {"trace_variant": "9", "primary_variant": "9", "bvh": "4", "shadow_cache": "off", "primary_cache": "on", "sort": "on",
-                               "sort_cell_bits": "5", "sort_major": "cell", "spp_batch": "0", "fetch_threshold": "8", "fetch_chunk": "0", "sample_layout": "pixel", "sort_dir_bits": "5"}.get(k, v))
+                               "sort_cell_bits": "5", "sort_major": "cell", "spp_batch": "0", "fetch_threshold": "8", "fetch_chunk": "0", "sample_layout": "pixel", "sort_dir_bits": "5", "shade_loop": "cursor"}.get(k, v))
     ctx.set_setting("primary_variant", "9")
