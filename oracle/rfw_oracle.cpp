@@ -63,6 +63,12 @@
 //   x = 123456789 ^ WangHash(p*16789 + s*1791), y,z,w = reference defaults; shadow rays use
 //   t in (1e-4, dist*(1-1e-4)) so a light's own triangle never shadows its centroid.
 //
+// Stage-level entries (rfworacle_generate_primary, _trace_closest, _trace_occluded, _shade_stage) expose the functions the
+// frames above are made of, one stage at a time, over caller-supplied rays / paths: a frame composed from them equals
+// rfworacle_render_frame's bit for bit (tests/test_shade_stage.py), so whatever is checked against a stage entry — the
+// product's launches per ray and per path at the benchmarked scale, tests/test_parity_scale_gpu.py — is checked against
+// the pinned pipeline.
+//
 // Build: g++ -O2 -ffp-contract=off -pthread -shared -fPIC (see oracle/Makefile).
 
 #include "../include/rfwb200.h"
