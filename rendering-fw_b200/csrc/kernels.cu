@@ -2201,8 +2201,9 @@ __device__ V3 RandomPointOnLight(const SceneView &sc, float r0, float r1, V3 I, 
 // with warp-aggregated slot allocation.
 // ------------------------------------------------------------------------------------------------
 #ifndef SHADE_MINB
-#define SHADE_MINB 7 // 72 registers (162 B of spills): shade 3.37 ms/frame vs 3.45 at 6 (80 registers) and 3.44 at 5 (96); IEEE build of an
-					 // earlier kernel: 4.94 at 6, 5.67 at 4, 4.92 at 8
+#define SHADE_MINB 7 // 72 registers: shade 3.37 ms/frame vs 3.45 at 6 (80 registers) and 3.44 at 5 (96); IEEE build of an
+					 // earlier kernel: 4.94 at 6, 5.67 at 4, 4.92 at 8.  Final kernel of round 2 (profiles/r02/sweep19): 2.93 / 2.89 /
+					 // 2.88 / 2.92 ms at 6 / 7 / 8 / 9 CTAs per SM (80 / 72 / 64 / 56 registers) — flat
 #endif
 __global__ void __launch_bounds__(128, SHADE_MINB) K_SHADE(const SceneView sc, const ShardView sh, const WavefrontView wf,
 											  const RenderSettings rs, const BatchView bv, const uint32_t pathLength,
