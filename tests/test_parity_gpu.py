@@ -770,13 +770,15 @@ def test_config5_lights_sharded_4k_tile_layout(product_lib):
 # ---- wavefront batching and re-ordering ---------------------------------------------------------------------
 @pytest.mark.parametrize("settings", [{"spp_batch": 1}, {"spp_batch": 3}, {"sort": "off"}, {"sort_cell_bits": 3, "sort_major": "octant"},
                                       {"sort_cell_bits": 6, "sort_dir_bits": 3}, {"sort": "off", "spp_batch": 2}, {"sample_layout": "planes"},
-                                      {"sample_layout": "planes", "spp_batch": 3}, {"sample_layout": "planes", "sort": "off", "spp_batch": 5}, {"sort_dir_bits": 3}, {"sample_layout": "planes", "sort_dir_bits": 3}])
+                                      {"sample_layout": "planes", "spp_batch": 3}, {"sample_layout": "planes", "sort": "off", "spp_batch": 5}, {"sort_dir_bits": 3}, {"sample_layout": "planes", "sort_dir_bits": 3},
+                                      {"shade_loop": "static"}, {"shade_loop": "static", "sort": "off", "spp_batch": 3}])
 @pytest.mark.parametrize("scene", ["cornell", "soup"])
 def test_wavefront_batching_and_reordering_do_not_change_a_single_bit(product_lib, scene, settings):
     """All samples of a frame travel in one wavefront (spp_batch) and the bounce queue is re-ordered by origin cell and
     direction octant before it is traced (sort): both only change WHEN a path is processed — every path owns its
     accumulator slot and the samples are folded in sample order — so frames are bit-identical to one-sample wavefronts
-    traced in emission order, which is the reference's schedule (CUDART/src/Context.cpp:83-159)."""
+    traced in emission order, which is the reference's schedule (CUDART/src/Context.cpp:83-159).  shade_loop=static (k_shade without
+    its work cursor) likewise only changes which warp shades a path."""
     W, H = 200, 100  # padded edge tiles
     imgs, counters = [], []
     for tuned in (False, True):
