@@ -26,9 +26,12 @@
 // (test_emode_frame_matches_the_reference_frame_loop, vectors tests/golden/ref_eframe_vectors.npz).
 // PINNED on reference code: the building blocks, the PT pipeline end to end (generatePrimaryRay, intersect_rays,
 // shade_rays control flow, NEE, connect, the bounce loop) and the E-mode frame around Embree's intersection calls.
+// The tree builder is pinned on the reference's in-tree node code: RFW/system/bvh {aabb,bvh_node,mbvh_node}.{h,cpp} compile from
+// where they lie into oracle/_ref/librfwref_bvh.so (ref_bvh_shim.cpp), and bvh_partition / bvh_subdivide / mbvh_merge_node(s) below
+// build the same trees byte for byte (tests/test_ref_pin_bvh.py, vectors tests/golden/ref_bvh_vectors.npz).  (The reference's tree
+// CLASSES call the un-vendored Rust crate rtbvh instead of that code today; rtbvh itself is absent.)
 // UNPINNED (restated from source, cited line by line, no executable reference): Embree's own traversal (absent; this
-// oracle's two-level MBVH stands in its place) and the BVH builder (rtbvh is an un-vendored Rust crate; only the in-tree
-// binned-SAH spec exists; the trees are checked against brute force).
+// oracle's two-level MBVH stands in its place).
 //
 // Two image models are restated:
 //   PT-mode  = the wavefront estimator of backends/CUDART/src/Kernels.cu (+ getShadingData.h,
@@ -2447,6 +2450,27 @@ extern "C"
 			memcpy(nodes_out, b.mnodes.data(), b.mnodes.size() * sizeof(MBVHNode));
 		if (prims_out && prim_cap >= b.prim_indices.size())
 			memcpy(prims_out, b.prim_indices.data(), b.prim_indices.size() * sizeof(uint32_t));
+		return RFWB200_OK;
+	}
+	// test hook: this file's builder (bvh_partition / bvh_subdivide / mbvh_merge_nodes) over caller-supplied boxes (n x (min3, max3)),
+	// for the pin against the reference's own in-tree node code (oracle/ref_build/ref_bvh_shim.cpp, tests/test_ref_pin_bvh.py).
+	// nodes_out: 32-byte BVH2 nodes, mnodes_out: 128-byte 4-wide nodes, prims_out: the primitive order; capacities in elements.
+	ORACLE_API int rfworacle_build_bvh_from_aabbs(const float *aabbs6, size_t n, void *nodes_out, size_t node_cap, uint32_t *prims_out,
+												  void *mnodes_out, size_t mnode_cap, size_t *n_nodes, size_t *n_mnodes)
+	{
+		static_assert(sizeof(AABB) == 24 && sizeof(BVHNode) == 32 && sizeof(MBVHNode) == 128, "node layouts");
+		if (!aabbs6 || !nodes_out || !prims_out || !mnodes_out || !n_nodes || !n_mnodes)
+			return fail("bad arguments");
+		std::vector<AABB> aabbs(n);
+		memcpy(static_cast<void *>(aabbs.data()), aabbs6, n * sizeof(AABB));
+		Bvh b;
+		build_bvh(b, aabbs);
+		*n_nodes = b.nodes.size(), *n_mnodes = b.mnodes.size();
+		if (b.nodes.size() > node_cap || b.mnodes.size() > mnode_cap)
+			return fail("buffer too small");
+		memcpy(nodes_out, static_cast<const void *>(b.nodes.data()), b.nodes.size() * sizeof(BVHNode));
+		memcpy(mnodes_out, static_cast<const void *>(b.mnodes.data()), b.mnodes.size() * sizeof(MBVHNode));
+		memcpy(prims_out, b.prim_indices.data(), n * sizeof(uint32_t));
 		return RFWB200_OK;
 	}
 	// the top-level MBVH over the instances, in the reference's node layout (for the host-compiled reference kernels)
